@@ -1,0 +1,220 @@
+/*
+ * searchlite_gpu.h — C ABI of the B200-native retrieval engine (libsearchlite_gpu.so).
+ *
+ * This is the drop-in boundary for searchlite-core's per-segment search hot path.  The
+ * reference has no inbound plugin interface; the seam a Rust
+ * `#[cfg(feature = "gpu")]` shim would bind is
+ *
+ *   IndexReader::search_segment            searchlite-core/src/api/reader.rs:2908-3128
+ *     -> execute_top_k_with_stats_and_mode_internal   src/query/wand.rs:398-456
+ *   SegmentReader::open (residency)         src/index/segment.rs:1239
+ *   hits.sort_by(SortKey) (segment merge)   src/api/reader.rs:2777, src/query/sort.rs:80-93
+ *   gpu::rerank (identity stub)             src/gpu/rerank.rs:3-5
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host buffer; handles own
+ * device memory; no callbacks cross the ABI (the reference's `accept` closure is replaced by
+ * data: matcher roles, filter programs, deleted-doc list).  Every function returns 0 on success
+ * and a negative slg_status on failure, never aborts or unwinds; slg_last_error() gives the text.
+ * A handle is thread-compatible: one in-flight call per handle, several handles may run
+ * concurrently.  All calls are synchronous unless stated otherwise.  There is no CPU fallback:
+ * without a usable CUDA device slg_open fails.
+ */
+#ifndef SEARCHLITE_GPU_H
+#define SEARCHLITE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct slg_index slg_index_t;
+typedef struct slg_batch slg_batch_t;
+
+typedef enum {
+  SLG_OK = 0,
+  SLG_ERR_INVALID = -1,     /* bad argument */
+  SLG_ERR_CUDA = -2,        /* CUDA runtime error (text in slg_last_error) */
+  SLG_ERR_NO_DEVICE = -3,   /* no CUDA device: there is no CPU fallback */
+  SLG_ERR_UNSUPPORTED = -4, /* valid request outside the built scope (e.g. k too large) */
+  SLG_ERR_OOM = -5
+} slg_status;
+
+/* ExecutionStrategy, src/api/types.rs:6-13.  All three return the EXACT top-k (bm25 == wand,
+ * query/wand.rs:459-566, :659-903).  BM25 scores every posting; WAND and BMW add safe
+ * block-max pruning (the reference's own `bmw` is not exact, SURVEY.md §8c — not reproduced). */
+typedef enum { SLG_EXEC_BM25 = 0, SLG_EXEC_WAND = 1, SLG_EXEC_BMW = 2 } slg_exec_t;
+
+/* term-group roles of the flat matcher, src/api/reader.rs:1485-1565 */
+enum { SLG_ROLE_SHOULD = 0, SLG_ROLE_MUST = 1, SLG_ROLE_MUST_NOT = 2 };
+enum { SLG_TERM_SCORED = 1u };
+#define SLG_MAX_QUERY_TERMS 64u
+#define SLG_MAX_GROUPS 32u
+#define SLG_MAX_K 2048u
+
+/* One "field:term" key of a query after search_segment's weight merge (api/reader.rs:2971-2983). */
+typedef struct {
+  uint32_t term_id; /* ordinal of the key in the handle's term space; UINT32_MAX = absent */
+  float weight;     /* > 0; sum of group.boost*field.boost over duplicate keys */
+  uint32_t leaf;    /* ScorePlan leaf (Sum-of-leaves plan; list terms in leaf order) */
+  uint32_t group;   /* matcher term group */
+  uint32_t flags;   /* SLG_TERM_SCORED if it contributes to the score */
+} slg_term_t;
+
+typedef struct {
+  uint32_t n_terms;
+  const slg_term_t *terms;
+  uint32_t n_groups;         /* 0 = plain OR of the scored terms (QueryString, min_should 1) */
+  const uint8_t *group_role; /* n_groups entries */
+  uint32_t min_should;       /* resolved minimum_should_match */
+  uint32_t leaf_count;       /* informational; the plan is Sum of leaves */
+  int32_t filter_id;         /* root filter from slg_filter_compile, -1 = none */
+} slg_query_t;
+
+/* RankedHit as merged by SortKey: score desc, segment_ord asc, doc_id asc */
+typedef struct {
+  uint32_t segment_ord;
+  uint32_t doc_id;
+  float score;
+} slg_hit_t;
+
+/* QueryStats, src/query/wand.rs:45-50 (+ pruning counters the example prints, examples/pruning.rs:198-203) */
+typedef struct {
+  uint64_t scored_docs;       /* docs that received at least one contribution */
+  uint64_t postings_advanced; /* postings decoded and scored */
+  uint64_t blocks_skipped;    /* (query, tile) items skipped by the block-max bound */
+  uint64_t candidates_examined;
+} slg_stats_t;
+
+/* Where the arrays of a view live. */
+enum { SLG_MEM_HOST = 0, SLG_MEM_DEVICE = 1 };
+
+/* One segment as SegmentReader holds it, already parsed into SoA (CSR postings + `_len:` column).
+ * Replaces SegmentReader::open + PostingsReader::read_at + field_lengths_for
+ * (index/segment.rs:1239, index/postings.rs:142-212, api/reader.rs:3604-3621). */
+typedef struct {
+  uint32_t segment_ord;
+  uint32_t doc_count;
+  uint64_t n_terms;
+  const uint64_t *term_offsets;        /* n_terms+1, CSR */
+  const uint32_t *post_docs;           /* ascending per term */
+  const uint32_t *post_tfs;
+  const int64_t *field_lengths;        /* `_len:<field>` i64 column, doc_count entries */
+  const uint8_t *field_length_present; /* nullable */
+  uint64_t total_tokens;               /* sum of field lengths: avgdl = total/doc_count, segment.rs:946-957 */
+  const uint32_t *deleted_docs;        /* HOST array, nullable */
+  uint32_t n_deleted;
+  int32_t memory_space;                /* SLG_MEM_HOST or SLG_MEM_DEVICE for the five arrays above */
+} slg_segment_view_t;
+
+/* Filter AST, src/api/types.rs:670-680, evaluated as src/query/filters.rs:84-149 over flat
+ * columns.  Prefix encoding: a node is followed by its n_children sub-trees. */
+enum {
+  SLG_F_KEYWORD_EQ = 0,
+  SLG_F_KEYWORD_IN = 1,
+  SLG_F_I64_RANGE = 2,
+  SLG_F_F64_RANGE = 3,
+  SLG_F_AND = 4,
+  SLG_F_OR = 5,
+  SLG_F_NOT = 6
+};
+typedef struct {
+  uint32_t op;
+  int32_t column;       /* handle from slg_add_*_column; -1 = unknown field (predicate false) */
+  int64_t i_min, i_max; /* inclusive */
+  double f_min, f_max;  /* inclusive */
+  uint32_t n_children;
+  uint32_t value_begin, value_end; /* keyword values: range in the strings array */
+} slg_filter_node_t;
+
+typedef enum { SLG_METRIC_COSINE = 0, SLG_METRIC_L2 = 1 } slg_metric_t;
+
+/* Engine counters (cumulative since open unless noted). */
+typedef struct {
+  uint64_t kernel_launches;    /* kernels this library launched */
+  uint64_t score_launches;     /* launches of the dominant scoring kernel */
+  double score_ms_total;       /* CUDA-event time of those launches, on the handle's stream */
+  double last_score_ms;
+  double last_batch_ms;        /* device time of the last slg_batch_run (all kernels) */
+  uint64_t last_posting_count; /* sum over queries of df of their scored terms, last batch */
+  uint64_t resident_bytes;     /* device bytes held by loaded segments */
+} slg_counters_t;
+
+/* ---- lifetime ---- */
+int32_t slg_open(int32_t device, slg_index_t **out);
+int32_t slg_close(slg_index_t *);
+/* text of the last error on this handle (or of the last failed slg_open when NULL) */
+const char *slg_last_error(const slg_index_t *);
+/* tuning knobs; 0 keeps the default.  tile_docs: docs per shared-memory tile (multiple of 1024). */
+int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm);
+
+/* ---- residency (SegmentReader::open) ---- */
+int32_t slg_load_segment(slg_index_t *, const slg_segment_view_t *view, float k1, float b);
+/* Same, from the reference's on-disk `.post` image (index/postings.rs:78-129): term t's list
+ * starts at post_image[term_post_offsets[t]]; decoded on the device. */
+int32_t slg_load_segment_post_image(slg_index_t *, const slg_segment_view_t *view_without_postings,
+                                    const uint8_t *post_image, uint64_t post_image_bytes,
+                                    const uint64_t *term_post_offsets, float k1, float b);
+/* fast-field columns of the last loaded segment (index/fastfields.rs:910-1039); return handle >= 0 */
+int32_t slg_add_i64_column(slg_index_t *, uint32_t segment_ord, const int64_t *values, const uint8_t *present);
+int32_t slg_add_f64_column(slg_index_t *, uint32_t segment_ord, const double *values, const uint8_t *present);
+int32_t slg_add_str_column(slg_index_t *, uint32_t segment_ord, const char *const *dict, uint32_t n_dict,
+                           const uint32_t *ords /* UINT32_MAX = missing */);
+/* segment statistics as the reference derives them (for the host shim and for tests) */
+int32_t slg_segment_stats(const slg_index_t *, uint32_t segment_ord, float *avgdl, float *live_docs,
+                          float *min_doc_len, uint64_t *n_postings);
+
+/* ---- filters (query/filters.rs) ---- */
+/* compiles a root filter against every loaded segment (one bitmap per segment); returns id >= 0 */
+int32_t slg_filter_compile(slg_index_t *, const slg_filter_node_t *nodes, uint32_t n_nodes,
+                           const char *const *strings);
+/* copy the filter's bitmap for one segment to the host: ceil(doc_count/32) words, LSB first */
+int32_t slg_filter_bitmap(slg_index_t *, int32_t filter_id, uint32_t segment_ord, uint32_t *bitmap_out);
+
+/* ---- batched search (search_segment + execute_top_k for Q queries, all loaded segments) ---- */
+/* k is the INTERNAL k (the reference passes limit+1, api/reader.rs:2595-2619).  out_hits has
+ * n_queries*k entries, per query sorted by (score desc, segment_ord asc, doc_id asc);
+ * out_counts[q] <= k.  out_stats nullable (n_queries entries). */
+int32_t slg_search_batch(slg_index_t *, const slg_query_t *queries, uint32_t n_queries, uint32_t k,
+                         slg_exec_t exec, uint32_t bmw_block_size, slg_hit_t *out_hits, uint32_t *out_counts,
+                         slg_stats_t *out_stats);
+
+/* The same in three steps, so a caller can keep a batch resident and re-run it:
+ * prepare = validate + upload; run = all kernels (asynchronous on the handle's stream unless
+ * sync != 0); fetch = device->host copy of the results of the last run. */
+int32_t slg_batch_prepare(slg_index_t *, const slg_query_t *queries, uint32_t n_queries, uint32_t k,
+                          slg_exec_t exec, uint32_t bmw_block_size, slg_batch_t **out);
+int32_t slg_batch_run(slg_batch_t *, int32_t sync);
+int32_t slg_batch_fetch(slg_batch_t *, slg_hit_t *out_hits, uint32_t *out_counts, slg_stats_t *out_stats);
+/* device pointers of the last run's results (n_queries*k slg_hit_t, n_queries u32) for an
+ * allgather by the caller; valid until the batch is re-run or freed */
+int32_t slg_batch_device_results(slg_batch_t *, void **dev_hits, void **dev_counts);
+int32_t slg_batch_free(slg_batch_t *);
+
+/* ---- shard merge (api/reader.rs:2777): gathered is n_shards x n_queries x k hits (DEVICE memory),
+ * counts n_shards x n_queries (DEVICE).  Writes n_queries x k merged hits / counts to HOST buffers. */
+int32_t slg_merge_gathered(slg_index_t *, const void *dev_gathered_hits, const void *dev_gathered_counts,
+                           uint32_t n_shards, uint32_t n_queries, uint32_t k, slg_hit_t *out_hits,
+                           uint32_t *out_counts);
+
+/* ---- vectors + rerank (what gpu::rerank should have been; vectors/mod.rs:63-129, api/reader.rs:218-254) ----
+ * offsets: doc -> row in values or UINT32_MAX (VectorStore, index/segment.rs:1030-1053).
+ * store_bf16 != 0 keeps the rows as bf16 in HBM (documented tolerance), else f32. */
+int32_t slg_load_vectors(slg_index_t *, uint32_t segment_ord, uint32_t dim, const uint32_t *offsets,
+                         const float *values, uint64_t n_rows, int32_t store_bf16);
+/* For each query: score every candidate hit as compute_hybrid_score (one clause):
+ * alpha*bm25 + (1-alpha)*similarity, missing vector => -1 (cosine) / f32::MIN (L2); re-sort by
+ * (score desc, segment_ord asc, doc_id asc).  cands is n_queries*cand_stride hits. */
+int32_t slg_rerank(slg_index_t *, const float *query_vecs, uint32_t n_queries, uint32_t dim,
+                   const slg_hit_t *cands, const uint32_t *cand_counts, uint32_t cand_stride, float alpha,
+                   slg_metric_t metric, slg_hit_t *out_hits, float *out_vector_scores);
+
+/* ---- introspection ---- */
+int32_t slg_get_counters(const slg_index_t *, slg_counters_t *out);
+const char *slg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1206 @@
+// slg_engine.cu — host side of libsearchlite_gpu.so: residency, batch preparation, kernel
+// launches and the C ABI declared in include/searchlite_gpu.h.
+//
+// Mirrors, for the hot path only:
+//   SegmentReader::open / live_docs / avg_field_length   searchlite-core/src/index/segment.rs:1239,1344,1365
+//   IndexReader::search_segment                           src/api/reader.rs:2908-3128
+//   execute_top_k_with_stats_and_mode_internal            src/query/wand.rs:398-456
+//   hits.sort_by(SortKey)                                 src/api/reader.rs:2777
+// There is no CPU fallback anywhere in this file: every search runs the CUDA kernels or fails.
+#include "../../include/searchlite_gpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "slg_filter.cuh"
+#include "slg_kernels.cuh"
+#include "slg_postimage.cuh"
+#include "slg_rerank.cuh"
+
+using namespace slg;
+
+namespace {
+
+thread_local std::string g_open_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p;
+      bytes = o.bytes;
+      o.p = nullptr;
+      o.bytes = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  cudaError_t alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    else p = nullptr;
+    return e;
+  }
+  template <class T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Column {
+  int kind = 0;  // 0 i64, 1 f64, 2 str
+  DevBuf values; // i64 / f64 / u32 ords
+  DevBuf present;
+  std::vector<std::string> dict;
+};
+
+struct Vectors {
+  uint32_t dim = 0;
+  uint64_t n_rows = 0;
+  bool bf16 = false;
+  DevBuf offsets;  // u32[doc_count]
+  DevBuf values;   // f32 or bf16 [n_rows][dim]
+};
+
+struct Segment {
+  uint32_t ord = 0, doc_count = 0;
+  uint64_t n_terms = 0, n_postings = 0, n_post_padded = 0;
+  uint32_t n_blocks = 0, n_deleted = 0;
+  float k1 = 0.9f, b = 0.4f, avgdl = 0, live_docs = 0, min_doc_len = 1;
+  std::vector<uint32_t> h_df;  // host copy (query ordering, validation)
+  DevBuf post_doc, post_tf, term_start, term_df, term_idf, term_max_tf, term_wide, tf_wide, term_blk, blk_max_doc,
+      blk_max_tf, nk, live_bits;
+  SegmentDev dev{};
+  std::vector<Column> columns;
+  std::vector<DevBuf> filter_bits;  // per filter id
+  DevBuf filter_ptrs;               // device array of pointers into filter_bits
+  Vectors vec;
+  size_t resident() const {
+    return post_doc.bytes + post_tf.bytes + term_start.bytes + term_df.bytes + term_idf.bytes + term_max_tf.bytes +
+           term_wide.bytes + tf_wide.bytes + term_blk.bytes + blk_max_doc.bytes + blk_max_tf.bytes + nk.bytes +
+           live_bits.bytes;
+  }
+};
+
+struct FilterProg {
+  std::vector<slg_filter_node_t> nodes;
+  std::vector<std::string> strings;
+};
+
+}  // namespace
+
+struct slg_index {
+  int device = 0;
+  int n_sm = 148;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<std::unique_ptr<Segment>> segs;
+  std::vector<FilterProg> filters;
+  std::string err;
+  slg_counters_t ctr{};
+  uint32_t tile_docs = 16384;
+  uint32_t ctas_per_sm = 0;  // 0 = as many as shared memory allows
+  Segment *find(uint32_t ord) {
+    for (auto &s : segs)
+      if (s->ord == ord) return s.get();
+    return nullptr;
+  }
+};
+
+struct slg_batch {
+  slg_index *ix = nullptr;
+  uint32_t Q = 0, k = 0, cap = 0, U = 0, T = 0;
+  slg_exec_t exec = SLG_EXEC_BM25;
+  bool matcher = false;
+  bool want_stats = false;
+  uint64_t posting_count = 0;
+  // packed inputs
+  std::vector<unsigned char> h_pack;
+  DevBuf d_pack;
+  size_t off_ut_term = 0, off_q_term_off = 0, off_qt_uterm = 0, off_qt_weight = 0, off_qt_group = 0, off_qt_flags = 0,
+         off_q_order = 0, off_q_must = 0, off_q_not = 0, off_q_should = 0, off_q_min = 0, off_q_filter = 0;
+  std::vector<uint32_t> h_ut_term, h_qt_uterm, h_q_term_off;
+  // state + outputs
+  DevBuf ut_rng, ut_tile_ub, thr_key, topk_count, lock, topk_keys, work_counter, stats;
+  DevBuf seg_hits, seg_counts;  // [S][Q][k], [S][Q]
+  DevBuf out_hits, out_counts;  // merged (aliases seg buffers when S == 1)
+  uint32_t n_segs_run = 0;
+  void *pinned = nullptr;
+  size_t pinned_bytes = 0;
+  ~slg_batch() {
+    if (pinned) cudaFreeHost(pinned);
+  }
+};
+
+namespace {
+
+int32_t fail(slg_index *ix, int32_t code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ix) ix->err = buf;
+  else g_open_error = buf;
+  return code;
+}
+
+#define SLG_CUDA(ix, call)                                                                         \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail((ix), e__ == cudaErrorMemoryAllocation ? SLG_ERR_OOM : SLG_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                    \
+  } while (0)
+
+inline void count_launch(slg_index *ix, uint64_t n = 1) { ix->ctr.kernel_launches += n; }
+
+// idf exactly as query/bm25.rs:2 with docs = live docs (api/reader.rs:2985) and df = list length
+inline float host_idf(float df, float docs) { return std::max(logf((docs - df + 0.5f) / (df + 0.5f)), 0.0f) + 1.0f; }
+inline float host_nk(float dl, float avgdl, float k1, float b) {
+  volatile float norm = avgdl > 0.0f ? dl / avgdl : 1.0f;
+  volatile float bn = b * norm;
+  volatile float omb = 1.0f - b;
+  volatile float s = omb + bn;
+  volatile float r = k1 * s;
+  return r;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// --------------------------------------------------------------------------------------------
+// residency
+int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_t *d_lens, const uint8_t *d_present,
+                       uint64_t total_tokens, const uint32_t *deleted, uint32_t n_deleted) {
+  cudaStream_t st = ix->stream;
+  Segment *s = seg.get();
+  // compute_avg_lengths index/segment.rs:946-957
+  s->avgdl = s->doc_count == 0 ? 0.0f : (float)total_tokens / (float)(uint64_t)s->doc_count;
+  // deleted docs -> live bitmap; live_docs index/segment.rs:1365-1370
+  uint32_t words = (s->doc_count + 31) / 32;
+  std::vector<uint32_t> live(words, 0xFFFFFFFFu);
+  if (s->doc_count & 31) live[words - 1] = (1u << (s->doc_count & 31)) - 1u;
+  uint32_t nd = 0;
+  for (uint32_t i = 0; i < n_deleted; i++) {
+    uint32_t d = deleted[i];
+    if (d < s->doc_count && (live[d >> 5] >> (d & 31) & 1u)) {
+      live[d >> 5] &= ~(1u << (d & 31));
+      nd++;
+    }
+  }
+  s->n_deleted = nd;
+  s->live_docs = (float)(s->doc_count - nd);
+  SLG_CUDA(ix, s->live_bits.alloc((size_t)std::max(words, 1u) * 4));
+  if (words) SLG_CUDA(ix, cudaMemcpyAsync(s->live_bits.p, live.data(), (size_t)words * 4, cudaMemcpyHostToDevice, st));
+  // idf per term on the host (glibc logf, like the reference's f32::ln)
+  std::vector<float> idf(s->n_terms);
+  for (uint64_t t = 0; t < s->n_terms; t++) idf[t] = host_idf((float)s->h_df[t], s->live_docs);
+  SLG_CUDA(ix, s->term_idf.alloc(s->n_terms * 4));
+  if (s->n_terms) SLG_CUDA(ix, cudaMemcpyAsync(s->term_idf.p, idf.data(), s->n_terms * 4, cudaMemcpyHostToDevice, st));
+  // norms
+  SLG_CUDA(ix, s->nk.alloc((size_t)std::max(s->doc_count, 1u) * 4));
+  DevBuf minbits;
+  SLG_CUDA(ix, minbits.alloc(4));
+  uint32_t inf_bits = 0x7F800000u;
+  SLG_CUDA(ix, cudaMemcpyAsync(minbits.p, &inf_bits, 4, cudaMemcpyHostToDevice, st));
+  if (s->doc_count) {
+    slg_norms_kernel<<<(s->doc_count + 255) / 256, 256, 0, st>>>(d_lens, d_present, s->doc_count, s->avgdl, s->k1, s->b,
+                                                                   s->nk.as<float>(), minbits.as<uint32_t>());
+    count_launch(ix);
+  }
+  uint32_t got = 0;
+  SLG_CUDA(ix, cudaMemcpyAsync(&got, minbits.p, 4, cudaMemcpyDeviceToHost, st));
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  float mn;
+  std::memcpy(&mn, &got, 4);
+  s->min_doc_len = std::isfinite(mn) ? mn : std::max(s->avgdl, 1.0f);  // query/wand.rs:117-121
+
+  SegmentDev &d = s->dev;
+  d.post_doc = s->post_doc.as<uint32_t>();
+  d.post_tf = s->post_tf.as<uint8_t>();
+  d.term_start = s->term_start.as<uint64_t>();
+  d.term_df = s->term_df.as<uint32_t>();
+  d.term_idf = s->term_idf.as<float>();
+  d.term_max_tf = s->term_max_tf.as<float>();
+  d.term_wide = s->term_wide.as<uint64_t>();
+  d.tf_wide = s->tf_wide.as<uint32_t>();
+  d.term_blk = s->term_blk.as<uint32_t>();
+  d.blk_max_doc = s->blk_max_doc.as<uint32_t>();
+  d.blk_max_tf = s->blk_max_tf.as<float>();
+  d.nk = s->nk.as<float>();
+  d.live_bits = s->live_bits.as<uint32_t>();
+  d.doc_count = s->doc_count;
+  d.k1p1 = s->k1 + 1.0f;
+  d.min_nk = host_nk(s->min_doc_len, s->avgdl, s->k1, s->b);
+  ix->ctr.resident_bytes += s->resident();
+  // replace a segment with the same ordinal
+  for (auto &old : ix->segs)
+    if (old->ord == s->ord) {
+      ix->ctr.resident_bytes -= old->resident();
+      old = std::move(seg);
+      return SLG_OK;
+    }
+  ix->segs.push_back(std::move(seg));
+  std::sort(ix->segs.begin(), ix->segs.end(), [](const auto &a, const auto &b2) { return a->ord < b2->ord; });
+  return SLG_OK;
+}
+
+// layout tables shared by both load paths: df -> padded starts, block starts
+int32_t build_layout(slg_index *ix, Segment *s) {
+  cudaStream_t st = ix->stream;
+  std::vector<uint64_t> start(s->n_terms + 1);
+  std::vector<uint32_t> blk(s->n_terms + 1);
+  uint64_t pos = 0, nb = 0, np = 0;
+  for (uint64_t t = 0; t < s->n_terms; t++) {
+    start[t] = pos;
+    blk[t] = (uint32_t)nb;
+    uint32_t df = s->h_df[t];
+    np += df;
+    pos += align_up(df, kTermAlign);
+    nb += (df + kBlock - 1) / kBlock;
+    if (nb > 0xFFFFFFF0ull) return fail(ix, SLG_ERR_UNSUPPORTED, "segment has too many posting blocks");
+  }
+  start[s->n_terms] = pos;
+  blk[s->n_terms] = (uint32_t)nb;
+  s->n_postings = np;
+  s->n_post_padded = pos + 1024;  // tail slack so that vector loads past a list never leave the buffer
+  s->n_blocks = (uint32_t)nb;
+  SLG_CUDA(ix, s->term_start.alloc((s->n_terms + 1) * 8));
+  SLG_CUDA(ix, s->term_blk.alloc((s->n_terms + 1) * 4));
+  SLG_CUDA(ix, s->term_df.alloc(std::max<uint64_t>(s->n_terms, 1) * 4));
+  SLG_CUDA(ix, cudaMemcpyAsync(s->term_start.p, start.data(), (s->n_terms + 1) * 8, cudaMemcpyHostToDevice, st));
+  SLG_CUDA(ix, cudaMemcpyAsync(s->term_blk.p, blk.data(), (s->n_terms + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (s->n_terms) SLG_CUDA(ix, cudaMemcpyAsync(s->term_df.p, s->h_df.data(), s->n_terms * 4, cudaMemcpyHostToDevice, st));
+  SLG_CUDA(ix, s->post_doc.alloc(s->n_post_padded * 4));
+  SLG_CUDA(ix, s->post_tf.alloc(s->n_post_padded));
+  SLG_CUDA(ix, cudaMemsetAsync(s->post_doc.p, 0xFF, s->n_post_padded * 4, st));
+  SLG_CUDA(ix, cudaMemsetAsync(s->post_tf.p, 0, s->n_post_padded, st));
+  SLG_CUDA(ix, s->blk_max_doc.alloc((size_t)std::max(s->n_blocks, 1u) * 4));
+  SLG_CUDA(ix, s->blk_max_tf.alloc((size_t)std::max(s->n_blocks, 1u) * 4));
+  SLG_CUDA(ix, s->term_max_tf.alloc(std::max<uint64_t>(s->n_terms, 1) * 4));
+  SLG_CUDA(ix, s->term_wide.alloc(std::max<uint64_t>(s->n_terms, 1) * 8));
+  SLG_CUDA(ix, cudaMemsetAsync(s->term_wide.p, 0xFF, std::max<uint64_t>(s->n_terms, 1) * 8, st));
+  SLG_CUDA(ix, cudaStreamSynchronize(st));  // host vectors go out of scope
+  return SLG_OK;
+}
+
+// after post_tf / blk_max_tf are filled: per-term max tf and the wide-tf side table
+int32_t build_wide(slg_index *ix, Segment *s, const uint64_t *d_csr_off, const uint32_t *d_csr_tfs) {
+  cudaStream_t st = ix->stream;
+  if (!s->n_terms) return SLG_OK;
+  slg_term_max_tf_kernel<<<(unsigned)((s->n_terms + 255) / 256), 256, 0, st>>>(s->term_blk.as<uint32_t>(), s->blk_max_tf.as<float>(),
+                                                                              s->n_terms, s->term_max_tf.as<float>());
+  count_launch(ix);
+  std::vector<float> mtf(s->n_terms);
+  SLG_CUDA(ix, cudaMemcpyAsync(mtf.data(), s->term_max_tf.p, s->n_terms * 4, cudaMemcpyDeviceToHost, st));
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  std::vector<uint32_t> wide_terms;
+  std::vector<uint64_t> wide_off;
+  uint64_t wpos = 0;
+  for (uint64_t t = 0; t < s->n_terms; t++)
+    if (mtf[t] >= 255.0f) {
+      wide_terms.push_back((uint32_t)t);
+      wide_off.push_back(wpos);
+      wpos += s->h_df[t];
+    }
+  if (wide_terms.empty()) return SLG_OK;
+  if (!d_csr_tfs) return fail(ix, SLG_ERR_UNSUPPORTED, "term frequency >= 255 needs the CSR load path");
+  SLG_CUDA(ix, s->tf_wide.alloc(wpos * 4));
+  DevBuf d_wt, d_wo;
+  SLG_CUDA(ix, d_wt.alloc(wide_terms.size() * 4));
+  SLG_CUDA(ix, d_wo.alloc(wide_off.size() * 8));
+  SLG_CUDA(ix, cudaMemcpyAsync(d_wt.p, wide_terms.data(), wide_terms.size() * 4, cudaMemcpyHostToDevice, st));
+  SLG_CUDA(ix, cudaMemcpyAsync(d_wo.p, wide_off.data(), wide_off.size() * 8, cudaMemcpyHostToDevice, st));
+  // term_wide[t] = offset such that tf_wide[term_wide[t] + i] is posting i of the term
+  std::vector<uint64_t> tw(s->n_terms, ~0ull);
+  for (size_t w = 0; w < wide_terms.size(); w++) tw[wide_terms[w]] = wide_off[w];
+  SLG_CUDA(ix, cudaMemcpyAsync(s->term_wide.p, tw.data(), s->n_terms * 8, cudaMemcpyHostToDevice, st));
+  dim3 grid(64, (unsigned)wide_terms.size());
+  slg_wide_tf_kernel<<<grid, 256, 0, st>>>(d_csr_off, d_csr_tfs, d_wt.as<uint32_t>(), d_wo.as<uint64_t>(),
+                                           (uint32_t)wide_terms.size(), s->tf_wide.as<uint32_t>());
+  count_launch(ix);
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  return SLG_OK;
+}
+
+template <class T>
+int32_t to_device(slg_index *ix, const T *src, size_t n, int space, DevBuf &tmp, const T **out) {
+  if (!src || n == 0) {
+    *out = nullptr;
+    return SLG_OK;
+  }
+  if (space == SLG_MEM_DEVICE) {
+    *out = src;
+    return SLG_OK;
+  }
+  SLG_CUDA(ix, tmp.alloc(n * sizeof(T)));
+  SLG_CUDA(ix, cudaMemcpyAsync(tmp.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ix->stream));
+  *out = tmp.as<T>();
+  return SLG_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// search
+int32_t select_smem(slg_index *ix, uint32_t tile_docs, uint32_t cap, bool matcher, size_t *out) {
+  size_t smem = (size_t)tile_docs * 4 + (size_t)cap * 8 + (matcher ? tile_docs : 0);
+  if (smem + 1024 > ix->smem_optin)
+    return fail(ix, SLG_ERR_UNSUPPORTED, "tile of %u docs with k buffer %u needs %zu B shared memory", tile_docs, cap, smem);
+  *out = smem;
+  return SLG_OK;
+}
+
+template <bool M, bool P, bool S>
+int32_t launch_score_t(slg_index *ix, const SegmentDev &sd, const BatchDev &bd, size_t smem, int grid) {
+  auto kern = slg_score_tiles_kernel<M, P, S>;
+  SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kThreads, smem, ix->stream>>>(sd, bd);
+  SLG_CUDA(ix, cudaGetLastError());
+  return SLG_OK;
+}
+
+int32_t launch_score(slg_index *ix, bool matcher, bool prune, bool stats, const SegmentDev &sd, const BatchDev &bd,
+                     size_t smem, int grid) {
+  int sel = (matcher ? 4 : 0) | (prune ? 2 : 0) | (stats ? 1 : 0);
+  switch (sel) {
+    case 0: return launch_score_t<false, false, false>(ix, sd, bd, smem, grid);
+    case 1: return launch_score_t<false, false, true>(ix, sd, bd, smem, grid);
+    case 2: return launch_score_t<false, true, false>(ix, sd, bd, smem, grid);
+    case 3: return launch_score_t<false, true, true>(ix, sd, bd, smem, grid);
+    case 4: return launch_score_t<true, false, false>(ix, sd, bd, smem, grid);
+    case 5: return launch_score_t<true, false, true>(ix, sd, bd, smem, grid);
+    case 6: return launch_score_t<true, true, false>(ix, sd, bd, smem, grid);
+    default: return launch_score_t<true, true, true>(ix, sd, bd, smem, grid);
+  }
+}
+
+}  // namespace
+
+/* ================================================================================================ C ABI */
+extern "C" {
+
+const char *slg_version(void) { return "searchlite-b200 0.1 (sm_100a)"; }
+
+const char *slg_last_error(const slg_index_t *ix) { return ix ? ix->err.c_str() : g_open_error.c_str(); }
+
+int32_t slg_open(int32_t device, slg_index_t **out) {
+  if (!out) return fail(nullptr, SLG_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, SLG_ERR_NO_DEVICE, "no CUDA device (%s); this engine has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= n) return fail(nullptr, SLG_ERR_INVALID, "device %d out of range (have %d)", device, n);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, SLG_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, SLG_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major < 10)
+    return fail(nullptr, SLG_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                prop.minor);
+  slg_index *ix = new slg_index();
+  ix->device = device;
+  ix->n_sm = prop.multiProcessorCount;
+  ix->smem_optin = prop.sharedMemPerBlockOptin;
+  e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ix->ev[i]);
+  if (e != cudaSuccess) {
+    int32_t rc = fail(nullptr, SLG_ERR_CUDA, "stream/event creation: %s", cudaGetErrorString(e));
+    delete ix;
+    return rc;
+  }
+  *out = ix;
+  return SLG_OK;
+}
+
+int32_t slg_close(slg_index_t *ix) {
+  if (!ix) return SLG_OK;
+  cudaSetDevice(ix->device);
+  cudaStreamSynchronize(ix->stream);
+  ix->segs.clear();
+  for (auto &ev : ix->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ix->stream) cudaStreamDestroy(ix->stream);
+  delete ix;
+  return SLG_OK;
+}
+
+int32_t slg_configure(slg_index_t *ix, uint32_t tile_docs, uint32_t ctas_per_sm) {
+  if (!ix) return SLG_ERR_INVALID;
+  if (tile_docs) {
+    if (tile_docs % 1024 || tile_docs > 49152) return fail(ix, SLG_ERR_INVALID, "tile_docs must be a multiple of 1024 <= 49152");
+    ix->tile_docs = tile_docs;
+  }
+  ix->ctas_per_sm = ctas_per_sm;
+  return SLG_OK;
+}
+
+int32_t slg_load_segment(slg_index_t *ix, const slg_segment_view_t *v, float k1, float b) {
+  if (!ix || !v) return SLG_ERR_INVALID;
+  if (!v->term_offsets || (v->n_terms && (!v->post_docs || !v->post_tfs)))
+    return fail(ix, SLG_ERR_INVALID, "segment view lacks postings");
+  if (v->doc_count && !v->field_lengths) return fail(ix, SLG_ERR_INVALID, "segment view lacks field lengths");
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  cudaStream_t st = ix->stream;
+  auto seg = std::make_unique<Segment>();
+  Segment *s = seg.get();
+  s->ord = v->segment_ord;
+  s->doc_count = v->doc_count;
+  s->n_terms = v->n_terms;
+  s->k1 = k1;
+  s->b = b;
+  // CSR offsets on the host (df, idf and the padded layout are host work: 1 M terms)
+  std::vector<uint64_t> off(v->n_terms + 1);
+  if (v->memory_space == SLG_MEM_DEVICE) {
+    SLG_CUDA(ix, cudaMemcpyAsync(off.data(), v->term_offsets, (v->n_terms + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SLG_CUDA(ix, cudaStreamSynchronize(st));
+  } else {
+    std::memcpy(off.data(), v->term_offsets, (v->n_terms + 1) * 8);
+  }
+  s->h_df.resize(v->n_terms);
+  for (uint64_t t = 0; t < v->n_terms; t++) {
+    uint64_t df = off[t + 1] - off[t];
+    if (off[t + 1] < off[t] || df > 0xFFFFFFFFull) return fail(ix, SLG_ERR_INVALID, "term_offsets not monotone at term %llu", (unsigned long long)t);
+    s->h_df[t] = (uint32_t)df;
+  }
+  int32_t rc = build_layout(ix, s);
+  if (rc) return rc;
+  const uint64_t n_post = off[v->n_terms] - off[0];
+  DevBuf t_off, t_docs, t_tfs, t_lens, t_pres;
+  const uint64_t *d_off;
+  const uint32_t *d_docs, *d_tfs;
+  const int64_t *d_lens;
+  const uint8_t *d_pres;
+  if ((rc = to_device(ix, v->term_offsets, (size_t)v->n_terms + 1, v->memory_space, t_off, &d_off))) return rc;
+  if ((rc = to_device(ix, v->post_docs ? v->post_docs + 0 : nullptr, (size_t)off[v->n_terms], v->memory_space, t_docs, &d_docs))) return rc;
+  if ((rc = to_device(ix, v->post_tfs, (size_t)off[v->n_terms], v->memory_space, t_tfs, &d_tfs))) return rc;
+  if ((rc = to_device(ix, v->field_lengths, (size_t)v->doc_count, v->memory_space, t_lens, &d_lens))) return rc;
+  if ((rc = to_device(ix, v->field_length_present, (size_t)v->doc_count, v->memory_space, t_pres, &d_pres))) return rc;
+  (void)n_post;
+  if (s->n_blocks) {
+    slg_transcode_csr_kernel<<<s->n_blocks, 128, 0, st>>>(d_off, d_docs, d_tfs, s->n_terms, s->term_start.as<uint64_t>(),
+                                                          s->term_blk.as<uint32_t>(), s->n_blocks, s->post_doc.as<uint32_t>(),
+                                                          s->post_tf.as<uint8_t>(), s->blk_max_doc.as<uint32_t>(),
+                                                          s->blk_max_tf.as<float>());
+    count_launch(ix);
+    SLG_CUDA(ix, cudaGetLastError());
+  }
+  if ((rc = build_wide(ix, s, d_off, d_tfs))) return rc;
+  rc = finish_segment(ix, std::move(seg), d_lens, d_pres, v->total_tokens, v->deleted_docs, v->n_deleted);
+  if (rc) return rc;
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  return SLG_OK;
+}
+
+int32_t slg_load_segment_post_image(slg_index_t *ix, const slg_segment_view_t *v, const uint8_t *post_image,
+                                    uint64_t post_image_bytes, const uint64_t *term_post_offsets, float k1, float b) {
+  if (!ix || !v || !post_image || !term_post_offsets) return SLG_ERR_INVALID;
+  if (v->doc_count && !v->field_lengths) return fail(ix, SLG_ERR_INVALID, "segment view lacks field lengths");
+  if (v->memory_space != SLG_MEM_HOST) return fail(ix, SLG_ERR_INVALID, "post image loads take host memory");
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  cudaStream_t st = ix->stream;
+  auto seg = std::make_unique<Segment>();
+  Segment *s = seg.get();
+  s->ord = v->segment_ord;
+  s->doc_count = v->doc_count;
+  s->n_terms = v->n_terms;
+  s->k1 = k1;
+  s->b = b;
+  // parse the fixed part of every list header on the host (index/postings.rs:142-168)
+  std::vector<PostTermHeader> hdr(v->n_terms);
+  s->h_df.resize(v->n_terms);
+  for (uint64_t t = 0; t < v->n_terms; t++) {
+    uint64_t o = term_post_offsets[t];
+    if (o + 17 > post_image_bytes) return fail(ix, SLG_ERR_INVALID, "posting header of term %llu is out of bounds", (unsigned long long)t);
+    const uint8_t *p = post_image + o;
+    uint32_t df, raw_block;
+    std::memcpy(&df, p, 4);
+    std::memcpy(&raw_block, p + 5, 4);
+    uint32_t bc = raw_block & 0x7FFFFFFFu;
+    bool has_meta = (raw_block >> 31) != 0;
+    uint64_t payload = o + 17 + ((has_meta && bc > 0) ? 4 + 8ull * bc : 0);
+    if (payload > post_image_bytes) return fail(ix, SLG_ERR_INVALID, "block table of term %llu is out of bounds", (unsigned long long)t);
+    hdr[t].payload = payload;
+    hdr[t].end = term_post_offsets[t + 1];
+    hdr[t].df = df;
+    hdr[t].has_positions = p[4] == 1;
+    s->h_df[t] = df;
+  }
+  int32_t rc = build_layout(ix, s);
+  if (rc) return rc;
+  DevBuf d_img, d_hdr, t_lens, t_pres;
+  SLG_CUDA(ix, d_img.alloc(post_image_bytes + 16));
+  SLG_CUDA(ix, cudaMemcpyAsync(d_img.p, post_image, post_image_bytes, cudaMemcpyHostToDevice, st));
+  SLG_CUDA(ix, d_hdr.alloc(std::max<uint64_t>(v->n_terms, 1) * sizeof(PostTermHeader)));
+  if (v->n_terms) SLG_CUDA(ix, cudaMemcpyAsync(d_hdr.p, hdr.data(), v->n_terms * sizeof(PostTermHeader), cudaMemcpyHostToDevice, st));
+  DevBuf d_err;
+  SLG_CUDA(ix, d_err.alloc(4));
+  SLG_CUDA(ix, cudaMemsetAsync(d_err.p, 0, 4, st));
+  if (v->n_terms) {
+    slg_decode_post_image_kernel<<<(unsigned)((v->n_terms + 3) / 4), 128, 0, st>>>(
+        d_img.as<uint8_t>(), post_image_bytes, d_hdr.as<PostTermHeader>(), v->n_terms, s->term_start.as<uint64_t>(),
+        s->term_blk.as<uint32_t>(), s->post_doc.as<uint32_t>(), s->post_tf.as<uint8_t>(), s->blk_max_doc.as<uint32_t>(),
+        s->blk_max_tf.as<float>(), d_err.as<uint32_t>());
+    count_launch(ix);
+    SLG_CUDA(ix, cudaGetLastError());
+  }
+  uint32_t derr = 0;
+  SLG_CUDA(ix, cudaMemcpyAsync(&derr, d_err.p, 4, cudaMemcpyDeviceToHost, st));
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  if (derr == 1) return fail(ix, SLG_ERR_INVALID, "malformed varint in the posting image");
+  if (derr == 2) return fail(ix, SLG_ERR_UNSUPPORTED, "term frequency >= 255 in a posting image (use the CSR load path)");
+  if ((rc = build_wide(ix, s, nullptr, nullptr))) return rc;
+  const int64_t *d_lens;
+  const uint8_t *d_pres;
+  if ((rc = to_device(ix, v->field_lengths, (size_t)v->doc_count, SLG_MEM_HOST, t_lens, &d_lens))) return rc;
+  if ((rc = to_device(ix, v->field_length_present, (size_t)v->doc_count, SLG_MEM_HOST, t_pres, &d_pres))) return rc;
+  rc = finish_segment(ix, std::move(seg), d_lens, d_pres, v->total_tokens, v->deleted_docs, v->n_deleted);
+  if (rc) return rc;
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  return SLG_OK;
+}
+
+int32_t slg_segment_stats(const slg_index_t *ixc, uint32_t segment_ord, float *avgdl, float *live_docs, float *min_doc_len,
+                          uint64_t *n_postings) {
+  slg_index *ix = const_cast<slg_index *>(ixc);
+  if (!ix) return SLG_ERR_INVALID;
+  Segment *s = ix->find(segment_ord);
+  if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
+  if (avgdl) *avgdl = s->avgdl;
+  if (live_docs) *live_docs = s->live_docs;
+  if (min_doc_len) *min_doc_len = s->min_doc_len;
+  if (n_postings) *n_postings = s->n_postings;
+  return SLG_OK;
+}
+
+/* ---- fast-field columns + filters ---- */
+static int32_t add_column(slg_index *ix, uint32_t segment_ord, int kind, const void *values, size_t elem,
+                          const uint8_t *present, const char *const *dict, uint32_t n_dict) {
+  if (!ix || !values) return SLG_ERR_INVALID;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  Segment *s = ix->find(segment_ord);
+  if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
+  Column c;
+  c.kind = kind;
+  SLG_CUDA(ix, c.values.alloc((size_t)s->doc_count * elem));
+  SLG_CUDA(ix, cudaMemcpy(c.values.p, values, (size_t)s->doc_count * elem, cudaMemcpyHostToDevice));
+  if (kind != 2) {
+    SLG_CUDA(ix, c.present.alloc(std::max<size_t>(s->doc_count, 1)));
+    if (present) SLG_CUDA(ix, cudaMemcpy(c.present.p, present, s->doc_count, cudaMemcpyHostToDevice));
+    else SLG_CUDA(ix, cudaMemset(c.present.p, 1, std::max<size_t>(s->doc_count, 1)));
+  }
+  for (uint32_t i = 0; i < n_dict; i++) c.dict.emplace_back(dict[i]);
+  s->columns.push_back(std::move(c));
+  return (int32_t)s->columns.size() - 1;
+}
+
+int32_t slg_add_i64_column(slg_index_t *ix, uint32_t segment_ord, const int64_t *values, const uint8_t *present) {
+  return add_column(ix, segment_ord, 0, values, 8, present, nullptr, 0);
+}
+int32_t slg_add_f64_column(slg_index_t *ix, uint32_t segment_ord, const double *values, const uint8_t *present) {
+  return add_column(ix, segment_ord, 1, values, 8, present, nullptr, 0);
+}
+int32_t slg_add_str_column(slg_index_t *ix, uint32_t segment_ord, const char *const *dict, uint32_t n_dict,
+                           const uint32_t *ords) {
+  if (n_dict && !dict) return SLG_ERR_INVALID;
+  return add_column(ix, segment_ord, 2, ords, 4, nullptr, dict, n_dict);
+}
+
+// index/fastfields.rs:475-481, ASCII path
+static bool ci_equals(const std::string &a, const std::string &b) {
+  if (a.size() != b.size()) return false;
+  for (size_t i = 0; i < a.size(); i++) {
+    unsigned char x = a[i], y = b[i];
+    if (x >= 'A' && x <= 'Z') x += 32;
+    if (y >= 'A' && y <= 'Z') y += 32;
+    if (x != y) return false;
+  }
+  return true;
+}
+
+static int32_t compile_filter_for_segment(slg_index *ix, Segment *s, const FilterProg &fp, DevBuf &bits_out) {
+  // Resolve keyword predicates to dictionary-ordinal sets on the host (string compares happen once
+  // per dictionary entry instead of once per doc, index/fastfields.rs:490-530), then evaluate the
+  // program for every doc on the device.
+  std::vector<FilterNodeDev> nodes(fp.nodes.size());
+  std::vector<uint32_t> ordset;  // concatenated bitsets over dictionaries
+  for (size_t i = 0; i < fp.nodes.size(); i++) {
+    const slg_filter_node_t &n = fp.nodes[i];
+    FilterNodeDev &d = nodes[i];
+    d.op = n.op;
+    d.n_children = n.n_children;
+    d.i_min = n.i_min;
+    d.i_max = n.i_max;
+    d.f_min = n.f_min;
+    d.f_max = n.f_max;
+    d.values = nullptr;
+    d.present = nullptr;
+    d.set_off = 0;
+    d.set_words = 0;
+    const Column *c = (n.column >= 0 && (size_t)n.column < s->columns.size()) ? &s->columns[n.column] : nullptr;
+    bool leaf = n.op <= SLG_F_F64_RANGE;
+    if (!leaf) continue;
+    int want = (n.op == SLG_F_I64_RANGE) ? 0 : (n.op == SLG_F_F64_RANGE ? 1 : 2);
+    if (!c || c->kind != want) {
+      d.op = FOP_FALSE;  // unknown field or wrong column type: predicate is false (fastfields.rs `_ => false`)
+      continue;
+    }
+    d.values = c->values.p;
+    d.present = c->present.as<uint8_t>();
+    if (want == 2) {
+      uint32_t words = ((uint32_t)c->dict.size() + 31) / 32;
+      d.set_off = (uint32_t)ordset.size();
+      d.set_words = words;
+      ordset.resize(ordset.size() + words, 0u);
+      if (n.value_end < n.value_begin || n.value_end > fp.strings.size()) return fail(ix, SLG_ERR_INVALID, "filter value range out of bounds");
+      for (uint32_t o = 0; o < c->dict.size(); o++)
+        for (uint32_t vi = n.value_begin; vi < n.value_end; vi++)
+          if (ci_equals(c->dict[o], fp.strings[vi])) {
+            ordset[d.set_off + (o >> 5)] |= 1u << (o & 31);
+            break;
+          }
+    }
+  }
+  uint32_t words = (s->doc_count + 31) / 32;
+  SLG_CUDA(ix, bits_out.alloc(std::max<size_t>(words, 1) * 4));
+  DevBuf d_nodes, d_set;
+  SLG_CUDA(ix, d_nodes.alloc(nodes.size() * sizeof(FilterNodeDev)));
+  SLG_CUDA(ix, cudaMemcpyAsync(d_nodes.p, nodes.data(), nodes.size() * sizeof(FilterNodeDev), cudaMemcpyHostToDevice, ix->stream));
+  SLG_CUDA(ix, d_set.alloc(std::max<size_t>(ordset.size(), 1) * 4));
+  if (!ordset.empty()) SLG_CUDA(ix, cudaMemcpyAsync(d_set.p, ordset.data(), ordset.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+  if (words) {
+    slg_filter_bitmap_kernel<<<(s->doc_count + 255) / 256, 256, 0, ix->stream>>>(d_nodes.as<FilterNodeDev>(), (uint32_t)nodes.size(),
+                                                                                 d_set.as<uint32_t>(), s->doc_count,
+                                                                                 bits_out.as<uint32_t>());
+    count_launch(ix);
+    SLG_CUDA(ix, cudaGetLastError());
+  }
+  SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));
+  return SLG_OK;
+}
+
+int32_t slg_filter_compile(slg_index_t *ix, const slg_filter_node_t *nodes, uint32_t n_nodes, const char *const *strings) {
+  if (!ix || !nodes || !n_nodes) return SLG_ERR_INVALID;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  if (n_nodes > kMaxFilterNodes) return fail(ix, SLG_ERR_UNSUPPORTED, "filter has more than %u nodes", kMaxFilterNodes);
+  FilterProg fp;
+  fp.nodes.assign(nodes, nodes + n_nodes);
+  uint32_t max_val = 0;
+  for (auto &n : fp.nodes) {
+    if (n.op > SLG_F_NOT) return fail(ix, SLG_ERR_INVALID, "unknown filter op %u", n.op);
+    if (n.op <= SLG_F_KEYWORD_IN) max_val = std::max(max_val, n.value_end);
+  }
+  if (max_val && !strings) return fail(ix, SLG_ERR_INVALID, "keyword filter without strings");
+  for (uint32_t i = 0; i < max_val; i++) fp.strings.emplace_back(strings[i]);
+  // validate the prefix encoding
+  {
+    uint32_t pos = 0;
+    std::vector<uint32_t> pending{1};
+    while (!pending.empty()) {
+      if (pending.back() == 0) {
+        pending.pop_back();
+        continue;
+      }
+      pending.back()--;
+      if (pos >= n_nodes) return fail(ix, SLG_ERR_INVALID, "filter program is truncated");
+      const auto &n = fp.nodes[pos++];
+      if (n.op == SLG_F_NOT && n.n_children != 1) return fail(ix, SLG_ERR_INVALID, "Not takes one child");
+      if (n.op >= SLG_F_AND) pending.push_back(n.n_children);
+      if (pending.size() > kMaxFilterDepth) return fail(ix, SLG_ERR_UNSUPPORTED, "filter nesting deeper than %u", kMaxFilterDepth);
+    }
+    if (pos != n_nodes) return fail(ix, SLG_ERR_INVALID, "filter program has trailing nodes");
+  }
+  for (auto &s : ix->segs) {
+    DevBuf bits;
+    int32_t rc = compile_filter_for_segment(ix, s.get(), fp, bits);
+    if (rc) return rc;
+    s->filter_bits.resize(ix->filters.size() + 1);
+    s->filter_bits[ix->filters.size()] = std::move(bits);
+    std::vector<const uint32_t *> ptrs;
+    for (auto &fb : s->filter_bits) ptrs.push_back(fb.as<uint32_t>());
+    SLG_CUDA(ix, s->filter_ptrs.alloc(ptrs.size() * sizeof(void *)));
+    SLG_CUDA(ix, cudaMemcpy(s->filter_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice));
+  }
+  ix->filters.push_back(std::move(fp));
+  return (int32_t)ix->filters.size() - 1;
+}
+
+int32_t slg_filter_bitmap(slg_index_t *ix, int32_t filter_id, uint32_t segment_ord, uint32_t *bitmap_out) {
+  if (!ix || !bitmap_out) return SLG_ERR_INVALID;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  Segment *s = ix->find(segment_ord);
+  if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
+  if (filter_id < 0 || (size_t)filter_id >= s->filter_bits.size() || !s->filter_bits[filter_id].p)
+    return fail(ix, SLG_ERR_INVALID, "filter %d is not compiled for segment %u", filter_id, segment_ord);
+  uint32_t words = (s->doc_count + 31) / 32;
+  SLG_CUDA(ix, cudaMemcpy(bitmap_out, s->filter_bits[filter_id].p, (size_t)words * 4, cudaMemcpyDeviceToHost));
+  return SLG_OK;
+}
+
+/* ---- batched search ---- */
+int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t n_queries, uint32_t k, slg_exec_t exec,
+                          uint32_t bmw_block_size, slg_batch_t **out) {
+  if (!ix || !out) return SLG_ERR_INVALID;
+  *out = nullptr;
+  if (!queries || n_queries == 0) return fail(ix, SLG_ERR_INVALID, "empty query batch");
+  if (k == 0) return fail(ix, SLG_ERR_INVALID, "k must be > 0 (the reference bails on limit == 0, api/reader.rs:2540)");
+  if (k > SLG_MAX_K) return fail(ix, SLG_ERR_UNSUPPORTED, "k = %u exceeds the built maximum %u", k, SLG_MAX_K);
+  if (exec != SLG_EXEC_BM25 && exec != SLG_EXEC_WAND && exec != SLG_EXEC_BMW) return fail(ix, SLG_ERR_INVALID, "unknown execution strategy");
+  if (ix->segs.empty()) return fail(ix, SLG_ERR_INVALID, "no segment loaded");
+  (void)bmw_block_size;  // bounds are taken over the stored 128-posting blocks; any block size gives the same (exact) result
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  auto bt = std::make_unique<slg_batch>();
+  bt->ix = ix;
+  bt->Q = n_queries;
+  bt->k = k;
+  bt->exec = exec;
+  bt->cap = std::max(1024u, 1u << (32 - __builtin_clz(4 * k - 1)));
+  const Segment *s0 = ix->segs[0].get();
+  uint64_t n_terms_space = 0;
+  for (auto &s : ix->segs) n_terms_space = std::max(n_terms_space, s->n_terms);
+
+  std::unordered_map<uint32_t, uint32_t> umap;
+  std::vector<uint32_t> &ut = bt->h_ut_term;
+  std::vector<uint32_t> &q_off = bt->h_q_term_off;
+  std::vector<uint32_t> &qt_u = bt->h_qt_uterm;
+  std::vector<float> qt_w;
+  std::vector<uint8_t> qt_g, qt_f, q_must(n_queries, 0), q_not(n_queries, 0), q_should(n_queries, 0), q_min(n_queries, 0);
+  std::vector<int32_t> q_filter(n_queries, -1);
+  std::vector<uint64_t> q_cost(n_queries, 0);
+  q_off.assign(n_queries + 1, 0);
+  bool matcher = false;
+  for (uint32_t qi = 0; qi < n_queries; qi++) {
+    const slg_query_t &q = queries[qi];
+    if (q.n_terms && !q.terms) return fail(ix, SLG_ERR_INVALID, "query %u has no terms pointer", qi);
+    if (q.n_groups > 8) return fail(ix, SLG_ERR_UNSUPPORTED, "query %u has %u term groups; this build supports 8", qi, q.n_groups);
+    if (q.n_groups && !q.group_role) return fail(ix, SLG_ERR_INVALID, "query %u has no group roles", qi);
+    if (q.filter_id >= (int32_t)ix->filters.size()) return fail(ix, SLG_ERR_INVALID, "query %u names unknown filter %d", qi, q.filter_id);
+    q_filter[qi] = q.filter_id < 0 ? -1 : q.filter_id;
+    uint32_t kept = 0;
+    bool need_mask = q.n_groups > 0;
+    for (uint32_t t = 0; t < q.n_terms; t++) {
+      const slg_term_t &tm = q.terms[t];
+      if (tm.term_id == 0xFFFFFFFFu || tm.term_id >= n_terms_space) continue;  // seg.postings(key) == None
+      bool scored = tm.flags & SLG_TERM_SCORED;
+      if (scored && !(tm.weight > 0.0f && std::isfinite(tm.weight)))
+        return fail(ix, SLG_ERR_UNSUPPORTED, "query %u term %u: weight must be finite and > 0", qi, t);
+      if (q.n_groups && tm.group >= q.n_groups) return fail(ix, SLG_ERR_INVALID, "query %u term %u: group out of range", qi, t);
+      if (!scored) need_mask = true;
+      auto it = umap.find(tm.term_id);
+      uint32_t u;
+      if (it == umap.end()) {
+        u = (uint32_t)ut.size();
+        umap.emplace(tm.term_id, u);
+        ut.push_back(tm.term_id);
+      } else {
+        u = it->second;
+      }
+      qt_u.push_back(u);
+      qt_w.push_back(tm.weight);
+      qt_g.push_back((uint8_t)(q.n_groups ? tm.group : 0));
+      qt_f.push_back(scored ? 1 : 0);
+      if (scored && tm.term_id < s0->n_terms) q_cost[qi] += s0->h_df[tm.term_id];
+      kept++;
+    }
+    if (kept > SLG_MAX_QUERY_TERMS) return fail(ix, SLG_ERR_UNSUPPORTED, "query %u has %u terms; the maximum is %u", qi, kept, SLG_MAX_QUERY_TERMS);
+    q_off[qi + 1] = q_off[qi] + kept;
+    if (need_mask) {
+      matcher = true;
+      if (q.n_groups == 0) {  // non-scored terms without groups: plain OR over group 0
+        q_should[qi] = 1;
+        q_min[qi] = 1;
+      }
+      for (uint32_t g = 0; g < q.n_groups; g++) {
+        uint8_t bit = (uint8_t)(1u << g);
+        if (q.group_role[g] == SLG_ROLE_MUST) q_must[qi] |= bit;
+        else if (q.group_role[g] == SLG_ROLE_MUST_NOT) q_not[qi] |= bit;
+        else q_should[qi] |= bit;
+      }
+      if (q.n_groups) q_min[qi] = (uint8_t)std::min<uint32_t>(q.min_should, 255);
+    }
+    bt->posting_count += q_cost[qi];
+  }
+  bt->matcher = matcher;
+  bt->U = (uint32_t)ut.size();
+  bt->T = (uint32_t)qt_u.size();
+  // processing order inside a tile: most expensive queries first
+  std::vector<uint32_t> order(n_queries);
+  for (uint32_t i = 0; i < n_queries; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b2) { return q_cost[a] > q_cost[b2]; });
+
+  // pack all inputs into one buffer: one H2D copy per batch
+  size_t pos = 0;
+  auto place = [&](size_t bytes) {
+    size_t o = pos;
+    pos = align_up(pos + std::max<size_t>(bytes, 4), 256);
+    return o;
+  };
+  bt->off_ut_term = place((size_t)bt->U * 4);
+  bt->off_q_term_off = place((size_t)(n_queries + 1) * 4);
+  bt->off_qt_uterm = place((size_t)bt->T * 4);
+  bt->off_qt_weight = place((size_t)bt->T * 4);
+  bt->off_qt_group = place(bt->T);
+  bt->off_qt_flags = place(bt->T);
+  bt->off_q_order = place((size_t)n_queries * 4);
+  bt->off_q_must = place(n_queries);
+  bt->off_q_not = place(n_queries);
+  bt->off_q_should = place(n_queries);
+  bt->off_q_min = place(n_queries);
+  bt->off_q_filter = place((size_t)n_queries * 4);
+  bt->h_pack.assign(pos, 0);
+  unsigned char *hp = bt->h_pack.data();
+  auto put = [&](size_t off, const void *src, size_t bytes) {
+    if (bytes) std::memcpy(hp + off, src, bytes);
+  };
+  put(bt->off_ut_term, ut.data(), (size_t)bt->U * 4);
+  put(bt->off_q_term_off, q_off.data(), (size_t)(n_queries + 1) * 4);
+  put(bt->off_qt_uterm, qt_u.data(), (size_t)bt->T * 4);
+  put(bt->off_qt_weight, qt_w.data(), (size_t)bt->T * 4);
+  put(bt->off_qt_group, qt_g.data(), bt->T);
+  put(bt->off_qt_flags, qt_f.data(), bt->T);
+  put(bt->off_q_order, order.data(), (size_t)n_queries * 4);
+  put(bt->off_q_must, q_must.data(), n_queries);
+  put(bt->off_q_not, q_not.data(), n_queries);
+  put(bt->off_q_should, q_should.data(), n_queries);
+  put(bt->off_q_min, q_min.data(), n_queries);
+  put(bt->off_q_filter, q_filter.data(), (size_t)n_queries * 4);
+  SLG_CUDA(ix, bt->d_pack.alloc(pos));
+  SLG_CUDA(ix, cudaMemcpyAsync(bt->d_pack.p, hp, pos, cudaMemcpyHostToDevice, ix->stream));
+
+  uint32_t max_tiles = 0;
+  for (auto &s : ix->segs) max_tiles = std::max(max_tiles, (s->doc_count + ix->tile_docs - 1) / ix->tile_docs);
+  max_tiles = std::max(max_tiles, 1u);
+  size_t S = ix->segs.size();
+  SLG_CUDA(ix, bt->ut_rng.alloc((size_t)std::max(bt->U, 1u) * (max_tiles + 1) * 4));
+  if (exec != SLG_EXEC_BM25) SLG_CUDA(ix, bt->ut_tile_ub.alloc((size_t)std::max(bt->U, 1u) * max_tiles * 4));
+  SLG_CUDA(ix, bt->thr_key.alloc((size_t)n_queries * 8));
+  SLG_CUDA(ix, bt->topk_count.alloc((size_t)n_queries * 4));
+  SLG_CUDA(ix, bt->lock.alloc((size_t)n_queries * 4));
+  SLG_CUDA(ix, bt->topk_keys.alloc((size_t)n_queries * k * 8));
+  SLG_CUDA(ix, bt->work_counter.alloc(4));
+  SLG_CUDA(ix, bt->stats.alloc((size_t)n_queries * 4 * 8));
+  SLG_CUDA(ix, bt->seg_hits.alloc(S * n_queries * k * sizeof(HitDev)));
+  SLG_CUDA(ix, bt->seg_counts.alloc(S * n_queries * 4));
+  if (S > 1) {
+    SLG_CUDA(ix, bt->out_hits.alloc((size_t)n_queries * k * sizeof(HitDev)));
+    SLG_CUDA(ix, bt->out_counts.alloc((size_t)n_queries * 4));
+  }
+  bt->pinned_bytes = (size_t)n_queries * k * sizeof(slg_hit_t) + (size_t)n_queries * 4 + (size_t)n_queries * 32;
+  SLG_CUDA(ix, cudaMallocHost(&bt->pinned, bt->pinned_bytes));
+  SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));
+  *out = bt.release();
+  return SLG_OK;
+}
+
+int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
+  if (!bt) return SLG_ERR_INVALID;
+  slg_index *ix = bt->ix;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  cudaStream_t st = ix->stream;
+  const bool prune = bt->exec != SLG_EXEC_BM25;
+  const uint32_t Q = bt->Q, k = bt->k;
+  unsigned char *dp = bt->d_pack.as<unsigned char>();
+  size_t smem = 0;
+  int32_t rc = select_smem(ix, ix->tile_docs, bt->cap, bt->matcher, &smem);
+  if (rc) return rc;
+  uint32_t per_sm = (uint32_t)std::max<size_t>(1, (ix->smem_optin + 1024) / (smem + 1024));
+  per_sm = std::min(per_sm, 8u);
+  if (ix->ctas_per_sm) per_sm = std::min(per_sm, ix->ctas_per_sm);
+  SLG_CUDA(ix, cudaEventRecord(ix->ev[0], st));
+  SLG_CUDA(ix, cudaMemsetAsync(bt->stats.p, 0, (size_t)Q * 32, st));
+  double score_ms_pending = 0;
+  (void)score_ms_pending;
+  uint32_t si = 0;
+  for (auto &sp : ix->segs) {
+    Segment *s = sp.get();
+    BatchDev bd{};
+    bd.ut_term = reinterpret_cast<const uint32_t *>(dp + bt->off_ut_term);
+    bd.ut_rng = bt->ut_rng.as<uint32_t>();
+    bd.ut_tile_ub = bt->ut_tile_ub.as<float>();
+    bd.q_term_off = reinterpret_cast<const uint32_t *>(dp + bt->off_q_term_off);
+    bd.qt_uterm = reinterpret_cast<const uint32_t *>(dp + bt->off_qt_uterm);
+    bd.qt_weight = reinterpret_cast<const float *>(dp + bt->off_qt_weight);
+    bd.qt_group = dp + bt->off_qt_group;
+    bd.qt_flags = dp + bt->off_qt_flags;
+    bd.q_order = reinterpret_cast<const uint32_t *>(dp + bt->off_q_order);
+    bd.q_must = dp + bt->off_q_must;
+    bd.q_not = dp + bt->off_q_not;
+    bd.q_should = dp + bt->off_q_should;
+    bd.q_min_should = dp + bt->off_q_min;
+    bd.q_filter = reinterpret_cast<const int32_t *>(dp + bt->off_q_filter);
+    bd.filter_bits = reinterpret_cast<const uint32_t *const *>(s->filter_ptrs.p);
+    bd.n_queries = Q;
+    bd.n_uterms = bt->U;
+    bd.k = k;
+    bd.cap = bt->cap;
+    bd.tile_docs = ix->tile_docs;
+    bd.n_tiles = std::max(1u, (s->doc_count + ix->tile_docs - 1) / ix->tile_docs);
+    bd.thr_key = bt->thr_key.as<unsigned long long>();
+    bd.topk_count = bt->topk_count.as<uint32_t>();
+    bd.lock = bt->lock.as<uint32_t>();
+    bd.topk_keys = bt->topk_keys.as<unsigned long long>();
+    bd.work_counter = bt->work_counter.as<uint32_t>();
+    bd.stats = bt->stats.as<unsigned long long>();
+    // queries that name a filter need its bitmap on every segment
+    if (!ix->filters.empty() && s->filter_bits.size() < ix->filters.size())
+      return fail(ix, SLG_ERR_INVALID, "segment %u was loaded after its filters were compiled", s->ord);
+
+    slg_fill_u64_kernel<<<(Q + 255) / 256, 256, 0, st>>>(bd.thr_key, kThrInit, Q);
+    count_launch(ix);
+    SLG_CUDA(ix, cudaMemsetAsync(bd.topk_count, 0, (size_t)Q * 4, st));
+    SLG_CUDA(ix, cudaMemsetAsync(bd.lock, 0, (size_t)Q * 4, st));
+    SLG_CUDA(ix, cudaMemsetAsync(bd.work_counter, 0, 4, st));
+    if (bt->U && s->doc_count) {
+      uint64_t n = (uint64_t)bt->U * (bd.n_tiles + 1);
+      slg_plan_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, bd);
+      count_launch(ix);
+      if (prune) {
+        uint64_t n2 = (uint64_t)bt->U * bd.n_tiles;
+        slg_plan_bounds_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(s->dev, bd);
+        count_launch(ix);
+      }
+      SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));
+      int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * per_sm, (uint64_t)bd.n_tiles * Q);
+      rc = launch_score(ix, bt->matcher, prune, true, s->dev, bd, smem, grid);
+      if (rc) return rc;
+      count_launch(ix);
+      ix->ctr.score_launches++;
+      SLG_CUDA(ix, cudaEventRecord(ix->ev[3], st));
+    }
+    HitDev *hits = bt->seg_hits.as<HitDev>() + (size_t)si * Q * k;
+    uint32_t *cnts = bt->seg_counts.as<uint32_t>() + (size_t)si * Q;
+    size_t fsmem = (size_t)(1u << (32 - __builtin_clz(std::max(k, 2u) - 1))) * 8;
+    slg_finalize_kernel<<<Q, kThreads, fsmem, st>>>(bd, s->ord, hits, cnts);
+    count_launch(ix);
+    SLG_CUDA(ix, cudaGetLastError());
+    if (ix->segs.size() > 1 && bt->U && s->doc_count) {
+      // per-segment score time must be read before the events are reused
+      SLG_CUDA(ix, cudaEventSynchronize(ix->ev[3]));
+      float ms = 0;
+      SLG_CUDA(ix, cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3]));
+      ix->ctr.score_ms_total += ms;
+      ix->ctr.last_score_ms = ms;
+    }
+    si++;
+  }
+  bt->n_segs_run = si;
+  if (si > 1) {
+    size_t msmem = (size_t)si * k * sizeof(HitDev);
+    if (msmem > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "merge of %u segments x k=%u does not fit shared memory", si, k);
+    SLG_CUDA(ix, cudaFuncSetAttribute(slg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    slg_merge_kernel<<<Q, kThreads, msmem, st>>>(bt->seg_hits.as<HitDev>(), bt->seg_counts.as<uint32_t>(), si, Q, k,
+                                                 bt->out_hits.as<HitDev>(), bt->out_counts.as<uint32_t>());
+    count_launch(ix);
+    SLG_CUDA(ix, cudaGetLastError());
+  }
+  SLG_CUDA(ix, cudaEventRecord(ix->ev[1], st));
+  ix->ctr.last_posting_count = bt->posting_count;
+  if (sync) {
+    SLG_CUDA(ix, cudaStreamSynchronize(st));
+    float ms = 0;
+    SLG_CUDA(ix, cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[1]));
+    ix->ctr.last_batch_ms = ms;
+    if (ix->segs.size() == 1 && bt->U) {
+      SLG_CUDA(ix, cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3]));
+      ix->ctr.score_ms_total += ms;
+      ix->ctr.last_score_ms = ms;
+    }
+  }
+  return SLG_OK;
+}
+
+int32_t slg_batch_device_results(slg_batch_t *bt, void **dev_hits, void **dev_counts) {
+  if (!bt || !dev_hits || !dev_counts) return SLG_ERR_INVALID;
+  bool merged = bt->n_segs_run > 1;
+  *dev_hits = merged ? bt->out_hits.p : bt->seg_hits.p;
+  *dev_counts = merged ? bt->out_counts.p : bt->seg_counts.p;
+  return SLG_OK;
+}
+
+int32_t slg_batch_fetch(slg_batch_t *bt, slg_hit_t *out_hits, uint32_t *out_counts, slg_stats_t *out_stats) {
+  if (!bt || !out_hits || !out_counts) return SLG_ERR_INVALID;
+  slg_index *ix = bt->ix;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  cudaStream_t st = ix->stream;
+  void *dh, *dc;
+  slg_batch_device_results(bt, &dh, &dc);
+  static_assert(sizeof(slg_hit_t) == sizeof(HitDev), "hit layout");
+  size_t hb = (size_t)bt->Q * bt->k * sizeof(slg_hit_t), cb = (size_t)bt->Q * 4, sb = (size_t)bt->Q * 32;
+  unsigned char *pin = static_cast<unsigned char *>(bt->pinned);
+  SLG_CUDA(ix, cudaMemcpyAsync(pin, dh, hb, cudaMemcpyDeviceToHost, st));
+  SLG_CUDA(ix, cudaMemcpyAsync(pin + hb, dc, cb, cudaMemcpyDeviceToHost, st));
+  if (out_stats) SLG_CUDA(ix, cudaMemcpyAsync(pin + hb + cb, bt->stats.p, sb, cudaMemcpyDeviceToHost, st));
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  std::memcpy(out_hits, pin, hb);
+  std::memcpy(out_counts, pin + hb, cb);
+  if (out_stats) {
+    const unsigned long long *sv = reinterpret_cast<const unsigned long long *>(pin + hb + cb);
+    for (uint32_t q = 0; q < bt->Q; q++) {
+      out_stats[q].scored_docs = sv[q * 4 + 0];
+      out_stats[q].postings_advanced = sv[q * 4 + 1];
+      out_stats[q].blocks_skipped = sv[q * 4 + 2];
+      out_stats[q].candidates_examined = sv[q * 4 + 3];
+    }
+  }
+  return SLG_OK;
+}
+
+int32_t slg_batch_free(slg_batch_t *bt) {
+  if (!bt) return SLG_OK;
+  cudaSetDevice(bt->ix->device);
+  cudaStreamSynchronize(bt->ix->stream);
+  delete bt;
+  return SLG_OK;
+}
+
+int32_t slg_search_batch(slg_index_t *ix, const slg_query_t *queries, uint32_t n_queries, uint32_t k, slg_exec_t exec,
+                         uint32_t bmw_block_size, slg_hit_t *out_hits, uint32_t *out_counts, slg_stats_t *out_stats) {
+  if (!ix) return SLG_ERR_INVALID;
+  if (!out_hits || !out_counts) return fail(ix, SLG_ERR_INVALID, "output buffers are NULL");
+  slg_batch_t *bt = nullptr;
+  int32_t rc = slg_batch_prepare(ix, queries, n_queries, k, exec, bmw_block_size, &bt);
+  if (rc) return rc;
+  rc = slg_batch_run(bt, 0);
+  if (rc == SLG_OK) rc = slg_batch_fetch(bt, out_hits, out_counts, out_stats);
+  if (rc == SLG_OK && ix->segs.size() == 1 && bt->U) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3]) == cudaSuccess) {
+      ix->ctr.score_ms_total += ms;
+      ix->ctr.last_score_ms = ms;
+    }
+    if (cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[1]) == cudaSuccess) ix->ctr.last_batch_ms = ms;
+  }
+  slg_batch_free(bt);
+  return rc;
+}
+
+int32_t slg_merge_gathered(slg_index_t *ix, const void *dev_hits, const void *dev_counts, uint32_t n_shards,
+                           uint32_t n_queries, uint32_t k, slg_hit_t *out_hits, uint32_t *out_counts) {
+  if (!ix || !dev_hits || !dev_counts || !out_hits || !out_counts || !n_shards || !n_queries || !k) return SLG_ERR_INVALID;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  cudaStream_t st = ix->stream;
+  size_t msmem = (size_t)n_shards * k * sizeof(HitDev);
+  if (msmem > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "merge of %u shards x k=%u does not fit shared memory", n_shards, k);
+  DevBuf oh, oc;
+  SLG_CUDA(ix, oh.alloc((size_t)n_queries * k * sizeof(HitDev)));
+  SLG_CUDA(ix, oc.alloc((size_t)n_queries * 4));
+  SLG_CUDA(ix, cudaFuncSetAttribute(slg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+  slg_merge_kernel<<<n_queries, kThreads, msmem, st>>>(static_cast<const HitDev *>(dev_hits), static_cast<const uint32_t *>(dev_counts),
+                                                       n_shards, n_queries, k, oh.as<HitDev>(), oc.as<uint32_t>());
+  count_launch(ix);
+  SLG_CUDA(ix, cudaGetLastError());
+  SLG_CUDA(ix, cudaMemcpyAsync(out_hits, oh.p, (size_t)n_queries * k * sizeof(HitDev), cudaMemcpyDeviceToHost, st));
+  SLG_CUDA(ix, cudaMemcpyAsync(out_counts, oc.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, st));
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  return SLG_OK;
+}
+
+/* ---- vectors + rerank ---- */
+int32_t slg_load_vectors(slg_index_t *ix, uint32_t segment_ord, uint32_t dim, const uint32_t *offsets, const float *values,
+                         uint64_t n_rows, int32_t store_bf16) {
+  if (!ix || !offsets || (!values && n_rows) || !dim) return SLG_ERR_INVALID;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  Segment *s = ix->find(segment_ord);
+  if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
+  if (dim % 8) return fail(ix, SLG_ERR_UNSUPPORTED, "vector dim must be a multiple of 8");
+  cudaStream_t st = ix->stream;
+  Vectors &v = s->vec;
+  v.dim = dim;
+  v.n_rows = n_rows;
+  v.bf16 = store_bf16 != 0;
+  SLG_CUDA(ix, v.offsets.alloc(std::max<size_t>(s->doc_count, 1) * 4));
+  SLG_CUDA(ix, cudaMemcpyAsync(v.offsets.p, offsets, (size_t)s->doc_count * 4, cudaMemcpyHostToDevice, st));
+  size_t n = (size_t)n_rows * dim;
+  if (!v.bf16) {
+    SLG_CUDA(ix, v.values.alloc(std::max<size_t>(n, 1) * 4));
+    if (n) SLG_CUDA(ix, cudaMemcpyAsync(v.values.p, values, n * 4, cudaMemcpyHostToDevice, st));
+  } else {
+    DevBuf tmp;
+    SLG_CUDA(ix, tmp.alloc(std::max<size_t>(n, 1) * 4));
+    if (n) SLG_CUDA(ix, cudaMemcpyAsync(tmp.p, values, n * 4, cudaMemcpyHostToDevice, st));
+    SLG_CUDA(ix, v.values.alloc(std::max<size_t>(n, 1) * 2));
+    if (n) {
+      slg_f32_to_bf16_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 1u << 20), 256, 0, st>>>(tmp.as<float>(), v.values.as<__nv_bfloat16>(), n);
+      count_launch(ix);
+    }
+    SLG_CUDA(ix, cudaStreamSynchronize(st));
+  }
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  return SLG_OK;
+}
+
+int32_t slg_rerank(slg_index_t *ix, const float *query_vecs, uint32_t n_queries, uint32_t dim, const slg_hit_t *cands,
+                   const uint32_t *cand_counts, uint32_t cand_stride, float alpha, slg_metric_t metric, slg_hit_t *out_hits,
+                   float *out_vector_scores) {
+  if (!ix || !query_vecs || !cands || !cand_counts || !out_hits || !n_queries || !cand_stride) return SLG_ERR_INVALID;
+  if (metric != SLG_METRIC_COSINE && metric != SLG_METRIC_L2) return fail(ix, SLG_ERR_INVALID, "unknown metric");
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  cudaStream_t st = ix->stream;
+  // segment table for the kernel
+  std::vector<RerankSegDev> segs;
+  for (auto &s : ix->segs) {
+    RerankSegDev r{};
+    r.segment_ord = s->ord;
+    r.doc_count = s->doc_count;
+    r.offsets = s->vec.offsets.as<uint32_t>();
+    r.values = s->vec.values.p;
+    r.bf16 = s->vec.bf16 ? 1 : 0;
+    r.dim = s->vec.dim;
+    if (s->vec.dim && s->vec.dim != dim) return fail(ix, SLG_ERR_INVALID, "query dim %u != stored dim %u", dim, s->vec.dim);
+    segs.push_back(r);
+  }
+  if (cand_stride > kMaxRerankCands) return fail(ix, SLG_ERR_UNSUPPORTED, "more than %u candidates per query", kMaxRerankCands);
+  DevBuf d_segs, d_q, d_c, d_n, d_o, d_vs;
+  size_t nh = (size_t)n_queries * cand_stride;
+  SLG_CUDA(ix, d_segs.alloc(segs.size() * sizeof(RerankSegDev)));
+  SLG_CUDA(ix, cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(RerankSegDev), cudaMemcpyHostToDevice, st));
+  SLG_CUDA(ix, d_q.alloc((size_t)n_queries * dim * 4));
+  SLG_CUDA(ix, cudaMemcpyAsync(d_q.p, query_vecs, (size_t)n_queries * dim * 4, cudaMemcpyHostToDevice, st));
+  SLG_CUDA(ix, d_c.alloc(nh * sizeof(HitDev)));
+  SLG_CUDA(ix, cudaMemcpyAsync(d_c.p, cands, nh * sizeof(HitDev), cudaMemcpyHostToDevice, st));
+  SLG_CUDA(ix, d_n.alloc((size_t)n_queries * 4));
+  SLG_CUDA(ix, cudaMemcpyAsync(d_n.p, cand_counts, (size_t)n_queries * 4, cudaMemcpyHostToDevice, st));
+  SLG_CUDA(ix, d_o.alloc(nh * sizeof(HitDev)));
+  SLG_CUDA(ix, d_vs.alloc(nh * 4));
+  size_t smem = (size_t)dim * 4 + (size_t)cand_stride * (sizeof(HitDev) + 4);
+  if (smem > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "rerank tile does not fit shared memory");
+  SLG_CUDA(ix, cudaFuncSetAttribute(slg_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  slg_rerank_kernel<<<n_queries, 256, smem, st>>>(d_segs.as<RerankSegDev>(), (uint32_t)segs.size(), d_q.as<float>(), dim,
+                                                  d_c.as<HitDev>(), d_n.as<uint32_t>(), cand_stride, alpha, (int)metric,
+                                                  d_o.as<HitDev>(), d_vs.as<float>());
+  count_launch(ix);
+  SLG_CUDA(ix, cudaGetLastError());
+  SLG_CUDA(ix, cudaMemcpyAsync(out_hits, d_o.p, nh * sizeof(HitDev), cudaMemcpyDeviceToHost, st));
+  if (out_vector_scores) SLG_CUDA(ix, cudaMemcpyAsync(out_vector_scores, d_vs.p, nh * 4, cudaMemcpyDeviceToHost, st));
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  return SLG_OK;
+}
+
+int32_t slg_get_counters(const slg_index_t *ix, slg_counters_t *out) {
+  if (!ix || !out) return SLG_ERR_INVALID;
+  *out = ix->ctr;
+  return SLG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,462 @@
+"""ctypes binding of libsearchlite_gpu.so — the host-side mirror of the reference's search API
+for the hot path (searchlite-core/src/api/reader.rs:2539 ``IndexReader::search`` →
+``search_segment`` :2908 → ``execute_top_k`` src/query/wand.rs:338).
+
+Names follow the reference: segments, postings, ``execution`` ∈ {"bm25", "wand", "bmw"}
+(src/api/types.rs:6-13), ``limit``/internal ``k = limit + 1`` (api/reader.rs:2595-2619).
+The binding fails loudly when the CUDA library is missing or no device is present: there is
+no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import build as _build
+
+EXECUTION = {"bm25": 0, "wand": 1, "bmw": 2}
+ROLE_SHOULD, ROLE_MUST, ROLE_MUST_NOT = 0, 1, 2
+TERM_SCORED = 1
+ABSENT_TERM = 0xFFFFFFFF
+MEM_HOST, MEM_DEVICE = 0, 1
+
+F_KEYWORD_EQ, F_KEYWORD_IN, F_I64_RANGE, F_F64_RANGE, F_AND, F_OR, F_NOT = range(7)
+METRIC = {"cosine": 0, "l2": 1}
+
+# numpy mirrors of the C structs (include/searchlite_gpu.h)
+TERM_DTYPE = np.dtype(
+    {"names": ["term_id", "weight", "leaf", "group", "flags"],
+     "formats": ["<u4", "<f4", "<u4", "<u4", "<u4"], "itemsize": 20})
+QUERY_DTYPE = np.dtype(
+    {"names": ["n_terms", "terms", "n_groups", "group_role", "min_should", "leaf_count", "filter_id"],
+     "formats": ["<u4", "<u8", "<u4", "<u8", "<u4", "<u4", "<i4"],
+     "offsets": [0, 8, 16, 24, 32, 36, 40], "itemsize": 48})
+HIT_DTYPE = np.dtype({"names": ["segment_ord", "doc_id", "score"], "formats": ["<u4", "<u4", "<f4"], "itemsize": 12})
+STATS_DTYPE = np.dtype(
+    {"names": ["scored_docs", "postings_advanced", "blocks_skipped", "candidates_examined"],
+     "formats": ["<u8"] * 4, "itemsize": 32})
+FILTER_DTYPE = np.dtype(
+    {"names": ["op", "column", "i_min", "i_max", "f_min", "f_max", "n_children", "value_begin", "value_end"],
+     "formats": ["<u4", "<i4", "<i8", "<i8", "<f8", "<f8", "<u4", "<u4", "<u4"],
+     "offsets": [0, 4, 8, 16, 24, 32, 40, 44, 48], "itemsize": 56})
+
+
+class SegmentView(C.Structure):
+    _fields_ = [
+        ("segment_ord", C.c_uint32), ("doc_count", C.c_uint32), ("n_terms", C.c_uint64),
+        ("term_offsets", C.c_void_p), ("post_docs", C.c_void_p), ("post_tfs", C.c_void_p),
+        ("field_lengths", C.c_void_p), ("field_length_present", C.c_void_p),
+        ("total_tokens", C.c_uint64), ("deleted_docs", C.c_void_p), ("n_deleted", C.c_uint32),
+        ("memory_space", C.c_int32),
+    ]
+
+
+class Counters(C.Structure):
+    _fields_ = [
+        ("kernel_launches", C.c_uint64), ("score_launches", C.c_uint64), ("score_ms_total", C.c_double),
+        ("last_score_ms", C.c_double), ("last_batch_ms", C.c_double), ("last_posting_count", C.c_uint64),
+        ("resident_bytes", C.c_uint64),
+    ]
+
+
+class SearchliteGpuError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"searchlite_gpu error {code}: {message}")
+        self.code = code
+
+
+_LIB = None
+
+# every symbol include/searchlite_gpu.h declares
+EXPORTED_SYMBOLS = [
+    "slg_open", "slg_close", "slg_last_error", "slg_configure", "slg_load_segment", "slg_load_segment_post_image",
+    "slg_add_i64_column", "slg_add_f64_column", "slg_add_str_column", "slg_segment_stats", "slg_filter_compile",
+    "slg_filter_bitmap", "slg_search_batch", "slg_batch_prepare", "slg_batch_run", "slg_batch_fetch",
+    "slg_batch_device_results", "slg_batch_free", "slg_merge_gathered", "slg_load_vectors", "slg_rerank",
+    "slg_get_counters", "slg_version",
+]
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen the in-tree CUDA library; raises if it is absent (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise RuntimeError(f"{path} is missing: build it with `python -m searchlite_b200.build`")
+        _build.build()
+    lib = C.CDLL(path)
+    lib.slg_last_error.restype = C.c_char_p
+    lib.slg_last_error.argtypes = [C.c_void_p]
+    lib.slg_version.restype = C.c_char_p
+    vp, u32, i32, u64, f32 = C.c_void_p, C.c_uint32, C.c_int32, C.c_uint64, C.c_float
+    sigs = {
+        "slg_open": [i32, C.POINTER(vp)],
+        "slg_close": [vp],
+        "slg_configure": [vp, u32, u32],
+        "slg_load_segment": [vp, C.POINTER(SegmentView), f32, f32],
+        "slg_load_segment_post_image": [vp, C.POINTER(SegmentView), vp, u64, vp, f32, f32],
+        "slg_add_i64_column": [vp, u32, vp, vp],
+        "slg_add_f64_column": [vp, u32, vp, vp],
+        "slg_add_str_column": [vp, u32, C.POINTER(C.c_char_p), u32, vp],
+        "slg_segment_stats": [vp, u32, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), C.POINTER(u64)],
+        "slg_filter_compile": [vp, vp, u32, C.POINTER(C.c_char_p)],
+        "slg_filter_bitmap": [vp, i32, u32, vp],
+        "slg_search_batch": [vp, vp, u32, u32, i32, u32, vp, vp, vp],
+        "slg_batch_prepare": [vp, vp, u32, u32, i32, u32, C.POINTER(vp)],
+        "slg_batch_run": [vp, i32],
+        "slg_batch_fetch": [vp, vp, vp, vp],
+        "slg_batch_device_results": [vp, C.POINTER(vp), C.POINTER(vp)],
+        "slg_batch_free": [vp],
+        "slg_merge_gathered": [vp, vp, vp, u32, u32, u32, vp, vp],
+        "slg_load_vectors": [vp, u32, u32, vp, vp, u64, i32],
+        "slg_rerank": [vp, vp, u32, u32, vp, vp, u32, f32, i32, vp, vp],
+        "slg_get_counters": [vp, C.POINTER(Counters)],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int32
+    _LIB = lib
+    return lib
+
+
+def _ptr(a) -> int:
+    """address of a numpy array / torch tensor / None"""
+    if a is None:
+        return 0
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a.data_ptr())  # torch tensor
+
+
+@dataclass
+class SegmentData:
+    """One segment as SegmentReader holds it (index/segment.rs:1239): CSR postings + `_len:` column.
+
+    Arrays are numpy (host) or torch CUDA tensors (device); all five must live in one space."""
+    segment_ord: int
+    doc_count: int
+    term_offsets: object   # u64/int64 [n_terms+1]
+    post_docs: object      # u32/int32 [n_postings]
+    post_tfs: object       # u32/int32 [n_postings]
+    field_lengths: object  # int64 [doc_count]
+    total_tokens: int
+    field_length_present: object = None
+    deleted_docs: Optional[np.ndarray] = None
+    fast_i64: dict = field(default_factory=dict)   # name -> (values int64, present u8|None)
+    fast_f64: dict = field(default_factory=dict)
+    fast_str: dict = field(default_factory=dict)   # name -> (dict list[str], ords u32)
+
+    @property
+    def n_terms(self) -> int:
+        return int(self.term_offsets.shape[0]) - 1
+
+    def is_device(self) -> bool:
+        return not isinstance(self.term_offsets, np.ndarray)
+
+    def to_host(self) -> "SegmentData":
+        if not self.is_device():
+            return self
+        cv = lambda t: None if t is None else t.cpu().numpy()
+        return SegmentData(self.segment_ord, self.doc_count, cv(self.term_offsets), cv(self.post_docs), cv(self.post_tfs),
+                           cv(self.field_lengths), self.total_tokens, cv(self.field_length_present), self.deleted_docs,
+                           self.fast_i64, self.fast_f64, self.fast_str)
+
+
+@dataclass
+class QueryBatch:
+    """Flat batch of queries as search_segment derives them (api/reader.rs:2971-3002): per query the
+    merged "field:term" keys with weights and leaves, the flat matcher (term-group roles +
+    minimum_should_match, api/reader.rs:1485-1565) and an optional root filter id."""
+    term_off: np.ndarray                  # int64 [Q+1]
+    terms: np.ndarray                     # TERM_DTYPE [T]
+    group_off: Optional[np.ndarray] = None  # int64 [Q+1]; None = plain OR queries
+    group_role: Optional[np.ndarray] = None  # u8 [G]
+    min_should: Optional[np.ndarray] = None  # u32 [Q]
+    filter_id: Optional[np.ndarray] = None   # i32 [Q]
+    _structs: Optional[np.ndarray] = None
+
+    @property
+    def n_queries(self) -> int:
+        return len(self.term_off) - 1
+
+    @staticmethod
+    def from_term_lists(term_lists: Sequence[Sequence[int]], weights: Optional[Sequence[Sequence[float]]] = None) -> "QueryBatch":
+        """plain OR queries (QueryString, minimum_should_match 1): each term is its own leaf"""
+        off = np.zeros(len(term_lists) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(t) for t in term_lists])
+        terms = np.zeros(int(off[-1]), dtype=TERM_DTYPE)
+        p = 0
+        for qi, tl in enumerate(term_lists):
+            for j, t in enumerate(tl):
+                terms[p] = (t, 1.0 if weights is None else weights[qi][j], j, 0, TERM_SCORED)
+                p += 1
+        return QueryBatch(off, terms)
+
+    @staticmethod
+    def from_bool(queries: Sequence[dict]) -> "QueryBatch":
+        """Bool queries: each dict has `must`, `should`, `must_not` (lists of term ids; one group per
+        term), optional `min_should` (defaults as api/reader.rs:1553-1561), optional `filter_id`."""
+        toff, goff = [0], [0]
+        trows, roles, mins, fids = [], [], [], []
+        for q in queries:
+            g = 0
+            leaf = 0
+            for role, key in ((ROLE_MUST, "must"), (ROLE_SHOULD, "should"), (ROLE_MUST_NOT, "must_not")):
+                for t in q.get(key, []):
+                    scored = role != ROLE_MUST_NOT
+                    trows.append((t, 1.0, leaf if scored else 0, g, TERM_SCORED if scored else 0))
+                    if scored:
+                        leaf += 1
+                    roles.append(role)
+                    g += 1
+            ms = q.get("min_should")
+            if ms is None:
+                ms = 0 if (not q.get("should") or q.get("must") or q.get("filter_id", -1) >= 0) else 1
+            mins.append(ms)
+            fids.append(q.get("filter_id", -1))
+            toff.append(len(trows))
+            goff.append(len(roles))
+        terms = np.array(trows, dtype=TERM_DTYPE) if trows else np.zeros(0, dtype=TERM_DTYPE)
+        return QueryBatch(np.array(toff, dtype=np.int64), terms, np.array(goff, dtype=np.int64),
+                          np.array(roles, dtype=np.uint8), np.array(mins, dtype=np.uint32), np.array(fids, dtype=np.int32))
+
+    def structs(self) -> np.ndarray:
+        """array of slg_query_t (same layout as the oracle's slo_query_t plus filter_id)"""
+        if self._structs is not None:
+            return self._structs
+        q = self.n_queries
+        self.terms = np.ascontiguousarray(self.terms)
+        s = np.zeros(q, dtype=QUERY_DTYPE)
+        s["n_terms"] = (self.term_off[1:] - self.term_off[:-1]).astype(np.uint32)
+        s["terms"] = self.terms.ctypes.data + self.term_off[:-1].astype(np.uint64) * np.uint64(TERM_DTYPE.itemsize)
+        if self.group_off is not None:
+            self.group_role = np.ascontiguousarray(self.group_role, dtype=np.uint8)
+            s["n_groups"] = (self.group_off[1:] - self.group_off[:-1]).astype(np.uint32)
+            s["group_role"] = self.group_role.ctypes.data + self.group_off[:-1].astype(np.uint64)
+            s["min_should"] = self.min_should
+        else:
+            s["n_groups"] = 0
+            s["group_role"] = 0
+            s["min_should"] = 1
+        s["leaf_count"] = 0
+        s["filter_id"] = -1 if self.filter_id is None else self.filter_id
+        self._structs = s
+        return s
+
+    def subset(self, lo: int, hi: int) -> "QueryBatch":
+        t0, t1 = int(self.term_off[lo]), int(self.term_off[hi])
+        qb = QueryBatch(self.term_off[lo:hi + 1] - t0, self.terms[t0:t1].copy())
+        if self.group_off is not None:
+            g0, g1 = int(self.group_off[lo]), int(self.group_off[hi])
+            qb.group_off = self.group_off[lo:hi + 1] - g0
+            qb.group_role = self.group_role[g0:g1].copy()
+            qb.min_should = self.min_should[lo:hi].copy()
+        if self.filter_id is not None:
+            qb.filter_id = self.filter_id[lo:hi].copy()
+        return qb
+
+
+class PreparedBatch:
+    """A query batch resident on the device (slg_batch_prepare)."""
+
+    def __init__(self, index: "GpuIndex", handle: int, n_queries: int, k: int, keepalive):
+        self.index, self.handle, self.n_queries, self.k = index, handle, n_queries, k
+        self._keepalive = keepalive
+
+    def run(self, sync: bool = True) -> None:
+        self.index._check(self.index.lib.slg_batch_run(self.handle, 1 if sync else 0))
+
+    def fetch(self, want_stats: bool = False):
+        hits = np.zeros((self.n_queries, self.k), dtype=HIT_DTYPE)
+        counts = np.zeros(self.n_queries, dtype=np.uint32)
+        stats = np.zeros(self.n_queries, dtype=STATS_DTYPE) if want_stats else None
+        self.index._check(self.index.lib.slg_batch_fetch(self.handle, _ptr(hits), _ptr(counts), _ptr(stats)))
+        return (hits, counts, stats) if want_stats else (hits, counts)
+
+    def device_results(self):
+        dh, dc = C.c_void_p(), C.c_void_p()
+        self.index._check(self.index.lib.slg_batch_device_results(self.handle, C.byref(dh), C.byref(dc)))
+        return dh.value, dc.value
+
+    def free(self) -> None:
+        if self.handle:
+            self.index.lib.slg_batch_free(self.handle)
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class GpuIndex:
+    """Device-resident index: the GPU stand-in for Index::reader() + IndexReader::search on the
+    BM25 top-k path.  One instance owns one CUDA device/stream."""
+
+    def __init__(self, device: int = 0, tile_docs: int = 0, ctas_per_sm: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.slg_open(device, C.byref(h))
+        if rc != 0:
+            raise SearchliteGpuError(rc, (self.lib.slg_last_error(None) or b"").decode())
+        self.handle = h
+        self.device = device
+        self._keep = []
+        if tile_docs or ctas_per_sm:
+            self._check(self.lib.slg_configure(self.handle, tile_docs, ctas_per_sm))
+
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise SearchliteGpuError(rc, (self.lib.slg_last_error(self.handle) or b"").decode())
+        return rc
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.slg_close(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- residency -------------------------------------------------------------------------
+    def _view(self, seg: SegmentData, with_postings: bool = True) -> SegmentView:
+        dev = seg.is_device()
+        v = SegmentView()
+        v.segment_ord, v.doc_count, v.n_terms = seg.segment_ord, seg.doc_count, seg.n_terms
+        if with_postings:
+            for name in ("term_offsets", "post_docs", "post_tfs"):
+                a = getattr(seg, name)
+                if isinstance(a, np.ndarray):
+                    want = np.uint64 if name == "term_offsets" else np.uint32
+                    if a.dtype.itemsize != np.dtype(want).itemsize:
+                        a = a.astype(want)
+                    a = np.ascontiguousarray(a)
+                    setattr(seg, name, a)
+                setattr(v, name, _ptr(a))
+        if isinstance(seg.field_lengths, np.ndarray):
+            seg.field_lengths = np.ascontiguousarray(seg.field_lengths, dtype=np.int64)
+        v.field_lengths = _ptr(seg.field_lengths)
+        v.field_length_present = _ptr(seg.field_length_present)
+        v.total_tokens = int(seg.total_tokens)
+        if seg.deleted_docs is not None and len(seg.deleted_docs):
+            seg.deleted_docs = np.ascontiguousarray(seg.deleted_docs, dtype=np.uint32)
+            v.deleted_docs = _ptr(seg.deleted_docs)
+            v.n_deleted = len(seg.deleted_docs)
+        v.memory_space = MEM_DEVICE if dev else MEM_HOST
+        return v
+
+    def load_segment(self, seg: SegmentData, k1: float = 0.9, b: float = 0.4) -> dict:
+        """SegmentReader::open for the hot path; also registers the segment's fast-field columns.
+        Returns {column name: handle}."""
+        if seg.is_device():
+            import torch
+            torch.cuda.synchronize()
+        v = self._view(seg)
+        self._check(self.lib.slg_load_segment(self.handle, C.byref(v), k1, b))
+        return self._add_columns(seg)
+
+    def load_segment_post_image(self, seg: SegmentData, post_image: np.ndarray, post_offsets: np.ndarray,
+                                k1: float = 0.9, b: float = 0.4) -> dict:
+        """Load from the reference's `.post` byte image (index/postings.rs:78-129)."""
+        host = seg.to_host()
+        v = self._view(host, with_postings=False)
+        v.memory_space = MEM_HOST
+        post_image = np.ascontiguousarray(post_image, dtype=np.uint8)
+        post_offsets = np.ascontiguousarray(post_offsets, dtype=np.uint64)
+        self._check(self.lib.slg_load_segment_post_image(self.handle, C.byref(v), _ptr(post_image), post_image.nbytes,
+                                                         _ptr(post_offsets), k1, b))
+        return self._add_columns(host)
+
+    def _add_columns(self, seg: SegmentData) -> dict:
+        handles = {}
+        for name, (vals, present) in seg.fast_i64.items():
+            vals = np.ascontiguousarray(vals, dtype=np.int64)
+            pres = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
+            handles[name] = self._check(self.lib.slg_add_i64_column(self.handle, seg.segment_ord, _ptr(vals), _ptr(pres)))
+        for name, (vals, present) in seg.fast_f64.items():
+            vals = np.ascontiguousarray(vals, dtype=np.float64)
+            pres = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
+            handles[name] = self._check(self.lib.slg_add_f64_column(self.handle, seg.segment_ord, _ptr(vals), _ptr(pres)))
+        for name, (dic, ords) in seg.fast_str.items():
+            ords = np.ascontiguousarray(ords, dtype=np.uint32)
+            arr = (C.c_char_p * len(dic))(*[s.encode() for s in dic])
+            handles[name] = self._check(self.lib.slg_add_str_column(self.handle, seg.segment_ord, arr, len(dic), _ptr(ords)))
+        return handles
+
+    def segment_stats(self, segment_ord: int) -> dict:
+        a, l, m, n = C.c_float(), C.c_float(), C.c_float(), C.c_uint64()
+        self._check(self.lib.slg_segment_stats(self.handle, segment_ord, C.byref(a), C.byref(l), C.byref(m), C.byref(n)))
+        return {"avgdl": a.value, "live_docs": l.value, "min_doc_len": m.value, "n_postings": n.value}
+
+    # ---- filters ---------------------------------------------------------------------------
+    def compile_filter(self, nodes: np.ndarray, strings: Sequence[str] = ()) -> int:
+        nodes = np.ascontiguousarray(nodes, dtype=FILTER_DTYPE)
+        arr = (C.c_char_p * max(len(strings), 1))(*[s.encode() for s in strings])
+        return self._check(self.lib.slg_filter_compile(self.handle, _ptr(nodes), len(nodes), arr))
+
+    def filter_bitmap(self, filter_id: int, segment_ord: int, doc_count: int) -> np.ndarray:
+        out = np.zeros((doc_count + 31) // 32, dtype=np.uint32)
+        self._check(self.lib.slg_filter_bitmap(self.handle, filter_id, segment_ord, _ptr(out)))
+        return out
+
+    # ---- search ----------------------------------------------------------------------------
+    def search_batch(self, batch: QueryBatch, k: int, execution: str = "bm25", bmw_block_size: int = 0,
+                     want_stats: bool = False):
+        """One call, host buffers in and out (the call a searchlite-core shim would make per batch)."""
+        s = batch.structs()
+        hits = np.zeros((batch.n_queries, k), dtype=HIT_DTYPE)
+        counts = np.zeros(batch.n_queries, dtype=np.uint32)
+        stats = np.zeros(batch.n_queries, dtype=STATS_DTYPE) if want_stats else None
+        self._check(self.lib.slg_search_batch(self.handle, _ptr(s), batch.n_queries, k, EXECUTION[execution],
+                                              bmw_block_size, _ptr(hits), _ptr(counts), _ptr(stats)))
+        return (hits, counts, stats) if want_stats else (hits, counts)
+
+    def prepare(self, batch: QueryBatch, k: int, execution: str = "bm25", bmw_block_size: int = 0) -> PreparedBatch:
+        s = batch.structs()
+        h = C.c_void_p()
+        self._check(self.lib.slg_batch_prepare(self.handle, _ptr(s), batch.n_queries, k, EXECUTION[execution],
+                                               bmw_block_size, C.byref(h)))
+        return PreparedBatch(self, h, batch.n_queries, k, batch)
+
+    def merge_gathered(self, dev_hits_ptr: int, dev_counts_ptr: int, n_shards: int, n_queries: int, k: int):
+        hits = np.zeros((n_queries, k), dtype=HIT_DTYPE)
+        counts = np.zeros(n_queries, dtype=np.uint32)
+        self._check(self.lib.slg_merge_gathered(self.handle, dev_hits_ptr, dev_counts_ptr, n_shards, n_queries, k,
+                                                _ptr(hits), _ptr(counts)))
+        return hits, counts
+
+    # ---- vectors ---------------------------------------------------------------------------
+    def load_vectors(self, segment_ord: int, offsets: np.ndarray, values: np.ndarray, store_bf16: bool = False) -> None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        n_rows, dim = (values.shape if values.ndim == 2 else (0, 0))
+        self._check(self.lib.slg_load_vectors(self.handle, segment_ord, dim, _ptr(offsets), _ptr(values), n_rows,
+                                              1 if store_bf16 else 0))
+
+    def rerank(self, query_vecs: np.ndarray, cands: np.ndarray, cand_counts: np.ndarray, alpha: float, metric: str = "cosine"):
+        query_vecs = np.ascontiguousarray(query_vecs, dtype=np.float32)
+        cands = np.ascontiguousarray(cands, dtype=HIT_DTYPE)
+        cand_counts = np.ascontiguousarray(cand_counts, dtype=np.uint32)
+        nq, stride = cands.shape
+        out = np.zeros((nq, stride), dtype=HIT_DTYPE)
+        vs = np.zeros((nq, stride), dtype=np.float32)
+        self._check(self.lib.slg_rerank(self.handle, _ptr(query_vecs), nq, query_vecs.shape[1], _ptr(cands), _ptr(cand_counts),
+                                        stride, alpha, METRIC[metric], _ptr(out), _ptr(vs)))
+        return out, vs
+
+    def counters(self) -> dict:
+        c = Counters()
+        self._check(self.lib.slg_get_counters(self.handle, C.byref(c)))
+        return {n: getattr(c, n) for n, _ in Counters._fields_}
