@@ -139,6 +139,8 @@ typedef struct {
   double last_batch_ms;        /* device time of the last slg_batch_run (all kernels) */
   uint64_t last_posting_count; /* sum over queries of df of their scored terms, last batch */
   uint64_t resident_bytes;     /* device bytes held by loaded segments */
+  uint64_t last_h2d_bytes;     /* host->device bytes of the last slg_batch_prepare */
+  uint64_t last_d2h_bytes;     /* device->host bytes of the last slg_batch_fetch / slg_merge_gathered */
 } slg_counters_t;
 
 /* ---- lifetime ---- */
@@ -190,6 +192,9 @@ int32_t slg_batch_fetch(slg_batch_t *, slg_hit_t *out_hits, uint32_t *out_counts
 /* device pointers of the last run's results (n_queries*k slg_hit_t, n_queries u32) for an
  * allgather by the caller; valid until the batch is re-run or freed */
 int32_t slg_batch_device_results(slg_batch_t *, void **dev_hits, void **dev_counts);
+/* device->device copy of the last run's results into caller buffers (e.g. the send buffer of an
+ * allgather), asynchronous on the handle's stream */
+int32_t slg_batch_copy_results_device(slg_batch_t *, void *dst_dev_hits, void *dst_dev_counts);
 int32_t slg_batch_free(slg_batch_t *);
 
 /* ---- shard merge (api/reader.rs:2777): gathered is n_shards x n_queries x k hits (DEVICE memory),
@@ -212,6 +217,9 @@ int32_t slg_rerank(slg_index_t *, const float *query_vecs, uint32_t n_queries, u
 
 /* ---- introspection ---- */
 int32_t slg_get_counters(const slg_index_t *, slg_counters_t *out);
+/* the cudaStream_t every call on this handle is ordered on (for callers that enqueue their own
+ * work — an NCCL allgather, timing events — between calls) */
+int32_t slg_get_stream(const slg_index_t *, void **cuda_stream);
 const char *slg_version(void);
 
 #ifdef __cplusplus

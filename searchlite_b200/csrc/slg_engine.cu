@@ -887,6 +887,7 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   put(bt->off_q_filter, q_filter.data(), (size_t)n_queries * 4);
   SLG_CUDA(ix, bt->d_pack.alloc(pos));
   SLG_CUDA(ix, cudaMemcpyAsync(bt->d_pack.p, hp, pos, cudaMemcpyHostToDevice, ix->stream));
+  ix->ctr.last_h2d_bytes = pos;
 
   uint32_t max_tiles = 0;
   for (auto &s : ix->segs) max_tiles = std::max(max_tiles, (s->doc_count + ix->tile_docs - 1) / ix->tile_docs);
@@ -929,8 +930,6 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
   if (ix->ctas_per_sm) per_sm = std::min(per_sm, ix->ctas_per_sm);
   SLG_CUDA(ix, cudaEventRecord(ix->ev[0], st));
   SLG_CUDA(ix, cudaMemsetAsync(bt->stats.p, 0, (size_t)Q * 32, st));
-  double score_ms_pending = 0;
-  (void)score_ms_pending;
   uint32_t si = 0;
   for (auto &sp : ix->segs) {
     Segment *s = sp.get();
@@ -1052,6 +1051,7 @@ int32_t slg_batch_fetch(slg_batch_t *bt, slg_hit_t *out_hits, uint32_t *out_coun
   SLG_CUDA(ix, cudaMemcpyAsync(pin + hb, dc, cb, cudaMemcpyDeviceToHost, st));
   if (out_stats) SLG_CUDA(ix, cudaMemcpyAsync(pin + hb + cb, bt->stats.p, sb, cudaMemcpyDeviceToHost, st));
   SLG_CUDA(ix, cudaStreamSynchronize(st));
+  ix->ctr.last_d2h_bytes = hb + cb + (out_stats ? sb : 0);
   std::memcpy(out_hits, pin, hb);
   std::memcpy(out_counts, pin + hb, cb);
   if (out_stats) {
@@ -1063,6 +1063,17 @@ int32_t slg_batch_fetch(slg_batch_t *bt, slg_hit_t *out_hits, uint32_t *out_coun
       out_stats[q].candidates_examined = sv[q * 4 + 3];
     }
   }
+  return SLG_OK;
+}
+
+int32_t slg_batch_copy_results_device(slg_batch_t *bt, void *dst_hits, void *dst_counts) {
+  if (!bt || !dst_hits || !dst_counts) return SLG_ERR_INVALID;
+  slg_index *ix = bt->ix;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  void *dh, *dc;
+  slg_batch_device_results(bt, &dh, &dc);
+  SLG_CUDA(ix, cudaMemcpyAsync(dst_hits, dh, (size_t)bt->Q * bt->k * sizeof(HitDev), cudaMemcpyDeviceToDevice, ix->stream));
+  SLG_CUDA(ix, cudaMemcpyAsync(dst_counts, dc, (size_t)bt->Q * 4, cudaMemcpyDeviceToDevice, ix->stream));
   return SLG_OK;
 }
 
@@ -1113,6 +1124,7 @@ int32_t slg_merge_gathered(slg_index_t *ix, const void *dev_hits, const void *de
   SLG_CUDA(ix, cudaMemcpyAsync(out_hits, oh.p, (size_t)n_queries * k * sizeof(HitDev), cudaMemcpyDeviceToHost, st));
   SLG_CUDA(ix, cudaMemcpyAsync(out_counts, oc.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, st));
   SLG_CUDA(ix, cudaStreamSynchronize(st));
+  ix->ctr.last_d2h_bytes = (size_t)n_queries * k * sizeof(HitDev) + (size_t)n_queries * 4;
   return SLG_OK;
 }
 
@@ -1194,6 +1206,12 @@ int32_t slg_rerank(slg_index_t *ix, const float *query_vecs, uint32_t n_queries,
   SLG_CUDA(ix, cudaMemcpyAsync(out_hits, d_o.p, nh * sizeof(HitDev), cudaMemcpyDeviceToHost, st));
   if (out_vector_scores) SLG_CUDA(ix, cudaMemcpyAsync(out_vector_scores, d_vs.p, nh * 4, cudaMemcpyDeviceToHost, st));
   SLG_CUDA(ix, cudaStreamSynchronize(st));
+  return SLG_OK;
+}
+
+int32_t slg_get_stream(const slg_index_t *ix, void **cuda_stream) {
+  if (!ix || !cuda_stream) return SLG_ERR_INVALID;
+  *cuda_stream = (void *)ix->stream;
   return SLG_OK;
 }
 

@@ -59,7 +59,7 @@ class Counters(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_uint64), ("score_launches", C.c_uint64), ("score_ms_total", C.c_double),
         ("last_score_ms", C.c_double), ("last_batch_ms", C.c_double), ("last_posting_count", C.c_uint64),
-        ("resident_bytes", C.c_uint64),
+        ("resident_bytes", C.c_uint64), ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64),
     ]
 
 
@@ -77,7 +77,7 @@ EXPORTED_SYMBOLS = [
     "slg_add_i64_column", "slg_add_f64_column", "slg_add_str_column", "slg_segment_stats", "slg_filter_compile",
     "slg_filter_bitmap", "slg_search_batch", "slg_batch_prepare", "slg_batch_run", "slg_batch_fetch",
     "slg_batch_device_results", "slg_batch_free", "slg_merge_gathered", "slg_load_vectors", "slg_rerank",
-    "slg_get_counters", "slg_version",
+    "slg_get_counters", "slg_version", "slg_batch_copy_results_device", "slg_get_stream",
 ]
 
 
@@ -118,6 +118,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_load_vectors": [vp, u32, u32, vp, vp, u64, i32],
         "slg_rerank": [vp, vp, u32, u32, vp, vp, u32, f32, i32, vp, vp],
         "slg_get_counters": [vp, C.POINTER(Counters)],
+        "slg_batch_copy_results_device": [vp, vp, vp],
+        "slg_get_stream": [vp, C.POINTER(vp)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -285,6 +287,9 @@ class PreparedBatch:
         dh, dc = C.c_void_p(), C.c_void_p()
         self.index._check(self.index.lib.slg_batch_device_results(self.handle, C.byref(dh), C.byref(dc)))
         return dh.value, dc.value
+
+    def copy_results_to(self, dst_hits_ptr: int, dst_counts_ptr: int) -> None:
+        self.index._check(self.index.lib.slg_batch_copy_results_device(self.handle, dst_hits_ptr, dst_counts_ptr))
 
     def free(self) -> None:
         if self.handle:
@@ -455,6 +460,11 @@ class GpuIndex:
         self._check(self.lib.slg_rerank(self.handle, _ptr(query_vecs), nq, query_vecs.shape[1], _ptr(cands), _ptr(cand_counts),
                                         stride, alpha, METRIC[metric], _ptr(out), _ptr(vs)))
         return out, vs
+
+    def stream_ptr(self) -> int:
+        s = C.c_void_p()
+        self._check(self.lib.slg_get_stream(self.handle, C.byref(s)))
+        return s.value
 
     def counters(self) -> dict:
         c = Counters()
