@@ -187,6 +187,8 @@ int32_t slg_search_batch(slg_index_t *, const slg_query_t *queries, uint32_t n_q
  * sync != 0); fetch = device->host copy of the results of the last run. */
 int32_t slg_batch_prepare(slg_index_t *, const slg_query_t *queries, uint32_t n_queries, uint32_t k,
                           slg_exec_t exec, uint32_t bmw_block_size, slg_batch_t **out);
+/* collect slg_stats_t counters in later runs (off by default: the counting costs a few percent) */
+int32_t slg_batch_enable_stats(slg_batch_t *, int32_t on);
 int32_t slg_batch_run(slg_batch_t *, int32_t sync);
 int32_t slg_batch_fetch(slg_batch_t *, slg_hit_t *out_hits, uint32_t *out_counts, slg_stats_t *out_stats);
 /* device pointers of the last run's results (n_queries*k slg_hit_t, n_queries u32) for an
@@ -220,6 +222,9 @@ int32_t slg_get_counters(const slg_index_t *, slg_counters_t *out);
 /* the cudaStream_t every call on this handle is ordered on (for callers that enqueue their own
  * work — an NCCL allgather, timing events — between calls) */
 int32_t slg_get_stream(const slg_index_t *, void **cuda_stream);
+/* device self-test: the scorer's division sequence against IEEE division on n pseudo-random
+ * operand pairs from the scorer's range; *mismatches must come back 0 */
+int32_t slg_selftest_div(slg_index_t *, uint64_t n, uint64_t seed, uint64_t *mismatches);
 const char *slg_version(void);
 
 #ifdef __cplusplus

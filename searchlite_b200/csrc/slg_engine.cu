@@ -981,7 +981,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
       }
       SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));
       int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * per_sm, (uint64_t)bd.n_tiles * Q);
-      rc = launch_score(ix, bt->matcher, prune, true, s->dev, bd, smem, grid);
+      rc = launch_score(ix, bt->matcher, prune, bt->want_stats, s->dev, bd, smem, grid);
       if (rc) return rc;
       count_launch(ix);
       ix->ctr.score_launches++;
@@ -1026,6 +1026,12 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
       ix->ctr.last_score_ms = ms;
     }
   }
+  return SLG_OK;
+}
+
+int32_t slg_batch_enable_stats(slg_batch_t *bt, int32_t on) {
+  if (!bt) return SLG_ERR_INVALID;
+  bt->want_stats = on != 0;
   return SLG_OK;
 }
 
@@ -1092,6 +1098,7 @@ int32_t slg_search_batch(slg_index_t *ix, const slg_query_t *queries, uint32_t n
   slg_batch_t *bt = nullptr;
   int32_t rc = slg_batch_prepare(ix, queries, n_queries, k, exec, bmw_block_size, &bt);
   if (rc) return rc;
+  bt->want_stats = out_stats != nullptr;
   rc = slg_batch_run(bt, 0);
   if (rc == SLG_OK) rc = slg_batch_fetch(bt, out_hits, out_counts, out_stats);
   if (rc == SLG_OK && ix->segs.size() == 1 && bt->U) {
@@ -1206,6 +1213,22 @@ int32_t slg_rerank(slg_index_t *ix, const float *query_vecs, uint32_t n_queries,
   SLG_CUDA(ix, cudaMemcpyAsync(out_hits, d_o.p, nh * sizeof(HitDev), cudaMemcpyDeviceToHost, st));
   if (out_vector_scores) SLG_CUDA(ix, cudaMemcpyAsync(out_vector_scores, d_vs.p, nh * 4, cudaMemcpyDeviceToHost, st));
   SLG_CUDA(ix, cudaStreamSynchronize(st));
+  return SLG_OK;
+}
+
+int32_t slg_selftest_div(slg_index_t *ix, uint64_t n, uint64_t seed, uint64_t *mismatches) {
+  if (!ix || !mismatches) return SLG_ERR_INVALID;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  DevBuf d;
+  SLG_CUDA(ix, d.alloc(8));
+  SLG_CUDA(ix, cudaMemsetAsync(d.p, 0, 8, ix->stream));
+  slg_selftest_div_kernel<<<ix->n_sm * 8, 256, 0, ix->stream>>>(n, seed, d.as<unsigned long long>());
+  count_launch(ix);
+  SLG_CUDA(ix, cudaGetLastError());
+  unsigned long long v = 0;
+  SLG_CUDA(ix, cudaMemcpyAsync(&v, d.p, 8, cudaMemcpyDeviceToHost, ix->stream));
+  SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));
+  *mismatches = v;
   return SLG_OK;
 }
 

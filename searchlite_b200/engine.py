@@ -77,7 +77,7 @@ EXPORTED_SYMBOLS = [
     "slg_add_i64_column", "slg_add_f64_column", "slg_add_str_column", "slg_segment_stats", "slg_filter_compile",
     "slg_filter_bitmap", "slg_search_batch", "slg_batch_prepare", "slg_batch_run", "slg_batch_fetch",
     "slg_batch_device_results", "slg_batch_free", "slg_merge_gathered", "slg_load_vectors", "slg_rerank",
-    "slg_get_counters", "slg_version", "slg_batch_copy_results_device", "slg_get_stream",
+    "slg_get_counters", "slg_version", "slg_batch_copy_results_device", "slg_get_stream", "slg_selftest_div", "slg_batch_enable_stats",
 ]
 
 
@@ -120,6 +120,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_get_counters": [vp, C.POINTER(Counters)],
         "slg_batch_copy_results_device": [vp, vp, vp],
         "slg_get_stream": [vp, C.POINTER(vp)],
+        "slg_selftest_div": [vp, u64, u64, C.POINTER(u64)],
+        "slg_batch_enable_stats": [vp, i32],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -272,6 +274,9 @@ class PreparedBatch:
     def __init__(self, index: "GpuIndex", handle: int, n_queries: int, k: int, keepalive):
         self.index, self.handle, self.n_queries, self.k = index, handle, n_queries, k
         self._keepalive = keepalive
+
+    def enable_stats(self, on: bool = True) -> None:
+        self.index._check(self.index.lib.slg_batch_enable_stats(self.handle, 1 if on else 0))
 
     def run(self, sync: bool = True) -> None:
         self.index._check(self.index.lib.slg_batch_run(self.handle, 1 if sync else 0))
@@ -460,6 +465,11 @@ class GpuIndex:
         self._check(self.lib.slg_rerank(self.handle, _ptr(query_vecs), nq, query_vecs.shape[1], _ptr(cands), _ptr(cand_counts),
                                         stride, alpha, METRIC[metric], _ptr(out), _ptr(vs)))
         return out, vs
+
+    def selftest_div(self, n: int, seed: int = 1) -> int:
+        m = C.c_uint64()
+        self._check(self.lib.slg_selftest_div(self.handle, n, seed, C.byref(m)))
+        return m.value
 
     def stream_ptr(self) -> int:
         s = C.c_void_p()

@@ -49,3 +49,9 @@ def test_pruned_modes_are_exact(small, execution):
     assert_parity(wand_h, wand_c, got_h, got_c, strict=False)   # reference default strategy, 1e-5 rule
     assert stats["blocks_skipped"].sum() > 0
     gi.close()
+
+
+def test_division_sequence_is_ieee_exact():
+    gi = GpuIndex(0)
+    assert gi.selftest_div(200_000_000, seed=3) == 0
+    gi.close()
