@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--execution", default="bm25", choices=["bm25", "wand", "bmw"])
     ap.add_argument("--tile-docs", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--sub-docs", type=int, default=0)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "cta", "warp"])
     ap.add_argument("--cpu-sample", type=int, default=256, help="queries in the CPU baseline sample (0 = skip)")
     ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")
@@ -215,7 +217,7 @@ def main():
     torch.cuda.synchronize()
     gen_s = time.time() - t0
     t0 = time.time()
-    gi = GpuIndex(local_rank, tile_docs=args.tile_docs, ctas_per_sm=args.ctas_per_sm)
+    gi = GpuIndex(local_rank, tile_docs=args.tile_docs, ctas_per_sm=args.ctas_per_sm, sub_docs=args.sub_docs, kernel=args.kernel)
     gi.load_segment(seg)
     load_s = time.time() - t0
     n_postings = gi.segment_stats(rank)["n_postings"]
@@ -316,7 +318,8 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, world), "execution": args.execution,
                    "l2": "inputs larger than L2 (resident postings >> 126 MB); no explicit flush",
-                   "postings_resident_this_rank": int(n_postings), "tile_docs": args.tile_docs or 16384},
+                   "postings_resident_this_rank": int(n_postings), "kernel": args.kernel,
+                   "tile_docs": args.tile_docs or 16384, "sub_docs": args.sub_docs or 2048},
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -148,8 +148,12 @@ int32_t slg_open(int32_t device, slg_index_t **out);
 int32_t slg_close(slg_index_t *);
 /* text of the last error on this handle (or of the last failed slg_open when NULL) */
 const char *slg_last_error(const slg_index_t *);
-/* tuning knobs; 0 keeps the default.  tile_docs: docs per shared-memory tile (multiple of 1024). */
-int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm);
+/* tuning knobs; 0 keeps the default.  tile_docs: docs per shared-memory tile of the CTA-per-item
+ * kernel (multiple of 1024); sub_docs: docs per warp-private tile of the warp-per-item kernel
+ * (multiple of 128); kernel_choice: 0 = automatic (warp kernel when k <= 32 and every query has
+ * <= 8 terms), 1 = CTA kernel, 2 = warp kernel. */
+int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, uint32_t sub_docs,
+                      uint32_t kernel_choice);
 
 /* ---- residency (SegmentReader::open) ---- */
 int32_t slg_load_segment(slg_index_t *, const slg_segment_view_t *view, float k1, float b);

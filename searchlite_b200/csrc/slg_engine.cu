@@ -24,6 +24,7 @@
 #include "slg_kernels.cuh"
 #include "slg_postimage.cuh"
 #include "slg_rerank.cuh"
+#include "slg_warp_kernel.cuh"
 
 using namespace slg;
 
@@ -120,6 +121,8 @@ struct slg_index {
   slg_counters_t ctr{};
   uint32_t tile_docs = 16384;
   uint32_t ctas_per_sm = 0;  // 0 = as many as shared memory allows
+  uint32_t sub_docs = 2048;  // warp kernel: docs per warp-private accumulator
+  uint32_t kernel_choice = 0;  // 0 auto, 1 CTA-per-item kernel, 2 warp-per-item kernel
   Segment *find(uint32_t ord) {
     for (auto &s : segs)
       if (s->ord == ord) return s.get();
@@ -142,6 +145,9 @@ struct slg_batch {
   std::vector<uint32_t> h_ut_term, h_qt_uterm, h_q_term_off;
   // state + outputs
   DevBuf ut_rng, ut_tile_ub, thr_key, topk_count, lock, topk_keys, work_counter, stats;
+  DevBuf qterms, qheads;  // warp kernel
+  uint32_t max_terms = 0;
+  bool use_warp = false;
   DevBuf seg_hits, seg_counts;  // [S][Q][k], [S][Q]
   DevBuf out_hits, out_counts;  // merged (aliases seg buffers when S == 1)
   uint32_t n_segs_run = 0;
@@ -393,6 +399,30 @@ int32_t launch_score(slg_index *ix, bool matcher, bool prune, bool stats, const 
   }
 }
 
+template <bool M, bool P, bool S>
+int32_t launch_warp_t(slg_index *ix, const SegmentDev &sd, const WarpBatchDev &wb, size_t smem, int grid) {
+  auto kern = slg_score_warp_kernel<M, P, S>;
+  SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kThreads, smem, ix->stream>>>(sd, wb);
+  SLG_CUDA(ix, cudaGetLastError());
+  return SLG_OK;
+}
+
+int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, const SegmentDev &sd, const WarpBatchDev &wb,
+                    size_t smem, int grid) {
+  int sel = (matcher ? 4 : 0) | (prune ? 2 : 0) | (stats ? 1 : 0);
+  switch (sel) {
+    case 0: return launch_warp_t<false, false, false>(ix, sd, wb, smem, grid);
+    case 1: return launch_warp_t<false, false, true>(ix, sd, wb, smem, grid);
+    case 2: return launch_warp_t<false, true, false>(ix, sd, wb, smem, grid);
+    case 3: return launch_warp_t<false, true, true>(ix, sd, wb, smem, grid);
+    case 4: return launch_warp_t<true, false, false>(ix, sd, wb, smem, grid);
+    case 5: return launch_warp_t<true, false, true>(ix, sd, wb, smem, grid);
+    case 6: return launch_warp_t<true, true, false>(ix, sd, wb, smem, grid);
+    default: return launch_warp_t<true, true, true>(ix, sd, wb, smem, grid);
+  }
+}
+
 }  // namespace
 
 /* ================================================================================================ C ABI */
@@ -446,8 +476,14 @@ int32_t slg_close(slg_index_t *ix) {
   return SLG_OK;
 }
 
-int32_t slg_configure(slg_index_t *ix, uint32_t tile_docs, uint32_t ctas_per_sm) {
+int32_t slg_configure(slg_index_t *ix, uint32_t tile_docs, uint32_t ctas_per_sm, uint32_t sub_docs, uint32_t kernel_choice) {
   if (!ix) return SLG_ERR_INVALID;
+  if (sub_docs) {
+    if (sub_docs % 128 || sub_docs > 8192) return fail(ix, SLG_ERR_INVALID, "sub_docs must be a multiple of 128 <= 8192");
+    ix->sub_docs = sub_docs;
+  }
+  if (kernel_choice > 2) return fail(ix, SLG_ERR_INVALID, "kernel_choice must be 0, 1 or 2");
+  ix->kernel_choice = kernel_choice;
   if (tile_docs) {
     if (tile_docs % 1024 || tile_docs > 49152) return fail(ix, SLG_ERR_INVALID, "tile_docs must be a multiple of 1024 <= 49152");
     ix->tile_docs = tile_docs;
@@ -825,6 +861,7 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
     }
     if (kept > SLG_MAX_QUERY_TERMS) return fail(ix, SLG_ERR_UNSUPPORTED, "query %u has %u terms; the maximum is %u", qi, kept, SLG_MAX_QUERY_TERMS);
     q_off[qi + 1] = q_off[qi] + kept;
+    bt->max_terms = std::max(bt->max_terms, kept);
     if (need_mask) {
       matcher = true;
       if (q.n_groups == 0) {  // non-scored terms without groups: plain OR over group 0
@@ -889,9 +926,17 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   SLG_CUDA(ix, cudaMemcpyAsync(bt->d_pack.p, hp, pos, cudaMemcpyHostToDevice, ix->stream));
   ix->ctr.last_h2d_bytes = pos;
 
+  bt->use_warp = ix->kernel_choice == 2 || (ix->kernel_choice == 0 && k <= kWarpMaxK && bt->max_terms <= kWarpMaxTerms);
+  if (bt->use_warp && (k > kWarpMaxK || bt->max_terms > kWarpMaxTerms))
+    return fail(ix, SLG_ERR_UNSUPPORTED, "the warp kernel handles k <= %u and <= %u terms per query", kWarpMaxK, kWarpMaxTerms);
+  const uint32_t plan_docs = bt->use_warp ? ix->sub_docs : ix->tile_docs;
   uint32_t max_tiles = 0;
-  for (auto &s : ix->segs) max_tiles = std::max(max_tiles, (s->doc_count + ix->tile_docs - 1) / ix->tile_docs);
+  for (auto &s : ix->segs) max_tiles = std::max(max_tiles, (s->doc_count + plan_docs - 1) / plan_docs);
   max_tiles = std::max(max_tiles, 1u);
+  if (bt->use_warp) {
+    SLG_CUDA(ix, bt->qterms.alloc((size_t)n_queries * kWarpMaxTerms * sizeof(QTerm)));
+    SLG_CUDA(ix, bt->qheads.alloc((size_t)n_queries * sizeof(QHead)));
+  }
   size_t S = ix->segs.size();
   SLG_CUDA(ix, bt->ut_rng.alloc((size_t)std::max(bt->U, 1u) * (max_tiles + 1) * 4));
   if (exec != SLG_EXEC_BM25) SLG_CUDA(ix, bt->ut_tile_ub.alloc((size_t)std::max(bt->U, 1u) * max_tiles * 4));
@@ -953,8 +998,9 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
     bd.n_uterms = bt->U;
     bd.k = k;
     bd.cap = bt->cap;
-    bd.tile_docs = ix->tile_docs;
-    bd.n_tiles = std::max(1u, (s->doc_count + ix->tile_docs - 1) / ix->tile_docs);
+    const uint32_t plan_docs = bt->use_warp ? ix->sub_docs : ix->tile_docs;
+    bd.tile_docs = plan_docs;
+    bd.n_tiles = std::max(1u, (s->doc_count + plan_docs - 1) / plan_docs);
     bd.thr_key = bt->thr_key.as<unsigned long long>();
     bd.topk_count = bt->topk_count.as<uint32_t>();
     bd.lock = bt->lock.as<uint32_t>();
@@ -979,9 +1025,41 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         slg_plan_bounds_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(s->dev, bd);
         count_launch(ix);
       }
+      if (bt->use_warp) {
+        slg_build_qterms_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, bd, bt->qterms.as<QTerm>(), bt->qheads.as<QHead>());
+        count_launch(ix);
+      }
       SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));
-      int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * per_sm, (uint64_t)bd.n_tiles * Q);
-      rc = launch_score(ix, bt->matcher, prune, bt->want_stats, s->dev, bd, smem, grid);
+      if (bt->use_warp) {
+        WarpBatchDev wb{};
+        wb.qterms = bt->qterms.as<QTerm>();
+        wb.qheads = bt->qheads.as<QHead>();
+        wb.rng = bd.ut_rng;
+        wb.sub_ub = bd.ut_tile_ub;
+        wb.filter_bits = bd.filter_bits;
+        wb.n_queries = Q;
+        wb.k = k;
+        wb.sub_docs = ix->sub_docs;
+        wb.n_sub = bd.n_tiles;
+        wb.n_groups = (bd.n_tiles + kSubPerGroup - 1) / kSubPerGroup;
+        wb.thr_key = bd.thr_key;
+        wb.topk_count = bd.topk_count;
+        wb.lock = bd.lock;
+        wb.topk_keys = bd.topk_keys;
+        wb.work_counter = bd.work_counter;
+        wb.stats = bd.stats;
+        const int warps = kThreads / 32;
+        size_t wsmem = (size_t)warps * ((size_t)ix->sub_docs * 4 + kWarpCand * 8 + (bt->matcher ? ix->sub_docs : 0));
+        if (wsmem + 1024 > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "sub_docs %u needs %zu B shared memory", ix->sub_docs, wsmem);
+        uint32_t wper = (uint32_t)std::max<size_t>(1, (ix->smem_optin + 1024) / (wsmem + 1024));
+        wper = std::min(wper, 8u);
+        if (ix->ctas_per_sm) wper = std::min(wper, ix->ctas_per_sm);
+        int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * wper, ((uint64_t)wb.n_groups * Q + warps - 1) / warps);
+        rc = launch_warp(ix, bt->matcher, prune, bt->want_stats, s->dev, wb, wsmem, grid);
+      } else {
+        int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * per_sm, (uint64_t)bd.n_tiles * Q);
+        rc = launch_score(ix, bt->matcher, prune, bt->want_stats, s->dev, bd, smem, grid);
+      }
       if (rc) return rc;
       count_launch(ix);
       ix->ctr.score_launches++;

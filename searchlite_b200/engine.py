@@ -99,7 +99,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     sigs = {
         "slg_open": [i32, C.POINTER(vp)],
         "slg_close": [vp],
-        "slg_configure": [vp, u32, u32],
+        "slg_configure": [vp, u32, u32, u32, u32],
         "slg_load_segment": [vp, C.POINTER(SegmentView), f32, f32],
         "slg_load_segment_post_image": [vp, C.POINTER(SegmentView), vp, u64, vp, f32, f32],
         "slg_add_i64_column": [vp, u32, vp, vp],
@@ -312,7 +312,9 @@ class GpuIndex:
     """Device-resident index: the GPU stand-in for Index::reader() + IndexReader::search on the
     BM25 top-k path.  One instance owns one CUDA device/stream."""
 
-    def __init__(self, device: int = 0, tile_docs: int = 0, ctas_per_sm: int = 0):
+    KERNEL = {"auto": 0, "cta": 1, "warp": 2}
+
+    def __init__(self, device: int = 0, tile_docs: int = 0, ctas_per_sm: int = 0, sub_docs: int = 0, kernel: str = "auto"):
         self.lib = load_library()
         h = C.c_void_p()
         rc = self.lib.slg_open(device, C.byref(h))
@@ -321,8 +323,8 @@ class GpuIndex:
         self.handle = h
         self.device = device
         self._keep = []
-        if tile_docs or ctas_per_sm:
-            self._check(self.lib.slg_configure(self.handle, tile_docs, ctas_per_sm))
+        if tile_docs or ctas_per_sm or sub_docs or kernel != "auto":
+            self._check(self.lib.slg_configure(self.handle, tile_docs, ctas_per_sm, sub_docs, self.KERNEL[kernel]))
 
     def _check(self, rc: int) -> int:
         if rc < 0:

@@ -21,13 +21,15 @@ def small():
     return seg, qb
 
 
-@pytest.mark.parametrize("tile_docs", [1024, 16384])
-@pytest.mark.parametrize("k", [11, 101])
-def test_bm25_bit_exact_vs_oracle(small, tile_docs, k):
+@pytest.mark.parametrize("kernel,tile_docs,sub_docs,k", [
+    ("cta", 1024, 0, 11), ("cta", 16384, 0, 11), ("cta", 1024, 0, 101), ("cta", 16384, 0, 101),
+    ("warp", 0, 128, 11), ("warp", 0, 2048, 11), ("warp", 0, 1024, 1), ("warp", 0, 2048, 32),
+])
+def test_bm25_bit_exact_vs_oracle(small, kernel, tile_docs, sub_docs, k):
     seg, qb = small
     ora = _oracle(seg)
     ref_h, ref_c = ora.search_batch(qb, k, "bm25")
-    gi = GpuIndex(0, tile_docs=tile_docs)
+    gi = GpuIndex(0, tile_docs=tile_docs, sub_docs=sub_docs, kernel=kernel)
     gi.load_segment(seg)
     st = gi.segment_stats(0)
     assert st["avgdl"] == ora.avgdl and st["live_docs"] == ora.live_docs and st["min_doc_len"] == ora.min_doc_len
@@ -36,13 +38,14 @@ def test_bm25_bit_exact_vs_oracle(small, tile_docs, k):
     gi.close()
 
 
+@pytest.mark.parametrize("kernel", ["cta", "warp"])
 @pytest.mark.parametrize("execution", ["wand", "bmw"])
-def test_pruned_modes_are_exact(small, execution):
+def test_pruned_modes_are_exact(small, execution, kernel):
     seg, qb = small
     ora = _oracle(seg)
     ref_h, ref_c = ora.search_batch(qb, 11, "bm25")
     wand_h, wand_c = ora.search_batch(qb, 11, "wand")
-    gi = GpuIndex(0, tile_docs=2048)
+    gi = GpuIndex(0, tile_docs=2048, sub_docs=256, kernel=kernel)
     gi.load_segment(seg)
     got_h, got_c, stats = gi.search_batch(qb, 11, execution, want_stats=True)
     assert_parity(ref_h, ref_c, got_h, got_c, strict=True)      # same arithmetic order as bm25
