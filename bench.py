@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--tile-docs", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--sub-docs", type=int, default=0)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "cta", "warp"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "cta", "warp", "warp-inplace", "auto-inplace"])
     ap.add_argument("--cpu-sample", type=int, default=256, help="queries in the CPU baseline sample (0 = skip)")
     ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")

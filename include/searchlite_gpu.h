@@ -151,7 +151,8 @@ const char *slg_last_error(const slg_index_t *);
 /* tuning knobs; 0 keeps the default.  tile_docs: docs per shared-memory tile of the CTA-per-item
  * kernel (multiple of 1024); sub_docs: docs per warp-private tile of the warp-per-item kernel
  * (multiple of 128); kernel_choice: 0 = automatic (warp kernel when k <= 32 and every query has
- * <= 8 terms), 1 = CTA kernel, 2 = warp kernel. */
+ * <= 8 terms), 1 = CTA kernel, 2 = warp kernel; add 256 to disable the per-batch score staging
+ * (decode + score every unique term of the batch once) and score postings in place. */
 int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, uint32_t sub_docs,
                       uint32_t kernel_choice);
 

@@ -123,6 +123,7 @@ struct slg_index {
   uint32_t ctas_per_sm = 0;  // 0 = as many as shared memory allows
   uint32_t sub_docs = 2048;  // warp kernel: docs per warp-private accumulator
   uint32_t kernel_choice = 0;  // 0 auto, 1 CTA-per-item kernel, 2 warp-per-item kernel
+  bool staging = true;         // decode + score unique terms once per batch (warp kernel, bm25)
   Segment *find(uint32_t ord) {
     for (auto &s : segs)
       if (s->ord == ord) return s.get();
@@ -146,6 +147,10 @@ struct slg_batch {
   // state + outputs
   DevBuf ut_rng, ut_tile_ub, thr_key, topk_count, lock, topk_keys, work_counter, stats;
   DevBuf qterms, qheads;  // warp kernel
+  DevBuf scores, d_sc_off, d_ublk;  // staged scores: [S][U] offsets / first blocks
+  std::vector<std::vector<uint64_t>> h_sc_off;  // per segment
+  std::vector<std::vector<uint32_t>> h_ublk;    // per segment, U+1 entries
+  bool staged = false;
   uint32_t max_terms = 0;
   bool use_warp = false;
   DevBuf seg_hits, seg_counts;  // [S][Q][k], [S][Q]
@@ -399,27 +404,35 @@ int32_t launch_score(slg_index *ix, bool matcher, bool prune, bool stats, const 
   }
 }
 
-template <bool M, bool P, bool S>
+template <bool M, bool P, bool S, bool G>
 int32_t launch_warp_t(slg_index *ix, const SegmentDev &sd, const WarpBatchDev &wb, size_t smem, int grid) {
-  auto kern = slg_score_warp_kernel<M, P, S>;
+  auto kern = slg_score_warp_kernel<M, P, S, G>;
   SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kThreads, smem, ix->stream>>>(sd, wb);
   SLG_CUDA(ix, cudaGetLastError());
   return SLG_OK;
 }
 
-int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, const SegmentDev &sd, const WarpBatchDev &wb,
-                    size_t smem, int grid) {
+int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, bool staged, const SegmentDev &sd,
+                    const WarpBatchDev &wb, size_t smem, int grid) {
   int sel = (matcher ? 4 : 0) | (prune ? 2 : 0) | (stats ? 1 : 0);
+  if (staged && !matcher) {
+    switch (sel) {
+      case 0: return launch_warp_t<false, false, false, true>(ix, sd, wb, smem, grid);
+      case 1: return launch_warp_t<false, false, true, true>(ix, sd, wb, smem, grid);
+      case 2: return launch_warp_t<false, true, false, true>(ix, sd, wb, smem, grid);
+      default: return launch_warp_t<false, true, true, true>(ix, sd, wb, smem, grid);
+    }
+  }
   switch (sel) {
-    case 0: return launch_warp_t<false, false, false>(ix, sd, wb, smem, grid);
-    case 1: return launch_warp_t<false, false, true>(ix, sd, wb, smem, grid);
-    case 2: return launch_warp_t<false, true, false>(ix, sd, wb, smem, grid);
-    case 3: return launch_warp_t<false, true, true>(ix, sd, wb, smem, grid);
-    case 4: return launch_warp_t<true, false, false>(ix, sd, wb, smem, grid);
-    case 5: return launch_warp_t<true, false, true>(ix, sd, wb, smem, grid);
-    case 6: return launch_warp_t<true, true, false>(ix, sd, wb, smem, grid);
-    default: return launch_warp_t<true, true, true>(ix, sd, wb, smem, grid);
+    case 0: return launch_warp_t<false, false, false, false>(ix, sd, wb, smem, grid);
+    case 1: return launch_warp_t<false, false, true, false>(ix, sd, wb, smem, grid);
+    case 2: return launch_warp_t<false, true, false, false>(ix, sd, wb, smem, grid);
+    case 3: return launch_warp_t<false, true, true, false>(ix, sd, wb, smem, grid);
+    case 4: return launch_warp_t<true, false, false, false>(ix, sd, wb, smem, grid);
+    case 5: return launch_warp_t<true, false, true, false>(ix, sd, wb, smem, grid);
+    case 6: return launch_warp_t<true, true, false, false>(ix, sd, wb, smem, grid);
+    default: return launch_warp_t<true, true, true, false>(ix, sd, wb, smem, grid);
   }
 }
 
@@ -482,8 +495,9 @@ int32_t slg_configure(slg_index_t *ix, uint32_t tile_docs, uint32_t ctas_per_sm,
     if (sub_docs % 128 || sub_docs > 8192) return fail(ix, SLG_ERR_INVALID, "sub_docs must be a multiple of 128 <= 8192");
     ix->sub_docs = sub_docs;
   }
-  if (kernel_choice > 2) return fail(ix, SLG_ERR_INVALID, "kernel_choice must be 0, 1 or 2");
-  ix->kernel_choice = kernel_choice;
+  if ((kernel_choice & 0xFF) > 2) return fail(ix, SLG_ERR_INVALID, "kernel_choice must be 0, 1 or 2 (+256 = no staging)");
+  ix->kernel_choice = kernel_choice & 0xFF;
+  ix->staging = !(kernel_choice & 256u);
   if (tile_docs) {
     if (tile_docs % 1024 || tile_docs > 49152) return fail(ix, SLG_ERR_INVALID, "tile_docs must be a multiple of 1024 <= 49152");
     ix->tile_docs = tile_docs;
@@ -936,6 +950,42 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   if (bt->use_warp) {
     SLG_CUDA(ix, bt->qterms.alloc((size_t)n_queries * kWarpMaxTerms * sizeof(QTerm)));
     SLG_CUDA(ix, bt->qheads.alloc((size_t)n_queries * sizeof(QHead)));
+    // staged scores: exhaustive mode without a matcher decodes + scores each unique term once per batch
+    bt->staged = ix->staging && !matcher && exec == SLG_EXEC_BM25 && bt->U > 0;
+    if (bt->staged) {
+      uint64_t max_slots = 0;
+      size_t nseg = ix->segs.size();
+      bt->h_sc_off.resize(nseg);
+      bt->h_ublk.resize(nseg);
+      std::vector<uint64_t> all_off;
+      std::vector<uint32_t> all_blk;
+      for (size_t si = 0; si < nseg; si++) {
+        const Segment *sg = ix->segs[si].get();
+        auto &off = bt->h_sc_off[si];
+        auto &blk = bt->h_ublk[si];
+        off.resize(bt->U);
+        blk.resize(bt->U + 1);
+        uint64_t pos = 0, nb = 0;
+        for (uint32_t u = 0; u < bt->U; u++) {
+          uint32_t df = ut[u] < sg->n_terms ? sg->h_df[ut[u]] : 0;
+          off[u] = pos;
+          blk[u] = (uint32_t)nb;
+          pos += align_up(df, kTermAlign);
+          nb += (df + kStageChunk - 1) / kStageChunk;
+        }
+        blk[bt->U] = (uint32_t)nb;
+        max_slots = std::max(max_slots, pos + 1024);
+        all_off.insert(all_off.end(), off.begin(), off.end());
+        all_blk.insert(all_blk.end(), blk.begin(), blk.end());
+      }
+      SLG_CUDA(ix, bt->scores.alloc(max_slots * 4));
+      SLG_CUDA(ix, bt->d_sc_off.alloc(all_off.size() * 8));
+      SLG_CUDA(ix, bt->d_ublk.alloc(all_blk.size() * 4));
+      SLG_CUDA(ix, cudaMemcpyAsync(bt->d_sc_off.p, all_off.data(), all_off.size() * 8, cudaMemcpyHostToDevice, ix->stream));
+      SLG_CUDA(ix, cudaMemcpyAsync(bt->d_ublk.p, all_blk.data(), all_blk.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+      SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));
+      ix->ctr.last_h2d_bytes += all_off.size() * 8 + all_blk.size() * 4;
+    }
   }
   size_t S = ix->segs.size();
   SLG_CUDA(ix, bt->ut_rng.alloc((size_t)std::max(bt->U, 1u) * (max_tiles + 1) * 4));
@@ -1025,8 +1075,18 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         slg_plan_bounds_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(s->dev, bd);
         count_launch(ix);
       }
+      const uint64_t *d_sc_off = nullptr;
       if (bt->use_warp) {
-        slg_build_qterms_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, bd, bt->qterms.as<QTerm>(), bt->qheads.as<QHead>());
+        if (bt->staged) {
+          d_sc_off = bt->d_sc_off.as<uint64_t>() + (size_t)si * bt->U;
+          const uint32_t *d_ublk = bt->d_ublk.as<uint32_t>() + (size_t)si * (bt->U + 1);
+          const uint32_t nblk = bt->h_ublk[si][bt->U];
+          if (nblk) {
+            slg_stage_scores_kernel<<<nblk, 256, 0, st>>>(s->dev, bd.ut_term, d_ublk, d_sc_off, bt->U, bt->scores.as<float>());
+            count_launch(ix);
+          }
+        }
+        slg_build_qterms_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, bd, d_sc_off, bt->qterms.as<QTerm>(), bt->qheads.as<QHead>());
         count_launch(ix);
       }
       SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));
@@ -1036,6 +1096,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         wb.qheads = bt->qheads.as<QHead>();
         wb.rng = bd.ut_rng;
         wb.sub_ub = bd.ut_tile_ub;
+        wb.scores = bt->scores.as<float>();
         wb.filter_bits = bd.filter_bits;
         wb.n_queries = Q;
         wb.k = k;
@@ -1049,13 +1110,13 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         wb.work_counter = bd.work_counter;
         wb.stats = bd.stats;
         const int warps = kThreads / 32;
-        size_t wsmem = (size_t)warps * ((size_t)ix->sub_docs * 4 + kWarpCand * 8 + (bt->matcher ? ix->sub_docs : 0));
+        size_t wsmem = (size_t)warps * warp_kernel_smem_per_warp(ix->sub_docs, bt->matcher, prune);
         if (wsmem + 1024 > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "sub_docs %u needs %zu B shared memory", ix->sub_docs, wsmem);
         uint32_t wper = (uint32_t)std::max<size_t>(1, (ix->smem_optin + 1024) / (wsmem + 1024));
         wper = std::min(wper, 8u);
         if (ix->ctas_per_sm) wper = std::min(wper, ix->ctas_per_sm);
         int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * wper, ((uint64_t)wb.n_groups * Q + warps - 1) / warps);
-        rc = launch_warp(ix, bt->matcher, prune, bt->want_stats, s->dev, wb, wsmem, grid);
+        rc = launch_warp(ix, bt->matcher, prune, bt->want_stats, bt->staged, s->dev, wb, wsmem, grid);
       } else {
         int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * per_sm, (uint64_t)bd.n_tiles * Q);
         rc = launch_score(ix, bt->matcher, prune, bt->want_stats, s->dev, bd, smem, grid);

@@ -13,6 +13,15 @@
 //                 is ever dropped unsorted)
 //   merge       = as in the CTA kernel: per-query lock, sort(local ∪ global)[:k], publish the new
 //                 k-th key as the query's threshold
+//
+// Decode + score is split from accumulation (STAGED): a batch of 4096 Zipfian queries names the
+// same head terms over and over (sum of df over term INSTANCES is ~17x the sum over UNIQUE
+// terms), so slg_stage_scores_kernel decodes every posting of every unique term of the batch
+// once — tf byte (or wide tf), norm gather, the reference's BM25 arithmetic — into a per-batch
+// f32 stream laid out like the posting array, and the accumulate loop of each (query, tile)
+// then only streams (doc, score) pairs out of L2 and adds them.  The per-query weight is applied
+// at accumulate time (score_tf: base * weight, query/wand.rs:284-285), so results are bit-identical
+// to computing the contribution in place.
 #pragma once
 #include "slg_kernels.cuh"
 
@@ -25,9 +34,9 @@ constexpr uint32_t kWarpCand = 64;
 
 struct __align__(16) QTerm {  // one query term resolved against one segment (32 B)
   uint64_t base;      // term_start: first padded posting index
-  uint64_t wide;      // offset into tf_wide or ~0ull
+  uint64_t sc_base;   // first slot of the term in the staged score stream
+  uint32_t term;      // term id in the segment
   uint32_t uterm;     // row of the range / bound tables
-  float idf;
   float weight;
   uint32_t flags;     // bit0 scored, bit1 valid, bits 8..15 group
 };
@@ -44,6 +53,7 @@ struct WarpBatchDev {
   const QHead *qheads;   // [Q]
   const uint32_t *rng;   // [U][n_sub+1]
   const float *sub_ub;   // [U][n_sub]   (PRUNE)
+  const float *scores;   // staged unit-weight contributions (STAGED)
   const uint32_t *const *filter_bits;
   uint32_t n_queries, k, sub_docs, n_sub, n_groups;
   unsigned long long *thr_key;
@@ -53,8 +63,57 @@ struct WarpBatchDev {
   unsigned long long *stats;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Stage: decode + score every posting of every unique term of the batch, once.
+// One CTA of 256 threads per chunk of kStageChunk postings of one unique term (8 postings per
+// thread: two 128-bit doc loads, one 64-bit tf load, eight norm gathers in flight, two 128-bit
+// score stores); uchunk[u] = first chunk of unique term u.
+constexpr uint32_t kStageChunk = 2048;
+__global__ void __launch_bounds__(256) slg_stage_scores_kernel(SegmentDev seg, const uint32_t *ut_term, const uint32_t *uchunk,
+                                                                const uint64_t *sc_off, uint32_t n_uterms, float *scores) {
+  const uint32_t chunk = blockIdx.x;
+  __shared__ uint32_t s_u;
+  if (threadIdx.x == 0) {
+    uint32_t lo = 0, hi = n_uterms;  // last u with uchunk[u] <= chunk
+    while (lo + 1 < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (uchunk[mid] <= chunk) lo = mid;
+      else hi = mid;
+    }
+    s_u = lo;
+  }
+  __syncthreads();
+  const uint32_t u = s_u;
+  const uint32_t term = ut_term[u];
+  const uint32_t df = seg.term_df[term];
+  const uint64_t base = seg.term_start[term];
+  const uint64_t wide = seg.term_wide[term];
+  const float idf = seg.term_idf[term], k1p1 = seg.k1p1;
+  const uint32_t *dptr = seg.post_doc + base;
+  const uint8_t *fptr = seg.post_tf + base;
+  float *out = scores + sc_off[u];
+  const uint32_t i = (chunk - uchunk[u]) * kStageChunk + threadIdx.x * 8;
+  if (i >= df) return;
+  // the padded layout (16-posting alignment + tail slack) makes the full 8-wide loads safe
+  const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(dptr + i));
+  const uint4 d1 = __ldg(reinterpret_cast<const uint4 *>(dptr + i + 4));
+  const uint2 f = __ldg(reinterpret_cast<const uint2 *>(fptr + i));
+  const uint32_t dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+  float nkv[8], sc[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) nkv[j] = (i + j < df) ? __ldg(seg.nk + dd[j]) : 1.0f;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    uint32_t tf = ((j < 4 ? f.x : f.y) >> (8 * (j & 3))) & 255u;
+    if (tf == 255u && wide != ~0ull && i + j < df) tf = seg.tf_wide[wide + i + j];
+    sc[j] = bm25_contrib_fast(tf, idf, k1p1, nkv[j], 1.0f);
+  }
+  *reinterpret_cast<float4 *>(out + i) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+  *reinterpret_cast<float4 *>(out + i + 4) = make_float4(sc[4], sc[5], sc[6], sc[7]);
+}
+
 // resolve the batch's query terms against one segment (runs once per segment per batch)
-__global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qterms, QHead *qheads) {
+__global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, const uint64_t *sc_off, QTerm *qterms, QHead *qheads) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= bt.n_queries) return;
   const uint32_t qi = bt.q_order[slot];
@@ -69,23 +128,29 @@ __global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qter
   for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
     QTerm r;
     r.base = 0;
-    r.wide = ~0ull;
+    r.sc_base = 0;
+    r.term = 0;
     r.uterm = 0;
-    r.idf = 0.0f;
     r.weight = 0.0f;
     r.flags = 0;
     if (t < nt) {
       const uint32_t u = bt.qt_uterm[t0 + t];
       const uint32_t term = bt.ut_term[u];
       r.base = seg.term_start[term];
-      r.wide = seg.term_wide[term];
+      r.sc_base = sc_off ? sc_off[u] : 0;
+      r.term = term;
       r.uterm = u;
-      r.idf = seg.term_idf[term];
       r.weight = bt.qt_weight[t0 + t];
       r.flags = (bt.qt_flags[t0 + t] & 1u) | 2u | ((uint32_t)bt.qt_group[t0 + t] << 8);
     }
     qterms[(uint64_t)slot * kWarpMaxTerms + t] = r;
   }
+}
+
+constexpr uint32_t kRbStride = 9;
+__host__ __device__ inline size_t warp_kernel_smem_per_warp(uint32_t sub_docs, bool matcher, bool prune) {
+  return (size_t)sub_docs * 4 + kWarpCand * 8 + kWarpMaxTerms * sizeof(QTerm) + kWarpMaxTerms * kRbStride * 4 +
+         (prune ? kWarpMaxTerms * 8 * 4 : 0) + (matcher ? sub_docs : 0);  // every term is a multiple of 16 B
 }
 
 // 64-key descending bitonic sort in the warp's shared buffer
@@ -107,17 +172,89 @@ __device__ __forceinline__ void warp_sort64_desc(unsigned long long *a, int lane
   }
 }
 
-template <bool MATCHER, bool PRUNE, bool STATS>
+// postings [lo, hi) of one term from the staged (doc, score) streams into the warp's accumulator
+template <bool FIRST, bool UNIT_W>
+__device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ dptr, const float *__restrict__ sptr, uint32_t lo,
+                                                  uint32_t hi, uint32_t tile_lo, float w, float *acc, int lane) {
+  if (hi - lo < 160u) {
+    // short range: one posting per lane per step keeps the lanes busy
+    for (uint32_t i = lo + lane; i < hi; i += 32) {
+      float s = __ldg(sptr + i);
+      if (!UNIT_W) s = __fmul_rn(s, w);
+      float *p = acc + (__ldg(dptr + i) - tile_lo);
+      *p = FIRST ? s : __fadd_rn(*p, s);
+    }
+    return;
+  }
+  const uint32_t a_lo = (lo + 3u) & ~3u, a_hi = hi & ~3u;
+  if (lane < (int)(a_lo - lo)) {
+    float s = __ldg(sptr + lo + lane);
+    if (!UNIT_W) s = __fmul_rn(s, w);
+    float *p = acc + (__ldg(dptr + lo + lane) - tile_lo);
+    *p = FIRST ? s : __fadd_rn(*p, s);
+  }
+  if (lane >= 4 && lane - 4 < (int)(hi - a_hi)) {
+    const uint32_t i = a_hi + (lane - 4);
+    float s = __ldg(sptr + i);
+    if (!UNIT_W) s = __fmul_rn(s, w);
+    float *p = acc + (__ldg(dptr + i) - tile_lo);
+    *p = FIRST ? s : __fadd_rn(*p, s);
+  }
+  uint32_t i = a_lo + lane * 4;
+  if (i >= a_hi) return;
+  uint4 d = __ldg(reinterpret_cast<const uint4 *>(dptr + i));
+  float4 s = __ldg(reinterpret_cast<const float4 *>(sptr + i));
+  for (;;) {
+    const uint32_t inext = i + 128;
+    const bool more = inext < a_hi;
+    uint4 dn = d;
+    float4 sn = s;
+    if (more) {
+      dn = __ldg(reinterpret_cast<const uint4 *>(dptr + inext));
+      sn = __ldg(reinterpret_cast<const float4 *>(sptr + inext));
+    }
+    if (!UNIT_W) {
+      s.x = __fmul_rn(s.x, w);
+      s.y = __fmul_rn(s.y, w);
+      s.z = __fmul_rn(s.z, w);
+      s.w = __fmul_rn(s.w, w);
+    }
+    float *p0 = acc + (d.x - tile_lo), *p1 = acc + (d.y - tile_lo), *p2 = acc + (d.z - tile_lo), *p3 = acc + (d.w - tile_lo);
+    if (FIRST) {
+      *p0 = s.x;
+      *p1 = s.y;
+      *p2 = s.z;
+      *p3 = s.w;
+    } else {
+      const float a0 = *p0, a1 = *p1, a2 = *p2, a3 = *p3;  // distinct docs: no aliasing inside a list
+      *p0 = __fadd_rn(a0, s.x);
+      *p1 = __fadd_rn(a1, s.y);
+      *p2 = __fadd_rn(a2, s.z);
+      *p3 = __fadd_rn(a3, s.w);
+    }
+    if (!more) break;
+    d = dn;
+    s = sn;
+    i = inext;
+  }
+}
+
+template <bool MATCHER, bool PRUNE, bool STATS, bool STAGED>
 __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg, WarpBatchDev wb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarps = kThreads / 32;
   const uint32_t sub_docs = wb.sub_docs;
-  // layout: [kWarps][sub_docs] f32 | [kWarps][64] u64 | [kWarps][sub_docs] u8
-  float *acc = reinterpret_cast<float *>(smem_raw) + (size_t)warp * sub_docs;
-  unsigned long long *cand =
-      reinterpret_cast<unsigned long long *>(smem_raw + (size_t)kWarps * sub_docs * 4) + (size_t)warp * kWarpCand;
-  uint8_t *gmask = smem_raw + (size_t)kWarps * sub_docs * 4 + (size_t)kWarps * kWarpCand * 8 + (size_t)warp * sub_docs;
+  // per-warp layout: acc f32[sub_docs] | cand u64[64] | qt QTerm[8] | rb u32[8][9] | ub f32[8][8] (PRUNE) | gmask u8[sub_docs] (MATCHER)
+  const size_t per_warp = warp_kernel_smem_per_warp(sub_docs, MATCHER, PRUNE);
+  unsigned char *mine = smem_raw + (size_t)warp * per_warp;
+  float *acc = reinterpret_cast<float *>(mine);
+  unsigned long long *cand = reinterpret_cast<unsigned long long *>(mine + (size_t)sub_docs * 4);
+  QTerm *qt = reinterpret_cast<QTerm *>(cand + kWarpCand);
+  uint32_t *rb = reinterpret_cast<uint32_t *>(qt + kWarpMaxTerms);   // [t][9], boundary j at rb[t*9 + j]
+  float *ubs = reinterpret_cast<float *>(rb + kWarpMaxTerms * kRbStride);   // [t][8]
+  uint8_t *gmask = reinterpret_cast<uint8_t *>(ubs + (PRUNE ? kWarpMaxTerms * 8 : 0));
+  (void)kWarps;
 
   const uint32_t k = wb.k;
   const uint32_t total_items = wb.n_groups * wb.n_queries;
@@ -138,119 +275,109 @@ __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg
 
     const uint32_t tg = item / wb.n_queries;
     const uint32_t qslot = item - tg * wb.n_queries;
-    // lanes 0..7: one query-term record each; every lane: the head
     const QHead head = wb.qheads[qslot];
     const uint32_t nt = head.nt;
-    QTerm my;
-    my.base = 0;
-    my.wide = ~0ull;
-    my.uterm = 0;
-    my.idf = 0.0f;
-    my.weight = 0.0f;
-    my.flags = 0;
-    if (lane < (int)kWarpMaxTerms) {
-      const uint4 *src = reinterpret_cast<const uint4 *>(wb.qterms + (uint64_t)qslot * kWarpMaxTerms + lane);
-      const uint4 a = __ldg(src), b = __ldg(src + 1);
-      my.base = (uint64_t)a.x | ((uint64_t)a.y << 32);
-      my.wide = (uint64_t)a.z | ((uint64_t)a.w << 32);
-      my.uterm = b.x;
-      my.idf = __uint_as_float(b.y);
-      my.weight = __uint_as_float(b.z);
-      my.flags = b.w;
+    // stage the query's term records: 8 records x 32 B = 16 lanes x 16 B
+    if (lane < 16) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(wb.qterms + (uint64_t)qslot * kWarpMaxTerms) + lane);
+      reinterpret_cast<uint4 *>(qt)[lane] = v;
     }
     unsigned long long thr = ld_cg_u64(wb.thr_key + head.qi);
+    __syncwarp();
     const uint32_t sub0 = tg * kSubPerGroup;
-    // range boundaries: lane j (0..8) holds boundary sub0+j of term t in rb[t]
-    uint32_t rb[kWarpMaxTerms];
-    float ubv[kWarpMaxTerms];
-#pragma unroll
-    for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
-      const uint32_t u = __shfl_sync(0xFFFFFFFFu, my.uterm, t);
-      rb[t] = 0;
-      ubv[t] = 0.0f;
+    // range boundaries sub0 .. sub0+8 of every term: lane = t*4 + c loads boundaries c, c+4, c+8
+    {
+      const uint32_t t = lane >> 2, c = lane & 3;
       if (t < nt) {
-        const uint32_t b = min(sub0 + (uint32_t)lane, wb.n_sub);
-        if (lane <= (int)kSubPerGroup) rb[t] = __ldg(wb.rng + (uint64_t)u * (wb.n_sub + 1) + b);
-        if (PRUNE && lane < (int)kSubPerGroup && sub0 + lane < wb.n_sub) ubv[t] = __ldg(wb.sub_ub + (uint64_t)u * wb.n_sub + sub0 + lane);
+        const uint32_t *row = wb.rng + (uint64_t)qt[t].uterm * (wb.n_sub + 1);
+        for (uint32_t j = c; j <= kSubPerGroup; j += 4) rb[t * kRbStride + j] = __ldg(row + min(sub0 + j, wb.n_sub));
+        if (PRUNE) {
+          const float *urow = wb.sub_ub + (uint64_t)qt[t].uterm * wb.n_sub;
+          for (uint32_t j = c; j < kSubPerGroup; j += 4) ubs[t * 8 + j] = (sub0 + j < wb.n_sub) ? __ldg(urow + sub0 + j) : 0.0f;
+        }
       }
     }
+    __syncwarp();
 
-    uint32_t cnt = 0;            // pending candidates in cand[]
+    uint32_t cnt = 0;  // pending candidates in cand[]
     uint32_t n_touched = 0, n_post = 0, n_skipped = 0;
     const uint32_t masks = head.masks;
 
+#pragma unroll 1
     for (uint32_t j = 0; j < kSubPerGroup; j++) {
       const uint32_t sub = sub0 + j;
       if (sub >= wb.n_sub) break;
       const uint32_t tile_lo = sub * sub_docs;
       const uint32_t tile_n = min(sub_docs, seg.doc_count - tile_lo);
-      // ranges of every term in this sub-tile
-      uint32_t tot = 0;
-      float ub = 0.0f;
-      uint32_t lo_t[kWarpMaxTerms], hi_t[kWarpMaxTerms];
-#pragma unroll
-      for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
-        lo_t[t] = __shfl_sync(0xFFFFFFFFu, rb[t], j);
-        hi_t[t] = __shfl_sync(0xFFFFFFFFu, rb[t], j + 1);
-        const uint32_t fl = __shfl_sync(0xFFFFFFFFu, my.flags, t);
-        if (t < nt && (fl & 1u)) {
-          tot += hi_t[t] - lo_t[t];
-          if (PRUNE) ub += __shfl_sync(0xFFFFFFFFu, ubv[t], j) * __shfl_sync(0xFFFFFFFFu, my.weight, t);
-        }
+      // total scored postings (and bound) of this sub-tile: lanes 0..nt-1 hold one term each
+      uint32_t mine_n = 0;
+      float mine_ub = 0.0f;
+      if (lane < (int)nt && (qt[lane].flags & 1u)) {
+        mine_n = rb[lane * kRbStride + j + 1] - rb[lane * kRbStride + j];
+        if (PRUNE) mine_ub = ubs[lane * 8 + j] * qt[lane].weight;
       }
-      if (tot == 0) continue;
+      const uint32_t any = __ballot_sync(0xFFFFFFFFu, mine_n != 0u);
+      if (any == 0u) continue;
       if (PRUNE) {
+        float ub = mine_ub;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) ub += __shfl_xor_sync(0xFFFFFFFFu, ub, o);  // terms live in lanes 0..7
+        ub = __shfl_sync(0xFFFFFFFFu, ub, 0);
         const float thr_score = __uint_as_float((uint32_t)(thr >> 32));
         if (thr != kThrInit && ub * 1.00001f < thr_score) {  // see slg_score_tiles_kernel
           n_skipped++;
           continue;
         }
       }
-      if (STATS) n_post += tot;
+      if (STATS) n_post += mine_n;
 
       // ---- accumulate ----
       bool first = true;
-#pragma unroll
-      for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
-        if (t >= nt) break;
-        const uint32_t lo = lo_t[t], hi = hi_t[t];
-        TermCtx tc;
-        const uint64_t base = __shfl_sync(0xFFFFFFFFu, my.base, t);
-        const uint64_t wide = __shfl_sync(0xFFFFFFFFu, my.wide, t);
-        const uint32_t fl = __shfl_sync(0xFFFFFFFFu, my.flags, t);
-        tc.idf = __shfl_sync(0xFFFFFFFFu, my.idf, t);
-        tc.w = __shfl_sync(0xFFFFFFFFu, my.weight, t);
-        if (hi > lo) {
-          tc.dptr = seg.post_doc + base;
-          tc.fptr = seg.post_tf + base;
+#pragma unroll 1
+      for (uint32_t t = 0; t < nt; t++) {
+        const uint32_t lo = rb[t * kRbStride + j], hi = rb[t * kRbStride + j + 1];
+        if (hi <= lo) continue;
+        const QTerm q = qt[t];
+        const bool scored = q.flags & 1u;
+        if (STAGED && !MATCHER) {
+          const uint32_t *dptr = seg.post_doc + q.base;
+          const float *sptr = wb.scores + q.sc_base;
+          if (q.weight == 1.0f) {
+            if (first) accumulate_staged<true, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, acc, lane);
+            else accumulate_staged<false, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, acc, lane);
+          } else {
+            if (first) accumulate_staged<true, false>(dptr, sptr, lo, hi, tile_lo, q.weight, acc, lane);
+            else accumulate_staged<false, false>(dptr, sptr, lo, hi, tile_lo, q.weight, acc, lane);
+          }
+        } else {
+          TermCtx tc;
+          const uint64_t wide = seg.term_wide[q.term];
+          tc.dptr = seg.post_doc + q.base;
+          tc.fptr = seg.post_tf + q.base;
           tc.wptr = wide != ~0ull ? seg.tf_wide + wide : nullptr;
-          tc.scored = fl & 1u;
-          tc.gbit = MATCHER ? (uint8_t)(1u << ((fl >> 8) & 7u)) : 0;
-          if (first && tc.scored && !MATCHER) accumulate_term<MATCHER, true, 32>(seg, tc, lo, hi, tile_lo, acc, gmask, lane);
+          tc.scored = scored;
+          tc.idf = seg.term_idf[q.term];
+          tc.w = q.weight;
+          tc.gbit = MATCHER ? (uint8_t)(1u << ((q.flags >> 8) & 7u)) : 0;
+          if (first && scored && !MATCHER) accumulate_term<MATCHER, true, 32>(seg, tc, lo, hi, tile_lo, acc, gmask, lane);
           else accumulate_term<MATCHER, false, 32>(seg, tc, lo, hi, tile_lo, acc, gmask, lane);
-          if (tc.scored) first = false;
-          __syncwarp();
         }
+        if (scored) first = false;
+        __syncwarp();
       }
 
       // ---- scan + clear; collect keys that beat the threshold ----
       const uint32_t thr_hi = (uint32_t)(thr >> 32);
+#pragma unroll 1
       for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) {
-        const uint32_t i = i0 + lane * 4;
-        uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, gm = 0;
-        if (i < tile_n) {
-          const float4 v = *reinterpret_cast<const float4 *>(acc + i);
-          b0 = __float_as_uint(v.x);
-          b1 = __float_as_uint(v.y);
-          b2 = __float_as_uint(v.z);
-          b3 = __float_as_uint(v.w);
-        }
+        const uint32_t i = i0 + lane * 4;  // (reads past tile_n stay inside the warp's buffer and are zero)
+        const float4 v = *reinterpret_cast<const float4 *>(acc + i);
+        const uint32_t b0 = __float_as_uint(v.x), b1 = __float_as_uint(v.y), b2 = __float_as_uint(v.z), b3 = __float_as_uint(v.w);
         const uint32_t m = max(max(b0, b1), max(b2, b3));
-        if (m != 0u) {
-          *reinterpret_cast<float4 *>(acc + i) = make_float4(0, 0, 0, 0);
-          if (STATS) n_touched += (b0 != 0u) + (b1 != 0u) + (b2 != 0u) + (b3 != 0u);
-        }
-        if (MATCHER && i < tile_n) {
+        uint32_t gm = 0;
+        if (m != 0u) *reinterpret_cast<float4 *>(acc + i) = make_float4(0, 0, 0, 0);
+        if (STATS) n_touched += (b0 != 0u) + (b1 != 0u) + (b2 != 0u) + (b3 != 0u);
+        if (MATCHER) {
           gm = *reinterpret_cast<const uint32_t *>(gmask + i);
           if (gm) *reinterpret_cast<uint32_t *>(gmask + i) = 0u;
         }
@@ -291,26 +418,23 @@ __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg
     }
 
     if (STATS) {
-      for (int o = 16; o > 0; o >>= 1) n_touched += __shfl_xor_sync(0xFFFFFFFFu, n_touched, o);
+      for (int o = 16; o > 0; o >>= 1) {
+        n_touched += __shfl_xor_sync(0xFFFFFFFFu, n_touched, o);
+        n_post += __shfl_xor_sync(0xFFFFFFFFu, n_post, o);
+      }
       if (lane == 0) {
         if (n_touched) atomicAdd(wb.stats + (uint64_t)head.qi * 4 + 0, (unsigned long long)n_touched);
         if (n_post) atomicAdd(wb.stats + (uint64_t)head.qi * 4 + 1, (unsigned long long)n_post);
+        if (n_skipped) atomicAdd(wb.stats + (uint64_t)head.qi * 4 + 2, (unsigned long long)n_skipped);
         if (cnt) atomicAdd(wb.stats + (uint64_t)head.qi * 4 + 3, (unsigned long long)cnt);
       }
     }
-    if (PRUNE && STATS && lane == 0 && n_skipped) atomicAdd(wb.stats + (uint64_t)head.qi * 4 + 2, (unsigned long long)n_skipped);
 
     // ---- merge into the query's global top-k (push_top_k, query/wand.rs:905-916) ----
     if (cnt > 0) {
       const unsigned long long thr_now = ld_cg_u64(wb.thr_key + head.qi);
-      const bool useful = (lane < (int)cnt && cand[lane] > thr_now) || (lane + 32 < (int)cnt && cand[lane + 32] > thr_now);
+      const bool useful = lane < (int)cnt && cand[lane] > thr_now;  // cnt <= 32 after every append
       if (__any_sync(0xFFFFFFFFu, useful)) {
-        if (cnt > 32) {  // (cannot happen: cnt <= 32 after every append) keep the merge buffer bounded
-          for (uint32_t z = cnt + lane; z < kWarpCand; z += 32) cand[z] = 0ull;
-          __syncwarp();
-          warp_sort64_desc(cand, lane);
-          cnt = min(cnt, k);
-        }
         if (lane == 0) {
           while (atomicCAS(wb.lock + head.qi, 0u, 1u) != 0u) __nanosleep(64);
           __threadfence();

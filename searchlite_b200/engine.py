@@ -312,7 +312,7 @@ class GpuIndex:
     """Device-resident index: the GPU stand-in for Index::reader() + IndexReader::search on the
     BM25 top-k path.  One instance owns one CUDA device/stream."""
 
-    KERNEL = {"auto": 0, "cta": 1, "warp": 2}
+    KERNEL = {"auto": 0, "cta": 1, "warp": 2, "warp-inplace": 2 + 256, "auto-inplace": 256}
 
     def __init__(self, device: int = 0, tile_docs: int = 0, ctas_per_sm: int = 0, sub_docs: int = 0, kernel: str = "auto"):
         self.lib = load_library()

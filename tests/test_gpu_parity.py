@@ -24,6 +24,7 @@ def small():
 @pytest.mark.parametrize("kernel,tile_docs,sub_docs,k", [
     ("cta", 1024, 0, 11), ("cta", 16384, 0, 11), ("cta", 1024, 0, 101), ("cta", 16384, 0, 101),
     ("warp", 0, 128, 11), ("warp", 0, 2048, 11), ("warp", 0, 1024, 1), ("warp", 0, 2048, 32),
+    ("warp-inplace", 0, 256, 11), ("warp-inplace", 0, 2048, 11),
 ])
 def test_bm25_bit_exact_vs_oracle(small, kernel, tile_docs, sub_docs, k):
     seg, qb = small
