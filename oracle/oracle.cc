@@ -32,10 +32,11 @@ constexpr uint32_t BLOCK_META_FLAG = 1u << 31;       // index/postings.rs:12
 
 // query/bm25.rs:1-6
 inline float bm25(float tf, float df, float doc_len, float avgdl, float docs, float k1, float b) {
-  float idf = std::max(logf((docs - df + 0.5f) / (df + 0.5f)), 0.0f) + 1.0f;
+  // f32::max returns the non-NaN operand (ln of a negative ratio, df > N + 0.5 after deletions): fmaxf
+  float idf = fmaxf(logf((docs - df + 0.5f) / (df + 0.5f)), 0.0f) + 1.0f;
   float norm_dl = avgdl > 0.0f ? doc_len / avgdl : 1.0f;
   float denom = tf + k1 * (1.0f - b + b * norm_dl);
-  return idf * (tf * (k1 + 1.0f)) / std::max(denom, 1e-6f);
+  return idf * (tf * (k1 + 1.0f)) / fmaxf(denom, 1e-6f);
 }
 
 // query/wand.rs:269-286
@@ -920,7 +921,7 @@ float slo_upper_bound_tf(float tf, float df, float doc_len, float avgdl, float d
                          float weight) {
   return upper_bound_tf(tf, df, doc_len, avgdl, docs, k1, b, weight);
 }
-float slo_idf(float df, float docs) { return std::max(logf((docs - df + 0.5f) / (df + 0.5f)), 0.0f) + 1.0f; }
+float slo_idf(float df, float docs) { return fmaxf(logf((docs - df + 0.5f) / (df + 0.5f)), 0.0f) + 1.0f; }
 
 size_t slo_varint_write_u32(uint32_t v, uint8_t *out) {
   std::vector<uint8_t> tmp;

@@ -20,6 +20,11 @@ HIT_DTYPE = np.dtype({"names": ["segment_ord", "doc_id", "score"], "formats": ["
 STATS_DTYPE = np.dtype({"names": ["scored_docs", "candidates_examined", "postings_advanced", "total_matches"],
                         "formats": ["<u8"] * 4, "itemsize": 32})
 
+FILTER_DTYPE = np.dtype(
+    {"names": ["op", "column", "i_min", "i_max", "f_min", "f_max", "n_children", "value_begin", "value_end"],
+     "formats": ["<u4", "<i4", "<i8", "<i8", "<f8", "<f8", "<u4", "<u4", "<u4"],
+     "offsets": [0, 4, 8, 16, 24, 32, 40, 44, 48], "itemsize": 56})  # slo_filter_node_t
+
 _LIB = None
 
 
@@ -175,7 +180,7 @@ class OracleIndex:
         stats = np.zeros(q, dtype=STATS_DTYPE) if want_stats else None
         arr = (C.c_char_p * max(len(strings), 1))(*[x.encode() for x in strings])
         nf = 0 if filter_nodes is None else len(filter_nodes)
-        fn = None if filter_nodes is None else np.ascontiguousarray(filter_nodes)
+        fn = None if filter_nodes is None else np.ascontiguousarray(filter_nodes, dtype=FILTER_DTYPE)
         rc = self.L.slo_search_batch(self.h, _p(s), q, k, EXEC[execution], block_size, _p(fn), nf, arr,
                                      1 if faithful else 0, threads, _p(hits), _p(counts), _p(stats))
         if rc < 0:
@@ -185,7 +190,7 @@ class OracleIndex:
     def filter_bitmap(self, filter_nodes, strings=()):
         out = np.zeros((self.doc_count + 31) // 32, dtype=np.uint32)
         arr = (C.c_char_p * max(len(strings), 1))(*[x.encode() for x in strings])
-        fn = np.ascontiguousarray(filter_nodes)
+        fn = np.ascontiguousarray(filter_nodes, dtype=FILTER_DTYPE)
         self.L.slo_filter_bitmap(self.h, _p(fn), len(fn), arr, _p(out))
         return out
 

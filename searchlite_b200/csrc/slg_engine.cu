@@ -187,7 +187,8 @@ int32_t fail(slg_index *ix, int32_t code, const char *fmt, ...) {
 inline void count_launch(slg_index *ix, uint64_t n = 1) { ix->ctr.kernel_launches += n; }
 
 // idf exactly as query/bm25.rs:2 with docs = live docs (api/reader.rs:2985) and df = list length
-inline float host_idf(float df, float docs) { return std::max(logf((docs - df + 0.5f) / (df + 0.5f)), 0.0f) + 1.0f; }
+// f32::max returns the non-NaN operand (ln of a negative ratio when df > N + 0.5 after deletions): fmaxf
+inline float host_idf(float df, float docs) { return fmaxf(logf((docs - df + 0.5f) / (df + 0.5f)), 0.0f) + 1.0f; }
 inline float host_nk(float dl, float avgdl, float k1, float b) {
   volatile float norm = avgdl > 0.0f ? dl / avgdl : 1.0f;
   volatile float bn = b * norm;

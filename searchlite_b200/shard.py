@@ -39,11 +39,12 @@ def gather_hits(local_hits: torch.Tensor, local_counts: torch.Tensor, group=None
     """all-gather of per-rank results.  local_hits: uint8 [Q*k*12], local_counts: int32 [Q].
     Returns ([world, Q*k*12] uint8, [world, Q] int32), rank-major."""
     world = dist.get_world_size(group)
-    hits = torch.empty((world,) + tuple(local_hits.shape), dtype=local_hits.dtype, device=local_hits.device)
-    counts = torch.empty((world,) + tuple(local_counts.shape), dtype=local_counts.dtype, device=local_counts.device)
-    dist.all_gather_into_tensor(hits, local_hits, group=group)
-    dist.all_gather_into_tensor(counts, local_counts, group=group)
-    return hits, counts
+    # flat outputs (rank-major concatenation): the form both NCCL and gloo accept
+    hits = torch.empty(world * local_hits.numel(), dtype=local_hits.dtype, device=local_hits.device)
+    counts = torch.empty(world * local_counts.numel(), dtype=local_counts.dtype, device=local_counts.device)
+    dist.all_gather_into_tensor(hits, local_hits.reshape(-1), group=group)
+    dist.all_gather_into_tensor(counts, local_counts.reshape(-1), group=group)
+    return hits.view(world, -1), counts.view(world, -1)
 
 
 class ShardedSearcher:
