@@ -1,0 +1,484 @@
+"""GPU parity for everything around the plain OR scan: golden fixtures through the C ABI, edge
+cases, deleted docs, the Bool matcher, fast-field filters, the `.post` image load path,
+multi-segment merge, weights, wide term frequencies, shard merge and the vector rerank.
+Every case is checked against the CPU oracle (or the committed golden bits) on the same inputs."""
+import numpy as np
+import pytest
+
+from searchlite_b200 import GpuIndex, QueryBatch, SearchliteGpuError, synth
+from searchlite_b200.engine import (FILTER_DTYPE, F_AND, F_F64_RANGE, F_I64_RANGE, F_KEYWORD_EQ, F_KEYWORD_IN, F_NOT, F_OR,
+                                    HIT_DTYPE)
+from tests.helpers import f32_bits, golden, hits_to_list, or_queries, segment_from_postings, token_corpus
+from tests.parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["cta", "warp", "warp-inplace"]
+
+
+def _oracle(seg, **kw):
+    from oracle import slo
+    return slo.OracleIndex(seg, **kw)
+
+
+def _gpu(seg, kernel="auto", k1=0.9, b=0.4, **kw):
+    gi = GpuIndex(0, kernel=kernel, **kw)
+    cols = gi.load_segment(seg, k1=k1, b=b)
+    return gi, cols
+
+
+def node(op, column=-1, i=(0, 0), f=(0.0, 0.0), nc=0, v=(0, 0)):
+    n = np.zeros(1, dtype=FILTER_DTYPE)
+    n[0] = (op, column, i[0], i[1], f[0], f[1], nc, v[0], v[1])
+    return n
+
+
+# ---- golden fixtures (tests/golden, made by tests/golden/make_golden.py) through the C ABI ----------
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_reference_literal_known_answer(kernel):
+    """query/wand.rs:969-1011 literal postings; expected bits frozen in wand_literal.json"""
+    g = golden("wand_literal.json")
+    seg = segment_from_postings([(t["docs"], t["tfs"]) for t in g["terms"]], [10] * 10)
+    gi, _ = _gpu(seg, kernel, k1=g["k1"], b=g["b"])
+    want = [(e["doc_id"], e["score_bits"]) for e in g["expected"]]
+    for mode in ("bm25", "wand", "bmw"):
+        h, c = gi.search_batch(or_queries([[0, 1]]), g["k"], mode)
+        assert hits_to_list(h, c) == want, mode
+    gi.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_small_corpus_topk_matches_golden_bits(kernel):
+    g = golden("small_topk.json")
+    seg = segment_from_postings([(p["docs"], p["tfs"]) for p in g["postings"]], g["field_lengths"], g["total_tokens"])
+    gi, _ = _gpu(seg, kernel, k1=g["k1"], b=g["b"])
+    for q in g["queries"]:
+        qb = or_queries([q["terms"]], [q["weights"]])
+        want = [(e["doc_id"], e["score_bits"]) for e in q["expected"]]
+        for mode in ("bm25", "wand", "bmw"):
+            h, c = gi.search_batch(qb, q["k"], mode)
+            assert hits_to_list(h, c) == want, (mode, q["terms"])
+    gi.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_tie_break_prefers_smaller_doc_id(kernel):
+    """query/wand.rs:952-966"""
+    seg = segment_from_postings([([1, 2], [1, 1])], [10] * 4)
+    gi, _ = _gpu(seg, kernel, k1=1.2, b=0.75)
+    h, c = gi.search_batch(or_queries([[0]]), 1, "bm25")
+    assert c[0] == 1 and h[0][0]["doc_id"] == 1
+    h, c = gi.search_batch(or_queries([[0]]), 2, "wand")
+    assert [int(x) for x in h[0]["doc_id"][:2]] == [1, 2] and h[0]["score"][0] == h[0]["score"][1]
+    gi.close()
+
+
+# ---- edge cases ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_empty_absent_and_ragged_queries(kernel):
+    seg = token_corpus([[0, 1], [1, 1, 2], [4], [0, 2, 2, 2, 4]], 6)  # term 3 and 5 have no postings
+    ora = _oracle(seg)
+    qb = or_queries([[], [0xFFFFFFFF], [2], [3], [5, 3], [0, 1, 2, 3, 4], [1], [999]])
+    gi, _ = _gpu(seg, kernel)
+    for k in (1, 3, 11):
+        ref = ora.search_batch(qb, k, "bm25")
+        for mode in ("bm25", "wand", "bmw"):
+            got = gi.search_batch(qb, k, mode)
+            assert_parity(*ref, *got, strict=True)
+    h, c = gi.search_batch(qb, 3, "bm25")
+    assert c.tolist()[:2] == [0, 0] and c[3] == 0 and c[4] == 0 and c[7] == 0
+    # unused output slots are marked invalid
+    assert h[0][0]["doc_id"] == 0xFFFFFFFF and h[0][0]["segment_ord"] == 0xFFFFFFFF
+    gi.close()
+
+
+def test_argument_errors_are_reported_not_fatal():
+    seg = token_corpus([[0, 1], [1]], 2)
+    gi = GpuIndex(0)
+    with pytest.raises(SearchliteGpuError):  # no segment yet
+        gi.search_batch(or_queries([[0]]), 3)
+    gi.load_segment(seg)
+    with pytest.raises(SearchliteGpuError):  # api/reader.rs:2540 bails on limit == 0
+        gi.search_batch(or_queries([[0]]), 0)
+    with pytest.raises(SearchliteGpuError) as e:
+        gi.search_batch(or_queries([[0]]), 1 << 20)
+    assert e.value.code == -4
+    with pytest.raises(SearchliteGpuError):
+        gi.search_batch(or_queries([[0]], [[-1.0]]), 3)
+    # the handle is still usable after errors
+    h, c = gi.search_batch(or_queries([[1]]), 3)
+    assert c[0] == 2
+    gi.close()
+
+
+@pytest.mark.parametrize("k", [1, 2, 33, 257, 2048])
+def test_large_k_goes_through_the_cta_kernel(k):
+    spec = synth.CorpusSpec(n_docs=9_000, vocab=500, seed=5, len_lo=5, len_hi=40)
+    seg = synth.generate_segment(spec, "cpu")
+    qb = synth.generate_queries(40, spec.vocab, seed=6, min_rank=2)
+    ora = _oracle(seg)
+    ref = ora.search_batch(qb, k, "bm25")
+    gi, _ = _gpu(seg)
+    for mode in ("bm25", "bmw"):
+        got = gi.search_batch(qb, k, mode)
+        assert_parity(*ref, *got, strict=True)
+    gi.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_many_terms_per_query(kernel):
+    spec = synth.CorpusSpec(n_docs=20_000, vocab=3_000, seed=15, len_lo=20, len_hi=60)
+    seg = synth.generate_segment(spec, "cpu")
+    n_terms = 8 if kernel.startswith("warp") else 40
+    qb = synth.generate_queries(30, spec.vocab, seed=16, min_terms=n_terms, max_terms=n_terms, min_rank=2)
+    ref = _oracle(seg).search_batch(qb, 11, "bm25")
+    gi, _ = _gpu(seg, kernel)
+    assert_parity(*ref, *gi.search_batch(qb, 11, "bm25"), strict=True)
+    gi.close()
+    if kernel == "warp":
+        gi, _ = _gpu(seg, "auto")  # more terms than the warp kernel holds: automatic choice must fall to the CTA kernel
+        qb2 = synth.generate_queries(10, spec.vocab, seed=17, min_terms=20, max_terms=20, min_rank=2)
+        assert_parity(*_oracle(seg).search_batch(qb2, 11, "bm25"), *gi.search_batch(qb2, 11, "bm25"), strict=True)
+        gi.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_weights_and_duplicate_keys(kernel):
+    """api/reader.rs:2971-2983: duplicate keys arrive merged (weight 2.0); boosts are plain weights"""
+    spec = synth.CorpusSpec(n_docs=12_000, vocab=1_000, seed=25, len_lo=10, len_hi=50)
+    seg = synth.generate_segment(spec, "cpu")
+    rng = np.random.default_rng(3)
+    tl = [rng.choice(np.arange(1, 400), size=rng.integers(1, 6), replace=False).tolist() for _ in range(60)]
+    w = [[float(np.float32(rng.choice([0.5, 1.0, 2.0, 3.25, 0.1]))) for _ in t] for t in tl]
+    qb = or_queries(tl, w)
+    ref = _oracle(seg).search_batch(qb, 11, "bm25")
+    gi, _ = _gpu(seg, kernel)
+    for mode in ("bm25", "wand", "bmw"):
+        assert_parity(*ref, *gi.search_batch(qb, 11, mode), strict=True)
+    gi.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_wide_term_frequencies(kernel):
+    """tf >= 255 does not fit the byte column: the exact side table must be used"""
+    n = 3000
+    rng = np.random.default_rng(9)
+    d0 = np.sort(rng.choice(n, size=1500, replace=False))
+    tf0 = rng.integers(1, 6, size=1500)
+    tf0[::37] = rng.integers(255, 70000, size=len(tf0[::37]))
+    tf0[5] = 255
+    tf0[6] = 254
+    d1 = np.sort(rng.choice(n, size=700, replace=False))
+    tf1 = rng.integers(1, 4, size=700)
+    lens = rng.integers(50, 400, size=n)
+    seg = segment_from_postings([(d0.tolist(), tf0.tolist()), (d1.tolist(), tf1.tolist())], lens.tolist())
+    ref = _oracle(seg).search_batch(or_queries([[0], [0, 1], [1, 0]]), 11, "bm25")
+    gi, _ = _gpu(seg, kernel)
+    for mode in ("bm25", "bmw"):
+        assert_parity(*ref, *gi.search_batch(or_queries([[0], [0, 1], [1, 0]]), 11, mode), strict=True)
+    gi.close()
+
+
+def test_zero_and_missing_field_lengths():
+    """query/wand.rs:77-84: a non-positive length scores as max(avgdl, 1)"""
+    lens = [0, 12, 7, 0, 30, 9]
+    present = np.array([1, 1, 1, 0, 1, 1], dtype=np.uint8)
+    seg = segment_from_postings([([0, 1, 3, 4], [1, 2, 1, 3]), ([2, 3, 5], [1, 1, 4])], lens, total_tokens=58)
+    seg.field_length_present = present
+    ora = _oracle(seg)
+    gi, _ = _gpu(seg)
+    st = gi.segment_stats(0)
+    assert st["min_doc_len"] == ora.min_doc_len == 7.0 and st["avgdl"] == ora.avgdl
+    assert_parity(*ora.search_batch(or_queries([[0, 1], [1], [0]]), 6, "bm25"), *gi.search_batch(or_queries([[0, 1], [1], [0]]), 6, "bm25"),
+                  strict=True)
+    gi.close()
+
+
+# ---- deleted docs + matcher: api/reader.rs:3009-3036, :1485-1565 --------------------------------------
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_deleted_docs(kernel):
+    spec = synth.CorpusSpec(n_docs=10_000, vocab=900, seed=31, len_lo=10, len_hi=40)
+    seg = synth.generate_segment(spec, "cpu")
+    seg.deleted_docs = np.unique(np.random.default_rng(1).integers(0, spec.n_docs, size=2500)).astype(np.uint32)
+    qb = synth.generate_queries(80, spec.vocab, seed=32, min_rank=2)
+    ora = _oracle(seg)
+    ref = ora.search_batch(qb, 11, "bm25")
+    assert not np.isin(ref[0]["doc_id"][ref[0]["segment_ord"] == 0], seg.deleted_docs).any()
+    gi, _ = _gpu(seg, kernel)
+    assert gi.segment_stats(0)["live_docs"] == ora.live_docs == float(spec.n_docs - len(seg.deleted_docs))
+    for mode in ("bm25", "wand", "bmw"):
+        assert_parity(*ref, *gi.search_batch(qb, 11, mode), strict=True)
+    gi.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_bool_matcher_literal(kernel):
+    """tests/query_ast.rs:52-58 style corpus"""
+    seg = token_corpus([[0, 1], [0, 2], [1, 2], [0, 1, 2], [3]], 4)
+    qb = QueryBatch.from_bool([
+        {"must": [0, 1]}, {"must": [0], "must_not": [2]}, {"should": [0, 1, 2], "min_should": 2}, {"should": [3]},
+        {"must": [0], "should": [1]}, {"must_not": [0], "should": [1, 2, 3]},
+    ])
+    ref = _oracle(seg).search_batch(qb, 5, "bm25")
+    gi, _ = _gpu(seg, kernel)
+    got = gi.search_batch(qb, 5, "bm25")
+    assert_parity(*ref, *got, strict=True)
+    assert [sorted(got[0][q]["doc_id"][: got[1][q]].tolist()) for q in range(4)] == [[0, 3], [0], [0, 1, 2, 3], [4]]
+    assert_parity(*ref, *gi.search_batch(qb, 5, "bmw"), strict=True)
+    gi.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_bool_matcher_random(kernel):
+    """C4 shape: Bool{must:[t1,t2(,t3)]} executed as OR-scan + reject (api/reader.rs:1527-1563)"""
+    spec = synth.CorpusSpec(n_docs=30_000, vocab=2_000, seed=41, len_lo=20, len_hi=80)
+    seg = synth.generate_segment(spec, "cpu")
+    rng = np.random.default_rng(4)
+    qs = []
+    for i in range(90):
+        t = rng.choice(np.arange(1, 120), size=5, replace=False).tolist()
+        kind = i % 5
+        if kind == 0:
+            qs.append({"must": t[:2]})
+        elif kind == 1:
+            qs.append({"must": t[:3]})
+        elif kind == 2:
+            qs.append({"must": t[:1], "must_not": t[1:2], "should": t[2:4]})
+        elif kind == 3:
+            qs.append({"should": t[:4], "min_should": 2})
+        else:
+            qs.append({"should": t[:3], "must_not": t[3:5]})
+    qb = QueryBatch.from_bool(qs)
+    ref = _oracle(seg).search_batch(qb, 11, "bm25")
+    assert ref[1].sum() > 0
+    gi, _ = _gpu(seg, kernel)
+    for mode in ("bm25", "wand", "bmw"):
+        assert_parity(*ref, *gi.search_batch(qb, 11, mode), strict=True)
+    gi.close()
+
+
+# ---- filters: query/filters.rs:84-149, index/fastfields.rs:475-657 --------------------------------------
+def test_filter_bitmaps_match_oracle_literal():
+    seg = token_corpus([[0], [0], [0], [0]], 1)
+    seg.fast_str["cat"] = (["News", "sports", "other"], np.array([0, 1, 0xFFFFFFFF, 2], dtype=np.uint32))
+    seg.fast_i64["year"] = (np.array([2024, 2019, 2025, 0], dtype=np.int64), np.array([1, 1, 1, 0], dtype=np.uint8))
+    seg.fast_f64["score"] = (np.array([0.75, 0.5, 1.5, 0.0]), np.array([1, 1, 1, 0], dtype=np.uint8))
+    ora = _oracle(seg)
+    gi, col = _gpu(seg)
+    ocol = ora.columns
+    cases = [
+        ([(F_KEYWORD_EQ, "cat", dict(v=(0, 1)))], ["news"], [0]),
+        ([(F_KEYWORD_IN, "cat", dict(v=(0, 2)))], ["sports", "NEWS"], [0, 1]),
+        ([(F_KEYWORD_EQ, "cat", dict(v=(0, 1)))], ["absent"], []),
+        ([(F_I64_RANGE, "year", dict(i=(2020, 2025)))], [], [0, 2]),
+        ([(F_I64_RANGE, "year", dict(i=(2025, 2030)))], [], [2]),
+        ([(F_F64_RANGE, "score", dict(f=(0.5, 1.0)))], [], [0, 1]),
+        ([(F_NOT, None, dict(nc=1)), (F_I64_RANGE, "year", dict(i=(0, 3000)))], [], [3]),
+        ([(F_AND, None, dict(nc=2)), (F_KEYWORD_EQ, "cat", dict(v=(0, 1))), (F_I64_RANGE, "year", dict(i=(2020, 2030)))], ["NEWS"], [0]),
+        ([(F_OR, None, dict(nc=2)), (F_KEYWORD_EQ, "cat", dict(v=(0, 1))), (F_I64_RANGE, "year", dict(i=(2019, 2019)))], ["other"], [1, 3]),
+        ([(F_KEYWORD_EQ, "nope", dict(v=(0, 1)))], ["news"], []),
+        ([(F_I64_RANGE, "cat", dict(i=(0, 10)))], [], []),  # wrong column type: predicate false
+    ]
+    for spec_nodes, strings, want in cases:
+        gnodes = np.concatenate([node(op, col.get(c, -1) if c else -1, **kw) for op, c, kw in spec_nodes])
+        onodes = np.concatenate([node(op, ocol.get(c, -1) if c else -1, **kw) for op, c, kw in spec_nodes])
+        fid = gi.compile_filter(gnodes, strings)
+        bm = gi.filter_bitmap(fid, 0, 4)
+        assert [d for d in range(4) if (bm[0] >> d) & 1] == want, spec_nodes
+        assert np.array_equal(bm, ora.filter_bitmap(onodes, strings))
+    gi.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_filtered_search_c4_shape(kernel):
+    """C4: Bool{must} + root filter And[KeywordEq(lang), I64Range(year)] at three selectivities"""
+    spec = synth.CorpusSpec(n_docs=40_000, vocab=3_000, seed=51, len_lo=20, len_hi=80)
+    seg = synth.generate_segment(spec, "cpu")
+    names, lang, year = synth.fast_fields(spec)
+    seg.fast_str["lang"] = (names, lang)
+    seg.fast_i64["year"] = (year, None)
+    ora = _oracle(seg)
+    gi, col = _gpu(seg, kernel)
+    rng = np.random.default_rng(6)
+    filters = [("en", 2000, 2025), ("es", 2010, 2020), ("sv", 2024, 2024)]
+    for lang_name, lo, hi in filters:
+        def prog(c):
+            return np.concatenate([node(F_AND, nc=2), node(F_KEYWORD_EQ, c["lang"], v=(0, 1)), node(F_I64_RANGE, c["year"], i=(lo, hi))])
+        fid = gi.compile_filter(prog(col), [lang_name.upper()])
+        want_bits = ora.filter_bitmap(prog(ora.columns), [lang_name.upper()])
+        assert np.array_equal(gi.filter_bitmap(fid, 0, spec.n_docs), want_bits)
+        qs = []
+        for i in range(40):
+            t = rng.choice(np.arange(1, 150), size=3, replace=False).tolist()
+            qs.append({"must": t[:2], "filter_id": fid} if i % 2 else {"should": t, "min_should": 1, "filter_id": fid})
+        qb = QueryBatch.from_bool(qs)
+        ref = ora.search_batch(qb, 11, "bm25", filter_nodes=prog(ora.columns), strings=[lang_name.upper()])
+        for mode in ("bm25", "bmw"):
+            assert_parity(*ref, *gi.search_batch(qb, 11, mode), strict=True)
+    # plain OR queries with a filter and without, mixed in one batch
+    qb = synth.generate_queries(30, spec.vocab, seed=52, min_rank=2)
+    qb.filter_id = np.array([0 if i % 2 else -1 for i in range(30)], dtype=np.int32)
+    got = gi.search_batch(qb, 11, "bm25")
+    plain = synth.generate_queries(30, spec.vocab, seed=52, min_rank=2)
+    ref_nofilter = ora.search_batch(plain, 11, "bm25")
+    def prog0(c):
+        return np.concatenate([node(F_AND, nc=2), node(F_KEYWORD_EQ, c["lang"], v=(0, 1)), node(F_I64_RANGE, c["year"], i=(2000, 2025))])
+    ref_filter = ora.search_batch(plain, 11, "bm25", filter_nodes=prog0(ora.columns), strings=["EN"])
+    for q in range(30):
+        src = ref_filter if q % 2 else ref_nofilter
+        assert_parity(src[0][q:q + 1], src[1][q:q + 1], got[0][q:q + 1], got[1][q:q + 1], strict=True)
+    gi.close()
+
+
+# ---- residency from the reference's `.post` byte image: index/postings.rs:78-212 --------------------------
+def test_post_image_load_equals_csr_load():
+    spec = synth.CorpusSpec(n_docs=25_000, vocab=2_500, seed=61, len_lo=20, len_hi=90)
+    seg = synth.generate_segment(spec, "cpu")
+    ora = _oracle(seg)
+    img, off = ora.build_post_image()
+    qb = synth.generate_queries(120, spec.vocab, seed=62, min_rank=2)
+    ref = ora.search_batch(qb, 11, "bm25")
+    gi = GpuIndex(0)
+    gi.load_segment_post_image(seg, img, off)
+    assert gi.segment_stats(0)["n_postings"] == len(seg.post_docs)
+    for mode in ("bm25", "bmw"):
+        assert_parity(*ref, *gi.search_batch(qb, 11, mode), strict=True)
+    gi.close()
+    # a truncated image is an error, not a crash
+    gi = GpuIndex(0)
+    with pytest.raises(SearchliteGpuError):
+        gi.load_segment_post_image(seg, img[: len(img) // 2], off)
+    gi.close()
+
+
+# ---- several segments in one handle: api/reader.rs:2670-2777 ----------------------------------------------
+@pytest.mark.parametrize("kernel", ["cta", "warp"])
+def test_multi_segment_merge_order(kernel):
+    from oracle import slo
+    from searchlite_b200.shard import shard_ranges
+    n_docs, vocab, world = 24_000, 1_500, 3
+    qb = synth.generate_queries(70, vocab, seed=72, min_rank=2)
+    gi = GpuIndex(0, kernel=kernel)
+    per_seg = []
+    for r, (lo, hi) in enumerate(shard_ranges(n_docs, world)):
+        spec = synth.CorpusSpec(n_docs=hi - lo, vocab=vocab, seed=71, len_lo=10, len_hi=60, segment_ord=r, doc_base=lo)
+        seg = synth.generate_segment(spec, "cpu")
+        gi.load_segment(seg)
+        per_seg.append(slo.OracleIndex(seg).search_batch(qb, 11, "bm25"))
+    got_h, got_c = gi.search_batch(qb, 11, "bm25")
+    for q in range(qb.n_queries):
+        want = slo.merge_hits([h[q, : c[q]] for h, c in per_seg], 11)
+        assert got_c[q] == len(want)
+        g = got_h[q, : got_c[q]]
+        assert np.array_equal(g["segment_ord"], want["segment_ord"]) and np.array_equal(g["doc_id"], want["doc_id"])
+        assert np.array_equal(g["score"].view(np.uint32), want["score"].view(np.uint32))
+    gi.close()
+
+
+def test_merge_gathered_matches_sortkey_order():
+    """api/reader.rs:2777 + query/sort.rs:80-93: score desc, segment_ord asc, doc_id asc"""
+    import torch
+    from oracle import slo
+    rng = np.random.default_rng(8)
+    n_shards, nq, k = 4, 50, 11
+    hits = np.zeros((n_shards, nq, k), dtype=HIT_DTYPE)
+    counts = rng.integers(0, k + 1, size=(n_shards, nq)).astype(np.uint32)
+    for s in range(n_shards):
+        for q in range(nq):
+            c = counts[s, q]
+            sc = np.sort(rng.choice(np.array([0.5, 1.0, 1.5, 2.0, 2.5, 3.0], dtype=np.float32), size=c))[::-1]
+            docs = rng.choice(1000, size=c, replace=False)
+            order = np.lexsort((docs, -sc))
+            hits[s, q, :c]["segment_ord"] = s
+            hits[s, q, :c]["doc_id"] = docs[order]
+            hits[s, q, :c]["score"] = sc[order]
+            hits[s, q, c:]["segment_ord"] = 0xFFFFFFFF
+            hits[s, q, c:]["doc_id"] = 0xFFFFFFFF
+    gi = GpuIndex(0)
+    dh = torch.from_numpy(hits.view(np.uint8).reshape(-1).copy()).cuda()
+    dc = torch.from_numpy(counts.view(np.int32).reshape(-1).copy()).cuda()
+    torch.cuda.synchronize()
+    mh, mc = gi.merge_gathered(dh.data_ptr(), dc.data_ptr(), n_shards, nq, k)
+    for q in range(nq):
+        want = slo.merge_hits([hits[s, q, : counts[s, q]] for s in range(n_shards)], k)
+        assert mc[q] == len(want)
+        assert mh[q, : mc[q]].tobytes() == want.tobytes()
+    gi.close()
+
+
+# ---- vectors + rerank: vectors/mod.rs:63-129, api/reader.rs:218-254 -------------------------------------
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_rerank_matches_oracle_formulae(metric, bf16):
+    from oracle import slo
+    L = slo.lib()
+    spec = synth.CorpusSpec(n_docs=5_000, vocab=600, seed=81, len_lo=10, len_hi=40)
+    seg = synth.generate_segment(spec, "cpu")
+    rng = np.random.default_rng(10)
+    dim, nq, k = 64, 25, 50
+    have = rng.random(spec.n_docs) < 0.9
+    offsets = np.full(spec.n_docs, 0xFFFFFFFF, dtype=np.uint32)
+    offsets[have] = np.arange(int(have.sum()), dtype=np.uint32)
+    vecs = rng.standard_normal((int(have.sum()), dim)).astype(np.float32)
+    qv = rng.standard_normal((nq, dim)).astype(np.float32)
+    if metric == "cosine":  # normalize_in_place, vectors/mod.rs:74-81
+        for row in vecs:
+            L.slo_normalize_in_place(row.ctypes.data, dim)
+        for row in qv:
+            L.slo_normalize_in_place(row.ctypes.data, dim)
+    gi, _ = _gpu(seg)
+    gi.load_vectors(0, offsets, vecs, store_bf16=bf16)
+    qb = synth.generate_queries(nq, spec.vocab, seed=82, min_rank=2)
+    cands, cc = gi.search_batch(qb, k, "bm25")
+    alpha = 0.5
+    out, vs = gi.rerank(qv, cands, cc, alpha, metric)
+    m = 0 if metric == "cosine" else 1
+    # bf16 storage is this build's choice: rows are rounded once, the arithmetic stays f32
+    tol = 2e-2 if bf16 else 2e-5
+    for q in range(nq):
+        n = int(cc[q])
+        exp = {}
+        for h in cands[q, :n]:
+            d = int(h["doc_id"])
+            if offsets[d] == 0xFFFFFFFF:
+                s = L.slo_hybrid_score(float(h["score"]), 0, 0.0, alpha, m)
+            else:
+                v = np.ascontiguousarray(vecs[offsets[d]])
+                sim = L.slo_metric_similarity(m, qv[q].ctypes.data, v.ctypes.data, dim)
+                s = L.slo_hybrid_score(float(h["score"]), 1, sim, alpha, m)
+            exp[d] = s
+        got = out[q, :n]
+        assert sorted(got["doc_id"].tolist()) == sorted(exp.keys())
+        for h in got:
+            e = exp[int(h["doc_id"])]
+            assert abs(float(h["score"]) - e) <= tol * max(1.0, abs(e)), (q, int(h["doc_id"]), float(h["score"]), e)
+        sc = got["score"]
+        assert np.all(sc[:-1] >= sc[1:])  # re-ordered by blended score
+        missing = [int(h["doc_id"]) for h in got if offsets[int(h["doc_id"])] == 0xFFFFFFFF]
+        if missing and metric == "cosine":
+            for h, v in zip(got, vs[q, :n]):
+                if int(h["doc_id"]) in missing:
+                    assert v == -1.0
+    # alpha shortcuts (api/reader.rs:241-247)
+    out1, _ = gi.rerank(qv, cands, cc, 1.0, metric)
+    for q in range(nq):
+        assert out1[q, : cc[q]].tobytes() == cands[q, : cc[q]].tobytes()
+    gi.close()
+
+
+# ---- statistics (QueryStats, query/wand.rs:45-50) -----------------------------------------------------------
+@pytest.mark.parametrize("kernel", ["cta", "warp", "warp-inplace"])
+def test_stats_count_scored_docs_and_postings(kernel):
+    spec = synth.CorpusSpec(n_docs=15_000, vocab=1_200, seed=91, len_lo=10, len_hi=50)
+    seg = synth.generate_segment(spec, "cpu")
+    qb = synth.generate_queries(50, spec.vocab, seed=92, min_rank=2)
+    gi, _ = _gpu(seg, kernel)
+    _, _, st = gi.search_batch(qb, 11, "bm25", want_stats=True)
+    off = seg.term_offsets.astype(np.int64)
+    for q in range(qb.n_queries):
+        terms = qb.terms["term_id"][qb.term_off[q]: qb.term_off[q + 1]]
+        n_post = int(sum(off[t + 1] - off[t] for t in terms))
+        n_docs = len(np.unique(np.concatenate([seg.post_docs[off[t]: off[t + 1]] for t in terms])))
+        assert st["postings_advanced"][q] == n_post
+        assert st["scored_docs"][q] == n_docs
+    gi.close()

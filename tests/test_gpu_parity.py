@@ -59,3 +59,47 @@ def test_division_sequence_is_ieee_exact():
     gi = GpuIndex(0)
     assert gi.selftest_div(200_000_000, seed=3) == 0
     gi.close()
+
+
+def test_full_size_c2_properties():
+    """BASELINE.json configs[1] at full size (10 M docs, 1 M-term vocabulary, 4096 queries, k = 11):
+    size-independent properties — every kernel variant and every execution strategy returns the
+    same bytes (idempotence across code paths), lists are ordered (score desc, doc asc) with unique
+    docs, counts are full — plus oracle parity on a bounded sample of the batch."""
+    import torch
+    spec = synth.CorpusSpec(n_docs=10_000_000, vocab=1_000_000, seed=20260101)
+    seg = synth.generate_segment(spec, "cuda:0")
+    qb = synth.generate_queries(4096, spec.vocab, seed=20260102)
+    k = 11
+    results = {}
+    for kernel, mode in (("auto", "bm25"), ("auto", "bmw"), ("warp-inplace", "bm25"), ("cta", "bm25")):
+        gi = GpuIndex(0, kernel=kernel)
+        gi.load_segment(seg)
+        p = gi.prepare(qb, k, mode)
+        p.run()
+        first = p.fetch()
+        p.run()
+        again = p.fetch()
+        assert first[0].tobytes() == again[0].tobytes() and first[1].tobytes() == again[1].tobytes()  # re-runnable
+        results[(kernel, mode)] = first
+        p.free()
+        gi.close()
+    base_h, base_c = results[("auto", "bm25")]
+    for key, (h, c) in results.items():
+        assert h.tobytes() == base_h.tobytes() and c.tobytes() == base_c.tobytes(), key
+    assert np.all(base_c == k)
+    sc, dc = base_h["score"], base_h["doc_id"].astype(np.int64)
+    assert np.all(sc[:, :-1] >= sc[:, 1:])
+    tie = sc[:, :-1] == sc[:, 1:]
+    assert np.all(dc[:, :-1][tie] < dc[:, 1:][tie])
+    assert all(len(set(row.tolist())) == k for row in dc[::64])
+    assert np.all(dc < spec.n_docs) and np.all(base_h["segment_ord"] == 0)
+    # oracle on a sample
+    host = seg.to_host()
+    del seg
+    torch.cuda.empty_cache()
+    from oracle import slo
+    ora = slo.OracleIndex(host)
+    n = 48
+    ref_h, ref_c = ora.search_batch(qb.subset(0, n), k, "bm25_dense", threads=slo.max_threads())
+    assert_parity(ref_h, ref_c, base_h[:n], base_c[:n], strict=True)
