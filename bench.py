@@ -53,7 +53,8 @@ def parse_args():
     ap.add_argument("--tile-docs", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--sub-docs", type=int, default=0)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "cta", "warp", "warp-inplace", "auto-inplace"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "cta", "warp", "reg", "warp-inplace", "auto-inplace"])
+    ap.add_argument("--option", action="append", default=[], help="engine residency option name=value (slg_set_option)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="queries in the CPU baseline sample (0 = skip)")
     ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")
@@ -217,7 +218,9 @@ def main():
     torch.cuda.synchronize()
     gen_s = time.time() - t0
     t0 = time.time()
-    gi = GpuIndex(local_rank, tile_docs=args.tile_docs, ctas_per_sm=args.ctas_per_sm, sub_docs=args.sub_docs, kernel=args.kernel)
+    options = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.option}
+    gi = GpuIndex(local_rank, tile_docs=args.tile_docs, ctas_per_sm=args.ctas_per_sm, sub_docs=args.sub_docs, kernel=args.kernel,
+                  options=options)
     gi.load_segment(seg)
     load_s = time.time() - t0
     n_postings = gi.segment_stats(rank)["n_postings"]
@@ -318,13 +321,13 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, world), "execution": args.execution,
                    "l2": "inputs larger than L2 (resident postings >> 126 MB); no explicit flush",
-                   "postings_resident_this_rank": int(n_postings), "kernel": args.kernel,
-                   "tile_docs": args.tile_docs or 16384, "sub_docs": args.sub_docs or 2048},
+                   "postings_resident_this_rank": int(n_postings), "kernel": args.kernel, "options": options},
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_kind": peak_kind, "kernel": "slg_score_tiles_kernel",
+                     "traffic": None, "peak_kind": peak_kind,
+                     "kernel": {"auto": "slg_score_reg_kernel", "reg": "slg_score_reg_kernel", "cta": "slg_score_tiles_kernel"}.get(args.kernel, "slg_score_warp_kernel"),
                      "kernel_ms": score_ms, "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "5 B x sum of df over the batch's query terms (this rank's segment)"},
         "setup": {"corpus_gen_s": round(gen_s, 1), "load_segment_s": round(load_s, 1), "resident_bytes": int(c1["resident_bytes"])},

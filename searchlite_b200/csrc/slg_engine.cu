@@ -23,6 +23,7 @@
 #include "slg_filter.cuh"
 #include "slg_kernels.cuh"
 #include "slg_postimage.cuh"
+#include "slg_reg_kernel.cuh"
 #include "slg_rerank.cuh"
 #include "slg_warp_kernel.cuh"
 
@@ -89,7 +90,10 @@ struct Segment {
   float k1 = 0.9f, b = 0.4f, avgdl = 0, live_docs = 0, min_doc_len = 1;
   std::vector<uint32_t> h_df;  // host copy (query ordering, validation)
   DevBuf post_doc, post_tf, term_start, term_df, term_idf, term_max_tf, term_wide, tf_wide, term_blk, blk_max_doc,
-      blk_max_tf, nk, live_bits;
+      blk_max_tf, nk, live_bits, post_score, cols, term_col;
+  uint32_t n_cols = 0;
+  uint64_t col_stride = 0;
+  std::vector<int32_t> h_term_col;  // host copy (tests, introspection); empty = no columns
   SegmentDev dev{};
   std::vector<Column> columns;
   std::vector<DevBuf> filter_bits;  // per filter id
@@ -98,7 +102,7 @@ struct Segment {
   size_t resident() const {
     return post_doc.bytes + post_tf.bytes + term_start.bytes + term_df.bytes + term_idf.bytes + term_max_tf.bytes +
            term_wide.bytes + tf_wide.bytes + term_blk.bytes + blk_max_doc.bytes + blk_max_tf.bytes + nk.bytes +
-           live_bits.bytes;
+           live_bits.bytes + post_score.bytes + cols.bytes + term_col.bytes;
   }
 };
 
@@ -122,8 +126,14 @@ struct slg_index {
   uint32_t tile_docs = 16384;
   uint32_t ctas_per_sm = 0;  // 0 = as many as shared memory allows
   uint32_t sub_docs = 2048;  // warp kernel: docs per warp-private accumulator
-  uint32_t kernel_choice = 0;  // 0 auto, 1 CTA-per-item kernel, 2 warp-per-item kernel
-  bool staging = true;         // decode + score unique terms once per batch (warp kernel, bm25)
+  uint32_t kernel_choice = 0;  // 0 auto, 1 CTA-per-item kernel, 2 warp-per-item kernel, 3 register-tile kernel
+  bool staging = true;         // use the resident per-posting scores (seg.post_score) where a kernel can
+  // residency options (slg_set_option), applied to segments loaded afterwards
+  bool resident_scores = true;   // build seg.post_score at load
+  uint32_t dense_den = 8;        // a term gets a dense column when df * dense_den >= doc_count; 0 = no columns
+  uint32_t dense_min_df = 256;   // ... and df >= this
+  uint64_t max_column_bytes = 24ull << 30;
+  uint32_t reg_tile_v = 8;       // register kernel: 128 * V docs per tile (4, 8 or 16)
   Segment *find(uint32_t ord) {
     for (auto &s : segs)
       if (s->ord == ord) return s.get();
@@ -146,13 +156,14 @@ struct slg_batch {
   std::vector<uint32_t> h_ut_term, h_qt_uterm, h_q_term_off;
   // state + outputs
   DevBuf ut_rng, ut_tile_ub, thr_key, topk_count, lock, topk_keys, work_counter, stats;
-  DevBuf qterms, qheads;  // warp kernel
-  DevBuf scores, d_sc_off, d_ublk;  // staged scores: [S][U] offsets / first blocks
-  std::vector<std::vector<uint64_t>> h_sc_off;  // per segment
-  std::vector<std::vector<uint32_t>> h_ublk;    // per segment, U+1 entries
+  DevBuf qterms, qheads;  // warp / register kernel term tables
   bool staged = false;
   uint32_t max_terms = 0;
-  bool use_warp = false;
+  bool use_warp = false, use_reg = false;
+  uint32_t plan_docs = 0, reg_v = 8;
+  DevBuf d_hot_slot, d_hot_cols;      // register kernel: [S][U] 1 + smem slot or 0; [S][max_hot] column offsets
+  std::vector<uint32_t> n_hot;        // per segment
+  uint32_t max_hot = 0;
   DevBuf seg_hits, seg_counts;  // [S][Q][k], [S][Q]
   DevBuf out_hits, out_counts;  // merged (aliases seg buffers when S == 1)
   uint32_t n_segs_run = 0;
@@ -261,9 +272,61 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
   d.blk_max_tf = s->blk_max_tf.as<float>();
   d.nk = s->nk.as<float>();
   d.live_bits = s->live_bits.as<uint32_t>();
+  d.post_score = nullptr;
+  d.cols = nullptr;
+  d.term_col = nullptr;
+  d.col_stride = 0;
+  d.n_terms = s->n_terms;
   d.doc_count = s->doc_count;
   d.k1p1 = s->k1 + 1.0f;
   d.min_nk = host_nk(s->min_doc_len, s->avgdl, s->k1, s->b);
+
+  // resident unit-weight scores: score_tf(tf, df, doc_len, ...) of every posting, once
+  if (ix->resident_scores && s->n_blocks) {
+    SLG_CUDA(ix, s->post_score.alloc(s->n_post_padded * 4));
+    SLG_CUDA(ix, cudaMemsetAsync(s->post_score.p, 0, s->n_post_padded * 4, st));
+    slg_score_postings_kernel<<<s->n_blocks, 128, 0, st>>>(d, s->n_blocks, s->post_score.as<float>());
+    count_launch(ix);
+    SLG_CUDA(ix, cudaGetLastError());
+    d.post_score = s->post_score.as<float>();
+    // dense columns for the high-df terms, largest df first until the byte budget is spent
+    if (ix->dense_den && s->doc_count) {
+      const uint64_t stride = align_up((uint64_t)s->doc_count, 2048) + 2048;  // a whole tile past the end stays in bounds and zero
+      std::vector<uint32_t> cand;
+      for (uint64_t t = 0; t < s->n_terms; t++) {
+        const uint64_t df = s->h_df[t];
+        if (df >= ix->dense_min_df && df * ix->dense_den >= s->doc_count) cand.push_back((uint32_t)t);
+      }
+      std::sort(cand.begin(), cand.end(), [&](uint32_t a, uint32_t b2) { return s->h_df[a] != s->h_df[b2] ? s->h_df[a] > s->h_df[b2] : a < b2; });
+      const uint64_t max_cols = ix->max_column_bytes / (stride * 4);
+      if (cand.size() > max_cols) cand.resize(max_cols);
+      if (!cand.empty()) {
+        std::vector<int32_t> tcol(s->n_terms, -1);
+        for (size_t c = 0; c < cand.size(); c++) tcol[cand[c]] = (int32_t)c;
+        DevBuf d_terms;
+        SLG_CUDA(ix, d_terms.alloc(cand.size() * 4));
+        SLG_CUDA(ix, cudaMemcpyAsync(d_terms.p, cand.data(), cand.size() * 4, cudaMemcpyHostToDevice, st));
+        SLG_CUDA(ix, s->term_col.alloc(s->n_terms * 4));
+        SLG_CUDA(ix, cudaMemcpyAsync(s->term_col.p, tcol.data(), s->n_terms * 4, cudaMemcpyHostToDevice, st));
+        SLG_CUDA(ix, s->cols.alloc(cand.size() * stride * 4));
+        SLG_CUDA(ix, cudaMemsetAsync(s->cols.p, 0, cand.size() * stride * 4, st));
+        s->n_cols = (uint32_t)cand.size();
+        s->col_stride = stride;
+        d.col_stride = stride;
+        for (size_t c0 = 0; c0 < cand.size(); c0 += 32768) {  // gridDim.y limit
+          const uint32_t nc = (uint32_t)std::min<size_t>(32768, cand.size() - c0);
+          slg_fill_columns_kernel<<<dim3(256, nc), 256, 0, st>>>(d, d_terms.as<uint32_t>() + c0, nc,
+                                                                  s->cols.as<float>() + c0 * stride);
+          count_launch(ix);
+        }
+        SLG_CUDA(ix, cudaGetLastError());
+        SLG_CUDA(ix, cudaStreamSynchronize(st));  // host vectors go out of scope
+        s->h_term_col = std::move(tcol);
+        d.cols = s->cols.as<float>();
+        d.term_col = s->term_col.as<int32_t>();
+      }
+    }
+  }
   ix->ctr.resident_bytes += s->resident();
   // replace a segment with the same ordinal
   for (auto &old : ix->segs)
@@ -437,6 +500,46 @@ int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, bool st
   }
 }
 
+template <int V>
+size_t reg_smem_bytes(uint32_t n_hot) { return (size_t)n_hot * 128 * V * 4 + (size_t)kRegWarps * reg_kernel_smem_per_warp<V>(); }
+
+// how many column slices of one tile fit next to the warps' private tiles
+uint32_t reg_max_hot(const slg_index *ix, uint32_t v) {
+  const size_t per_warp = (size_t)128 * v * 4 + kWarpCand * 8;
+  const size_t fixed = (size_t)kRegWarps * per_warp + 1024;  // + static shared and slack
+  if (ix->smem_optin <= fixed) return 0;
+  return (uint32_t)((ix->smem_optin - fixed) / ((size_t)128 * v * 4));
+}
+
+template <int V, bool P, bool S>
+int32_t launch_reg_t(slg_index *ix, const SegmentDev &sd, const RegBatchDev &rb, int max_grid) {
+  auto kern = slg_score_reg_kernel<V, P, S>;
+  const size_t smem = reg_smem_bytes<V>(rb.n_hot);
+  SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(max_grid, ix->n_sm);  // persistent: one CTA per SM, tiles from a global counter
+  kern<<<grid, kRegThreads, smem, ix->stream>>>(sd, rb);
+  SLG_CUDA(ix, cudaGetLastError());
+  return SLG_OK;
+}
+
+template <int V>
+int32_t launch_reg_v(slg_index *ix, bool prune, bool stats, const SegmentDev &sd, const RegBatchDev &rb, int grid) {
+  switch ((prune ? 2 : 0) | (stats ? 1 : 0)) {
+    case 0: return launch_reg_t<V, false, false>(ix, sd, rb, grid);
+    case 1: return launch_reg_t<V, false, true>(ix, sd, rb, grid);
+    case 2: return launch_reg_t<V, true, false>(ix, sd, rb, grid);
+    default: return launch_reg_t<V, true, true>(ix, sd, rb, grid);
+  }
+}
+
+int32_t launch_reg(slg_index *ix, uint32_t v, bool prune, bool stats, const SegmentDev &sd, const RegBatchDev &rb, int grid) {
+  switch (v) {
+    case 4: return launch_reg_v<4>(ix, prune, stats, sd, rb, grid);
+    case 16: return launch_reg_v<16>(ix, prune, stats, sd, rb, grid);
+    default: return launch_reg_v<8>(ix, prune, stats, sd, rb, grid);
+  }
+}
+
 }  // namespace
 
 /* ================================================================================================ C ABI */
@@ -496,7 +599,7 @@ int32_t slg_configure(slg_index_t *ix, uint32_t tile_docs, uint32_t ctas_per_sm,
     if (sub_docs % 128 || sub_docs > 8192) return fail(ix, SLG_ERR_INVALID, "sub_docs must be a multiple of 128 <= 8192");
     ix->sub_docs = sub_docs;
   }
-  if ((kernel_choice & 0xFF) > 2) return fail(ix, SLG_ERR_INVALID, "kernel_choice must be 0, 1 or 2 (+256 = no staging)");
+  if ((kernel_choice & 0xFF) > 3) return fail(ix, SLG_ERR_INVALID, "kernel_choice must be 0..3 (+256 = score postings in place)");
   ix->kernel_choice = kernel_choice & 0xFF;
   ix->staging = !(kernel_choice & 256u);
   if (tile_docs) {
@@ -504,6 +607,20 @@ int32_t slg_configure(slg_index_t *ix, uint32_t tile_docs, uint32_t ctas_per_sm,
     ix->tile_docs = tile_docs;
   }
   ix->ctas_per_sm = ctas_per_sm;
+  return SLG_OK;
+}
+
+int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
+  if (!ix || !name) return SLG_ERR_INVALID;
+  const std::string n(name);
+  if (n == "resident_scores") ix->resident_scores = value != 0;
+  else if (n == "dense_den") ix->dense_den = (uint32_t)value;
+  else if (n == "dense_min_df") ix->dense_min_df = (uint32_t)value;
+  else if (n == "max_column_bytes") ix->max_column_bytes = value;
+  else if (n == "reg_tile_v") {
+    if (value != 4 && value != 8 && value != 16) return fail(ix, SLG_ERR_INVALID, "reg_tile_v must be 4, 8 or 16");
+    ix->reg_tile_v = (uint32_t)value;
+  } else return fail(ix, SLG_ERR_INVALID, "unknown option '%s'", name);
   return SLG_OK;
 }
 
@@ -643,6 +760,14 @@ int32_t slg_segment_stats(const slg_index_t *ixc, uint32_t segment_ord, float *a
   if (min_doc_len) *min_doc_len = s->min_doc_len;
   if (n_postings) *n_postings = s->n_postings;
   return SLG_OK;
+}
+
+int32_t slg_term_has_column(const slg_index_t *ixc, uint32_t segment_ord, uint32_t term_id) {
+  slg_index *ix = const_cast<slg_index *>(ixc);
+  if (!ix) return SLG_ERR_INVALID;
+  Segment *s = ix->find(segment_ord);
+  if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
+  return term_id < s->h_term_col.size() && s->h_term_col[term_id] >= 0 ? 1 : 0;
 }
 
 /* ---- fast-field columns + filters ---- */
@@ -941,52 +1066,61 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   SLG_CUDA(ix, cudaMemcpyAsync(bt->d_pack.p, hp, pos, cudaMemcpyHostToDevice, ix->stream));
   ix->ctr.last_h2d_bytes = pos;
 
-  bt->use_warp = ix->kernel_choice == 2 || (ix->kernel_choice == 0 && k <= kWarpMaxK && bt->max_terms <= kWarpMaxTerms);
-  if (bt->use_warp && (k > kWarpMaxK || bt->max_terms > kWarpMaxTerms))
+  const bool small = k <= kWarpMaxK && bt->max_terms <= kWarpMaxTerms;
+  bool all_scores = ix->staging;
+  for (auto &s : ix->segs) all_scores = all_scores && (s->post_score.p != nullptr || s->n_blocks == 0);
+  // register-tile kernel: plain OR queries (no matcher), small k, few terms, resident scores
+  bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && all_scores);
+  if (bt->use_reg && !(small && !matcher && all_scores))
+    return fail(ix, SLG_ERR_UNSUPPORTED, "the register kernel handles plain OR queries, k <= %u, <= %u terms per query, resident scores",
+                kWarpMaxK, kWarpMaxTerms);
+  bt->use_warp = !bt->use_reg && (ix->kernel_choice == 2 || (ix->kernel_choice == 0 && small));
+  if (bt->use_warp && !small)
     return fail(ix, SLG_ERR_UNSUPPORTED, "the warp kernel handles k <= %u and <= %u terms per query", kWarpMaxK, kWarpMaxTerms);
-  const uint32_t plan_docs = bt->use_warp ? ix->sub_docs : ix->tile_docs;
+  bt->plan_docs = bt->use_reg ? 128u * ix->reg_tile_v : (bt->use_warp ? ix->sub_docs : ix->tile_docs);
+  const uint32_t plan_docs = bt->plan_docs;
   uint32_t max_tiles = 0;
   for (auto &s : ix->segs) max_tiles = std::max(max_tiles, (s->doc_count + plan_docs - 1) / plan_docs);
   max_tiles = std::max(max_tiles, 1u);
-  if (bt->use_warp) {
+  if (bt->use_warp || bt->use_reg) {
+    static_assert(sizeof(QTerm) == sizeof(RTerm) && sizeof(QHead) == sizeof(RHead), "term tables share one allocation");
     SLG_CUDA(ix, bt->qterms.alloc((size_t)n_queries * kWarpMaxTerms * sizeof(QTerm)));
     SLG_CUDA(ix, bt->qheads.alloc((size_t)n_queries * sizeof(QHead)));
-    // staged scores: exhaustive mode without a matcher decodes + scores each unique term once per batch
-    bt->staged = ix->staging && !matcher && exec == SLG_EXEC_BM25 && bt->U > 0;
-    if (bt->staged) {
-      uint64_t max_slots = 0;
-      size_t nseg = ix->segs.size();
-      bt->h_sc_off.resize(nseg);
-      bt->h_ublk.resize(nseg);
-      std::vector<uint64_t> all_off;
-      std::vector<uint32_t> all_blk;
-      for (size_t si = 0; si < nseg; si++) {
-        const Segment *sg = ix->segs[si].get();
-        auto &off = bt->h_sc_off[si];
-        auto &blk = bt->h_ublk[si];
-        off.resize(bt->U);
-        blk.resize(bt->U + 1);
-        uint64_t pos = 0, nb = 0;
-        for (uint32_t u = 0; u < bt->U; u++) {
-          uint32_t df = ut[u] < sg->n_terms ? sg->h_df[ut[u]] : 0;
-          off[u] = pos;
-          blk[u] = (uint32_t)nb;
-          pos += align_up(df, kTermAlign);
-          nb += (df + kStageChunk - 1) / kStageChunk;
-        }
-        blk[bt->U] = (uint32_t)nb;
-        max_slots = std::max(max_slots, pos + 1024);
-        all_off.insert(all_off.end(), off.begin(), off.end());
-        all_blk.insert(all_blk.end(), blk.begin(), blk.end());
+    // the (doc, score) stream form of the warp kernel: no matcher, resident scores
+    bt->staged = bt->use_warp && all_scores && !matcher && bt->U > 0;
+  }
+  if (bt->use_reg) {
+    // per segment: the columns this batch uses most (by query-term instances) get a shared-memory slot
+    bt->reg_v = ix->reg_tile_v;
+    bt->max_hot = reg_max_hot(ix, bt->reg_v);
+    const size_t nseg = ix->segs.size();
+    std::vector<uint32_t> inst(bt->U, 0);
+    for (uint32_t u : qt_u) inst[u]++;
+    std::vector<uint32_t> hot_slot(nseg * std::max(bt->U, 1u), 0);
+    std::vector<uint64_t> hot_cols(nseg * std::max(bt->max_hot, 1u), 0);
+    bt->n_hot.assign(nseg, 0);
+    for (size_t si = 0; si < nseg; si++) {
+      const Segment *sg = ix->segs[si].get();
+      if (sg->h_term_col.empty() || !bt->max_hot) continue;
+      std::vector<uint32_t> cand;
+      for (uint32_t u = 0; u < bt->U; u++)
+        if (ut[u] < sg->h_term_col.size() && sg->h_term_col[ut[u]] >= 0) cand.push_back(u);
+      std::sort(cand.begin(), cand.end(), [&](uint32_t a, uint32_t b2) { return inst[a] != inst[b2] ? inst[a] > inst[b2] : a < b2; });
+      // a column named by a single query gains nothing from staging
+      while (!cand.empty() && inst[cand.back()] < 2) cand.pop_back();
+      if (cand.size() > bt->max_hot) cand.resize(bt->max_hot);
+      for (size_t h = 0; h < cand.size(); h++) {
+        hot_slot[si * bt->U + cand[h]] = (uint32_t)h + 1;
+        hot_cols[si * bt->max_hot + h] = (uint64_t)sg->h_term_col[ut[cand[h]]] * sg->col_stride;
       }
-      SLG_CUDA(ix, bt->scores.alloc(max_slots * 4));
-      SLG_CUDA(ix, bt->d_sc_off.alloc(all_off.size() * 8));
-      SLG_CUDA(ix, bt->d_ublk.alloc(all_blk.size() * 4));
-      SLG_CUDA(ix, cudaMemcpyAsync(bt->d_sc_off.p, all_off.data(), all_off.size() * 8, cudaMemcpyHostToDevice, ix->stream));
-      SLG_CUDA(ix, cudaMemcpyAsync(bt->d_ublk.p, all_blk.data(), all_blk.size() * 4, cudaMemcpyHostToDevice, ix->stream));
-      SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));
-      ix->ctr.last_h2d_bytes += all_off.size() * 8 + all_blk.size() * 4;
+      bt->n_hot[si] = (uint32_t)cand.size();
     }
+    SLG_CUDA(ix, bt->d_hot_slot.alloc(hot_slot.size() * 4));
+    SLG_CUDA(ix, bt->d_hot_cols.alloc(hot_cols.size() * 8));
+    SLG_CUDA(ix, cudaMemcpyAsync(bt->d_hot_slot.p, hot_slot.data(), hot_slot.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+    SLG_CUDA(ix, cudaMemcpyAsync(bt->d_hot_cols.p, hot_cols.data(), hot_cols.size() * 8, cudaMemcpyHostToDevice, ix->stream));
+    SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));  // host vectors go out of scope
+    ix->ctr.last_h2d_bytes += hot_slot.size() * 4 + hot_cols.size() * 8;
   }
   size_t S = ix->segs.size();
   SLG_CUDA(ix, bt->ut_rng.alloc((size_t)std::max(bt->U, 1u) * (max_tiles + 1) * 4));
@@ -1049,7 +1183,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
     bd.n_uterms = bt->U;
     bd.k = k;
     bd.cap = bt->cap;
-    const uint32_t plan_docs = bt->use_warp ? ix->sub_docs : ix->tile_docs;
+    const uint32_t plan_docs = bt->plan_docs;
     bd.tile_docs = plan_docs;
     bd.n_tiles = std::max(1u, (s->doc_count + plan_docs - 1) / plan_docs);
     bd.thr_key = bt->thr_key.as<unsigned long long>();
@@ -1069,35 +1203,58 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
     SLG_CUDA(ix, cudaMemsetAsync(bd.work_counter, 0, 4, st));
     if (bt->U && s->doc_count) {
       uint64_t n = (uint64_t)bt->U * (bd.n_tiles + 1);
-      slg_plan_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, bd);
-      count_launch(ix);
-      if (prune) {
-        uint64_t n2 = (uint64_t)bt->U * bd.n_tiles;
-        slg_plan_bounds_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(s->dev, bd);
+      uint64_t n2 = (uint64_t)bt->U * bd.n_tiles;
+      if (bt->use_reg) {  // transposed tables: one row per tile boundary
+        slg_plan_ranges_t_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, bd, prune || bt->want_stats);
         count_launch(ix);
-      }
-      const uint64_t *d_sc_off = nullptr;
-      if (bt->use_warp) {
-        if (bt->staged) {
-          d_sc_off = bt->d_sc_off.as<uint64_t>() + (size_t)si * bt->U;
-          const uint32_t *d_ublk = bt->d_ublk.as<uint32_t>() + (size_t)si * (bt->U + 1);
-          const uint32_t nblk = bt->h_ublk[si][bt->U];
-          if (nblk) {
-            slg_stage_scores_kernel<<<nblk, 256, 0, st>>>(s->dev, bd.ut_term, d_ublk, d_sc_off, bt->U, bt->scores.as<float>());
-            count_launch(ix);
-          }
+        if (prune) {
+          slg_plan_bounds_t_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(s->dev, bd);
+          count_launch(ix);
         }
-        slg_build_qterms_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, bd, d_sc_off, bt->qterms.as<QTerm>(), bt->qheads.as<QHead>());
+      } else {
+        slg_plan_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, bd);
+        count_launch(ix);
+        if (prune) {
+          slg_plan_bounds_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(s->dev, bd);
+          count_launch(ix);
+        }
+      }
+      if (bt->use_reg) {
+        slg_build_rterms_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, bd, bt->d_hot_slot.as<uint32_t>() + (size_t)si * bt->U,
+                                                                  bt->qterms.as<RTerm>(), bt->qheads.as<RHead>());
+        count_launch(ix);
+      } else if (bt->use_warp) {
+        slg_build_qterms_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, bd, bt->qterms.as<QTerm>(), bt->qheads.as<QHead>());
         count_launch(ix);
       }
       SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));
-      if (bt->use_warp) {
+      if (bt->use_reg) {
+        RegBatchDev rb{};
+        rb.rterms = bt->qterms.as<RTerm>();
+        rb.rheads = bt->qheads.as<RHead>();
+        rb.rng_t = bd.ut_rng;
+        rb.ub_t = bd.ut_tile_ub;
+        rb.hot_cols = bt->d_hot_cols.as<uint64_t>() + (size_t)si * bt->max_hot;
+        rb.filter_bits = bd.filter_bits;
+        rb.n_queries = Q;
+        rb.n_uterms = bt->U;
+        rb.k = k;
+        rb.n_tiles = bd.n_tiles;
+        rb.n_hot = bt->n_hot[si];
+        rb.thr_key = bd.thr_key;
+        rb.topk_count = bd.topk_count;
+        rb.lock = bd.lock;
+        rb.topk_keys = bd.topk_keys;
+        rb.work_counter = bd.work_counter;
+        rb.stats = bd.stats;
+        rc = launch_reg(ix, bt->reg_v, prune, bt->want_stats, s->dev, rb, (int)bd.n_tiles);
+      } else if (bt->use_warp) {
         WarpBatchDev wb{};
         wb.qterms = bt->qterms.as<QTerm>();
         wb.qheads = bt->qheads.as<QHead>();
         wb.rng = bd.ut_rng;
         wb.sub_ub = bd.ut_tile_ub;
-        wb.scores = bt->scores.as<float>();
+        wb.scores = s->dev.post_score;
         wb.filter_bits = bd.filter_bits;
         wb.n_queries = Q;
         wb.k = k;

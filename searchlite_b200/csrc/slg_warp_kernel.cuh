@@ -14,14 +14,12 @@
 //   merge       = as in the CTA kernel: per-query lock, sort(local ∪ global)[:k], publish the new
 //                 k-th key as the query's threshold
 //
-// Decode + score is split from accumulation (STAGED): a batch of 4096 Zipfian queries names the
-// same head terms over and over (sum of df over term INSTANCES is ~17x the sum over UNIQUE
-// terms), so slg_stage_scores_kernel decodes every posting of every unique term of the batch
-// once — tf byte (or wide tf), norm gather, the reference's BM25 arithmetic — into a per-batch
-// f32 stream laid out like the posting array, and the accumulate loop of each (query, tile)
-// then only streams (doc, score) pairs out of L2 and adds them.  The per-query weight is applied
-// at accumulate time (score_tf: base * weight, query/wand.rs:284-285), so results are bit-identical
-// to computing the contribution in place.
+// Decode + score is split from accumulation (STAGED): the unit-weight BM25 contribution of every
+// posting is computed once at segment load (seg.post_score, slg_score_postings_kernel: tf byte or
+// wide tf, norm gather, the reference's arithmetic) into an f32 stream laid out like the posting
+// array, and the accumulate loop of each (query, tile) then only streams (doc, score) pairs and
+// adds them.  The per-query weight is applied at accumulate time (score_tf: base * weight,
+// query/wand.rs:284-285), so results are bit-identical to computing the contribution in place.
 #pragma once
 #include "slg_kernels.cuh"
 
@@ -53,7 +51,7 @@ struct WarpBatchDev {
   const QHead *qheads;   // [Q]
   const uint32_t *rng;   // [U][n_sub+1]
   const float *sub_ub;   // [U][n_sub]   (PRUNE)
-  const float *scores;   // staged unit-weight contributions (STAGED)
+  const float *scores;   // seg.post_score: resident unit-weight contributions (STAGED)
   const uint32_t *const *filter_bits;
   uint32_t n_queries, k, sub_docs, n_sub, n_groups;
   unsigned long long *thr_key;
@@ -63,57 +61,8 @@ struct WarpBatchDev {
   unsigned long long *stats;
 };
 
-// ------------------------------------------------------------------------------------------------
-// Stage: decode + score every posting of every unique term of the batch, once.
-// One CTA of 256 threads per chunk of kStageChunk postings of one unique term (8 postings per
-// thread: two 128-bit doc loads, one 64-bit tf load, eight norm gathers in flight, two 128-bit
-// score stores); uchunk[u] = first chunk of unique term u.
-constexpr uint32_t kStageChunk = 2048;
-__global__ void __launch_bounds__(256) slg_stage_scores_kernel(SegmentDev seg, const uint32_t *ut_term, const uint32_t *uchunk,
-                                                                const uint64_t *sc_off, uint32_t n_uterms, float *scores) {
-  const uint32_t chunk = blockIdx.x;
-  __shared__ uint32_t s_u;
-  if (threadIdx.x == 0) {
-    uint32_t lo = 0, hi = n_uterms;  // last u with uchunk[u] <= chunk
-    while (lo + 1 < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (uchunk[mid] <= chunk) lo = mid;
-      else hi = mid;
-    }
-    s_u = lo;
-  }
-  __syncthreads();
-  const uint32_t u = s_u;
-  const uint32_t term = ut_term[u];
-  const uint32_t df = seg.term_df[term];
-  const uint64_t base = seg.term_start[term];
-  const uint64_t wide = seg.term_wide[term];
-  const float idf = seg.term_idf[term], k1p1 = seg.k1p1;
-  const uint32_t *dptr = seg.post_doc + base;
-  const uint8_t *fptr = seg.post_tf + base;
-  float *out = scores + sc_off[u];
-  const uint32_t i = (chunk - uchunk[u]) * kStageChunk + threadIdx.x * 8;
-  if (i >= df) return;
-  // the padded layout (16-posting alignment + tail slack) makes the full 8-wide loads safe
-  const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(dptr + i));
-  const uint4 d1 = __ldg(reinterpret_cast<const uint4 *>(dptr + i + 4));
-  const uint2 f = __ldg(reinterpret_cast<const uint2 *>(fptr + i));
-  const uint32_t dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-  float nkv[8], sc[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) nkv[j] = (i + j < df) ? __ldg(seg.nk + dd[j]) : 1.0f;
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    uint32_t tf = ((j < 4 ? f.x : f.y) >> (8 * (j & 3))) & 255u;
-    if (tf == 255u && wide != ~0ull && i + j < df) tf = seg.tf_wide[wide + i + j];
-    sc[j] = bm25_contrib_fast(tf, idf, k1p1, nkv[j], 1.0f);
-  }
-  *reinterpret_cast<float4 *>(out + i) = make_float4(sc[0], sc[1], sc[2], sc[3]);
-  *reinterpret_cast<float4 *>(out + i + 4) = make_float4(sc[4], sc[5], sc[6], sc[7]);
-}
-
 // resolve the batch's query terms against one segment (runs once per segment per batch)
-__global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, const uint64_t *sc_off, QTerm *qterms, QHead *qheads) {
+__global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qterms, QHead *qheads) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= bt.n_queries) return;
   const uint32_t qi = bt.q_order[slot];
@@ -136,8 +85,8 @@ __global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, const uint6
     if (t < nt) {
       const uint32_t u = bt.qt_uterm[t0 + t];
       const uint32_t term = bt.ut_term[u];
-      r.base = seg.term_start[term];
-      r.sc_base = sc_off ? sc_off[u] : 0;
+      r.base = term < seg.n_terms ? seg.term_start[term] : 0;
+      r.sc_base = r.base;  // seg.post_score is laid out like seg.post_doc
       r.term = term;
       r.uterm = u;
       r.weight = bt.qt_weight[t0 + t];

@@ -78,6 +78,7 @@ EXPORTED_SYMBOLS = [
     "slg_filter_bitmap", "slg_search_batch", "slg_batch_prepare", "slg_batch_run", "slg_batch_fetch",
     "slg_batch_device_results", "slg_batch_free", "slg_merge_gathered", "slg_load_vectors", "slg_rerank",
     "slg_get_counters", "slg_version", "slg_batch_copy_results_device", "slg_get_stream", "slg_selftest_div", "slg_batch_enable_stats",
+    "slg_set_option", "slg_term_has_column",
 ]
 
 
@@ -122,6 +123,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_get_stream": [vp, C.POINTER(vp)],
         "slg_selftest_div": [vp, u64, u64, C.POINTER(u64)],
         "slg_batch_enable_stats": [vp, i32],
+        "slg_set_option": [vp, C.c_char_p, u64],
+        "slg_term_has_column": [vp, u32, u32],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -312,9 +315,10 @@ class GpuIndex:
     """Device-resident index: the GPU stand-in for Index::reader() + IndexReader::search on the
     BM25 top-k path.  One instance owns one CUDA device/stream."""
 
-    KERNEL = {"auto": 0, "cta": 1, "warp": 2, "warp-inplace": 2 + 256, "auto-inplace": 256}
+    KERNEL = {"auto": 0, "cta": 1, "warp": 2, "reg": 3, "warp-inplace": 2 + 256, "auto-inplace": 256}
 
-    def __init__(self, device: int = 0, tile_docs: int = 0, ctas_per_sm: int = 0, sub_docs: int = 0, kernel: str = "auto"):
+    def __init__(self, device: int = 0, tile_docs: int = 0, ctas_per_sm: int = 0, sub_docs: int = 0, kernel: str = "auto",
+                 options: Optional[dict] = None):
         self.lib = load_library()
         h = C.c_void_p()
         rc = self.lib.slg_open(device, C.byref(h))
@@ -325,6 +329,15 @@ class GpuIndex:
         self._keep = []
         if tile_docs or ctas_per_sm or sub_docs or kernel != "auto":
             self._check(self.lib.slg_configure(self.handle, tile_docs, ctas_per_sm, sub_docs, self.KERNEL[kernel]))
+        for name, value in (options or {}).items():
+            self.set_option(name, value)
+
+    def set_option(self, name: str, value: int) -> None:
+        """residency / tuning options (slg_set_option); applies to segments loaded afterwards"""
+        self._check(self.lib.slg_set_option(self.handle, name.encode(), int(value)))
+
+    def term_has_column(self, segment_ord: int, term_id: int) -> bool:
+        return bool(self._check(self.lib.slg_term_has_column(self.handle, segment_ord, int(term_id))))
 
     def _check(self, rc: int) -> int:
         if rc < 0:

@@ -56,3 +56,37 @@ def or_queries(term_lists, weights=None) -> QueryBatch:
 
 def hits_to_list(hits, counts, q: int = 0):
     return [(int(h["doc_id"]), f32_bits(h["score"])) for h in hits[q][: int(counts[q])]]
+
+
+def canonical_batch(gi, qb: QueryBatch, segment_ord: int = 0) -> QueryBatch:
+    """The register-tile kernel's summation order (include/searchlite_gpu.h, slg_set_option): per query
+    the terms WITHOUT a dense column first, then the terms WITH one, both in query order.  The oracle's
+    `bm25` mode on this permuted batch is what that kernel must reproduce bit for bit."""
+    terms = qb.terms.copy()
+    cache = {}
+    for q in range(qb.n_queries):
+        a, b = int(qb.term_off[q]), int(qb.term_off[q + 1])
+        rows = terms[a:b].copy()
+        has = []
+        for t in rows["term_id"].tolist():
+            if t not in cache:
+                cache[t] = False if t == 0xFFFFFFFF else gi.term_has_column(segment_ord, t)
+            has.append(cache[t])
+        order = [i for i, h in enumerate(has) if not h] + [i for i, h in enumerate(has) if h]
+        terms[a:b] = rows[order]
+    out = QueryBatch(qb.term_off.copy(), terms)
+    out.filter_id = None if qb.filter_id is None else qb.filter_id.copy()
+    return out
+
+
+def assert_engine_parity(gi, ora, qb: QueryBatch, k: int, got, segment_ord: int = 0, exact_order: bool = False, **oracle_kw):
+    """got = (hits, counts) of the engine for plain OR batch `qb`.  Bit-exact against the oracle on the
+    engine's declared summation order, and within the 1e-5 rule against the reference (query) order."""
+    from tests.parity import assert_parity
+    ref = ora.search_batch(qb, k, "bm25", **oracle_kw)
+    if exact_order:
+        assert_parity(*ref, *got, strict=True)
+        return
+    assert_parity(*ref, *got, strict=False)
+    canon = ora.search_batch(canonical_batch(gi, qb, segment_ord), k, "bm25", **oracle_kw)
+    assert_parity(*canon, *got, strict=True)

@@ -8,12 +8,16 @@ import pytest
 from searchlite_b200 import GpuIndex, QueryBatch, SearchliteGpuError, synth
 from searchlite_b200.engine import (FILTER_DTYPE, F_AND, F_F64_RANGE, F_I64_RANGE, F_KEYWORD_EQ, F_KEYWORD_IN, F_NOT, F_OR,
                                     HIT_DTYPE)
-from tests.helpers import f32_bits, golden, hits_to_list, or_queries, segment_from_postings, token_corpus
+from tests.helpers import (assert_engine_parity, f32_bits, golden, hits_to_list, or_queries, segment_from_postings,
+                           token_corpus)
 from tests.parity import assert_parity
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = ["cta", "warp", "warp-inplace"]
+MATCHER_KERNELS = ["cta", "warp", "warp-inplace"]      # Bool queries: query-order kernels
+KERNELS = MATCHER_KERNELS + ["reg", "reg-dense"]       # plain OR queries: also the register-tile kernel
+# reg-dense: every term with >= 2 postings and df >= N/64 gets a column (exercises the column path on tiny corpora)
+REG_DENSE = {"dense_min_df": 2, "dense_den": 64}
 
 
 def _oracle(seg, **kw):
@@ -22,9 +26,18 @@ def _oracle(seg, **kw):
 
 
 def _gpu(seg, kernel="auto", k1=0.9, b=0.4, **kw):
-    gi = GpuIndex(0, kernel=kernel, **kw)
+    if kernel == "reg-dense":
+        gi = GpuIndex(0, kernel="reg", options=REG_DENSE, **kw)
+    else:
+        gi = GpuIndex(0, kernel=kernel, **kw)
     cols = gi.load_segment(seg, k1=k1, b=b)
     return gi, cols
+
+
+def _check(gi, ora, qb, k, got, kernel, **oracle_kw):
+    """query-order kernels: bit-exact vs the oracle; register-tile kernel: bit-exact vs the oracle on its
+    declared term order + 1e-5 rule vs the query order"""
+    assert_engine_parity(gi, ora, qb, k, got, exact_order=kernel in MATCHER_KERNELS, **oracle_kw)
 
 
 def node(op, column=-1, i=(0, 0), f=(0.0, 0.0), nc=0, v=(0, 0)):
@@ -34,7 +47,7 @@ def node(op, column=-1, i=(0, 0), f=(0.0, 0.0), nc=0, v=(0, 0)):
 
 
 # ---- golden fixtures (tests/golden, made by tests/golden/make_golden.py) through the C ABI ----------
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", MATCHER_KERNELS + ["reg"])
 def test_reference_literal_known_answer(kernel):
     """query/wand.rs:969-1011 literal postings; expected bits frozen in wand_literal.json"""
     g = golden("wand_literal.json")
@@ -47,7 +60,7 @@ def test_reference_literal_known_answer(kernel):
     gi.close()
 
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", MATCHER_KERNELS + ["reg"])  # no term of this corpus reaches the default column cutoff
 def test_small_corpus_topk_matches_golden_bits(kernel):
     g = golden("small_topk.json")
     seg = segment_from_postings([(p["docs"], p["tfs"]) for p in g["postings"]], g["field_lengths"], g["total_tokens"])
@@ -81,10 +94,8 @@ def test_empty_absent_and_ragged_queries(kernel):
     qb = or_queries([[], [0xFFFFFFFF], [2], [3], [5, 3], [0, 1, 2, 3, 4], [1], [999]])
     gi, _ = _gpu(seg, kernel)
     for k in (1, 3, 11):
-        ref = ora.search_batch(qb, k, "bm25")
         for mode in ("bm25", "wand", "bmw"):
-            got = gi.search_batch(qb, k, mode)
-            assert_parity(*ref, *got, strict=True)
+            _check(gi, ora, qb, k, gi.search_batch(qb, k, mode), kernel)
     h, c = gi.search_batch(qb, 3, "bm25")
     assert c.tolist()[:2] == [0, 0] and c[3] == 0 and c[4] == 0 and c[7] == 0
     # unused output slots are marked invalid
@@ -117,11 +128,10 @@ def test_large_k_goes_through_the_cta_kernel(k):
     seg = synth.generate_segment(spec, "cpu")
     qb = synth.generate_queries(40, spec.vocab, seed=6, min_rank=2)
     ora = _oracle(seg)
-    ref = ora.search_batch(qb, k, "bm25")
     gi, _ = _gpu(seg)
     for mode in ("bm25", "bmw"):
         got = gi.search_batch(qb, k, mode)
-        assert_parity(*ref, *got, strict=True)
+        assert_engine_parity(gi, ora, qb, k, got, exact_order=k > 32)  # k <= 32 runs the register-tile kernel
     gi.close()
 
 
@@ -129,11 +139,13 @@ def test_large_k_goes_through_the_cta_kernel(k):
 def test_many_terms_per_query(kernel):
     spec = synth.CorpusSpec(n_docs=20_000, vocab=3_000, seed=15, len_lo=20, len_hi=60)
     seg = synth.generate_segment(spec, "cpu")
-    n_terms = 8 if kernel.startswith("warp") else 40
+    n_terms = 40 if kernel == "cta" else 8
     qb = synth.generate_queries(30, spec.vocab, seed=16, min_terms=n_terms, max_terms=n_terms, min_rank=2)
-    ref = _oracle(seg).search_batch(qb, 11, "bm25")
     gi, _ = _gpu(seg, kernel)
-    assert_parity(*ref, *gi.search_batch(qb, 11, "bm25"), strict=True)
+    _check(gi, _oracle(seg), qb, 11, gi.search_batch(qb, 11, "bm25"), kernel)
+    if kernel != "cta":
+        with pytest.raises(SearchliteGpuError):  # an explicit kernel choice that cannot hold the batch is an error
+            gi.search_batch(synth.generate_queries(3, spec.vocab, seed=18, min_terms=9, max_terms=9, min_rank=2), 11, "bm25")
     gi.close()
     if kernel == "warp":
         gi, _ = _gpu(seg, "auto")  # more terms than the warp kernel holds: automatic choice must fall to the CTA kernel
@@ -151,10 +163,10 @@ def test_weights_and_duplicate_keys(kernel):
     tl = [rng.choice(np.arange(1, 400), size=rng.integers(1, 6), replace=False).tolist() for _ in range(60)]
     w = [[float(np.float32(rng.choice([0.5, 1.0, 2.0, 3.25, 0.1]))) for _ in t] for t in tl]
     qb = or_queries(tl, w)
-    ref = _oracle(seg).search_batch(qb, 11, "bm25")
+    ora = _oracle(seg)
     gi, _ = _gpu(seg, kernel)
     for mode in ("bm25", "wand", "bmw"):
-        assert_parity(*ref, *gi.search_batch(qb, 11, mode), strict=True)
+        _check(gi, ora, qb, 11, gi.search_batch(qb, 11, mode), kernel)
     gi.close()
 
 
@@ -172,10 +184,11 @@ def test_wide_term_frequencies(kernel):
     tf1 = rng.integers(1, 4, size=700)
     lens = rng.integers(50, 400, size=n)
     seg = segment_from_postings([(d0.tolist(), tf0.tolist()), (d1.tolist(), tf1.tolist())], lens.tolist())
-    ref = _oracle(seg).search_batch(or_queries([[0], [0, 1], [1, 0]]), 11, "bm25")
+    ora = _oracle(seg)
+    qb = or_queries([[0], [0, 1], [1, 0]])
     gi, _ = _gpu(seg, kernel)
     for mode in ("bm25", "bmw"):
-        assert_parity(*ref, *gi.search_batch(or_queries([[0], [0, 1], [1, 0]]), 11, mode), strict=True)
+        _check(gi, ora, qb, 11, gi.search_batch(qb, 11, mode), kernel)
     gi.close()
 
 
@@ -207,11 +220,11 @@ def test_deleted_docs(kernel):
     gi, _ = _gpu(seg, kernel)
     assert gi.segment_stats(0)["live_docs"] == ora.live_docs == float(spec.n_docs - len(seg.deleted_docs))
     for mode in ("bm25", "wand", "bmw"):
-        assert_parity(*ref, *gi.search_batch(qb, 11, mode), strict=True)
+        _check(gi, ora, qb, 11, gi.search_batch(qb, 11, mode), kernel)
     gi.close()
 
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", MATCHER_KERNELS + ["auto"])
 def test_bool_matcher_literal(kernel):
     """tests/query_ast.rs:52-58 style corpus"""
     seg = token_corpus([[0, 1], [0, 2], [1, 2], [0, 1, 2], [3]], 4)
@@ -228,7 +241,7 @@ def test_bool_matcher_literal(kernel):
     gi.close()
 
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", MATCHER_KERNELS + ["auto"])
 def test_bool_matcher_random(kernel):
     """C4 shape: Bool{must:[t1,t2(,t3)]} executed as OR-scan + reject (api/reader.rs:1527-1563)"""
     spec = synth.CorpusSpec(n_docs=30_000, vocab=2_000, seed=41, len_lo=20, len_hi=80)
@@ -289,7 +302,7 @@ def test_filter_bitmaps_match_oracle_literal():
     gi.close()
 
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", MATCHER_KERNELS + ["auto"])
 def test_filtered_search_c4_shape(kernel):
     """C4: Bool{must} + root filter And[KeywordEq(lang), I64Range(year)] at three selectivities"""
     spec = synth.CorpusSpec(n_docs=40_000, vocab=3_000, seed=51, len_lo=20, len_hi=80)
@@ -326,7 +339,8 @@ def test_filtered_search_c4_shape(kernel):
     ref_filter = ora.search_batch(plain, 11, "bm25", filter_nodes=prog0(ora.columns), strings=["EN"])
     for q in range(30):
         src = ref_filter if q % 2 else ref_nofilter
-        assert_parity(src[0][q:q + 1], src[1][q:q + 1], got[0][q:q + 1], got[1][q:q + 1], strict=True)
+        # "auto" runs plain OR queries on the register-tile kernel (its own term order): 1e-5 rule
+        assert_parity(src[0][q:q + 1], src[1][q:q + 1], got[0][q:q + 1], got[1][q:q + 1], strict=kernel != "auto")
     gi.close()
 
 
@@ -337,12 +351,15 @@ def test_post_image_load_equals_csr_load():
     ora = _oracle(seg)
     img, off = ora.build_post_image()
     qb = synth.generate_queries(120, spec.vocab, seed=62, min_rank=2)
-    ref = ora.search_batch(qb, 11, "bm25")
     gi = GpuIndex(0)
     gi.load_segment_post_image(seg, img, off)
     assert gi.segment_stats(0)["n_postings"] == len(seg.post_docs)
     for mode in ("bm25", "bmw"):
-        assert_parity(*ref, *gi.search_batch(qb, 11, mode), strict=True)
+        assert_engine_parity(gi, ora, qb, 11, gi.search_batch(qb, 11, mode))
+    gi.close()
+    gi = GpuIndex(0, kernel="warp")
+    gi.load_segment_post_image(seg, img, off)
+    assert_parity(*ora.search_batch(qb, 11, "bm25"), *gi.search_batch(qb, 11, "bm25"), strict=True)
     gi.close()
     # a truncated image is an error, not a crash
     gi = GpuIndex(0)
@@ -352,10 +369,11 @@ def test_post_image_load_equals_csr_load():
 
 
 # ---- several segments in one handle: api/reader.rs:2670-2777 ----------------------------------------------
-@pytest.mark.parametrize("kernel", ["cta", "warp"])
+@pytest.mark.parametrize("kernel", ["cta", "warp", "reg"])
 def test_multi_segment_merge_order(kernel):
     from oracle import slo
     from searchlite_b200.shard import shard_ranges
+    from tests.helpers import canonical_batch
     n_docs, vocab, world = 24_000, 1_500, 3
     qb = synth.generate_queries(70, vocab, seed=72, min_rank=2)
     gi = GpuIndex(0, kernel=kernel)
@@ -364,7 +382,8 @@ def test_multi_segment_merge_order(kernel):
         spec = synth.CorpusSpec(n_docs=hi - lo, vocab=vocab, seed=71, len_lo=10, len_hi=60, segment_ord=r, doc_base=lo)
         seg = synth.generate_segment(spec, "cpu")
         gi.load_segment(seg)
-        per_seg.append(slo.OracleIndex(seg).search_batch(qb, 11, "bm25"))
+        # the register-tile kernel's term order depends on which terms have a column in THIS segment
+        per_seg.append(slo.OracleIndex(seg).search_batch(canonical_batch(gi, qb, r) if kernel == "reg" else qb, 11, "bm25"))
     got_h, got_c = gi.search_batch(qb, 11, "bm25")
     for q in range(qb.n_queries):
         want = slo.merge_hits([h[q, : c[q]] for h, c in per_seg], 11)
@@ -467,7 +486,7 @@ def test_rerank_matches_oracle_formulae(metric, bf16):
 
 
 # ---- statistics (QueryStats, query/wand.rs:45-50) -----------------------------------------------------------
-@pytest.mark.parametrize("kernel", ["cta", "warp", "warp-inplace"])
+@pytest.mark.parametrize("kernel", ["cta", "warp", "warp-inplace", "reg"])
 def test_stats_count_scored_docs_and_postings(kernel):
     spec = synth.CorpusSpec(n_docs=15_000, vocab=1_200, seed=91, len_lo=10, len_hi=50)
     seg = synth.generate_segment(spec, "cpu")
