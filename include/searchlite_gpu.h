@@ -150,25 +150,29 @@ int32_t slg_close(slg_index_t *);
 const char *slg_last_error(const slg_index_t *);
 /* tuning knobs; 0 keeps the default.  tile_docs: docs per shared-memory tile of the CTA-per-item
  * kernel (multiple of 1024); sub_docs: docs per warp-private tile of the warp-per-item kernel
- * (multiple of 128); kernel_choice: 0 = automatic (register-tile kernel for plain OR queries with
+ * (multiple of 128); kernel_choice: 0 = automatic (tile-sweep kernel for plain OR queries with
  * k <= 32 and <= 8 terms per query, warp kernel for the same shape with a Bool matcher, CTA kernel
- * otherwise), 1 = CTA kernel, 2 = warp kernel, 3 = register-tile kernel; add 256 to ignore the
+ * otherwise), 1 = CTA kernel, 2 = warp kernel, 3 = tile-sweep kernel; add 256 to ignore the
  * resident per-posting scores and score postings in place. */
 int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, uint32_t sub_docs,
                       uint32_t kernel_choice);
-/* residency options for segments loaded AFTER the call:
+/* residency / tuning options; the residency ones apply to segments loaded AFTER the call:
  *   "resident_scores"  1/0  keep the unit-weight BM25 contribution of every posting in HBM (default 1)
  *   "dense_den"        n    terms with df * n >= doc_count also get a doc-indexed f32 score column
  *                           (default 8; 0 = no columns)
  *   "dense_min_df"     n    ... and df >= n (default 256)
  *   "max_column_bytes" n    byte budget of the columns of one segment, largest df first (default 24 GiB)
- *   "reg_tile_v"       4|8|16  register-tile kernel: 128 * v docs per tile (default 8)
- * Float contract: the register-tile kernel sums a doc's contributions over the query's terms
+ *   "reg_tile_v"       4|8|16  tile-sweep kernel: 128 * v docs per register tile (default 4)
+ *   "sweep_min_postings" n  tile-sweep kernel: a query without a column term whose terms hold fewer than
+ *                           n postings is scored posting-driven by the warp kernel instead of being swept
+ *                           over every tile (default 0 = doc_count / 64; 1 = sweep every query)
+ *   "seed_docs"        n    tile-sweep kernel: docs scored by the contention-free seed pass (default 16384)
+ * Float contract: the tile-sweep kernel sums a doc's contributions over the query's terms
  * WITHOUT a column first, then over the terms WITH a column, each group in query order (one left
  * fold) — brute_force (query/wand.rs:527-548) on that permutation of the query; the other kernels
  * sum in query order.  Both agree with the reference within the 1e-5 rule. */
 int32_t slg_set_option(slg_index_t *, const char *name, uint64_t value);
-/* 1 if `term_id` of the segment has a dense column (it is summed last by the register-tile kernel) */
+/* 1 if `term_id` of the segment has a dense column (it is summed last by the tile-sweep kernel) */
 int32_t slg_term_has_column(const slg_index_t *, uint32_t segment_ord, uint32_t term_id);
 
 /* ---- residency (SegmentReader::open) ---- */

@@ -23,8 +23,8 @@
 #include "slg_filter.cuh"
 #include "slg_kernels.cuh"
 #include "slg_postimage.cuh"
-#include "slg_reg_kernel.cuh"
 #include "slg_rerank.cuh"
+#include "slg_sweep_kernel.cuh"
 #include "slg_warp_kernel.cuh"
 
 using namespace slg;
@@ -90,8 +90,8 @@ struct Segment {
   float k1 = 0.9f, b = 0.4f, avgdl = 0, live_docs = 0, min_doc_len = 1;
   std::vector<uint32_t> h_df;  // host copy (query ordering, validation)
   DevBuf post_doc, post_tf, term_start, term_df, term_idf, term_max_tf, term_wide, tf_wide, term_blk, blk_max_doc,
-      blk_max_tf, nk, live_bits, post_score, cols, term_col;
-  uint32_t n_cols = 0;
+      blk_max_tf, nk, live_bits, post_score, cols, term_col, col_tmax;
+  uint32_t n_cols = 0, tmax_stride = 0;
   uint64_t col_stride = 0;
   std::vector<int32_t> h_term_col;  // host copy (tests, introspection); empty = no columns
   SegmentDev dev{};
@@ -102,7 +102,7 @@ struct Segment {
   size_t resident() const {
     return post_doc.bytes + post_tf.bytes + term_start.bytes + term_df.bytes + term_idf.bytes + term_max_tf.bytes +
            term_wide.bytes + tf_wide.bytes + term_blk.bytes + blk_max_doc.bytes + blk_max_tf.bytes + nk.bytes +
-           live_bits.bytes + post_score.bytes + cols.bytes + term_col.bytes;
+           live_bits.bytes + post_score.bytes + cols.bytes + term_col.bytes + col_tmax.bytes;
   }
 };
 
@@ -133,7 +133,9 @@ struct slg_index {
   uint32_t dense_den = 8;        // a term gets a dense column when df * dense_den >= doc_count; 0 = no columns
   uint32_t dense_min_df = 256;   // ... and df >= this
   uint64_t max_column_bytes = 24ull << 30;
-  uint32_t reg_tile_v = 8;       // register kernel: 128 * V docs per tile (4, 8 or 16)
+  uint32_t reg_tile_v = 4;       // sweep kernel: 128 * V docs per tile (4, 8 or 16)
+  uint64_t sweep_min_postings = 0;  // sweep: a query without column terms and sum(df) below this goes to the warp kernel (0 = doc_count / 64)
+  uint32_t seed_docs = 16384;    // sweep: docs of the seed pass
   Segment *find(uint32_t ord) {
     for (auto &s : segs)
       if (s->ord == ord) return s.get();
@@ -161,9 +163,14 @@ struct slg_batch {
   uint32_t max_terms = 0;
   bool use_warp = false, use_reg = false;
   uint32_t plan_docs = 0, reg_v = 8;
-  DevBuf d_hot_slot, d_hot_cols;      // register kernel: [S][U] 1 + smem slot or 0; [S][max_hot] column offsets
+  DevBuf d_hot_slot, d_hot_cols;      // sweep kernel: [S][U] 1 + smem slot or 0; [S][max_hot] column offsets
   std::vector<uint32_t> n_hot;        // per segment
   uint32_t max_hot = 0;
+  uint32_t n_heavy = 0, n_light = 0;  // sweep: slots [0, n_heavy) of q_order are swept, the rest go to the warp kernel
+  uint32_t n_rows = 0, n_light_u = 0; // rows of the sweep's range table; unique terms of the light queries
+  uint32_t sweep_tiles_max = 0, sub_tiles_max = 0;
+  DevBuf d_u_row, d_row_u, d_light_u; // [U] row or ~0; [n_rows] unique term; [n_light_u] unique term
+  DevBuf sw_recs, sw_weights, sw_ubw, sw_slot_qi, sw_rng;
   DevBuf seg_hits, seg_counts;  // [S][Q][k], [S][Q]
   DevBuf out_hits, out_counts;  // merged (aliases seg buffers when S == 1)
   uint32_t n_segs_run = 0;
@@ -317,6 +324,16 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
           const uint32_t nc = (uint32_t)std::min<size_t>(32768, cand.size() - c0);
           slg_fill_columns_kernel<<<dim3(256, nc), 256, 0, st>>>(d, d_terms.as<uint32_t>() + c0, nc,
                                                                   s->cols.as<float>() + c0 * stride);
+          count_launch(ix);
+        }
+        SLG_CUDA(ix, cudaGetLastError());
+        // exact per-512-doc maxima of every column: the tile bounds of the pruned modes
+        s->tmax_stride = (uint32_t)(stride / 512);
+        SLG_CUDA(ix, s->col_tmax.alloc(cand.size() * s->tmax_stride * 4));
+        {
+          const uint64_t warps = (uint64_t)cand.size() * s->tmax_stride;
+          slg_column_tmax_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(s->cols.as<float>(), stride, (uint32_t)cand.size(),
+                                                                                     s->tmax_stride, s->col_tmax.as<float>());
           count_launch(ix);
         }
         SLG_CUDA(ix, cudaGetLastError());
@@ -501,42 +518,44 @@ int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, bool st
 }
 
 template <int V>
-size_t reg_smem_bytes(uint32_t n_hot) { return (size_t)n_hot * 128 * V * 4 + (size_t)kRegWarps * reg_kernel_smem_per_warp<V>(); }
+size_t sweep_smem_bytes(uint32_t n_hot, uint32_t n_slots) {
+  return (size_t)n_hot * 128 * V * 4 + (size_t)((n_slots + 3u) & ~3u) * 4 + (size_t)kSweepWarps * sweep_smem_per_warp<V>();
+}
 
-// how many column slices of one tile fit next to the warps' private tiles
-uint32_t reg_max_hot(const slg_index *ix, uint32_t v) {
+// how many column slices of one tile fit next to the threshold cache and the warps' private tiles
+uint32_t sweep_max_hot(const slg_index *ix, uint32_t v, uint32_t n_slots) {
   const size_t per_warp = (size_t)128 * v * 4 + kWarpCand * 8;
-  const size_t fixed = (size_t)kRegWarps * per_warp + 1024;  // + static shared and slack
+  const size_t fixed = (size_t)kSweepWarps * per_warp + (size_t)((n_slots + 3u) & ~3u) * 4 + 1024;  // + static shared and slack
   if (ix->smem_optin <= fixed) return 0;
-  return (uint32_t)((ix->smem_optin - fixed) / ((size_t)128 * v * 4));
+  return (uint32_t)std::min<size_t>(254, (ix->smem_optin - fixed) / ((size_t)128 * v * 4));
 }
 
 template <int V, bool P, bool S>
-int32_t launch_reg_t(slg_index *ix, const SegmentDev &sd, const RegBatchDev &rb, int max_grid) {
-  auto kern = slg_score_reg_kernel<V, P, S>;
-  const size_t smem = reg_smem_bytes<V>(rb.n_hot);
+int32_t launch_sweep_t(slg_index *ix, const SegmentDev &sd, const SweepDev &sw, int grid) {
+  auto kern = slg_score_sweep_kernel<V, P, S>;
+  const size_t smem = sweep_smem_bytes<V>(sw.n_hot, sw.n_slots);
+  if (smem + 1024 > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "sweep kernel needs %zu B shared memory", smem);
   SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = std::min(max_grid, ix->n_sm);  // persistent: one CTA per SM, tiles from a global counter
-  kern<<<grid, kRegThreads, smem, ix->stream>>>(sd, rb);
+  kern<<<grid, kSweepThreads, smem, ix->stream>>>(sd, sw);
   SLG_CUDA(ix, cudaGetLastError());
   return SLG_OK;
 }
 
 template <int V>
-int32_t launch_reg_v(slg_index *ix, bool prune, bool stats, const SegmentDev &sd, const RegBatchDev &rb, int grid) {
+int32_t launch_sweep_v(slg_index *ix, bool prune, bool stats, const SegmentDev &sd, const SweepDev &sw, int grid) {
   switch ((prune ? 2 : 0) | (stats ? 1 : 0)) {
-    case 0: return launch_reg_t<V, false, false>(ix, sd, rb, grid);
-    case 1: return launch_reg_t<V, false, true>(ix, sd, rb, grid);
-    case 2: return launch_reg_t<V, true, false>(ix, sd, rb, grid);
-    default: return launch_reg_t<V, true, true>(ix, sd, rb, grid);
+    case 0: return launch_sweep_t<V, false, false>(ix, sd, sw, grid);
+    case 1: return launch_sweep_t<V, false, true>(ix, sd, sw, grid);
+    case 2: return launch_sweep_t<V, true, false>(ix, sd, sw, grid);
+    default: return launch_sweep_t<V, true, true>(ix, sd, sw, grid);
   }
 }
 
-int32_t launch_reg(slg_index *ix, uint32_t v, bool prune, bool stats, const SegmentDev &sd, const RegBatchDev &rb, int grid) {
+int32_t launch_sweep(slg_index *ix, uint32_t v, bool prune, bool stats, const SegmentDev &sd, const SweepDev &sw, int grid) {
   switch (v) {
-    case 4: return launch_reg_v<4>(ix, prune, stats, sd, rb, grid);
-    case 16: return launch_reg_v<16>(ix, prune, stats, sd, rb, grid);
-    default: return launch_reg_v<8>(ix, prune, stats, sd, rb, grid);
+    case 4: return launch_sweep_v<4>(ix, prune, stats, sd, sw, grid);
+    case 16: return launch_sweep_v<16>(ix, prune, stats, sd, sw, grid);
+    default: return launch_sweep_v<8>(ix, prune, stats, sd, sw, grid);
   }
 }
 
@@ -620,7 +639,9 @@ int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
   else if (n == "reg_tile_v") {
     if (value != 4 && value != 8 && value != 16) return fail(ix, SLG_ERR_INVALID, "reg_tile_v must be 4, 8 or 16");
     ix->reg_tile_v = (uint32_t)value;
-  } else return fail(ix, SLG_ERR_INVALID, "unknown option '%s'", name);
+  } else if (n == "sweep_min_postings") ix->sweep_min_postings = value;
+  else if (n == "seed_docs") ix->seed_docs = (uint32_t)value;
+  else return fail(ix, SLG_ERR_INVALID, "unknown option '%s'", name);
   return SLG_OK;
 }
 
@@ -1021,10 +1042,43 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bt->matcher = matcher;
   bt->U = (uint32_t)ut.size();
   bt->T = (uint32_t)qt_u.size();
-  // processing order inside a tile: most expensive queries first
+  // kernel selection
+  const bool small = k <= kWarpMaxK && bt->max_terms <= kWarpMaxTerms;
+  bool all_scores = ix->staging;
+  for (auto &s : ix->segs) all_scores = all_scores && (s->post_score.p != nullptr || s->n_blocks == 0);
+  // tile-sweep kernel: plain OR queries (no matcher), small k, few terms, resident scores
+  bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && all_scores);
+  if (bt->use_reg && !(small && !matcher && all_scores))
+    return fail(ix, SLG_ERR_UNSUPPORTED, "the sweep kernel handles plain OR queries, k <= %u, <= %u terms per query, resident scores",
+                kWarpMaxK, kWarpMaxTerms);
+  bt->use_warp = !bt->use_reg && (ix->kernel_choice == 2 || (ix->kernel_choice == 0 && small));
+  if (bt->use_warp && !small)
+    return fail(ix, SLG_ERR_UNSUPPORTED, "the warp kernel handles k <= %u and <= %u terms per query", kWarpMaxK, kWarpMaxTerms);
+
+  // processing order inside a tile: most expensive queries first.  Sweep kernel: the "heavy" queries
+  // (a column term in any segment, or enough postings that most tiles hold some) come first and are
+  // swept; the "light" rest is scored posting-driven by the warp kernel.
   std::vector<uint32_t> order(n_queries);
   for (uint32_t i = 0; i < n_queries; i++) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b2) { return q_cost[a] > q_cost[b2]; });
+  std::vector<uint8_t> heavy(n_queries, 0);
+  if (bt->use_reg) {
+    std::vector<uint8_t> u_col(bt->U, 0);
+    for (uint32_t u = 0; u < bt->U; u++)
+      for (auto &sg : ix->segs)
+        if (ut[u] < sg->h_term_col.size() && sg->h_term_col[ut[u]] >= 0) u_col[u] = 1;
+    uint64_t max_docs = 0;
+    for (auto &sg : ix->segs) max_docs = std::max<uint64_t>(max_docs, sg->doc_count);
+    for (uint32_t qi = 0; qi < n_queries; qi++) {
+      bool h = q_cost[qi] >= (ix->sweep_min_postings ? ix->sweep_min_postings : std::max<uint64_t>(1, max_docs / 64));
+      for (uint32_t t = q_off[qi]; t < q_off[qi + 1] && !h; t++) h = u_col[qt_u[t]] != 0;
+      heavy[qi] = h;
+      bt->n_heavy += h;
+    }
+    bt->n_light = n_queries - bt->n_heavy;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b2) {
+    return heavy[a] != heavy[b2] ? heavy[a] > heavy[b2] : q_cost[a] > q_cost[b2];
+  });
 
   // pack all inputs into one buffer: one H2D copy per batch
   size_t pos = 0;
@@ -1066,45 +1120,55 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   SLG_CUDA(ix, cudaMemcpyAsync(bt->d_pack.p, hp, pos, cudaMemcpyHostToDevice, ix->stream));
   ix->ctr.last_h2d_bytes = pos;
 
-  const bool small = k <= kWarpMaxK && bt->max_terms <= kWarpMaxTerms;
-  bool all_scores = ix->staging;
-  for (auto &s : ix->segs) all_scores = all_scores && (s->post_score.p != nullptr || s->n_blocks == 0);
-  // register-tile kernel: plain OR queries (no matcher), small k, few terms, resident scores
-  bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && all_scores);
-  if (bt->use_reg && !(small && !matcher && all_scores))
-    return fail(ix, SLG_ERR_UNSUPPORTED, "the register kernel handles plain OR queries, k <= %u, <= %u terms per query, resident scores",
-                kWarpMaxK, kWarpMaxTerms);
-  bt->use_warp = !bt->use_reg && (ix->kernel_choice == 2 || (ix->kernel_choice == 0 && small));
-  if (bt->use_warp && !small)
-    return fail(ix, SLG_ERR_UNSUPPORTED, "the warp kernel handles k <= %u and <= %u terms per query", kWarpMaxK, kWarpMaxTerms);
-  bt->plan_docs = bt->use_reg ? 128u * ix->reg_tile_v : (bt->use_warp ? ix->sub_docs : ix->tile_docs);
+  bt->plan_docs = bt->use_reg ? ix->sub_docs : (bt->use_warp ? ix->sub_docs : ix->tile_docs);
   const uint32_t plan_docs = bt->plan_docs;
   uint32_t max_tiles = 0;
   for (auto &s : ix->segs) max_tiles = std::max(max_tiles, (s->doc_count + plan_docs - 1) / plan_docs);
   max_tiles = std::max(max_tiles, 1u);
-  if (bt->use_warp || bt->use_reg) {
-    static_assert(sizeof(QTerm) == sizeof(RTerm) && sizeof(QHead) == sizeof(RHead), "term tables share one allocation");
-    SLG_CUDA(ix, bt->qterms.alloc((size_t)n_queries * kWarpMaxTerms * sizeof(QTerm)));
-    SLG_CUDA(ix, bt->qheads.alloc((size_t)n_queries * sizeof(QHead)));
+  const uint32_t n_warp_slots = bt->use_reg ? bt->n_light : n_queries;
+  if (bt->use_warp || (bt->use_reg && bt->n_light)) {
+    SLG_CUDA(ix, bt->qterms.alloc((size_t)n_warp_slots * kWarpMaxTerms * sizeof(QTerm)));
+    SLG_CUDA(ix, bt->qheads.alloc((size_t)n_warp_slots * sizeof(QHead)));
     // the (doc, score) stream form of the warp kernel: no matcher, resident scores
-    bt->staged = bt->use_warp && all_scores && !matcher && bt->U > 0;
+    bt->staged = all_scores && !matcher && bt->U > 0;
   }
   if (bt->use_reg) {
-    // per segment: the columns this batch uses most (by query-term instances) get a shared-memory slot
     bt->reg_v = ix->reg_tile_v;
-    bt->max_hot = reg_max_hot(ix, bt->reg_v);
     const size_t nseg = ix->segs.size();
+    // rows of the sweep's range table: the unique terms of the heavy queries; the light queries'
+    // unique terms get rows of the warp kernel's table
+    std::vector<uint32_t> u_row(std::max(bt->U, 1u), 0xFFFFFFFFu), row_u, light_u;
+    std::vector<uint8_t> u_light(bt->U, 0);
     std::vector<uint32_t> inst(bt->U, 0);
-    for (uint32_t u : qt_u) inst[u]++;
+    for (uint32_t qi = 0; qi < n_queries; qi++)
+      for (uint32_t t = q_off[qi]; t < q_off[qi + 1]; t++) {
+        const uint32_t u = qt_u[t];
+        if (heavy[qi]) {
+          inst[u]++;
+          if (u_row[u] == 0xFFFFFFFFu) {
+            u_row[u] = (uint32_t)row_u.size();
+            row_u.push_back(u);
+          }
+        } else if (!u_light[u]) {
+          u_light[u] = 1;
+          light_u.push_back(u);
+        }
+      }
+    bt->n_rows = (uint32_t)row_u.size();
+    bt->n_light_u = (uint32_t)light_u.size();
+    // per segment: the columns the heavy queries use most (by query-term instances) get a shared-memory slot
+    bt->max_hot = sweep_max_hot(ix, bt->reg_v, std::min(bt->n_heavy, kSweepMaxSlots));
     std::vector<uint32_t> hot_slot(nseg * std::max(bt->U, 1u), 0);
     std::vector<uint64_t> hot_cols(nseg * std::max(bt->max_hot, 1u), 0);
     bt->n_hot.assign(nseg, 0);
     for (size_t si = 0; si < nseg; si++) {
       const Segment *sg = ix->segs[si].get();
+      const uint32_t tile = 128u * bt->reg_v;
+      bt->sweep_tiles_max = std::max(bt->sweep_tiles_max, std::max(1u, (sg->doc_count + tile - 1) / tile));
       if (sg->h_term_col.empty() || !bt->max_hot) continue;
       std::vector<uint32_t> cand;
       for (uint32_t u = 0; u < bt->U; u++)
-        if (ut[u] < sg->h_term_col.size() && sg->h_term_col[ut[u]] >= 0) cand.push_back(u);
+        if (inst[u] && ut[u] < sg->h_term_col.size() && sg->h_term_col[ut[u]] >= 0) cand.push_back(u);
       std::sort(cand.begin(), cand.end(), [&](uint32_t a, uint32_t b2) { return inst[a] != inst[b2] ? inst[a] > inst[b2] : a < b2; });
       // a column named by a single query gains nothing from staging
       while (!cand.empty() && inst[cand.back()] < 2) cand.pop_back();
@@ -1115,21 +1179,37 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
       }
       bt->n_hot[si] = (uint32_t)cand.size();
     }
-    SLG_CUDA(ix, bt->d_hot_slot.alloc(hot_slot.size() * 4));
-    SLG_CUDA(ix, bt->d_hot_cols.alloc(hot_cols.size() * 8));
-    SLG_CUDA(ix, cudaMemcpyAsync(bt->d_hot_slot.p, hot_slot.data(), hot_slot.size() * 4, cudaMemcpyHostToDevice, ix->stream));
-    SLG_CUDA(ix, cudaMemcpyAsync(bt->d_hot_cols.p, hot_cols.data(), hot_cols.size() * 8, cudaMemcpyHostToDevice, ix->stream));
+    auto upload = [&](DevBuf &d, const void *src, size_t bytes) -> cudaError_t {
+      cudaError_t e = d.alloc(bytes);
+      if (e != cudaSuccess || !bytes) return e;
+      ix->ctr.last_h2d_bytes += bytes;
+      return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, ix->stream);
+    };
+    SLG_CUDA(ix, upload(bt->d_hot_slot, hot_slot.data(), hot_slot.size() * 4));
+    SLG_CUDA(ix, upload(bt->d_hot_cols, hot_cols.data(), hot_cols.size() * 8));
+    SLG_CUDA(ix, upload(bt->d_u_row, u_row.data(), u_row.size() * 4));
+    SLG_CUDA(ix, upload(bt->d_row_u, row_u.data(), row_u.size() * 4));
+    SLG_CUDA(ix, upload(bt->d_light_u, light_u.data(), light_u.size() * 4));
     SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));  // host vectors go out of scope
-    ix->ctr.last_h2d_bytes += hot_slot.size() * 4 + hot_cols.size() * 8;
+    if (bt->n_heavy) {
+      SLG_CUDA(ix, bt->sw_recs.alloc((size_t)bt->n_heavy * kSweepRec * sizeof(uint4)));
+      SLG_CUDA(ix, bt->sw_weights.alloc((size_t)bt->n_heavy * 8 * 4));
+      SLG_CUDA(ix, bt->sw_ubw.alloc((size_t)bt->n_heavy * 8 * 4));
+      SLG_CUDA(ix, bt->sw_slot_qi.alloc((size_t)bt->n_heavy * 4));
+      SLG_CUDA(ix, bt->sw_rng.alloc((size_t)std::max(bt->n_rows, 1u) * (bt->sweep_tiles_max + 1) * 4));
+    }
   }
   size_t S = ix->segs.size();
-  SLG_CUDA(ix, bt->ut_rng.alloc((size_t)std::max(bt->U, 1u) * (max_tiles + 1) * 4));
-  if (exec != SLG_EXEC_BM25) SLG_CUDA(ix, bt->ut_tile_ub.alloc((size_t)std::max(bt->U, 1u) * max_tiles * 4));
+  bt->sub_tiles_max = max_tiles;
+  if (!bt->use_reg || bt->n_light) {
+    SLG_CUDA(ix, bt->ut_rng.alloc((size_t)std::max(bt->U, 1u) * (max_tiles + 1) * 4));
+    if (exec != SLG_EXEC_BM25) SLG_CUDA(ix, bt->ut_tile_ub.alloc((size_t)std::max(bt->U, 1u) * max_tiles * 4));
+  }
   SLG_CUDA(ix, bt->thr_key.alloc((size_t)n_queries * 8));
   SLG_CUDA(ix, bt->topk_count.alloc((size_t)n_queries * 4));
   SLG_CUDA(ix, bt->lock.alloc((size_t)n_queries * 4));
   SLG_CUDA(ix, bt->topk_keys.alloc((size_t)n_queries * k * 8));
-  SLG_CUDA(ix, bt->work_counter.alloc(4));
+  SLG_CUDA(ix, bt->work_counter.alloc(64 * 4));
   SLG_CUDA(ix, bt->stats.alloc((size_t)n_queries * 4 * 8));
   SLG_CUDA(ix, bt->seg_hits.alloc(S * n_queries * k * sizeof(HitDev)));
   SLG_CUDA(ix, bt->seg_counts.alloc(S * n_queries * 4));
@@ -1200,55 +1280,93 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
     count_launch(ix);
     SLG_CUDA(ix, cudaMemsetAsync(bd.topk_count, 0, (size_t)Q * 4, st));
     SLG_CUDA(ix, cudaMemsetAsync(bd.lock, 0, (size_t)Q * 4, st));
-    SLG_CUDA(ix, cudaMemsetAsync(bd.work_counter, 0, 4, st));
+    SLG_CUDA(ix, cudaMemsetAsync(bd.work_counter, 0, 64 * 4, st));
     if (bt->U && s->doc_count) {
-      uint64_t n = (uint64_t)bt->U * (bd.n_tiles + 1);
-      uint64_t n2 = (uint64_t)bt->U * bd.n_tiles;
-      if (bt->use_reg) {  // transposed tables: one row per tile boundary
-        slg_plan_ranges_t_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, bd, prune || bt->want_stats);
-        count_launch(ix);
-        if (prune) {
-          slg_plan_bounds_t_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(s->dev, bd);
-          count_launch(ix);
-        }
-      } else {
-        slg_plan_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, bd);
-        count_launch(ix);
-        if (prune) {
-          slg_plan_bounds_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(s->dev, bd);
-          count_launch(ix);
-        }
-      }
+      // ---- plans and per-segment query tables ----
+      BatchDev bw = bd;  // the view of the warp kernel: all queries, or the light ones behind the heavy slots
+      uint32_t n_warp_rows = bt->U;
+      const uint32_t *warp_rows = nullptr;
       if (bt->use_reg) {
-        slg_build_rterms_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, bd, bt->d_hot_slot.as<uint32_t>() + (size_t)si * bt->U,
-                                                                  bt->qterms.as<RTerm>(), bt->qheads.as<RHead>());
+        bw.q_order = bd.q_order + bt->n_heavy;
+        bw.n_queries = bt->n_light;
+        n_warp_rows = bt->n_light_u;
+        warp_rows = bt->d_light_u.as<uint32_t>();
+      }
+      const bool run_warp_side = !bt->use_reg || bt->n_light;
+      if (run_warp_side && n_warp_rows) {
+        uint64_t n = (uint64_t)n_warp_rows * (bd.n_tiles + 1);
+        uint64_t n2 = (uint64_t)n_warp_rows * bd.n_tiles;
+        slg_plan_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, bd, warp_rows, n_warp_rows);
         count_launch(ix);
-      } else if (bt->use_warp) {
-        slg_build_qterms_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, bd, bt->qterms.as<QTerm>(), bt->qheads.as<QHead>());
+        if (prune) {
+          slg_plan_bounds_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(s->dev, bd, warp_rows, n_warp_rows);
+          count_launch(ix);
+        }
+      }
+      if ((bt->use_warp || (bt->use_reg && bt->n_light)) && bw.n_queries) {
+        slg_build_qterms_kernel<<<(bw.n_queries + 127) / 128, 128, 0, st>>>(s->dev, bw, bt->qterms.as<QTerm>(), bt->qheads.as<QHead>());
         count_launch(ix);
       }
+      const uint32_t sw_tile = 128u * bt->reg_v;
+      const uint32_t sw_tiles = std::max(1u, (s->doc_count + sw_tile - 1) / sw_tile);
+      if (bt->use_reg && bt->n_heavy) {
+        if (bt->n_rows) {
+          slg_sweep_plan_kernel<<<dim3(bt->n_rows, 8), 256, 0, st>>>(s->dev, bd.ut_term, bt->d_row_u.as<uint32_t>(), bt->n_rows, sw_tile,
+                                                                      sw_tiles, bt->want_stats, bt->sw_rng.as<uint32_t>());
+          count_launch(ix);
+        }
+        slg_build_sweep_kernel<<<(bt->n_heavy + 127) / 128, 128, 0, st>>>(
+            s->dev, bd, bt->n_heavy, bt->d_hot_slot.as<uint32_t>() + (size_t)si * bt->U, bt->d_u_row.as<uint32_t>(),
+            bt->sw_recs.as<uint4>(), bt->sw_weights.as<float>(), bt->sw_ubw.as<float>(), bt->sw_slot_qi.as<uint32_t>());
+        count_launch(ix);
+      }
+      SLG_CUDA(ix, cudaGetLastError());
       SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));
-      if (bt->use_reg) {
-        RegBatchDev rb{};
-        rb.rterms = bt->qterms.as<RTerm>();
-        rb.rheads = bt->qheads.as<RHead>();
-        rb.rng_t = bd.ut_rng;
-        rb.ub_t = bd.ut_tile_ub;
-        rb.hot_cols = bt->d_hot_cols.as<uint64_t>() + (size_t)si * bt->max_hot;
-        rb.filter_bits = bd.filter_bits;
-        rb.n_queries = Q;
-        rb.n_uterms = bt->U;
-        rb.k = k;
-        rb.n_tiles = bd.n_tiles;
-        rb.n_hot = bt->n_hot[si];
-        rb.thr_key = bd.thr_key;
-        rb.topk_count = bd.topk_count;
-        rb.lock = bd.lock;
-        rb.topk_keys = bd.topk_keys;
-        rb.work_counter = bd.work_counter;
-        rb.stats = bd.stats;
-        rc = launch_reg(ix, bt->reg_v, prune, bt->want_stats, s->dev, rb, (int)bd.n_tiles);
-      } else if (bt->use_warp) {
+      // ---- scoring ----
+      if (bt->use_reg && bt->n_heavy) {
+        // seed pass over the first tiles (slots split across CTAs), then the sweep proper
+        const uint32_t seed_tiles = std::min(sw_tiles, std::max(1u, std::min(sw_tiles / 4, ix->seed_docs / sw_tile)));
+        uint32_t chunk_id = 0;
+        for (uint32_t c0 = 0; c0 < bt->n_heavy; c0 += kSweepMaxSlots, chunk_id++) {
+          if (chunk_id + 1 >= 64) return fail(ix, SLG_ERR_UNSUPPORTED, "more than %u swept queries in one batch", 63 * kSweepMaxSlots);
+          SweepDev sw{};
+          sw.recs = bt->sw_recs.as<uint4>() + (size_t)c0 * kSweepRec;
+          sw.weights = bt->sw_weights.as<float>() + (size_t)c0 * 8;
+          sw.ubw = bt->sw_ubw.as<float>() + (size_t)c0 * 8;
+          sw.slot_qi = bt->sw_slot_qi.as<uint32_t>() + c0;
+          sw.rng = bt->sw_rng.as<uint32_t>();
+          sw.col_tmax = s->col_tmax.as<float>();
+          sw.hot_cols = bt->d_hot_cols.as<uint64_t>() + (size_t)si * bt->max_hot;
+          sw.filter_bits = bd.filter_bits;
+          sw.n_slots = std::min(kSweepMaxSlots, bt->n_heavy - c0);
+          sw.k = k;
+          sw.n_tiles = sw_tiles;
+          sw.n_hot = bt->n_hot[si];
+          sw.tmax_stride = s->tmax_stride;
+          sw.thr_key = bd.thr_key;
+          sw.topk_count = bd.topk_count;
+          sw.lock = bd.lock;
+          sw.topk_keys = bd.topk_keys;
+          sw.work_counter = bd.work_counter + 1 + chunk_id;
+          sw.stats = bd.stats;
+          sw.seed = 1;
+          sw.tile_begin = 0;
+          sw.tile_end = seed_tiles;
+          rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, s->dev, sw, (int)std::min<uint32_t>((uint32_t)ix->n_sm, sw.n_slots));
+          if (rc) return rc;
+          count_launch(ix);
+          if (seed_tiles < sw_tiles) {
+            sw.seed = 0;
+            sw.tile_begin = seed_tiles;
+            sw.tile_end = sw_tiles;
+            rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, s->dev, sw, (int)std::min<uint32_t>((uint32_t)ix->n_sm, sw_tiles - seed_tiles));
+            if (rc) return rc;
+            count_launch(ix);
+          }
+        }
+        ix->ctr.score_launches++;
+      }
+      if ((bt->use_warp || (bt->use_reg && bt->n_light)) && bw.n_queries) {
         WarpBatchDev wb{};
         wb.qterms = bt->qterms.as<QTerm>();
         wb.qheads = bt->qheads.as<QHead>();
@@ -1256,7 +1374,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         wb.sub_ub = bd.ut_tile_ub;
         wb.scores = s->dev.post_score;
         wb.filter_bits = bd.filter_bits;
-        wb.n_queries = Q;
+        wb.n_queries = bw.n_queries;
         wb.k = k;
         wb.sub_docs = ix->sub_docs;
         wb.n_sub = bd.n_tiles;
@@ -1273,15 +1391,18 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         uint32_t wper = (uint32_t)std::max<size_t>(1, (ix->smem_optin + 1024) / (wsmem + 1024));
         wper = std::min(wper, 8u);
         if (ix->ctas_per_sm) wper = std::min(wper, ix->ctas_per_sm);
-        int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * wper, ((uint64_t)wb.n_groups * Q + warps - 1) / warps);
+        int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * wper, ((uint64_t)wb.n_groups * wb.n_queries + warps - 1) / warps);
         rc = launch_warp(ix, bt->matcher, prune, bt->want_stats, bt->staged, s->dev, wb, wsmem, grid);
-      } else {
+        if (rc) return rc;
+        count_launch(ix);
+        if (!bt->use_reg) ix->ctr.score_launches++;
+      } else if (!bt->use_reg && !bt->use_warp) {
         int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * per_sm, (uint64_t)bd.n_tiles * Q);
         rc = launch_score(ix, bt->matcher, prune, bt->want_stats, s->dev, bd, smem, grid);
+        if (rc) return rc;
+        count_launch(ix);
+        ix->ctr.score_launches++;
       }
-      if (rc) return rc;
-      count_launch(ix);
-      ix->ctr.score_launches++;
       SLG_CUDA(ix, cudaEventRecord(ix->ev[3], st));
     }
     HitDev *hits = bt->seg_hits.as<HitDev>() + (size_t)si * Q * k;

@@ -15,9 +15,13 @@ from tests.parity import assert_parity
 pytestmark = pytest.mark.gpu
 
 MATCHER_KERNELS = ["cta", "warp", "warp-inplace"]      # Bool queries: query-order kernels
-KERNELS = MATCHER_KERNELS + ["reg", "reg-dense"]       # plain OR queries: also the register-tile kernel
+KERNELS = MATCHER_KERNELS + ["reg", "reg-dense", "reg-sweep", "reg-light"]  # plain OR queries: also the tile-sweep kernel
 # reg-dense: every term with >= 2 postings and df >= N/64 gets a column (exercises the column path on tiny corpora)
-REG_DENSE = {"dense_min_df": 2, "dense_den": 64}
+# reg-sweep: no columns, every query swept (sparse-scatter path only); reg-light: no columns, every query handed
+# to the warp kernel behind the sweep's front end
+REG_OPTIONS = {"reg-dense": {"dense_min_df": 2, "dense_den": 64, "sweep_min_postings": 1},
+               "reg-sweep": {"dense_den": 0, "sweep_min_postings": 1},
+               "reg-light": {"dense_den": 0, "sweep_min_postings": 1 << 40}}
 
 
 def _oracle(seg, **kw):
@@ -26,8 +30,8 @@ def _oracle(seg, **kw):
 
 
 def _gpu(seg, kernel="auto", k1=0.9, b=0.4, **kw):
-    if kernel == "reg-dense":
-        gi = GpuIndex(0, kernel="reg", options=REG_DENSE, **kw)
+    if kernel in REG_OPTIONS:
+        gi = GpuIndex(0, kernel="reg", options=REG_OPTIONS[kernel], **kw)
     else:
         gi = GpuIndex(0, kernel=kernel, **kw)
     cols = gi.load_segment(seg, k1=k1, b=b)
@@ -369,21 +373,21 @@ def test_post_image_load_equals_csr_load():
 
 
 # ---- several segments in one handle: api/reader.rs:2670-2777 ----------------------------------------------
-@pytest.mark.parametrize("kernel", ["cta", "warp", "reg"])
+@pytest.mark.parametrize("kernel", ["cta", "warp", "reg", "reg-dense", "reg-sweep"])
 def test_multi_segment_merge_order(kernel):
     from oracle import slo
     from searchlite_b200.shard import shard_ranges
     from tests.helpers import canonical_batch
     n_docs, vocab, world = 24_000, 1_500, 3
     qb = synth.generate_queries(70, vocab, seed=72, min_rank=2)
-    gi = GpuIndex(0, kernel=kernel)
+    gi = GpuIndex(0, kernel="reg", options=REG_OPTIONS[kernel]) if kernel in REG_OPTIONS else GpuIndex(0, kernel=kernel)
     per_seg = []
     for r, (lo, hi) in enumerate(shard_ranges(n_docs, world)):
         spec = synth.CorpusSpec(n_docs=hi - lo, vocab=vocab, seed=71, len_lo=10, len_hi=60, segment_ord=r, doc_base=lo)
         seg = synth.generate_segment(spec, "cpu")
         gi.load_segment(seg)
         # the register-tile kernel's term order depends on which terms have a column in THIS segment
-        per_seg.append(slo.OracleIndex(seg).search_batch(canonical_batch(gi, qb, r) if kernel == "reg" else qb, 11, "bm25"))
+        per_seg.append(slo.OracleIndex(seg).search_batch(canonical_batch(gi, qb, r) if kernel.startswith("reg") else qb, 11, "bm25"))
     got_h, got_c = gi.search_batch(qb, 11, "bm25")
     for q in range(qb.n_queries):
         want = slo.merge_hits([h[q, : c[q]] for h, c in per_seg], 11)
@@ -486,7 +490,7 @@ def test_rerank_matches_oracle_formulae(metric, bf16):
 
 
 # ---- statistics (QueryStats, query/wand.rs:45-50) -----------------------------------------------------------
-@pytest.mark.parametrize("kernel", ["cta", "warp", "warp-inplace", "reg"])
+@pytest.mark.parametrize("kernel", ["cta", "warp", "warp-inplace", "reg", "reg-dense", "reg-sweep", "reg-light"])
 def test_stats_count_scored_docs_and_postings(kernel):
     spec = synth.CorpusSpec(n_docs=15_000, vocab=1_200, seed=91, len_lo=10, len_hi=50)
     seg = synth.generate_segment(spec, "cpu")

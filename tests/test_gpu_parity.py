@@ -52,11 +52,14 @@ def test_bm25_bit_exact_vs_oracle(small, kernel, tile_docs, sub_docs, k):
 @pytest.mark.parametrize("v", [4, 8, 16])
 @pytest.mark.parametrize("k", [1, 11, 32])
 @pytest.mark.parametrize("dense_den", [0, 8, 64])
-def test_register_kernel_vs_oracle(small, v, k, dense_den):
-    """dense_den 0: no columns (pure sparse path, query order); 8: default; 64: most query terms are columns"""
+@pytest.mark.parametrize("min_postings", [0, 1])
+def test_register_kernel_vs_oracle(small, v, k, dense_den, min_postings):
+    """dense_den 0: no columns (pure sparse path, query order); 8: default; 64: most query terms are columns.
+    min_postings 0: queries with few postings go to the warp kernel; 1: every query is swept"""
     seg, qb = small
     ora = _oracle(seg)
-    gi = GpuIndex(0, kernel="reg", options={**DENSE, "dense_den": dense_den, "reg_tile_v": v})
+    gi = GpuIndex(0, kernel="reg", options={**DENSE, "dense_den": dense_den, "reg_tile_v": v, "sweep_min_postings": min_postings,
+                                            "seed_docs": 4096 if k == 11 else 16384})
     gi.load_segment(seg)
     n_col = sum(gi.term_has_column(0, int(t)) for t in np.unique(qb.terms["term_id"]))
     assert (n_col == 0) == (dense_den == 0)
