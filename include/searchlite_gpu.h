@@ -168,11 +168,11 @@ int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, u
  *                           over every tile (default 0 = doc_count / 64; 1 = sweep every query)
  *   "seed_docs"        n    tile-sweep kernel: docs scored by the contention-free seed pass (default 16384)
  * Float contract: the tile-sweep kernel sums a doc's contributions over the query's terms
- * WITHOUT a column first, then over the terms WITH a column, each group in query order (one left
+ * WITH a column first, then over the terms WITHOUT one, each group in query order (one left
  * fold) — brute_force (query/wand.rs:527-548) on that permutation of the query; the other kernels
  * sum in query order.  Both agree with the reference within the 1e-5 rule. */
 int32_t slg_set_option(slg_index_t *, const char *name, uint64_t value);
-/* 1 if `term_id` of the segment has a dense column (it is summed last by the tile-sweep kernel) */
+/* 1 if `term_id` of the segment has a dense column (it is summed first by the tile-sweep kernel) */
 int32_t slg_term_has_column(const slg_index_t *, uint32_t segment_ord, uint32_t term_id);
 
 /* ---- residency (SegmentReader::open) ---- */

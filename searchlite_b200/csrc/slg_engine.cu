@@ -170,7 +170,8 @@ struct slg_batch {
   uint32_t n_rows = 0, n_light_u = 0; // rows of the sweep's range table; unique terms of the light queries
   uint32_t sweep_tiles_max = 0, sub_tiles_max = 0;
   DevBuf d_u_row, d_row_u, d_light_u; // [U] row or ~0; [n_rows] unique term; [n_light_u] unique term
-  DevBuf sw_recs, sw_weights, sw_ubw, sw_slot_qi, sw_rng;
+  DevBuf sw_sstat, sw_weights, sw_ubw, sw_rng, sw_records, sw_slot_qi;
+  bool any_weight = false;             // some scored term has weight != 1
   DevBuf seg_hits, seg_counts;  // [S][Q][k], [S][Q]
   DevBuf out_hits, out_counts;  // merged (aliases seg buffers when S == 1)
   uint32_t n_segs_run = 0;
@@ -518,22 +519,22 @@ int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, bool st
 }
 
 template <int V>
-size_t sweep_smem_bytes(uint32_t n_hot, uint32_t n_slots) {
-  return (size_t)n_hot * 128 * V * 4 + (size_t)((n_slots + 3u) & ~3u) * 4 + (size_t)kSweepWarps * sweep_smem_per_warp<V>();
+size_t sweep_smem_bytes(uint32_t n_hot) {
+  return (size_t)n_hot * 128 * V * 4 + (size_t)kSweepWarps * sweep_smem_per_warp<V>();
 }
 
-// how many column slices of one tile fit next to the threshold cache and the warps' private tiles
-uint32_t sweep_max_hot(const slg_index *ix, uint32_t v, uint32_t n_slots) {
+// how many column slices of one tile fit next to the warps' private tiles
+uint32_t sweep_max_hot(const slg_index *ix, uint32_t v) {
   const size_t per_warp = (size_t)128 * v * 4 + kWarpCand * 8;
-  const size_t fixed = (size_t)kSweepWarps * per_warp + (size_t)((n_slots + 3u) & ~3u) * 4 + 1024;  // + static shared and slack
+  const size_t fixed = (size_t)kSweepWarps * per_warp + 1024;  // + static shared and slack
   if (ix->smem_optin <= fixed) return 0;
-  return (uint32_t)std::min<size_t>(254, (ix->smem_optin - fixed) / ((size_t)128 * v * 4));
+  return (uint32_t)std::min<size_t>(253, (ix->smem_optin - fixed) / ((size_t)128 * v * 4));
 }
 
-template <int V, bool P, bool S>
+template <int V, bool P, bool S, bool W>
 int32_t launch_sweep_t(slg_index *ix, const SegmentDev &sd, const SweepDev &sw, int grid) {
-  auto kern = slg_score_sweep_kernel<V, P, S>;
-  const size_t smem = sweep_smem_bytes<V>(sw.n_hot, sw.n_slots);
+  auto kern = slg_score_sweep_kernel<V, P, S, W>;
+  const size_t smem = sweep_smem_bytes<V>(sw.n_hot);
   if (smem + 1024 > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "sweep kernel needs %zu B shared memory", smem);
   SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kSweepThreads, smem, ix->stream>>>(sd, sw);
@@ -542,20 +543,24 @@ int32_t launch_sweep_t(slg_index *ix, const SegmentDev &sd, const SweepDev &sw, 
 }
 
 template <int V>
-int32_t launch_sweep_v(slg_index *ix, bool prune, bool stats, const SegmentDev &sd, const SweepDev &sw, int grid) {
-  switch ((prune ? 2 : 0) | (stats ? 1 : 0)) {
-    case 0: return launch_sweep_t<V, false, false>(ix, sd, sw, grid);
-    case 1: return launch_sweep_t<V, false, true>(ix, sd, sw, grid);
-    case 2: return launch_sweep_t<V, true, false>(ix, sd, sw, grid);
-    default: return launch_sweep_t<V, true, true>(ix, sd, sw, grid);
+int32_t launch_sweep_v(slg_index *ix, bool prune, bool stats, bool weights, const SegmentDev &sd, const SweepDev &sw, int grid) {
+  switch ((prune ? 4 : 0) | (stats ? 2 : 0) | (weights ? 1 : 0)) {
+    case 0: return launch_sweep_t<V, false, false, false>(ix, sd, sw, grid);
+    case 1: return launch_sweep_t<V, false, false, true>(ix, sd, sw, grid);
+    case 2: return launch_sweep_t<V, false, true, false>(ix, sd, sw, grid);
+    case 3: return launch_sweep_t<V, false, true, true>(ix, sd, sw, grid);
+    case 4: return launch_sweep_t<V, true, false, false>(ix, sd, sw, grid);
+    case 5: return launch_sweep_t<V, true, false, true>(ix, sd, sw, grid);
+    case 6: return launch_sweep_t<V, true, true, false>(ix, sd, sw, grid);
+    default: return launch_sweep_t<V, true, true, true>(ix, sd, sw, grid);
   }
 }
 
-int32_t launch_sweep(slg_index *ix, uint32_t v, bool prune, bool stats, const SegmentDev &sd, const SweepDev &sw, int grid) {
+int32_t launch_sweep(slg_index *ix, uint32_t v, bool prune, bool stats, bool weights, const SegmentDev &sd, const SweepDev &sw, int grid) {
   switch (v) {
-    case 4: return launch_sweep_v<4>(ix, prune, stats, sd, sw, grid);
-    case 16: return launch_sweep_v<16>(ix, prune, stats, sd, sw, grid);
-    default: return launch_sweep_v<8>(ix, prune, stats, sd, sw, grid);
+    case 4: return launch_sweep_v<4>(ix, prune, stats, weights, sd, sw, grid);
+    case 16: return launch_sweep_v<16>(ix, prune, stats, weights, sd, sw, grid);
+    default: return launch_sweep_v<8>(ix, prune, stats, weights, sd, sw, grid);
   }
 }
 
@@ -1046,10 +1051,13 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   const bool small = k <= kWarpMaxK && bt->max_terms <= kWarpMaxTerms;
   bool all_scores = ix->staging;
   for (auto &s : ix->segs) all_scores = all_scores && (s->post_score.p != nullptr || s->n_blocks == 0);
+  bool sweepable = all_scores;  // the sweep addresses postings with 32-bit indices
+  for (auto &s : ix->segs) sweepable = sweepable && s->n_post_padded < (1ull << 32);
   // tile-sweep kernel: plain OR queries (no matcher), small k, few terms, resident scores
-  bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && all_scores);
-  if (bt->use_reg && !(small && !matcher && all_scores))
-    return fail(ix, SLG_ERR_UNSUPPORTED, "the sweep kernel handles plain OR queries, k <= %u, <= %u terms per query, resident scores",
+  bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && sweepable);
+  if (bt->use_reg && !(small && !matcher && sweepable))
+    return fail(ix, SLG_ERR_UNSUPPORTED,
+                "the sweep kernel handles plain OR queries, k <= %u, <= %u terms per query, resident scores, < 2^32 postings per segment",
                 kWarpMaxK, kWarpMaxTerms);
   bt->use_warp = !bt->use_reg && (ix->kernel_choice == 2 || (ix->kernel_choice == 0 && small));
   if (bt->use_warp && !small)
@@ -1157,7 +1165,7 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
     bt->n_rows = (uint32_t)row_u.size();
     bt->n_light_u = (uint32_t)light_u.size();
     // per segment: the columns the heavy queries use most (by query-term instances) get a shared-memory slot
-    bt->max_hot = sweep_max_hot(ix, bt->reg_v, std::min(bt->n_heavy, kSweepMaxSlots));
+    bt->max_hot = sweep_max_hot(ix, bt->reg_v);
     std::vector<uint32_t> hot_slot(nseg * std::max(bt->U, 1u), 0);
     std::vector<uint64_t> hot_cols(nseg * std::max(bt->max_hot, 1u), 0);
     bt->n_hot.assign(nseg, 0);
@@ -1192,10 +1200,12 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
     SLG_CUDA(ix, upload(bt->d_light_u, light_u.data(), light_u.size() * 4));
     SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));  // host vectors go out of scope
     if (bt->n_heavy) {
-      SLG_CUDA(ix, bt->sw_recs.alloc((size_t)bt->n_heavy * kSweepRec * sizeof(uint4)));
+      for (float w : qt_w) bt->any_weight = bt->any_weight || w != 1.0f;
+      SLG_CUDA(ix, bt->sw_sstat.alloc((size_t)bt->n_heavy * kSweepSlotWords * 4));
       SLG_CUDA(ix, bt->sw_weights.alloc((size_t)bt->n_heavy * 8 * 4));
       SLG_CUDA(ix, bt->sw_ubw.alloc((size_t)bt->n_heavy * 8 * 4));
       SLG_CUDA(ix, bt->sw_slot_qi.alloc((size_t)bt->n_heavy * 4));
+      SLG_CUDA(ix, bt->sw_records.alloc((size_t)bt->sweep_tiles_max * std::min(bt->n_heavy, kSweepMaxSlots) * kSweepRecWords * 4));
       SLG_CUDA(ix, bt->sw_rng.alloc((size_t)std::max(bt->n_rows, 1u) * (bt->sweep_tiles_max + 1) * 4));
     }
   }
@@ -1317,7 +1327,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         }
         slg_build_sweep_kernel<<<(bt->n_heavy + 127) / 128, 128, 0, st>>>(
             s->dev, bd, bt->n_heavy, bt->d_hot_slot.as<uint32_t>() + (size_t)si * bt->U, bt->d_u_row.as<uint32_t>(),
-            bt->sw_recs.as<uint4>(), bt->sw_weights.as<float>(), bt->sw_ubw.as<float>(), bt->sw_slot_qi.as<uint32_t>());
+            bt->sw_sstat.as<uint4>(), bt->sw_weights.as<float>(), bt->sw_ubw.as<float>(), bt->sw_slot_qi.as<uint32_t>());
         count_launch(ix);
       }
       SLG_CUDA(ix, cudaGetLastError());
@@ -1330,10 +1340,11 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         for (uint32_t c0 = 0; c0 < bt->n_heavy; c0 += kSweepMaxSlots, chunk_id++) {
           if (chunk_id + 1 >= 64) return fail(ix, SLG_ERR_UNSUPPORTED, "more than %u swept queries in one batch", 63 * kSweepMaxSlots);
           SweepDev sw{};
-          sw.recs = bt->sw_recs.as<uint4>() + (size_t)c0 * kSweepRec;
+          sw.sstat = bt->sw_sstat.as<uint4>() + (size_t)c0 * (kSweepSlotWords / 4);
           sw.weights = bt->sw_weights.as<float>() + (size_t)c0 * 8;
           sw.ubw = bt->sw_ubw.as<float>() + (size_t)c0 * 8;
           sw.slot_qi = bt->sw_slot_qi.as<uint32_t>() + c0;
+          sw.records = bt->sw_records.as<uint32_t>();
           sw.rng = bt->sw_rng.as<uint32_t>();
           sw.col_tmax = s->col_tmax.as<float>();
           sw.hot_cols = bt->d_hot_cols.as<uint64_t>() + (size_t)si * bt->max_hot;
@@ -1349,17 +1360,24 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
           sw.topk_keys = bd.topk_keys;
           sw.work_counter = bd.work_counter + 1 + chunk_id;
           sw.stats = bd.stats;
+          {
+            const dim3 rgrid((sw.n_slots + 127) / 128, (sw_tiles + kSweepTileGroup - 1) / kSweepTileGroup);
+            if (prune) slg_sweep_records_kernel<true><<<rgrid, 128, 0, st>>>(sw, bt->reg_v, bt->want_stats);
+            else slg_sweep_records_kernel<false><<<rgrid, 128, 0, st>>>(sw, bt->reg_v, bt->want_stats);
+            SLG_CUDA(ix, cudaGetLastError());
+            count_launch(ix);
+          }
           sw.seed = 1;
           sw.tile_begin = 0;
           sw.tile_end = seed_tiles;
-          rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, s->dev, sw, (int)std::min<uint32_t>((uint32_t)ix->n_sm, sw.n_slots));
+          rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, bt->any_weight, s->dev, sw, (int)std::min<uint32_t>((uint32_t)ix->n_sm, sw.n_slots));
           if (rc) return rc;
           count_launch(ix);
           if (seed_tiles < sw_tiles) {
             sw.seed = 0;
             sw.tile_begin = seed_tiles;
             sw.tile_end = sw_tiles;
-            rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, s->dev, sw, (int)std::min<uint32_t>((uint32_t)ix->n_sm, sw_tiles - seed_tiles));
+            rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, bt->any_weight, s->dev, sw, (int)std::min<uint32_t>((uint32_t)ix->n_sm, sw_tiles - seed_tiles));
             if (rc) return rc;
             count_launch(ix);
           }

@@ -17,15 +17,20 @@
 //                     staged in shared memory once per tile and every query that names one of them
 //                     reads it from there (L2 -> SM traffic drops from 8 B per visit to one column
 //                     slice per tile per CTA).
-//   register tile     one warp = one (query, tile): lane L holds docs {128*i + 4*L .. +3 : i < V} in
-//                     registers.  The query's terms without a column are scattered into a
-//                     warp-private shared tile first (posting-driven, a few postings per tile), the
-//                     tile is read once into the registers (and cleared), the columns are added in
-//                     registers, and the registers are compared against the query's running k-th
-//                     score — no accumulator scan, no shared-memory traffic for the dense part.
-//   software pipeline every per-item input (query record, tile ranges of the sparse terms, the first
-//                     32 postings) is loaded one to three items ahead by the same warp, which walks a
-//                     static, rotated sequence of query slots; nothing in an item waits on L2.
+//   item records      before the sweep, slg_sweep_records_kernel resolves every query's sparse terms
+//                     against every tile (posting ranges from the range table, a compacted list of
+//                     the non-empty ones, a bitmap of where each term starts in their concatenation,
+//                     the tile's upper bound for the pruned modes) into an 80-byte record per
+//                     (tile, query).  All per-(query, tile) bookkeeping is scalar, coalesced,
+//                     embarrassingly parallel code there; the sweep streams the records.
+//   register tile     then one warp = one (query, tile): lane L holds docs {128*i + 4*L .. +3 : i < V}
+//                     in registers.  The column terms are added in registers (staged slice from shared
+//                     memory, conflict-free 128-bit reads) and compared against the query's k-th
+//                     score; only if the query also has sparse postings in the tile is the register
+//                     tile parked in a warp-private shared tile, the (doc, score) postings added to it
+//                     and the touched docs re-checked.  No accumulator scan, no clearing.
+//   software pipeline a warp walks a static, rotated sequence of query slots; the record of item i+2
+//                     and the first 64 postings of item i+1 are in flight while item i is computed.
 //   seed pass         the same kernel first runs tiles [0, seed_tiles) with the query slots split
 //                     across CTAs (no two warps share a query), which gives every query a useful
 //                     threshold before 148 CTAs start merging into the same top-k lists.
@@ -33,8 +38,8 @@
 // Queries for which a sweep over every tile would be wasted work (no column term and few postings)
 // are "light": they go to slg_score_warp_kernel in the same batch run.
 //
-// Summation order (the float contract of this kernel): the query's terms WITHOUT a column in query
-// order, then the terms WITH a column in query order, one left fold.  That is brute_force
+// Summation order (the float contract of this kernel): the query's terms WITH a column in query
+// order, then the terms WITHOUT one in query order, one left fold.  That is brute_force
 // (query/wand.rs:527-548) applied to a permutation of the query's terms; tests check it bit for bit
 // against the oracle run on the permuted query and against the reference order under the 1e-5 rule.
 //
@@ -49,26 +54,37 @@ namespace slg {
 
 constexpr int kSweepThreads = 512;  // 16 warps, one CTA per SM
 constexpr int kSweepWarps = kSweepThreads / 32;
-constexpr uint32_t kSweepRec = 9;   // uint4 per query slot: 8 term records + head
-constexpr uint32_t kSweepMaxSlots = 8192;  // query slots per launch (threshold cache in shared memory)
+constexpr uint32_t kSweepSlotWords = 32;   // static description of one query slot
+constexpr uint32_t kSweepRecWords = 20;    // per-(tile, slot) record
+constexpr uint32_t kSweepMaxSlots = 16384; // query slots per launch
+constexpr uint32_t kSweepTileGroup = 8;    // tiles resolved by one thread of the record kernel
 
-// term record (uint4): x | y << 32 = base, z = row of the tile-range table, w = code
-//   base  sparse: first padded posting index (post_doc / post_score); column: element offset in seg.cols
-//   code  bits 0..1 kind (0 none, 1 sparse, 2 column), bits 2..9 1 + shared-memory slot of the
-//         column's staged slice (0 = read the column from global), bits 10..30 column index,
-//         bit 31 weight != 1
-// head (uint4): x = query index, y = filter id, z = ns | nt << 8 | any_weight << 16
-constexpr uint32_t kSweepWBit = 0x80000000u;
+// static slot description, 32 words:
+//   [0..7]   row of the tile-range table per term position (sparse terms, and column terms when
+//            statistics are wanted); positions: sparse terms first, then column terms, query order
+//   [8..15]  sparse: first padded posting index of the term (u32); column: column index
+//   [16,17]  per column term c one byte: 1 + shared-memory slot of its staged slice, 255 = read the
+//            column from global memory
+//   [18] query index  [19] filter id  [20] ns | ncol << 4 | any_weight << 8
+// per-(tile, slot) record, 20 words — the sparse terms of the slot resolved against the tile:
+//   [0..3]  B: 128-bit map over the concatenated postings of the non-empty sparse terms (query order);
+//           bit j set = the r-th (r >= 1) non-empty term starts at position j.  rank(j) = popc(B[0..j])
+//   [4] tot | ncol << 16 | nne << 20 | ns << 24   [5] upper bound of the tile for this query (PRUNE)
+//   [6,7]   copy of static words 16, 17
+//   [8..15] adj_r = first posting of the r-th non-empty sparse term - its position in the concatenation
+//   [16] 3 bits per r: term position of the r-th non-empty sparse term (weights)
+//   [17] postings of all terms of the query inside the tile (statistics)
 
 struct SweepDev {
-  const uint4 *recs;            // [n_slots][kSweepRec]
-  const float *weights;         // [n_slots][8]
+  const uint4 *sstat;           // [n_slots][8]
+  const uint32_t *slot_qi;      // [n_slots] query index of the slot
+  const float *weights;         // [n_slots][8] term positions as in sstat
   const float *ubw;             // [n_slots][8] PRUNE: weight * term-wide bound (sparse) or weight (column)
-  const uint32_t *slot_qi;      // [n_slots]
   const uint32_t *rng;          // [rows][n_tiles + 1] first posting with doc >= tile * TILE
   const float *col_tmax;        // [n_cols][tmax_stride] column maxima per 512 docs (PRUNE)
   const uint64_t *hot_cols;     // [n_hot] element offset of each staged column in seg.cols
   const uint32_t *const *filter_bits;
+  uint32_t *records;            // [n_tiles][n_slots][kSweepRecWords]
   uint32_t n_slots, k, n_tiles, n_hot;
   uint32_t tile_begin, tile_end;  // tiles of this launch
   uint32_t seed;                  // 1: every CTA walks all tiles of the launch over its own share of the slots
@@ -85,10 +101,12 @@ __host__ __device__ constexpr size_t sweep_smem_per_warp() {
   return (size_t)128 * V * 4 + kWarpCand * 8;  // M f32[128*V] | cand u64[64]
 }
 
-__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
-  const uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)v, src), hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), src);
-  return ((uint64_t)hi << 32) | lo;
+__device__ __forceinline__ uint4 ld_cg_u4(const void *p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // append the keys of one ballot round to the warp's candidate buffer; when more than 32 are pending,
 // sort, keep the best k and raise the local threshold (exact: nothing is dropped unsorted)
@@ -109,12 +127,12 @@ __device__ __forceinline__ void sweep_push(bool pass, unsigned long long key, un
   }
 }
 
-// Slow path of one (query, tile): the register tile has been parked in M.  Collect the keys that
-// beat the query's current k-th key, clear M, merge into the query's global top-k (push_top_k,
-// query/wand.rs:905-916).  Returns the score bits of the best threshold now known.
+// Slow path of one (query, tile): M holds the final scores of the tile.  Collect the keys that beat
+// the query's current k-th key and merge them into the query's global top-k (push_top_k,
+// query/wand.rs:905-916).  Returns the number of candidates collected.
 template <int V>
-__device__ __noinline__ uint2 sweep_collect(float *M, unsigned long long *cand, uint32_t tile_lo, uint32_t qi, int32_t filter,
-                                            const SegmentDev &seg, const SweepDev &sw, int lane) {
+__device__ __noinline__ uint32_t sweep_collect(const float *M, unsigned long long *cand, uint32_t tile_lo, uint32_t qi, int32_t filter,
+                                               const SegmentDev &seg, const SweepDev &sw, int lane) {
   constexpr uint32_t TILE = 128u * V;
   const uint32_t k = sw.k;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -126,7 +144,6 @@ __device__ __noinline__ uint2 sweep_collect(float *M, unsigned long long *cand, 
     const float4 v = *reinterpret_cast<const float4 *>(M + i);
     const uint32_t bits[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
     const uint32_t m = max(max(bits[0], bits[1]), max(bits[2], bits[3]));
-    if (m != 0u) *reinterpret_cast<float4 *>(M + i) = make_float4(0, 0, 0, 0);
     if (__any_sync(0xFFFFFFFFu, m >= (uint32_t)(thr >> 32) && m != 0u)) {
 #pragma unroll
       for (int e = 0; e < 4; e++) {
@@ -143,7 +160,6 @@ __device__ __noinline__ uint2 sweep_collect(float *M, unsigned long long *cand, 
   const uint32_t n_cand = cnt;
   if (cnt > 0) {
     const unsigned long long thr_now = ld_cg_u64(sw.thr_key + qi);
-    thr = max(thr, thr_now);
     const bool useful = lane < (int)cnt && cand[lane] > thr_now;  // cnt <= 32 after every append
     if (__any_sync(0xFFFFFFFFu, useful)) {
       if (lane == 0) {
@@ -160,7 +176,6 @@ __device__ __noinline__ uint2 sweep_collect(float *M, unsigned long long *cand, 
       warp_sort64_desc(cand, lane);
       total = min(total, k);
       if (lane < (int)total) st_cg_u64(gk + lane, cand[lane]);
-      if (total == k) thr = max(thr, cand[k - 1]);
       __threadfence();
       __syncwarp();
       if (lane == 0) {
@@ -172,28 +187,79 @@ __device__ __noinline__ uint2 sweep_collect(float *M, unsigned long long *cand, 
       __syncwarp();
     }
   }
-  return make_uint2(thr == kThrInit ? 0u : (uint32_t)(thr >> 32), n_cand);
+  return n_cand;
 }
 
-template <int V, bool PRUNE, bool STATS>
+// A column that is not staged in shared memory (rare: more distinct columns in the batch than slots):
+// out of line so that the staged path carries none of its address arithmetic.
+template <int V>
+__device__ __noinline__ void sweep_load_column_global(const float *col, int lane, float4 *cv) {
+  const float4 *cp = reinterpret_cast<const float4 *>(col) + lane;
+#pragma unroll
+  for (int v = 0; v < V; v++) cv[v] = __ldg(cp + v * 32);
+}
+
+// Sparse postings of an item with more than 128 of them in the tile (no columns, or unusually long
+// lists): term by term straight from the range table, 32 postings at a time.  M holds the parked
+// register tile.
+template <bool WEIGHTS>
+__device__ __noinline__ void sweep_scatter_long(float *M, uint32_t slot, uint32_t tile, uint32_t tile_lo, const SegmentDev &seg,
+                                                const SweepDev &sw, int lane) {
+  const uint32_t *sst = reinterpret_cast<const uint32_t *>(sw.sstat + (size_t)slot * 8);
+  const uint32_t ns = __ldg(sst + 20) & 15u;
+  uint32_t lo = 0, hi = 0, base = 0;
+  float w = 1.0f;
+  if ((uint32_t)lane < ns) {
+    const uint32_t *p = sw.rng + (uint64_t)__ldg(sst + lane) * (sw.n_tiles + 1) + tile;
+    lo = __ldg(p);
+    hi = __ldg(p + 1);
+    base = __ldg(sst + 8 + lane);
+    if (WEIGHTS) w = __ldg(sw.weights + (size_t)slot * 8 + lane);
+  }
+#pragma unroll 1
+  for (uint32_t t = 0; t < ns; t++) {
+    const uint32_t start = __shfl_sync(0xFFFFFFFFu, base + lo, t), cnt = __shfl_sync(0xFFFFFFFFu, hi - lo, t);
+    const float wt = __shfl_sync(0xFFFFFFFFu, w, t);
+#pragma unroll 1
+    for (uint32_t b = 0; b < cnt; b += 32) {
+      const uint32_t j = b + lane;
+      if (j < cnt) {
+        const uint32_t doc = __ldg(seg.post_doc + start + j);
+        float s = __ldg(seg.post_score + start + j);
+        if (WEIGHTS) s = __fmul_rn(s, wt);
+        M[doc - tile_lo] = __fadd_rn(M[doc - tile_lo], s);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// one item of a warp's pipeline
+struct SweepItem {
+  uint4 b;          // record words 0..3 (every lane holds the same values)
+  uint4 m;          // record words 4..7
+  uint32_t a;       // lane r < 8: adj_r
+  uint32_t d0, d1;  // postings of rounds 0 and 1: doc, score
+  float s0, s1;
+  uint32_t slot, qi;
+  unsigned long long thr;  // the query's k-th key when the item entered the pipeline's last stage
+};
+
+template <int V, bool PRUNE, bool STATS, bool WEIGHTS>
 __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const SegmentDev seg, const SweepDev sw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr uint32_t TILE = 128u * V;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // layout: hot f32[n_hot][TILE] | thr_s u32[n_slots rounded to 4] | per warp: M f32[TILE], cand u64[64]
+  // layout: hot f32[n_hot][TILE] | per warp: M f32[TILE], cand u64[64]
   float *hot = reinterpret_cast<float *>(smem_raw);
-  uint32_t *thr_s = reinterpret_cast<uint32_t *>(smem_raw + (size_t)sw.n_hot * TILE * 4);
-  unsigned char *mine = reinterpret_cast<unsigned char *>(thr_s + ((sw.n_slots + 3u) & ~3u)) + (size_t)warp * sweep_smem_per_warp<V>();
+  unsigned char *mine = smem_raw + (size_t)sw.n_hot * TILE * 4 + (size_t)warp * sweep_smem_per_warp<V>();
   float *M = reinterpret_cast<float *>(mine);
   unsigned long long *cand = reinterpret_cast<unsigned long long *>(mine + (size_t)TILE * 4);
   __shared__ uint32_t s_tile;
 
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t rng_stride = sw.n_tiles + 1;
-  (void)lt_mask;
-
-  for (uint32_t i = lane * 4; i < TILE; i += 128) *reinterpret_cast<float4 *>(M + i) = make_float4(0, 0, 0, 0);
+  const uint32_t le_mask = lt_mask | (1u << lane);
 
   // query slots of this CTA: all of them, or (seed pass) its own share
   uint32_t slot_lo = 0, slot_n = sw.n_slots;
@@ -206,7 +272,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
   const int n_iter = slot_n > (uint32_t)warp ? (int)((slot_n - warp + kSweepWarps - 1) / kSweepWarps) : 0;
 
   for (uint32_t it = 0;; it++) {
-    __syncthreads();  // every warp is done with the previous tile's staged slices and thresholds
+    __syncthreads();  // every warp is done with the previous tile's staged slices
     uint32_t tile;
     if (sw.seed) {
       tile = sw.tile_begin + it;
@@ -217,14 +283,13 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
     }
     if (tile >= sw.tile_end) break;
     const uint32_t tile_lo = tile * TILE;
-    // ---- stage this tile's slices of the batch's hottest columns, refresh the threshold cache ----
+    const uint32_t *recs = sw.records + ((size_t)tile * sw.n_slots + slot_lo) * kSweepRecWords;
+
+    // ---- pull this tile's records into L2, stage the tile's slices of the hottest columns ----
+    for (uint32_t i = threadIdx.x * 32; i < slot_n * kSweepRecWords; i += kSweepThreads * 32) prefetch_l2(recs + i);
     for (uint32_t i = threadIdx.x; i < sw.n_hot * (TILE / 4); i += kSweepThreads) {
       const uint32_t h = i / (TILE / 4), o = i - h * (TILE / 4);
       reinterpret_cast<float4 *>(hot)[i] = ldg_stream_f4(reinterpret_cast<const float4 *>(seg.cols + sw.hot_cols[h] + tile_lo) + o);
-    }
-    for (uint32_t s = threadIdx.x; s < slot_n; s += kSweepThreads) {
-      const unsigned long long t = ld_cg_u64(sw.thr_key + sw.slot_qi[slot_lo + s]);
-      thr_s[slot_lo + s] = t == kThrInit ? 0u : (uint32_t)(t >> 32);
     }
     __syncthreads();
 
@@ -234,256 +299,302 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
     auto slot_at = [&](int p) -> uint32_t {
       uint32_t s = rot + (uint32_t)warp + (uint32_t)kSweepWarps * (uint32_t)p;
       if (s >= slot_n) s -= slot_n;
-      return slot_lo + s;
+      return s;  // relative to slot_lo
     };
 
-    // ---- software pipeline over this warp's items: D (record) -> R (ranges) -> P (postings) -> X ----
-    uint4 recD = make_uint4(0, 0, 0, 0), recR = recD, recP = recD, recX = recD;
-    uint32_t lo2 = 0, hi2 = 0, lo1 = 0, hi1 = 0;
-    float w2 = 1.0f, w1 = 1.0f, w0 = 1.0f;
-    float ub2 = 0.0f, ub1 = 0.0f, tmax2 = 0.0f, tmax1 = 0.0f;
-    uint32_t tot0 = 0, E0 = 0, own0 = 0, pd0 = 0, npost0 = 0;
-    uint64_t st0 = 0;
-    float ps0 = 0.0f, bound0 = 0.0f;
-    (void)ub2; (void)ub1; (void)tmax2; (void)tmax1; (void)npost0; (void)bound0;
-
-#pragma unroll 1
-    for (int i = -3; i < n_iter; i++) {
-      // ---- P: item i + 1 — counts, owners, first 32 postings ----
-      uint32_t totN = 0, EN = 0, ownN = 0, pdN = 0, npostN = 0;
-      uint64_t stN = 0;
-      float psN = 0.0f, boundN = 0.0f;
-      if (i + 1 >= 0 && i + 1 < n_iter) {
-        const uint32_t kind = lane < 8 ? (recP.w & 3u) : 0u;
-        const uint32_t cnt = kind == 1u ? hi1 - lo1 : 0u;
-        uint32_t inc = cnt;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          const uint32_t v = __shfl_up_sync(FULL, inc, o);
-          if (lane >= o) inc += v;
-        }
-        totN = __shfl_sync(FULL, inc, 7);
-        EN = inc - cnt;
-        stN = (((uint64_t)recP.y << 32) | recP.x) + lo1 - EN;
-        if (totN) {
-          // owner of position j: the last term slot s in 0..7 whose exclusive prefix E_s <= j
-          uint32_t o = 0;
-          uint32_t e = __shfl_sync(FULL, EN, 4);
-          if ((uint32_t)lane >= e) o = 4;
-          e = __shfl_sync(FULL, EN, o + 2);
-          if ((uint32_t)lane >= e) o += 2;
-          e = __shfl_sync(FULL, EN, o + 1);
-          if ((uint32_t)lane >= e) o += 1;
-          ownN = o;
-          const uint64_t idx = shfl_u64(stN, o) + lane;
-          if ((uint32_t)lane < totN) {
-            pdN = __ldg(seg.post_doc + idx);
-            psN = __ldg(seg.post_score + idx);
-          }
-        }
-        if (PRUNE) {
-          float b = kind == 1u ? (cnt ? ub1 : 0.0f) : (kind == 2u ? __fmul_rn(tmax1, ub1) : 0.0f);
-#pragma unroll
-          for (int o = 4; o > 0; o >>= 1) b += __shfl_xor_sync(FULL, b, o);  // terms live in lanes 0..7
-          boundN = __shfl_sync(FULL, b, 0);
-        }
-        if (STATS) npostN = kind ? hi1 - lo1 : 0u;
+    // D: record of item p.  Every lane reads the same header words (one sector, broadcast).
+    auto stage_d = [&](SweepItem &x, int p) {
+      x.b = make_uint4(0, 0, 0, 0);
+      x.m = make_uint4(0, 0, 0, 0);
+      x.a = 0;
+      if (p < n_iter) {
+        x.slot = slot_at(p);
+        const uint32_t *rec = recs + (size_t)x.slot * kSweepRecWords;
+        x.b = __ldg(reinterpret_cast<const uint4 *>(rec));
+        x.m = __ldg(reinterpret_cast<const uint4 *>(rec) + 1);
+        if (lane < 8) x.a = __ldg(rec + 8 + lane);
+        x.qi = __ldg(sw.slot_qi + slot_lo + x.slot);
       }
-      // ---- R: item i + 2 — tile ranges of the sparse terms, weights, bounds ----
-      if (i + 2 >= 0 && i + 2 < n_iter) {
-        lo2 = hi2 = 0;
-        w2 = 1.0f;
-        if (lane < 8) {
-          const uint32_t kind = recR.w & 3u;
-          if (kind == 1u || (STATS && kind == 2u)) {
-            const uint32_t *p = sw.rng + (uint64_t)recR.z * rng_stride + tile;
-            lo2 = __ldg(p);
-            hi2 = __ldg(p + 1);
-          }
-          if ((recR.w & kSweepWBit) || PRUNE) {
-            const uint32_t s = slot_at(i + 2);
-            if (recR.w & kSweepWBit) w2 = __ldg(sw.weights + (uint64_t)s * 8 + lane);
-            if (PRUNE) {
-              ub2 = kind ? __ldg(sw.ubw + (uint64_t)s * 8 + lane) : 0.0f;
-              tmax2 = 0.0f;
-              if (kind == 2u) {
-                const float *tm = sw.col_tmax + (uint64_t)((recR.w >> 10) & 0x1FFFFFu) * sw.tmax_stride + (uint64_t)tile * (V / 4);
+    };
+    // posting index of position 32 * rho + lane of the concatenated non-empty terms
+    auto owner_rank = [&](const SweepItem &x, int rho) -> uint32_t {
+      uint32_t r = 0;
+      if (rho > 0) r += __popc(x.b.x);
+      if (rho > 1) r += __popc(x.b.y);
+      if (rho > 2) r += __popc(x.b.z);
+      const uint32_t bw = rho == 0 ? x.b.x : (rho == 1 ? x.b.y : (rho == 2 ? x.b.z : x.b.w));
+      return r + __popc(bw & le_mask);
+    };
+    auto load_round = [&](const SweepItem &x, int rho, uint32_t tot, uint32_t &d, float &s) {
+      d = tile_lo;
+      s = 0.0f;
+      if (tot > 32u * rho) {
+        const uint32_t idx = __shfl_sync(FULL, x.a, owner_rank(x, rho)) + 32u * rho + lane;
+        if (32u * rho + lane < tot) {
+          d = __ldg(seg.post_doc + idx);
+          s = __ldg(seg.post_score + idx);
+        }
+      }
+    };
+    // P: rounds 0 and 1 of the item's postings
+    auto stage_p = [&](SweepItem &x) {
+      uint32_t tot = x.m.x & 0xFFFFu;
+      x.thr = kThrInit;
+      if (x.m.x & 0xFFFFFu) x.thr = ld_cg_u64(sw.thr_key + x.qi);
+      if (tot > 128u) tot = 0;
+      load_round(x, 0, tot, x.d0, x.s0);
+      load_round(x, 1, tot, x.d1, x.s1);
+    };
+    // X: the item itself
+    auto stage_x = [&](SweepItem &x) {
+      const uint32_t meta = x.m.x;
+      if ((meta & 0xFFFFFu) == 0u) return;  // no postings and no column terms (or no item)
+      const uint32_t tot = meta & 0xFFFFu, ncol = (meta >> 16) & 15u;
+      const uint32_t slot = slot_lo + x.slot;
+      const uint32_t *sst = reinterpret_cast<const uint32_t *>(sw.sstat + (size_t)slot * 8);
+      const uint32_t qi = x.qi;
+      const uint32_t thr_hi = x.thr == kThrInit ? 0u : (uint32_t)(x.thr >> 32);
+      if (PRUNE) {
+        // safe skip: nothing in this tile can reach the k-th score (the postings in flight are dropped)
+        if (thr_hi != 0u && __uint_as_float(x.m.y) * 1.00001f < __uint_as_float(thr_hi)) {
+          if (STATS && lane == 0) atomicAdd(sw.stats + (uint64_t)qi * 4 + 2, 1ull);
+          return;
+        }
+      }
+      // rounds 2 and 3 travel while the columns are added
+      uint32_t d2, d3;
+      float s2, s3;
+      load_round(x, 2, tot > 128u ? 0u : tot, d2, s2);
+      load_round(x, 3, tot > 128u ? 0u : tot, d3, s3);
+      float4 R[V];
 #pragma unroll
-                for (int j = 0; j < V / 4; j++) tmax2 = fmaxf(tmax2, __ldg(tm + j));
-              }
+      for (int v = 0; v < V; v++) R[v] = make_float4(0, 0, 0, 0);
+      // ---- column terms in query order: staged slice (shared) or global, adds in registers ----
+      const uint64_t cc = ((uint64_t)x.m.w << 32) | x.m.z;
+#pragma unroll 1
+      for (uint32_t c = 0; c < ncol; c++) {
+        const uint32_t hs = (uint32_t)(cc >> (8 * c)) & 255u;
+        float4 cv[V];
+        if (hs != 255u) {
+          const float4 *cp = reinterpret_cast<const float4 *>(hot + (size_t)(hs - 1) * TILE) + lane;
+#pragma unroll
+          for (int v = 0; v < V; v++) cv[v] = cp[v * 32];
+        } else {
+          const uint32_t col = __ldg(sst + 8 + ((meta >> 24) & 15u) + c);
+          sweep_load_column_global<V>(seg.cols + (uint64_t)col * seg.col_stride + tile_lo, lane, cv);
+        }
+        if (WEIGHTS) {
+          const float w = __ldg(sw.weights + (size_t)slot * 8 + ((meta >> 24) & 15u) + c);
+          if (w != 1.0f) {
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+              cv[v].x = __fmul_rn(cv[v].x, w);
+              cv[v].y = __fmul_rn(cv[v].y, w);
+              cv[v].z = __fmul_rn(cv[v].z, w);
+              cv[v].w = __fmul_rn(cv[v].w, w);
             }
           }
         }
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          R[v].x = __fadd_rn(R[v].x, cv[v].x);
+          R[v].y = __fadd_rn(R[v].y, cv[v].y);
+          R[v].z = __fadd_rn(R[v].z, cv[v].z);
+          R[v].w = __fadd_rn(R[v].w, cv[v].w);
+        }
       }
-      // ---- D: item i + 3 — query record ----
-      if (i + 3 < n_iter) {
-        recD = make_uint4(0, 0, 0, 0);
-        if (lane < (int)kSweepRec) recD = __ldg(sw.recs + (uint64_t)slot_at(i + 3) * kSweepRec + lane);
+      // ---- compare the registers with the running k-th score ----
+      uint32_t mx = 0;
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        const uint32_t b0 = __float_as_uint(R[v].x), b1 = __float_as_uint(R[v].y), b2 = __float_as_uint(R[v].z), b3 = __float_as_uint(R[v].w);
+        mx = max(mx, max(max(b0, b1), max(b2, b3)));
       }
-
-      // ---- X: item i ----
-      if (i >= 0) {
-        const uint32_t slot = slot_at(i);
-        const uint32_t hd = __shfl_sync(FULL, recX.z, 8);
-        const uint32_t ns = hd & 255u, nt = (hd >> 8) & 255u;
-        const bool anyw = (hd >> 16) != 0u;
-        const uint32_t thr_hi = thr_s[slot];
-        bool skip = false;
-        if (PRUNE) skip = thr_hi != 0u && bound0 * 1.00001f < __uint_as_float(thr_hi);
-        if (!skip && (tot0 != 0u || nt > ns)) {
-          float4 R[V];
-          if (tot0) {
-            // ---- sparse terms: scatter (doc, score) into the warp's shared tile, query order ----
-            uint32_t own = own0, doc = pd0;
-            float s = ps0;
-            uint32_t j0 = 0;
-#pragma unroll 1
-            for (;;) {
-              const bool valid = j0 + lane < tot0;
-              if (anyw) s = __fmul_rn(s, __shfl_sync(FULL, w0, own));
-              const uint32_t local = doc - tile_lo;
-              const uint32_t o_first = __shfl_sync(FULL, own, 0);
-              if (!__any_sync(FULL, valid && own != o_first)) {
-                // one term in this round: its docs are distinct
-                if (valid) M[local] = __fadd_rn(M[local], s);
-              } else {
-                // several terms: lanes that hit the same doc add in lane (= term) order
-                const uint32_t grp = __match_any_sync(FULL, valid ? local : (0x80000000u | (uint32_t)lane));
-                const uint32_t rank = __popc(grp & lt_mask);
-                const uint32_t maxr = __reduce_max_sync(FULL, rank);
-                for (uint32_t r = 0; r <= maxr; r++) {
-                  if (valid && rank == r) M[local] = __fadd_rn(M[local], s);
-                  __syncwarp();
-                }
-              }
-              j0 += 32;
-              if (j0 >= tot0) break;
-              __syncwarp();
-              const uint32_t j = j0 + lane;
-              uint32_t o = 0;
-              uint32_t e = __shfl_sync(FULL, E0, 4);
-              if (j >= e) o = 4;
-              e = __shfl_sync(FULL, E0, o + 2);
-              if (j >= e) o += 2;
-              e = __shfl_sync(FULL, E0, o + 1);
-              if (j >= e) o += 1;
-              own = o;
-              const uint64_t idx = shfl_u64(st0, o) + j;
-              doc = tile_lo;
-              s = 0.0f;
-              if (j < tot0) {
-                doc = __ldg(seg.post_doc + idx);
-                s = __ldg(seg.post_score + idx);
+      bool hit = mx >= thr_hi && mx != 0u;
+      if (tot) {
+        // ---- sparse terms: park the register tile, add the (doc, score) postings in query order ----
+#pragma unroll
+        for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
+        __syncwarp();
+        if (tot <= 128u) {
+          float wst = 1.0f;
+          uint32_t posmap = 0;
+          if (WEIGHTS) {
+            wst = lane < 8 ? __ldg(sw.weights + (size_t)slot * 8 + lane) : 1.0f;
+            posmap = __ldg(recs + (size_t)x.slot * kSweepRecWords + 16);
+          }
+          // one round: lanes of one term hit distinct docs; terms are applied one after the other
+          auto round = [&](int rho, uint32_t d, float s) {
+            if (tot <= 32u * rho) return;
+            const bool valid = 32u * rho + lane < tot;
+            const uint32_t local = d - tile_lo;
+            const uint32_t bw = rho == 0 ? x.b.x : (rho == 1 ? x.b.y : (rho == 2 ? x.b.z : x.b.w));
+            const uint32_t myr = owner_rank(x, rho);
+            if (WEIGHTS) s = __fmul_rn(s, __shfl_sync(FULL, wst, (posmap >> (3 * myr)) & 7u));
+            if (bw == 0u) {
+              if (valid) M[local] = __fadd_rn(M[local], s);
+            } else {
+              const uint32_t r_lo = __shfl_sync(FULL, myr, 0), r_hi = __shfl_sync(FULL, myr, 31);
+              for (uint32_t r = r_lo; r <= r_hi; r++) {
+                if (valid && myr == r) M[local] = __fadd_rn(M[local], s);
+                __syncwarp();
               }
             }
             __syncwarp();
-#pragma unroll
-            for (int v = 0; v < V; v++) {
-              R[v] = *reinterpret_cast<const float4 *>(M + v * 128 + lane * 4);
-              *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = make_float4(0, 0, 0, 0);
-            }
-          } else {
-#pragma unroll
-            for (int v = 0; v < V; v++) R[v] = make_float4(0, 0, 0, 0);
-          }
-
-          // ---- column terms in query order: staged slice (shared) or global, adds in registers ----
-#pragma unroll 1
-          for (uint32_t dt = ns; dt < nt; dt++) {
-            const uint32_t code = __shfl_sync(FULL, recX.w, dt);
-            const uint32_t hs = (code >> 2) & 255u;
-            float4 c[V];
-            if (hs) {
-              const float4 *cp = reinterpret_cast<const float4 *>(hot + (size_t)(hs - 1) * TILE) + lane;
-#pragma unroll
-              for (int v = 0; v < V; v++) c[v] = cp[v * 32];
-            } else {
-              const uint64_t coff = ((uint64_t)__shfl_sync(FULL, recX.y, dt) << 32) | __shfl_sync(FULL, recX.x, dt);
-              const float4 *cp = reinterpret_cast<const float4 *>(seg.cols + coff + tile_lo) + lane;
-#pragma unroll
-              for (int v = 0; v < V; v++) c[v] = __ldg(cp + v * 32);
-            }
-            if (code & kSweepWBit) {
-              const float w = __shfl_sync(FULL, w0, dt);
-#pragma unroll
-              for (int v = 0; v < V; v++) {
-                c[v].x = __fmul_rn(c[v].x, w);
-                c[v].y = __fmul_rn(c[v].y, w);
-                c[v].z = __fmul_rn(c[v].z, w);
-                c[v].w = __fmul_rn(c[v].w, w);
-              }
-            }
-#pragma unroll
-            for (int v = 0; v < V; v++) {
-              R[v].x = __fadd_rn(R[v].x, c[v].x);
-              R[v].y = __fadd_rn(R[v].y, c[v].y);
-              R[v].z = __fadd_rn(R[v].z, c[v].z);
-              R[v].w = __fadd_rn(R[v].w, c[v].w);
-            }
-          }
-
-          // ---- compare the registers with the running k-th score ----
-          uint32_t mx = 0, n_touched = 0;
+          };
+          round(0, x.d0, x.s0);
+          round(1, x.d1, x.s1);
+          round(2, d2, s2);
+          round(3, d3, s3);
+          // the touched docs against the threshold
+          auto recheck = [&](int rho, uint32_t d) {
+            if (tot <= 32u * rho) return;
+            const uint32_t v = (32u * rho + lane < tot) ? __float_as_uint(M[d - tile_lo]) : 0u;
+            hit = hit || (v >= thr_hi && v != 0u);
+          };
+          recheck(0, x.d0);
+          recheck(1, x.d1);
+          recheck(2, d2);
+          recheck(3, d3);
+        } else {
+          sweep_scatter_long<WEIGHTS>(M, slot, tile, tile_lo, seg, sw, lane);
+          uint32_t m2 = 0;
 #pragma unroll
           for (int v = 0; v < V; v++) {
-            const uint32_t b0 = __float_as_uint(R[v].x), b1 = __float_as_uint(R[v].y), b2 = __float_as_uint(R[v].z), b3 = __float_as_uint(R[v].w);
-            mx = max(mx, max(max(b0, b1), max(b2, b3)));
-            if (STATS) n_touched += (b0 != 0u) + (b1 != 0u) + (b2 != 0u) + (b3 != 0u);
+            const float4 q = *reinterpret_cast<const float4 *>(M + v * 128 + lane * 4);
+            m2 = max(m2, max(max(__float_as_uint(q.x), __float_as_uint(q.y)), max(__float_as_uint(q.z), __float_as_uint(q.w))));
           }
-          uint32_t n_cand = 0;
-          if (__any_sync(FULL, mx >= thr_hi && mx != 0u)) {
-            // rare after warm-up: park the registers in the (zero) shared tile and walk it
-#pragma unroll
-            for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
-            __syncwarp();
-            const uint32_t qi = __shfl_sync(FULL, recX.x, 8);
-            const int32_t filter = (int32_t)__shfl_sync(FULL, recX.y, 8);
-            const uint2 t = sweep_collect<V>(M, cand, tile_lo, qi, filter, seg, sw, lane);
-            n_cand = t.y;
-            if (lane == 0 && t.x > thr_hi) thr_s[slot] = t.x;
-            __syncwarp();
-          }
-          if (STATS) {
-            uint32_t n_post = npost0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              n_touched += __shfl_xor_sync(FULL, n_touched, o);
-              n_post += __shfl_xor_sync(FULL, n_post, o);
-            }
-            const uint32_t qi = __shfl_sync(FULL, recX.x, 8);
-            if (lane == 0) {
-              if (n_touched) atomicAdd(sw.stats + (uint64_t)qi * 4 + 0, (unsigned long long)n_touched);
-              if (n_post) atomicAdd(sw.stats + (uint64_t)qi * 4 + 1, (unsigned long long)n_post);
-              if (n_cand) atomicAdd(sw.stats + (uint64_t)qi * 4 + 3, (unsigned long long)n_cand);
-            }
-          }
-        } else if (STATS && skip) {
-          const uint32_t qi = __shfl_sync(FULL, recX.x, 8);
-          if (lane == 0) atomicAdd(sw.stats + (uint64_t)qi * 4 + 2, 1ull);
+          hit = hit || (m2 >= thr_hi && m2 != 0u);
         }
       }
-
-      // ---- rotate the pipeline ----
-      recX = recP;
-      recP = recR;
-      recR = recD;
-      lo1 = lo2;
-      hi1 = hi2;
-      w0 = w1;
-      w1 = w2;
-      if (PRUNE) {
-        ub1 = ub2;
-        tmax1 = tmax2;
-        bound0 = boundN;
+      uint32_t n_cand = 0;
+      if (__any_sync(FULL, hit)) {
+        // rare after warm-up: walk the tile's final scores in shared memory
+        if (!tot) {
+#pragma unroll
+          for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
+        }
+        __syncwarp();
+        n_cand = sweep_collect<V>(M, cand, tile_lo, qi, (int32_t)__ldg(sst + 19), seg, sw, lane);
+        __syncwarp();
       }
-      tot0 = totN;
-      E0 = EN;
-      own0 = ownN;
-      pd0 = pdN;
-      ps0 = psN;
-      st0 = stN;
-      if (STATS) npost0 = npostN;
+      if (STATS) {
+        uint32_t n_touched = 0;
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          float4 q = R[v];
+          if (tot) q = *reinterpret_cast<const float4 *>(M + v * 128 + lane * 4);
+          n_touched += (q.x != 0.0f) + (q.y != 0.0f) + (q.z != 0.0f) + (q.w != 0.0f);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_touched += __shfl_xor_sync(FULL, n_touched, o);
+        if (lane == 0) {
+          const uint32_t n_post = __ldg(recs + (size_t)x.slot * kSweepRecWords + 17);
+          if (n_touched) atomicAdd(sw.stats + (uint64_t)qi * 4 + 0, (unsigned long long)n_touched);
+          if (n_post) atomicAdd(sw.stats + (uint64_t)qi * 4 + 1, (unsigned long long)n_post);
+          if (n_cand) atomicAdd(sw.stats + (uint64_t)qi * 4 + 3, (unsigned long long)n_cand);
+        }
+        __syncwarp();
+      }
+    };
+
+    // ---- software pipeline over this warp's items, unrolled by three so no state is copied ----
+    SweepItem i0, i1, i2;
+    stage_d(i0, 0);
+    stage_d(i1, 1);
+    stage_p(i0);
+#pragma unroll 1
+    for (int i = 0; i < n_iter; i += 3) {
+      stage_d(i2, i + 2);
+      stage_p(i1);
+      stage_x(i0);
+      stage_d(i0, i + 3);
+      stage_p(i2);
+      stage_x(i1);
+      stage_d(i1, i + 4);
+      stage_p(i0);
+      stage_x(i2);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// records[tile][slot]: every query slot resolved against every tile (layout above).  One thread per
+// (slot, group of kSweepTileGroup consecutive tiles): the static description is read once and each
+// term's range row is walked over consecutive entries.
+template <bool PRUNE>
+__global__ void __launch_bounds__(128) slg_sweep_records_kernel(SweepDev sw, uint32_t tile_v, bool stats) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= sw.n_slots) return;
+  const uint32_t tile0 = blockIdx.y * kSweepTileGroup;
+  const uint4 *st = sw.sstat + (size_t)s * (kSweepSlotWords / 4);
+  const uint4 r0 = __ldg(st), r1 = __ldg(st + 1), b0 = __ldg(st + 2), b1 = __ldg(st + 3), m0 = __ldg(st + 4);
+  const uint32_t m1 = __ldg(reinterpret_cast<const uint32_t *>(st + 5));
+  const uint32_t rows[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  const uint32_t bases[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const uint32_t ns = m1 & 15u, ncol = (m1 >> 4) & 15u;
+  const uint32_t rng_stride = sw.n_tiles + 1;
+  float ub[8];
+#pragma unroll
+  for (int t = 0; t < 8; t++) ub[t] = (PRUNE && (uint32_t)t < ns + ncol) ? __ldg(sw.ubw + (size_t)s * 8 + t) : 0.0f;
+  uint32_t prev[8];
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    prev[t] = 0;
+    if ((uint32_t)t < ns || (stats && (uint32_t)t < ns + ncol)) prev[t] = __ldg(sw.rng + (uint64_t)rows[t] * rng_stride + tile0);
+  }
+#pragma unroll 1
+  for (uint32_t tile = tile0; tile < tile0 + kSweepTileGroup && tile < sw.n_tiles; tile++) {
+    uint32_t rec[kSweepRecWords];
+#pragma unroll
+    for (uint32_t i = 0; i < kSweepRecWords; i++) rec[i] = 0u;
+    uint32_t E = 0, nne = 0, n_post = 0, posmap = 0;
+    uint32_t B[4] = {0u, 0u, 0u, 0u};
+    float bound = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      uint32_t next = 0;
+      if ((uint32_t)t < ns || (stats && (uint32_t)t < ns + ncol)) next = __ldg(sw.rng + (uint64_t)rows[t] * rng_stride + tile + 1);
+      const uint32_t lo = prev[t], span = next - lo;
+      prev[t] = next;
+      n_post += span;
+      const uint32_t cnt = (uint32_t)t < ns ? span : 0u;
+      if (cnt) {
+        const uint32_t adj = bases[t] + lo - E;
+        // rec[8 + nne] = adj without dynamic register indexing
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+          if (nne == (uint32_t)r) rec[8 + r] = adj;
+        if (nne && E < 128u) {
+#pragma unroll
+          for (int wd = 0; wd < 4; wd++)
+            if ((E >> 5) == (uint32_t)wd) B[wd] |= 1u << (E & 31u);
+        }
+        posmap |= (uint32_t)t << (3 * nne);
+        if (PRUNE) bound += ub[t];
+        nne++;
+        E += cnt;
+      }
+      if (PRUNE && (uint32_t)t >= ns && (uint32_t)t < ns + ncol) {
+        const float *tm = sw.col_tmax + (uint64_t)bases[t] * sw.tmax_stride + (uint64_t)tile * (tile_v / 4);
+        float tmax = 0.0f;
+        for (uint32_t j = 0; j < tile_v / 4; j++) tmax = fmaxf(tmax, __ldg(tm + j));
+        bound += __fmul_rn(tmax, ub[t]);
+      }
+    }
+    rec[0] = B[0];
+    rec[1] = B[1];
+    rec[2] = B[2];
+    rec[3] = B[3];
+    rec[4] = min(E, 0xFFFFu) | (ncol << 16) | (nne << 20) | (ns << 24);
+    rec[5] = __float_as_uint(bound);
+    rec[6] = m0.x;
+    rec[7] = m0.y;
+    rec[16] = posmap;
+    rec[17] = n_post;
+    uint4 *out = reinterpret_cast<uint4 *>(sw.records + ((size_t)tile * sw.n_slots + s) * kSweepRecWords);
+#pragma unroll
+    for (uint32_t i = 0; i < kSweepRecWords / 4; i++) out[i] = make_uint4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
   }
 }
 
@@ -527,57 +638,56 @@ __global__ void __launch_bounds__(256) slg_sweep_plan_kernel(SegmentDev seg, con
   }
 }
 
-// Query records in the kernel's canonical term order: sparse (no column) first, then column terms,
-// both in query order.  hot_slot[u] = 1 + shared-memory slot of unique term u's column, or 0;
-// u_row[u] = row of the range table.  Runs once per segment per batch.
+// Static slot descriptions (layout above): sparse terms first, then column terms, both in query
+// order.  hot_slot[u] = 1 + shared-memory slot of unique term u's column, or 0; u_row[u] = row of the
+// range table.  Runs once per segment per batch.
 __global__ void slg_build_sweep_kernel(SegmentDev seg, BatchDev bt, uint32_t n_slots, const uint32_t *hot_slot, const uint32_t *u_row,
-                                       uint4 *recs, float *weights, float *ubw, uint32_t *slot_qi) {
+                                       uint4 *sstat, float *weights, float *ubw, uint32_t *slot_qi) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_slots) return;
   const uint32_t qi = bt.q_order[slot];
   const uint32_t t0 = bt.q_term_off[qi], nt = bt.q_term_off[qi + 1] - t0;
-  uint32_t n_out = 0, ns = 0, anyw = 0;
-  uint4 *out = recs + (uint64_t)slot * kSweepRec;
+  uint32_t *out = reinterpret_cast<uint32_t *>(sstat + (uint64_t)slot * (kSweepSlotWords / 4));
+  for (uint32_t i = 0; i < kSweepSlotWords; i++) out[i] = 0u;
+  for (uint32_t i = 0; i < 8; i++) {
+    weights[(uint64_t)slot * 8 + i] = 1.0f;
+    ubw[(uint64_t)slot * 8 + i] = 0.0f;
+  }
+  uint32_t p = 0, ns = 0, ncol = 0, anyw = 0;
+  unsigned long long cc = 0;
   for (int pass = 0; pass < 2; pass++) {
     for (uint32_t t = 0; t < nt && t < kWarpMaxTerms; t++) {
       const uint32_t u = bt.qt_uterm[t0 + t];
       const uint32_t term = bt.ut_term[u];
       if (term >= seg.n_terms) continue;  // seg.postings(key) == None
-      const uint32_t df = seg.term_df[term];
-      if (df == 0) continue;
+      if (seg.term_df[term] == 0) continue;
       const int32_t col = seg.term_col ? seg.term_col[term] : -1;
       if ((col >= 0) != (pass == 1)) continue;
       const float w = bt.qt_weight[t0 + t];
-      uint64_t base;
-      uint32_t code;
-      float ub = 0.0f;
+      float ub = w;
+      out[p] = u_row[u];
       if (col >= 0) {
-        base = (uint64_t)col * seg.col_stride;
-        code = 2u | ((hot_slot ? hot_slot[u] : 0u) << 2) | ((uint32_t)col << 10);
-        ub = w;
+        out[8 + p] = (uint32_t)col;
+        const uint32_t hs = hot_slot ? hot_slot[u] : 0u;
+        cc |= (unsigned long long)(hs ? hs : 255u) << (8 * ncol);
+        ncol++;
       } else {
-        base = seg.term_start[term];
-        code = 1u;
+        out[8 + p] = (uint32_t)seg.term_start[term];
         const float mtf = seg.term_max_tf[term];
-        if (mtf > 0.0f) ub = __fmul_rn(bm25_contrib(mtf, seg.term_idf[term], seg.k1p1, seg.min_nk, 1.0f), w);
+        ub = mtf > 0.0f ? __fmul_rn(bm25_contrib(mtf, seg.term_idf[term], seg.k1p1, seg.min_nk, 1.0f), w) : 0.0f;
+        ns++;
       }
-      if (w != 1.0f) {
-        code |= kSweepWBit;
-        anyw = 1;
-      }
-      out[n_out] = make_uint4((uint32_t)base, (uint32_t)(base >> 32), u_row[u], code);
-      weights[(uint64_t)slot * 8 + n_out] = w;
-      ubw[(uint64_t)slot * 8 + n_out] = ub;
-      n_out++;
+      if (w != 1.0f) anyw = 1;
+      weights[(uint64_t)slot * 8 + p] = w;
+      ubw[(uint64_t)slot * 8 + p] = ub;
+      p++;
     }
-    if (pass == 0) ns = n_out;
   }
-  for (uint32_t t = n_out; t < kWarpMaxTerms; t++) {
-    out[t] = make_uint4(0, 0, 0, 0);
-    weights[(uint64_t)slot * 8 + t] = 1.0f;
-    ubw[(uint64_t)slot * 8 + t] = 0.0f;
-  }
-  out[8] = make_uint4(qi, (uint32_t)bt.q_filter[qi], ns | (n_out << 8) | (anyw << 16), 0u);
+  out[16] = (uint32_t)cc;
+  out[17] = (uint32_t)(cc >> 32);
+  out[18] = qi;
+  out[19] = (uint32_t)bt.q_filter[qi];
+  out[20] = ns | (ncol << 4) | (anyw << 8);
   slot_qi[slot] = qi;
 }
 

@@ -2,7 +2,7 @@
 
 Float contract (include/searchlite_gpu.h): the CTA and warp kernels sum a doc's contributions in query
 term order — bit-identical to the oracle's `bm25` mode (brute_force, query/wand.rs:527-548); the
-register-tile kernel sums the terms without a dense column first, then the column terms —
+tile-sweep kernel sums the terms with a dense column first, then the terms without one —
 bit-identical to the oracle on that permutation of the query and within the north-star 1e-5 rule of
 the query order."""
 import numpy as np
