@@ -162,7 +162,7 @@ int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, u
  *                           (default 8; 0 = no columns)
  *   "dense_min_df"     n    ... and df >= n (default 256)
  *   "max_column_bytes" n    byte budget of the columns of one segment, largest df first (default 24 GiB)
- *   "reg_tile_v"       4|8|16  tile-sweep kernel: 128 * v docs per register tile (default 4)
+ *   "reg_tile_v"       4|8     tile-sweep kernel: 128 * v docs per register tile (default 8)
  *   "sweep_min_postings" n  tile-sweep kernel: a query without a column term whose terms hold fewer than
  *                           n postings is scored posting-driven by the warp kernel instead of being swept
  *                           over every tile (default 0 = doc_count / 64; 1 = sweep every query)

@@ -133,7 +133,7 @@ struct slg_index {
   uint32_t dense_den = 8;        // a term gets a dense column when df * dense_den >= doc_count; 0 = no columns
   uint32_t dense_min_df = 256;   // ... and df >= this
   uint64_t max_column_bytes = 24ull << 30;
-  uint32_t reg_tile_v = 4;       // sweep kernel: 128 * V docs per tile (4, 8 or 16)
+  uint32_t reg_tile_v = 8;       // sweep kernel: 128 * V docs per tile (4 or 8)
   uint64_t sweep_min_postings = 0;  // sweep: a query without column terms and sum(df) below this goes to the warp kernel (0 = doc_count / 64)
   uint32_t seed_docs = 16384;    // sweep: docs of the seed pass
   Segment *find(uint32_t ord) {
@@ -163,9 +163,6 @@ struct slg_batch {
   uint32_t max_terms = 0;
   bool use_warp = false, use_reg = false;
   uint32_t plan_docs = 0, reg_v = 8;
-  DevBuf d_hot_slot, d_hot_cols;      // sweep kernel: [S][U] 1 + smem slot or 0; [S][max_hot] column offsets
-  std::vector<uint32_t> n_hot;        // per segment
-  uint32_t max_hot = 0;
   uint32_t n_heavy = 0, n_light = 0;  // sweep: slots [0, n_heavy) of q_order are swept, the rest go to the warp kernel
   uint32_t n_rows = 0, n_light_u = 0; // rows of the sweep's range table; unique terms of the light queries
   uint32_t sweep_tiles_max = 0, sub_tiles_max = 0;
@@ -306,7 +303,7 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
         if (df >= ix->dense_min_df && df * ix->dense_den >= s->doc_count) cand.push_back((uint32_t)t);
       }
       std::sort(cand.begin(), cand.end(), [&](uint32_t a, uint32_t b2) { return s->h_df[a] != s->h_df[b2] ? s->h_df[a] > s->h_df[b2] : a < b2; });
-      const uint64_t max_cols = ix->max_column_bytes / (stride * 4);
+      const uint64_t max_cols = std::min<uint64_t>(65535, ix->max_column_bytes / (stride * 4));  // 16-bit column ids in the sweep records
       if (cand.size() > max_cols) cand.resize(max_cols);
       if (!cand.empty()) {
         std::vector<int32_t> tcol(s->n_terms, -1);
@@ -519,22 +516,12 @@ int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, bool st
 }
 
 template <int V>
-size_t sweep_smem_bytes(uint32_t n_hot) {
-  return (size_t)n_hot * 128 * V * 4 + (size_t)kSweepWarps * sweep_smem_per_warp<V>();
-}
-
-// how many column slices of one tile fit next to the warps' private tiles
-uint32_t sweep_max_hot(const slg_index *ix, uint32_t v) {
-  const size_t per_warp = (size_t)128 * v * 4 + kWarpCand * 8;
-  const size_t fixed = (size_t)kSweepWarps * per_warp + 1024;  // + static shared and slack
-  if (ix->smem_optin <= fixed) return 0;
-  return (uint32_t)std::min<size_t>(253, (ix->smem_optin - fixed) / ((size_t)128 * v * 4));
-}
+size_t sweep_smem_bytes() { return (size_t)kSweepWarps * sweep_smem_per_warp<V>(); }
 
 template <int V, bool P, bool S, bool W>
 int32_t launch_sweep_t(slg_index *ix, const SegmentDev &sd, const SweepDev &sw, int grid) {
   auto kern = slg_score_sweep_kernel<V, P, S, W>;
-  const size_t smem = sweep_smem_bytes<V>(sw.n_hot);
+  const size_t smem = sweep_smem_bytes<V>();
   if (smem + 1024 > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "sweep kernel needs %zu B shared memory", smem);
   SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kSweepThreads, smem, ix->stream>>>(sd, sw);
@@ -559,7 +546,6 @@ int32_t launch_sweep_v(slg_index *ix, bool prune, bool stats, bool weights, cons
 int32_t launch_sweep(slg_index *ix, uint32_t v, bool prune, bool stats, bool weights, const SegmentDev &sd, const SweepDev &sw, int grid) {
   switch (v) {
     case 4: return launch_sweep_v<4>(ix, prune, stats, weights, sd, sw, grid);
-    case 16: return launch_sweep_v<16>(ix, prune, stats, weights, sd, sw, grid);
     default: return launch_sweep_v<8>(ix, prune, stats, weights, sd, sw, grid);
   }
 }
@@ -642,7 +628,7 @@ int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
   else if (n == "dense_min_df") ix->dense_min_df = (uint32_t)value;
   else if (n == "max_column_bytes") ix->max_column_bytes = value;
   else if (n == "reg_tile_v") {
-    if (value != 4 && value != 8 && value != 16) return fail(ix, SLG_ERR_INVALID, "reg_tile_v must be 4, 8 or 16");
+    if (value != 4 && value != 8) return fail(ix, SLG_ERR_INVALID, "reg_tile_v must be 4 or 8");
     ix->reg_tile_v = (uint32_t)value;
   } else if (n == "sweep_min_postings") ix->sweep_min_postings = value;
   else if (n == "seed_docs") ix->seed_docs = (uint32_t)value;
@@ -1084,8 +1070,24 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
     }
     bt->n_light = n_queries - bt->n_heavy;
   }
+  // swept queries are ordered by their first column term (segment 0): the warps of a CTA walk
+  // neighbouring slots at the same time and share that column's tile slice through L1
+  std::vector<uint32_t> q_col(n_queries, 0xFFFFFFFFu);
+  if (bt->use_reg && !ix->segs.empty()) {
+    const Segment *sg0 = ix->segs[0].get();
+    for (uint32_t qi = 0; qi < n_queries; qi++)
+      for (uint32_t t = q_off[qi]; t < q_off[qi + 1]; t++) {
+        const uint32_t term = ut[qt_u[t]];
+        if (term < sg0->h_term_col.size() && sg0->h_term_col[term] >= 0) {
+          q_col[qi] = (uint32_t)sg0->h_term_col[term];
+          break;
+        }
+      }
+  }
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b2) {
-    return heavy[a] != heavy[b2] ? heavy[a] > heavy[b2] : q_cost[a] > q_cost[b2];
+    if (heavy[a] != heavy[b2]) return heavy[a] > heavy[b2];
+    if (q_col[a] != q_col[b2]) return q_col[a] < q_col[b2];
+    return q_cost[a] > q_cost[b2];
   });
 
   // pack all inputs into one buffer: one H2D copy per batch
@@ -1164,28 +1166,9 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
       }
     bt->n_rows = (uint32_t)row_u.size();
     bt->n_light_u = (uint32_t)light_u.size();
-    // per segment: the columns the heavy queries use most (by query-term instances) get a shared-memory slot
-    bt->max_hot = sweep_max_hot(ix, bt->reg_v);
-    std::vector<uint32_t> hot_slot(nseg * std::max(bt->U, 1u), 0);
-    std::vector<uint64_t> hot_cols(nseg * std::max(bt->max_hot, 1u), 0);
-    bt->n_hot.assign(nseg, 0);
-    for (size_t si = 0; si < nseg; si++) {
-      const Segment *sg = ix->segs[si].get();
+    for (auto &sg : ix->segs) {
       const uint32_t tile = 128u * bt->reg_v;
       bt->sweep_tiles_max = std::max(bt->sweep_tiles_max, std::max(1u, (sg->doc_count + tile - 1) / tile));
-      if (sg->h_term_col.empty() || !bt->max_hot) continue;
-      std::vector<uint32_t> cand;
-      for (uint32_t u = 0; u < bt->U; u++)
-        if (inst[u] && ut[u] < sg->h_term_col.size() && sg->h_term_col[ut[u]] >= 0) cand.push_back(u);
-      std::sort(cand.begin(), cand.end(), [&](uint32_t a, uint32_t b2) { return inst[a] != inst[b2] ? inst[a] > inst[b2] : a < b2; });
-      // a column named by a single query gains nothing from staging
-      while (!cand.empty() && inst[cand.back()] < 2) cand.pop_back();
-      if (cand.size() > bt->max_hot) cand.resize(bt->max_hot);
-      for (size_t h = 0; h < cand.size(); h++) {
-        hot_slot[si * bt->U + cand[h]] = (uint32_t)h + 1;
-        hot_cols[si * bt->max_hot + h] = (uint64_t)sg->h_term_col[ut[cand[h]]] * sg->col_stride;
-      }
-      bt->n_hot[si] = (uint32_t)cand.size();
     }
     auto upload = [&](DevBuf &d, const void *src, size_t bytes) -> cudaError_t {
       cudaError_t e = d.alloc(bytes);
@@ -1193,8 +1176,6 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
       ix->ctr.last_h2d_bytes += bytes;
       return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, ix->stream);
     };
-    SLG_CUDA(ix, upload(bt->d_hot_slot, hot_slot.data(), hot_slot.size() * 4));
-    SLG_CUDA(ix, upload(bt->d_hot_cols, hot_cols.data(), hot_cols.size() * 8));
     SLG_CUDA(ix, upload(bt->d_u_row, u_row.data(), u_row.size() * 4));
     SLG_CUDA(ix, upload(bt->d_row_u, row_u.data(), row_u.size() * 4));
     SLG_CUDA(ix, upload(bt->d_light_u, light_u.data(), light_u.size() * 4));
@@ -1326,7 +1307,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
           count_launch(ix);
         }
         slg_build_sweep_kernel<<<(bt->n_heavy + 127) / 128, 128, 0, st>>>(
-            s->dev, bd, bt->n_heavy, bt->d_hot_slot.as<uint32_t>() + (size_t)si * bt->U, bt->d_u_row.as<uint32_t>(),
+            s->dev, bd, bt->n_heavy, bt->d_u_row.as<uint32_t>(),
             bt->sw_sstat.as<uint4>(), bt->sw_weights.as<float>(), bt->sw_ubw.as<float>(), bt->sw_slot_qi.as<uint32_t>());
         count_launch(ix);
       }
@@ -1347,12 +1328,10 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
           sw.records = bt->sw_records.as<uint32_t>();
           sw.rng = bt->sw_rng.as<uint32_t>();
           sw.col_tmax = s->col_tmax.as<float>();
-          sw.hot_cols = bt->d_hot_cols.as<uint64_t>() + (size_t)si * bt->max_hot;
           sw.filter_bits = bd.filter_bits;
           sw.n_slots = std::min(kSweepMaxSlots, bt->n_heavy - c0);
           sw.k = k;
           sw.n_tiles = sw_tiles;
-          sw.n_hot = bt->n_hot[si];
           sw.tmax_stride = s->tmax_stride;
           sw.thr_key = bd.thr_key;
           sw.topk_count = bd.topk_count;

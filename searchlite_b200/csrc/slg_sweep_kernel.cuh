@@ -63,14 +63,13 @@ constexpr uint32_t kSweepTileGroup = 8;    // tiles resolved by one thread of th
 //   [0..7]   row of the tile-range table per term position (sparse terms, and column terms when
 //            statistics are wanted); positions: sparse terms first, then column terms, query order
 //   [8..15]  sparse: first padded posting index of the term (u32); column: column index
-//   [16,17]  per column term c one byte: 1 + shared-memory slot of its staged slice, 255 = read the
-//            column from global memory
+//   [16,17]  column index of column terms 0..3, 16 bits each   [21,22] the same for column terms 4..7
 //   [18] query index  [19] filter id  [20] ns | ncol << 4 | any_weight << 8
 // per-(tile, slot) record, 20 words — the sparse terms of the slot resolved against the tile:
 //   [0..3]  B: 128-bit map over the concatenated postings of the non-empty sparse terms (query order);
 //           bit j set = the r-th (r >= 1) non-empty term starts at position j.  rank(j) = popc(B[0..j])
 //   [4] tot | ncol << 16 | nne << 20 | ns << 24   [5] upper bound of the tile for this query (PRUNE)
-//   [6,7]   copy of static words 16, 17
+//   [6,7]   copy of static words 16, 17   [18,19] copy of static words 21, 22
 //   [8..15] adj_r = first posting of the r-th non-empty sparse term - its position in the concatenation
 //   [16] 3 bits per r: term position of the r-th non-empty sparse term (weights)
 //   [17] postings of all terms of the query inside the tile (statistics)
@@ -82,10 +81,9 @@ struct SweepDev {
   const float *ubw;             // [n_slots][8] PRUNE: weight * term-wide bound (sparse) or weight (column)
   const uint32_t *rng;          // [rows][n_tiles + 1] first posting with doc >= tile * TILE
   const float *col_tmax;        // [n_cols][tmax_stride] column maxima per 512 docs (PRUNE)
-  const uint64_t *hot_cols;     // [n_hot] element offset of each staged column in seg.cols
   const uint32_t *const *filter_bits;
   uint32_t *records;            // [n_tiles][n_slots][kSweepRecWords]
-  uint32_t n_slots, k, n_tiles, n_hot;
+  uint32_t n_slots, k, n_tiles;
   uint32_t tile_begin, tile_end;  // tiles of this launch
   uint32_t seed;                  // 1: every CTA walks all tiles of the launch over its own share of the slots
   uint32_t tmax_stride;
@@ -190,15 +188,6 @@ __device__ __noinline__ uint32_t sweep_collect(const float *M, unsigned long lon
   return n_cand;
 }
 
-// A column that is not staged in shared memory (rare: more distinct columns in the batch than slots):
-// out of line so that the staged path carries none of its address arithmetic.
-template <int V>
-__device__ __noinline__ void sweep_load_column_global(const float *col, int lane, float4 *cv) {
-  const float4 *cp = reinterpret_cast<const float4 *>(col) + lane;
-#pragma unroll
-  for (int v = 0; v < V; v++) cv[v] = __ldg(cp + v * 32);
-}
-
 // Sparse postings of an item with more than 128 of them in the tile (no columns, or unusually long
 // lists): term by term straight from the range table, 32 postings at a time.  M holds the parked
 // register tile.
@@ -251,15 +240,15 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
   constexpr uint32_t TILE = 128u * V;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // layout: hot f32[n_hot][TILE] | per warp: M f32[TILE], cand u64[64]
-  float *hot = reinterpret_cast<float *>(smem_raw);
-  unsigned char *mine = smem_raw + (size_t)sw.n_hot * TILE * 4 + (size_t)warp * sweep_smem_per_warp<V>();
+  // layout per warp: M f32[TILE], cand u64[64]
+  unsigned char *mine = smem_raw + (size_t)warp * sweep_smem_per_warp<V>();
   float *M = reinterpret_cast<float *>(mine);
   unsigned long long *cand = reinterpret_cast<unsigned long long *>(mine + (size_t)TILE * 4);
-  __shared__ uint32_t s_tile;
 
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t le_mask = lt_mask | (1u << lane);
+  const uint32_t *__restrict__ post_doc = seg.post_doc;
+  const float *__restrict__ post_score = seg.post_score;
 
   // query slots of this CTA: all of them, or (seed pass) its own share
   uint32_t slot_lo = 0, slot_n = sw.n_slots;
@@ -270,53 +259,45 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
   }
   if (slot_n == 0) return;
   const int n_iter = slot_n > (uint32_t)warp ? (int)((slot_n - warp + kSweepWarps - 1) / kSweepWarps) : 0;
+  const uint32_t *__restrict__ slot_qi = sw.slot_qi + slot_lo;
 
-  for (uint32_t it = 0;; it++) {
-    __syncthreads();  // every warp is done with the previous tile's staged slices
-    uint32_t tile;
-    if (sw.seed) {
-      tile = sw.tile_begin + it;
-    } else {
-      if (threadIdx.x == 0) s_tile = sw.tile_begin + atomicAdd(sw.work_counter, 1u);
-      __syncthreads();
-      tile = s_tile;
-    }
-    if (tile >= sw.tile_end) break;
+  // tiles: the seed pass walks all tiles of the launch; the sweep proper deals them round-robin
+  for (uint32_t tile = sw.tile_begin + (sw.seed ? 0u : blockIdx.x); tile < sw.tile_end; tile += sw.seed ? 1u : gridDim.x) {
+    __syncthreads();  // keeps the warps of the CTA on one tile: they share the tile's column slices through L1
     const uint32_t tile_lo = tile * TILE;
-    const uint32_t *recs = sw.records + ((size_t)tile * sw.n_slots + slot_lo) * kSweepRecWords;
-
-    // ---- pull this tile's records into L2, stage the tile's slices of the hottest columns ----
-    for (uint32_t i = threadIdx.x * 32; i < slot_n * kSweepRecWords; i += kSweepThreads * 32) prefetch_l2(recs + i);
-    for (uint32_t i = threadIdx.x; i < sw.n_hot * (TILE / 4); i += kSweepThreads) {
-      const uint32_t h = i / (TILE / 4), o = i - h * (TILE / 4);
-      reinterpret_cast<float4 *>(hot)[i] = ldg_stream_f4(reinterpret_cast<const float4 *>(seg.cols + sw.hot_cols[h] + tile_lo) + o);
-    }
-    __syncthreads();
+    const unsigned char *__restrict__ recs =
+        reinterpret_cast<const unsigned char *>(sw.records + ((size_t)tile * sw.n_slots + slot_lo) * kSweepRecWords);
+    for (uint32_t i = threadIdx.x * 128; i < slot_n * kSweepRecWords * 4; i += kSweepThreads * 128) prefetch_l2(recs + i);
+    const float *__restrict__ cols_tile = seg.cols + tile_lo + lane * 4;
 
     // this warp walks slots rot + warp, rot + warp + 16, ... (mod slot_n): CTAs on different tiles
-    // are on different queries at any moment, so their top-k merges do not pile up on one lock
+    // are on different queries at any moment, so their top-k merges do not pile up on one lock.
+    // Slots are ordered by their first column term: the 16 warps read the same column slice at about
+    // the same time and all but the first find it in L1.
     const uint32_t rot = sw.seed ? 0u : (uint32_t)(((uint64_t)tile * 2654435761ull >> 9) % slot_n);
-    auto slot_at = [&](int p) -> uint32_t {
-      uint32_t s = rot + (uint32_t)warp + (uint32_t)kSweepWarps * (uint32_t)p;
-      if (s >= slot_n) s -= slot_n;
-      return s;  // relative to slot_lo
-    };
+    uint32_t next_slot = rot + (uint32_t)warp;  // slot of the next item to enter the pipeline
+    if (next_slot >= slot_n) next_slot -= slot_n;
+    int entered = 0;
 
-    // D: record of item p.  Every lane reads the same header words (one sector, broadcast).
-    auto stage_d = [&](SweepItem &x, int p) {
+    // D: record of the next item.  Every lane reads the same header words (one sector, broadcast).
+    auto stage_d = [&](SweepItem &x) {
       x.b = make_uint4(0, 0, 0, 0);
       x.m = make_uint4(0, 0, 0, 0);
       x.a = 0;
-      if (p < n_iter) {
-        x.slot = slot_at(p);
-        const uint32_t *rec = recs + (size_t)x.slot * kSweepRecWords;
-        x.b = __ldg(reinterpret_cast<const uint4 *>(rec));
-        x.m = __ldg(reinterpret_cast<const uint4 *>(rec) + 1);
-        if (lane < 8) x.a = __ldg(rec + 8 + lane);
-        x.qi = __ldg(sw.slot_qi + slot_lo + x.slot);
+      x.qi = 0;
+      if (entered < n_iter) {
+        x.slot = next_slot;
+        const unsigned char *rec = recs + next_slot * (kSweepRecWords * 4);
+        x.b = ldg_nc_u4(reinterpret_cast<const uint32_t *>(rec));
+        x.m = ldg_nc_u4(reinterpret_cast<const uint32_t *>(rec + 16));
+        if (lane < 8) x.a = ldg_nc_u32(rec + 32 + lane * 4);
+        x.qi = ldg_nc_u32(slot_qi + next_slot);
+        next_slot += kSweepWarps;
+        if (next_slot >= slot_n) next_slot -= slot_n;
       }
+      entered++;
     };
-    // posting index of position 32 * rho + lane of the concatenated non-empty terms
+    // rank of position 32 * rho + lane among the starts of the concatenated non-empty terms
     auto owner_rank = [&](const SweepItem &x, int rho) -> uint32_t {
       uint32_t r = 0;
       if (rho > 0) r += __popc(x.b.x);
@@ -331,12 +312,12 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
       if (tot > 32u * rho) {
         const uint32_t idx = __shfl_sync(FULL, x.a, owner_rank(x, rho)) + 32u * rho + lane;
         if (32u * rho + lane < tot) {
-          d = __ldg(seg.post_doc + idx);
-          s = __ldg(seg.post_score + idx);
+          d = ldg_nc_u32(post_doc + idx);
+          s = __uint_as_float(ldg_nc_u32(post_score + idx));
         }
       }
     };
-    // P: rounds 0 and 1 of the item's postings
+    // P: rounds 0 and 1 of the item's postings, its threshold, its first column slice towards L1
     auto stage_p = [&](SweepItem &x) {
       uint32_t tot = x.m.x & 0xFFFFu;
       x.thr = kThrInit;
@@ -351,7 +332,6 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
       if ((meta & 0xFFFFFu) == 0u) return;  // no postings and no column terms (or no item)
       const uint32_t tot = meta & 0xFFFFu, ncol = (meta >> 16) & 15u;
       const uint32_t slot = slot_lo + x.slot;
-      const uint32_t *sst = reinterpret_cast<const uint32_t *>(sw.sstat + (size_t)slot * 8);
       const uint32_t qi = x.qi;
       const uint32_t thr_hi = x.thr == kThrInit ? 0u : (uint32_t)(x.thr >> 32);
       if (PRUNE) {
@@ -369,38 +349,37 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
       float4 R[V];
 #pragma unroll
       for (int v = 0; v < V; v++) R[v] = make_float4(0, 0, 0, 0);
-      // ---- column terms in query order: staged slice (shared) or global, adds in registers ----
-      const uint64_t cc = ((uint64_t)x.m.w << 32) | x.m.z;
+      // ---- column terms in query order: the tile's slice of the column (L1), adds in registers ----
 #pragma unroll 1
       for (uint32_t c = 0; c < ncol; c++) {
-        const uint32_t hs = (uint32_t)(cc >> (8 * c)) & 255u;
-        float4 cv[V];
-        if (hs != 255u) {
-          const float4 *cp = reinterpret_cast<const float4 *>(hot + (size_t)(hs - 1) * TILE) + lane;
-#pragma unroll
-          for (int v = 0; v < V; v++) cv[v] = cp[v * 32];
+        uint32_t col;
+        if (c < 4) {
+          const uint32_t wd = c < 2 ? x.m.z : x.m.w;
+          col = (wd >> (16 * (c & 1))) & 0xFFFFu;
         } else {
-          const uint32_t col = __ldg(sst + 8 + ((meta >> 24) & 15u) + c);
-          sweep_load_column_global<V>(seg.cols + (uint64_t)col * seg.col_stride + tile_lo, lane, cv);
+          col = (ldg_nc_u32(recs + x.slot * (kSweepRecWords * 4) + 72 + (c >> 1 & 1) * 4) >> (16 * (c & 1))) & 0xFFFFu;
         }
-        if (WEIGHTS) {
-          const float w = __ldg(sw.weights + (size_t)slot * 8 + ((meta >> 24) & 15u) + c);
-          if (w != 1.0f) {
+        const float4 *cp = reinterpret_cast<const float4 *>(cols_tile + (uint64_t)col * seg.col_stride);
+        float w = 1.0f;
+        if (WEIGHTS) w = __ldg(sw.weights + (size_t)slot * 8 + ((meta >> 24) & 15u) + c);
 #pragma unroll
-            for (int v = 0; v < V; v++) {
+        for (int h = 0; h < V; h += 4) {
+          float4 cv[4];
+#pragma unroll
+          for (int v = 0; v < 4; v++) cv[v] = __ldg(cp + (h + v) * 32);
+#pragma unroll
+          for (int v = 0; v < 4; v++) {
+            if (WEIGHTS) {
               cv[v].x = __fmul_rn(cv[v].x, w);
               cv[v].y = __fmul_rn(cv[v].y, w);
               cv[v].z = __fmul_rn(cv[v].z, w);
               cv[v].w = __fmul_rn(cv[v].w, w);
             }
+            R[h + v].x = __fadd_rn(R[h + v].x, cv[v].x);
+            R[h + v].y = __fadd_rn(R[h + v].y, cv[v].y);
+            R[h + v].z = __fadd_rn(R[h + v].z, cv[v].z);
+            R[h + v].w = __fadd_rn(R[h + v].w, cv[v].w);
           }
-        }
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          R[v].x = __fadd_rn(R[v].x, cv[v].x);
-          R[v].y = __fadd_rn(R[v].y, cv[v].y);
-          R[v].z = __fadd_rn(R[v].z, cv[v].z);
-          R[v].w = __fadd_rn(R[v].w, cv[v].w);
         }
       }
       // ---- compare the registers with the running k-th score ----
@@ -421,22 +400,22 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
           uint32_t posmap = 0;
           if (WEIGHTS) {
             wst = lane < 8 ? __ldg(sw.weights + (size_t)slot * 8 + lane) : 1.0f;
-            posmap = __ldg(recs + (size_t)x.slot * kSweepRecWords + 16);
+            posmap = ldg_nc_u32(recs + x.slot * (kSweepRecWords * 4) + 64);
           }
           // one round: lanes of one term hit distinct docs; terms are applied one after the other
           auto round = [&](int rho, uint32_t d, float s) {
             if (tot <= 32u * rho) return;
             const bool valid = 32u * rho + lane < tot;
-            const uint32_t local = d - tile_lo;
+            float *slot_p = M + (d - tile_lo);
             const uint32_t bw = rho == 0 ? x.b.x : (rho == 1 ? x.b.y : (rho == 2 ? x.b.z : x.b.w));
-            const uint32_t myr = owner_rank(x, rho);
-            if (WEIGHTS) s = __fmul_rn(s, __shfl_sync(FULL, wst, (posmap >> (3 * myr)) & 7u));
+            if (WEIGHTS) s = __fmul_rn(s, __shfl_sync(FULL, wst, (posmap >> (3 * owner_rank(x, rho))) & 7u));
             if (bw == 0u) {
-              if (valid) M[local] = __fadd_rn(M[local], s);
+              if (valid) *slot_p = __fadd_rn(*slot_p, s);
             } else {
-              const uint32_t r_lo = __shfl_sync(FULL, myr, 0), r_hi = __shfl_sync(FULL, myr, 31);
-              for (uint32_t r = r_lo; r <= r_hi; r++) {
-                if (valid && myr == r) M[local] = __fadd_rn(M[local], s);
+              const uint32_t myr = __popc(bw & le_mask);  // rank inside the round
+              const uint32_t r_hi = __popc(bw);
+              for (uint32_t r = 0; r <= r_hi; r++) {
+                if (valid && myr == r) *slot_p = __fadd_rn(*slot_p, s);
                 __syncwarp();
               }
             }
@@ -475,7 +454,8 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
           for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
         }
         __syncwarp();
-        n_cand = sweep_collect<V>(M, cand, tile_lo, qi, (int32_t)__ldg(sst + 19), seg, sw, lane);
+        const int32_t filter = (int32_t)__ldg(reinterpret_cast<const uint32_t *>(sw.sstat + (size_t)slot * 8) + 19);
+        n_cand = sweep_collect<V>(M, cand, tile_lo, qi, filter, seg, sw, lane);
         __syncwarp();
       }
       if (STATS) {
@@ -489,7 +469,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n_touched += __shfl_xor_sync(FULL, n_touched, o);
         if (lane == 0) {
-          const uint32_t n_post = __ldg(recs + (size_t)x.slot * kSweepRecWords + 17);
+          const uint32_t n_post = ldg_nc_u32(recs + x.slot * (kSweepRecWords * 4) + 68);
           if (n_touched) atomicAdd(sw.stats + (uint64_t)qi * 4 + 0, (unsigned long long)n_touched);
           if (n_post) atomicAdd(sw.stats + (uint64_t)qi * 4 + 1, (unsigned long long)n_post);
           if (n_cand) atomicAdd(sw.stats + (uint64_t)qi * 4 + 3, (unsigned long long)n_cand);
@@ -500,18 +480,18 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
 
     // ---- software pipeline over this warp's items, unrolled by three so no state is copied ----
     SweepItem i0, i1, i2;
-    stage_d(i0, 0);
-    stage_d(i1, 1);
+    stage_d(i0);
+    stage_d(i1);
     stage_p(i0);
 #pragma unroll 1
     for (int i = 0; i < n_iter; i += 3) {
-      stage_d(i2, i + 2);
+      stage_d(i2);
       stage_p(i1);
       stage_x(i0);
-      stage_d(i0, i + 3);
+      stage_d(i0);
       stage_p(i2);
       stage_x(i1);
-      stage_d(i1, i + 4);
+      stage_d(i1);
       stage_p(i0);
       stage_x(i2);
     }
@@ -529,7 +509,8 @@ __global__ void __launch_bounds__(128) slg_sweep_records_kernel(SweepDev sw, uin
   const uint32_t tile0 = blockIdx.y * kSweepTileGroup;
   const uint4 *st = sw.sstat + (size_t)s * (kSweepSlotWords / 4);
   const uint4 r0 = __ldg(st), r1 = __ldg(st + 1), b0 = __ldg(st + 2), b1 = __ldg(st + 3), m0 = __ldg(st + 4);
-  const uint32_t m1 = __ldg(reinterpret_cast<const uint32_t *>(st + 5));
+  const uint4 m1v = __ldg(st + 5);
+  const uint32_t m1 = m1v.x;
   const uint32_t rows[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
   const uint32_t bases[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   const uint32_t ns = m1 & 15u, ncol = (m1 >> 4) & 15u;
@@ -592,6 +573,8 @@ __global__ void __launch_bounds__(128) slg_sweep_records_kernel(SweepDev sw, uin
     rec[7] = m0.y;
     rec[16] = posmap;
     rec[17] = n_post;
+    rec[18] = m1v.y;
+    rec[19] = m1v.z;
     uint4 *out = reinterpret_cast<uint4 *>(sw.records + ((size_t)tile * sw.n_slots + s) * kSweepRecWords);
 #pragma unroll
     for (uint32_t i = 0; i < kSweepRecWords / 4; i++) out[i] = make_uint4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
@@ -639,9 +622,8 @@ __global__ void __launch_bounds__(256) slg_sweep_plan_kernel(SegmentDev seg, con
 }
 
 // Static slot descriptions (layout above): sparse terms first, then column terms, both in query
-// order.  hot_slot[u] = 1 + shared-memory slot of unique term u's column, or 0; u_row[u] = row of the
-// range table.  Runs once per segment per batch.
-__global__ void slg_build_sweep_kernel(SegmentDev seg, BatchDev bt, uint32_t n_slots, const uint32_t *hot_slot, const uint32_t *u_row,
+// order.  u_row[u] = row of the range table.  Runs once per segment per batch.
+__global__ void slg_build_sweep_kernel(SegmentDev seg, BatchDev bt, uint32_t n_slots, const uint32_t *u_row,
                                        uint4 *sstat, float *weights, float *ubw, uint32_t *slot_qi) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_slots) return;
@@ -654,7 +636,6 @@ __global__ void slg_build_sweep_kernel(SegmentDev seg, BatchDev bt, uint32_t n_s
     ubw[(uint64_t)slot * 8 + i] = 0.0f;
   }
   uint32_t p = 0, ns = 0, ncol = 0, anyw = 0;
-  unsigned long long cc = 0;
   for (int pass = 0; pass < 2; pass++) {
     for (uint32_t t = 0; t < nt && t < kWarpMaxTerms; t++) {
       const uint32_t u = bt.qt_uterm[t0 + t];
@@ -668,8 +649,7 @@ __global__ void slg_build_sweep_kernel(SegmentDev seg, BatchDev bt, uint32_t n_s
       out[p] = u_row[u];
       if (col >= 0) {
         out[8 + p] = (uint32_t)col;
-        const uint32_t hs = hot_slot ? hot_slot[u] : 0u;
-        cc |= (unsigned long long)(hs ? hs : 255u) << (8 * ncol);
+        out[(ncol < 4 ? 16 : 19) + (ncol >> 1)] |= (uint32_t)col << (16 * (ncol & 1));  // words 16, 17, 21, 22
         ncol++;
       } else {
         out[8 + p] = (uint32_t)seg.term_start[term];
@@ -683,8 +663,6 @@ __global__ void slg_build_sweep_kernel(SegmentDev seg, BatchDev bt, uint32_t n_s
       p++;
     }
   }
-  out[16] = (uint32_t)cc;
-  out[17] = (uint32_t)(cc >> 32);
   out[18] = qi;
   out[19] = (uint32_t)bt.q_filter[qi];
   out[20] = ns | (ncol << 4) | (anyw << 8);

@@ -49,7 +49,7 @@ def test_bm25_bit_exact_vs_oracle(small, kernel, tile_docs, sub_docs, k):
     gi.close()
 
 
-@pytest.mark.parametrize("v", [4, 8, 16])
+@pytest.mark.parametrize("v", [4, 8])
 @pytest.mark.parametrize("k", [1, 11, 32])
 @pytest.mark.parametrize("dense_den", [0, 8, 64])
 @pytest.mark.parametrize("min_postings", [0, 1])
