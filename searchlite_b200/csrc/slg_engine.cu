@@ -136,6 +136,7 @@ struct slg_index {
   uint32_t reg_tile_v = 8;       // sweep kernel: 128 * V docs per tile (4 or 8)
   uint64_t sweep_min_postings = 0;  // sweep: a query without column terms and sum(df) below this goes to the warp kernel (0 = doc_count / 64)
   uint32_t seed_docs = 16384;    // sweep: docs of the seed pass
+  uint32_t part_tiles = 0;       // sweep: tiles per unit of work (0 = automatic)
   Segment *find(uint32_t ord) {
     for (auto &s : segs)
       if (s->ord == ord) return s.get();
@@ -167,7 +168,8 @@ struct slg_batch {
   uint32_t n_rows = 0, n_light_u = 0; // rows of the sweep's range table; unique terms of the light queries
   uint32_t sweep_tiles_max = 0, sub_tiles_max = 0;
   DevBuf d_u_row, d_row_u, d_light_u; // [U] row or ~0; [n_rows] unique term; [n_light_u] unique term
-  DevBuf sw_sstat, sw_weights, sw_ubw, sw_rng, sw_records, sw_slot_qi;
+  DevBuf sw_sstat, sw_weights, sw_ubw, sw_rng, sw_records, d_chunk_cols;  // d_chunk_cols: [S][n_chunks][kSweepStage]
+  uint32_t n_chunks = 0;
   bool any_weight = false;             // some scored term has weight != 1
   DevBuf seg_hits, seg_counts;  // [S][Q][k], [S][Q]
   DevBuf out_hits, out_counts;  // merged (aliases seg buffers when S == 1)
@@ -296,7 +298,7 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
     d.post_score = s->post_score.as<float>();
     // dense columns for the high-df terms, largest df first until the byte budget is spent
     if (ix->dense_den && s->doc_count) {
-      const uint64_t stride = align_up((uint64_t)s->doc_count, 2048) + 2048;  // a whole tile past the end stays in bounds and zero
+      const uint64_t stride = align_up((uint64_t)s->doc_count, 4096) + 4096;  // a whole staged block past the end stays in bounds and zero
       std::vector<uint32_t> cand;
       for (uint64_t t = 0; t < s->n_terms; t++) {
         const uint64_t df = s->h_df[t];
@@ -515,9 +517,6 @@ int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, bool st
   }
 }
 
-template <int V>
-size_t sweep_smem_bytes() { return (size_t)kSweepWarps * sweep_smem_per_warp<V>(); }
-
 template <int V, bool P, bool S, bool W>
 int32_t launch_sweep_t(slg_index *ix, const SegmentDev &sd, const SweepDev &sw, int grid) {
   auto kern = slg_score_sweep_kernel<V, P, S, W>;
@@ -632,6 +631,7 @@ int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
     ix->reg_tile_v = (uint32_t)value;
   } else if (n == "sweep_min_postings") ix->sweep_min_postings = value;
   else if (n == "seed_docs") ix->seed_docs = (uint32_t)value;
+  else if (n == "part_tiles") ix->part_tiles = (uint32_t)value;
   else return fail(ix, SLG_ERR_INVALID, "unknown option '%s'", name);
   return SLG_OK;
 }
@@ -1170,12 +1170,37 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
       const uint32_t tile = 128u * bt->reg_v;
       bt->sweep_tiles_max = std::max(bt->sweep_tiles_max, std::max(1u, (sg->doc_count + tile - 1) / tile));
     }
+    // per segment and chunk of kSweepChunk swept slots: the columns staged in shared memory — the ones
+    // the chunk's queries name most
+    bt->n_chunks = (bt->n_heavy + kSweepChunk - 1) / kSweepChunk;
+    std::vector<uint32_t> chunk_cols(std::max<size_t>(1, nseg * bt->n_chunks * kSweepStage), 0xFFFFFFFFu);
+    for (size_t si = 0; si < nseg; si++) {
+      const Segment *sg = ix->segs[si].get();
+      if (sg->h_term_col.empty()) continue;
+      for (uint32_t ch = 0; ch < bt->n_chunks; ch++) {
+        std::vector<std::pair<uint32_t, uint32_t>> cnt;  // (column, uses)
+        for (uint32_t sl = ch * kSweepChunk; sl < std::min(bt->n_heavy, (ch + 1) * kSweepChunk); sl++) {
+          const uint32_t qi = order[sl];
+          for (uint32_t t = q_off[qi]; t < q_off[qi + 1]; t++) {
+            const uint32_t term = ut[qt_u[t]];
+            if (term >= sg->h_term_col.size() || sg->h_term_col[term] < 0) continue;
+            const uint32_t col = (uint32_t)sg->h_term_col[term];
+            auto it = std::find_if(cnt.begin(), cnt.end(), [&](const auto &p2) { return p2.first == col; });
+            if (it == cnt.end()) cnt.emplace_back(col, 1u);
+            else it->second++;
+          }
+        }
+        std::stable_sort(cnt.begin(), cnt.end(), [](const auto &a, const auto &b2) { return a.second > b2.second; });
+        for (size_t i = 0; i < cnt.size() && i < kSweepStage; i++) chunk_cols[(si * bt->n_chunks + ch) * kSweepStage + i] = cnt[i].first;
+      }
+    }
     auto upload = [&](DevBuf &d, const void *src, size_t bytes) -> cudaError_t {
       cudaError_t e = d.alloc(bytes);
       if (e != cudaSuccess || !bytes) return e;
       ix->ctr.last_h2d_bytes += bytes;
       return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, ix->stream);
     };
+    SLG_CUDA(ix, upload(bt->d_chunk_cols, chunk_cols.data(), chunk_cols.size() * 4));
     SLG_CUDA(ix, upload(bt->d_u_row, u_row.data(), u_row.size() * 4));
     SLG_CUDA(ix, upload(bt->d_row_u, row_u.data(), row_u.size() * 4));
     SLG_CUDA(ix, upload(bt->d_light_u, light_u.data(), light_u.size() * 4));
@@ -1185,7 +1210,6 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
       SLG_CUDA(ix, bt->sw_sstat.alloc((size_t)bt->n_heavy * kSweepSlotWords * 4));
       SLG_CUDA(ix, bt->sw_weights.alloc((size_t)bt->n_heavy * 8 * 4));
       SLG_CUDA(ix, bt->sw_ubw.alloc((size_t)bt->n_heavy * 8 * 4));
-      SLG_CUDA(ix, bt->sw_slot_qi.alloc((size_t)bt->n_heavy * 4));
       SLG_CUDA(ix, bt->sw_records.alloc((size_t)bt->sweep_tiles_max * std::min(bt->n_heavy, kSweepMaxSlots) * kSweepRecWords * 4));
       SLG_CUDA(ix, bt->sw_rng.alloc((size_t)std::max(bt->n_rows, 1u) * (bt->sweep_tiles_max + 1) * 4));
     }
@@ -1307,29 +1331,30 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
           count_launch(ix);
         }
         slg_build_sweep_kernel<<<(bt->n_heavy + 127) / 128, 128, 0, st>>>(
-            s->dev, bd, bt->n_heavy, bt->d_u_row.as<uint32_t>(),
-            bt->sw_sstat.as<uint4>(), bt->sw_weights.as<float>(), bt->sw_ubw.as<float>(), bt->sw_slot_qi.as<uint32_t>());
+            s->dev, bd, bt->n_heavy, bt->d_u_row.as<uint32_t>(), bt->d_chunk_cols.as<uint32_t>() + (size_t)si * bt->n_chunks * kSweepStage,
+            bt->sw_sstat.as<uint4>(), bt->sw_weights.as<float>(), bt->sw_ubw.as<float>());
         count_launch(ix);
       }
       SLG_CUDA(ix, cudaGetLastError());
       SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));
       // ---- scoring ----
       if (bt->use_reg && bt->n_heavy) {
-        // seed pass over the first tiles (slots split across CTAs), then the sweep proper
+        // seed pass over the first tiles (gives every query a threshold), then the rest in ranges of tiles
         const uint32_t seed_tiles = std::min(sw_tiles, std::max(1u, std::min(sw_tiles / 4, ix->seed_docs / sw_tile)));
-        uint32_t chunk_id = 0;
-        for (uint32_t c0 = 0; c0 < bt->n_heavy; c0 += kSweepMaxSlots, chunk_id++) {
-          if (chunk_id + 1 >= 64) return fail(ix, SLG_ERR_UNSUPPORTED, "more than %u swept queries in one batch", 63 * kSweepMaxSlots);
+        uint32_t launch_id = 0;
+        for (uint32_t c0 = 0; c0 < bt->n_heavy; c0 += kSweepMaxSlots) {
+          if (launch_id + 3 >= 64) return fail(ix, SLG_ERR_UNSUPPORTED, "more than %u swept queries in one batch", 30 * kSweepMaxSlots);
           SweepDev sw{};
           sw.sstat = bt->sw_sstat.as<uint4>() + (size_t)c0 * (kSweepSlotWords / 4);
           sw.weights = bt->sw_weights.as<float>() + (size_t)c0 * 8;
           sw.ubw = bt->sw_ubw.as<float>() + (size_t)c0 * 8;
-          sw.slot_qi = bt->sw_slot_qi.as<uint32_t>() + c0;
           sw.records = bt->sw_records.as<uint32_t>();
           sw.rng = bt->sw_rng.as<uint32_t>();
           sw.col_tmax = s->col_tmax.as<float>();
+          sw.chunk_cols = bt->d_chunk_cols.as<uint32_t>() + ((size_t)si * bt->n_chunks + c0 / kSweepChunk) * kSweepStage;
           sw.filter_bits = bd.filter_bits;
           sw.n_slots = std::min(kSweepMaxSlots, bt->n_heavy - c0);
+          sw.n_chunks = (sw.n_slots + kSweepChunk - 1) / kSweepChunk;
           sw.k = k;
           sw.n_tiles = sw_tiles;
           sw.tmax_stride = s->tmax_stride;
@@ -1337,7 +1362,6 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
           sw.topk_count = bd.topk_count;
           sw.lock = bd.lock;
           sw.topk_keys = bd.topk_keys;
-          sw.work_counter = bd.work_counter + 1 + chunk_id;
           sw.stats = bd.stats;
           {
             const dim3 rgrid((sw.n_slots + 127) / 128, (sw_tiles + kSweepTileGroup - 1) / kSweepTileGroup);
@@ -1346,17 +1370,23 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
             SLG_CUDA(ix, cudaGetLastError());
             count_launch(ix);
           }
-          sw.seed = 1;
+          sw.work_counter = bd.work_counter + 1 + launch_id++;
           sw.tile_begin = 0;
           sw.tile_end = seed_tiles;
-          rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, bt->any_weight, s->dev, sw, (int)std::min<uint32_t>((uint32_t)ix->n_sm, sw.n_slots));
+          sw.part_tiles = seed_tiles;
+          rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, bt->any_weight, s->dev, sw, (int)std::min<uint32_t>((uint32_t)ix->n_sm, sw.n_chunks));
           if (rc) return rc;
           count_launch(ix);
           if (seed_tiles < sw_tiles) {
-            sw.seed = 0;
+            sw.work_counter = bd.work_counter + 1 + launch_id++;
             sw.tile_begin = seed_tiles;
             sw.tile_end = sw_tiles;
-            rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, bt->any_weight, s->dev, sw, (int)std::min<uint32_t>((uint32_t)ix->n_sm, sw_tiles - seed_tiles));
+            // enough units for an even finish: about 24 per SM
+            const uint32_t want_parts = std::max(1u, (24u * (uint32_t)ix->n_sm + sw.n_chunks - 1) / sw.n_chunks);
+            sw.part_tiles = ix->part_tiles ? ix->part_tiles : std::max(32u, (sw_tiles - seed_tiles + want_parts - 1) / want_parts);
+            sw.part_tiles = (sw.part_tiles + 31u) & ~31u;  // whole staged blocks
+            const uint64_t units = (uint64_t)sw.n_chunks * ((sw_tiles - seed_tiles + sw.part_tiles - 1) / sw.part_tiles);
+            rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, bt->any_weight, s->dev, sw, (int)std::min<uint64_t>((uint64_t)ix->n_sm, units));
             if (rc) return rc;
             count_launch(ix);
           }

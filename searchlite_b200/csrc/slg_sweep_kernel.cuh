@@ -54,8 +54,10 @@ namespace slg {
 
 constexpr int kSweepThreads = 512;  // 16 warps, one CTA per SM
 constexpr int kSweepWarps = kSweepThreads / 32;
+constexpr uint32_t kSweepChunk = kSweepWarps;  // query slots per chunk: one per warp
+constexpr uint32_t kSweepBlockDocs = 4096; // docs per staged block of column slices (SB = 4096 / TILE tiles)
 constexpr uint32_t kSweepSlotWords = 32;   // static description of one query slot
-constexpr uint32_t kSweepRecWords = 20;    // per-(tile, slot) record
+constexpr uint32_t kSweepRecWords = 20;    // per-(slot, tile) record
 constexpr uint32_t kSweepMaxSlots = 16384; // query slots per launch
 constexpr uint32_t kSweepTileGroup = 8;    // tiles resolved by one thread of the record kernel
 
@@ -63,29 +65,29 @@ constexpr uint32_t kSweepTileGroup = 8;    // tiles resolved by one thread of th
 //   [0..7]   row of the tile-range table per term position (sparse terms, and column terms when
 //            statistics are wanted); positions: sparse terms first, then column terms, query order
 //   [8..15]  sparse: first padded posting index of the term (u32); column: column index
-//   [16,17]  column index of column terms 0..3, 16 bits each   [21,22] the same for column terms 4..7
+//   [16,17]  per column term c one byte: index of its slice among the chunk's staged columns, or
+//            255 = read the column from global memory
 //   [18] query index  [19] filter id  [20] ns | ncol << 4 | any_weight << 8
-// per-(tile, slot) record, 20 words — the sparse terms of the slot resolved against the tile:
+// per-(slot, tile) record, 20 words — the sparse terms of the slot resolved against the tile:
 //   [0..3]  B: 128-bit map over the concatenated postings of the non-empty sparse terms (query order);
 //           bit j set = the r-th (r >= 1) non-empty term starts at position j.  rank(j) = popc(B[0..j])
 //   [4] tot | ncol << 16 | nne << 20 | ns << 24   [5] upper bound of the tile for this query (PRUNE)
-//   [6,7]   copy of static words 16, 17   [18,19] copy of static words 21, 22
 //   [8..15] adj_r = first posting of the r-th non-empty sparse term - its position in the concatenation
 //   [16] 3 bits per r: term position of the r-th non-empty sparse term (weights)
 //   [17] postings of all terms of the query inside the tile (statistics)
 
 struct SweepDev {
   const uint4 *sstat;           // [n_slots][8]
-  const uint32_t *slot_qi;      // [n_slots] query index of the slot
   const float *weights;         // [n_slots][8] term positions as in sstat
   const float *ubw;             // [n_slots][8] PRUNE: weight * term-wide bound (sparse) or weight (column)
   const uint32_t *rng;          // [rows][n_tiles + 1] first posting with doc >= tile * TILE
   const float *col_tmax;        // [n_cols][tmax_stride] column maxima per 512 docs (PRUNE)
+  const uint32_t *chunk_cols;   // [n_chunks][kSweepStage] staged column of the chunk or ~0
   const uint32_t *const *filter_bits;
-  uint32_t *records;            // [n_tiles][n_slots][kSweepRecWords]
-  uint32_t n_slots, k, n_tiles;
+  uint32_t *records;            // [n_slots][n_tiles][kSweepRecWords]
+  uint32_t n_slots, k, n_tiles, n_chunks;
   uint32_t tile_begin, tile_end;  // tiles of this launch
-  uint32_t seed;                  // 1: every CTA walks all tiles of the launch over its own share of the slots
+  uint32_t part_tiles;            // tiles per unit of work (chunk x tile range)
   uint32_t tmax_stride;
   unsigned long long *thr_key;
   uint32_t *topk_count, *lock;
@@ -94,17 +96,63 @@ struct SweepDev {
   unsigned long long *stats;
 };
 
+// column slices staged per chunk: what fits next to the warps' private tiles
+template <int V>
+__host__ __device__ constexpr uint32_t sweep_stage() { return V >= 8 ? 3u : 4u; }
+constexpr uint32_t kSweepStage = 4;  // row length of the chunk_cols table (>= sweep_stage<V>())
+
 template <int V>
 __host__ __device__ constexpr size_t sweep_smem_per_warp() {
-  return (size_t)128 * V * 4 + kWarpCand * 8;  // M f32[128*V] | cand u64[64]
+  // M f32[128*V] | cand u64[64] | record ring u32[8][24] | posting ring u32[4][128]
+  return (size_t)128 * V * 4 + kWarpCand * 8 + 768 + 2048;
+}
+template <int V>
+__host__ __device__ constexpr size_t sweep_smem_bytes() {
+  // slices f32[2][stage][kSweepBlockDocs] | mbarrier[2] | per-warp areas
+  return (size_t)2 * sweep_stage<V>() * kSweepBlockDocs * 4 + 16 + (size_t)kSweepWarps * sweep_smem_per_warp<V>();
 }
 
-__device__ __forceinline__ uint4 ld_cg_u4(const void *p) {
-  uint4 v;
-  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
+// ---- mbarrier + bulk-copy (TMA) primitives for the slice staging ----
+__device__ __forceinline__ void mbar_init(void *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(void *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem, const void *gmem, uint32_t bytes, void *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem)),
+               "l"(gmem), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // append the keys of one ballot round to the warp's candidate buffer; when more than 32 are pending,
 // sort, keep the best k and raise the local threshold (exact: nothing is dropped unsorted)
@@ -125,17 +173,21 @@ __device__ __forceinline__ void sweep_push(bool pass, unsigned long long key, un
   }
 }
 
-// Slow path of one (query, tile): M holds the final scores of the tile.  Collect the keys that beat
-// the query's current k-th key and merge them into the query's global top-k (push_top_k,
-// query/wand.rs:905-916).  Returns the number of candidates collected.
+// Slow path of one (query, tile): M holds the final scores of the tile.  The keys that beat the
+// warp's current k-th key go to its local candidate list (at most 32 entries between calls; every key
+// that can still be in the query's top k is in it).  state = {cnt, thr}.
+struct SweepLocal {
+  unsigned long long thr;
+  uint32_t cnt;
+};
 template <int V>
-__device__ __noinline__ uint32_t sweep_collect(const float *M, unsigned long long *cand, uint32_t tile_lo, uint32_t qi, int32_t filter,
-                                               const SegmentDev &seg, const SweepDev &sw, int lane) {
+__device__ __noinline__ SweepLocal sweep_collect(const float *M, unsigned long long *cand, uint32_t tile_lo, int32_t filter,
+                                                  SweepLocal st, const SegmentDev &seg, const SweepDev &sw, int lane) {
   constexpr uint32_t TILE = 128u * V;
   const uint32_t k = sw.k;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  unsigned long long thr = ld_cg_u64(sw.thr_key + qi);
-  uint32_t cnt = 0;
+  unsigned long long thr = st.thr;
+  uint32_t cnt = st.cnt;
 #pragma unroll 1
   for (uint32_t i0 = 0; i0 < TILE; i0 += 128) {
     const uint32_t i = i0 + lane * 4;
@@ -155,37 +207,40 @@ __device__ __noinline__ uint32_t sweep_collect(const float *M, unsigned long lon
     }
   }
   __syncwarp();
-  const uint32_t n_cand = cnt;
-  if (cnt > 0) {
-    const unsigned long long thr_now = ld_cg_u64(sw.thr_key + qi);
-    const bool useful = lane < (int)cnt && cand[lane] > thr_now;  // cnt <= 32 after every append
-    if (__any_sync(0xFFFFFFFFu, useful)) {
-      if (lane == 0) {
-        while (atomicCAS(sw.lock + qi, 0u, 1u) != 0u) __nanosleep(64);
-        __threadfence();
-      }
-      __syncwarp();
-      const uint32_t ng = ld_cg_u32(sw.topk_count + qi);
-      unsigned long long *gk = sw.topk_keys + (uint64_t)qi * k;
-      if (lane < (int)ng) cand[cnt + lane] = ld_cg_u64(gk + lane);
-      uint32_t total = cnt + ng;
-      for (uint32_t z = total + lane; z < kWarpCand; z += 32) cand[z] = 0ull;
-      __syncwarp();
-      warp_sort64_desc(cand, lane);
-      total = min(total, k);
-      if (lane < (int)total) st_cg_u64(gk + lane, cand[lane]);
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) {
-        st_cg_u32(sw.topk_count + qi, total);
-        if (total == k) st_cg_u64(sw.thr_key + qi, cand[k - 1]);
-        __threadfence();
-        atomicExch(sw.lock + qi, 0u);
-      }
-      __syncwarp();
-    }
+  st.thr = thr;
+  st.cnt = cnt;
+  return st;
+}
+
+// merge the warp's local candidates into the query's global top-k (push_top_k, query/wand.rs:905-916)
+__device__ __noinline__ void sweep_merge_global(unsigned long long *cand, uint32_t cnt, uint32_t qi, const SweepDev &sw, int lane) {
+  const uint32_t k = sw.k;
+  const unsigned long long thr_now = ld_cg_u64(sw.thr_key + qi);
+  const bool useful = lane < (int)cnt && cand[lane] > thr_now;  // cnt <= 32 after every append
+  if (!__any_sync(0xFFFFFFFFu, useful)) return;
+  if (lane == 0) {
+    while (atomicCAS(sw.lock + qi, 0u, 1u) != 0u) __nanosleep(64);
+    __threadfence();
   }
-  return n_cand;
+  __syncwarp();
+  const uint32_t ng = ld_cg_u32(sw.topk_count + qi);
+  unsigned long long *gk = sw.topk_keys + (uint64_t)qi * k;
+  if (lane < (int)ng) cand[cnt + lane] = ld_cg_u64(gk + lane);
+  uint32_t total = cnt + ng;
+  for (uint32_t z = total + lane; z < kWarpCand; z += 32) cand[z] = 0ull;
+  __syncwarp();
+  warp_sort64_desc(cand, lane);
+  total = min(total, k);
+  if (lane < (int)total) st_cg_u64(gk + lane, cand[lane]);
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) {
+    st_cg_u32(sw.topk_count + qi, total);
+    if (total == k) st_cg_u64(sw.thr_key + qi, cand[k - 1]);
+    __threadfence();
+    atomicExch(sw.lock + qi, 0u);
+  }
+  __syncwarp();
 }
 
 // Sparse postings of an item with more than 128 of them in the tile (no columns, or unusually long
@@ -223,283 +278,334 @@ __device__ __noinline__ void sweep_scatter_long(float *M, uint32_t slot, uint32_
   }
 }
 
-// one item of a warp's pipeline
-struct SweepItem {
-  uint4 b;          // record words 0..3 (every lane holds the same values)
-  uint4 m;          // record words 4..7
-  uint32_t a;       // lane r < 8: adj_r
-  uint32_t d0, d1;  // postings of rounds 0 and 1: doc, score
-  float s0, s1;
-  uint32_t slot, qi;
-  unsigned long long thr;  // the query's k-th key when the item entered the pipeline's last stage
-};
-
+// One CTA = one chunk of 16 query slots (one per warp) over a range of tiles.  The slots of a chunk
+// are neighbours in the column-sorted slot order, so a handful of column slices — bulk-copied (TMA)
+// into shared memory one block of kSweepBlockDocs docs ahead — serve most of their column terms.
+// Each warp keeps its query's running threshold and candidates to itself for the whole range and
+// merges into the query's global list once at the end; its records and postings arrive through
+// private cp.async rings, four and two tiles ahead.
 template <int V, bool PRUNE, bool STATS, bool WEIGHTS>
 __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const SegmentDev seg, const SweepDev sw) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr uint32_t TILE = 128u * V;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
+  constexpr uint32_t STAGE = sweep_stage<V>();
+  constexpr uint32_t SB = kSweepBlockDocs / TILE;  // tiles per staged block
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // layout per warp: M f32[TILE], cand u64[64]
-  unsigned char *mine = smem_raw + (size_t)warp * sweep_smem_per_warp<V>();
+  float *slices = reinterpret_cast<float *>(smem_raw);  // [2][STAGE][kSweepBlockDocs]
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)2 * STAGE * kSweepBlockDocs * 4);  // [2]
+  unsigned char *mine = smem_raw + (size_t)2 * STAGE * kSweepBlockDocs * 4 + 16 + (size_t)warp * sweep_smem_per_warp<V>();
   float *M = reinterpret_cast<float *>(mine);
   unsigned long long *cand = reinterpret_cast<unsigned long long *>(mine + (size_t)TILE * 4);
+  uint32_t *recring = reinterpret_cast<uint32_t *>(mine + (size_t)TILE * 4 + kWarpCand * 8);  // [8][24]
+  uint32_t *postring = recring + 192;                                                          // [4][128]
+  __shared__ uint32_t s_unit;
 
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t le_mask = lt_mask | (1u << lane);
   const uint32_t *__restrict__ post_doc = seg.post_doc;
   const float *__restrict__ post_score = seg.post_score;
+  const uint32_t n_parts = (sw.tile_end - sw.tile_begin + sw.part_tiles - 1) / sw.part_tiles;
+  const uint32_t n_units = sw.n_chunks * n_parts;
 
-  // query slots of this CTA: all of them, or (seed pass) its own share
-  uint32_t slot_lo = 0, slot_n = sw.n_slots;
-  if (sw.seed) {
-    const uint32_t per = (sw.n_slots + gridDim.x - 1) / gridDim.x;
-    slot_lo = min(blockIdx.x * per, sw.n_slots);
-    slot_n = min(per, sw.n_slots - slot_lo);
+  if (threadIdx.x == 0) {
+    mbar_init(mbar, 1);
+    mbar_init(mbar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (slot_n == 0) return;
-  const int n_iter = slot_n > (uint32_t)warp ? (int)((slot_n - warp + kSweepWarps - 1) / kSweepWarps) : 0;
-  const uint32_t *__restrict__ slot_qi = sw.slot_qi + slot_lo;
+  uint32_t phase0 = 0, phase1 = 0;  // parity of the next completion of each slice buffer
 
-  // tiles: the seed pass walks all tiles of the launch; the sweep proper deals them round-robin
-  for (uint32_t tile = sw.tile_begin + (sw.seed ? 0u : blockIdx.x); tile < sw.tile_end; tile += sw.seed ? 1u : gridDim.x) {
-    __syncthreads();  // keeps the warps of the CTA on one tile: they share the tile's column slices through L1
-    const uint32_t tile_lo = tile * TILE;
-    const unsigned char *__restrict__ recs =
-        reinterpret_cast<const unsigned char *>(sw.records + ((size_t)tile * sw.n_slots + slot_lo) * kSweepRecWords);
-    for (uint32_t i = threadIdx.x * 128; i < slot_n * kSweepRecWords * 4; i += kSweepThreads * 128) prefetch_l2(recs + i);
-    const float *__restrict__ cols_tile = seg.cols + tile_lo + lane * 4;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_unit = atomicAdd(sw.work_counter, 1u);
+    __syncthreads();
+    const uint32_t unit = s_unit;
+    if (unit >= n_units) break;
+    const uint32_t chunk = unit % sw.n_chunks, part = unit / sw.n_chunks;
+    const uint32_t t0 = sw.tile_begin + part * sw.part_tiles, t1 = min(t0 + sw.part_tiles, sw.tile_end);
+    const uint32_t n_blocks = (t1 - t0 + SB - 1) / SB;
 
-    // this warp walks slots rot + warp, rot + warp + 16, ... (mod slot_n): CTAs on different tiles
-    // are on different queries at any moment, so their top-k merges do not pile up on one lock.
-    // Slots are ordered by their first column term: the 16 warps read the same column slice at about
-    // the same time and all but the first find it in L1.
-    const uint32_t rot = sw.seed ? 0u : (uint32_t)(((uint64_t)tile * 2654435761ull >> 9) % slot_n);
-    uint32_t next_slot = rot + (uint32_t)warp;  // slot of the next item to enter the pipeline
-    if (next_slot >= slot_n) next_slot -= slot_n;
-    int entered = 0;
-
-    // D: record of the next item.  Every lane reads the same header words (one sector, broadcast).
-    auto stage_d = [&](SweepItem &x) {
-      x.b = make_uint4(0, 0, 0, 0);
-      x.m = make_uint4(0, 0, 0, 0);
-      x.a = 0;
-      x.qi = 0;
-      if (entered < n_iter) {
-        x.slot = next_slot;
-        const unsigned char *rec = recs + next_slot * (kSweepRecWords * 4);
-        x.b = ldg_nc_u4(reinterpret_cast<const uint32_t *>(rec));
-        x.m = ldg_nc_u4(reinterpret_cast<const uint32_t *>(rec + 16));
-        if (lane < 8) x.a = ldg_nc_u32(rec + 32 + lane * 4);
-        x.qi = ldg_nc_u32(slot_qi + next_slot);
-        next_slot += kSweepWarps;
-        if (next_slot >= slot_n) next_slot -= slot_n;
+    // ---- the chunk's staged columns: one bulk copy per column and block, issued by thread 0 ----
+    auto issue_block = [&](uint32_t j) {  // block j of the unit -> buffer j & 1
+      const uint32_t buf = j & 1u;
+      uint32_t n_stage = 0;
+#pragma unroll
+      for (uint32_t i = 0; i < STAGE; i++)
+        if (__ldg(sw.chunk_cols + (size_t)chunk * kSweepStage + i) != 0xFFFFFFFFu) n_stage = i + 1;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive_expect_tx(mbar + buf, n_stage * kSweepBlockDocs * 4);
+      for (uint32_t i = 0; i < n_stage; i++) {
+        const uint32_t c = __ldg(sw.chunk_cols + (size_t)chunk * kSweepStage + i);
+        bulk_copy_g2s(slices + ((size_t)buf * STAGE + i) * kSweepBlockDocs,
+                      seg.cols + (uint64_t)c * seg.col_stride + (uint64_t)(t0 + j * SB) * TILE, kSweepBlockDocs * 4, mbar + buf);
       }
-      entered++;
+    };
+    if (threadIdx.x == 0) issue_block(0);
+
+    // ---- this warp's query ----
+    const uint32_t slot = chunk * kSweepChunk + warp;
+    const bool active = slot < sw.n_slots;
+    const uint32_t *sst = reinterpret_cast<const uint32_t *>(sw.sstat + (size_t)(active ? slot : 0) * 8);
+    const uint32_t smeta = active ? __ldg(sst + 20) : 0u;
+    const uint32_t ns = smeta & 15u, ncol = (smeta >> 4) & 15u;
+    const uint64_t cc = ((uint64_t)__ldg(sst + 17) << 32) | __ldg(sst + 16);
+    const uint32_t qi = __ldg(sst + 18);
+    const int32_t filter = (int32_t)__ldg(sst + 19);
+    const uint32_t colidx = (lane < 8 && (uint32_t)lane < ncol) ? __ldg(sst + 8 + ns + lane) : 0u;  // lane c: column of column term c
+    float wst = 1.0f, wcol = 1.0f;
+    if (WEIGHTS && active && lane < 8) {
+      wst = __ldg(sw.weights + (size_t)slot * 8 + lane);
+      if ((uint32_t)lane < ncol) wcol = __ldg(sw.weights + (size_t)slot * 8 + ns + lane);
+    }
+    (void)wst;
+    (void)wcol;
+    SweepLocal loc;
+    loc.thr = active ? ld_cg_u64(sw.thr_key + qi) : ~0ull;
+    loc.cnt = 0;
+    const uint32_t *__restrict__ recs = sw.records + (size_t)(active ? slot : 0) * sw.n_tiles * kSweepRecWords;
+
+    auto copy_record = [&](uint32_t tile) {
+      if (active && tile < t1 && lane < (int)(kSweepRecWords / 4))
+        cp_async_16(recring + ((tile - t0) & 7u) * 24 + lane * 4, recs + (size_t)tile * kSweepRecWords + lane * 4);
     };
     // rank of position 32 * rho + lane among the starts of the concatenated non-empty terms
-    auto owner_rank = [&](const SweepItem &x, int rho) -> uint32_t {
+    auto owner_rank = [&](const uint4 &b, int rho) -> uint32_t {
       uint32_t r = 0;
-      if (rho > 0) r += __popc(x.b.x);
-      if (rho > 1) r += __popc(x.b.y);
-      if (rho > 2) r += __popc(x.b.z);
-      const uint32_t bw = rho == 0 ? x.b.x : (rho == 1 ? x.b.y : (rho == 2 ? x.b.z : x.b.w));
+      if (rho > 0) r += __popc(b.x);
+      if (rho > 1) r += __popc(b.y);
+      if (rho > 2) r += __popc(b.z);
+      const uint32_t bw = rho == 0 ? b.x : (rho == 1 ? b.y : (rho == 2 ? b.z : b.w));
       return r + __popc(bw & le_mask);
     };
-    auto load_round = [&](const SweepItem &x, int rho, uint32_t tot, uint32_t &d, float &s) {
-      d = tile_lo;
-      s = 0.0f;
-      if (tot > 32u * rho) {
-        const uint32_t idx = __shfl_sync(FULL, x.a, owner_rank(x, rho)) + 32u * rho + lane;
-        if (32u * rho + lane < tot) {
-          d = ldg_nc_u32(post_doc + idx);
-          s = __uint_as_float(ldg_nc_u32(post_score + idx));
+    // rounds 0 and 1 of a tile's postings: asynchronous copies into the posting ring
+    auto copy_postings = [&](uint32_t tile) {
+      if (!active || tile >= t1) return;
+      const uint32_t *rr = recring + ((tile - t0) & 7u) * 24;
+      const uint4 b = *reinterpret_cast<const uint4 *>(rr);
+      const uint32_t tot = rr[4] & 0xFFFFu;
+      if (tot == 0u || tot > 128u) return;
+      const uint32_t a = lane < 8 ? rr[8 + lane] : 0u;
+      uint32_t *pr = postring + ((tile - t0) & 3u) * 128;
+      {
+        const uint32_t idx = __shfl_sync(FULL, a, owner_rank(b, 0)) + lane;
+        if ((uint32_t)lane < tot) {
+          cp_async_4(pr + lane, post_doc + idx);
+          cp_async_4(pr + 32 + lane, post_score + idx);
         }
       }
-    };
-    // P: rounds 0 and 1 of the item's postings, its threshold, its first column slice towards L1
-    auto stage_p = [&](SweepItem &x) {
-      uint32_t tot = x.m.x & 0xFFFFu;
-      x.thr = kThrInit;
-      if (x.m.x & 0xFFFFFu) x.thr = ld_cg_u64(sw.thr_key + x.qi);
-      if (tot > 128u) tot = 0;
-      load_round(x, 0, tot, x.d0, x.s0);
-      load_round(x, 1, tot, x.d1, x.s1);
-    };
-    // X: the item itself
-    auto stage_x = [&](SweepItem &x) {
-      const uint32_t meta = x.m.x;
-      if ((meta & 0xFFFFFu) == 0u) return;  // no postings and no column terms (or no item)
-      const uint32_t tot = meta & 0xFFFFu, ncol = (meta >> 16) & 15u;
-      const uint32_t slot = slot_lo + x.slot;
-      const uint32_t qi = x.qi;
-      const uint32_t thr_hi = x.thr == kThrInit ? 0u : (uint32_t)(x.thr >> 32);
-      if (PRUNE) {
-        // safe skip: nothing in this tile can reach the k-th score (the postings in flight are dropped)
-        if (thr_hi != 0u && __uint_as_float(x.m.y) * 1.00001f < __uint_as_float(thr_hi)) {
-          if (STATS && lane == 0) atomicAdd(sw.stats + (uint64_t)qi * 4 + 2, 1ull);
-          return;
+      if (tot > 32u) {
+        const uint32_t idx = __shfl_sync(FULL, a, owner_rank(b, 1)) + 32u + lane;
+        if (32u + lane < tot) {
+          cp_async_4(pr + 64 + lane, post_doc + idx);
+          cp_async_4(pr + 96 + lane, post_score + idx);
         }
-      }
-      // rounds 2 and 3 travel while the columns are added
-      uint32_t d2, d3;
-      float s2, s3;
-      load_round(x, 2, tot > 128u ? 0u : tot, d2, s2);
-      load_round(x, 3, tot > 128u ? 0u : tot, d3, s3);
-      float4 R[V];
-#pragma unroll
-      for (int v = 0; v < V; v++) R[v] = make_float4(0, 0, 0, 0);
-      // ---- column terms in query order: the tile's slice of the column (L1), adds in registers ----
-#pragma unroll 1
-      for (uint32_t c = 0; c < ncol; c++) {
-        uint32_t col;
-        if (c < 4) {
-          const uint32_t wd = c < 2 ? x.m.z : x.m.w;
-          col = (wd >> (16 * (c & 1))) & 0xFFFFu;
-        } else {
-          col = (ldg_nc_u32(recs + x.slot * (kSweepRecWords * 4) + 72 + (c >> 1 & 1) * 4) >> (16 * (c & 1))) & 0xFFFFu;
-        }
-        const float4 *cp = reinterpret_cast<const float4 *>(cols_tile + (uint64_t)col * seg.col_stride);
-        float w = 1.0f;
-        if (WEIGHTS) w = __ldg(sw.weights + (size_t)slot * 8 + ((meta >> 24) & 15u) + c);
-#pragma unroll
-        for (int h = 0; h < V; h += 4) {
-          float4 cv[4];
-#pragma unroll
-          for (int v = 0; v < 4; v++) cv[v] = __ldg(cp + (h + v) * 32);
-#pragma unroll
-          for (int v = 0; v < 4; v++) {
-            if (WEIGHTS) {
-              cv[v].x = __fmul_rn(cv[v].x, w);
-              cv[v].y = __fmul_rn(cv[v].y, w);
-              cv[v].z = __fmul_rn(cv[v].z, w);
-              cv[v].w = __fmul_rn(cv[v].w, w);
-            }
-            R[h + v].x = __fadd_rn(R[h + v].x, cv[v].x);
-            R[h + v].y = __fadd_rn(R[h + v].y, cv[v].y);
-            R[h + v].z = __fadd_rn(R[h + v].z, cv[v].z);
-            R[h + v].w = __fadd_rn(R[h + v].w, cv[v].w);
-          }
-        }
-      }
-      // ---- compare the registers with the running k-th score ----
-      uint32_t mx = 0;
-#pragma unroll
-      for (int v = 0; v < V; v++) {
-        const uint32_t b0 = __float_as_uint(R[v].x), b1 = __float_as_uint(R[v].y), b2 = __float_as_uint(R[v].z), b3 = __float_as_uint(R[v].w);
-        mx = max(mx, max(max(b0, b1), max(b2, b3)));
-      }
-      bool hit = mx >= thr_hi && mx != 0u;
-      if (tot) {
-        // ---- sparse terms: park the register tile, add the (doc, score) postings in query order ----
-#pragma unroll
-        for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
-        __syncwarp();
-        if (tot <= 128u) {
-          float wst = 1.0f;
-          uint32_t posmap = 0;
-          if (WEIGHTS) {
-            wst = lane < 8 ? __ldg(sw.weights + (size_t)slot * 8 + lane) : 1.0f;
-            posmap = ldg_nc_u32(recs + x.slot * (kSweepRecWords * 4) + 64);
-          }
-          // one round: lanes of one term hit distinct docs; terms are applied one after the other
-          auto round = [&](int rho, uint32_t d, float s) {
-            if (tot <= 32u * rho) return;
-            const bool valid = 32u * rho + lane < tot;
-            float *slot_p = M + (d - tile_lo);
-            const uint32_t bw = rho == 0 ? x.b.x : (rho == 1 ? x.b.y : (rho == 2 ? x.b.z : x.b.w));
-            if (WEIGHTS) s = __fmul_rn(s, __shfl_sync(FULL, wst, (posmap >> (3 * owner_rank(x, rho))) & 7u));
-            if (bw == 0u) {
-              if (valid) *slot_p = __fadd_rn(*slot_p, s);
-            } else {
-              const uint32_t myr = __popc(bw & le_mask);  // rank inside the round
-              const uint32_t r_hi = __popc(bw);
-              for (uint32_t r = 0; r <= r_hi; r++) {
-                if (valid && myr == r) *slot_p = __fadd_rn(*slot_p, s);
-                __syncwarp();
-              }
-            }
-            __syncwarp();
-          };
-          round(0, x.d0, x.s0);
-          round(1, x.d1, x.s1);
-          round(2, d2, s2);
-          round(3, d3, s3);
-          // the touched docs against the threshold
-          auto recheck = [&](int rho, uint32_t d) {
-            if (tot <= 32u * rho) return;
-            const uint32_t v = (32u * rho + lane < tot) ? __float_as_uint(M[d - tile_lo]) : 0u;
-            hit = hit || (v >= thr_hi && v != 0u);
-          };
-          recheck(0, x.d0);
-          recheck(1, x.d1);
-          recheck(2, d2);
-          recheck(3, d3);
-        } else {
-          sweep_scatter_long<WEIGHTS>(M, slot, tile, tile_lo, seg, sw, lane);
-          uint32_t m2 = 0;
-#pragma unroll
-          for (int v = 0; v < V; v++) {
-            const float4 q = *reinterpret_cast<const float4 *>(M + v * 128 + lane * 4);
-            m2 = max(m2, max(max(__float_as_uint(q.x), __float_as_uint(q.y)), max(__float_as_uint(q.z), __float_as_uint(q.w))));
-          }
-          hit = hit || (m2 >= thr_hi && m2 != 0u);
-        }
-      }
-      uint32_t n_cand = 0;
-      if (__any_sync(FULL, hit)) {
-        // rare after warm-up: walk the tile's final scores in shared memory
-        if (!tot) {
-#pragma unroll
-          for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
-        }
-        __syncwarp();
-        const int32_t filter = (int32_t)__ldg(reinterpret_cast<const uint32_t *>(sw.sstat + (size_t)slot * 8) + 19);
-        n_cand = sweep_collect<V>(M, cand, tile_lo, qi, filter, seg, sw, lane);
-        __syncwarp();
-      }
-      if (STATS) {
-        uint32_t n_touched = 0;
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          float4 q = R[v];
-          if (tot) q = *reinterpret_cast<const float4 *>(M + v * 128 + lane * 4);
-          n_touched += (q.x != 0.0f) + (q.y != 0.0f) + (q.z != 0.0f) + (q.w != 0.0f);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n_touched += __shfl_xor_sync(FULL, n_touched, o);
-        if (lane == 0) {
-          const uint32_t n_post = ldg_nc_u32(recs + x.slot * (kSweepRecWords * 4) + 68);
-          if (n_touched) atomicAdd(sw.stats + (uint64_t)qi * 4 + 0, (unsigned long long)n_touched);
-          if (n_post) atomicAdd(sw.stats + (uint64_t)qi * 4 + 1, (unsigned long long)n_post);
-          if (n_cand) atomicAdd(sw.stats + (uint64_t)qi * 4 + 3, (unsigned long long)n_cand);
-        }
-        __syncwarp();
       }
     };
 
-    // ---- software pipeline over this warp's items, unrolled by three so no state is copied ----
-    SweepItem i0, i1, i2;
-    stage_d(i0);
-    stage_d(i1);
-    stage_p(i0);
+    // ---- prologue of the warp's rings: records of t0 .. t0 + 3, postings of t0 and t0 + 1 ----
+    copy_record(t0);
+    copy_record(t0 + 1);
+    copy_record(t0 + 2);
+    copy_record(t0 + 3);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    copy_postings(t0);
+    copy_postings(t0 + 1);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+
 #pragma unroll 1
-    for (int i = 0; i < n_iter; i += 3) {
-      stage_d(i2);
-      stage_p(i1);
-      stage_x(i0);
-      stage_d(i0);
-      stage_p(i2);
-      stage_x(i1);
-      stage_d(i1);
-      stage_p(i0);
-      stage_x(i2);
+    for (uint32_t j = 0; j < n_blocks; j++) {
+      __syncthreads();  // every warp is done with block j - 1: its buffer may be overwritten
+      if (threadIdx.x == 0 && j + 1 < n_blocks) issue_block(j + 1);
+      const uint32_t buf = j & 1u;
+      if (buf == 0) {
+        mbar_wait(mbar, phase0);
+        phase0 ^= 1u;
+      } else {
+        mbar_wait(mbar + 1, phase1);
+        phase1 ^= 1u;
+      }
+      if (!active) continue;
+      const float *blk = slices + (size_t)buf * STAGE * kSweepBlockDocs + lane * 4;
+
+#pragma unroll 1
+      for (uint32_t t = t0 + j * SB; t < min(t0 + (j + 1) * SB, t1); t++) {
+        // ring upkeep: everything issued two tiles ago has landed (record t + 2, postings t)
+        cp_async_wait<1>();
+        __syncwarp();
+        copy_record(t + 4);
+        copy_postings(t + 2);
+        cp_async_commit();
+
+        // ---- the item (query, tile t) ----
+        const uint32_t tile_lo = t * TILE;
+        const uint32_t *rr = recring + ((t - t0) & 7u) * 24;
+        const uint4 b = *reinterpret_cast<const uint4 *>(rr);
+        const uint32_t meta = rr[4];
+        const uint32_t tot = meta & 0xFFFFu;
+        const uint32_t thr_hi = loc.thr == kThrInit ? 0u : (uint32_t)(loc.thr >> 32);
+        if ((tot | ncol) == 0u) continue;
+        if (PRUNE && thr_hi != 0u && __uint_as_float(rr[5]) * 1.00001f < __uint_as_float(thr_hi)) {
+          if (STATS && lane == 0) atomicAdd(sw.stats + (uint64_t)qi * 4 + 2, 1ull);
+          continue;
+        }
+        const uint32_t a = lane < 8 ? rr[8 + lane] : 0u;
+        // rounds 2 and 3 travel while the columns are added
+        uint32_t d2 = tile_lo, d3 = tile_lo;
+        float s2 = 0.0f, s3 = 0.0f;
+        if (tot > 64u && tot <= 128u) {
+          uint32_t idx = __shfl_sync(FULL, a, owner_rank(b, 2)) + 64u + lane;
+          if (64u + lane < tot) {
+            d2 = ldg_nc_u32(post_doc + idx);
+            s2 = __uint_as_float(ldg_nc_u32(post_score + idx));
+          }
+          if (tot > 96u) {
+            idx = __shfl_sync(FULL, a, owner_rank(b, 3)) + 96u + lane;
+            if (96u + lane < tot) {
+              d3 = ldg_nc_u32(post_doc + idx);
+              s3 = __uint_as_float(ldg_nc_u32(post_score + idx));
+            }
+          }
+        }
+        unsigned long long thr_new = 0ull;
+        if (((t - t0) & 63u) == 63u) thr_new = ld_cg_u64(sw.thr_key + qi);  // what other ranges of this query found
+        float4 R[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) R[v] = make_float4(0, 0, 0, 0);
+        // ---- column terms in query order: staged slice (shared) or global, adds in registers ----
+        const uint32_t in_blk = (t - t0 - j * SB) * TILE;
+#pragma unroll 1
+        for (uint32_t c = 0; c < ncol; c++) {
+          const uint32_t code = (uint32_t)(cc >> (8 * c)) & 255u;
+          const float4 *cp;
+          if (code < STAGE) cp = reinterpret_cast<const float4 *>(blk + (size_t)code * kSweepBlockDocs + in_blk);
+          else cp = reinterpret_cast<const float4 *>(seg.cols + (uint64_t)__shfl_sync(FULL, colidx, c) * seg.col_stride + tile_lo) + lane;
+          float w = 1.0f;
+          if (WEIGHTS) w = __shfl_sync(FULL, wcol, c);
+#pragma unroll
+          for (int h = 0; h < V; h += 4) {
+            float4 cv[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) cv[v] = cp[(h + v) * 32];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+              if (WEIGHTS) {
+                cv[v].x = __fmul_rn(cv[v].x, w);
+                cv[v].y = __fmul_rn(cv[v].y, w);
+                cv[v].z = __fmul_rn(cv[v].z, w);
+                cv[v].w = __fmul_rn(cv[v].w, w);
+              }
+              R[h + v].x = __fadd_rn(R[h + v].x, cv[v].x);
+              R[h + v].y = __fadd_rn(R[h + v].y, cv[v].y);
+              R[h + v].z = __fadd_rn(R[h + v].z, cv[v].z);
+              R[h + v].w = __fadd_rn(R[h + v].w, cv[v].w);
+            }
+          }
+        }
+        // ---- compare the registers with the running k-th score ----
+        uint32_t mx = 0;
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          const uint32_t b0 = __float_as_uint(R[v].x), b1 = __float_as_uint(R[v].y), b2 = __float_as_uint(R[v].z), b3 = __float_as_uint(R[v].w);
+          mx = max(mx, max(max(b0, b1), max(b2, b3)));
+        }
+        bool hit = mx >= thr_hi && mx != 0u;
+        if (tot) {
+          // ---- sparse terms: park the register tile, add the (doc, score) postings in query order ----
+#pragma unroll
+          for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
+          __syncwarp();
+          if (tot <= 128u) {
+            const uint32_t *pr = postring + ((t - t0) & 3u) * 128;
+            const uint32_t d0 = pr[lane], d1 = pr[64 + lane];
+            const float s0 = __uint_as_float(pr[32 + lane]), s1 = __uint_as_float(pr[96 + lane]);
+            const uint32_t posmap = WEIGHTS ? rr[16] : 0u;
+            (void)posmap;
+            // one round: lanes of one term hit distinct docs; terms are applied one after the other
+            auto round = [&](int rho, uint32_t d, float s) {
+              if (tot <= 32u * rho) return;
+              const bool valid = 32u * rho + lane < tot;
+              float *slot_p = M + (valid ? d - tile_lo : 0u);
+              const uint32_t bw = rho == 0 ? b.x : (rho == 1 ? b.y : (rho == 2 ? b.z : b.w));
+              if (WEIGHTS) s = __fmul_rn(s, __shfl_sync(FULL, wst, (posmap >> (3 * owner_rank(b, rho))) & 7u));
+              if (bw == 0u) {
+                if (valid) *slot_p = __fadd_rn(*slot_p, s);
+              } else {
+                const uint32_t myr = __popc(bw & le_mask);  // rank inside the round
+                const uint32_t r_hi = __popc(bw);
+                for (uint32_t r = 0; r <= r_hi; r++) {
+                  if (valid && myr == r) *slot_p = __fadd_rn(*slot_p, s);
+                  __syncwarp();
+                }
+              }
+              __syncwarp();
+            };
+            round(0, d0, s0);
+            round(1, d1, s1);
+            round(2, d2, s2);
+            round(3, d3, s3);
+            // the touched docs against the threshold
+            auto recheck = [&](int rho, uint32_t d) {
+              if (tot <= 32u * rho) return;
+              const uint32_t v = (32u * rho + lane < tot) ? __float_as_uint(M[d - tile_lo]) : 0u;
+              hit = hit || (v >= thr_hi && v != 0u);
+            };
+            recheck(0, d0);
+            recheck(1, d1);
+            recheck(2, d2);
+            recheck(3, d3);
+          } else {
+            sweep_scatter_long<WEIGHTS>(M, slot, t, tile_lo, seg, sw, lane);
+            uint32_t m2 = 0;
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+              const float4 q = *reinterpret_cast<const float4 *>(M + v * 128 + lane * 4);
+              m2 = max(m2, max(max(__float_as_uint(q.x), __float_as_uint(q.y)), max(__float_as_uint(q.z), __float_as_uint(q.w))));
+            }
+            hit = hit || (m2 >= thr_hi && m2 != 0u);
+          }
+        }
+        const uint32_t cnt_before = loc.cnt;
+        if (__any_sync(FULL, hit)) {
+          // rare after warm-up: walk the tile's final scores in shared memory
+          if (!tot) {
+#pragma unroll
+            for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
+          }
+          __syncwarp();
+          loc = sweep_collect<V>(M, cand, tile_lo, filter, loc, seg, sw, lane);
+        }
+        if (thr_new > loc.thr && thr_new != kThrInit) loc.thr = thr_new;
+        if (STATS) {
+          uint32_t n_touched = 0;
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            float4 q = R[v];
+            if (tot) q = *reinterpret_cast<const float4 *>(M + v * 128 + lane * 4);
+            n_touched += (q.x != 0.0f) + (q.y != 0.0f) + (q.z != 0.0f) + (q.w != 0.0f);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) n_touched += __shfl_xor_sync(FULL, n_touched, o);
+          if (lane == 0) {
+            if (n_touched) atomicAdd(sw.stats + (uint64_t)qi * 4 + 0, (unsigned long long)n_touched);
+            if (rr[17]) atomicAdd(sw.stats + (uint64_t)qi * 4 + 1, (unsigned long long)rr[17]);
+            if (loc.cnt > cnt_before) atomicAdd(sw.stats + (uint64_t)qi * 4 + 3, (unsigned long long)(loc.cnt - cnt_before));
+          }
+          __syncwarp();
+        }
+      }
     }
+    cp_async_wait<0>();
+    __syncwarp();
+    if (active && loc.cnt) sweep_merge_global(cand, loc.cnt, qi, sw, lane);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// records[tile][slot]: every query slot resolved against every tile (layout above).  One thread per
+// records[slot][tile]: every query slot resolved against every tile (layout above).  One thread per
 // (slot, group of kSweepTileGroup consecutive tiles): the static description is read once and each
 // term's range row is walked over consecutive entries.
 template <bool PRUNE>
@@ -569,13 +675,9 @@ __global__ void __launch_bounds__(128) slg_sweep_records_kernel(SweepDev sw, uin
     rec[3] = B[3];
     rec[4] = min(E, 0xFFFFu) | (ncol << 16) | (nne << 20) | (ns << 24);
     rec[5] = __float_as_uint(bound);
-    rec[6] = m0.x;
-    rec[7] = m0.y;
     rec[16] = posmap;
     rec[17] = n_post;
-    rec[18] = m1v.y;
-    rec[19] = m1v.z;
-    uint4 *out = reinterpret_cast<uint4 *>(sw.records + ((size_t)tile * sw.n_slots + s) * kSweepRecWords);
+    uint4 *out = reinterpret_cast<uint4 *>(sw.records + ((size_t)s * sw.n_tiles + tile) * kSweepRecWords);
 #pragma unroll
     for (uint32_t i = 0; i < kSweepRecWords / 4; i++) out[i] = make_uint4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
   }
@@ -622,9 +724,10 @@ __global__ void __launch_bounds__(256) slg_sweep_plan_kernel(SegmentDev seg, con
 }
 
 // Static slot descriptions (layout above): sparse terms first, then column terms, both in query
-// order.  u_row[u] = row of the range table.  Runs once per segment per batch.
-__global__ void slg_build_sweep_kernel(SegmentDev seg, BatchDev bt, uint32_t n_slots, const uint32_t *u_row,
-                                       uint4 *sstat, float *weights, float *ubw, uint32_t *slot_qi) {
+// order.  u_row[u] = row of the range table; chunk_cols = the columns staged for each chunk of
+// kSweepChunk slots.  Runs once per segment per batch.
+__global__ void slg_build_sweep_kernel(SegmentDev seg, BatchDev bt, uint32_t n_slots, const uint32_t *u_row, const uint32_t *chunk_cols,
+                                       uint4 *sstat, float *weights, float *ubw) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_slots) return;
   const uint32_t qi = bt.q_order[slot];
@@ -649,7 +752,10 @@ __global__ void slg_build_sweep_kernel(SegmentDev seg, BatchDev bt, uint32_t n_s
       out[p] = u_row[u];
       if (col >= 0) {
         out[8 + p] = (uint32_t)col;
-        out[(ncol < 4 ? 16 : 19) + (ncol >> 1)] |= (uint32_t)col << (16 * (ncol & 1));  // words 16, 17, 21, 22
+        uint32_t code = 255u;
+        for (uint32_t i = 0; i < kSweepStage; i++)
+          if (chunk_cols[(uint64_t)(slot / kSweepChunk) * kSweepStage + i] == (uint32_t)col) code = i;
+        out[16 + (ncol >> 2)] |= code << (8 * (ncol & 3));
         ncol++;
       } else {
         out[8 + p] = (uint32_t)seg.term_start[term];
@@ -666,7 +772,6 @@ __global__ void slg_build_sweep_kernel(SegmentDev seg, BatchDev bt, uint32_t n_s
   out[18] = qi;
   out[19] = (uint32_t)bt.q_filter[qi];
   out[20] = ns | (ncol << 4) | (anyw << 8);
-  slot_qi[slot] = qi;
 }
 
 // ------------------------------------------------------------------------------------------------

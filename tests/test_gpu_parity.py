@@ -79,7 +79,7 @@ def test_register_kernel_is_the_default_for_plain_or_queries(small):
     assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
     assert_engine_parity(gi, _oracle(seg), qb, 11, a)
     # the column budget caps how many terms get a column; results stay within the contract
-    capped = GpuIndex(0, options={**DENSE, "max_column_bytes": 3 * (53248 * 4)})
+    capped = GpuIndex(0, options={**DENSE, "max_column_bytes": 3 * (57344 * 4)})
     capped.load_segment(seg)
     assert sum(capped.term_has_column(0, t) for t in range(200)) == 3
     assert_engine_parity(capped, _oracle(seg), qb, 11, capped.search_batch(qb, 11, "bm25"))
