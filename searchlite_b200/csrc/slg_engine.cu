@@ -90,7 +90,7 @@ struct Segment {
   float k1 = 0.9f, b = 0.4f, avgdl = 0, live_docs = 0, min_doc_len = 1;
   std::vector<uint32_t> h_df;  // host copy (query ordering, validation)
   DevBuf post_doc, post_tf, term_start, term_df, term_idf, term_max_tf, term_wide, tf_wide, term_blk, blk_max_doc,
-      blk_max_tf, nk, live_bits, post_score, cols, term_col, col_tmax;
+      blk_max_tf, nk, live_bits, post_score, post_pair, cols, term_col, col_tmax;
   uint32_t n_cols = 0, tmax_stride = 0;
   uint64_t col_stride = 0;
   std::vector<int32_t> h_term_col;  // host copy (tests, introspection); empty = no columns
@@ -102,7 +102,7 @@ struct Segment {
   size_t resident() const {
     return post_doc.bytes + post_tf.bytes + term_start.bytes + term_df.bytes + term_idf.bytes + term_max_tf.bytes +
            term_wide.bytes + tf_wide.bytes + term_blk.bytes + blk_max_doc.bytes + blk_max_tf.bytes + nk.bytes +
-           live_bits.bytes + post_score.bytes + cols.bytes + term_col.bytes + col_tmax.bytes;
+           live_bits.bytes + post_score.bytes + post_pair.bytes + cols.bytes + term_col.bytes + col_tmax.bytes;
   }
 };
 
@@ -296,6 +296,13 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
     count_launch(ix);
     SLG_CUDA(ix, cudaGetLastError());
     d.post_score = s->post_score.as<float>();
+    if (s->n_post_padded < (1ull << 32)) {  // the sweep kernel's posting stream (32-bit posting indices)
+      SLG_CUDA(ix, s->post_pair.alloc(s->n_post_padded * 8));
+      slg_pair_postings_kernel<<<ix->n_sm * 8, 256, 0, st>>>(s->post_doc.as<uint32_t>(), s->post_score.as<float>(), s->n_post_padded,
+                                                             s->post_pair.as<uint2>());
+      count_launch(ix);
+      SLG_CUDA(ix, cudaGetLastError());
+    }
     // dense columns for the high-df terms, largest df first until the byte budget is spent
     if (ix->dense_den && s->doc_count) {
       const uint64_t stride = align_up((uint64_t)s->doc_count, 4096) + 4096;  // a whole staged block past the end stays in bounds and zero
@@ -1038,7 +1045,7 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bool all_scores = ix->staging;
   for (auto &s : ix->segs) all_scores = all_scores && (s->post_score.p != nullptr || s->n_blocks == 0);
   bool sweepable = all_scores;  // the sweep addresses postings with 32-bit indices
-  for (auto &s : ix->segs) sweepable = sweepable && s->n_post_padded < (1ull << 32);
+  for (auto &s : ix->segs) sweepable = sweepable && (s->post_pair.p != nullptr || s->n_blocks == 0);
   // tile-sweep kernel: plain OR queries (no matcher), small k, few terms, resident scores
   bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && sweepable);
   if (bt->use_reg && !(small && !matcher && sweepable))
@@ -1350,6 +1357,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
           sw.ubw = bt->sw_ubw.as<float>() + (size_t)c0 * 8;
           sw.records = bt->sw_records.as<uint32_t>();
           sw.rng = bt->sw_rng.as<uint32_t>();
+          sw.post_pair = s->post_pair.as<uint2>();
           sw.col_tmax = s->col_tmax.as<float>();
           sw.chunk_cols = bt->d_chunk_cols.as<uint32_t>() + ((size_t)si * bt->n_chunks + c0 / kSweepChunk) * kSweepStage;
           sw.filter_bits = bd.filter_bits;

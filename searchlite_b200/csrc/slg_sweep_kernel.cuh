@@ -54,7 +54,7 @@ namespace slg {
 
 constexpr int kSweepThreads = 512;  // 16 warps, one CTA per SM
 constexpr int kSweepWarps = kSweepThreads / 32;
-constexpr uint32_t kSweepChunk = kSweepWarps;  // query slots per chunk: one per warp
+constexpr uint32_t kSweepChunk = 64;       // query slots per chunk
 constexpr uint32_t kSweepBlockDocs = 4096; // docs per staged block of column slices (SB = 4096 / TILE tiles)
 constexpr uint32_t kSweepSlotWords = 32;   // static description of one query slot
 constexpr uint32_t kSweepRecWords = 20;    // per-(slot, tile) record
@@ -81,6 +81,7 @@ struct SweepDev {
   const float *weights;         // [n_slots][8] term positions as in sstat
   const float *ubw;             // [n_slots][8] PRUNE: weight * term-wide bound (sparse) or weight (column)
   const uint32_t *rng;          // [rows][n_tiles + 1] first posting with doc >= tile * TILE
+  const uint2 *post_pair;       // [n_post_padded] (doc, unit-weight score bits) of every posting
   const float *col_tmax;        // [n_cols][tmax_stride] column maxima per 512 docs (PRUNE)
   const uint32_t *chunk_cols;   // [n_chunks][kSweepStage] staged column of the chunk or ~0
   const uint32_t *const *filter_bits;
@@ -108,8 +109,8 @@ __host__ __device__ constexpr size_t sweep_smem_per_warp() {
 }
 template <int V>
 __host__ __device__ constexpr size_t sweep_smem_bytes() {
-  // slices f32[2][stage][kSweepBlockDocs] | mbarrier[2] | per-warp areas
-  return (size_t)2 * sweep_stage<V>() * kSweepBlockDocs * 4 + 16 + (size_t)kSweepWarps * sweep_smem_per_warp<V>();
+  // slices f32[2][stage][kSweepBlockDocs] | mbarrier[2] | query state u32[kSweepChunk][8] | per-warp areas
+  return (size_t)2 * sweep_stage<V>() * kSweepBlockDocs * 4 + 16 + (size_t)kSweepChunk * 32 + (size_t)kSweepWarps * sweep_smem_per_warp<V>();
 }
 
 // ---- mbarrier + bulk-copy (TMA) primitives for the slice staging ----
@@ -147,6 +148,10 @@ __device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -278,33 +283,50 @@ __device__ __noinline__ void sweep_scatter_long(float *M, uint32_t slot, uint32_
   }
 }
 
-// One CTA = one chunk of 16 query slots (one per warp) over a range of tiles.  The slots of a chunk
-// are neighbours in the column-sorted slot order, so a handful of column slices — bulk-copied (TMA)
-// into shared memory one block of kSweepBlockDocs docs ahead — serve most of their column terms.
-// Each warp keeps its query's running threshold and candidates to itself for the whole range and
-// merges into the query's global list once at the end; its records and postings arrive through
-// private cp.async rings, four and two tiles ahead.
+// Slow path of one (query, tile): M holds the final scores of the tile.  Collect the keys that beat
+// the query's current k-th key and merge them into the query's global top-k (push_top_k,
+// query/wand.rs:905-916).  Returns the score bits of the query's k-th key afterwards (0 = none yet).
+template <int V>
+__device__ __noinline__ uint32_t sweep_collect_merge(const float *M, unsigned long long *cand, uint32_t tile_lo, uint32_t qi, int32_t filter,
+                                                     const SegmentDev &seg, const SweepDev &sw, int lane, uint32_t *n_cand) {
+  SweepLocal st;
+  st.thr = ld_cg_u64(sw.thr_key + qi);
+  st.cnt = 0;
+  st = sweep_collect<V>(M, cand, tile_lo, filter, st, seg, sw, lane);
+  *n_cand = st.cnt;
+  if (st.cnt) sweep_merge_global(cand, st.cnt, qi, sw, lane);
+  const unsigned long long t = ld_cg_u64(sw.thr_key + qi);
+  return t == kThrInit ? 0u : (uint32_t)(t >> 32);
+}
+
+// One CTA = one chunk of kSweepChunk query slots over a range of tiles.  The slots of a chunk are
+// neighbours in the column-sorted slot order, so a handful of column slices — bulk-copied (TMA) into
+// shared memory one block of kSweepBlockDocs docs ahead — serve most of their column terms.  Inside a
+// block every warp walks its own interleaved share of the (query, tile) items, so each warp sees a
+// mix of cheap and expensive queries and the one barrier per block costs little.  Records and
+// postings of the items arrive through warp-private cp.async rings, four and two items ahead.
 template <int V, bool PRUNE, bool STATS, bool WEIGHTS>
 __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const SegmentDev seg, const SweepDev sw) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr uint32_t TILE = 128u * V;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   constexpr uint32_t STAGE = sweep_stage<V>();
-  constexpr uint32_t SB = kSweepBlockDocs / TILE;  // tiles per staged block
+  constexpr uint32_t BT = kSweepBlockDocs / TILE;           // tiles per staged block
+  constexpr uint32_t IPW = kSweepChunk * BT / kSweepWarps;  // items per warp and block
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float *slices = reinterpret_cast<float *>(smem_raw);  // [2][STAGE][kSweepBlockDocs]
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)2 * STAGE * kSweepBlockDocs * 4);  // [2]
-  unsigned char *mine = smem_raw + (size_t)2 * STAGE * kSweepBlockDocs * 4 + 16 + (size_t)warp * sweep_smem_per_warp<V>();
+  uint32_t *q_state = reinterpret_cast<uint32_t *>(mbar + 2);  // [kSweepChunk][8]: cc lo, cc hi, ns | ncol << 4, thr, qi, filter, -, -
+  unsigned char *mine = reinterpret_cast<unsigned char *>(q_state + kSweepChunk * 8) + (size_t)warp * sweep_smem_per_warp<V>();
   float *M = reinterpret_cast<float *>(mine);
   unsigned long long *cand = reinterpret_cast<unsigned long long *>(mine + (size_t)TILE * 4);
   uint32_t *recring = reinterpret_cast<uint32_t *>(mine + (size_t)TILE * 4 + kWarpCand * 8);  // [8][24]
-  uint32_t *postring = recring + 192;                                                          // [4][128]
+  uint2 *postring = reinterpret_cast<uint2 *>(recring + 192);                                  // [4][2][32]
   __shared__ uint32_t s_unit;
 
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t le_mask = lt_mask | (1u << lane);
-  const uint32_t *__restrict__ post_doc = seg.post_doc;
-  const float *__restrict__ post_score = seg.post_score;
+  const uint2 *__restrict__ post_pair = sw.post_pair;
   const uint32_t n_parts = (sw.tile_end - sw.tile_begin + sw.part_tiles - 1) / sw.part_tiles;
   const uint32_t n_units = sw.n_chunks * n_parts;
 
@@ -323,7 +345,9 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
     if (unit >= n_units) break;
     const uint32_t chunk = unit % sw.n_chunks, part = unit / sw.n_chunks;
     const uint32_t t0 = sw.tile_begin + part * sw.part_tiles, t1 = min(t0 + sw.part_tiles, sw.tile_end);
-    const uint32_t n_blocks = (t1 - t0 + SB - 1) / SB;
+    const uint32_t n_blocks = (t1 - t0 + BT - 1) / BT;
+    const uint32_t slot0 = chunk * kSweepChunk;
+    const uint32_t nq = min(kSweepChunk, sw.n_slots - slot0);
 
     // ---- the chunk's staged columns: one bulk copy per column and block, issued by thread 0 ----
     auto issue_block = [&](uint32_t j) {  // block j of the unit -> buffer j & 1
@@ -337,36 +361,41 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
       for (uint32_t i = 0; i < n_stage; i++) {
         const uint32_t c = __ldg(sw.chunk_cols + (size_t)chunk * kSweepStage + i);
         bulk_copy_g2s(slices + ((size_t)buf * STAGE + i) * kSweepBlockDocs,
-                      seg.cols + (uint64_t)c * seg.col_stride + (uint64_t)(t0 + j * SB) * TILE, kSweepBlockDocs * 4, mbar + buf);
+                      seg.cols + (uint64_t)c * seg.col_stride + (uint64_t)(t0 + j * BT) * TILE, kSweepBlockDocs * 4, mbar + buf);
       }
     };
     if (threadIdx.x == 0) issue_block(0);
-
-    // ---- this warp's query ----
-    const uint32_t slot = chunk * kSweepChunk + warp;
-    const bool active = slot < sw.n_slots;
-    const uint32_t *sst = reinterpret_cast<const uint32_t *>(sw.sstat + (size_t)(active ? slot : 0) * 8);
-    const uint32_t smeta = active ? __ldg(sst + 20) : 0u;
-    const uint32_t ns = smeta & 15u, ncol = (smeta >> 4) & 15u;
-    const uint64_t cc = ((uint64_t)__ldg(sst + 17) << 32) | __ldg(sst + 16);
-    const uint32_t qi = __ldg(sst + 18);
-    const int32_t filter = (int32_t)__ldg(sst + 19);
-    const uint32_t colidx = (lane < 8 && (uint32_t)lane < ncol) ? __ldg(sst + 8 + ns + lane) : 0u;  // lane c: column of column term c
-    float wst = 1.0f, wcol = 1.0f;
-    if (WEIGHTS && active && lane < 8) {
-      wst = __ldg(sw.weights + (size_t)slot * 8 + lane);
-      if ((uint32_t)lane < ncol) wcol = __ldg(sw.weights + (size_t)slot * 8 + ns + lane);
+    // ---- the chunk's queries ----
+    if (threadIdx.x < kSweepChunk) {
+      uint32_t *qs = q_state + threadIdx.x * 8;
+      if (threadIdx.x < nq) {
+        const uint32_t *sst = reinterpret_cast<const uint32_t *>(sw.sstat + (size_t)(slot0 + threadIdx.x) * 8);
+        const uint32_t qi = __ldg(sst + 18);
+        const unsigned long long t = ld_cg_u64(sw.thr_key + qi);
+        qs[0] = __ldg(sst + 16);
+        qs[1] = __ldg(sst + 17);
+        qs[2] = __ldg(sst + 20) & 255u;
+        qs[3] = t == kThrInit ? 0u : (uint32_t)(t >> 32);
+        qs[4] = qi;
+        qs[5] = __ldg(sst + 19);
+      } else {
+        qs[2] = 0u;
+      }
     }
-    (void)wst;
-    (void)wcol;
-    SweepLocal loc;
-    loc.thr = active ? ld_cg_u64(sw.thr_key + qi) : ~0ull;
-    loc.cnt = 0;
-    const uint32_t *__restrict__ recs = sw.records + (size_t)(active ? slot : 0) * sw.n_tiles * kSweepRecWords;
+    __syncthreads();
 
-    auto copy_record = [&](uint32_t tile) {
-      if (active && tile < t1 && lane < (int)(kSweepRecWords / 4))
-        cp_async_16(recring + ((tile - t0) & 7u) * 24 + lane * 4, recs + (size_t)tile * kSweepRecWords + lane * 4);
+    // item g of this warp: block g / IPW; inside the block item i = warp + 16 * (g % IPW) of the
+    // (query, tile) grid, tile-minor: this warp keeps one tile of the block and walks the queries
+    auto item_q = [&](uint32_t g) -> uint32_t { return ((uint32_t)warp + kSweepWarps * (g % IPW)) / BT; };
+    auto item_tile = [&](uint32_t g) -> uint32_t { return t0 + (g / IPW) * BT + ((uint32_t)warp + kSweepWarps * (g % IPW)) % BT; };
+    const uint32_t n_items = n_blocks * IPW;
+    const uint32_t *__restrict__ recs = sw.records + (size_t)slot0 * sw.n_tiles * kSweepRecWords;
+
+    auto copy_record = [&](uint32_t g) {
+      if (g >= n_items) return;
+      const uint32_t q = item_q(g), tile = item_tile(g);
+      if (q < nq && tile < t1 && lane < (int)(kSweepRecWords / 4))
+        cp_async_16(recring + (g & 7u) * 24 + lane * 4, recs + ((size_t)q * sw.n_tiles + tile) * kSweepRecWords + lane * 4);
     };
     // rank of position 32 * rho + lane among the starts of the concatenated non-empty terms
     auto owner_rank = [&](const uint4 &b, int rho) -> uint32_t {
@@ -377,119 +406,127 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
       const uint32_t bw = rho == 0 ? b.x : (rho == 1 ? b.y : (rho == 2 ? b.z : b.w));
       return r + __popc(bw & le_mask);
     };
-    // rounds 0 and 1 of a tile's postings: asynchronous copies into the posting ring
-    auto copy_postings = [&](uint32_t tile) {
-      if (!active || tile >= t1) return;
-      const uint32_t *rr = recring + ((tile - t0) & 7u) * 24;
+    // rounds 0 and 1 of an item's postings: asynchronous copies into the posting ring
+    auto copy_postings = [&](uint32_t g) {
+      if (g >= n_items) return;
+      if (item_q(g) >= nq || item_tile(g) >= t1) return;
+      const uint32_t *rr = recring + (g & 7u) * 24;
       const uint4 b = *reinterpret_cast<const uint4 *>(rr);
       const uint32_t tot = rr[4] & 0xFFFFu;
       if (tot == 0u || tot > 128u) return;
       const uint32_t a = lane < 8 ? rr[8 + lane] : 0u;
-      uint32_t *pr = postring + ((tile - t0) & 3u) * 128;
-      {
-        const uint32_t idx = __shfl_sync(FULL, a, owner_rank(b, 0)) + lane;
-        if ((uint32_t)lane < tot) {
-          cp_async_4(pr + lane, post_doc + idx);
-          cp_async_4(pr + 32 + lane, post_score + idx);
-        }
-      }
+      uint2 *pr = postring + (g & 3u) * 64;
+      const uint32_t idx0 = __shfl_sync(FULL, a, owner_rank(b, 0)) + lane;
+      if ((uint32_t)lane < tot) cp_async_8(pr + lane, post_pair + idx0);
       if (tot > 32u) {
-        const uint32_t idx = __shfl_sync(FULL, a, owner_rank(b, 1)) + 32u + lane;
-        if (32u + lane < tot) {
-          cp_async_4(pr + 64 + lane, post_doc + idx);
-          cp_async_4(pr + 96 + lane, post_score + idx);
-        }
+        const uint32_t idx1 = __shfl_sync(FULL, a, owner_rank(b, 1)) + 32u + lane;
+        if (32u + lane < tot) cp_async_8(pr + 32 + lane, post_pair + idx1);
       }
     };
 
-    // ---- prologue of the warp's rings: records of t0 .. t0 + 3, postings of t0 and t0 + 1 ----
-    copy_record(t0);
-    copy_record(t0 + 1);
-    copy_record(t0 + 2);
-    copy_record(t0 + 3);
+    // ---- prologue of the warp's rings: records of items 0..3, postings of items 0 and 1 ----
+    copy_record(0);
+    copy_record(1);
+    copy_record(2);
+    copy_record(3);
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
-    copy_postings(t0);
-    copy_postings(t0 + 1);
+    copy_postings(0);
+    copy_postings(1);
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
 
+    const float *blk = slices + lane * 4;
 #pragma unroll 1
-    for (uint32_t j = 0; j < n_blocks; j++) {
-      __syncthreads();  // every warp is done with block j - 1: its buffer may be overwritten
-      if (threadIdx.x == 0 && j + 1 < n_blocks) issue_block(j + 1);
-      const uint32_t buf = j & 1u;
-      if (buf == 0) {
-        mbar_wait(mbar, phase0);
-        phase0 ^= 1u;
-      } else {
-        mbar_wait(mbar + 1, phase1);
-        phase1 ^= 1u;
+    for (uint32_t g = 0; g < n_items; g++) {
+      if ((g % IPW) == 0u) {
+        // ---- next block: every warp is done with the block before, so its buffer may be refilled ----
+        const uint32_t j = g / IPW;
+        __syncthreads();
+        if (threadIdx.x == 0 && j + 1 < n_blocks) issue_block(j + 1);
+        if (threadIdx.x < nq) {  // what other ranges of these queries have found meanwhile
+          const unsigned long long t = ld_cg_u64(sw.thr_key + q_state[threadIdx.x * 8 + 4]);
+          if (t != kThrInit) atomicMax(q_state + threadIdx.x * 8 + 3, (uint32_t)(t >> 32));
+        }
+        if ((j & 1u) == 0u) {
+          mbar_wait(mbar, phase0);
+          phase0 ^= 1u;
+        } else {
+          mbar_wait(mbar + 1, phase1);
+          phase1 ^= 1u;
+        }
+        blk = slices + (size_t)(j & 1u) * STAGE * kSweepBlockDocs + lane * 4;
       }
-      if (!active) continue;
-      const float *blk = slices + (size_t)buf * STAGE * kSweepBlockDocs + lane * 4;
+      // ring upkeep: everything issued two items ago has landed (record g + 2, postings g)
+      cp_async_wait<1>();
+      __syncwarp();
+      copy_record(g + 4);
+      copy_postings(g + 2);
+      cp_async_commit();
 
-#pragma unroll 1
-      for (uint32_t t = t0 + j * SB; t < min(t0 + (j + 1) * SB, t1); t++) {
-        // ring upkeep: everything issued two tiles ago has landed (record t + 2, postings t)
-        cp_async_wait<1>();
-        __syncwarp();
-        copy_record(t + 4);
-        copy_postings(t + 2);
-        cp_async_commit();
-
-        // ---- the item (query, tile t) ----
-        const uint32_t tile_lo = t * TILE;
-        const uint32_t *rr = recring + ((t - t0) & 7u) * 24;
-        const uint4 b = *reinterpret_cast<const uint4 *>(rr);
-        const uint32_t meta = rr[4];
-        const uint32_t tot = meta & 0xFFFFu;
-        const uint32_t thr_hi = loc.thr == kThrInit ? 0u : (uint32_t)(loc.thr >> 32);
-        if ((tot | ncol) == 0u) continue;
-        if (PRUNE && thr_hi != 0u && __uint_as_float(rr[5]) * 1.00001f < __uint_as_float(thr_hi)) {
-          if (STATS && lane == 0) atomicAdd(sw.stats + (uint64_t)qi * 4 + 2, 1ull);
-          continue;
-        }
+      const uint32_t q = item_q(g), t = item_tile(g);
+      if (q >= nq || t >= t1) continue;
+      // ---- the item (query q, tile t) ----
+      const uint32_t tile_lo = t * TILE;
+      const uint32_t *rr = recring + (g & 7u) * 24;
+      const uint4 qs = *reinterpret_cast<const uint4 *>(q_state + q * 8);
+      const uint32_t ns = qs.z & 15u, ncol = qs.z >> 4;
+      const uint32_t thr_hi = qs.w;
+      const uint4 b = *reinterpret_cast<const uint4 *>(rr);
+      const uint32_t tot = rr[4] & 0xFFFFu;
+      if ((tot | ncol) == 0u) continue;
+      if (PRUNE && thr_hi != 0u && __uint_as_float(rr[5]) * 1.00001f < __uint_as_float(thr_hi)) {
+        if (STATS && lane == 0) atomicAdd(sw.stats + (uint64_t)q_state[q * 8 + 4] * 4 + 2, 1ull);
+        continue;
+      }
+      // rounds 2 and 3 travel while the columns are added
+      uint2 p2 = make_uint2(tile_lo, 0u), p3 = make_uint2(tile_lo, 0u);
+      if (tot > 64u && tot <= 128u) {
         const uint32_t a = lane < 8 ? rr[8 + lane] : 0u;
-        // rounds 2 and 3 travel while the columns are added
-        uint32_t d2 = tile_lo, d3 = tile_lo;
-        float s2 = 0.0f, s3 = 0.0f;
-        if (tot > 64u && tot <= 128u) {
-          uint32_t idx = __shfl_sync(FULL, a, owner_rank(b, 2)) + 64u + lane;
-          if (64u + lane < tot) {
-            d2 = ldg_nc_u32(post_doc + idx);
-            s2 = __uint_as_float(ldg_nc_u32(post_score + idx));
-          }
-          if (tot > 96u) {
-            idx = __shfl_sync(FULL, a, owner_rank(b, 3)) + 96u + lane;
-            if (96u + lane < tot) {
-              d3 = ldg_nc_u32(post_doc + idx);
-              s3 = __uint_as_float(ldg_nc_u32(post_score + idx));
-            }
-          }
+        uint32_t idx = __shfl_sync(FULL, a, owner_rank(b, 2)) + 64u + lane;
+        if (64u + lane < tot) p2 = __ldg(post_pair + idx);
+        if (tot > 96u) {
+          idx = __shfl_sync(FULL, a, owner_rank(b, 3)) + 96u + lane;
+          if (96u + lane < tot) p3 = __ldg(post_pair + idx);
         }
-        unsigned long long thr_new = 0ull;
-        if (((t - t0) & 63u) == 63u) thr_new = ld_cg_u64(sw.thr_key + qi);  // what other ranges of this query found
-        float4 R[V];
+      }
+      float4 R[V];
 #pragma unroll
-        for (int v = 0; v < V; v++) R[v] = make_float4(0, 0, 0, 0);
-        // ---- column terms in query order: staged slice (shared) or global, adds in registers ----
-        const uint32_t in_blk = (t - t0 - j * SB) * TILE;
+      for (int v = 0; v < V; v++) R[v] = make_float4(0, 0, 0, 0);
+      // ---- column terms in query order: staged slice (shared) or global, adds in registers ----
+      const uint64_t cc = ((uint64_t)qs.y << 32) | qs.x;
+      const uint32_t in_blk = ((t - t0) % BT) * TILE;
 #pragma unroll 1
-        for (uint32_t c = 0; c < ncol; c++) {
-          const uint32_t code = (uint32_t)(cc >> (8 * c)) & 255u;
-          const float4 *cp;
-          if (code < STAGE) cp = reinterpret_cast<const float4 *>(blk + (size_t)code * kSweepBlockDocs + in_blk);
-          else cp = reinterpret_cast<const float4 *>(seg.cols + (uint64_t)__shfl_sync(FULL, colidx, c) * seg.col_stride + tile_lo) + lane;
-          float w = 1.0f;
-          if (WEIGHTS) w = __shfl_sync(FULL, wcol, c);
+      for (uint32_t c = 0; c < ncol; c++) {
+        const uint32_t code = (uint32_t)(cc >> (8 * c)) & 255u;
+        float w = 1.0f;
+        if (WEIGHTS) w = __ldg(sw.weights + (size_t)(slot0 + q) * 8 + ns + c);
+        if (code < STAGE) {
+          const float4 *cp = reinterpret_cast<const float4 *>(blk + (size_t)code * kSweepBlockDocs + in_blk);
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            float4 cv = cp[v * 32];
+            if (WEIGHTS) {
+              cv.x = __fmul_rn(cv.x, w);
+              cv.y = __fmul_rn(cv.y, w);
+              cv.z = __fmul_rn(cv.z, w);
+              cv.w = __fmul_rn(cv.w, w);
+            }
+            R[v].x = __fadd_rn(R[v].x, cv.x);
+            R[v].y = __fadd_rn(R[v].y, cv.y);
+            R[v].z = __fadd_rn(R[v].z, cv.z);
+            R[v].w = __fadd_rn(R[v].w, cv.w);
+          }
+        } else {
+          const uint32_t col = __ldg(reinterpret_cast<const uint32_t *>(sw.sstat + (size_t)(slot0 + q) * 8) + 8 + ns + c);
+          const float4 *cp = reinterpret_cast<const float4 *>(seg.cols + (uint64_t)col * seg.col_stride + tile_lo) + lane;
 #pragma unroll
           for (int h = 0; h < V; h += 4) {
             float4 cv[4];
 #pragma unroll
-            for (int v = 0; v < 4; v++) cv[v] = cp[(h + v) * 32];
+            for (int v = 0; v < 4; v++) cv[v] = __ldg(cp + (h + v) * 32);
 #pragma unroll
             for (int v = 0; v < 4; v++) {
               if (WEIGHTS) {
@@ -505,102 +542,106 @@ __global__ void __launch_bounds__(kSweepThreads, 1) slg_score_sweep_kernel(const
             }
           }
         }
-        // ---- compare the registers with the running k-th score ----
-        uint32_t mx = 0;
+      }
+      // ---- compare the registers with the running k-th score ----
+      uint32_t mx = 0;
 #pragma unroll
-        for (int v = 0; v < V; v++) {
-          const uint32_t b0 = __float_as_uint(R[v].x), b1 = __float_as_uint(R[v].y), b2 = __float_as_uint(R[v].z), b3 = __float_as_uint(R[v].w);
-          mx = max(mx, max(max(b0, b1), max(b2, b3)));
-        }
-        bool hit = mx >= thr_hi && mx != 0u;
-        if (tot) {
-          // ---- sparse terms: park the register tile, add the (doc, score) postings in query order ----
+      for (int v = 0; v < V; v++) {
+        const uint32_t b0 = __float_as_uint(R[v].x), b1 = __float_as_uint(R[v].y), b2 = __float_as_uint(R[v].z), b3 = __float_as_uint(R[v].w);
+        mx = max(mx, max(max(b0, b1), max(b2, b3)));
+      }
+      bool hit = mx >= thr_hi && mx != 0u;
+      if (tot) {
+        // ---- sparse terms: park the register tile, add the (doc, score) postings in query order ----
 #pragma unroll
-          for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
-          __syncwarp();
-          if (tot <= 128u) {
-            const uint32_t *pr = postring + ((t - t0) & 3u) * 128;
-            const uint32_t d0 = pr[lane], d1 = pr[64 + lane];
-            const float s0 = __uint_as_float(pr[32 + lane]), s1 = __uint_as_float(pr[96 + lane]);
-            const uint32_t posmap = WEIGHTS ? rr[16] : 0u;
-            (void)posmap;
-            // one round: lanes of one term hit distinct docs; terms are applied one after the other
-            auto round = [&](int rho, uint32_t d, float s) {
-              if (tot <= 32u * rho) return;
-              const bool valid = 32u * rho + lane < tot;
-              float *slot_p = M + (valid ? d - tile_lo : 0u);
-              const uint32_t bw = rho == 0 ? b.x : (rho == 1 ? b.y : (rho == 2 ? b.z : b.w));
-              if (WEIGHTS) s = __fmul_rn(s, __shfl_sync(FULL, wst, (posmap >> (3 * owner_rank(b, rho))) & 7u));
-              if (bw == 0u) {
-                if (valid) *slot_p = __fadd_rn(*slot_p, s);
-              } else {
-                const uint32_t myr = __popc(bw & le_mask);  // rank inside the round
-                const uint32_t r_hi = __popc(bw);
-                for (uint32_t r = 0; r <= r_hi; r++) {
-                  if (valid && myr == r) *slot_p = __fadd_rn(*slot_p, s);
-                  __syncwarp();
-                }
+        for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
+        __syncwarp();
+        if (tot <= 128u) {
+          const uint2 *pr = postring + (g & 3u) * 64;
+          const uint2 p0 = pr[lane], p1 = pr[32 + lane];
+          float wst = 1.0f;
+          uint32_t posmap = 0;
+          if (WEIGHTS) {
+            wst = lane < 8 ? __ldg(sw.weights + (size_t)(slot0 + q) * 8 + lane) : 1.0f;
+            posmap = rr[16];
+          }
+          // one round: lanes of one term hit distinct docs; terms are applied one after the other
+          auto round = [&](int rho, uint2 p) {
+            if (tot <= 32u * rho) return;
+            const bool valid = 32u * rho + lane < tot;
+            float *slot_p = M + (valid ? p.x - tile_lo : 0u);
+            float s = __uint_as_float(p.y);
+            const uint32_t bw = rho == 0 ? b.x : (rho == 1 ? b.y : (rho == 2 ? b.z : b.w));
+            if (WEIGHTS) s = __fmul_rn(s, __shfl_sync(FULL, wst, (posmap >> (3 * owner_rank(b, rho))) & 7u));
+            if (bw == 0u) {
+              if (valid) *slot_p = __fadd_rn(*slot_p, s);
+            } else {
+              const uint32_t myr = __popc(bw & le_mask);  // rank inside the round
+              const uint32_t r_hi = __popc(bw);
+              for (uint32_t r = 0; r <= r_hi; r++) {
+                if (valid && myr == r) *slot_p = __fadd_rn(*slot_p, s);
+                __syncwarp();
               }
-              __syncwarp();
-            };
-            round(0, d0, s0);
-            round(1, d1, s1);
-            round(2, d2, s2);
-            round(3, d3, s3);
-            // the touched docs against the threshold
-            auto recheck = [&](int rho, uint32_t d) {
-              if (tot <= 32u * rho) return;
-              const uint32_t v = (32u * rho + lane < tot) ? __float_as_uint(M[d - tile_lo]) : 0u;
-              hit = hit || (v >= thr_hi && v != 0u);
-            };
-            recheck(0, d0);
-            recheck(1, d1);
-            recheck(2, d2);
-            recheck(3, d3);
-          } else {
-            sweep_scatter_long<WEIGHTS>(M, slot, t, tile_lo, seg, sw, lane);
-            uint32_t m2 = 0;
-#pragma unroll
-            for (int v = 0; v < V; v++) {
-              const float4 q = *reinterpret_cast<const float4 *>(M + v * 128 + lane * 4);
-              m2 = max(m2, max(max(__float_as_uint(q.x), __float_as_uint(q.y)), max(__float_as_uint(q.z), __float_as_uint(q.w))));
             }
-            hit = hit || (m2 >= thr_hi && m2 != 0u);
-          }
-        }
-        const uint32_t cnt_before = loc.cnt;
-        if (__any_sync(FULL, hit)) {
-          // rare after warm-up: walk the tile's final scores in shared memory
-          if (!tot) {
-#pragma unroll
-            for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
-          }
-          __syncwarp();
-          loc = sweep_collect<V>(M, cand, tile_lo, filter, loc, seg, sw, lane);
-        }
-        if (thr_new > loc.thr && thr_new != kThrInit) loc.thr = thr_new;
-        if (STATS) {
-          uint32_t n_touched = 0;
+            __syncwarp();
+          };
+          round(0, p0);
+          round(1, p1);
+          round(2, p2);
+          round(3, p3);
+          // the touched docs against the threshold
+          auto recheck = [&](int rho, uint2 p) {
+            if (tot <= 32u * rho) return;
+            const uint32_t v = (32u * rho + lane < tot) ? __float_as_uint(M[p.x - tile_lo]) : 0u;
+            hit = hit || (v >= thr_hi && v != 0u);
+          };
+          recheck(0, p0);
+          recheck(1, p1);
+          recheck(2, p2);
+          recheck(3, p3);
+        } else {
+          sweep_scatter_long<WEIGHTS>(M, slot0 + q, t, tile_lo, seg, sw, lane);
+          uint32_t m2 = 0;
 #pragma unroll
           for (int v = 0; v < V; v++) {
-            float4 q = R[v];
-            if (tot) q = *reinterpret_cast<const float4 *>(M + v * 128 + lane * 4);
-            n_touched += (q.x != 0.0f) + (q.y != 0.0f) + (q.z != 0.0f) + (q.w != 0.0f);
+            const float4 x = *reinterpret_cast<const float4 *>(M + v * 128 + lane * 4);
+            m2 = max(m2, max(max(__float_as_uint(x.x), __float_as_uint(x.y)), max(__float_as_uint(x.z), __float_as_uint(x.w))));
           }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) n_touched += __shfl_xor_sync(FULL, n_touched, o);
-          if (lane == 0) {
-            if (n_touched) atomicAdd(sw.stats + (uint64_t)qi * 4 + 0, (unsigned long long)n_touched);
-            if (rr[17]) atomicAdd(sw.stats + (uint64_t)qi * 4 + 1, (unsigned long long)rr[17]);
-            if (loc.cnt > cnt_before) atomicAdd(sw.stats + (uint64_t)qi * 4 + 3, (unsigned long long)(loc.cnt - cnt_before));
-          }
-          __syncwarp();
+          hit = hit || (m2 >= thr_hi && m2 != 0u);
         }
+      }
+      uint32_t n_cand = 0;
+      if (__any_sync(FULL, hit)) {
+        // rare after warm-up: walk the tile's final scores in shared memory
+        if (!tot) {
+#pragma unroll
+          for (int v = 0; v < V; v++) *reinterpret_cast<float4 *>(M + v * 128 + lane * 4) = R[v];
+        }
+        __syncwarp();
+        const uint32_t thr_now = sweep_collect_merge<V>(M, cand, tile_lo, q_state[q * 8 + 4], (int32_t)q_state[q * 8 + 5], seg, sw, lane, &n_cand);
+        if (lane == 0) atomicMax(q_state + q * 8 + 3, thr_now);
+        __syncwarp();
+      }
+      if (STATS) {
+        uint32_t n_touched = 0;
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          float4 x = R[v];
+          if (tot) x = *reinterpret_cast<const float4 *>(M + v * 128 + lane * 4);
+          n_touched += (x.x != 0.0f) + (x.y != 0.0f) + (x.z != 0.0f) + (x.w != 0.0f);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_touched += __shfl_xor_sync(FULL, n_touched, o);
+        if (lane == 0) {
+          const uint32_t qi = q_state[q * 8 + 4];
+          if (n_touched) atomicAdd(sw.stats + (uint64_t)qi * 4 + 0, (unsigned long long)n_touched);
+          if (rr[17]) atomicAdd(sw.stats + (uint64_t)qi * 4 + 1, (unsigned long long)rr[17]);
+          if (n_cand) atomicAdd(sw.stats + (uint64_t)qi * 4 + 3, (unsigned long long)n_cand);
+        }
+        __syncwarp();
       }
     }
     cp_async_wait<0>();
-    __syncwarp();
-    if (active && loc.cnt) sweep_merge_global(cand, loc.cnt, qi, sw, lane);
   }
 }
 
@@ -801,6 +842,12 @@ __global__ void __launch_bounds__(128) slg_score_postings_kernel(SegmentDev seg,
   const uint64_t wide = seg.term_wide[term];
   if (tf == 255u && wide != ~0ull) tf = seg.tf_wide[wide + i];
   post_score[base + i] = bm25_contrib_fast(tf, seg.term_idf[term], seg.k1p1, seg.nk[doc], 1.0f);
+}
+
+// (doc, score bits) of every posting side by side: one 8-byte copy per posting in the sweep
+__global__ void slg_pair_postings_kernel(const uint32_t *post_doc, const float *post_score, uint64_t n, uint2 *post_pair) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    post_pair[i] = make_uint2(post_doc[i], __float_as_uint(post_score[i]));
 }
 
 // grid (chunks, n_cols): column c holds the scores of term col_terms[c] at their doc slots
