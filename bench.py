@@ -327,7 +327,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": None, "peak_kind": peak_kind,
-                     "kernel": {"auto": "slg_score_sweep_kernel", "reg": "slg_score_sweep_kernel", "cta": "slg_score_tiles_kernel"}.get(args.kernel, "slg_score_warp_kernel"),
+                     "kernel": {"reg": "slg_score_warp_kernel<COLS> / slg_score_sweep_kernel", "cta": "slg_score_tiles_kernel"}.get(args.kernel, "slg_score_warp_kernel"),
                      "kernel_ms": score_ms, "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "5 B x sum of df over the batch's query terms (this rank's segment)"},
         "setup": {"corpus_gen_s": round(gen_s, 1), "load_segment_s": round(load_s, 1), "resident_bytes": int(c1["resident_bytes"])},

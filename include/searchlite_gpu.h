@@ -150,10 +150,10 @@ int32_t slg_close(slg_index_t *);
 const char *slg_last_error(const slg_index_t *);
 /* tuning knobs; 0 keeps the default.  tile_docs: docs per shared-memory tile of the CTA-per-item
  * kernel (multiple of 1024); sub_docs: docs per warp-private tile of the warp-per-item kernel
- * (multiple of 128); kernel_choice: 0 = automatic (tile-sweep kernel for plain OR queries with
- * k <= 32 and <= 8 terms per query, warp kernel for the same shape with a Bool matcher, CTA kernel
- * otherwise), 1 = CTA kernel, 2 = warp kernel, 3 = tile-sweep kernel; add 256 to ignore the
- * resident per-posting scores and score postings in place. */
+ * (multiple of 128); kernel_choice: 0 = automatic (warp kernel for k <= 32 and <= 8 terms per query,
+ * CTA kernel otherwise), 1 = CTA kernel, 2 = warp kernel, 3 = column front end for plain OR queries
+ * (see "heavy_kernel" below); add 256 to ignore the resident per-posting scores and score postings
+ * in place. */
 int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, uint32_t sub_docs,
                       uint32_t kernel_choice);
 /* residency / tuning options; the residency ones apply to segments loaded AFTER the call:
@@ -162,17 +162,20 @@ int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, u
  *                           (default 8; 0 = no columns)
  *   "dense_min_df"     n    ... and df >= n (default 256)
  *   "max_column_bytes" n    byte budget of the columns of one segment, largest df first (default 24 GiB)
+ *   "heavy_kernel"     0|1  column front end (kernel_choice 3): 0 = warp kernel that sums a query's column
+ *                           terms from their dense columns (default), 1 = tile-sweep kernel
  *   "reg_tile_v"       4|8     tile-sweep kernel: 128 * v docs per register tile (default 8)
  *   "sweep_min_postings" n  tile-sweep kernel: a query without a column term whose terms hold fewer than
  *                           n postings is scored posting-driven by the warp kernel instead of being swept
  *                           over every tile (default 0 = doc_count / 64; 1 = sweep every query)
- *   "seed_docs"        n    tile-sweep kernel: docs scored by the contention-free seed pass (default 16384)
- * Float contract: the tile-sweep kernel sums a doc's contributions over the query's terms
- * WITH a column first, then over the terms WITHOUT one, each group in query order (one left
- * fold) — brute_force (query/wand.rs:527-548) on that permutation of the query; the other kernels
- * sum in query order.  Both agree with the reference within the 1e-5 rule. */
+ *   "seed_docs"        n    tile-sweep kernel: docs scored by the seed pass (default 16384)
+ *   "part_tiles"       n    tile-sweep kernel: tiles per unit of work (default 0 = automatic)
+ * Float contract: the column front ends sum a doc's contributions over the query's terms WITH a
+ * column first, then over the terms WITHOUT one, each group in query order (one left fold) —
+ * brute_force (query/wand.rs:527-548) on that permutation of the query; the other kernels sum in
+ * query order.  Both agree with the reference within the 1e-5 rule. */
 int32_t slg_set_option(slg_index_t *, const char *name, uint64_t value);
-/* 1 if `term_id` of the segment has a dense column (it is summed first by the tile-sweep kernel) */
+/* 1 if `term_id` of the segment has a dense column (it is summed first by the column front ends) */
 int32_t slg_term_has_column(const slg_index_t *, uint32_t segment_ord, uint32_t term_id);
 
 /* ---- residency (SegmentReader::open) ---- */

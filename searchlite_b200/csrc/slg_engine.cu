@@ -137,6 +137,7 @@ struct slg_index {
   uint64_t sweep_min_postings = 0;  // sweep: a query without column terms and sum(df) below this goes to the warp kernel (0 = doc_count / 64)
   uint32_t seed_docs = 16384;    // sweep: docs of the seed pass
   uint32_t part_tiles = 0;       // sweep: tiles per unit of work (0 = automatic)
+  uint32_t heavy_kernel = 0;     // column front end: 0 = warp kernel summing column terms from their columns, 1 = tile-sweep kernel
   Segment *find(uint32_t ord) {
     for (auto &s : segs)
       if (s->ord == ord) return s.get();
@@ -171,6 +172,7 @@ struct slg_batch {
   DevBuf sw_sstat, sw_weights, sw_ubw, sw_rng, sw_records, d_chunk_cols;  // d_chunk_cols: [S][n_chunks][kSweepStage]
   uint32_t n_chunks = 0;
   bool any_weight = false;             // some scored term has weight != 1
+  bool warp_cols = false;              // the warp kernel sums column terms from their dense columns
   DevBuf seg_hits, seg_counts;  // [S][Q][k], [S][Q]
   DevBuf out_hits, out_counts;  // merged (aliases seg buffers when S == 1)
   uint32_t n_segs_run = 0;
@@ -492,18 +494,26 @@ int32_t launch_score(slg_index *ix, bool matcher, bool prune, bool stats, const 
   }
 }
 
-template <bool M, bool P, bool S, bool G>
+template <bool M, bool P, bool S, bool G, bool C = false>
 int32_t launch_warp_t(slg_index *ix, const SegmentDev &sd, const WarpBatchDev &wb, size_t smem, int grid) {
-  auto kern = slg_score_warp_kernel<M, P, S, G>;
+  auto kern = slg_score_warp_kernel<M, P, S, G, C>;
   SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kThreads, smem, ix->stream>>>(sd, wb);
   SLG_CUDA(ix, cudaGetLastError());
   return SLG_OK;
 }
 
-int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, bool staged, const SegmentDev &sd,
+int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, bool staged, bool cols, const SegmentDev &sd,
                     const WarpBatchDev &wb, size_t smem, int grid) {
   int sel = (matcher ? 4 : 0) | (prune ? 2 : 0) | (stats ? 1 : 0);
+  if (staged && !matcher && cols) {
+    switch (sel) {
+      case 0: return launch_warp_t<false, false, false, true, true>(ix, sd, wb, smem, grid);
+      case 1: return launch_warp_t<false, false, true, true, true>(ix, sd, wb, smem, grid);
+      case 2: return launch_warp_t<false, true, false, true, true>(ix, sd, wb, smem, grid);
+      default: return launch_warp_t<false, true, true, true, true>(ix, sd, wb, smem, grid);
+    }
+  }
   if (staged && !matcher) {
     switch (sel) {
       case 0: return launch_warp_t<false, false, false, true>(ix, sd, wb, smem, grid);
@@ -639,6 +649,10 @@ int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
   } else if (n == "sweep_min_postings") ix->sweep_min_postings = value;
   else if (n == "seed_docs") ix->seed_docs = (uint32_t)value;
   else if (n == "part_tiles") ix->part_tiles = (uint32_t)value;
+  else if (n == "heavy_kernel") {
+    if (value > 1) return fail(ix, SLG_ERR_INVALID, "heavy_kernel must be 0 (warp kernel + columns) or 1 (tile sweep)");
+    ix->heavy_kernel = (uint32_t)value;
+  }
   else return fail(ix, SLG_ERR_INVALID, "unknown option '%s'", name);
   return SLG_OK;
 }
@@ -1047,7 +1061,9 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bool sweepable = all_scores;  // the sweep addresses postings with 32-bit indices
   for (auto &s : ix->segs) sweepable = sweepable && (s->post_pair.p != nullptr || s->n_blocks == 0);
   // tile-sweep kernel: plain OR queries (no matcher), small k, few terms, resident scores
-  bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && sweepable);
+  // (explicit choice only: on the measured workloads neither column front end beats the plain warp kernel,
+  // which also keeps the reference's summation order)
+  bt->use_reg = ix->kernel_choice == 3;
   if (bt->use_reg && !(small && !matcher && sweepable))
     return fail(ix, SLG_ERR_UNSUPPORTED,
                 "the sweep kernel handles plain OR queries, k <= %u, <= %u terms per query, resident scores, < 2^32 postings per segment",
@@ -1069,7 +1085,8 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
         if (ut[u] < sg->h_term_col.size() && sg->h_term_col[ut[u]] >= 0) u_col[u] = 1;
     uint64_t max_docs = 0;
     for (auto &sg : ix->segs) max_docs = std::max<uint64_t>(max_docs, sg->doc_count);
-    for (uint32_t qi = 0; qi < n_queries; qi++) {
+    bt->warp_cols = ix->sub_docs <= 4096;
+    for (uint32_t qi = 0; qi < n_queries && ix->heavy_kernel == 1; qi++) {
       bool h = q_cost[qi] >= (ix->sweep_min_postings ? ix->sweep_min_postings : std::max<uint64_t>(1, max_docs / 64));
       for (uint32_t t = q_off[qi]; t < q_off[qi + 1] && !h; t++) h = u_col[qt_u[t]] != 0;
       heavy[qi] = h;
@@ -1326,7 +1343,8 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         }
       }
       if ((bt->use_warp || (bt->use_reg && bt->n_light)) && bw.n_queries) {
-        slg_build_qterms_kernel<<<(bw.n_queries + 127) / 128, 128, 0, st>>>(s->dev, bw, bt->qterms.as<QTerm>(), bt->qheads.as<QHead>());
+        slg_build_qterms_kernel<<<(bw.n_queries + 127) / 128, 128, 0, st>>>(s->dev, bw, bt->qterms.as<QTerm>(), bt->qheads.as<QHead>(),
+                                                                            bt->use_reg && bt->warp_cols && bt->staged);
         count_launch(ix);
       }
       const uint32_t sw_tile = 128u * bt->reg_v;
@@ -1427,10 +1445,10 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         wper = std::min(wper, 8u);
         if (ix->ctas_per_sm) wper = std::min(wper, ix->ctas_per_sm);
         int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * wper, ((uint64_t)wb.n_groups * wb.n_queries + warps - 1) / warps);
-        rc = launch_warp(ix, bt->matcher, prune, bt->want_stats, bt->staged, s->dev, wb, wsmem, grid);
+        rc = launch_warp(ix, bt->matcher, prune, bt->want_stats, bt->staged, bt->use_reg && bt->warp_cols, s->dev, wb, wsmem, grid);
         if (rc) return rc;
         count_launch(ix);
-        if (!bt->use_reg) ix->ctr.score_launches++;
+        if (!bt->use_reg || !bt->n_heavy) ix->ctr.score_launches++;
       } else if (!bt->use_reg && !bt->use_warp) {
         int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * per_sm, (uint64_t)bd.n_tiles * Q);
         rc = launch_score(ix, bt->matcher, prune, bt->want_stats, s->dev, bd, smem, grid);

@@ -32,11 +32,11 @@ constexpr uint32_t kWarpCand = 64;
 
 struct __align__(16) QTerm {  // one query term resolved against one segment (32 B)
   uint64_t base;      // term_start: first padded posting index
-  uint64_t sc_base;   // first slot of the term in the staged score stream
+  uint64_t sc_base;   // COLS: element offset of the term's dense column in seg.cols (flags bit 2), else = base
   uint32_t term;      // term id in the segment
   uint32_t uterm;     // row of the range / bound tables
   float weight;
-  uint32_t flags;     // bit0 scored, bit1 valid, bits 8..15 group
+  uint32_t flags;     // bit0 scored, bit1 valid, bit2 summed from its dense column (COLS), bits 8..15 group
 };
 
 struct __align__(16) QHead {  // 16 B per query slot (processing order)
@@ -62,7 +62,9 @@ struct WarpBatchDev {
 };
 
 // resolve the batch's query terms against one segment (runs once per segment per batch)
-__global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qterms, QHead *qheads) {
+// use_cols: terms with a dense column (seg.term_col) are flagged; the kernel then sums them from the
+// column, before the query's other terms (the float contract of the column path, see slg_score_warp_kernel)
+__global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qterms, QHead *qheads, bool use_cols) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= bt.n_queries) return;
   const uint32_t qi = bt.q_order[slot];
@@ -91,6 +93,10 @@ __global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qter
       r.uterm = u;
       r.weight = bt.qt_weight[t0 + t];
       r.flags = (bt.qt_flags[t0 + t] & 1u) | 2u | ((uint32_t)bt.qt_group[t0 + t] << 8);
+      if (use_cols && seg.term_col && term < seg.n_terms && seg.term_col[term] >= 0 && (r.flags & 1u)) {
+        r.flags |= 4u;
+        r.sc_base = (uint64_t)seg.term_col[term] * seg.col_stride;
+      }
     }
     qterms[(uint64_t)slot * kWarpMaxTerms + t] = r;
   }
@@ -188,7 +194,11 @@ __device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ d
   }
 }
 
-template <bool MATCHER, bool PRUNE, bool STATS, bool STAGED>
+// COLS (plain OR queries with resident scores): a term with a dense column is not scattered posting by
+// posting; the warp first fills its accumulator with the sum of the query's column slices (128-bit
+// loads, query order), then scatters the remaining terms on top.  Float contract of that path: the
+// terms WITH a column in query order, then the terms WITHOUT one in query order, one left fold.
+template <bool MATCHER, bool PRUNE, bool STATS, bool STAGED, bool COLS = false>
 __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg, WarpBatchDev wb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -267,6 +277,8 @@ __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg
       }
       const uint32_t any = __ballot_sync(0xFFFFFFFFu, mine_n != 0u);
       if (any == 0u) continue;
+      uint32_t colmask = 0;  // term slots summed from a column
+      if (COLS) colmask = __ballot_sync(0xFFFFFFFFu, lane < (int)nt && (qt[lane].flags & 5u) == 5u);
       if (PRUNE) {
         float ub = mine_ub;
 #pragma unroll
@@ -282,10 +294,41 @@ __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg
 
       // ---- accumulate ----
       bool first = true;
+      if (COLS && colmask) {
+        // column terms: accumulator = sum of the column slices, query order; four rows of 128 docs per
+        // step so that four 128-bit loads per column are in flight
+#pragma unroll 1
+        for (uint32_t i0 = 0; i0 < sub_docs; i0 += 512) {
+          float4 v[4];
+#pragma unroll
+          for (int r = 0; r < 4; r++) v[r] = make_float4(0, 0, 0, 0);
+          for (uint32_t m = colmask; m; m &= m - 1) {
+            const uint32_t t = __ffs(m) - 1;
+            const float4 *cp = reinterpret_cast<const float4 *>(seg.cols + qt[t].sc_base + tile_lo + i0) + lane;
+            const float w = qt[t].weight;
+            float4 c[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) c[r] = (i0 + r * 128 < sub_docs) ? __ldg(cp + r * 32) : make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+              v[r].x = __fadd_rn(v[r].x, __fmul_rn(c[r].x, w));
+              v[r].y = __fadd_rn(v[r].y, __fmul_rn(c[r].y, w));
+              v[r].z = __fadd_rn(v[r].z, __fmul_rn(c[r].z, w));
+              v[r].w = __fadd_rn(v[r].w, __fmul_rn(c[r].w, w));
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+            if (i0 + r * 128 < sub_docs) *reinterpret_cast<float4 *>(acc + i0 + r * 128 + lane * 4) = v[r];
+        }
+        first = false;
+        __syncwarp();
+      }
 #pragma unroll 1
       for (uint32_t t = 0; t < nt; t++) {
         const uint32_t lo = rb[t * kRbStride + j], hi = rb[t * kRbStride + j + 1];
         if (hi <= lo) continue;
+        if (COLS && ((colmask >> t) & 1u)) continue;
         const QTerm q = qt[t];
         const bool scored = q.flags & 1u;
         if (STAGED && !MATCHER) {

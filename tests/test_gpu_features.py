@@ -15,13 +15,15 @@ from tests.parity import assert_parity
 pytestmark = pytest.mark.gpu
 
 MATCHER_KERNELS = ["cta", "warp", "warp-inplace"]      # Bool queries: query-order kernels
-KERNELS = MATCHER_KERNELS + ["reg", "reg-dense", "reg-sweep", "reg-light"]  # plain OR queries: also the tile-sweep kernel
+KERNELS = MATCHER_KERNELS + ["reg", "reg-dense", "reg-sweep", "reg-sweep-dense", "reg-light"]  # plain OR queries: also the column front end
+# "reg" = the automatic choice for plain OR queries: the warp kernel summing column terms from their dense columns.
 # reg-dense: every term with >= 2 postings and df >= N/64 gets a column (exercises the column path on tiny corpora)
-# reg-sweep: no columns, every query swept (sparse-scatter path only); reg-light: no columns, every query handed
-# to the warp kernel behind the sweep's front end
-REG_OPTIONS = {"reg-dense": {"dense_min_df": 2, "dense_den": 64, "sweep_min_postings": 1},
-               "reg-sweep": {"dense_den": 0, "sweep_min_postings": 1},
-               "reg-light": {"dense_den": 0, "sweep_min_postings": 1 << 40}}
+# reg-sweep*: the tile-sweep kernel (heavy_kernel 1), every query swept, without / with columns
+# reg-light: the tile-sweep front end with every query handed to the warp kernel
+REG_OPTIONS = {"reg-dense": {"dense_min_df": 2, "dense_den": 64},
+               "reg-sweep": {"heavy_kernel": 1, "dense_den": 0, "sweep_min_postings": 1},
+               "reg-sweep-dense": {"heavy_kernel": 1, "dense_min_df": 2, "dense_den": 64, "sweep_min_postings": 1},
+               "reg-light": {"heavy_kernel": 1, "dense_den": 0, "sweep_min_postings": 1 << 40}}
 
 
 def _oracle(seg, **kw):
@@ -41,7 +43,7 @@ def _gpu(seg, kernel="auto", k1=0.9, b=0.4, **kw):
 def _check(gi, ora, qb, k, got, kernel, **oracle_kw):
     """query-order kernels: bit-exact vs the oracle; register-tile kernel: bit-exact vs the oracle on its
     declared term order + 1e-5 rule vs the query order"""
-    assert_engine_parity(gi, ora, qb, k, got, exact_order=kernel in MATCHER_KERNELS, **oracle_kw)
+    assert_engine_parity(gi, ora, qb, k, got, exact_order=kernel in MATCHER_KERNELS + ["auto"], **oracle_kw)
 
 
 def node(op, column=-1, i=(0, 0), f=(0.0, 0.0), nc=0, v=(0, 0)):
@@ -135,7 +137,7 @@ def test_large_k_goes_through_the_cta_kernel(k):
     gi, _ = _gpu(seg)
     for mode in ("bm25", "bmw"):
         got = gi.search_batch(qb, k, mode)
-        assert_engine_parity(gi, ora, qb, k, got, exact_order=k > 32)  # k <= 32 runs the register-tile kernel
+        assert_engine_parity(gi, ora, qb, k, got, exact_order=True)  # warp kernel for k <= 32, CTA kernel above: query order
     gi.close()
 
 
@@ -359,7 +361,11 @@ def test_post_image_load_equals_csr_load():
     gi.load_segment_post_image(seg, img, off)
     assert gi.segment_stats(0)["n_postings"] == len(seg.post_docs)
     for mode in ("bm25", "bmw"):
-        assert_engine_parity(gi, ora, qb, 11, gi.search_batch(qb, 11, mode))
+        assert_engine_parity(gi, ora, qb, 11, gi.search_batch(qb, 11, mode), exact_order=True)
+    gi.close()
+    gi = GpuIndex(0, kernel="reg")
+    gi.load_segment_post_image(seg, img, off)
+    assert_engine_parity(gi, ora, qb, 11, gi.search_batch(qb, 11, "bm25"))
     gi.close()
     gi = GpuIndex(0, kernel="warp")
     gi.load_segment_post_image(seg, img, off)
@@ -373,7 +379,7 @@ def test_post_image_load_equals_csr_load():
 
 
 # ---- several segments in one handle: api/reader.rs:2670-2777 ----------------------------------------------
-@pytest.mark.parametrize("kernel", ["cta", "warp", "reg", "reg-dense", "reg-sweep"])
+@pytest.mark.parametrize("kernel", ["cta", "warp", "reg", "reg-dense", "reg-sweep", "reg-sweep-dense"])
 def test_multi_segment_merge_order(kernel):
     from oracle import slo
     from searchlite_b200.shard import shard_ranges
@@ -490,7 +496,7 @@ def test_rerank_matches_oracle_formulae(metric, bf16):
 
 
 # ---- statistics (QueryStats, query/wand.rs:45-50) -----------------------------------------------------------
-@pytest.mark.parametrize("kernel", ["cta", "warp", "warp-inplace", "reg", "reg-dense", "reg-sweep", "reg-light"])
+@pytest.mark.parametrize("kernel", ["cta", "warp", "warp-inplace", "reg", "reg-dense", "reg-sweep", "reg-sweep-dense", "reg-light"])
 def test_stats_count_scored_docs_and_postings(kernel):
     spec = synth.CorpusSpec(n_docs=15_000, vocab=1_200, seed=91, len_lo=10, len_hi=50)
     seg = synth.generate_segment(spec, "cpu")

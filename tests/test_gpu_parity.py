@@ -49,17 +49,15 @@ def test_bm25_bit_exact_vs_oracle(small, kernel, tile_docs, sub_docs, k):
     gi.close()
 
 
-@pytest.mark.parametrize("v", [4, 8])
 @pytest.mark.parametrize("k", [1, 11, 32])
 @pytest.mark.parametrize("dense_den", [0, 8, 64])
-@pytest.mark.parametrize("min_postings", [0, 1])
-def test_register_kernel_vs_oracle(small, v, k, dense_den, min_postings):
-    """dense_den 0: no columns (pure sparse path, query order); 8: default; 64: most query terms are columns.
-    min_postings 0: queries with few postings go to the warp kernel; 1: every query is swept"""
+@pytest.mark.parametrize("sub_docs", [256, 2048])
+def test_column_front_end_vs_oracle(small, k, dense_den, sub_docs):
+    """column front end 0: warp kernel, column terms summed from their dense columns.
+    dense_den 0: no columns (query order); 8: default; 64: most query terms are columns"""
     seg, qb = small
     ora = _oracle(seg)
-    gi = GpuIndex(0, kernel="reg", options={**DENSE, "dense_den": dense_den, "reg_tile_v": v, "sweep_min_postings": min_postings,
-                                            "seed_docs": 4096 if k == 11 else 16384})
+    gi = GpuIndex(0, kernel="reg", sub_docs=sub_docs, options={**DENSE, "dense_den": dense_den})
     gi.load_segment(seg)
     n_col = sum(gi.term_has_column(0, int(t)) for t in np.unique(qb.terms["term_id"]))
     assert (n_col == 0) == (dense_den == 0)
@@ -69,21 +67,54 @@ def test_register_kernel_vs_oracle(small, v, k, dense_den, min_postings):
     gi.close()
 
 
-def test_register_kernel_is_the_default_for_plain_or_queries(small):
+@pytest.mark.parametrize("v", [4, 8])
+@pytest.mark.parametrize("k", [1, 11, 32])
+@pytest.mark.parametrize("dense_den", [0, 8, 64])
+@pytest.mark.parametrize("min_postings", [0, 1])
+def test_sweep_kernel_vs_oracle(small, v, k, dense_den, min_postings):
+    """the tile-sweep kernel (heavy_kernel 1).  dense_den 0: no columns (pure sparse path, query order); 8:
+    default; 64: most query terms are columns.  min_postings 0: queries with few postings go to the warp
+    kernel; 1: every query is swept"""
     seg, qb = small
+    ora = _oracle(seg)
+    gi = GpuIndex(0, kernel="reg", options={**DENSE, "heavy_kernel": 1, "dense_den": dense_den, "reg_tile_v": v,
+                                            "sweep_min_postings": min_postings, "seed_docs": 4096 if k == 11 else 16384})
+    gi.load_segment(seg)
+    n_col = sum(gi.term_has_column(0, int(t)) for t in np.unique(qb.terms["term_id"]))
+    assert (n_col == 0) == (dense_den == 0)
+    for mode in ("bm25", "wand", "bmw"):
+        got = gi.search_batch(qb, k, mode)
+        assert_engine_parity(gi, ora, qb, k, got, exact_order=(dense_den == 0))
+    gi.close()
+
+
+def test_automatic_kernel_keeps_query_order_and_column_budget(small):
+    seg, qb = small
+    ora = _oracle(seg)
+    ref = ora.search_batch(qb, 11, "bm25")
+    # automatic choice for plain OR queries: the warp kernel, reference summation order, bit-exact
     gi = GpuIndex(0, options=DENSE)
     gi.load_segment(seg)
-    reg = GpuIndex(0, kernel="reg", options=DENSE)
-    reg.load_segment(seg)
-    a, b = gi.search_batch(qb, 11, "bm25"), reg.search_batch(qb, 11, "bm25")
+    auto = gi.search_batch(qb, 11, "bm25")
+    assert_parity(*ref, *auto, strict=True)
+    warp = GpuIndex(0, kernel="warp", options=DENSE)
+    warp.load_segment(seg)
+    w = warp.search_batch(qb, 11, "bm25")
+    assert auto[0].tobytes() == w[0].tobytes() and auto[1].tobytes() == w[1].tobytes()
+    # both column front ends share one float contract
+    r0 = GpuIndex(0, kernel="reg", options={**DENSE, "heavy_kernel": 0})
+    r0.load_segment(seg)
+    r1 = GpuIndex(0, kernel="reg", options={**DENSE, "heavy_kernel": 1})
+    r1.load_segment(seg)
+    a, b = r0.search_batch(qb, 11, "bm25"), r1.search_batch(qb, 11, "bm25")
     assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
-    assert_engine_parity(gi, _oracle(seg), qb, 11, a)
+    assert_engine_parity(r0, ora, qb, 11, a)
     # the column budget caps how many terms get a column; results stay within the contract
-    capped = GpuIndex(0, options={**DENSE, "max_column_bytes": 3 * (57344 * 4)})
+    capped = GpuIndex(0, kernel="reg", options={**DENSE, "max_column_bytes": 3 * (57344 * 4)})
     capped.load_segment(seg)
     assert sum(capped.term_has_column(0, t) for t in range(200)) == 3
-    assert_engine_parity(capped, _oracle(seg), qb, 11, capped.search_batch(qb, 11, "bm25"))
-    for g in (gi, reg, capped):
+    assert_engine_parity(capped, ora, qb, 11, capped.search_batch(qb, 11, "bm25"))
+    for g in (gi, warp, r0, r1, capped):
         g.close()
 
 
@@ -104,10 +135,11 @@ def test_pruned_modes_are_exact(small, execution, kernel):
 
 
 @pytest.mark.parametrize("execution", ["wand", "bmw"])
-def test_register_kernel_pruning_skips_work_and_stays_exact(small, execution):
+@pytest.mark.parametrize("heavy_kernel", [0, 1])
+def test_column_paths_pruning_skips_work_and_stays_exact(small, execution, heavy_kernel):
     seg, qb = small
     ora = _oracle(seg)
-    gi = GpuIndex(0, kernel="reg", options={**DENSE, "reg_tile_v": 4})
+    gi = GpuIndex(0, kernel="reg", sub_docs=256, options={**DENSE, "reg_tile_v": 4, "heavy_kernel": heavy_kernel})
     gi.load_segment(seg)
     full_h, full_c, full_st = gi.search_batch(qb, 11, "bm25", want_stats=True)
     got_h, got_c, st = gi.search_batch(qb, 11, execution, want_stats=True)
@@ -139,8 +171,9 @@ def test_full_size_c2_properties():
     k = 11
     results = {}
     canon = None
-    for kernel, mode in (("auto", "bm25"), ("auto", "bmw"), ("warp", "bm25"), ("warp-inplace", "bm25"), ("cta", "bm25")):
-        gi = GpuIndex(0, kernel=kernel)
+    for kernel, mode, opts in (("auto", "bm25", {}), ("auto", "bmw", {}), ("reg", "bm25", {"heavy_kernel": 0}), ("reg", "bmw", {"heavy_kernel": 0}),
+                               ("reg", "bm25", {"heavy_kernel": 1}), ("warp-inplace", "bm25", {}), ("cta", "bm25", {})):
+        gi = GpuIndex(0, kernel=kernel, options=opts)
         gi.load_segment(seg)
         p = gi.prepare(qb, k, mode)
         p.run()
@@ -148,17 +181,19 @@ def test_full_size_c2_properties():
         p.run()
         again = p.fetch()
         assert first[0].tobytes() == again[0].tobytes() and first[1].tobytes() == again[1].tobytes()  # re-runnable
-        results[(kernel, mode)] = first
-        if kernel == "auto" and canon is None:
+        results[(kernel, mode, opts.get("heavy_kernel"))] = first
+        if kernel == "reg" and canon is None:
             from tests.helpers import canonical_batch
             canon = canonical_batch(gi, qb.subset(0, 48))
             assert any(gi.term_has_column(0, int(t)) for t in qb.terms["term_id"][:200])
         p.free()
         gi.close()
-    base_h, base_c = results[("auto", "bm25")]
-    assert results[("auto", "bmw")][0].tobytes() == base_h.tobytes()
-    w_h, w_c = results[("warp", "bm25")]
-    for key in (("warp-inplace", "bm25"), ("cta", "bm25")):
+    w_h, w_c = results[("auto", "bm25", None)]                      # query order (warp kernel)
+    base_h, base_c = results[("reg", "bm25", 0)]                    # column order
+    assert results[("auto", "bmw", None)][0].tobytes() == w_h.tobytes()
+    assert results[("reg", "bmw", 0)][0].tobytes() == base_h.tobytes()
+    assert results[("reg", "bm25", 1)][0].tobytes() == base_h.tobytes() and results[("reg", "bm25", 1)][1].tobytes() == base_c.tobytes()
+    for key in (("warp-inplace", "bm25", None), ("cta", "bm25", None)):
         assert results[key][0].tobytes() == w_h.tobytes() and results[key][1].tobytes() == w_c.tobytes(), key
     assert_parity(w_h, w_c, base_h, base_c, strict=False)
     assert np.all(base_c == k)
