@@ -33,18 +33,30 @@ namespace {
 
 thread_local std::string g_open_error;
 
+// Per-batch buffers come from the device's stream-ordered pool (cudaMallocAsync): a prepare/free pair
+// per batch then costs microseconds instead of a cudaMalloc/cudaFree round trip per buffer.  The scope
+// guard names the stream; everything else (segment residency) uses plain cudaMalloc.
+thread_local cudaStream_t g_pool_stream = nullptr;
+struct PoolScope {
+  cudaStream_t prev;
+  explicit PoolScope(cudaStream_t s) : prev(g_pool_stream) { g_pool_stream = s; }
+  ~PoolScope() { g_pool_stream = prev; }
+};
+
 struct DevBuf {
   void *p = nullptr;
   size_t bytes = 0;
+  cudaStream_t pool = nullptr;  // non-null: allocated with cudaMallocAsync on this stream
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), pool(o.pool) { o.p = nullptr; o.bytes = 0; }
   DevBuf &operator=(DevBuf &&o) noexcept {
     if (this != &o) {
       release();
       p = o.p;
       bytes = o.bytes;
+      pool = o.pool;
       o.p = nullptr;
       o.bytes = 0;
     }
@@ -52,14 +64,18 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (pool) cudaFreeAsync(p, pool);
+      else cudaFree(p);
+    }
     p = nullptr;
     bytes = 0;
   }
   cudaError_t alloc(size_t n) {
     release();
     if (n == 0) n = 16;
-    cudaError_t e = cudaMalloc(&p, n);
+    pool = g_pool_stream;
+    cudaError_t e = pool ? cudaMallocAsync(&p, n, pool) : cudaMalloc(&p, n);
     if (e == cudaSuccess) bytes = n;
     else p = nullptr;
     return e;
@@ -123,6 +139,9 @@ struct slg_index {
   std::vector<FilterProg> filters;
   std::string err;
   slg_counters_t ctr{};
+  void *pinned = nullptr;        // host staging buffer kept between batches (one batch at a time uses it)
+  size_t pinned_bytes = 0;
+  bool pinned_busy = false;
   uint32_t tile_docs = 16384;
   uint32_t ctas_per_sm = 0;  // 0 = as many as shared memory allows
   uint32_t sub_docs = 2048;  // warp kernel: docs per warp-private accumulator
@@ -178,8 +197,18 @@ struct slg_batch {
   uint32_t n_segs_run = 0;
   void *pinned = nullptr;
   size_t pinned_bytes = 0;
+  bool pinned_from_index = false;
   ~slg_batch() {
-    if (pinned) cudaFreeHost(pinned);
+    if (pinned_from_index) ix->pinned_busy = false;
+    else if (pinned) {
+      if (!ix->pinned_busy && pinned_bytes > ix->pinned_bytes) {  // keep the larger buffer for the next batch
+        if (ix->pinned) cudaFreeHost(ix->pinned);
+        ix->pinned = pinned;
+        ix->pinned_bytes = pinned_bytes;
+      } else {
+        cudaFreeHost(pinned);
+      }
+    }
   }
 };
 
@@ -596,6 +625,14 @@ int32_t slg_open(int32_t device, slg_index_t **out) {
   ix->device = device;
   ix->n_sm = prop.multiProcessorCount;
   ix->smem_optin = prop.sharedMemPerBlockOptin;
+  {
+    // keep freed per-batch buffers in the pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
   for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ix->ev[i]);
   if (e != cudaSuccess) {
@@ -611,6 +648,7 @@ int32_t slg_close(slg_index_t *ix) {
   if (!ix) return SLG_OK;
   cudaSetDevice(ix->device);
   cudaStreamSynchronize(ix->stream);
+  if (ix->pinned) cudaFreeHost(ix->pinned);
   ix->segs.clear();
   for (auto &ev : ix->ev)
     if (ev) cudaEventDestroy(ev);
@@ -979,6 +1017,7 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   if (ix->segs.empty()) return fail(ix, SLG_ERR_INVALID, "no segment loaded");
   (void)bmw_block_size;  // bounds are taken over the stored 128-posting blocks; any block size gives the same (exact) result
   SLG_CUDA(ix, cudaSetDevice(ix->device));
+  PoolScope pool_scope(ix->stream);
   auto bt = std::make_unique<slg_batch>();
   bt->ix = ix;
   bt->Q = n_queries;
@@ -1257,7 +1296,13 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
     SLG_CUDA(ix, bt->out_counts.alloc((size_t)n_queries * 4));
   }
   bt->pinned_bytes = (size_t)n_queries * k * sizeof(slg_hit_t) + (size_t)n_queries * 4 + (size_t)n_queries * 32;
-  SLG_CUDA(ix, cudaMallocHost(&bt->pinned, bt->pinned_bytes));
+  if (!ix->pinned_busy && ix->pinned && ix->pinned_bytes >= bt->pinned_bytes) {
+    bt->pinned = ix->pinned;
+    bt->pinned_from_index = true;
+    ix->pinned_busy = true;
+  } else {
+    SLG_CUDA(ix, cudaMallocHost(&bt->pinned, bt->pinned_bytes));
+  }
   SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));
   *out = bt.release();
   return SLG_OK;
