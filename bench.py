@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=256, help="queries in the CPU baseline sample (0 = skip)")
     ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pruned", action="store_true", help="skip the extra timing of the block-max pruned execution")
     return ap.parse_args()
 
 
@@ -306,6 +307,45 @@ def main():
     prepared.run(sync=True)
     got_h, got_c = (searcher.exchange_and_merge(prepared) if world > 1 else prepared.fetch())
 
+    # ---- the same batch with block-max pruning (configs[1] names it): exact result, fewer postings scored ----
+    pruned = None
+    if args.execution == "bm25" and not args.no_pruned:
+        pp = gi.prepare(qb, k, "bmw")
+
+        def step_pruned():
+            pp.run(sync=True)
+            return searcher.exchange_and_merge(pp) if world > 1 else None
+        for _ in range(args.warmup):
+            step_pruned()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            p0.record(stream)
+            for _ in range(args.steps):
+                step_pruned()
+            p1.record(stream)
+        barrier()
+        tp = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        pr_ms = float(tp.item()) / args.steps
+        pp.run(sync=True)
+        pr_h, pr_c = (searcher.exchange_and_merge(pp) if world > 1 else pp.fetch())
+        pruned = {"execution": "bmw", "value": args.queries / (pr_ms / 1e3), "unit": "queries/s", "ms_per_step": pr_ms,
+                  "speedup_vs_exhaustive": ms_step / pr_ms,
+                  "identical_to_exhaustive": bool(pr_h.tobytes() == got_h.tobytes() and pr_c.tobytes() == got_c.tobytes())}
+        if world == 1 and not args.no_e2e:
+            for _ in range(max(1, args.warmup)):
+                gi.search_batch(qb, k, "bmw")
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            for _ in range(args.steps):
+                gi.search_batch(qb, k, "bmw")
+            torch.cuda.synchronize()
+            pe_ms = 1e3 * (time.perf_counter() - w0) / args.steps
+            pruned["e2e"] = {"value": args.queries / (pe_ms / 1e3), "unit": "queries/s", "ms_per_step": pe_ms}
+        pp.free()
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -330,8 +370,14 @@ def main():
                      "kernel": {"reg": "slg_score_warp_kernel<COLS> / slg_score_sweep_kernel", "cta": "slg_score_tiles_kernel"}.get(args.kernel, "slg_score_warp_kernel"),
                      "kernel_ms": score_ms, "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "5 B x sum of df over the batch's query terms (this rank's segment)"},
+        "pruned": pruned,
         "setup": {"corpus_gen_s": round(gen_s, 1), "load_segment_s": round(load_s, 1), "resident_bytes": int(c1["resident_bytes"])},
     }
+    if (world == 1 and args.execution == "bm25" and args.kernel in ("auto", "warp") and args.docs == 10_000_000
+            and args.queries == 4096 and not options and not args.sub_docs):
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one `ncu --set full` capture
+        line["roofline"]["traffic"] = 5.602360e9 + 12.372224e6
+        line["roofline"]["traffic_source"] = "profiles/r1_v5_warp_kernel_summary.txt"
 
     # ---- CPU baseline + parity on a bounded sample (rank 0, N = 1) ----
     if host_seg is not None:

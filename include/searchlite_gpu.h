@@ -162,6 +162,10 @@ int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, u
  *                           (default 8; 0 = no columns)
  *   "dense_min_df"     n    ... and df >= n (default 256)
  *   "max_column_bytes" n    byte budget of the columns of one segment, largest df first (default 24 GiB)
+ *   "maxscore_pct"     n    pruned executions of the warp kernel (MaxScore): per (query, tile) the terms whose
+ *                           bounds sum to less than n % of the running k-th score are not scattered; docs touched
+ *                           by the other terms are rescored exactly if they can still qualify (default 35;
+ *                           0 = tile skipping only).  The result is bit-identical to the exhaustive run.
  *   "heavy_kernel"     0|1  column front end (kernel_choice 3): 0 = warp kernel that sums a query's column
  *                           terms from their dense columns (default), 1 = tile-sweep kernel
  *   "reg_tile_v"       4|8     tile-sweep kernel: 128 * v docs per register tile (default 8)

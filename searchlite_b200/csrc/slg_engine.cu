@@ -156,6 +156,7 @@ struct slg_index {
   uint64_t sweep_min_postings = 0;  // sweep: a query without column terms and sum(df) below this goes to the warp kernel (0 = doc_count / 64)
   uint32_t seed_docs = 16384;    // sweep: docs of the seed pass
   uint32_t part_tiles = 0;       // sweep: tiles per unit of work (0 = automatic)
+  uint32_t maxscore_pct = 35;    // pruned warp kernel: non-essential bounds may sum to this % of the k-th score (0 = tile skip only)
   uint32_t heavy_kernel = 0;     // column front end: 0 = warp kernel summing column terms from their columns, 1 = tile-sweep kernel
   Segment *find(uint32_t ord) {
     for (auto &s : segs)
@@ -313,6 +314,8 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
   d.post_score = nullptr;
   d.cols = nullptr;
   d.term_col = nullptr;
+  d.col_tmax = nullptr;
+  d.tmax_stride = 0;
   d.col_stride = 0;
   d.n_terms = s->n_terms;
   d.doc_count = s->doc_count;
@@ -379,6 +382,8 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
         s->h_term_col = std::move(tcol);
         d.cols = s->cols.as<float>();
         d.term_col = s->term_col.as<int32_t>();
+        d.col_tmax = s->col_tmax.as<float>();
+        d.tmax_stride = s->tmax_stride;
       }
     }
   }
@@ -687,6 +692,7 @@ int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
   } else if (n == "sweep_min_postings") ix->sweep_min_postings = value;
   else if (n == "seed_docs") ix->seed_docs = (uint32_t)value;
   else if (n == "part_tiles") ix->part_tiles = (uint32_t)value;
+  else if (n == "maxscore_pct") ix->maxscore_pct = (uint32_t)std::min<uint64_t>(value, 100);
   else if (n == "heavy_kernel") {
     if (value > 1) return fail(ix, SLG_ERR_INVALID, "heavy_kernel must be 0 (warp kernel + columns) or 1 (tile sweep)");
     ix->heavy_kernel = (uint32_t)value;
@@ -1477,6 +1483,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         wb.sub_docs = ix->sub_docs;
         wb.n_sub = bd.n_tiles;
         wb.n_groups = (bd.n_tiles + kSubPerGroup - 1) / kSubPerGroup;
+        wb.ms_frac = (float)ix->maxscore_pct / 100.0f;
         wb.thr_key = bd.thr_key;
         wb.topk_count = bd.topk_count;
         wb.lock = bd.lock;

@@ -32,7 +32,7 @@ constexpr uint32_t kWarpCand = 64;
 
 struct __align__(16) QTerm {  // one query term resolved against one segment (32 B)
   uint64_t base;      // term_start: first padded posting index
-  uint64_t sc_base;   // COLS: element offset of the term's dense column in seg.cols (flags bit 2), else = base
+  uint64_t sc_base;   // element offset of the term's dense column in seg.cols, ~0 = the term has none
   uint32_t term;      // term id in the segment
   uint32_t uterm;     // row of the range / bound tables
   float weight;
@@ -54,6 +54,7 @@ struct WarpBatchDev {
   const float *scores;   // seg.post_score: resident unit-weight contributions (STAGED)
   const uint32_t *const *filter_bits;
   uint32_t n_queries, k, sub_docs, n_sub, n_groups;
+  float ms_frac;         // MaxScore: the non-essential bounds may sum to at most this fraction of the k-th score
   unsigned long long *thr_key;
   uint32_t *topk_count, *lock;
   unsigned long long *topk_keys;
@@ -87,15 +88,15 @@ __global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qter
     if (t < nt) {
       const uint32_t u = bt.qt_uterm[t0 + t];
       const uint32_t term = bt.ut_term[u];
-      r.base = term < seg.n_terms ? seg.term_start[term] : 0;
-      r.sc_base = r.base;  // seg.post_score is laid out like seg.post_doc
+      r.base = term < seg.n_terms ? seg.term_start[term] : 0;  // seg.post_score is laid out like seg.post_doc
+      r.sc_base = ~0ull;
       r.term = term;
       r.uterm = u;
       r.weight = bt.qt_weight[t0 + t];
       r.flags = (bt.qt_flags[t0 + t] & 1u) | 2u | ((uint32_t)bt.qt_group[t0 + t] << 8);
-      if (use_cols && seg.term_col && term < seg.n_terms && seg.term_col[term] >= 0 && (r.flags & 1u)) {
-        r.flags |= 4u;
+      if (seg.term_col && term < seg.n_terms && seg.term_col[term] >= 0 && (r.flags & 1u)) {
         r.sc_base = (uint64_t)seg.term_col[term] * seg.col_stride;
+        if (use_cols) r.flags |= 4u;
       }
     }
     qterms[(uint64_t)slot * kWarpMaxTerms + t] = r;
@@ -104,8 +105,9 @@ __global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qter
 
 constexpr uint32_t kRbStride = 9;
 __host__ __device__ inline size_t warp_kernel_smem_per_warp(uint32_t sub_docs, bool matcher, bool prune) {
+  // (every term is a multiple of 16 B)
   return (size_t)sub_docs * 4 + kWarpCand * 8 + kWarpMaxTerms * sizeof(QTerm) + kWarpMaxTerms * kRbStride * 4 +
-         (prune ? kWarpMaxTerms * 8 * 4 : 0) + (matcher ? sub_docs : 0);  // every term is a multiple of 16 B
+         (prune ? kWarpMaxTerms * 8 * 4 : 0) + (matcher ? sub_docs : 0);
 }
 
 // 64-key descending bitonic sort in the warp's shared buffer
@@ -198,8 +200,21 @@ __device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ d
 // posting; the warp first fills its accumulator with the sum of the query's column slices (128-bit
 // loads, query order), then scatters the remaining terms on top.  Float contract of that path: the
 // terms WITH a column in query order, then the terms WITHOUT one in query order, one left fold.
+//
+// PRUNE on plain OR queries with resident scores adds MaxScore on top of the tile skip.  Per (query,
+// sub-tile) the terms are ranked by their bound inside the sub-tile; the longest prefix whose bounds
+// sum to less than the running k-th score is "non-essential": a doc that holds only such terms cannot
+// enter the top k, so their postings are not scattered at all (the prefix is also capped at a fraction
+// of the threshold, ms_frac: with loose bounds too many docs would need the exact rescoring below).
+// A doc touched by the other terms is a
+// candidate if its partial score plus the non-essential bounds can still reach the threshold; its
+// exact score is then recomputed over ALL terms in query order — dense-column lookup for column terms,
+// binary search inside the sub-tile's posting range otherwise — so the result is bit-identical to
+// the exhaustive run.  (TermState upper bounds: query/wand.rs:238-303; the reference's wand_loop
+// prunes document-at-a-time with the same bounds, query/wand.rs:659-903.)
 template <bool MATCHER, bool PRUNE, bool STATS, bool STAGED, bool COLS = false>
 __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg, WarpBatchDev wb) {
+  constexpr bool MAXSCORE = PRUNE && !MATCHER && STAGED && !COLS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarps = kThreads / 32;
@@ -213,6 +228,10 @@ __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg
   uint32_t *rb = reinterpret_cast<uint32_t *>(qt + kWarpMaxTerms);   // [t][9], boundary j at rb[t*9 + j]
   float *ubs = reinterpret_cast<float *>(rb + kWarpMaxTerms * kRbStride);   // [t][8]
   uint8_t *gmask = reinterpret_cast<uint8_t *>(ubs + (PRUNE ? kWarpMaxTerms * 8 : 0));
+  // MaxScore: up to 64 pending doc ids share the upper half of the candidate buffer, which is only
+  // written by the sort inside push_keys — and that never runs while doc ids are parked there
+  uint32_t *pend = reinterpret_cast<uint32_t *>(cand + 32);
+  (void)pend;
   (void)kWarps;
 
   const uint32_t k = wb.k;
@@ -290,7 +309,25 @@ __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg
           continue;
         }
       }
-      if (STATS) n_post += mine_n;
+      // ---- MaxScore: the non-essential terms of this sub-tile ----
+      uint32_t nmask = 0;
+      float sum_n = 0.0f;
+      if (MAXSCORE && thr != kThrInit) {
+        const float thr_score = __uint_as_float((uint32_t)(thr >> 32));
+        float pre = 0.0f;  // bounds of the terms ranked at or below this lane's term, ascending by bound
+#pragma unroll
+        for (int m = 0; m < (int)kWarpMaxTerms; m++) {
+          const float u = __shfl_sync(0xFFFFFFFFu, mine_ub, m);
+          if (u < mine_ub || (u == mine_ub && m <= lane)) pre += u;
+        }
+        const bool noness = mine_n != 0u && pre * 1.00001f < thr_score * wb.ms_frac;
+        nmask = __ballot_sync(0xFFFFFFFFu, noness);
+        float sn = noness ? pre : 0.0f;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) sn = fmaxf(sn, __shfl_xor_sync(0xFFFFFFFFu, sn, o));
+        sum_n = __shfl_sync(0xFFFFFFFFu, sn, 0);
+      }
+      if (STATS) n_post += ((nmask >> lane) & 1u) ? 0u : mine_n;
 
       // ---- accumulate ----
       bool first = true;
@@ -329,11 +366,12 @@ __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg
         const uint32_t lo = rb[t * kRbStride + j], hi = rb[t * kRbStride + j + 1];
         if (hi <= lo) continue;
         if (COLS && ((colmask >> t) & 1u)) continue;
+        if (MAXSCORE && ((nmask >> t) & 1u)) continue;
         const QTerm q = qt[t];
         const bool scored = q.flags & 1u;
         if (STAGED && !MATCHER) {
           const uint32_t *dptr = seg.post_doc + q.base;
-          const float *sptr = wb.scores + q.sc_base;
+          const float *sptr = wb.scores + q.base;
           if (q.weight == 1.0f) {
             if (first) accumulate_staged<true, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, acc, lane);
             else accumulate_staged<false, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, acc, lane);
@@ -359,7 +397,71 @@ __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg
       }
 
       // ---- scan + clear; collect keys that beat the threshold ----
-      const uint32_t thr_hi = (uint32_t)(thr >> 32);
+      uint32_t thr_hi = (uint32_t)(thr >> 32);
+      if (MAXSCORE && nmask) {
+        // a partial score below this cannot reach the threshold even with every non-essential bound added
+        const float cut = __uint_as_float(thr_hi) * 0.99998f - sum_n * 1.00002f;
+        thr_hi = cut > 0.0f ? __float_as_uint(cut) : 0u;
+      }
+      // append one ballot round of keys to the warp's candidates; past 32 pending: sort, keep the best k
+      auto push_keys = [&](bool pass, unsigned long long key) {
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
+        if (!bal) return;
+        if (pass) cand[cnt + __popc(bal & lt_mask)] = key;
+        cnt += __popc(bal);
+        __syncwarp();
+        if (cnt > 32) {
+          // keep the best k of everything seen so far in this item; raise the local threshold
+          for (uint32_t z = cnt + lane; z < kWarpCand; z += 32) cand[z] = 0ull;
+          __syncwarp();
+          warp_sort64_desc(cand, lane);
+          cnt = min(cnt, k);
+          if (cnt == k) thr = max(thr, cand[k - 1]);
+          __syncwarp();
+        }
+      };
+      // MaxScore: exact score of one parked doc per lane — every term of the query at the doc, query
+      // order: column lookup or binary search inside the sub-tile's posting range
+      uint32_t npend = 0;
+      auto rescore = [&](bool have, uint32_t doc) {
+        float s = 0.0f;
+        if (have) {
+          for (uint32_t t = 0; t < nt; t++) {
+            const QTerm &q = qt[t];
+            if (!(q.flags & 1u)) continue;
+            float c = 0.0f;
+            if (q.sc_base != ~0ull) {
+              c = __ldg(seg.cols + q.sc_base + doc);
+            } else {
+              const uint32_t *dp = seg.post_doc + q.base;
+              const uint32_t end = rb[t * kRbStride + j + 1];
+              uint32_t lo = rb[t * kRbStride + j], hi = end;
+              while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(dp + mid) < doc) lo = mid + 1;
+                else hi = mid;
+              }
+              if (lo < end && __ldg(dp + lo) == doc) c = __ldg(wb.scores + q.base + lo);
+            }
+            if (c != 0.0f) s = __fadd_rn(s, __fmul_rn(c, q.weight));
+          }
+        }
+        const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - doc);
+        bool pass = have && key > thr;
+        if (pass) pass = (seg.live_bits[doc >> 5] >> (doc & 31)) & 1u;
+        if (pass && head.filter >= 0) pass = (wb.filter_bits[head.filter][doc >> 5] >> (doc & 31)) & 1u;
+        push_keys(pass, key);
+      };
+      // every parked doc (at most 64): read them all before the first push may reuse the buffer
+      auto rescore_pending = [&]() {
+        const uint32_t n = npend;
+        npend = 0;
+        const uint32_t d0 = lane < (int)n ? pend[lane] : 0u;
+        const uint32_t d1 = 32u + lane < n ? pend[32 + lane] : 0u;
+        __syncwarp();
+        rescore(lane < (int)n, d0);
+        if (n > 32u) rescore(32u + lane < n, d1);
+      };
 #pragma unroll 1
       for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) {
         const uint32_t i = i0 + lane * 4;  // (reads past tile_n stay inside the warp's buffer and are zero)
@@ -375,37 +477,37 @@ __global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg
         }
         if (__any_sync(0xFFFFFFFFu, m >= thr_hi && m != 0u)) {
           const uint32_t bits[4] = {b0, b1, b2, b3};
+          if (MAXSCORE && nmask) {
+            // partial scores: park the docs that can still make it, rescore them 32 at a time
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            bool pass = bits[e] >= thr_hi && bits[e] != 0u;
-            const uint32_t doc = tile_lo + i + e;
-            const unsigned long long key = ((unsigned long long)bits[e] << 32) | (unsigned long long)(0xFFFFFFFFu - doc);
-            if (pass) pass = key > thr;
-            if (pass) pass = (seg.live_bits[doc >> 5] >> (doc & 31)) & 1u;
-            if (pass && MATCHER) {
-              const uint32_t mm = (gm >> (8 * e)) & 255u;
-              const uint32_t must = masks & 255u, nots = (masks >> 8) & 255u, should = (masks >> 16) & 255u;
-              pass = ((mm & must) == must) && ((mm & nots) == 0u) && (__popc(mm & should) >= (int)(masks >> 24));
-            }
-            if (pass && head.filter >= 0) pass = (wb.filter_bits[head.filter][doc >> 5] >> (doc & 31)) & 1u;
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
-            if (bal) {
-              if (pass) cand[cnt + __popc(bal & lt_mask)] = key;
-              cnt += __popc(bal);
+            for (int e = 0; e < 4; e++) {
+              const bool pass = bits[e] >= thr_hi && bits[e] != 0u;
+              const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
+              if (pass) pend[npend + __popc(bal & lt_mask)] = tile_lo + i + e;
+              npend += __popc(bal);
               __syncwarp();
-              if (cnt > 32) {
-                // keep the best k of everything seen so far in this item; raise the local threshold
-                for (uint32_t z = cnt + lane; z < kWarpCand; z += 32) cand[z] = 0ull;
-                __syncwarp();
-                warp_sort64_desc(cand, lane);
-                cnt = min(cnt, k);
-                if (cnt == k) thr = max(thr, cand[k - 1]);
-                __syncwarp();
+              if (npend >= 32u) rescore_pending();
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              bool pass = bits[e] >= thr_hi && bits[e] != 0u;
+              const uint32_t doc = tile_lo + i + e;
+              const unsigned long long key = ((unsigned long long)bits[e] << 32) | (unsigned long long)(0xFFFFFFFFu - doc);
+              if (pass) pass = key > thr;
+              if (pass) pass = (seg.live_bits[doc >> 5] >> (doc & 31)) & 1u;
+              if (pass && MATCHER) {
+                const uint32_t mm = (gm >> (8 * e)) & 255u;
+                const uint32_t must = masks & 255u, nots = (masks >> 8) & 255u, should = (masks >> 16) & 255u;
+                pass = ((mm & must) == must) && ((mm & nots) == 0u) && (__popc(mm & should) >= (int)(masks >> 24));
               }
+              if (pass && head.filter >= 0) pass = (wb.filter_bits[head.filter][doc >> 5] >> (doc & 31)) & 1u;
+              push_keys(pass, key);
             }
           }
         }
       }
+      if (MAXSCORE && npend) rescore_pending();
       __syncwarp();
     }
 
