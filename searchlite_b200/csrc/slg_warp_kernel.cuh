@@ -129,70 +129,65 @@ __device__ __forceinline__ void warp_sort64_desc(unsigned long long *a, int lane
   }
 }
 
-// postings [lo, hi) of one term from the staged (doc, score) streams into the warp's accumulator
+// postings [lo, hi) of one term from the resident (doc, score) streams into the warp's accumulator.
+// Lane L takes postings L, L + 32, L + 64, L + 96 of every group of 128: one shared-memory instruction
+// then touches 32 CONSECUTIVE postings, whose docs lie close together — for the dense head terms that
+// carry most of the work they spread over the 32 banks far better than every fourth posting does.
+// The next group's loads are issued before this group's read-modify-writes.
 template <bool FIRST, bool UNIT_W>
 __device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ dptr, const float *__restrict__ sptr, uint32_t lo,
                                                   uint32_t hi, uint32_t tile_lo, float w, float *acc, int lane) {
-  if (hi - lo < 160u) {
-    // short range: one posting per lane per step keeps the lanes busy
+  if (hi - lo <= 32u) {
+    // short range: one posting per lane per step
     for (uint32_t i = lo + lane; i < hi; i += 32) {
-      float s = __ldg(sptr + i);
-      if (!UNIT_W) s = __fmul_rn(s, w);
+      float v = __ldg(sptr + i);
+      if (!UNIT_W) v = __fmul_rn(v, w);
       float *p = acc + (__ldg(dptr + i) - tile_lo);
-      *p = FIRST ? s : __fadd_rn(*p, s);
+      *p = FIRST ? v : __fadd_rn(*p, v);
     }
     return;
   }
-  const uint32_t a_lo = (lo + 3u) & ~3u, a_hi = hi & ~3u;
-  if (lane < (int)(a_lo - lo)) {
-    float s = __ldg(sptr + lo + lane);
-    if (!UNIT_W) s = __fmul_rn(s, w);
-    float *p = acc + (__ldg(dptr + lo + lane) - tile_lo);
-    *p = FIRST ? s : __fadd_rn(*p, s);
+  uint32_t i = lo + lane;
+  uint32_t d[4];
+  float s[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    d[k] = tile_lo;
+    s[k] = 0.0f;
+    if (i + 32 * k < hi) {
+      d[k] = __ldg(dptr + i + 32 * k);
+      s[k] = __ldg(sptr + i + 32 * k);
+    }
   }
-  if (lane >= 4 && lane - 4 < (int)(hi - a_hi)) {
-    const uint32_t i = a_hi + (lane - 4);
-    float s = __ldg(sptr + i);
-    if (!UNIT_W) s = __fmul_rn(s, w);
-    float *p = acc + (__ldg(dptr + i) - tile_lo);
-    *p = FIRST ? s : __fadd_rn(*p, s);
-  }
-  uint32_t i = a_lo + lane * 4;
-  if (i >= a_hi) return;
-  uint4 d = __ldg(reinterpret_cast<const uint4 *>(dptr + i));
-  float4 s = __ldg(reinterpret_cast<const float4 *>(sptr + i));
   for (;;) {
     const uint32_t inext = i + 128;
-    const bool more = inext < a_hi;
-    uint4 dn = d;
-    float4 sn = s;
-    if (more) {
-      dn = __ldg(reinterpret_cast<const uint4 *>(dptr + inext));
-      sn = __ldg(reinterpret_cast<const float4 *>(sptr + inext));
+    uint32_t dn[4];
+    float sn[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      dn[k] = tile_lo;
+      sn[k] = 0.0f;
+      if (inext + 32 * k < hi) {
+        dn[k] = __ldg(dptr + inext + 32 * k);
+        sn[k] = __ldg(sptr + inext + 32 * k);
+      }
     }
-    if (!UNIT_W) {
-      s.x = __fmul_rn(s.x, w);
-      s.y = __fmul_rn(s.y, w);
-      s.z = __fmul_rn(s.z, w);
-      s.w = __fmul_rn(s.w, w);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i + 32 * k < hi) {
+        float v = s[k];
+        if (!UNIT_W) v = __fmul_rn(v, w);
+        float *p = acc + (d[k] - tile_lo);
+        *p = FIRST ? v : __fadd_rn(*p, v);  // distinct docs inside a list: no aliasing between lanes
+      }
     }
-    float *p0 = acc + (d.x - tile_lo), *p1 = acc + (d.y - tile_lo), *p2 = acc + (d.z - tile_lo), *p3 = acc + (d.w - tile_lo);
-    if (FIRST) {
-      *p0 = s.x;
-      *p1 = s.y;
-      *p2 = s.z;
-      *p3 = s.w;
-    } else {
-      const float a0 = *p0, a1 = *p1, a2 = *p2, a3 = *p3;  // distinct docs: no aliasing inside a list
-      *p0 = __fadd_rn(a0, s.x);
-      *p1 = __fadd_rn(a1, s.y);
-      *p2 = __fadd_rn(a2, s.z);
-      *p3 = __fadd_rn(a3, s.w);
-    }
-    if (!more) break;
-    d = dn;
-    s = sn;
+    if (inext - lane >= hi) break;
     i = inext;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      d[k] = dn[k];
+      s[k] = sn[k];
+    }
   }
 }
 
@@ -213,7 +208,7 @@ __device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ d
 // the exhaustive run.  (TermState upper bounds: query/wand.rs:238-303; the reference's wand_loop
 // prunes document-at-a-time with the same bounds, query/wand.rs:659-903.)
 template <bool MATCHER, bool PRUNE, bool STATS, bool STAGED, bool COLS = false>
-__global__ void __launch_bounds__(kThreads) slg_score_warp_kernel(SegmentDev seg, WarpBatchDev wb) {
+__global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev seg, WarpBatchDev wb) {
   constexpr bool MAXSCORE = PRUNE && !MATCHER && STAGED && !COLS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
