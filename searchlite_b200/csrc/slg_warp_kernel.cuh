@@ -134,16 +134,21 @@ __device__ __forceinline__ void warp_sort64_desc(unsigned long long *a, int lane
 // then touches 32 CONSECUTIVE postings, whose docs lie close together — for the dense head terms that
 // carry most of the work they spread over the 32 banks far better than every fourth posting does.
 // The next group's loads are issued before this group's read-modify-writes.
+// wmax collects (as bits; scores are positive) the largest value this lane wrote: contributions are
+// positive, so the largest value ever written to the accumulator is the largest final score of the
+// sub-tile, and the scan for candidates can be skipped when it is below the threshold.
 template <bool FIRST, bool UNIT_W>
 __device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ dptr, const float *__restrict__ sptr, uint32_t lo,
-                                                  uint32_t hi, uint32_t tile_lo, float w, float *acc, int lane) {
+                                                  uint32_t hi, uint32_t tile_lo, float w, float *acc, int lane, uint32_t &wmax) {
   if (hi - lo <= 32u) {
     // short range: one posting per lane per step
     for (uint32_t i = lo + lane; i < hi; i += 32) {
       float v = __ldg(sptr + i);
       if (!UNIT_W) v = __fmul_rn(v, w);
       float *p = acc + (__ldg(dptr + i) - tile_lo);
-      *p = FIRST ? v : __fadd_rn(*p, v);
+      if (!FIRST) v = __fadd_rn(*p, v);
+      *p = v;
+      wmax = max(wmax, __float_as_uint(v));
     }
     return;
   }
@@ -178,7 +183,9 @@ __device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ d
         float v = s[k];
         if (!UNIT_W) v = __fmul_rn(v, w);
         float *p = acc + (d[k] - tile_lo);
-        *p = FIRST ? v : __fadd_rn(*p, v);  // distinct docs inside a list: no aliasing between lanes
+        if (!FIRST) v = __fadd_rn(*p, v);  // distinct docs inside a list: no aliasing between lanes
+        *p = v;
+        wmax = max(wmax, __float_as_uint(v));
       }
     }
     if (inext - lane >= hi) break;
@@ -326,7 +333,9 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
 
       // ---- accumulate ----
       bool first = true;
+      uint32_t wmax = 0;  // largest value written to the accumulator by this lane (bits)
       if (COLS && colmask) {
+        wmax = 0xFFFFFFFFu;
         // column terms: accumulator = sum of the column slices, query order; four rows of 128 docs per
         // step so that four 128-bit loads per column are in flight
 #pragma unroll 1
@@ -368,11 +377,11 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
           const uint32_t *dptr = seg.post_doc + q.base;
           const float *sptr = wb.scores + q.base;
           if (q.weight == 1.0f) {
-            if (first) accumulate_staged<true, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, acc, lane);
-            else accumulate_staged<false, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, acc, lane);
+            if (first) accumulate_staged<true, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, acc, lane, wmax);
+            else accumulate_staged<false, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, acc, lane, wmax);
           } else {
-            if (first) accumulate_staged<true, false>(dptr, sptr, lo, hi, tile_lo, q.weight, acc, lane);
-            else accumulate_staged<false, false>(dptr, sptr, lo, hi, tile_lo, q.weight, acc, lane);
+            if (first) accumulate_staged<true, false>(dptr, sptr, lo, hi, tile_lo, q.weight, acc, lane, wmax);
+            else accumulate_staged<false, false>(dptr, sptr, lo, hi, tile_lo, q.weight, acc, lane, wmax);
           }
         } else {
           TermCtx tc;
@@ -386,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
           tc.gbit = MATCHER ? (uint8_t)(1u << ((q.flags >> 8) & 7u)) : 0;
           if (first && scored && !MATCHER) accumulate_term<MATCHER, true, 32>(seg, tc, lo, hi, tile_lo, acc, gmask, lane);
           else accumulate_term<MATCHER, false, 32>(seg, tc, lo, hi, tile_lo, acc, gmask, lane);
+          wmax = 0xFFFFFFFFu;  // not tracked on this path
         }
         if (scored) first = false;
         __syncwarp();
@@ -397,6 +407,13 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
         // a partial score below this cannot reach the threshold even with every non-essential bound added
         const float cut = __uint_as_float(thr_hi) * 0.99998f - sum_n * 1.00002f;
         thr_hi = cut > 0.0f ? __float_as_uint(cut) : 0u;
+      }
+      if (!STATS && !MATCHER && __reduce_max_sync(0xFFFFFFFFu, wmax) < thr_hi) {
+        // no score of this sub-tile reaches the threshold: nothing to collect, only clear
+#pragma unroll 4
+        for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) *reinterpret_cast<float4 *>(acc + i0 + lane * 4) = make_float4(0, 0, 0, 0);
+        __syncwarp();
+        continue;
       }
       // append one ballot round of keys to the warp's candidates; past 32 pending: sort, keep the best k
       auto push_keys = [&](bool pass, unsigned long long key) {
