@@ -376,8 +376,8 @@ def main():
     if (world == 1 and args.execution == "bm25" and args.kernel in ("auto", "warp") and args.docs == 10_000_000
             and args.queries == 4096 and not options and not args.sub_docs):
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one `ncu --set full` capture
-        line["roofline"]["traffic"] = 5.602360e9 + 12.372224e6
-        line["roofline"]["traffic_source"] = "profiles/r1_v5_warp_kernel_summary.txt"
+        line["roofline"]["traffic"] = 5.608199e9 + 13.091840e6
+        line["roofline"]["traffic_source"] = "profiles/r1_v7_warp_kernel_summary.txt"
 
     # ---- CPU baseline + parity on a bounded sample (rank 0, N = 1) ----
     if host_seg is not None:
