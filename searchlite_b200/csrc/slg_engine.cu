@@ -1386,7 +1386,13 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
       if (run_warp_side && n_warp_rows) {
         uint64_t n = (uint64_t)n_warp_rows * (bd.n_tiles + 1);
         uint64_t n2 = (uint64_t)n_warp_rows * bd.n_tiles;
-        slg_plan_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, bd, warp_rows, n_warp_rows);
+        if (warp_rows) {
+          slg_plan_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, bd, warp_rows, n_warp_rows);
+        } else {
+          // every unique term: short lists are walked once, long lists take one binary search per boundary
+          slg_sweep_plan_kernel<<<dim3(n_warp_rows, 8), 256, 0, st>>>(s->dev, bd.ut_term, nullptr, n_warp_rows, bd.tile_docs, bd.n_tiles,
+                                                                     true, bd.ut_rng);
+        }
         count_launch(ix);
         if (prune) {
           slg_plan_bounds_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(s->dev, bd, warp_rows, n_warp_rows);

@@ -736,14 +736,17 @@ __global__ void __launch_bounds__(256) slg_sweep_plan_kernel(SegmentDev seg, con
                                                               bool column_rows, uint32_t *rng) {
   const uint32_t r = blockIdx.x;
   if (r >= n_rows) return;
-  const uint32_t term = ut_term[row_u[r]];
-  if (term >= seg.n_terms) return;  // the record builder drops terms this segment does not hold
-  if (!column_rows && seg.term_col && seg.term_col[term] >= 0) return;
-  const uint32_t df = seg.term_df[term];
-  const uint32_t *d = seg.post_doc + seg.term_start[term];
+  const uint32_t term = ut_term[row_u ? row_u[r] : r];
   uint32_t *out = rng + (uint64_t)r * (n_tiles + 1);
   const uint32_t step = gridDim.y * blockDim.x;
   const uint32_t first = blockIdx.y * blockDim.x + threadIdx.x;
+  if (term >= seg.n_terms) {  // a key this segment does not hold: empty list
+    for (uint32_t j = first; j <= n_tiles; j += step) out[j] = 0u;
+    return;
+  }
+  if (!column_rows && seg.term_col && seg.term_col[term] >= 0) return;
+  const uint32_t df = seg.term_df[term];
+  const uint32_t *d = seg.post_doc + seg.term_start[term];
   if ((uint64_t)df <= 8ull * (n_tiles + 1)) {
     for (uint32_t i = first; i <= df; i += step) {
       const uint32_t a = i ? d[i - 1] / tile_docs + 1 : 0u;
