@@ -1649,6 +1649,7 @@ int32_t slg_merge_gathered(slg_index_t *ix, const void *dev_hits, const void *de
   cudaStream_t st = ix->stream;
   size_t msmem = (size_t)n_shards * k * sizeof(HitDev);
   if (msmem > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "merge of %u shards x k=%u does not fit shared memory", n_shards, k);
+  PoolScope pool_scope(st);  // per-call buffers from the stream-ordered pool
   DevBuf oh, oc;
   SLG_CUDA(ix, oh.alloc((size_t)n_queries * k * sizeof(HitDev)));
   SLG_CUDA(ix, oc.alloc((size_t)n_queries * 4));
@@ -1719,6 +1720,7 @@ int32_t slg_rerank(slg_index_t *ix, const float *query_vecs, uint32_t n_queries,
     segs.push_back(r);
   }
   if (cand_stride > kMaxRerankCands) return fail(ix, SLG_ERR_UNSUPPORTED, "more than %u candidates per query", kMaxRerankCands);
+  PoolScope pool_scope(st);  // per-call buffers from the stream-ordered pool
   DevBuf d_segs, d_q, d_c, d_n, d_o, d_vs;
   size_t nh = (size_t)n_queries * cand_stride;
   SLG_CUDA(ix, d_segs.alloc(segs.size() * sizeof(RerankSegDev)));
