@@ -216,7 +216,7 @@ __device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ d
 // prunes document-at-a-time with the same bounds, query/wand.rs:659-903.)
 template <bool MATCHER, bool PRUNE, bool STATS, bool STAGED, bool COLS = false>
 __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev seg, WarpBatchDev wb) {
-  constexpr bool MAXSCORE = PRUNE && !MATCHER && STAGED && !COLS;
+  constexpr bool MAXSCORE = PRUNE && !MATCHER && STAGED;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarps = kThreads / 32;
@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
     for (uint32_t i = lane * 4; i < sub_docs; i += 128) *reinterpret_cast<uint32_t *>(gmask + i) = 0u;
   __syncwarp();
 
+  bool dirty = false;  // COLS: the accumulator still holds the scores of the last column sub-tile
+  (void)dirty;
   uint32_t item = 0;
   if (lane == 0) item = atomicAdd(wb.work_counter, 1u);
   item = __shfl_sync(0xFFFFFFFFu, item, 0);
@@ -329,15 +331,23 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
         for (int o = 4; o > 0; o >>= 1) sn = fmaxf(sn, __shfl_xor_sync(0xFFFFFFFFu, sn, o));
         sum_n = __shfl_sync(0xFFFFFFFFu, sn, 0);
       }
+      if (COLS) colmask &= ~nmask;  // a non-essential column term is looked up for the parked docs only
       if (STATS) n_post += ((nmask >> lane) & 1u) ? 0u : mine_n;
 
       // ---- accumulate ----
       bool first = true;
       uint32_t wmax = 0;  // largest value written to the accumulator by this lane (bits)
+      if (COLS && !colmask && dirty) {
+        // no column term this time: the scores the last column sub-tile left behind have to go
+#pragma unroll 4
+        for (uint32_t i0 = 0; i0 < sub_docs; i0 += 128) *reinterpret_cast<float4 *>(acc + i0 + lane * 4) = make_float4(0, 0, 0, 0);
+        dirty = false;
+        __syncwarp();
+      }
       if (COLS && colmask) {
-        wmax = 0xFFFFFFFFu;
         // column terms: accumulator = sum of the column slices, query order; four rows of 128 docs per
-        // step so that four 128-bit loads per column are in flight
+        // step so that four 128-bit loads per column are in flight.  Every slot is overwritten, so a
+        // dirty accumulator needs no clearing first.
 #pragma unroll 1
         for (uint32_t i0 = 0; i0 < sub_docs; i0 += 512) {
           float4 v[4];
@@ -359,10 +369,13 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
             }
           }
 #pragma unroll
-          for (int r = 0; r < 4; r++)
+          for (int r = 0; r < 4; r++) {
             if (i0 + r * 128 < sub_docs) *reinterpret_cast<float4 *>(acc + i0 + r * 128 + lane * 4) = v[r];
+            wmax = max(wmax, max(max(__float_as_uint(v[r].x), __float_as_uint(v[r].y)), max(__float_as_uint(v[r].z), __float_as_uint(v[r].w))));
+          }
         }
         first = false;
+        dirty = false;
         __syncwarp();
       }
 #pragma unroll 1
@@ -409,9 +422,14 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
         thr_hi = cut > 0.0f ? __float_as_uint(cut) : 0u;
       }
       if (!STATS && !MATCHER && __reduce_max_sync(0xFFFFFFFFu, wmax) < thr_hi) {
-        // no score of this sub-tile reaches the threshold: nothing to collect, only clear
+        // no score of this sub-tile reaches the threshold: nothing to collect, only clear — and not even
+        // that after a column fill: the next column fill overwrites every slot
+        if (COLS && colmask) {
+          dirty = true;
+        } else {
 #pragma unroll 4
-        for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) *reinterpret_cast<float4 *>(acc + i0 + lane * 4) = make_float4(0, 0, 0, 0);
+          for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) *reinterpret_cast<float4 *>(acc + i0 + lane * 4) = make_float4(0, 0, 0, 0);
+        }
         __syncwarp();
         continue;
       }
@@ -438,9 +456,12 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
       auto rescore = [&](bool have, uint32_t doc) {
         float s = 0.0f;
         if (have) {
-          for (uint32_t t = 0; t < nt; t++) {
+          for (uint32_t tt = 0; tt < (COLS ? 2u * nt : nt); tt++) {
+            // COLS: the kernel's order — the terms summed from columns first, then the others
+            const uint32_t t = tt < nt ? tt : tt - nt;
             const QTerm &q = qt[t];
             if (!(q.flags & 1u)) continue;
+            if (COLS && (((q.flags >> 2) & 1u) != 0u) != (tt < nt)) continue;
             float c = 0.0f;
             if (q.sc_base != ~0ull) {
               c = __ldg(seg.cols + q.sc_base + doc);
