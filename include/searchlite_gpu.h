@@ -150,10 +150,10 @@ int32_t slg_close(slg_index_t *);
 const char *slg_last_error(const slg_index_t *);
 /* tuning knobs; 0 keeps the default.  tile_docs: docs per shared-memory tile of the CTA-per-item
  * kernel (multiple of 1024); sub_docs: docs per warp-private tile of the warp-per-item kernel
- * (multiple of 128); kernel_choice: 0 = automatic (warp kernel for k <= 32 and <= 8 terms per query,
- * CTA kernel otherwise), 1 = CTA kernel, 2 = warp kernel, 3 = column front end for plain OR queries
- * (see "heavy_kernel" below); add 256 to ignore the resident per-posting scores and score postings
- * in place. */
+ * (multiple of 128); kernel_choice: 0 = automatic (column front end — see "heavy_kernel" below — for
+ * plain OR queries with k <= 32 and <= 8 terms per query, warp kernel for the same shape with a Bool
+ * matcher, CTA kernel otherwise), 1 = CTA kernel, 2 = warp kernel (query summation order), 3 = column
+ * front end; add 256 to ignore the resident per-posting scores and score postings in place. */
 int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, uint32_t sub_docs,
                       uint32_t kernel_choice);
 /* residency / tuning options; the residency ones apply to segments loaded AFTER the call:

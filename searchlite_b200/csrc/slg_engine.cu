@@ -1106,9 +1106,8 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bool sweepable = all_scores;  // the sweep addresses postings with 32-bit indices
   for (auto &s : ix->segs) sweepable = sweepable && (s->post_pair.p != nullptr || s->n_blocks == 0);
   // tile-sweep kernel: plain OR queries (no matcher), small k, few terms, resident scores
-  // (explicit choice only: on the measured workloads neither column front end beats the plain warp kernel,
-  // which also keeps the reference's summation order)
-  bt->use_reg = ix->kernel_choice == 3;
+  // column front end: plain OR queries (no matcher), small k, few terms, resident scores and columns
+  bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && sweepable);
   if (bt->use_reg && !(small && !matcher && sweepable))
     return fail(ix, SLG_ERR_UNSUPPORTED,
                 "the sweep kernel handles plain OR queries, k <= %u, <= %u terms per query, resident scores, < 2^32 postings per segment",

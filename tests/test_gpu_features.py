@@ -43,7 +43,7 @@ def _gpu(seg, kernel="auto", k1=0.9, b=0.4, **kw):
 def _check(gi, ora, qb, k, got, kernel, **oracle_kw):
     """query-order kernels: bit-exact vs the oracle; register-tile kernel: bit-exact vs the oracle on its
     declared term order + 1e-5 rule vs the query order"""
-    assert_engine_parity(gi, ora, qb, k, got, exact_order=kernel in MATCHER_KERNELS + ["auto"], **oracle_kw)
+    assert_engine_parity(gi, ora, qb, k, got, exact_order=kernel in MATCHER_KERNELS, **oracle_kw)
 
 
 def node(op, column=-1, i=(0, 0), f=(0.0, 0.0), nc=0, v=(0, 0)):
@@ -137,7 +137,7 @@ def test_large_k_goes_through_the_cta_kernel(k):
     gi, _ = _gpu(seg)
     for mode in ("bm25", "bmw"):
         got = gi.search_batch(qb, k, mode)
-        assert_engine_parity(gi, ora, qb, k, got, exact_order=True)  # warp kernel for k <= 32, CTA kernel above: query order
+        assert_engine_parity(gi, ora, qb, k, got, exact_order=k > 32)  # k <= 32 runs the column front end (its own term order)
     gi.close()
 
 
@@ -361,9 +361,9 @@ def test_post_image_load_equals_csr_load():
     gi.load_segment_post_image(seg, img, off)
     assert gi.segment_stats(0)["n_postings"] == len(seg.post_docs)
     for mode in ("bm25", "bmw"):
-        assert_engine_parity(gi, ora, qb, 11, gi.search_batch(qb, 11, mode), exact_order=True)
+        assert_engine_parity(gi, ora, qb, 11, gi.search_batch(qb, 11, mode))
     gi.close()
-    gi = GpuIndex(0, kernel="reg")
+    gi = GpuIndex(0, kernel="reg", options={"heavy_kernel": 1})
     gi.load_segment_post_image(seg, img, off)
     assert_engine_parity(gi, ora, qb, 11, gi.search_batch(qb, 11, "bm25"))
     gi.close()

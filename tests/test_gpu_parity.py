@@ -1,5 +1,6 @@
 """GPU parity: CUDA engine (through the C ABI) vs the CPU oracle on the same seeded inputs.
 
+
 Float contract (include/searchlite_gpu.h): the CTA and warp kernels sum a doc's contributions in query
 term order — bit-identical to the oracle's `bm25` mode (brute_force, query/wand.rs:527-548); the
 tile-sweep kernel sums the terms with a dense column first, then the terms without one —
@@ -88,19 +89,15 @@ def test_sweep_kernel_vs_oracle(small, v, k, dense_den, min_postings):
     gi.close()
 
 
-def test_automatic_kernel_keeps_query_order_and_column_budget(small):
+def test_automatic_kernel_is_the_column_front_end(small):
     seg, qb = small
     ora = _oracle(seg)
     ref = ora.search_batch(qb, 11, "bm25")
-    # automatic choice for plain OR queries: the warp kernel, reference summation order, bit-exact
+    # automatic choice for plain OR queries: the warp kernel summing column terms from their columns
     gi = GpuIndex(0, options=DENSE)
     gi.load_segment(seg)
     auto = gi.search_batch(qb, 11, "bm25")
-    assert_parity(*ref, *auto, strict=True)
-    warp = GpuIndex(0, kernel="warp", options=DENSE)
-    warp.load_segment(seg)
-    w = warp.search_batch(qb, 11, "bm25")
-    assert auto[0].tobytes() == w[0].tobytes() and auto[1].tobytes() == w[1].tobytes()
+    assert_engine_parity(gi, ora, qb, 11, auto)
     # both column front ends share one float contract
     r0 = GpuIndex(0, kernel="reg", options={**DENSE, "heavy_kernel": 0})
     r0.load_segment(seg)
@@ -108,9 +105,13 @@ def test_automatic_kernel_keeps_query_order_and_column_budget(small):
     r1.load_segment(seg)
     a, b = r0.search_batch(qb, 11, "bm25"), r1.search_batch(qb, 11, "bm25")
     assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
-    assert_engine_parity(r0, ora, qb, 11, a)
+    assert auto[0].tobytes() == a[0].tobytes() and auto[1].tobytes() == a[1].tobytes()
+    # the explicit warp kernel keeps the reference's summation order, bit for bit
+    warp = GpuIndex(0, kernel="warp", options=DENSE)
+    warp.load_segment(seg)
+    assert_parity(*ref, *warp.search_batch(qb, 11, "bm25"), strict=True)
     # the column budget caps how many terms get a column; results stay within the contract
-    capped = GpuIndex(0, kernel="reg", options={**DENSE, "max_column_bytes": 3 * (57344 * 4)})
+    capped = GpuIndex(0, options={**DENSE, "max_column_bytes": 3 * (57344 * 4)})
     capped.load_segment(seg)
     assert sum(capped.term_has_column(0, t) for t in range(200)) == 3
     assert_engine_parity(capped, ora, qb, 11, capped.search_batch(qb, 11, "bm25"))
@@ -171,8 +172,8 @@ def test_full_size_c2_properties():
     k = 11
     results = {}
     canon = None
-    for kernel, mode, opts in (("auto", "bm25", {}), ("auto", "bmw", {}), ("reg", "bm25", {"heavy_kernel": 0}), ("reg", "bmw", {"heavy_kernel": 0}),
-                               ("reg", "bm25", {"heavy_kernel": 1}), ("warp-inplace", "bm25", {}), ("cta", "bm25", {})):
+    for kernel, mode, opts in (("auto", "bm25", {}), ("auto", "bmw", {}), ("reg", "bm25", {"heavy_kernel": 1}), ("warp", "bm25", {}),
+                               ("warp", "bmw", {}), ("warp-inplace", "bm25", {}), ("cta", "bm25", {})):
         gi = GpuIndex(0, kernel=kernel, options=opts)
         gi.load_segment(seg)
         p = gi.prepare(qb, k, mode)
@@ -182,16 +183,16 @@ def test_full_size_c2_properties():
         again = p.fetch()
         assert first[0].tobytes() == again[0].tobytes() and first[1].tobytes() == again[1].tobytes()  # re-runnable
         results[(kernel, mode, opts.get("heavy_kernel"))] = first
-        if kernel == "reg" and canon is None:
+        if kernel == "auto" and canon is None:
             from tests.helpers import canonical_batch
             canon = canonical_batch(gi, qb.subset(0, 48))
             assert any(gi.term_has_column(0, int(t)) for t in qb.terms["term_id"][:200])
         p.free()
         gi.close()
-    w_h, w_c = results[("auto", "bm25", None)]                      # query order (warp kernel)
-    base_h, base_c = results[("reg", "bm25", 0)]                    # column order
-    assert results[("auto", "bmw", None)][0].tobytes() == w_h.tobytes()
-    assert results[("reg", "bmw", 0)][0].tobytes() == base_h.tobytes()
+    base_h, base_c = results[("auto", "bm25", None)]               # column order (automatic choice)
+    w_h, w_c = results[("warp", "bm25", None)]                     # query order
+    assert results[("auto", "bmw", None)][0].tobytes() == base_h.tobytes()
+    assert results[("warp", "bmw", None)][0].tobytes() == w_h.tobytes()
     assert results[("reg", "bm25", 1)][0].tobytes() == base_h.tobytes() and results[("reg", "bm25", 1)][1].tobytes() == base_c.tobytes()
     for key in (("warp-inplace", "bm25", None), ("cta", "bm25", None)):
         assert results[key][0].tobytes() == w_h.tobytes() and results[key][1].tobytes() == w_c.tobytes(), key
