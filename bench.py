@@ -373,11 +373,15 @@ def main():
         "pruned": pruned,
         "setup": {"corpus_gen_s": round(gen_s, 1), "load_segment_s": round(load_s, 1), "resident_bytes": int(c1["resident_bytes"])},
     }
-    if (world == 1 and args.execution == "bm25" and args.kernel == "warp" and args.docs == 10_000_000
+    if (world == 1 and args.execution == "bm25" and args.kernel in ("auto", "warp") and args.docs == 10_000_000
             and args.queries == 4096 and not options and not args.sub_docs):
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one `ncu --set full` capture
-        line["roofline"]["traffic"] = 5.608199e9 + 13.091840e6
-        line["roofline"]["traffic_source"] = "profiles/r1_v7_warp_kernel_summary.txt"
+        if args.kernel == "auto":
+            line["roofline"]["traffic"] = 7.356216e9 + 13.366272e6
+            line["roofline"]["traffic_source"] = "profiles/r1_v8_warp_cols_kernel_summary.txt"
+        else:
+            line["roofline"]["traffic"] = 5.608199e9 + 13.091840e6
+            line["roofline"]["traffic_source"] = "profiles/r1_v7_warp_kernel_summary.txt"
 
     # ---- CPU baseline + parity on a bounded sample (rank 0, N = 1) ----
     if host_seg is not None:

@@ -1375,7 +1375,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
       BatchDev bw = bd;  // the view of the warp kernel: all queries, or the light ones behind the heavy slots
       uint32_t n_warp_rows = bt->U;
       const uint32_t *warp_rows = nullptr;
-      if (bt->use_reg) {
+      if (bt->use_reg && bt->n_heavy) {  // only the light queries' terms behind the swept slots
         bw.q_order = bd.q_order + bt->n_heavy;
         bw.n_queries = bt->n_light;
         n_warp_rows = bt->n_light_u;
