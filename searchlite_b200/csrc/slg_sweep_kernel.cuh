@@ -1,47 +1,48 @@
-// slg_sweep_kernel.cuh — K2/K3, tile-sweep variant with register accumulators: the default for plain
-// OR queries (no matcher), k <= 32 and <= 8 terms per query — the shape of BASELINE.json configs[1].
+// slg_sweep_kernel.cuh — K2/K3, tile-sweep variant with register accumulators (kernel choice 3 with
+// option heavy_kernel = 1) for plain OR queries (no matcher), k <= 32 and <= 8 terms per query — the
+// shape of BASELINE.json configs[1].  Correct on every parity test, not (yet) the fastest path: see
+// profiles/r1_sweep_experiments.txt for the six variants measured in round 1 and what limits them.
 //
 // Why this shape.  A batch names the same head terms over and over (at C2 the sum of df over term
 // INSTANCES is ~17x the sum over UNIQUE terms, and 83 % of all posting visits belong to the ~90 terms
-// with df >= N/8).  Scatter kernels (slg_score_warp_kernel) spend their time on instruction issue:
-// every visit is a shared-memory read-modify-write and every (query, tile) ends with a scan of the
-// whole accumulator (profiles/r1_v3_warp_kernel_summary.txt: 68 warp instructions per 32 visits).
+// with df >= N/8).  The scatter kernel (slg_score_warp_kernel) is bound by the shared-memory pipe:
+// every visit is a read-modify-write and every (query, sub-tile) ends with a clear.
 //
-//   resident scores   seg.post_score[i] = unit-weight BM25 contribution of posting i, computed once at
-//                     segment load with score_tf's arithmetic (query/wand.rs:269-286).
+//   resident scores   seg.post_score / sw.post_pair: unit-weight BM25 contribution of every posting,
+//                     computed once at segment load with score_tf's arithmetic (query/wand.rs:269-286).
 //   dense columns     a term with df >= doc_count / dense_den also has a doc-indexed f32 column
 //                     (score or +0.0f).  Adding a column to a tile is a 128-bit load + 4 FADD per 4
 //                     docs; x + 0.0f == x, so docs without the term are unaffected bit for bit.
-//   tile ownership    one CTA owns a tile of TILE = 128*V docs at a time and sweeps ALL heavy queries
-//                     of the batch over it.  The tile's slices of the batch's most-used columns are
-//                     staged in shared memory once per tile and every query that names one of them
-//                     reads it from there (L2 -> SM traffic drops from 8 B per visit to one column
-//                     slice per tile per CTA).
+//   chunks            the swept queries are sorted by their first column term and cut into chunks of
+//                     kSweepChunk; one CTA takes one (chunk, range of tiles) unit at a time.  The
+//                     chunk's most-used columns are bulk-copied (cp.async.bulk + mbarrier) into
+//                     shared memory one block of kSweepBlockDocs docs ahead, double buffered.
 //   item records      before the sweep, slg_sweep_records_kernel resolves every query's sparse terms
 //                     against every tile (posting ranges from the range table, a compacted list of
 //                     the non-empty ones, a bitmap of where each term starts in their concatenation,
 //                     the tile's upper bound for the pruned modes) into an 80-byte record per
-//                     (tile, query).  All per-(query, tile) bookkeeping is scalar, coalesced,
-//                     embarrassingly parallel code there; the sweep streams the records.
-//   register tile     then one warp = one (query, tile): lane L holds docs {128*i + 4*L .. +3 : i < V}
-//                     in registers.  The column terms are added in registers (staged slice from shared
-//                     memory, conflict-free 128-bit reads) and compared against the query's k-th
-//                     score; only if the query also has sparse postings in the tile is the register
-//                     tile parked in a warp-private shared tile, the (doc, score) postings added to it
-//                     and the touched docs re-checked.  No accumulator scan, no clearing.
-//   software pipeline a warp walks a static, rotated sequence of query slots; the record of item i+2
-//                     and the first 64 postings of item i+1 are in flight while item i is computed.
-//   seed pass         the same kernel first runs tiles [0, seed_tiles) with the query slots split
-//                     across CTAs (no two warps share a query), which gives every query a useful
-//                     threshold before 148 CTAs start merging into the same top-k lists.
+//                     (query, tile).  All per-(query, tile) bookkeeping is scalar, embarrassingly
+//                     parallel code there; the sweep streams the records.
+//   register tile     one warp = one (query, tile) at a time: lane L holds docs {128*i + 4*L .. +3 :
+//                     i < V} in registers.  The column terms are added in registers (staged slice from
+//                     shared memory, conflict-free 128-bit reads) and compared against the query's
+//                     k-th score; only if the query also has sparse postings in the tile is the
+//                     register tile parked in a warp-private shared tile, the (doc, score) postings
+//                     added to it and the touched docs re-checked.  No accumulator scan, no clearing.
+//   cp.async rings    inside a block every warp walks its own interleaved share of the (query, tile)
+//                     items; the record of item g + 4 and the first 64 postings of item g + 2 are in
+//                     flight (warp-private cp.async rings) while item g is computed.
+//   seed pass         the same kernel first runs the first tiles alone, which gives every query a
+//                     useful threshold before many CTAs start merging into the same top-k lists.
 //
 // Queries for which a sweep over every tile would be wasted work (no column term and few postings)
 // are "light": they go to slg_score_warp_kernel in the same batch run.
 //
-// Summation order (the float contract of this kernel): the query's terms WITH a column in query
-// order, then the terms WITHOUT one in query order, one left fold.  That is brute_force
-// (query/wand.rs:527-548) applied to a permutation of the query's terms; tests check it bit for bit
-// against the oracle run on the permuted query and against the reference order under the 1e-5 rule.
+// Summation order (the float contract of this kernel, shared with slg_score_warp_kernel<COLS>): the
+// query's terms WITH a column in query order, then the terms WITHOUT one in query order, one left
+// fold.  That is brute_force (query/wand.rs:527-548) applied to a permutation of the query's terms;
+// tests check it bit for bit against the oracle run on the permuted query and against the reference
+// order under the 1e-5 rule.
 //
 // PRUNE (safe, exact result): a (query, tile) item is skipped iff
 //   sum over sparse terms with postings in the tile of w * term-wide bound (query/wand.rs:289-303)

@@ -1,5 +1,5 @@
 // slg_warp_kernel.cuh — K2/K3, warp-autonomous variant (the default for k <= 32 and <= 8 terms
-// per query).
+// per query; with COLS for plain OR queries, without for Bool queries and kernel choice 2).
 //
 // Same arithmetic, same key order and same per-query global top-k protocol as
 // slg_score_tiles_kernel, but the unit of cooperation is one WARP instead of one CTA, so no block
@@ -20,6 +20,13 @@
 // array, and the accumulate loop of each (query, tile) then only streams (doc, score) pairs and
 // adds them.  The per-query weight is applied at accumulate time (score_tf: base * weight,
 // query/wand.rs:284-285), so results are bit-identical to computing the contribution in place.
+//
+// The kernel is bound by the shared-memory pipe (profiles/r1_v7_warp_kernel_summary.txt); three things
+// keep that traffic down: one shared-memory instruction touches 32 consecutive postings (fewer bank
+// conflicts on dense lists), every lane tracks the largest value it wrote so that a sub-tile whose best
+// score is below the query's threshold is cleared without being read back, and — template flag COLS,
+// the automatic choice for plain OR queries — terms with a dense column are summed from it with
+// 128-bit loads instead of being scattered, which also removes the clearing between sub-tiles.
 #pragma once
 #include "slg_kernels.cuh"
 
