@@ -166,6 +166,7 @@ int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, u
  *                           bounds sum to less than n % of the running k-th score are not scattered; docs touched
  *                           by the other terms are rescored exactly if they can still qualify (default 35;
  *                           0 = tile skipping only).  The result is bit-identical to the exhaustive run.
+ *   "keep_positions"   1/0  keep term positions resident when a posting image carries them (default 1)
  *   "heavy_kernel"     0|1  column front end (kernel_choice 3): 0 = warp kernel that sums a query's column
  *                           terms from their dense columns (default), 1 = tile-sweep kernel
  *   "reg_tile_v"       4|8     tile-sweep kernel: 128 * v docs per register tile (default 8)
@@ -189,6 +190,71 @@ int32_t slg_load_segment(slg_index_t *, const slg_segment_view_t *view, float k1
 int32_t slg_load_segment_post_image(slg_index_t *, const slg_segment_view_t *view_without_postings,
                                     const uint8_t *post_image, uint64_t post_image_bytes,
                                     const uint64_t *term_post_offsets, float k1, float b);
+/* ---- residency from the reference's own segment files ----
+ * One segment as the reference's writer left it on disk; the caller reads or mmaps the files and passes
+ * their bytes (SegmentReader::open, index/segment.rs:1239-1330, reads the same four):
+ *   terms  seg_<id>.terms  index/terms.rs:10-25        post  seg_<id>.post  index/postings.rs:78-129
+ *   fast   seg_<id>.fast   index/fastfields.rs:409-424 meta  seg_<id>.meta  index/segment.rs:43-53 (JSON)
+ * doc_count / deleted_docs / checksums come from the segment's MANIFEST.json entry (SegmentMeta,
+ * index/manifest.rs:24-37).  checksums (nullable) = crc32 of the whole {terms, postings, fast, meta} files,
+ * verified like verify_checksums (index/segment.rs:1140-1200). */
+typedef struct {
+  uint32_t segment_ord;
+  uint32_t doc_count;
+  const uint8_t *terms;
+  uint64_t terms_bytes;
+  const uint8_t *post;
+  uint64_t post_bytes;
+  const uint8_t *fast;
+  uint64_t fast_bytes;
+  const uint8_t *meta;
+  uint64_t meta_bytes;
+  const uint32_t *deleted_docs;
+  uint32_t n_deleted;
+  const uint32_t *checksums;
+} slg_segment_files_t;
+
+typedef struct {
+  uint64_t n_terms_total;     /* keys in .terms, all fields */
+  uint64_t n_terms_field;     /* keys "<field>:..." */
+  uint64_t n_postings;        /* sum of their df */
+  float avgdl;                /* .meta avg_field_lengths[field] (0 when absent, index/segment.rs:1344-1351) */
+  uint32_t has_positions;     /* some list of the field carries positions */
+  uint32_t has_length_column; /* `_len:<field>` is present in .fast */
+  uint32_t n_fast_columns, n_scalar_columns;
+  uint32_t crc_terms, crc_postings, crc_fast, crc_meta; /* crc32 of the images as given */
+} slg_segment_info_t;
+
+/* Host-only: parse + validate the files (checksums, crc of .terms, structure of .fast, .meta JSON) without
+ * touching a device.  err (nullable) receives the message on failure. */
+int32_t slg_inspect_segment_files(const slg_segment_files_t *files, const char *field, slg_segment_info_t *out, char *err,
+                                  uint64_t err_cap);
+/* Load one segment for scoring text field `field` (one text field per handle).  Term ids of such a handle
+ * are handed out per "field:token" key in order of first appearance across the loaded segments —
+ * slg_term_lookup resolves a key; a segment that lacks a key treats it as an empty list
+ * (seg.postings(key) == None, api/reader.rs:2986-2988).  avgdl is the .meta value, N/df/min_doc_len are
+ * per segment as in the reference; postings are decoded on the device; scalar I64/F64/Str fast fields
+ * become filter columns addressed by name (slg_column_lookup); list and nested columns are skipped.
+ * Positions stay resident for slg_phrase_compile unless option "keep_positions" is 0. */
+int32_t slg_load_segment_files(slg_index_t *, const slg_segment_files_t *files, const char *field, float k1, float b);
+/* The same for every segment of an index directory, in MANIFEST.json order (segment_ord = position).
+ * vector_field (nullable): also load seg_<id>_vectors/<vector_field>.bin of every segment. */
+int32_t slg_load_index_dir(slg_index_t *, const char *dir, const char *field, float k1, float b, const char *vector_field,
+                           int32_t store_bf16, uint32_t *n_segments_out);
+/* <field>.bin image ("VCTR", index/segment.rs:1030-1119) -> slg_load_vectors.  metric_out nullable: 0 cosine, 1 l2 */
+int32_t slg_load_vector_file(slg_index_t *, uint32_t segment_ord, const uint8_t *bytes, uint64_t n_bytes, int32_t store_bf16,
+                             int32_t *metric_out);
+/* *term_id = id of "field:token" in the handle's term space, UINT32_MAX if no loaded segment holds it */
+int32_t slg_term_lookup(const slg_index_t *, const char *key, uint32_t *term_id);
+/* column handle of a fast field loaded from files, -1 if unknown */
+int32_t slg_column_lookup(const slg_index_t *, const char *name);
+
+/* Term positions of a segment loaded through slg_load_segment (PostingEntry.positions, index/postings.rs:14-19):
+ * term_offsets is the view's CSR, position_offsets has one entry per posting + 1, positions are absolute and
+ * ascending per posting.  HOST arrays. */
+int32_t slg_load_positions(slg_index_t *, uint32_t segment_ord, const uint64_t *term_offsets, const uint64_t *position_offsets,
+                           const uint32_t *positions);
+
 /* fast-field columns of the last loaded segment (index/fastfields.rs:910-1039); return handle >= 0 */
 int32_t slg_add_i64_column(slg_index_t *, uint32_t segment_ord, const int64_t *values, const uint8_t *present);
 int32_t slg_add_f64_column(slg_index_t *, uint32_t segment_ord, const double *values, const uint8_t *present);
@@ -204,6 +270,20 @@ int32_t slg_filter_compile(slg_index_t *, const slg_filter_node_t *nodes, uint32
                            const char *const *strings);
 /* copy the filter's bitmap for one segment to the host: ceil(doc_count/32) words, LSB first */
 int32_t slg_filter_bitmap(slg_index_t *, int32_t filter_id, uint32_t segment_ord, uint32_t *bitmap_out);
+
+/* ---- phrases (query/phrase.rs:4-48, api/reader.rs:1584-1597) ----
+ * A phrase is compiled, like a root filter, into one doc bitmap per loaded segment and the returned id is used
+ * wherever a filter id is (slg_query_t.filter_id, slg_filter_bitmap): a doc is in the bitmap iff it holds every
+ * term, each with at least one position, and positions p_0 < p_1 < ... (phrase order) exist whose gaps
+ * sum to <= slop.  A term the segment lacks gives an empty bitmap.  Needs resident positions.
+ * The matcher requires every phrase of a query (api/reader.rs:1504-1508): AND them, and the root filter,
+ * with slg_filter_combine. */
+int32_t slg_phrase_compile(slg_index_t *, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop);
+enum { SLG_COMBINE_AND = 0, SLG_COMBINE_OR = 1, SLG_COMBINE_AND_NOT = 2 };
+/* new filter id = a op b, per segment */
+int32_t slg_filter_combine(slg_index_t *, uint32_t op, int32_t a, int32_t b);
+/* release the bitmaps of a filter / phrase id (ids are not reused; a batch naming a freed id is rejected) */
+int32_t slg_filter_free(slg_index_t *, int32_t filter_id);
 
 /* ---- batched search (search_segment + execute_top_k for Q queries, all loaded segments) ---- */
 /* k is the INTERNAL k (the reference passes limit+1, api/reader.rs:2595-2619).  out_hits has

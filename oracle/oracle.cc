@@ -1127,6 +1127,60 @@ int slo_filter_bitmap(const slo_index_t *ix, const slo_filter_node_t *filter, ui
   return 0;
 }
 
+// ---- phrases ----
+// query/phrase.rs:22-39: the recursive search, kept depth first and in the reference's iteration order.
+static bool phrase_search(const uint32_t *const *positions, const uint32_t *counts, uint32_t n, uint32_t idx, uint32_t prev,
+                          int32_t remaining) {
+  if (idx >= n) return true;
+  for (uint32_t i = 0; i < counts[idx]; i++) {
+    const uint32_t pos = positions[idx][i];
+    if (pos <= prev) continue;
+    const uint32_t prev1 = prev == 0xFFFFFFFFu ? prev : prev + 1;           // prev.saturating_add(1)
+    const int32_t gap = (int32_t)(pos > prev1 ? pos - prev1 : 0u);           // pos.saturating_sub(..) as i32
+    if (gap > remaining) break;  // positions are sorted; no later entry will shrink the gap
+    if (phrase_search(positions, counts, n, idx + 1, pos, remaining - gap)) return true;
+  }
+  return false;
+}
+// query/phrase.rs:4-48 from the point where the doc's position lists are collected (:15-47)
+int slo_matches_phrase_positions(uint32_t n_terms, const uint32_t *const *positions, const uint32_t *counts, uint32_t slop) {
+  if (n_terms == 0) return 1;                       // :5-7
+  for (uint32_t j = 0; j < n_terms; j++)
+    if (counts[j] == 0) return 0;                   // :16-18
+  if (n_terms == 1) return 1;                       // :19-21
+  for (uint32_t i = 0; i < counts[0]; i++)          // :41-46
+    if (phrase_search(positions, counts, n_terms, 1, positions[0][i], (int32_t)slop)) return 1;
+  return 0;
+}
+// matches_phrase for every doc of a segment held as CSR postings + positions (one variant, one term per
+// phrase position, api/reader.rs:1584-1597 + 1681-1712); a phrase term the segment lacks => no doc matches
+int slo_phrase_bitmap(uint32_t doc_count, uint64_t n_terms, const uint64_t *term_offsets, const uint32_t *docs,
+                      const uint64_t *pos_offsets, const uint32_t *positions, const uint32_t *phrase_terms, uint32_t n_phrase,
+                      uint32_t slop, uint32_t *bitmap_out) {
+  const uint32_t words = (doc_count + 31) / 32;
+  std::memset(bitmap_out, 0, (size_t)words * 4);
+  for (uint32_t j = 0; j < n_phrase; j++)
+    if (phrase_terms[j] >= n_terms || term_offsets[phrase_terms[j] + 1] == term_offsets[phrase_terms[j]]) return 0;
+  std::vector<const uint32_t *> lists(n_phrase);
+  std::vector<uint32_t> counts(n_phrase);
+  for (uint32_t d = 0; d < doc_count; d++) {
+    bool all = true;
+    for (uint32_t j = 0; j < n_phrase && all; j++) {
+      const uint64_t lo = term_offsets[phrase_terms[j]], hi = term_offsets[phrase_terms[j] + 1];
+      const uint32_t *it = std::lower_bound(docs + lo, docs + hi, d);  // term_posts.iter().find(|p| p.doc_id == doc_id), :10
+      if (it == docs + hi || *it != d) {
+        all = false;
+        break;
+      }
+      const uint64_t pi = (uint64_t)(it - docs);
+      lists[j] = positions + pos_offsets[pi];
+      counts[j] = (uint32_t)(pos_offsets[pi + 1] - pos_offsets[pi]);
+    }
+    if (all && slo_matches_phrase_positions(n_phrase, lists.data(), counts.data(), slop)) bitmap_out[d >> 5] |= 1u << (d & 31);
+  }
+  return 0;
+}
+
 // vectors/mod.rs:74-81
 void slo_normalize_in_place(float *v, size_t dim) {
   float s = 0.0f;

@@ -166,6 +166,14 @@ uint32_t slo_merge_hits(const slo_hit_t *hits, uint32_t n, uint32_t limit, slo_h
 int slo_filter_bitmap(const slo_index_t *, const slo_filter_node_t *filter, uint32_t n_filter_nodes,
                       const char *const *strings, uint32_t *bitmap_out /* ceil(doc_count/32) words */);
 
+/* ---- phrases (query/phrase.rs:4-48) ---- */
+/* matches_phrase on the position lists of one doc (lists in phrase order, ascending) */
+int slo_matches_phrase_positions(uint32_t n_terms, const uint32_t *const *positions, const uint32_t *counts, uint32_t slop);
+/* matches_phrase for every doc of a CSR segment with positions (pos_offsets: one entry per posting + 1) -> bitmap */
+int slo_phrase_bitmap(uint32_t doc_count, uint64_t n_terms, const uint64_t *term_offsets, const uint32_t *docs,
+                      const uint64_t *pos_offsets, const uint32_t *positions, const uint32_t *phrase_terms, uint32_t n_phrase,
+                      uint32_t slop, uint32_t *bitmap_out);
+
 /* ---- vectors (vectors/mod.rs:74-129, api/reader.rs:218-254) ---- */
 enum { SLO_METRIC_COSINE = 0, SLO_METRIC_L2 = 1 };
 void slo_normalize_in_place(float *v, size_t dim);

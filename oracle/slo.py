@@ -86,6 +86,9 @@ def lib() -> C.CDLL:
     L.slo_merge_hits.argtypes = [vp, u32, u32, vp]
     L.slo_merge_hits.restype = u32
     L.slo_filter_bitmap.argtypes = [vp, vp, u32, C.POINTER(C.c_char_p), vp]
+    L.slo_matches_phrase_positions.argtypes = [u32, vp, vp, u32]
+    L.slo_matches_phrase_positions.restype = C.c_int
+    L.slo_phrase_bitmap.argtypes = [u32, u64, vp, vp, vp, vp, vp, u32, u32, vp]
     L.slo_normalize_in_place.argtypes = [vp, sz]
     L.slo_normalize_in_place.restype = None
     L.slo_metric_similarity.argtypes = [C.c_int, vp, vp, sz]
@@ -204,3 +207,24 @@ def merge_hits(hit_lists, limit: int):
 
 def max_threads() -> int:
     return lib().slo_max_threads()
+
+
+def matches_phrase_positions(position_lists, slop: int) -> bool:
+    """query/phrase.rs:4-48 on one doc's position lists (phrase order)."""
+    arrs = [np.ascontiguousarray(p, dtype=np.uint32) for p in position_lists]
+    ptrs = (C.c_void_p * max(len(arrs), 1))(*[a.ctypes.data for a in arrs])
+    counts = np.array([len(a) for a in arrs], dtype=np.uint32)
+    return bool(lib().slo_matches_phrase_positions(len(arrs), ptrs, _p(counts), slop))
+
+
+def phrase_bitmap(doc_count: int, term_offsets, docs, pos_offsets, positions, phrase_terms, slop: int) -> np.ndarray:
+    """Bitmap (uint32 words, LSB first) of the docs matches_phrase accepts."""
+    term_offsets = np.ascontiguousarray(term_offsets, dtype=np.uint64)
+    docs = np.ascontiguousarray(docs, dtype=np.uint32)
+    pos_offsets = np.ascontiguousarray(pos_offsets, dtype=np.uint64)
+    positions = np.ascontiguousarray(positions, dtype=np.uint32)
+    pt = np.ascontiguousarray(phrase_terms, dtype=np.uint32)
+    out = np.zeros((doc_count + 31) // 32, dtype=np.uint32)
+    lib().slo_phrase_bitmap(doc_count, len(term_offsets) - 1, _p(term_offsets), _p(docs), _p(pos_offsets), _p(positions), _p(pt),
+                            len(pt), slop, _p(out))
+    return out

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsearchlite_gpu.so")
 SOURCES = ["slg_engine.cu"]
-HEADERS = ["slg_kernels.cuh", "slg_warp_kernel.cuh", "slg_sweep_kernel.cuh", "slg_filter.cuh", "slg_postimage.cuh", "slg_rerank.cuh",
+HEADERS = ["slg_kernels.cuh", "slg_phrase.cuh", "slg_segfiles.h", "slg_warp_kernel.cuh", "slg_sweep_kernel.cuh", "slg_filter.cuh", "slg_postimage.cuh", "slg_rerank.cuh",
            os.path.join("..", "..", "include", "searchlite_gpu.h")]
 
 NVCC_FLAGS = [

@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cub/cub.cuh>
 #include <limits>
 #include <memory>
 #include <string>
@@ -22,7 +23,9 @@
 
 #include "slg_filter.cuh"
 #include "slg_kernels.cuh"
+#include "slg_phrase.cuh"
 #include "slg_postimage.cuh"
+#include "slg_segfiles.h"
 #include "slg_rerank.cuh"
 #include "slg_sweep_kernel.cuh"
 #include "slg_warp_kernel.cuh"
@@ -84,8 +87,12 @@ struct DevBuf {
   T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+struct CastU64 {
+  __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; }
+};
+
 struct Column {
-  int kind = 0;  // 0 i64, 1 f64, 2 str
+  int kind = -1;  // 0 i64, 1 f64, 2 str; -1 = the segment lacks this column (predicates on it are false)
   DevBuf values; // i64 / f64 / u32 ords
   DevBuf present;
   std::vector<std::string> dict;
@@ -115,10 +122,17 @@ struct Segment {
   std::vector<DevBuf> filter_bits;  // per filter id
   DevBuf filter_ptrs;               // device array of pointers into filter_bits
   Vectors vec;
+  // term positions (index/postings.rs:117-125), kept for phrase matching: positions of padded posting slot i are
+  // pos[pos_begin[i] .. pos_begin[i+1])
+  DevBuf pos_begin, pos;
+  uint64_t n_positions = 0;
+  bool has_positions = false;
+  bool avgdl_given = false;  // avgdl comes from the segment's .meta file instead of total_tokens / doc_count
   size_t resident() const {
     return post_doc.bytes + post_tf.bytes + term_start.bytes + term_df.bytes + term_idf.bytes + term_max_tf.bytes +
            term_wide.bytes + tf_wide.bytes + term_blk.bytes + blk_max_doc.bytes + blk_max_tf.bytes + nk.bytes +
-           live_bits.bytes + post_score.bytes + post_pair.bytes + cols.bytes + term_col.bytes + col_tmax.bytes;
+           live_bits.bytes + post_score.bytes + post_pair.bytes + cols.bytes + term_col.bytes + col_tmax.bytes +
+           pos_begin.bytes + pos.bytes;
   }
 };
 
@@ -158,6 +172,12 @@ struct slg_index {
   uint32_t part_tiles = 0;       // sweep: tiles per unit of work (0 = automatic)
   uint32_t maxscore_pct = 35;    // pruned warp kernel: non-essential bounds may sum to this % of the k-th score (0 = tile skip only)
   uint32_t heavy_kernel = 0;     // column front end: 0 = warp kernel summing column terms from their columns, 1 = tile-sweep kernel
+  bool keep_positions = true;    // keep term positions resident when a posting image carries them (SegmentReader keep_positions)
+  // term space of segments loaded from the reference's files: "field:token" key -> term id, in order of first appearance
+  std::unordered_map<std::string, uint32_t> term_ids;
+  std::string term_field;        // the text field those keys belong to
+  // fast-field columns by name (handles are indices into every segment's `columns`)
+  std::vector<std::string> column_names;
   Segment *find(uint32_t ord) {
     for (auto &s : segs)
       if (s->ord == ord) return s.get();
@@ -257,7 +277,7 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
   cudaStream_t st = ix->stream;
   Segment *s = seg.get();
   // compute_avg_lengths index/segment.rs:946-957
-  s->avgdl = s->doc_count == 0 ? 0.0f : (float)total_tokens / (float)(uint64_t)s->doc_count;
+  if (!s->avgdl_given) s->avgdl = s->doc_count == 0 ? 0.0f : (float)total_tokens / (float)(uint64_t)s->doc_count;
   // deleted docs -> live bitmap; live_docs index/segment.rs:1365-1370
   uint32_t words = (s->doc_count + 31) / 32;
   std::vector<uint32_t> live(words, 0xFFFFFFFFu);
@@ -697,6 +717,7 @@ int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
     if (value > 1) return fail(ix, SLG_ERR_INVALID, "heavy_kernel must be 0 (warp kernel + columns) or 1 (tile sweep)");
     ix->heavy_kernel = (uint32_t)value;
   }
+  else if (n == "keep_positions") ix->keep_positions = value != 0;
   else return fail(ix, SLG_ERR_INVALID, "unknown option '%s'", name);
   return SLG_OK;
 }
@@ -758,11 +779,33 @@ int32_t slg_load_segment(slg_index_t *ix, const slg_segment_view_t *v, float k1,
   return SLG_OK;
 }
 
-int32_t slg_load_segment_post_image(slg_index_t *ix, const slg_segment_view_t *v, const uint8_t *post_image,
-                                    uint64_t post_image_bytes, const uint64_t *term_post_offsets, float k1, float b) {
-  if (!ix || !v || !post_image || !term_post_offsets) return SLG_ERR_INVALID;
-  if (v->doc_count && !v->field_lengths) return fail(ix, SLG_ERR_INVALID, "segment view lacks field lengths");
-  if (v->memory_space != SLG_MEM_HOST) return fail(ix, SLG_ERR_INVALID, "post image loads take host memory");
+namespace {
+
+// exclusive prefix sum of per-slot position counts -> pos_begin[n_post_padded + 1]; allocates pos
+int32_t scan_positions(slg_index *ix, Segment *s, DevBuf &npos) {
+  cudaStream_t st = ix->stream;
+  const uint64_t n = s->n_post_padded + 1;  // npos holds n entries, the last one zero
+  if (n > 0x7FFFFFFFull) return fail(ix, SLG_ERR_UNSUPPORTED, "segment has too many posting slots for the position index");
+  SLG_CUDA(ix, s->pos_begin.alloc(n * 8));
+  size_t tmp_bytes = 0;
+  auto in = cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *>(npos.as<uint32_t>(), CastU64());
+  SLG_CUDA(ix, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, s->pos_begin.as<uint64_t>(), (int)n, st));
+  DevBuf tmp;
+  SLG_CUDA(ix, tmp.alloc(tmp_bytes));
+  SLG_CUDA(ix, cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, s->pos_begin.as<uint64_t>(), (int)n, st));
+  count_launch(ix, 2);
+  uint64_t total = 0;
+  SLG_CUDA(ix, cudaMemcpyAsync(&total, s->pos_begin.as<uint64_t>() + (n - 1), 8, cudaMemcpyDeviceToHost, st));
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  s->n_positions = total;
+  SLG_CUDA(ix, s->pos.alloc(std::max<uint64_t>(total, 1) * 4));
+  return SLG_OK;
+}
+
+// Residency from a `.post` image.  begin[t] = offset of term t's list (UINT64_MAX: the segment lacks the
+// term), end[t] = an offset the list does not reach past.  avgdl: the .meta value or nullptr (derive it).
+int32_t load_post_image(slg_index *ix, const slg_segment_view_t *v, const uint8_t *post_image, uint64_t post_image_bytes,
+                        const uint64_t *begin, const uint64_t *end, const float *avgdl, float k1, float b) {
   SLG_CUDA(ix, cudaSetDevice(ix->device));
   cudaStream_t st = ix->stream;
   auto seg = std::make_unique<Segment>();
@@ -772,11 +815,21 @@ int32_t slg_load_segment_post_image(slg_index_t *ix, const slg_segment_view_t *v
   s->n_terms = v->n_terms;
   s->k1 = k1;
   s->b = b;
+  if (avgdl) {
+    s->avgdl = *avgdl;
+    s->avgdl_given = true;
+  }
   // parse the fixed part of every list header on the host (index/postings.rs:142-168)
   std::vector<PostTermHeader> hdr(v->n_terms);
   s->h_df.resize(v->n_terms);
+  bool any_positions = false;
   for (uint64_t t = 0; t < v->n_terms; t++) {
-    uint64_t o = term_post_offsets[t];
+    const uint64_t o = begin[t];
+    if (o == ~0ull) {  // seg.postings(key) == None
+      hdr[t] = PostTermHeader{0, 0, 0, 0};
+      s->h_df[t] = 0;
+      continue;
+    }
     if (o + 17 > post_image_bytes) return fail(ix, SLG_ERR_INVALID, "posting header of term %llu is out of bounds", (unsigned long long)t);
     const uint8_t *p = post_image + o;
     uint32_t df, raw_block;
@@ -785,20 +838,28 @@ int32_t slg_load_segment_post_image(slg_index_t *ix, const slg_segment_view_t *v
     uint32_t bc = raw_block & 0x7FFFFFFFu;
     bool has_meta = (raw_block >> 31) != 0;
     uint64_t payload = o + 17 + ((has_meta && bc > 0) ? 4 + 8ull * bc : 0);
-    if (payload > post_image_bytes) return fail(ix, SLG_ERR_INVALID, "block table of term %llu is out of bounds", (unsigned long long)t);
+    if (payload > post_image_bytes || end[t] > post_image_bytes || end[t] < payload)
+      return fail(ix, SLG_ERR_INVALID, "block table of term %llu is out of bounds", (unsigned long long)t);
     hdr[t].payload = payload;
-    hdr[t].end = term_post_offsets[t + 1];
+    hdr[t].end = end[t];
     hdr[t].df = df;
     hdr[t].has_positions = p[4] == 1;
+    any_positions |= hdr[t].has_positions && df > 0;
     s->h_df[t] = df;
   }
   int32_t rc = build_layout(ix, s);
   if (rc) return rc;
-  DevBuf d_img, d_hdr, t_lens, t_pres;
+  const bool keep_pos = any_positions && ix->keep_positions;
+  DevBuf d_img, d_hdr, t_lens, t_pres, d_npos, d_posbyte;
   SLG_CUDA(ix, d_img.alloc(post_image_bytes + 16));
   SLG_CUDA(ix, cudaMemcpyAsync(d_img.p, post_image, post_image_bytes, cudaMemcpyHostToDevice, st));
   SLG_CUDA(ix, d_hdr.alloc(std::max<uint64_t>(v->n_terms, 1) * sizeof(PostTermHeader)));
   if (v->n_terms) SLG_CUDA(ix, cudaMemcpyAsync(d_hdr.p, hdr.data(), v->n_terms * sizeof(PostTermHeader), cudaMemcpyHostToDevice, st));
+  if (keep_pos) {
+    SLG_CUDA(ix, d_npos.alloc((s->n_post_padded + 1) * 4));
+    SLG_CUDA(ix, d_posbyte.alloc((s->n_post_padded + 1) * 4));
+    SLG_CUDA(ix, cudaMemsetAsync(d_npos.p, 0, (s->n_post_padded + 1) * 4, st));
+  }
   DevBuf d_err;
   SLG_CUDA(ix, d_err.alloc(4));
   SLG_CUDA(ix, cudaMemsetAsync(d_err.p, 0, 4, st));
@@ -806,7 +867,8 @@ int32_t slg_load_segment_post_image(slg_index_t *ix, const slg_segment_view_t *v
     slg_decode_post_image_kernel<<<(unsigned)((v->n_terms + 3) / 4), 128, 0, st>>>(
         d_img.as<uint8_t>(), post_image_bytes, d_hdr.as<PostTermHeader>(), v->n_terms, s->term_start.as<uint64_t>(),
         s->term_blk.as<uint32_t>(), s->post_doc.as<uint32_t>(), s->post_tf.as<uint8_t>(), s->blk_max_doc.as<uint32_t>(),
-        s->blk_max_tf.as<float>(), d_err.as<uint32_t>());
+        s->blk_max_tf.as<float>(), keep_pos ? d_npos.as<uint32_t>() : nullptr, keep_pos ? d_posbyte.as<uint32_t>() : nullptr,
+        d_err.as<uint32_t>());
     count_launch(ix);
     SLG_CUDA(ix, cudaGetLastError());
   }
@@ -815,6 +877,22 @@ int32_t slg_load_segment_post_image(slg_index_t *ix, const slg_segment_view_t *v
   SLG_CUDA(ix, cudaStreamSynchronize(st));
   if (derr == 1) return fail(ix, SLG_ERR_INVALID, "malformed varint in the posting image");
   if (derr == 2) return fail(ix, SLG_ERR_UNSUPPORTED, "term frequency >= 255 in a posting image (use the CSR load path)");
+  if (derr == 3) return fail(ix, SLG_ERR_UNSUPPORTED, "a posting list with positions is longer than 4 GiB");
+  if (keep_pos) {
+    if ((rc = scan_positions(ix, s, d_npos))) return rc;
+    if (s->n_blocks) {
+      slg_decode_positions_kernel<<<s->n_blocks, 128, 0, st>>>(d_img.as<uint8_t>(), d_hdr.as<PostTermHeader>(), s->n_terms,
+                                                               s->term_start.as<uint64_t>(), s->term_blk.as<uint32_t>(),
+                                                               s->term_df.as<uint32_t>(), s->n_blocks, d_posbyte.as<uint32_t>(),
+                                                               s->pos_begin.as<uint64_t>(), s->pos.as<uint32_t>(), d_err.as<uint32_t>());
+      count_launch(ix);
+      SLG_CUDA(ix, cudaGetLastError());
+      SLG_CUDA(ix, cudaMemcpyAsync(&derr, d_err.p, 4, cudaMemcpyDeviceToHost, st));
+      SLG_CUDA(ix, cudaStreamSynchronize(st));
+      if (derr) return fail(ix, SLG_ERR_INVALID, "malformed position varint in the posting image");
+    }
+    s->has_positions = true;
+  }
   if ((rc = build_wide(ix, s, nullptr, nullptr))) return rc;
   const int64_t *d_lens;
   const uint8_t *d_pres;
@@ -823,6 +901,342 @@ int32_t slg_load_segment_post_image(slg_index_t *ix, const slg_segment_view_t *v
   rc = finish_segment(ix, std::move(seg), d_lens, d_pres, v->total_tokens, v->deleted_docs, v->n_deleted);
   if (rc) return rc;
   SLG_CUDA(ix, cudaStreamSynchronize(st));
+  return SLG_OK;
+}
+
+}  // namespace
+
+int32_t slg_load_segment_post_image(slg_index_t *ix, const slg_segment_view_t *v, const uint8_t *post_image,
+                                    uint64_t post_image_bytes, const uint64_t *term_post_offsets, float k1, float b) {
+  if (!ix || !v || !post_image || !term_post_offsets) return SLG_ERR_INVALID;
+  if (v->doc_count && !v->field_lengths) return fail(ix, SLG_ERR_INVALID, "segment view lacks field lengths");
+  if (v->memory_space != SLG_MEM_HOST) return fail(ix, SLG_ERR_INVALID, "post image loads take host memory");
+  return load_post_image(ix, v, post_image, post_image_bytes, term_post_offsets, term_post_offsets + 1, nullptr, k1, b);
+}
+
+/* ---- residency from the reference's segment files (SegmentReader::open, index/segment.rs:1239-1330) ---- */
+namespace {
+
+struct ParsedSegmentFiles {
+  std::vector<slgf::TermEntry> terms;      // every key of .terms
+  std::vector<slgf::FastColumn> fast;      // every column of .fast
+  const slgf::FastColumn *len_col = nullptr;  // `_len:<field>`
+  float avgdl = 0.0f;
+  uint64_t n_field_terms = 0;
+  uint64_t df_sum = 0;
+  bool any_positions = false;
+};
+
+// verify_checksums + read_terms + FastFieldsReader::open + the .meta fields the search path reads
+bool parse_segment_files(const slg_segment_files_t *f, const char *field, ParsedSegmentFiles &out, std::string &err) {
+  if (!f->terms || !f->post || !f->fast || !f->meta) {
+    err = "segment files: terms, post, fast and meta images are all required";
+    return false;
+  }
+  if (f->checksums) {  // SegmentMeta.checksums, index/segment.rs:1140-1200
+    const char *label[4] = {"terms", "postings", "fast", "meta"};
+    const uint8_t *img[4] = {f->terms, f->post, f->fast, f->meta};
+    const uint64_t len[4] = {f->terms_bytes, f->post_bytes, f->fast_bytes, f->meta_bytes};
+    for (int i = 0; i < 4; i++) {
+      const uint32_t actual = slgf::crc32(img[i], len[i]);
+      if (actual != f->checksums[i]) {
+        err = std::string("segment failed checksum for ") + label[i] + " (expected " + std::to_string(f->checksums[i]) +
+              ", found " + std::to_string(actual) + ")";
+        return false;
+      }
+    }
+  }
+  if (!slgf::parse_terms(f->terms, f->terms_bytes, out.terms, err)) return false;
+  if (!slgf::parse_fast(f->fast, f->fast_bytes, out.fast, err)) return false;
+  const std::string len_key = std::string("_len:") + field;  // doc_length_key, index/fastfields.rs:1162-1164
+  for (auto &c : out.fast) {
+    if (c.type <= 2 && c.doc_len != f->doc_count) {
+      err = "fast-field column '" + c.name + "' has " + std::to_string(c.doc_len) + " rows, the segment " + std::to_string(f->doc_count) + " docs";
+      return false;
+    }
+    if (c.name == len_key && c.type == 0) out.len_col = &c;
+  }
+  slgf::Json root = slgf::json_root(f->meta, f->meta_bytes);
+  if (root.kind() != '{') {
+    err = "segment meta is not a JSON object";
+    return false;
+  }
+  // SegmentReader::avg_field_length, index/segment.rs:1344-1351: missing field => 0.0; serde_json reads an f32 as f64 -> f32
+  out.avgdl = (float)slgf::json_number(slgf::json_get(slgf::json_get(root, "avg_field_lengths"), field), 0.0);
+  const std::string prefix = std::string(field) + ":";
+  for (auto &t : out.terms) {
+    if (t.offset + 17 > f->post_bytes) {
+      err = "a term's posting offset lies outside the posting file";
+      return false;
+    }
+    if (t.key_len >= prefix.size() && std::memcmp(t.key, prefix.data(), prefix.size()) == 0) {
+      out.n_field_terms++;
+      uint32_t df;
+      std::memcpy(&df, f->post + t.offset, 4);
+      out.df_sum += df;
+      out.any_positions |= f->post[t.offset + 4] == 1;
+    }
+  }
+  return true;
+}
+
+}  // namespace
+
+int32_t slg_inspect_segment_files(const slg_segment_files_t *files, const char *field, slg_segment_info_t *out, char *err,
+                                  uint64_t err_cap) {
+  if (!files || !field || !out) return SLG_ERR_INVALID;
+  ParsedSegmentFiles ps;
+  std::string e;
+  if (!parse_segment_files(files, field, ps, e)) {
+    if (err && err_cap) snprintf(err, (size_t)err_cap, "%s", e.c_str());
+    return SLG_ERR_INVALID;
+  }
+  std::memset(out, 0, sizeof(*out));
+  out->n_terms_total = ps.terms.size();
+  out->n_terms_field = ps.n_field_terms;
+  out->n_postings = ps.df_sum;
+  out->avgdl = ps.avgdl;
+  out->has_positions = ps.any_positions;
+  out->has_length_column = ps.len_col != nullptr;
+  out->n_fast_columns = (uint32_t)ps.fast.size();
+  for (auto &c : ps.fast) out->n_scalar_columns += c.type <= 2;
+  out->crc_terms = slgf::crc32(files->terms, files->terms_bytes);
+  out->crc_postings = slgf::crc32(files->post, files->post_bytes);
+  out->crc_fast = slgf::crc32(files->fast, files->fast_bytes);
+  out->crc_meta = slgf::crc32(files->meta, files->meta_bytes);
+  return SLG_OK;
+}
+
+int32_t slg_load_segment_files(slg_index_t *ix, const slg_segment_files_t *f, const char *field, float k1, float b) {
+  if (!ix || !f || !field) return SLG_ERR_INVALID;
+  if (!ix->term_field.empty() && ix->term_field != field)
+    return fail(ix, SLG_ERR_UNSUPPORTED, "this handle scores field '%s'; one text field per handle", ix->term_field.c_str());
+  ParsedSegmentFiles ps;
+  std::string e;
+  if (!parse_segment_files(f, field, ps, e)) return fail(ix, SLG_ERR_INVALID, "%s", e.c_str());
+  // every list's end: the next list's offset in file order (lists of all fields share the file)
+  std::vector<uint64_t> all_off;
+  all_off.reserve(ps.terms.size() + 1);
+  for (auto &t : ps.terms) all_off.push_back(t.offset);
+  all_off.push_back(f->post_bytes);
+  std::sort(all_off.begin(), all_off.end());
+  // the handle's term space grows by the keys this segment adds
+  const std::string prefix = std::string(field) + ":";
+  std::vector<std::pair<uint32_t, uint64_t>> mine;  // (term id, offset)
+  mine.reserve((size_t)ps.n_field_terms);
+  for (auto &t : ps.terms) {
+    if (t.key_len < prefix.size() || std::memcmp(t.key, prefix.data(), prefix.size()) != 0) continue;
+    auto it = ix->term_ids.emplace(std::string(t.key, t.key_len), (uint32_t)ix->term_ids.size()).first;
+    mine.emplace_back(it->second, t.offset);
+  }
+  ix->term_field = field;
+  const uint64_t n_terms = ix->term_ids.size();
+  std::vector<uint64_t> begin(n_terms, ~0ull), end(n_terms, 0);
+  for (auto &m : mine) {
+    begin[m.first] = m.second;
+    end[m.first] = *std::upper_bound(all_off.begin(), all_off.end(), m.second);
+  }
+  // `_len:<field>` (field_lengths_for, api/reader.rs:3604-3621: absent column or value => 0)
+  std::vector<int64_t> lens(f->doc_count, 0);
+  std::vector<uint8_t> pres(f->doc_count, 0);
+  uint64_t total = 0;
+  if (ps.len_col) {
+    std::memcpy(lens.data(), ps.len_col->values, (size_t)f->doc_count * 8);
+    std::memcpy(pres.data(), ps.len_col->presence, f->doc_count);
+    for (uint32_t d = 0; d < f->doc_count; d++)
+      if (pres[d] && lens[d] > 0) total += (uint64_t)lens[d];
+  }
+  slg_segment_view_t v{};
+  v.segment_ord = f->segment_ord;
+  v.doc_count = f->doc_count;
+  v.n_terms = n_terms;
+  v.field_lengths = lens.data();
+  v.field_length_present = pres.data();
+  v.total_tokens = total;
+  v.deleted_docs = f->deleted_docs;
+  v.n_deleted = f->n_deleted;
+  v.memory_space = SLG_MEM_HOST;
+  int32_t rc = load_post_image(ix, &v, f->post, f->post_bytes, begin.data(), end.data(), &ps.avgdl, k1, b);
+  if (rc) return rc;
+  // scalar fast-field columns, by name (the file's field order is HashMap order, index/fastfields.rs:414)
+  Segment *s = ix->find(f->segment_ord);
+  for (auto &c : ps.fast) {
+    if (c.type > 2 || &c == ps.len_col) continue;
+    size_t h = 0;
+    while (h < ix->column_names.size() && ix->column_names[h] != c.name) h++;
+    if (h == ix->column_names.size()) ix->column_names.push_back(c.name);
+    if (s->columns.size() <= h) s->columns.resize(h + 1);
+    Column col;
+    col.kind = c.type;
+    const size_t elem = c.type == 2 ? 4 : 8;
+    SLG_CUDA(ix, col.values.alloc(std::max<size_t>((size_t)s->doc_count * elem, 1)));
+    SLG_CUDA(ix, cudaMemcpy(col.values.p, c.values, (size_t)s->doc_count * elem, cudaMemcpyHostToDevice));
+    if (c.type != 2) {
+      SLG_CUDA(ix, col.present.alloc(std::max<size_t>(s->doc_count, 1)));
+      SLG_CUDA(ix, cudaMemcpy(col.present.p, c.presence, s->doc_count, cudaMemcpyHostToDevice));
+    }
+    col.dict = c.dict;
+    s->columns[h] = std::move(col);
+  }
+  return SLG_OK;
+}
+
+int32_t slg_load_vector_file(slg_index_t *ix, uint32_t segment_ord, const uint8_t *bytes, uint64_t n_bytes, int32_t store_bf16,
+                             int32_t *metric_out) {
+  if (!ix || !bytes) return SLG_ERR_INVALID;
+  Segment *s = ix->find(segment_ord);
+  if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
+  slgf::VectorFile vf;
+  std::string e;
+  if (!slgf::parse_vector_file(bytes, n_bytes, vf, e)) return fail(ix, SLG_ERR_INVALID, "%s", e.c_str());
+  if (vf.doc_count != s->doc_count)
+    return fail(ix, SLG_ERR_INVALID, "vector doc count mismatch: expected %u, found %u", s->doc_count, vf.doc_count);
+  // the header is 24 bytes, so both arrays are 4-byte aligned whenever the image is
+  std::vector<uint32_t> off(vf.doc_count);
+  std::memcpy(off.data(), vf.offsets, (size_t)vf.doc_count * 4);
+  std::vector<float> vals((size_t)vf.vector_count * vf.dim);
+  std::memcpy(vals.data(), vf.values, vals.size() * 4);
+  if (metric_out) *metric_out = vf.metric;
+  return slg_load_vectors(ix, segment_ord, vf.dim, off.data(), vals.data(), vf.vector_count, store_bf16);
+}
+
+namespace {
+bool read_file(const std::string &path, std::vector<uint8_t> &out) {
+  FILE *fp = fopen(path.c_str(), "rb");
+  if (!fp) return false;
+  fseek(fp, 0, SEEK_END);
+  long n = ftell(fp);
+  fseek(fp, 0, SEEK_SET);
+  out.resize(n > 0 ? (size_t)n : 0);
+  size_t got = out.empty() ? 0 : fread(out.data(), 1, out.size(), fp);
+  fclose(fp);
+  return got == out.size();
+}
+// the manifest stores `root.join(name)` strings (index/directory.rs:16-46); the index may have moved since
+std::string in_dir(const std::string &dir, const std::string &stored) {
+  size_t slash = stored.find_last_of('/');
+  return dir + "/" + (slash == std::string::npos ? stored : stored.substr(slash + 1));
+}
+}  // namespace
+
+int32_t slg_load_index_dir(slg_index_t *ix, const char *dir, const char *field, float k1, float b, const char *vector_field,
+                           int32_t store_bf16, uint32_t *n_segments_out) {
+  if (!ix || !dir || !field) return SLG_ERR_INVALID;
+  std::vector<uint8_t> man;
+  const std::string d(dir);
+  if (!read_file(d + "/MANIFEST.json", man)) return fail(ix, SLG_ERR_INVALID, "cannot read %s/MANIFEST.json", dir);
+  slgf::Json root = slgf::json_root(man.data(), man.size());
+  std::vector<slgf::Json> segs;
+  if (!slgf::json_elements(slgf::json_get(root, "segments"), segs)) return fail(ix, SLG_ERR_INVALID, "manifest has no segments array");
+  uint32_t ord = 0;
+  for (auto &sm : segs) {  // IndexReader::open keeps manifest order; segment_ord is that index (api/reader.rs:2670)
+    slgf::Json paths = slgf::json_get(sm, "paths");
+    std::vector<uint8_t> terms, post, fast, meta;
+    const char *names[4] = {"terms", "postings", "fast", "meta"};
+    std::vector<uint8_t> *bufs[4] = {&terms, &post, &fast, &meta};
+    uint32_t crcs[4];
+    bool have_crc = true;
+    slgf::Json sums = slgf::json_get(sm, "checksums");
+    for (int i = 0; i < 4; i++) {
+      const std::string stored = slgf::json_string(slgf::json_get(paths, names[i]));
+      if (stored.empty()) return fail(ix, SLG_ERR_INVALID, "segment %u: manifest lacks paths.%s", ord, names[i]);
+      if (!read_file(in_dir(d, stored), *bufs[i])) return fail(ix, SLG_ERR_INVALID, "cannot read %s", in_dir(d, stored).c_str());
+      slgf::Json c = slgf::json_get(sums, names[i]);
+      if (c.ok()) crcs[i] = (uint32_t)slgf::json_number(c);
+      else have_crc = false;
+    }
+    std::vector<uint32_t> deleted;
+    std::vector<slgf::Json> del;
+    slgf::json_elements(slgf::json_get(sm, "deleted_docs"), del);
+    for (auto &x : del) deleted.push_back((uint32_t)slgf::json_number(x));
+    slg_segment_files_t f{};
+    f.segment_ord = ord;
+    f.doc_count = (uint32_t)slgf::json_number(slgf::json_get(sm, "doc_count"));
+    f.terms = terms.data();
+    f.terms_bytes = terms.size();
+    f.post = post.data();
+    f.post_bytes = post.size();
+    f.fast = fast.data();
+    f.fast_bytes = fast.size();
+    f.meta = meta.data();
+    f.meta_bytes = meta.size();
+    f.deleted_docs = deleted.data();
+    f.n_deleted = (uint32_t)deleted.size();
+    f.checksums = have_crc ? crcs : nullptr;
+    int32_t rc = slg_load_segment_files(ix, &f, field, k1, b);
+    if (rc) return rc;
+    if (vector_field && *vector_field) {
+      const std::string vdir = slgf::json_string(slgf::json_get(paths, "vector_dir"));
+      if (vdir.empty()) return fail(ix, SLG_ERR_INVALID, "segment missing vector directory path");  // segment.rs:969-972
+      std::vector<uint8_t> vb;
+      const std::string vp = in_dir(d, vdir) + "/" + vector_field + ".bin";
+      if (!read_file(vp, vb)) return fail(ix, SLG_ERR_INVALID, "cannot read %s", vp.c_str());
+      if ((rc = slg_load_vector_file(ix, ord, vb.data(), vb.size(), store_bf16, nullptr))) return rc;
+    }
+    ord++;
+  }
+  if (n_segments_out) *n_segments_out = ord;
+  return SLG_OK;
+}
+
+int32_t slg_term_lookup(const slg_index_t *ix, const char *key, uint32_t *term_id) {
+  if (!ix || !key || !term_id) return SLG_ERR_INVALID;
+  auto it = ix->term_ids.find(key);
+  *term_id = it == ix->term_ids.end() ? 0xFFFFFFFFu : it->second;
+  return SLG_OK;
+}
+
+int32_t slg_column_lookup(const slg_index_t *ix, const char *name) {
+  if (!ix || !name) return SLG_ERR_INVALID;
+  for (size_t h = 0; h < ix->column_names.size(); h++)
+    if (ix->column_names[h] == name) return (int32_t)h;
+  return -1;
+}
+
+/* ---- term positions handed over as CSR (the positions of PostingEntry, index/postings.rs:14-19) ---- */
+int32_t slg_load_positions(slg_index_t *ix, uint32_t segment_ord, const uint64_t *term_offsets, const uint64_t *position_offsets,
+                           const uint32_t *positions) {
+  if (!ix || !term_offsets || !position_offsets) return SLG_ERR_INVALID;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  cudaStream_t st = ix->stream;
+  Segment *s = ix->find(segment_ord);
+  if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
+  for (uint64_t t = 0; t < s->n_terms; t++)
+    if (term_offsets[t + 1] - term_offsets[t] != s->h_df[t])
+      return fail(ix, SLG_ERR_INVALID, "term offsets do not match the loaded postings at term %llu", (unsigned long long)t);
+  const uint64_t n_post = term_offsets[s->n_terms];
+  const uint64_t n_pos = position_offsets[n_post];
+  if (n_pos && !positions) return SLG_ERR_INVALID;
+  ix->ctr.resident_bytes -= s->pos_begin.bytes + s->pos.bytes;
+  s->has_positions = false;
+  DevBuf d_off, d_poff, d_pos, d_npos;
+  SLG_CUDA(ix, d_off.alloc((s->n_terms + 1) * 8));
+  SLG_CUDA(ix, d_poff.alloc((n_post + 1) * 8));
+  SLG_CUDA(ix, d_pos.alloc(std::max<uint64_t>(n_pos, 1) * 4));
+  SLG_CUDA(ix, d_npos.alloc((s->n_post_padded + 1) * 4));
+  SLG_CUDA(ix, cudaMemcpyAsync(d_off.p, term_offsets, (s->n_terms + 1) * 8, cudaMemcpyHostToDevice, st));
+  SLG_CUDA(ix, cudaMemcpyAsync(d_poff.p, position_offsets, (n_post + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (n_pos) SLG_CUDA(ix, cudaMemcpyAsync(d_pos.p, positions, n_pos * 4, cudaMemcpyHostToDevice, st));
+  SLG_CUDA(ix, cudaMemsetAsync(d_npos.p, 0, (s->n_post_padded + 1) * 4, st));
+  if (s->n_blocks) {
+    slg_csr_position_counts_kernel<<<s->n_blocks, 128, 0, st>>>(d_off.as<uint64_t>(), d_poff.as<uint64_t>(), s->n_terms,
+                                                                s->term_start.as<uint64_t>(), s->term_blk.as<uint32_t>(), s->n_blocks,
+                                                                d_npos.as<uint32_t>());
+    count_launch(ix);
+  }
+  int32_t rc = scan_positions(ix, s, d_npos);
+  if (rc) return rc;
+  if (s->n_positions != n_pos) return fail(ix, SLG_ERR_INVALID, "position offsets are inconsistent");
+  if (s->n_blocks) {
+    slg_csr_position_copy_kernel<<<s->n_blocks, 128, 0, st>>>(d_off.as<uint64_t>(), d_poff.as<uint64_t>(), d_pos.as<uint32_t>(),
+                                                              s->n_terms, s->term_start.as<uint64_t>(), s->term_blk.as<uint32_t>(),
+                                                              s->n_blocks, s->pos_begin.as<uint64_t>(), s->pos.as<uint32_t>());
+    count_launch(ix);
+  }
+  SLG_CUDA(ix, cudaGetLastError());
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  s->has_positions = true;
+  ix->ctr.resident_bytes += s->pos_begin.bytes + s->pos.bytes;
   return SLG_OK;
 }
 
@@ -890,6 +1304,25 @@ static bool ci_equals(const std::string &a, const std::string &b) {
     if (x != y) return false;
   }
   return true;
+}
+
+// A filter id names one bitmap per loaded segment (root filters, phrases and their combinations alike).
+static int32_t register_filter(slg_index *ix, FilterProg fp, std::vector<DevBuf> &per_seg) {
+  const size_t id = ix->filters.size();
+  for (size_t si = 0; si < ix->segs.size(); si++) {
+    Segment *s = ix->segs[si].get();
+    s->filter_bits.resize(id + 1);
+    s->filter_bits[id] = std::move(per_seg[si]);
+    std::vector<const uint32_t *> ptrs;
+    for (auto &fb : s->filter_bits) ptrs.push_back(fb.as<uint32_t>());
+    if (s->filter_ptrs.bytes < ptrs.size() * sizeof(void *)) {
+      SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));  // a running batch may still read the old table
+      SLG_CUDA(ix, s->filter_ptrs.alloc(std::max<size_t>(64, ptrs.size() * 2) * sizeof(void *)));
+    }
+    SLG_CUDA(ix, cudaMemcpy(s->filter_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice));
+  }
+  ix->filters.push_back(std::move(fp));
+  return (int32_t)id;
 }
 
 static int32_t compile_filter_for_segment(slg_index *ix, Segment *s, const FilterProg &fp, DevBuf &bits_out) {
@@ -984,19 +1417,12 @@ int32_t slg_filter_compile(slg_index_t *ix, const slg_filter_node_t *nodes, uint
     }
     if (pos != n_nodes) return fail(ix, SLG_ERR_INVALID, "filter program has trailing nodes");
   }
-  for (auto &s : ix->segs) {
-    DevBuf bits;
-    int32_t rc = compile_filter_for_segment(ix, s.get(), fp, bits);
+  std::vector<DevBuf> per_seg(ix->segs.size());
+  for (size_t si = 0; si < ix->segs.size(); si++) {
+    int32_t rc = compile_filter_for_segment(ix, ix->segs[si].get(), fp, per_seg[si]);
     if (rc) return rc;
-    s->filter_bits.resize(ix->filters.size() + 1);
-    s->filter_bits[ix->filters.size()] = std::move(bits);
-    std::vector<const uint32_t *> ptrs;
-    for (auto &fb : s->filter_bits) ptrs.push_back(fb.as<uint32_t>());
-    SLG_CUDA(ix, s->filter_ptrs.alloc(ptrs.size() * sizeof(void *)));
-    SLG_CUDA(ix, cudaMemcpy(s->filter_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice));
   }
-  ix->filters.push_back(std::move(fp));
-  return (int32_t)ix->filters.size() - 1;
+  return register_filter(ix, std::move(fp), per_seg);
 }
 
 int32_t slg_filter_bitmap(slg_index_t *ix, int32_t filter_id, uint32_t segment_ord, uint32_t *bitmap_out) {
@@ -1008,6 +1434,82 @@ int32_t slg_filter_bitmap(slg_index_t *ix, int32_t filter_id, uint32_t segment_o
     return fail(ix, SLG_ERR_INVALID, "filter %d is not compiled for segment %u", filter_id, segment_ord);
   uint32_t words = (s->doc_count + 31) / 32;
   SLG_CUDA(ix, cudaMemcpy(bitmap_out, s->filter_bits[filter_id].p, (size_t)words * 4, cudaMemcpyDeviceToHost));
+  return SLG_OK;
+}
+
+/* ---- phrases (query/phrase.rs:4-48) and bitmap algebra ---- */
+int32_t slg_phrase_compile(slg_index_t *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop) {
+  if (!ix || !term_ids || !n_terms) return SLG_ERR_INVALID;
+  if (n_terms > kMaxPhraseTerms) return fail(ix, SLG_ERR_UNSUPPORTED, "phrase has more than %u terms", kMaxPhraseTerms);
+  if (ix->segs.empty()) return fail(ix, SLG_ERR_INVALID, "no segment loaded");
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  cudaStream_t st = ix->stream;
+  std::vector<DevBuf> per_seg(ix->segs.size());
+  for (size_t si = 0; si < ix->segs.size(); si++) {
+    Segment *s = ix->segs[si].get();
+    if (!s->has_positions) return fail(ix, SLG_ERR_INVALID, "segment %u holds no term positions (index without positions, or keep_positions = 0)", s->ord);
+    const uint32_t words = (s->doc_count + 31) / 32;
+    SLG_CUDA(ix, per_seg[si].alloc(std::max<size_t>(words, 1) * 4));
+    SLG_CUDA(ix, cudaMemsetAsync(per_seg[si].p, 0, std::max<size_t>(words, 1) * 4, st));
+    PhraseDev ph{};
+    ph.n = n_terms;
+    ph.slop = slop;
+    bool absent = false;
+    for (uint32_t j = 0; j < n_terms; j++) {
+      const uint32_t t = term_ids[j];
+      if (t == 0xFFFFFFFFu || t >= s->n_terms || s->h_df[t] == 0) {  // api/reader.rs:1690-1697: no postings => no variant => no match
+        absent = true;
+        break;
+      }
+      ph.df[j] = s->h_df[t];
+      if (ph.df[j] < ph.df[ph.driver]) ph.driver = j;
+    }
+    if (absent) continue;
+    // term starts of the phrase terms (the full table lives on the device)
+    for (uint32_t j = 0; j < n_terms; j++)
+      SLG_CUDA(ix, cudaMemcpyAsync(&ph.start[j], s->term_start.as<uint64_t>() + term_ids[j], 8, cudaMemcpyDeviceToHost, st));
+    SLG_CUDA(ix, cudaStreamSynchronize(st));
+    const uint32_t n = ph.df[ph.driver];
+    slg_phrase_bitmap_kernel<<<(n + 255) / 256, 256, 0, st>>>(ph, s->post_doc.as<uint32_t>(), s->pos_begin.as<uint64_t>(),
+                                                              s->pos.as<uint32_t>(), s->doc_count, per_seg[si].as<uint32_t>());
+    count_launch(ix);
+    SLG_CUDA(ix, cudaGetLastError());
+  }
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  return register_filter(ix, FilterProg{}, per_seg);
+}
+
+int32_t slg_filter_combine(slg_index_t *ix, uint32_t op, int32_t a, int32_t b) {
+  if (!ix) return SLG_ERR_INVALID;
+  if (op > SLG_COMBINE_AND_NOT) return fail(ix, SLG_ERR_INVALID, "unknown combine op %u", op);
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  cudaStream_t st = ix->stream;
+  std::vector<DevBuf> per_seg(ix->segs.size());
+  for (size_t si = 0; si < ix->segs.size(); si++) {
+    Segment *s = ix->segs[si].get();
+    for (int32_t f : {a, b})
+      if (f < 0 || (size_t)f >= s->filter_bits.size() || !s->filter_bits[f].p)
+        return fail(ix, SLG_ERR_INVALID, "filter %d is not compiled for segment %u", f, s->ord);
+    const uint32_t words = (s->doc_count + 31) / 32;
+    SLG_CUDA(ix, per_seg[si].alloc(std::max<size_t>(words, 1) * 4));
+    if (words) {
+      slg_bitmap_combine_kernel<<<(words + 255) / 256, 256, 0, st>>>(s->filter_bits[a].as<uint32_t>(), s->filter_bits[b].as<uint32_t>(),
+                                                                    words, op, per_seg[si].as<uint32_t>());
+      count_launch(ix);
+    }
+  }
+  SLG_CUDA(ix, cudaGetLastError());
+  SLG_CUDA(ix, cudaStreamSynchronize(st));
+  return register_filter(ix, FilterProg{}, per_seg);
+}
+
+int32_t slg_filter_free(slg_index_t *ix, int32_t filter_id) {
+  if (!ix) return SLG_ERR_INVALID;
+  if (filter_id < 0 || (size_t)filter_id >= ix->filters.size()) return fail(ix, SLG_ERR_INVALID, "no filter %d", filter_id);
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));
+  for (auto &s : ix->segs)
+    if ((size_t)filter_id < s->filter_bits.size()) s->filter_bits[filter_id].release();
   return SLG_OK;
 }
 
@@ -1051,6 +1553,10 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
     if (q.n_groups && !q.group_role) return fail(ix, SLG_ERR_INVALID, "query %u has no group roles", qi);
     if (q.filter_id >= (int32_t)ix->filters.size()) return fail(ix, SLG_ERR_INVALID, "query %u names unknown filter %d", qi, q.filter_id);
     q_filter[qi] = q.filter_id < 0 ? -1 : q.filter_id;
+    if (q.filter_id >= 0)
+      for (auto &sg : ix->segs)
+        if ((size_t)q.filter_id >= sg->filter_bits.size() || !sg->filter_bits[q.filter_id].p)
+          return fail(ix, SLG_ERR_INVALID, "query %u names filter %d, which is freed or not compiled for segment %u", qi, q.filter_id, sg->ord);
     uint32_t kept = 0;
     bool need_mask = q.n_groups > 0;
     for (uint32_t t = 0; t < q.n_terms; t++) {

@@ -7,7 +7,9 @@
 // varints are LEB128 (util/varint.rs:5-49).  The host parses the fixed header; the payload is
 // decoded here: one warp per term, 32 bytes per step, every lane that holds a terminator byte
 // assembles its own varint from the (at most 4) bytes before it.  Lists with positions have a
-// data-dependent varint count per posting and are walked by one lane.
+// data-dependent varint count per posting and are walked by one lane; when positions are kept the walk
+// records, per posting, the position count and the byte offset of its deltas, and
+// slg_decode_positions_kernel (slg_phrase.cuh) decodes them one thread per posting.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -43,6 +45,7 @@ __global__ void __launch_bounds__(128) slg_decode_post_image_kernel(const uint8_
                                                                      const uint64_t *term_start, const uint32_t *term_blk,
                                                                      uint32_t *post_doc, uint8_t *post_tf,
                                                                      uint32_t *blk_max_doc, float *blk_max_tf,
+                                                                     uint32_t *post_npos, uint32_t *post_posbyte,
                                                                      uint32_t *err) {
   const uint64_t term = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -58,6 +61,11 @@ __global__ void __launch_bounds__(128) slg_decode_post_image_kernel(const uint8_
         if (!read_varint_seq(img, p, h.end, d) || !read_varint_seq(img, p, h.end, tf) || !read_varint_seq(img, p, h.end, np)) {
           atomicMax(err, 1u);
           break;
+        }
+        if (post_npos) {  // positions stay resident: where this posting's deltas start (slg_decode_positions_kernel)
+          if (p - h.payload > 0xFFFFFFFFull) atomicMax(err, 3u);
+          post_npos[out0 + i] = np;
+          post_posbyte[out0 + i] = (uint32_t)(p - h.payload);
         }
         bool ok = true;
         for (uint32_t j = 0; j < np && ok; j++) ok = read_varint_seq(img, p, h.end, x);

@@ -55,6 +55,28 @@ class SegmentView(C.Structure):
     ]
 
 
+class SegmentFiles(C.Structure):
+    """slg_segment_files_t: one segment as the reference's writer left it on disk"""
+    _fields_ = [
+        ("segment_ord", C.c_uint32), ("doc_count", C.c_uint32),
+        ("terms", C.c_void_p), ("terms_bytes", C.c_uint64), ("post", C.c_void_p), ("post_bytes", C.c_uint64),
+        ("fast", C.c_void_p), ("fast_bytes", C.c_uint64), ("meta", C.c_void_p), ("meta_bytes", C.c_uint64),
+        ("deleted_docs", C.c_void_p), ("n_deleted", C.c_uint32), ("checksums", C.c_void_p),
+    ]
+
+
+class SegmentInfo(C.Structure):
+    _fields_ = [
+        ("n_terms_total", C.c_uint64), ("n_terms_field", C.c_uint64), ("n_postings", C.c_uint64), ("avgdl", C.c_float),
+        ("has_positions", C.c_uint32), ("has_length_column", C.c_uint32), ("n_fast_columns", C.c_uint32),
+        ("n_scalar_columns", C.c_uint32), ("crc_terms", C.c_uint32), ("crc_postings", C.c_uint32), ("crc_fast", C.c_uint32),
+        ("crc_meta", C.c_uint32),
+    ]
+
+
+COMBINE = {"and": 0, "or": 1, "and_not": 2}
+
+
 class Counters(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_uint64), ("score_launches", C.c_uint64), ("score_ms_total", C.c_double),
@@ -79,6 +101,8 @@ EXPORTED_SYMBOLS = [
     "slg_batch_device_results", "slg_batch_free", "slg_merge_gathered", "slg_load_vectors", "slg_rerank",
     "slg_get_counters", "slg_version", "slg_batch_copy_results_device", "slg_get_stream", "slg_selftest_div", "slg_batch_enable_stats",
     "slg_set_option", "slg_term_has_column",
+    "slg_inspect_segment_files", "slg_load_segment_files", "slg_load_index_dir", "slg_load_vector_file", "slg_term_lookup",
+    "slg_column_lookup", "slg_load_positions", "slg_phrase_compile", "slg_filter_combine", "slg_filter_free",
 ]
 
 
@@ -125,6 +149,16 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_batch_enable_stats": [vp, i32],
         "slg_set_option": [vp, C.c_char_p, u64],
         "slg_term_has_column": [vp, u32, u32],
+        "slg_inspect_segment_files": [C.POINTER(SegmentFiles), C.c_char_p, C.POINTER(SegmentInfo), C.c_char_p, u64],
+        "slg_load_segment_files": [vp, C.POINTER(SegmentFiles), C.c_char_p, f32, f32],
+        "slg_load_index_dir": [vp, C.c_char_p, C.c_char_p, f32, f32, C.c_char_p, i32, C.POINTER(u32)],
+        "slg_load_vector_file": [vp, u32, vp, u64, i32, C.POINTER(i32)],
+        "slg_term_lookup": [vp, C.c_char_p, C.POINTER(u32)],
+        "slg_column_lookup": [vp, C.c_char_p],
+        "slg_load_positions": [vp, u32, vp, vp, vp],
+        "slg_phrase_compile": [vp, vp, u32, u32],
+        "slg_filter_combine": [vp, u32, i32, i32],
+        "slg_filter_free": [vp, i32],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -132,6 +166,41 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         fn.restype = C.c_int32
     _LIB = lib
     return lib
+
+
+def segment_files_struct(segment_ord: int, doc_count: int, terms: bytes, post: bytes, fast: bytes, meta: bytes,
+                         deleted_docs=None, checksums=None):
+    """(slg_segment_files_t, keepalive) over byte strings / uint8 arrays"""
+    keep = [np.frombuffer(x, dtype=np.uint8) if not isinstance(x, np.ndarray) else np.ascontiguousarray(x, dtype=np.uint8)
+            for x in (terms, post, fast, meta)]
+    f = SegmentFiles()
+    f.segment_ord, f.doc_count = segment_ord, doc_count
+    for name, a in zip(("terms", "post", "fast", "meta"), keep):
+        setattr(f, name, a.ctypes.data if a.size else 0)
+        setattr(f, name + "_bytes", a.size)
+    if deleted_docs is not None and len(deleted_docs):
+        d = np.ascontiguousarray(deleted_docs, dtype=np.uint32)
+        keep.append(d)
+        f.deleted_docs, f.n_deleted = d.ctypes.data, len(d)
+    if checksums is not None:
+        c = np.ascontiguousarray(checksums, dtype=np.uint32)
+        assert len(c) == 4, "checksums = crc32 of (terms, postings, fast, meta)"
+        keep.append(c)
+        f.checksums = c.ctypes.data
+    return f, keep
+
+
+def inspect_segment_files(doc_count: int, terms: bytes, post: bytes, fast: bytes, meta: bytes, field: str, checksums=None) -> dict:
+    """Host-only validation of a segment's files (no device needed): raises SearchliteGpuError on a bad file."""
+    lib = load_library()
+    f, keep = segment_files_struct(0, doc_count, terms, post, fast, meta, None, checksums)
+    info = SegmentInfo()
+    err = C.create_string_buffer(512)
+    rc = lib.slg_inspect_segment_files(C.byref(f), field.encode(), C.byref(info), err, 512)
+    del keep
+    if rc:
+        raise SearchliteGpuError(rc, err.value.decode(errors="replace"))
+    return {n: getattr(info, n) for n, _ in SegmentInfo._fields_}
 
 
 def _ptr(a) -> int:
@@ -403,6 +472,47 @@ class GpuIndex:
         self._check(self.lib.slg_load_segment_post_image(self.handle, C.byref(v), _ptr(post_image), post_image.nbytes,
                                                          _ptr(post_offsets), k1, b))
         return self._add_columns(host)
+
+    def load_segment_files(self, segment_ord: int, doc_count: int, terms: bytes, post: bytes, fast: bytes, meta: bytes,
+                           field: str, deleted_docs=None, checksums=None, k1: float = 0.9, b: float = 0.4) -> None:
+        """SegmentReader::open from the reference's own files (index/segment.rs:1239-1330), given as bytes."""
+        f, keep = segment_files_struct(segment_ord, doc_count, terms, post, fast, meta, deleted_docs, checksums)
+        self._check(self.lib.slg_load_segment_files(self.handle, C.byref(f), field.encode(), k1, b))
+        del keep
+
+    def load_index_dir(self, path: str, field: str, k1: float = 0.9, b: float = 0.4, vector_field: Optional[str] = None,
+                       store_bf16: bool = False) -> int:
+        """Every segment of an index directory in MANIFEST.json order; returns the segment count."""
+        n = C.c_uint32()
+        vf = vector_field.encode() if vector_field else None
+        self._check(self.lib.slg_load_index_dir(self.handle, path.encode(), field.encode(), k1, b, vf, int(store_bf16), C.byref(n)))
+        return n.value
+
+    def term_lookup(self, key: str) -> int:
+        """term id of a "field:token" key in the handle's term space (ABSENT_TERM if unknown)"""
+        t = C.c_uint32()
+        self._check(self.lib.slg_term_lookup(self.handle, key.encode(), C.byref(t)))
+        return t.value
+
+    def column_lookup(self, name: str) -> int:
+        return int(self.lib.slg_column_lookup(self.handle, name.encode()))
+
+    def load_positions(self, segment_ord: int, term_offsets: np.ndarray, position_offsets: np.ndarray, positions: np.ndarray) -> None:
+        to = np.ascontiguousarray(term_offsets, dtype=np.uint64)
+        po = np.ascontiguousarray(position_offsets, dtype=np.uint64)
+        ps = np.ascontiguousarray(positions, dtype=np.uint32)
+        self._check(self.lib.slg_load_positions(self.handle, segment_ord, _ptr(to), _ptr(po), _ptr(ps)))
+
+    def compile_phrase(self, term_ids: Sequence[int], slop: int = 0) -> int:
+        """matches_phrase (query/phrase.rs:4-48) as a per-segment doc bitmap; the id is used like a filter id"""
+        t = np.ascontiguousarray(term_ids, dtype=np.uint32)
+        return self._check(self.lib.slg_phrase_compile(self.handle, _ptr(t), len(t), slop))
+
+    def combine_filters(self, op: str, a: int, b: int) -> int:
+        return self._check(self.lib.slg_filter_combine(self.handle, COMBINE[op], a, b))
+
+    def free_filter(self, filter_id: int) -> None:
+        self._check(self.lib.slg_filter_free(self.handle, filter_id))
 
     def _add_columns(self, seg: SegmentData) -> dict:
         handles = {}
