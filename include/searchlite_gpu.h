@@ -251,9 +251,9 @@ int32_t slg_column_lookup(const slg_index_t *, const char *name);
 
 /* Term positions of a segment loaded through slg_load_segment (PostingEntry.positions, index/postings.rs:14-19):
  * term_offsets is the view's CSR, position_offsets has one entry per posting + 1, positions are absolute and
- * ascending per posting.  HOST arrays. */
+ * ascending per posting.  memory_space: SLG_MEM_HOST or SLG_MEM_DEVICE for the three arrays. */
 int32_t slg_load_positions(slg_index_t *, uint32_t segment_ord, const uint64_t *term_offsets, const uint64_t *position_offsets,
-                           const uint32_t *positions);
+                           const uint32_t *positions, int32_t memory_space);
 
 /* fast-field columns of the last loaded segment (index/fastfields.rs:910-1039); return handle >= 0 */
 int32_t slg_add_i64_column(slg_index_t *, uint32_t segment_ord, const int64_t *values, const uint8_t *present);
@@ -279,6 +279,10 @@ int32_t slg_filter_bitmap(slg_index_t *, int32_t filter_id, uint32_t segment_ord
  * The matcher requires every phrase of a query (api/reader.rs:1504-1508): AND them, and the root filter,
  * with slg_filter_combine. */
 int32_t slg_phrase_compile(slg_index_t *, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop);
+/* The phrases of a whole query batch in one launch per segment: phrase i = term_ids[phrase_offsets[i] ..
+ * phrase_offsets[i+1]) with slops[i] (slops nullable = all 0); out_ids receives n_phrases consecutive ids. */
+int32_t slg_phrase_compile_batch(slg_index_t *, const uint32_t *term_ids, const uint32_t *phrase_offsets, const uint32_t *slops,
+                                 uint32_t n_phrases, int32_t *out_ids);
 enum { SLG_COMBINE_AND = 0, SLG_COMBINE_OR = 1, SLG_COMBINE_AND_NOT = 2 };
 /* new filter id = a op b, per segment */
 int32_t slg_filter_combine(slg_index_t *, uint32_t op, int32_t a, int32_t b);

@@ -50,33 +50,43 @@ struct DevBuf {
   void *p = nullptr;
   size_t bytes = 0;
   cudaStream_t pool = nullptr;  // non-null: allocated with cudaMallocAsync on this stream
+  bool borrowed = false;        // a view into another DevBuf's allocation: never freed here
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), pool(o.pool) { o.p = nullptr; o.bytes = 0; }
+  DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), pool(o.pool), borrowed(o.borrowed) { o.p = nullptr; o.bytes = 0; }
   DevBuf &operator=(DevBuf &&o) noexcept {
     if (this != &o) {
       release();
       p = o.p;
       bytes = o.bytes;
       pool = o.pool;
+      borrowed = o.borrowed;
       o.p = nullptr;
       o.bytes = 0;
     }
     return *this;
   }
   ~DevBuf() { release(); }
+  void view(void *ptr, size_t n) {  // borrow [ptr, ptr + n) from a slab that outlives this view
+    release();
+    p = ptr;
+    bytes = n;
+    borrowed = true;
+  }
   void release() {
-    if (p) {
+    if (p && !borrowed) {
       if (pool) cudaFreeAsync(p, pool);
       else cudaFree(p);
     }
     p = nullptr;
     bytes = 0;
+    borrowed = false;
   }
   cudaError_t alloc(size_t n) {
     release();
     if (n == 0) n = 16;
+    borrowed = false;
     pool = g_pool_stream;
     cudaError_t e = pool ? cudaMallocAsync(&p, n, pool) : cudaMalloc(&p, n);
     if (e == cudaSuccess) bytes = n;
@@ -119,7 +129,9 @@ struct Segment {
   std::vector<int32_t> h_term_col;  // host copy (tests, introspection); empty = no columns
   SegmentDev dev{};
   std::vector<Column> columns;
-  std::vector<DevBuf> filter_bits;  // per filter id
+  std::vector<DevBuf> filter_bits;  // per filter id (owning, or a view into one of filter_slabs)
+  std::vector<std::shared_ptr<DevBuf>> filter_slabs;  // per filter id: the slab a view borrows from (or null)
+  std::vector<uint64_t> h_start;    // host copy of term_start
   DevBuf filter_ptrs;               // device array of pointers into filter_bits
   Vectors vec;
   // term positions (index/postings.rs:117-125), kept for phrase matching: positions of padded posting slot i are
@@ -456,6 +468,7 @@ int32_t build_layout(slg_index *ix, Segment *s) {
   SLG_CUDA(ix, s->term_wide.alloc(std::max<uint64_t>(s->n_terms, 1) * 8));
   SLG_CUDA(ix, cudaMemsetAsync(s->term_wide.p, 0xFF, std::max<uint64_t>(s->n_terms, 1) * 8, st));
   SLG_CUDA(ix, cudaStreamSynchronize(st));  // host vectors go out of scope
+  s->h_start = std::move(start);
   return SLG_OK;
 }
 
@@ -1195,41 +1208,44 @@ int32_t slg_column_lookup(const slg_index_t *ix, const char *name) {
 
 /* ---- term positions handed over as CSR (the positions of PostingEntry, index/postings.rs:14-19) ---- */
 int32_t slg_load_positions(slg_index_t *ix, uint32_t segment_ord, const uint64_t *term_offsets, const uint64_t *position_offsets,
-                           const uint32_t *positions) {
+                           const uint32_t *positions, int32_t memory_space) {
   if (!ix || !term_offsets || !position_offsets) return SLG_ERR_INVALID;
   SLG_CUDA(ix, cudaSetDevice(ix->device));
   cudaStream_t st = ix->stream;
   Segment *s = ix->find(segment_ord);
   if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
+  const bool dev = memory_space == SLG_MEM_DEVICE;
+  std::vector<uint64_t> off(s->n_terms + 1);
+  if (dev) SLG_CUDA(ix, cudaMemcpy(off.data(), term_offsets, (s->n_terms + 1) * 8, cudaMemcpyDeviceToHost));
+  else std::memcpy(off.data(), term_offsets, (s->n_terms + 1) * 8);
   for (uint64_t t = 0; t < s->n_terms; t++)
-    if (term_offsets[t + 1] - term_offsets[t] != s->h_df[t])
+    if (off[t + 1] - off[t] != s->h_df[t])
       return fail(ix, SLG_ERR_INVALID, "term offsets do not match the loaded postings at term %llu", (unsigned long long)t);
-  const uint64_t n_post = term_offsets[s->n_terms];
-  const uint64_t n_pos = position_offsets[n_post];
+  const uint64_t n_post = off[s->n_terms];
+  uint64_t n_pos = 0;
+  if (dev) SLG_CUDA(ix, cudaMemcpy(&n_pos, position_offsets + n_post, 8, cudaMemcpyDeviceToHost));
+  else n_pos = position_offsets[n_post];
   if (n_pos && !positions) return SLG_ERR_INVALID;
   ix->ctr.resident_bytes -= s->pos_begin.bytes + s->pos.bytes;
   s->has_positions = false;
-  DevBuf d_off, d_poff, d_pos, d_npos;
-  SLG_CUDA(ix, d_off.alloc((s->n_terms + 1) * 8));
-  SLG_CUDA(ix, d_poff.alloc((n_post + 1) * 8));
-  SLG_CUDA(ix, d_pos.alloc(std::max<uint64_t>(n_pos, 1) * 4));
+  DevBuf t_off, t_poff, t_pos, d_npos;
+  const uint64_t *d_off, *d_poff;
+  const uint32_t *d_pos;
+  int32_t rc;
+  if ((rc = to_device(ix, term_offsets, (size_t)s->n_terms + 1, memory_space, t_off, &d_off))) return rc;
+  if ((rc = to_device(ix, position_offsets, (size_t)n_post + 1, memory_space, t_poff, &d_poff))) return rc;
+  if ((rc = to_device(ix, positions, (size_t)n_pos, memory_space, t_pos, &d_pos))) return rc;
   SLG_CUDA(ix, d_npos.alloc((s->n_post_padded + 1) * 4));
-  SLG_CUDA(ix, cudaMemcpyAsync(d_off.p, term_offsets, (s->n_terms + 1) * 8, cudaMemcpyHostToDevice, st));
-  SLG_CUDA(ix, cudaMemcpyAsync(d_poff.p, position_offsets, (n_post + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (n_pos) SLG_CUDA(ix, cudaMemcpyAsync(d_pos.p, positions, n_pos * 4, cudaMemcpyHostToDevice, st));
   SLG_CUDA(ix, cudaMemsetAsync(d_npos.p, 0, (s->n_post_padded + 1) * 4, st));
   if (s->n_blocks) {
-    slg_csr_position_counts_kernel<<<s->n_blocks, 128, 0, st>>>(d_off.as<uint64_t>(), d_poff.as<uint64_t>(), s->n_terms,
-                                                                s->term_start.as<uint64_t>(), s->term_blk.as<uint32_t>(), s->n_blocks,
-                                                                d_npos.as<uint32_t>());
+    slg_csr_position_counts_kernel<<<s->n_blocks, 128, 0, st>>>(d_off, d_poff, s->n_terms, s->term_start.as<uint64_t>(),
+                                                                s->term_blk.as<uint32_t>(), s->n_blocks, d_npos.as<uint32_t>());
     count_launch(ix);
   }
-  int32_t rc = scan_positions(ix, s, d_npos);
-  if (rc) return rc;
+  if ((rc = scan_positions(ix, s, d_npos))) return rc;
   if (s->n_positions != n_pos) return fail(ix, SLG_ERR_INVALID, "position offsets are inconsistent");
   if (s->n_blocks) {
-    slg_csr_position_copy_kernel<<<s->n_blocks, 128, 0, st>>>(d_off.as<uint64_t>(), d_poff.as<uint64_t>(), d_pos.as<uint32_t>(),
-                                                              s->n_terms, s->term_start.as<uint64_t>(), s->term_blk.as<uint32_t>(),
+    slg_csr_position_copy_kernel<<<s->n_blocks, 128, 0, st>>>(d_off, d_poff, d_pos, s->n_terms, s->term_start.as<uint64_t>(), s->term_blk.as<uint32_t>(),
                                                               s->n_blocks, s->pos_begin.as<uint64_t>(), s->pos.as<uint32_t>());
     count_launch(ix);
   }
@@ -1312,6 +1328,7 @@ static int32_t register_filter(slg_index *ix, FilterProg fp, std::vector<DevBuf>
   for (size_t si = 0; si < ix->segs.size(); si++) {
     Segment *s = ix->segs[si].get();
     s->filter_bits.resize(id + 1);
+    s->filter_slabs.resize(id + 1);
     s->filter_bits[id] = std::move(per_seg[si]);
     std::vector<const uint32_t *> ptrs;
     for (auto &fb : s->filter_bits) ptrs.push_back(fb.as<uint32_t>());
@@ -1438,45 +1455,95 @@ int32_t slg_filter_bitmap(slg_index_t *ix, int32_t filter_id, uint32_t segment_o
 }
 
 /* ---- phrases (query/phrase.rs:4-48) and bitmap algebra ---- */
-int32_t slg_phrase_compile(slg_index_t *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop) {
-  if (!ix || !term_ids || !n_terms) return SLG_ERR_INVALID;
-  if (n_terms > kMaxPhraseTerms) return fail(ix, SLG_ERR_UNSUPPORTED, "phrase has more than %u terms", kMaxPhraseTerms);
+int32_t slg_phrase_compile_batch(slg_index_t *ix, const uint32_t *term_ids, const uint32_t *phrase_offsets, const uint32_t *slops,
+                                 uint32_t n_phrases, int32_t *out_ids) {
+  if (!ix || !term_ids || !phrase_offsets || !n_phrases || !out_ids) return SLG_ERR_INVALID;
   if (ix->segs.empty()) return fail(ix, SLG_ERR_INVALID, "no segment loaded");
+  for (uint32_t i = 0; i < n_phrases; i++) {
+    const uint32_t n = phrase_offsets[i + 1] - phrase_offsets[i];
+    if (phrase_offsets[i + 1] <= phrase_offsets[i]) return fail(ix, SLG_ERR_INVALID, "phrase %u has no terms", i);
+    if (n > kMaxPhraseTerms) return fail(ix, SLG_ERR_UNSUPPORTED, "phrase %u has more than %u terms", i, kMaxPhraseTerms);
+  }
   SLG_CUDA(ix, cudaSetDevice(ix->device));
   cudaStream_t st = ix->stream;
-  std::vector<DevBuf> per_seg(ix->segs.size());
+  // per segment: one slab holding every phrase's bitmap, one table of phrase descriptors, one launch
+  std::vector<std::shared_ptr<DevBuf>> slabs(ix->segs.size());
+  std::vector<uint64_t> stride(ix->segs.size());
   for (size_t si = 0; si < ix->segs.size(); si++) {
     Segment *s = ix->segs[si].get();
     if (!s->has_positions) return fail(ix, SLG_ERR_INVALID, "segment %u holds no term positions (index without positions, or keep_positions = 0)", s->ord);
-    const uint32_t words = (s->doc_count + 31) / 32;
-    SLG_CUDA(ix, per_seg[si].alloc(std::max<size_t>(words, 1) * 4));
-    SLG_CUDA(ix, cudaMemsetAsync(per_seg[si].p, 0, std::max<size_t>(words, 1) * 4, st));
-    PhraseDev ph{};
-    ph.n = n_terms;
-    ph.slop = slop;
-    bool absent = false;
-    for (uint32_t j = 0; j < n_terms; j++) {
-      const uint32_t t = term_ids[j];
-      if (t == 0xFFFFFFFFu || t >= s->n_terms || s->h_df[t] == 0) {  // api/reader.rs:1690-1697: no postings => no variant => no match
-        absent = true;
-        break;
+    const uint64_t words = align_up(std::max<uint64_t>((s->doc_count + 31) / 32, 1), 32);  // 128-byte rows
+    stride[si] = words;
+    slabs[si] = std::make_shared<DevBuf>();
+    SLG_CUDA(ix, slabs[si]->alloc(words * 4 * n_phrases));
+    SLG_CUDA(ix, cudaMemsetAsync(slabs[si]->p, 0, words * 4 * n_phrases, st));
+    std::vector<PhraseDev> ph(n_phrases);
+    std::vector<uint32_t> blk_off(n_phrases + 1, 0);
+    for (uint32_t i = 0; i < n_phrases; i++) {
+      PhraseDev &p = ph[i];
+      std::memset(&p, 0, sizeof(p));
+      const uint32_t *t = term_ids + phrase_offsets[i];
+      p.n = phrase_offsets[i + 1] - phrase_offsets[i];
+      p.slop = slops ? slops[i] : 0;
+      bool absent = false;
+      for (uint32_t j = 0; j < p.n; j++) {
+        if (t[j] == 0xFFFFFFFFu || t[j] >= s->n_terms || s->h_df[t[j]] == 0) {  // api/reader.rs:1690-1697: no postings => no variant => no match
+          absent = true;
+          break;
+        }
+        p.df[j] = s->h_df[t[j]];
+        p.start[j] = s->h_start[t[j]];
+        if (p.df[j] < p.df[p.driver]) p.driver = j;
       }
-      ph.df[j] = s->h_df[t];
-      if (ph.df[j] < ph.df[ph.driver]) ph.driver = j;
+      const uint64_t blocks = absent ? 0 : ((uint64_t)p.df[p.driver] + 255) / 256;
+      if (absent) p.n = 0;
+      if (blk_off[i] + blocks > 0x7FFFFFFFull) return fail(ix, SLG_ERR_UNSUPPORTED, "phrase batch is too large for one launch");
+      blk_off[i + 1] = blk_off[i] + (uint32_t)blocks;
     }
-    if (absent) continue;
-    // term starts of the phrase terms (the full table lives on the device)
-    for (uint32_t j = 0; j < n_terms; j++)
-      SLG_CUDA(ix, cudaMemcpyAsync(&ph.start[j], s->term_start.as<uint64_t>() + term_ids[j], 8, cudaMemcpyDeviceToHost, st));
-    SLG_CUDA(ix, cudaStreamSynchronize(st));
-    const uint32_t n = ph.df[ph.driver];
-    slg_phrase_bitmap_kernel<<<(n + 255) / 256, 256, 0, st>>>(ph, s->post_doc.as<uint32_t>(), s->pos_begin.as<uint64_t>(),
-                                                              s->pos.as<uint32_t>(), s->doc_count, per_seg[si].as<uint32_t>());
-    count_launch(ix);
-    SLG_CUDA(ix, cudaGetLastError());
+    if (blk_off[n_phrases]) {
+      DevBuf d_ph, d_off;
+      SLG_CUDA(ix, d_ph.alloc(ph.size() * sizeof(PhraseDev)));
+      SLG_CUDA(ix, d_off.alloc(blk_off.size() * 4));
+      SLG_CUDA(ix, cudaMemcpyAsync(d_ph.p, ph.data(), ph.size() * sizeof(PhraseDev), cudaMemcpyHostToDevice, st));
+      SLG_CUDA(ix, cudaMemcpyAsync(d_off.p, blk_off.data(), blk_off.size() * 4, cudaMemcpyHostToDevice, st));
+      slg_phrase_bitmap_kernel<<<blk_off[n_phrases], 256, 0, st>>>(d_ph.as<PhraseDev>(), d_off.as<uint32_t>(), n_phrases,
+                                                                 s->post_doc.as<uint32_t>(), s->pos_begin.as<uint64_t>(),
+                                                                 s->pos.as<uint32_t>(), s->doc_count, slabs[si]->as<uint32_t>(), words);
+      count_launch(ix);
+      SLG_CUDA(ix, cudaGetLastError());
+      SLG_CUDA(ix, cudaStreamSynchronize(st));  // the host tables go out of scope
+    }
   }
   SLG_CUDA(ix, cudaStreamSynchronize(st));
-  return register_filter(ix, FilterProg{}, per_seg);
+  // ids: consecutive; every segment's entry is a view into its slab
+  const size_t id0 = ix->filters.size();
+  for (size_t si = 0; si < ix->segs.size(); si++) {
+    Segment *s = ix->segs[si].get();
+    s->filter_bits.resize(id0 + n_phrases);
+    s->filter_slabs.resize(id0 + n_phrases);
+    for (uint32_t i = 0; i < n_phrases; i++) {
+      s->filter_bits[id0 + i].view(slabs[si]->as<uint32_t>() + (uint64_t)i * stride[si], stride[si] * 4);
+      s->filter_slabs[id0 + i] = slabs[si];
+    }
+    std::vector<const uint32_t *> ptrs;
+    for (auto &fb : s->filter_bits) ptrs.push_back(fb.as<uint32_t>());
+    if (s->filter_ptrs.bytes < ptrs.size() * sizeof(void *))
+      SLG_CUDA(ix, s->filter_ptrs.alloc(std::max<size_t>(64, ptrs.size() * 2) * sizeof(void *)));
+    SLG_CUDA(ix, cudaMemcpy(s->filter_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice));
+  }
+  for (uint32_t i = 0; i < n_phrases; i++) {
+    ix->filters.push_back(FilterProg{});
+    out_ids[i] = (int32_t)(id0 + i);
+  }
+  return SLG_OK;
+}
+
+int32_t slg_phrase_compile(slg_index_t *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop) {
+  if (!ix || !term_ids || !n_terms) return SLG_ERR_INVALID;
+  const uint32_t off[2] = {0, n_terms};
+  int32_t id = -1;
+  const int32_t rc = slg_phrase_compile_batch(ix, term_ids, off, &slop, 1, &id);
+  return rc ? rc : id;
 }
 
 int32_t slg_filter_combine(slg_index_t *ix, uint32_t op, int32_t a, int32_t b) {
@@ -1509,7 +1576,10 @@ int32_t slg_filter_free(slg_index_t *ix, int32_t filter_id) {
   SLG_CUDA(ix, cudaSetDevice(ix->device));
   SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));
   for (auto &s : ix->segs)
-    if ((size_t)filter_id < s->filter_bits.size()) s->filter_bits[filter_id].release();
+    if ((size_t)filter_id < s->filter_bits.size()) {
+      s->filter_bits[filter_id].release();
+      if ((size_t)filter_id < s->filter_slabs.size()) s->filter_slabs[filter_id].reset();  // the slab goes with its last view
+    }
   return SLG_OK;
 }
 

@@ -136,12 +136,31 @@ __device__ __forceinline__ uint32_t phrase_lower_bound(const uint32_t *docs, uin
   return lo;
 }
 
-// One thread per posting of the driver term.  bits must be zeroed; live / deleted docs are not consulted
-// here (accept() checks them separately, api/reader.rs:3010).
-__global__ void __launch_bounds__(256) slg_phrase_bitmap_kernel(PhraseDev ph, const uint32_t *post_doc, const uint64_t *pos_begin,
-                                                                 const uint32_t *pos, uint32_t doc_count, uint32_t *bits) {
-  const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i0 >= ph.df[ph.driver]) return;
+// One thread per posting of a phrase's driver term; a batch of phrases shares one launch: CTA b serves
+// phrase i with blk_off[i] <= b < blk_off[i+1] and writes row i (row_words words) of `bits`, which must be
+// zeroed.  Live / deleted docs are not consulted here (accept() checks them separately, api/reader.rs:3010).
+__global__ void __launch_bounds__(256) slg_phrase_bitmap_kernel(const PhraseDev *phrases, const uint32_t *blk_off, uint32_t n_phrases,
+                                                                 const uint32_t *post_doc, const uint64_t *pos_begin,
+                                                                 const uint32_t *pos, uint32_t doc_count, uint32_t *bits,
+                                                                 uint64_t row_words) {
+  __shared__ PhraseDev ph;
+  __shared__ uint32_t s_first;
+  if (threadIdx.x == 0) {
+    uint32_t lo = 0, hi = n_phrases;  // last phrase with blk_off[i] <= blockIdx.x (empty phrases share an offset)
+    while (lo + 1 < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (blk_off[mid] <= blockIdx.x) lo = mid;
+      else hi = mid;
+    }
+    s_first = lo;
+  }
+  __syncthreads();
+  const uint32_t pi = s_first;
+  for (uint32_t w = threadIdx.x; w < sizeof(PhraseDev) / 4; w += blockDim.x)
+    reinterpret_cast<uint32_t *>(&ph)[w] = reinterpret_cast<const uint32_t *>(&phrases[pi])[w];
+  __syncthreads();
+  const uint64_t i0 = (uint64_t)(blockIdx.x - blk_off[pi]) * blockDim.x + threadIdx.x;
+  if (ph.n == 0 || i0 >= ph.df[ph.driver]) return;
   const uint32_t doc = post_doc[ph.start[ph.driver] + i0];
   if (doc >= doc_count) return;
   uint64_t pb[kMaxPhraseTerms];  // current cursor into pos[]
@@ -177,7 +196,7 @@ __global__ void __launch_bounds__(256) slg_phrase_bitmap_kernel(PhraseDev ph, co
     if (!chain) break;  // term j has no position after this chain's prefix: none for a later start either
     if ((uint64_t)prev - p0 - (ph.n - 1) <= (uint64_t)ph.slop) hit = true;
   }
-  if (hit) atomicOr(&bits[doc >> 5], 1u << (doc & 31));
+  if (hit) atomicOr(&bits[(uint64_t)pi * row_words + (doc >> 5)], 1u << (doc & 31));
 }
 
 // out = a op b over bitmap words: 0 and, 1 or, 2 and-not.  Tail bits of a and b are zero, so are out's.

@@ -102,7 +102,7 @@ EXPORTED_SYMBOLS = [
     "slg_get_counters", "slg_version", "slg_batch_copy_results_device", "slg_get_stream", "slg_selftest_div", "slg_batch_enable_stats",
     "slg_set_option", "slg_term_has_column",
     "slg_inspect_segment_files", "slg_load_segment_files", "slg_load_index_dir", "slg_load_vector_file", "slg_term_lookup",
-    "slg_column_lookup", "slg_load_positions", "slg_phrase_compile", "slg_filter_combine", "slg_filter_free",
+    "slg_column_lookup", "slg_load_positions", "slg_phrase_compile", "slg_phrase_compile_batch", "slg_filter_combine", "slg_filter_free",
 ]
 
 
@@ -155,8 +155,9 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_load_vector_file": [vp, u32, vp, u64, i32, C.POINTER(i32)],
         "slg_term_lookup": [vp, C.c_char_p, C.POINTER(u32)],
         "slg_column_lookup": [vp, C.c_char_p],
-        "slg_load_positions": [vp, u32, vp, vp, vp],
+        "slg_load_positions": [vp, u32, vp, vp, vp, i32],
         "slg_phrase_compile": [vp, vp, u32, u32],
+        "slg_phrase_compile_batch": [vp, vp, vp, vp, u32, vp],
         "slg_filter_combine": [vp, u32, i32, i32],
         "slg_filter_free": [vp, i32],
     }
@@ -497,16 +498,35 @@ class GpuIndex:
     def column_lookup(self, name: str) -> int:
         return int(self.lib.slg_column_lookup(self.handle, name.encode()))
 
-    def load_positions(self, segment_ord: int, term_offsets: np.ndarray, position_offsets: np.ndarray, positions: np.ndarray) -> None:
-        to = np.ascontiguousarray(term_offsets, dtype=np.uint64)
-        po = np.ascontiguousarray(position_offsets, dtype=np.uint64)
-        ps = np.ascontiguousarray(positions, dtype=np.uint32)
-        self._check(self.lib.slg_load_positions(self.handle, segment_ord, _ptr(to), _ptr(po), _ptr(ps)))
+    def load_positions(self, segment_ord: int, term_offsets, position_offsets, positions) -> None:
+        """numpy arrays (host) or torch CUDA tensors (int64 offsets, int32 positions), all in one space"""
+        if isinstance(term_offsets, np.ndarray):
+            to = np.ascontiguousarray(term_offsets, dtype=np.uint64)
+            po = np.ascontiguousarray(position_offsets, dtype=np.uint64)
+            ps = np.ascontiguousarray(positions, dtype=np.uint32)
+            space = MEM_HOST
+        else:
+            import torch
+            to, po, ps = term_offsets.contiguous(), position_offsets.contiguous(), positions.contiguous()
+            assert to.dtype == torch.int64 and po.dtype == torch.int64 and ps.dtype == torch.int32
+            torch.cuda.synchronize()
+            space = MEM_DEVICE
+        self._check(self.lib.slg_load_positions(self.handle, segment_ord, _ptr(to), _ptr(po), _ptr(ps), space))
 
     def compile_phrase(self, term_ids: Sequence[int], slop: int = 0) -> int:
         """matches_phrase (query/phrase.rs:4-48) as a per-segment doc bitmap; the id is used like a filter id"""
         t = np.ascontiguousarray(term_ids, dtype=np.uint32)
         return self._check(self.lib.slg_phrase_compile(self.handle, _ptr(t), len(t), slop))
+
+    def compile_phrases(self, phrases: Sequence[Sequence[int]], slops: Optional[Sequence[int]] = None) -> np.ndarray:
+        """every phrase of a query batch in one launch per segment; returns their (consecutive) ids"""
+        off = np.zeros(len(phrases) + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(p) for p in phrases])
+        flat = np.ascontiguousarray([t for p in phrases for t in p], dtype=np.uint32)
+        sl = None if slops is None else np.ascontiguousarray(slops, dtype=np.uint32)
+        out = np.zeros(len(phrases), dtype=np.int32)
+        self._check(self.lib.slg_phrase_compile_batch(self.handle, _ptr(flat), _ptr(off), _ptr(sl), len(phrases), _ptr(out)))
+        return out
 
     def combine_filters(self, op: str, a: int, b: int) -> int:
         return self._check(self.lib.slg_filter_combine(self.handle, COMBINE[op], a, b))

@@ -124,6 +124,41 @@ def generate_segment(spec: CorpusSpec, device="cpu", chunk_docs: int = 1 << 18) 
     return seg
 
 
+def token_terms(spec: CorpusSpec, d0: int, d1: int, cdf: torch.Tensor, device) -> tuple:
+    """term id of every (doc, position) of local docs [d0, d1): (term[n, len_hi], valid[n, len_hi]) — the pure function
+    of (seed, doc, position) both generate_segment and generate_positions are built on"""
+    pos = torch.arange(spec.len_hi, dtype=torch.int64, device=device)
+    gdoc = torch.arange(d0, d1, dtype=torch.int64, device=device) + spec.doc_base
+    u = uniform01(hash2(spec.seed, gdoc[:, None] * 512 + pos[None, :]))
+    term = torch.searchsorted(cdf, u, right=True).clamp_(max=spec.vocab - 1)
+    lens = doc_lengths(spec, device)[d0:d1]
+    return term, pos[None, :] < lens[:, None]
+
+
+def generate_positions(spec: CorpusSpec, device="cpu", chunk_docs: int = 1 << 18) -> torch.Tensor:
+    """Token positions of the corpus in the posting order of generate_segment (term-major, docs ascending,
+    positions ascending inside a posting): int32 [total_tokens].  The positions of posting p are
+    positions[off[p] : off[p] + tf[p]] with off = exclusive cumsum of the segment's post_tfs
+    (the writer records position = token index, searchlite-core/src/index/segment.rs:675-684)."""
+    device = torch.device(device)
+    assert spec.len_hi < 512 and spec.vocab <= (1 << 22) and spec.n_docs < (1 << 32)
+    cdf = zipf_cdf(spec.vocab, spec.zipf_s).to(device)
+    pos = torch.arange(spec.len_hi, dtype=torch.int64, device=device)
+    keys = []
+    for d0 in range(0, spec.n_docs, chunk_docs):
+        d1 = min(spec.n_docs, d0 + chunk_docs)
+        term, valid = token_terms(spec, d0, d1, cdf, device)
+        local = torch.arange(d0, d1, dtype=torch.int64, device=device)
+        k = ((term << 41) | (local[:, None] << 9) | pos[None, :])[valid]
+        del term, valid
+        keys.append(torch.sort(k)[0])
+        del k
+    allk = torch.cat(keys) if len(keys) > 1 else keys[0]
+    del keys
+    allk, _ = torch.sort(allk)
+    return (allk & 511).to(torch.int32)
+
+
 def generate_queries(n_queries: int, vocab: int, seed: int = 20260102, zipf_s: float = 1.0, min_terms: int = 2,
                      max_terms: int = 5, min_rank: int = 10) -> QueryBatch:
     """OR queries of min_terms..max_terms DISTINCT terms drawn from the corpus Zipf conditional on

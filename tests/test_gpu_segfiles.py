@@ -276,6 +276,17 @@ def test_phrase_bitmaps_match_the_oracle(source, tmp_path):
         n_nonempty += bool(want.any())
         gi.free_filter(fid)
     assert n_nonempty > 20
+    # the whole batch in one launch gives the same bitmaps; freeing one id leaves its slab neighbours alone
+    batch_ids = gi.compile_phrases([[tid(f"body:{t}") for t in toks] for toks, _ in cases] + [[tid("body:w1"), ABSENT_TERM]],
+                                   [sl for _, sl in cases] + [0])
+    assert len(set(batch_ids.tolist())) == len(cases) + 1
+    gi.free_filter(int(batch_ids[1]))
+    for (toks, slop), fid in list(zip(cases, batch_ids))[::3]:
+        want = slo.phrase_bitmap(n, o_toff, o_docs, g_poff, g_pos, [tid(f"body:{t}") for t in toks], slop)
+        assert np.array_equal(gi.filter_bitmap(int(fid), 0, n), want), (toks, slop)
+    assert not gi.filter_bitmap(int(batch_ids[-1]), 0, n).any()
+    with pytest.raises(SearchliteGpuError):
+        gi.filter_bitmap(int(batch_ids[1]), 0, n)
     # a term the segment lacks: no doc matches (api/reader.rs:1690-1697)
     fid = gi.compile_phrase([tid("body:w1"), ABSENT_TERM], 0)
     assert not gi.filter_bitmap(fid, 0, n).any()

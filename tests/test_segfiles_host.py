@@ -186,3 +186,22 @@ def test_manifest_and_meta_are_plain_json(tmp_path):
     assert on_disk["segments"][0]["doc_count"] == 20 and on_disk == man
     meta = json.load(open(tmp_path / "seg_a1.meta"))
     assert set(meta["avg_field_lengths"]) == {"body", "title"}
+
+
+def test_synthetic_positions_follow_the_posting_order():
+    """synth.generate_positions: positions of posting p = the token indexes of its term in its doc, ascending"""
+    from searchlite_b200 import synth
+    spec = synth.CorpusSpec(n_docs=3000, vocab=500, seed=5, len_lo=5, len_hi=40)
+    seg = synth.generate_segment(spec, "cpu")
+    pos = synth.generate_positions(spec, "cpu", chunk_docs=1000).numpy()
+    assert len(pos) == seg.total_tokens == int(seg.post_tfs.sum())
+    off = np.zeros(len(seg.post_tfs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(seg.post_tfs.astype(np.int64))
+    term, valid = synth.token_terms(spec, 0, spec.n_docs, synth.zipf_cdf(spec.vocab, spec.zipf_s), "cpu")
+    term, valid = term.numpy(), valid.numpy()
+    toff = seg.term_offsets.astype(np.int64)
+    for t in (0, 1, 7, 100, 499):
+        for p in range(toff[t], min(toff[t + 1], toff[t] + 40)):
+            d, ps = seg.post_docs[p], pos[off[p]:off[p + 1]]
+            assert (np.diff(ps) > 0).all() and (term[d, ps] == t).all()
+            assert int((term[d][valid[d]] == t).sum()) == len(ps) == seg.post_tfs[p]
