@@ -72,8 +72,9 @@ def test_struct_layouts_match_the_header():
     src = r'''
     #include "include/searchlite_gpu.h"
     #include <stdio.h>
-    int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(slg_term_t), sizeof(slg_query_t), sizeof(slg_hit_t),
-      sizeof(slg_stats_t), sizeof(slg_filter_node_t), sizeof(slg_segment_view_t), sizeof(slg_counters_t));return 0;}
+    int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(slg_term_t), sizeof(slg_query_t), sizeof(slg_hit_t),
+      sizeof(slg_stats_t), sizeof(slg_filter_node_t), sizeof(slg_segment_view_t), sizeof(slg_counters_t),
+      sizeof(slg_segment_files_t), sizeof(slg_segment_info_t));return 0;}
     '''
     import subprocess
     import tempfile
@@ -83,7 +84,7 @@ def test_struct_layouts_match_the_header():
         exe = os.path.join(td, "s")
         subprocess.run(["gcc", "-std=c99", "-I", ROOT, "-o", exe, c], check=True, cwd=ROOT)  # the header is plain C
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [20, 48, 12, 32, 56, 80, 72]
+    assert sizes == [20, 48, 12, 32, 56, 80, 72, C.sizeof(engine.SegmentFiles), C.sizeof(engine.SegmentInfo)]
 
 
 def test_query_batch_builders():
