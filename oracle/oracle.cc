@@ -348,6 +348,8 @@ struct slo_index {
   const uint64_t *offsets = nullptr;
   const uint32_t *docs = nullptr;
   const uint32_t *tfs = nullptr;
+  const uint64_t *pos_offsets = nullptr;  // BORROWED, one entry per posting + 1 (positions on)
+  const uint32_t *positions = nullptr;
   bool has_lens = false;
   std::vector<float> lens;  // api/reader.rs:3604-3621
   float avgdl = 0.0f;       // index/segment.rs:946-957
@@ -1010,13 +1012,26 @@ int slo_index_set_deleted(slo_index_t *ix, const uint32_t *docs, uint32_t n) {
   return 0;
 }
 
+int slo_index_set_positions(slo_index_t *ix, const uint64_t *pos_offsets, const uint32_t *positions) {
+  ix->pos_offsets = pos_offsets;
+  ix->positions = positions;
+  return 0;
+}
+
 int slo_index_build_post_image(slo_index_t *ix) {
   ix->post_image.clear();
   ix->post_off.assign(ix->n_terms + 1, 0);
   for (uint64_t t = 0; t < ix->n_terms; t++) {
     ix->post_off[t] = ix->post_image.size();
     uint64_t o = ix->offsets[t], e = ix->offsets[t + 1];
-    encode_postings(ix->docs + o, ix->tfs + o, e - o, false, nullptr, nullptr, ix->post_image);
+    if (ix->pos_offsets) {  // positions on, as every reference test / bench / FFI index is written
+      std::vector<uint32_t> rel(e - o + 1);
+      const uint64_t base = ix->pos_offsets[o];
+      for (uint64_t i = o; i <= e; i++) rel[i - o] = (uint32_t)(ix->pos_offsets[i] - base);
+      encode_postings(ix->docs + o, ix->tfs + o, e - o, true, rel.data(), ix->positions + base, ix->post_image);
+    } else {
+      encode_postings(ix->docs + o, ix->tfs + o, e - o, false, nullptr, nullptr, ix->post_image);
+    }
   }
   ix->post_off[ix->n_terms] = ix->post_image.size();
   return 0;

@@ -128,6 +128,8 @@ int slo_index_set_postings(slo_index_t *, uint64_t n_terms, const uint64_t *offs
 int slo_index_set_field_lengths(slo_index_t *, const int64_t *lens, const uint8_t *present, uint64_t total_tokens);
 int slo_index_set_deleted(slo_index_t *, const uint32_t *docs, uint32_t n);
 /* also build the reference's varint `.post` image per term so SLO "faithful" timing can re-decode per query */
+/* positions of every posting (BORROWED; CSR over the postings): the image is then written with positions on */
+int slo_index_set_positions(slo_index_t *, const uint64_t *pos_offsets, const uint32_t *positions);
 int slo_index_build_post_image(slo_index_t *);
 uint64_t slo_index_post_image_size(const slo_index_t *);
 const uint8_t *slo_index_post_image(const slo_index_t *);

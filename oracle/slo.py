@@ -66,6 +66,7 @@ def lib() -> C.CDLL:
     L.slo_index_set_field_lengths.argtypes = [vp, vp, vp, u64]
     L.slo_index_set_deleted.argtypes = [vp, vp, u32]
     L.slo_index_build_post_image.argtypes = [vp]
+    L.slo_index_set_positions.argtypes = [vp, vp, vp]
     L.slo_index_post_image_size.argtypes = [vp]
     L.slo_index_post_image_size.restype = u64
     L.slo_index_post_image.argtypes = [vp]
@@ -159,6 +160,13 @@ class OracleIndex:
     @property
     def min_doc_len(self):
         return self.L.slo_index_min_doc_len(self.h)
+
+    def set_positions(self, pos_offsets, positions):
+        """positions on: build_post_image then writes `varint npos | npos x varint delta` per posting"""
+        self.pos_offsets = np.ascontiguousarray(pos_offsets, dtype=np.uint64)
+        self.positions = np.ascontiguousarray(positions, dtype=np.uint32)
+        self.L.slo_index_set_positions(self.h, _p(self.pos_offsets), _p(self.positions))
+        self._has_image = False
 
     def build_post_image(self):
         """the reference's `.post` byte image of every term + per-term offsets (n_terms+1)"""

@@ -17,7 +17,7 @@ HEADERS = ["slg_kernels.cuh", "slg_phrase.cuh", "slg_segfiles.h", "slg_warp_kern
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-pthread",
     "--fmad=false",            # never contract a*b+c: the reference's f32 arithmetic is unfused
     "-shared",
 ]

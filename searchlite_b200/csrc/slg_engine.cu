@@ -951,7 +951,7 @@ bool parse_segment_files(const slg_segment_files_t *f, const char *field, Parsed
     const uint8_t *img[4] = {f->terms, f->post, f->fast, f->meta};
     const uint64_t len[4] = {f->terms_bytes, f->post_bytes, f->fast_bytes, f->meta_bytes};
     for (int i = 0; i < 4; i++) {
-      const uint32_t actual = slgf::crc32(img[i], len[i]);
+      const uint32_t actual = slgf::crc32_parallel(img[i], len[i]);
       if (actual != f->checksums[i]) {
         err = std::string("segment failed checksum for ") + label[i] + " (expected " + std::to_string(f->checksums[i]) +
               ", found " + std::to_string(actual) + ")";
@@ -1013,10 +1013,10 @@ int32_t slg_inspect_segment_files(const slg_segment_files_t *files, const char *
   out->has_length_column = ps.len_col != nullptr;
   out->n_fast_columns = (uint32_t)ps.fast.size();
   for (auto &c : ps.fast) out->n_scalar_columns += c.type <= 2;
-  out->crc_terms = slgf::crc32(files->terms, files->terms_bytes);
-  out->crc_postings = slgf::crc32(files->post, files->post_bytes);
-  out->crc_fast = slgf::crc32(files->fast, files->fast_bytes);
-  out->crc_meta = slgf::crc32(files->meta, files->meta_bytes);
+  out->crc_terms = slgf::crc32_parallel(files->terms, files->terms_bytes);
+  out->crc_postings = slgf::crc32_parallel(files->post, files->post_bytes);
+  out->crc_fast = slgf::crc32_parallel(files->fast, files->fast_bytes);
+  out->crc_meta = slgf::crc32_parallel(files->meta, files->meta_bytes);
   return SLG_OK;
 }
 

@@ -205,3 +205,27 @@ def test_synthetic_positions_follow_the_posting_order():
             d, ps = seg.post_docs[p], pos[off[p]:off[p + 1]]
             assert (np.diff(ps) > 0).all() and (term[d, ps] == t).all()
             assert int((term[d][valid[d]] == t).sum()) == len(ps) == seg.post_tfs[p]
+
+
+def test_oracle_image_with_positions_equals_the_writer_image():
+    """slo_index_build_post_image with positions on (tools/fileload_bench.py's encoder) == tests/segwriter.py's .post bytes"""
+    from searchlite_b200.engine import SegmentData
+    seg = small_segment(seed=4, n_docs=400, vocab=50)
+    seg.text_fields = ["body"]
+    keys, toff, docs, tfs, poff, pos, lens = sw.csr_of(seg, "body")
+    o = slo.OracleIndex(SegmentData(0, len(seg.docs), toff, docs, tfs, lens, int(lens.sum())))
+    o.set_positions(poff, pos)
+    img, off = o.build_post_image()
+    post, _ = seg.post_and_terms()  # keys sorted == term id order of csr_of
+    assert img.tobytes() == post and off[-1] == len(post)
+
+
+def test_parallel_crc32_of_a_large_file_equals_zlib():
+    """files above a few MB are checksummed on all host cores and the parts combined (GF(2) shift): same value as one pass"""
+    rng = np.random.default_rng(1)
+    terms = struct.pack("<Q", 0) + struct.pack("<I", zlib.crc32(b""))
+    fast = b"FFV1" + struct.pack("<I", 0)
+    for n in (50_000_003, 4 * (4 << 20), 8_388_609):
+        post = rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+        info = inspect_segment_files(0, terms, post, fast, b"{}", "body")
+        assert info["crc_postings"] == zlib.crc32(post), n
