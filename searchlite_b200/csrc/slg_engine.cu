@@ -15,6 +15,10 @@
 #include <cstdio>
 #include <cstring>
 #include <cub/cub.cuh>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <limits>
 #include <memory>
 #include <string>
@@ -740,6 +744,8 @@ int32_t slg_load_segment(slg_index_t *ix, const slg_segment_view_t *v, float k1,
   if (!v->term_offsets || (v->n_terms && (!v->post_docs || !v->post_tfs)))
     return fail(ix, SLG_ERR_INVALID, "segment view lacks postings");
   if (v->doc_count && !v->field_lengths) return fail(ix, SLG_ERR_INVALID, "segment view lacks field lengths");
+  if (!ix->term_field.empty())
+    return fail(ix, SLG_ERR_INVALID, "this handle's term ids come from the files of field '%s' (slg_term_lookup); caller-assigned ids need their own handle", ix->term_field.c_str());
   SLG_CUDA(ix, cudaSetDevice(ix->device));
   cudaStream_t st = ix->stream;
   auto seg = std::make_unique<Segment>();
@@ -1024,6 +1030,8 @@ int32_t slg_load_segment_files(slg_index_t *ix, const slg_segment_files_t *f, co
   if (!ix || !f || !field) return SLG_ERR_INVALID;
   if (!ix->term_field.empty() && ix->term_field != field)
     return fail(ix, SLG_ERR_UNSUPPORTED, "this handle scores field '%s'; one text field per handle", ix->term_field.c_str());
+  if (ix->term_field.empty() && !ix->segs.empty())
+    return fail(ix, SLG_ERR_INVALID, "this handle holds segments loaded with caller-assigned term ids; file segments need their own handle");
   ParsedSegmentFiles ps;
   std::string e;
   if (!parse_segment_files(f, field, ps, e)) return fail(ix, SLG_ERR_INVALID, "%s", e.c_str());
@@ -1104,27 +1112,53 @@ int32_t slg_load_vector_file(slg_index_t *ix, uint32_t segment_ord, const uint8_
   if (!slgf::parse_vector_file(bytes, n_bytes, vf, e)) return fail(ix, SLG_ERR_INVALID, "%s", e.c_str());
   if (vf.doc_count != s->doc_count)
     return fail(ix, SLG_ERR_INVALID, "vector doc count mismatch: expected %u, found %u", s->doc_count, vf.doc_count);
-  // the header is 24 bytes, so both arrays are 4-byte aligned whenever the image is
-  std::vector<uint32_t> off(vf.doc_count);
-  std::memcpy(off.data(), vf.offsets, (size_t)vf.doc_count * 4);
-  std::vector<float> vals((size_t)vf.vector_count * vf.dim);
-  std::memcpy(vals.data(), vf.values, vals.size() * 4);
   if (metric_out) *metric_out = vf.metric;
-  return slg_load_vectors(ix, segment_ord, vf.dim, off.data(), vals.data(), vf.vector_count, store_bf16);
+  // slg_load_vectors only copies from these pointers (no host dereference), so the image needs no alignment and no staging
+  // copy — the rows of a 100 M-doc shard are 19 GB
+  return slg_load_vectors(ix, segment_ord, vf.dim, reinterpret_cast<const uint32_t *>(vf.offsets),
+                          reinterpret_cast<const float *>(vf.values), vf.vector_count, store_bf16);
 }
 
 namespace {
-bool read_file(const std::string &path, std::vector<uint8_t> &out) {
-  FILE *fp = fopen(path.c_str(), "rb");
-  if (!fp) return false;
-  fseek(fp, 0, SEEK_END);
-  long n = ftell(fp);
-  fseek(fp, 0, SEEK_SET);
-  out.resize(n > 0 ? (size_t)n : 0);
-  size_t got = out.empty() ? 0 : fread(out.data(), 1, out.size(), fp);
-  fclose(fp);
-  return got == out.size();
-}
+// read-only mapping of a file: the `.post` of a 10 M-doc index is ~12 GB, so no private copy is made —
+// crc32 and the host-to-device copy read the page cache directly
+struct MappedFile {
+  const uint8_t *p = nullptr;
+  size_t n = 0;
+  MappedFile() = default;
+  MappedFile(const MappedFile &) = delete;
+  MappedFile &operator=(const MappedFile &) = delete;
+  ~MappedFile() {
+    if (p && n) munmap(const_cast<uint8_t *>(p), n);
+  }
+  bool open(const std::string &path) {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+      ::close(fd);
+      return false;
+    }
+    n = (size_t)st.st_size;
+    if (n) {
+      void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m == MAP_FAILED) {
+        ::close(fd);
+        n = 0;
+        return false;
+      }
+      madvise(m, n, MADV_SEQUENTIAL);
+      p = static_cast<const uint8_t *>(m);
+    } else {
+      static const uint8_t empty = 0;
+      p = &empty;
+    }
+    ::close(fd);
+    return true;
+  }
+  const uint8_t *data() const { return p; }
+  size_t size() const { return n; }
+};
 // the manifest stores `root.join(name)` strings (index/directory.rs:16-46); the index may have moved since
 std::string in_dir(const std::string &dir, const std::string &stored) {
   size_t slash = stored.find_last_of('/');
@@ -1135,25 +1169,25 @@ std::string in_dir(const std::string &dir, const std::string &stored) {
 int32_t slg_load_index_dir(slg_index_t *ix, const char *dir, const char *field, float k1, float b, const char *vector_field,
                            int32_t store_bf16, uint32_t *n_segments_out) {
   if (!ix || !dir || !field) return SLG_ERR_INVALID;
-  std::vector<uint8_t> man;
+  MappedFile man;
   const std::string d(dir);
-  if (!read_file(d + "/MANIFEST.json", man)) return fail(ix, SLG_ERR_INVALID, "cannot read %s/MANIFEST.json", dir);
+  if (!man.open(d + "/MANIFEST.json")) return fail(ix, SLG_ERR_INVALID, "cannot read %s/MANIFEST.json", dir);
   slgf::Json root = slgf::json_root(man.data(), man.size());
   std::vector<slgf::Json> segs;
   if (!slgf::json_elements(slgf::json_get(root, "segments"), segs)) return fail(ix, SLG_ERR_INVALID, "manifest has no segments array");
   uint32_t ord = 0;
   for (auto &sm : segs) {  // IndexReader::open keeps manifest order; segment_ord is that index (api/reader.rs:2670)
     slgf::Json paths = slgf::json_get(sm, "paths");
-    std::vector<uint8_t> terms, post, fast, meta;
+    MappedFile terms, post, fast, meta;
     const char *names[4] = {"terms", "postings", "fast", "meta"};
-    std::vector<uint8_t> *bufs[4] = {&terms, &post, &fast, &meta};
+    MappedFile *bufs[4] = {&terms, &post, &fast, &meta};
     uint32_t crcs[4];
     bool have_crc = true;
     slgf::Json sums = slgf::json_get(sm, "checksums");
     for (int i = 0; i < 4; i++) {
       const std::string stored = slgf::json_string(slgf::json_get(paths, names[i]));
       if (stored.empty()) return fail(ix, SLG_ERR_INVALID, "segment %u: manifest lacks paths.%s", ord, names[i]);
-      if (!read_file(in_dir(d, stored), *bufs[i])) return fail(ix, SLG_ERR_INVALID, "cannot read %s", in_dir(d, stored).c_str());
+      if (!bufs[i]->open(in_dir(d, stored))) return fail(ix, SLG_ERR_INVALID, "cannot read %s", in_dir(d, stored).c_str());
       slgf::Json c = slgf::json_get(sums, names[i]);
       if (c.ok()) crcs[i] = (uint32_t)slgf::json_number(c);
       else have_crc = false;
@@ -1181,9 +1215,9 @@ int32_t slg_load_index_dir(slg_index_t *ix, const char *dir, const char *field, 
     if (vector_field && *vector_field) {
       const std::string vdir = slgf::json_string(slgf::json_get(paths, "vector_dir"));
       if (vdir.empty()) return fail(ix, SLG_ERR_INVALID, "segment missing vector directory path");  // segment.rs:969-972
-      std::vector<uint8_t> vb;
+      MappedFile vb;
       const std::string vp = in_dir(d, vdir) + "/" + vector_field + ".bin";
-      if (!read_file(vp, vb)) return fail(ix, SLG_ERR_INVALID, "cannot read %s", vp.c_str());
+      if (!vb.open(vp)) return fail(ix, SLG_ERR_INVALID, "cannot read %s", vp.c_str());
       if ((rc = slg_load_vector_file(ix, ord, vb.data(), vb.size(), store_bf16, nullptr))) return rc;
     }
     ord++;

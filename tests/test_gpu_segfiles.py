@@ -133,6 +133,13 @@ def test_index_dir_load_equals_csr_load_and_oracle(index_dir):
     ga = GpuIndex(0)
     ga.load_index_dir(root, "body")
     assert_parity(*oracle_merged(csr, qb, k), *ga.search_batch(qb, k, "bm25"), strict=False)
+    # one term space per handle: file keys and caller-assigned ids do not mix
+    with pytest.raises(SearchliteGpuError, match="caller-assigned"):
+        gi.load_segment(csr[0])
+    with pytest.raises(SearchliteGpuError, match="caller-assigned"):
+        g2.load_index_dir(root, "body")
+    with pytest.raises(SearchliteGpuError, match="one text field per handle"):
+        gi.load_index_dir(root, "title")
     for h in (gi, g2, ga):
         h.close()
 
