@@ -229,7 +229,12 @@ typedef struct {
  * touching a device.  err (nullable) receives the message on failure. */
 int32_t slg_inspect_segment_files(const slg_segment_files_t *files, const char *field, slg_segment_info_t *out, char *err,
                                   uint64_t err_cap);
-/* Load one segment for scoring text field `field` (one text field per handle).  Term ids of such a handle
+/* Load one segment for scoring the text field(s) `field`: one name, or several separated by commas
+ * ("title,body") — every "f:token" key of a named field enters the term space and is scored with ITS field's
+ * `_len:<f>` column, avg_field_lengths[f] and minimum doc length (ScoredTerm carries them per key,
+ * api/reader.rs:2990-2994), which is what a QueryString over several default fields needs
+ * (query/planner.rs:284-312: one key per field in the term's group, all on one leaf).  Every segment of a
+ * handle must name the same list.  Term ids of such a handle
  * are handed out per "field:token" key in order of first appearance across the loaded segments —
  * slg_term_lookup resolves a key; a segment that lacks a key treats it as an empty list
  * (seg.postings(key) == None, api/reader.rs:2986-2988).  avgdl is the .meta value, N/df/min_doc_len are
@@ -263,6 +268,8 @@ int32_t slg_add_str_column(slg_index_t *, uint32_t segment_ord, const char *cons
 /* segment statistics as the reference derives them (for the host shim and for tests) */
 int32_t slg_segment_stats(const slg_index_t *, uint32_t segment_ord, float *avgdl, float *live_docs,
                           float *min_doc_len, uint64_t *n_postings);
+/* avgdl and minimum positive doc length of the field_index-th scored field (0 = the first / only one) */
+int32_t slg_field_stats(const slg_index_t *, uint32_t segment_ord, uint32_t field_index, float *avgdl, float *min_doc_len);
 
 /* ---- filters (query/filters.rs) ---- */
 /* compiles a root filter against every loaded segment (one bitmap per segment); returns id >= 0 */

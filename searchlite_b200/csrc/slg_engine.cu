@@ -10,6 +10,7 @@
 #include "../../include/searchlite_gpu.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -144,9 +145,19 @@ struct Segment {
   uint64_t n_positions = 0;
   bool has_positions = false;
   bool avgdl_given = false;  // avgdl comes from the segment's .meta file instead of total_tokens / doc_count
+  // further text fields of a handle that scores several ("title:..." next to "body:..."): field 0 is the one the
+  // load call passes directly; these are set before finish_segment, which consumes the device copies
+  struct ExtraField {
+    DevBuf d_lens, d_present;
+    float avgdl = 0.0f;
+  };
+  std::vector<ExtraField> extra_fields;
+  std::vector<uint8_t> h_term_field;      // per term, empty = single field
+  std::vector<float> f_avgdl, f_min_len;  // per field (index 0 = avgdl / min_doc_len)
+  DevBuf term_field;
   size_t resident() const {
     return post_doc.bytes + post_tf.bytes + term_start.bytes + term_df.bytes + term_idf.bytes + term_max_tf.bytes +
-           term_wide.bytes + tf_wide.bytes + term_blk.bytes + blk_max_doc.bytes + blk_max_tf.bytes + nk.bytes +
+           term_wide.bytes + tf_wide.bytes + term_blk.bytes + blk_max_doc.bytes + blk_max_tf.bytes + nk.bytes + term_field.bytes +
            live_bits.bytes + post_score.bytes + post_pair.bytes + cols.bytes + term_col.bytes + col_tmax.bytes +
            pos_begin.bytes + pos.bytes;
   }
@@ -191,7 +202,8 @@ struct slg_index {
   bool keep_positions = true;    // keep term positions resident when a posting image carries them (SegmentReader keep_positions)
   // term space of segments loaded from the reference's files: "field:token" key -> term id, in order of first appearance
   std::unordered_map<std::string, uint32_t> term_ids;
-  std::string term_field;        // the text field those keys belong to
+  std::string term_field;        // the text field(s) those keys belong to, as named at load ("body" or "title,body")
+  std::vector<uint8_t> term_field_of;  // term id -> index of its field in that list
   // fast-field columns by name (handles are indices into every segment's `columns`)
   std::vector<std::string> column_names;
   Segment *find(uint32_t ord) {
@@ -286,6 +298,21 @@ inline float host_nk(float dl, float avgdl, float k1, float b) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// SLG_LOAD_TRACE=1: wall-clock time of every residency stage on stderr (the stream is synchronised at each mark)
+struct StageTimer {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  explicit StageTimer(cudaStream_t s) : on(getenv("SLG_LOAD_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[slg load] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 // --------------------------------------------------------------------------------------------
 // residency
 int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_t *d_lens, const uint8_t *d_present,
@@ -315,23 +342,41 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
   for (uint64_t t = 0; t < s->n_terms; t++) idf[t] = host_idf((float)s->h_df[t], s->live_docs);
   SLG_CUDA(ix, s->term_idf.alloc(s->n_terms * 4));
   if (s->n_terms) SLG_CUDA(ix, cudaMemcpyAsync(s->term_idf.p, idf.data(), s->n_terms * 4, cudaMemcpyHostToDevice, st));
-  // norms
-  SLG_CUDA(ix, s->nk.alloc((size_t)std::max(s->doc_count, 1u) * 4));
+  // norms: one [doc_count] vector per scored text field
+  const uint32_t n_fields = 1 + (uint32_t)s->extra_fields.size();
+  if (n_fields > kMaxFields) return fail(ix, SLG_ERR_UNSUPPORTED, "more than %u text fields in one handle", kMaxFields);
+  const size_t nk_stride = s->doc_count;
+  SLG_CUDA(ix, s->nk.alloc(std::max<size_t>(nk_stride * n_fields, 1) * 4));
+  s->f_avgdl.assign(n_fields, 0.0f);
+  s->f_min_len.assign(n_fields, 1.0f);
   DevBuf minbits;
   SLG_CUDA(ix, minbits.alloc(4));
-  uint32_t inf_bits = 0x7F800000u;
-  SLG_CUDA(ix, cudaMemcpyAsync(minbits.p, &inf_bits, 4, cudaMemcpyHostToDevice, st));
-  if (s->doc_count) {
-    slg_norms_kernel<<<(s->doc_count + 255) / 256, 256, 0, st>>>(d_lens, d_present, s->doc_count, s->avgdl, s->k1, s->b,
-                                                                   s->nk.as<float>(), minbits.as<uint32_t>());
-    count_launch(ix);
+  for (uint32_t f = 0; f < n_fields; f++) {
+    const float avgdl_f = f == 0 ? s->avgdl : s->extra_fields[f - 1].avgdl;
+    const int64_t *lens_f = f == 0 ? d_lens : s->extra_fields[f - 1].d_lens.as<int64_t>();
+    const uint8_t *pres_f = f == 0 ? d_present : s->extra_fields[f - 1].d_present.as<uint8_t>();
+    uint32_t inf_bits = 0x7F800000u;
+    SLG_CUDA(ix, cudaMemcpyAsync(minbits.p, &inf_bits, 4, cudaMemcpyHostToDevice, st));
+    if (s->doc_count) {
+      slg_norms_kernel<<<(s->doc_count + 255) / 256, 256, 0, st>>>(lens_f, pres_f, s->doc_count, avgdl_f, s->k1, s->b,
+                                                                     s->nk.as<float>() + nk_stride * f, minbits.as<uint32_t>());
+      count_launch(ix);
+    }
+    uint32_t got = 0;
+    SLG_CUDA(ix, cudaMemcpyAsync(&got, minbits.p, 4, cudaMemcpyDeviceToHost, st));
+    SLG_CUDA(ix, cudaStreamSynchronize(st));
+    float mn;
+    std::memcpy(&mn, &got, 4);
+    s->f_avgdl[f] = avgdl_f;
+    s->f_min_len[f] = std::isfinite(mn) ? mn : std::max(avgdl_f, 1.0f);  // query/wand.rs:117-121
   }
-  uint32_t got = 0;
-  SLG_CUDA(ix, cudaMemcpyAsync(&got, minbits.p, 4, cudaMemcpyDeviceToHost, st));
-  SLG_CUDA(ix, cudaStreamSynchronize(st));
-  float mn;
-  std::memcpy(&mn, &got, 4);
-  s->min_doc_len = std::isfinite(mn) ? mn : std::max(s->avgdl, 1.0f);  // query/wand.rs:117-121
+  s->min_doc_len = s->f_min_len[0];
+  s->extra_fields.clear();  // the device copies of the length columns are no longer needed
+  if (n_fields > 1) {
+    if (s->h_term_field.size() != s->n_terms) return fail(ix, SLG_ERR_INVALID, "multi-field segment without a term -> field table");
+    SLG_CUDA(ix, s->term_field.alloc(std::max<uint64_t>(s->n_terms, 1)));
+    if (s->n_terms) SLG_CUDA(ix, cudaMemcpyAsync(s->term_field.p, s->h_term_field.data(), s->n_terms, cudaMemcpyHostToDevice, st));
+  }
 
   SegmentDev &d = s->dev;
   d.post_doc = s->post_doc.as<uint32_t>();
@@ -357,6 +402,9 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
   d.doc_count = s->doc_count;
   d.k1p1 = s->k1 + 1.0f;
   d.min_nk = host_nk(s->min_doc_len, s->avgdl, s->k1, s->b);
+  d.term_field = n_fields > 1 ? s->term_field.as<uint8_t>() : nullptr;
+  for (uint32_t f = 0; f < kMaxFields; f++)
+    d.min_nk_f[f] = f < n_fields ? host_nk(s->f_min_len[f], s->f_avgdl[f], s->k1, s->b) : d.min_nk;
 
   // resident unit-weight scores: score_tf(tf, df, doc_len, ...) of every posting, once
   if (ix->resident_scores && s->n_blocks) {
@@ -823,8 +871,15 @@ int32_t scan_positions(slg_index *ix, Segment *s, DevBuf &npos) {
 
 // Residency from a `.post` image.  begin[t] = offset of term t's list (UINT64_MAX: the segment lacks the
 // term), end[t] = an offset the list does not reach past.  avgdl: the .meta value or nullptr (derive it).
+struct FieldInput {  // a further text field: its `_len:` column (host) and its avgdl
+  const int64_t *lens;
+  const uint8_t *present;
+  float avgdl;
+};
+
 int32_t load_post_image(slg_index *ix, const slg_segment_view_t *v, const uint8_t *post_image, uint64_t post_image_bytes,
-                        const uint64_t *begin, const uint64_t *end, const float *avgdl, float k1, float b) {
+                        const uint64_t *begin, const uint64_t *end, const float *avgdl, float k1, float b,
+                        const std::vector<FieldInput> *more_fields = nullptr, const std::vector<uint8_t> *term_field = nullptr) {
   SLG_CUDA(ix, cudaSetDevice(ix->device));
   cudaStream_t st = ix->stream;
   auto seg = std::make_unique<Segment>();
@@ -866,8 +921,11 @@ int32_t load_post_image(slg_index *ix, const slg_segment_view_t *v, const uint8_
     any_positions |= hdr[t].has_positions && df > 0;
     s->h_df[t] = df;
   }
+  StageTimer tm(st);
+  tm.mark("list headers (host)");
   int32_t rc = build_layout(ix, s);
   if (rc) return rc;
+  tm.mark("layout tables");
   const bool keep_pos = any_positions && ix->keep_positions;
   DevBuf d_img, d_hdr, t_lens, t_pres, d_npos, d_posbyte;
   SLG_CUDA(ix, d_img.alloc(post_image_bytes + 16));
@@ -882,6 +940,7 @@ int32_t load_post_image(slg_index *ix, const slg_segment_view_t *v, const uint8_
   DevBuf d_err;
   SLG_CUDA(ix, d_err.alloc(4));
   SLG_CUDA(ix, cudaMemsetAsync(d_err.p, 0, 4, st));
+  tm.mark("image -> device");
   if (v->n_terms) {
     slg_decode_post_image_kernel<<<(unsigned)((v->n_terms + 3) / 4), 128, 0, st>>>(
         d_img.as<uint8_t>(), post_image_bytes, d_hdr.as<PostTermHeader>(), v->n_terms, s->term_start.as<uint64_t>(),
@@ -897,6 +956,7 @@ int32_t load_post_image(slg_index *ix, const slg_segment_view_t *v, const uint8_
   if (derr == 1) return fail(ix, SLG_ERR_INVALID, "malformed varint in the posting image");
   if (derr == 2) return fail(ix, SLG_ERR_UNSUPPORTED, "term frequency >= 255 in a posting image (use the CSR load path)");
   if (derr == 3) return fail(ix, SLG_ERR_UNSUPPORTED, "a posting list with positions is longer than 4 GiB");
+  tm.mark("decode docs + tfs");
   if (keep_pos) {
     if ((rc = scan_positions(ix, s, d_npos))) return rc;
     if (s->n_blocks) {
@@ -911,15 +971,31 @@ int32_t load_post_image(slg_index *ix, const slg_segment_view_t *v, const uint8_
       if (derr) return fail(ix, SLG_ERR_INVALID, "malformed position varint in the posting image");
     }
     s->has_positions = true;
+    tm.mark("decode positions");
   }
   if ((rc = build_wide(ix, s, nullptr, nullptr))) return rc;
   const int64_t *d_lens;
   const uint8_t *d_pres;
   if ((rc = to_device(ix, v->field_lengths, (size_t)v->doc_count, SLG_MEM_HOST, t_lens, &d_lens))) return rc;
   if ((rc = to_device(ix, v->field_length_present, (size_t)v->doc_count, SLG_MEM_HOST, t_pres, &d_pres))) return rc;
+  if (more_fields && !more_fields->empty()) {
+    for (const FieldInput &fi : *more_fields) {
+      Segment::ExtraField ef;
+      ef.avgdl = fi.avgdl;
+      SLG_CUDA(ix, ef.d_lens.alloc(std::max<size_t>(v->doc_count, 1) * 8));
+      SLG_CUDA(ix, ef.d_present.alloc(std::max<size_t>(v->doc_count, 1)));
+      if (v->doc_count) {
+        SLG_CUDA(ix, cudaMemcpyAsync(ef.d_lens.p, fi.lens, (size_t)v->doc_count * 8, cudaMemcpyHostToDevice, st));
+        SLG_CUDA(ix, cudaMemcpyAsync(ef.d_present.p, fi.present, v->doc_count, cudaMemcpyHostToDevice, st));
+      }
+      s->extra_fields.push_back(std::move(ef));
+    }
+    if (term_field) s->h_term_field = *term_field;
+  }
   rc = finish_segment(ix, std::move(seg), d_lens, d_pres, v->total_tokens, v->deleted_docs, v->n_deleted);
   if (rc) return rc;
   SLG_CUDA(ix, cudaStreamSynchronize(st));
+  tm.mark("norms, scores, columns");
   return SLG_OK;
 }
 
@@ -939,17 +1015,44 @@ namespace {
 struct ParsedSegmentFiles {
   std::vector<slgf::TermEntry> terms;      // every key of .terms
   std::vector<slgf::FastColumn> fast;      // every column of .fast
-  const slgf::FastColumn *len_col = nullptr;  // `_len:<field>`
-  float avgdl = 0.0f;
+  std::vector<std::string> fields;         // the scored text fields, in the caller's order
+  std::vector<const slgf::FastColumn *> len_col;  // `_len:<field>` per field (or null)
+  std::vector<float> avgdl;                // per field
+  std::vector<int32_t> term_field;         // per entry of `terms`: index into fields or -1
   uint64_t n_field_terms = 0;
   uint64_t df_sum = 0;
   bool any_positions = false;
 };
 
+// "body" or "title,body": the text fields a handle scores
+std::vector<std::string> split_fields(const char *spec) {
+  std::vector<std::string> out;
+  std::string cur;
+  for (const char *p = spec;; p++) {
+    if (*p == ',' || *p == '\0') {
+      if (!cur.empty()) out.push_back(cur);
+      cur.clear();
+      if (!*p) break;
+    } else {
+      cur.push_back(*p);
+    }
+  }
+  return out;
+}
+
 // verify_checksums + read_terms + FastFieldsReader::open + the .meta fields the search path reads
-bool parse_segment_files(const slg_segment_files_t *f, const char *field, ParsedSegmentFiles &out, std::string &err) {
+bool parse_segment_files(const slg_segment_files_t *f, const char *field_spec, ParsedSegmentFiles &out, std::string &err) {
   if (!f->terms || !f->post || !f->fast || !f->meta) {
     err = "segment files: terms, post, fast and meta images are all required";
+    return false;
+  }
+  out.fields = split_fields(field_spec);
+  if (out.fields.empty()) {
+    err = "no text field named";
+    return false;
+  }
+  if (out.fields.size() > kMaxFields) {
+    err = "more than " + std::to_string(kMaxFields) + " text fields in one handle";
     return false;
   }
   if (f->checksums) {  // SegmentMeta.checksums, index/segment.rs:1140-1200
@@ -967,34 +1070,48 @@ bool parse_segment_files(const slg_segment_files_t *f, const char *field, Parsed
   }
   if (!slgf::parse_terms(f->terms, f->terms_bytes, out.terms, err)) return false;
   if (!slgf::parse_fast(f->fast, f->fast_bytes, out.fast, err)) return false;
-  const std::string len_key = std::string("_len:") + field;  // doc_length_key, index/fastfields.rs:1162-1164
-  for (auto &c : out.fast) {
-    if (c.type <= 2 && c.doc_len != f->doc_count) {
-      err = "fast-field column '" + c.name + "' has " + std::to_string(c.doc_len) + " rows, the segment " + std::to_string(f->doc_count) + " docs";
-      return false;
-    }
-    if (c.name == len_key && c.type == 0) out.len_col = &c;
-  }
   slgf::Json root = slgf::json_root(f->meta, f->meta_bytes);
   if (root.kind() != '{') {
     err = "segment meta is not a JSON object";
     return false;
   }
-  // SegmentReader::avg_field_length, index/segment.rs:1344-1351: missing field => 0.0; serde_json reads an f32 as f64 -> f32
-  out.avgdl = (float)slgf::json_number(slgf::json_get(slgf::json_get(root, "avg_field_lengths"), field), 0.0);
-  const std::string prefix = std::string(field) + ":";
-  for (auto &t : out.terms) {
+  for (auto &c : out.fast)
+    if (c.type <= 2 && c.doc_len != f->doc_count) {
+      err = "fast-field column '" + c.name + "' has " + std::to_string(c.doc_len) + " rows, the segment " + std::to_string(f->doc_count) + " docs";
+      return false;
+    }
+  const slgf::Json avgs = slgf::json_get(root, "avg_field_lengths");
+  for (auto &field : out.fields) {
+    const std::string len_key = "_len:" + field;  // doc_length_key, index/fastfields.rs:1162-1164
+    const slgf::FastColumn *lc = nullptr;
+    for (auto &c : out.fast)
+      if (c.name == len_key && c.type == 0) lc = &c;
+    out.len_col.push_back(lc);
+    // SegmentReader::avg_field_length, index/segment.rs:1344-1351: missing field => 0.0; serde_json reads an f32 as f64 -> f32
+    out.avgdl.push_back((float)slgf::json_number(slgf::json_get(avgs, field.c_str()), 0.0));
+  }
+  out.term_field.assign(out.terms.size(), -1);
+  for (size_t i = 0; i < out.terms.size(); i++) {
+    const slgf::TermEntry &t = out.terms[i];
     if (t.offset + 17 > f->post_bytes) {
       err = "a term's posting offset lies outside the posting file";
       return false;
     }
-    if (t.key_len >= prefix.size() && std::memcmp(t.key, prefix.data(), prefix.size()) == 0) {
-      out.n_field_terms++;
-      uint32_t df;
-      std::memcpy(&df, f->post + t.offset, 4);
-      out.df_sum += df;
-      out.any_positions |= f->post[t.offset + 4] == 1;
-    }
+    // keys are "<field>:<token>" (index/segment.rs:675-679); field names hold no ':' in the reference's schemas,
+    // so the field is the text before the first colon
+    const char *colon = static_cast<const char *>(std::memchr(t.key, ':', t.key_len));
+    if (!colon) continue;
+    const size_t fl = (size_t)(colon - t.key);
+    for (size_t fi = 0; fi < out.fields.size(); fi++)
+      if (out.fields[fi].size() == fl && std::memcmp(t.key, out.fields[fi].data(), fl) == 0) {
+        out.term_field[i] = (int32_t)fi;
+        out.n_field_terms++;
+        uint32_t df;
+        std::memcpy(&df, f->post + t.offset, 4);
+        out.df_sum += df;
+        out.any_positions |= f->post[t.offset + 4] == 1;
+        break;
+      }
   }
   return true;
 }
@@ -1014,9 +1131,9 @@ int32_t slg_inspect_segment_files(const slg_segment_files_t *files, const char *
   out->n_terms_total = ps.terms.size();
   out->n_terms_field = ps.n_field_terms;
   out->n_postings = ps.df_sum;
-  out->avgdl = ps.avgdl;
+  out->avgdl = ps.avgdl[0];
   out->has_positions = ps.any_positions;
-  out->has_length_column = ps.len_col != nullptr;
+  out->has_length_column = ps.len_col[0] != nullptr;
   out->n_fast_columns = (uint32_t)ps.fast.size();
   for (auto &c : ps.fast) out->n_scalar_columns += c.type <= 2;
   out->crc_terms = slgf::crc32_parallel(files->terms, files->terms_bytes);
@@ -1029,12 +1146,14 @@ int32_t slg_inspect_segment_files(const slg_segment_files_t *files, const char *
 int32_t slg_load_segment_files(slg_index_t *ix, const slg_segment_files_t *f, const char *field, float k1, float b) {
   if (!ix || !f || !field) return SLG_ERR_INVALID;
   if (!ix->term_field.empty() && ix->term_field != field)
-    return fail(ix, SLG_ERR_UNSUPPORTED, "this handle scores field '%s'; one text field per handle", ix->term_field.c_str());
+    return fail(ix, SLG_ERR_UNSUPPORTED, "this handle scores field(s) '%s'; every segment of a handle names the same field list", ix->term_field.c_str());
   if (ix->term_field.empty() && !ix->segs.empty())
     return fail(ix, SLG_ERR_INVALID, "this handle holds segments loaded with caller-assigned term ids; file segments need their own handle");
   ParsedSegmentFiles ps;
   std::string e;
+  StageTimer tm(ix->stream);
   if (!parse_segment_files(f, field, ps, e)) return fail(ix, SLG_ERR_INVALID, "%s", e.c_str());
+  tm.mark("crc32 + parse files (host)");
   // every list's end: the next list's offset in file order (lists of all fields share the file)
   std::vector<uint64_t> all_off;
   all_off.reserve(ps.terms.size() + 1);
@@ -1042,47 +1161,62 @@ int32_t slg_load_segment_files(slg_index_t *ix, const slg_segment_files_t *f, co
   all_off.push_back(f->post_bytes);
   std::sort(all_off.begin(), all_off.end());
   // the handle's term space grows by the keys this segment adds
-  const std::string prefix = std::string(field) + ":";
-  std::vector<std::pair<uint32_t, uint64_t>> mine;  // (term id, offset)
+  struct Mine {
+    uint32_t id;
+    uint64_t offset;
+    uint8_t field;
+  };
+  std::vector<Mine> mine;
   mine.reserve((size_t)ps.n_field_terms);
-  for (auto &t : ps.terms) {
-    if (t.key_len < prefix.size() || std::memcmp(t.key, prefix.data(), prefix.size()) != 0) continue;
+  for (size_t i = 0; i < ps.terms.size(); i++) {
+    if (ps.term_field[i] < 0) continue;
+    const slgf::TermEntry &t = ps.terms[i];
     auto it = ix->term_ids.emplace(std::string(t.key, t.key_len), (uint32_t)ix->term_ids.size()).first;
-    mine.emplace_back(it->second, t.offset);
+    if (it->second >= ix->term_field_of.size()) ix->term_field_of.resize(it->second + 1, 0);
+    ix->term_field_of[it->second] = (uint8_t)ps.term_field[i];
+    mine.push_back(Mine{it->second, t.offset, (uint8_t)ps.term_field[i]});
   }
   ix->term_field = field;
   const uint64_t n_terms = ix->term_ids.size();
   std::vector<uint64_t> begin(n_terms, ~0ull), end(n_terms, 0);
   for (auto &m : mine) {
-    begin[m.first] = m.second;
-    end[m.first] = *std::upper_bound(all_off.begin(), all_off.end(), m.second);
+    begin[m.id] = m.offset;
+    end[m.id] = *std::upper_bound(all_off.begin(), all_off.end(), m.offset);
   }
-  // `_len:<field>` (field_lengths_for, api/reader.rs:3604-3621: absent column or value => 0)
-  std::vector<int64_t> lens(f->doc_count, 0);
-  std::vector<uint8_t> pres(f->doc_count, 0);
+  // `_len:<field>` per field (field_lengths_for, api/reader.rs:3604-3621: absent column or value => 0)
+  const size_t n_fields = ps.fields.size();
+  std::vector<std::vector<int64_t>> lens(n_fields, std::vector<int64_t>(f->doc_count, 0));
+  std::vector<std::vector<uint8_t>> pres(n_fields, std::vector<uint8_t>(f->doc_count, 0));
   uint64_t total = 0;
-  if (ps.len_col) {
-    std::memcpy(lens.data(), ps.len_col->values, (size_t)f->doc_count * 8);
-    std::memcpy(pres.data(), ps.len_col->presence, f->doc_count);
-    for (uint32_t d = 0; d < f->doc_count; d++)
-      if (pres[d] && lens[d] > 0) total += (uint64_t)lens[d];
+  for (size_t fi = 0; fi < n_fields; fi++) {
+    if (!ps.len_col[fi]) continue;
+    std::memcpy(lens[fi].data(), ps.len_col[fi]->values, (size_t)f->doc_count * 8);
+    std::memcpy(pres[fi].data(), ps.len_col[fi]->presence, f->doc_count);
+    if (fi == 0)
+      for (uint32_t d = 0; d < f->doc_count; d++)
+        if (pres[0][d] && lens[0][d] > 0) total += (uint64_t)lens[0][d];
   }
+  tm.mark("term space + lengths (host)");
+  std::vector<FieldInput> more;
+  for (size_t fi = 1; fi < n_fields; fi++) more.push_back(FieldInput{lens[fi].data(), pres[fi].data(), ps.avgdl[fi]});
+  std::vector<uint8_t> term_field(ix->term_field_of.begin(), ix->term_field_of.end());
+  term_field.resize(n_terms, 0);
   slg_segment_view_t v{};
   v.segment_ord = f->segment_ord;
   v.doc_count = f->doc_count;
   v.n_terms = n_terms;
-  v.field_lengths = lens.data();
-  v.field_length_present = pres.data();
+  v.field_lengths = lens[0].data();
+  v.field_length_present = pres[0].data();
   v.total_tokens = total;
   v.deleted_docs = f->deleted_docs;
   v.n_deleted = f->n_deleted;
   v.memory_space = SLG_MEM_HOST;
-  int32_t rc = load_post_image(ix, &v, f->post, f->post_bytes, begin.data(), end.data(), &ps.avgdl, k1, b);
+  int32_t rc = load_post_image(ix, &v, f->post, f->post_bytes, begin.data(), end.data(), &ps.avgdl[0], k1, b, &more, &term_field);
   if (rc) return rc;
   // scalar fast-field columns, by name (the file's field order is HashMap order, index/fastfields.rs:414)
   Segment *s = ix->find(f->segment_ord);
   for (auto &c : ps.fast) {
-    if (c.type > 2 || &c == ps.len_col) continue;
+    if (c.type > 2 || c.name.compare(0, 5, "_len:") == 0) continue;
     size_t h = 0;
     while (h < ix->column_names.size() && ix->column_names[h] != c.name) h++;
     if (h == ix->column_names.size()) ix->column_names.push_back(c.name);
@@ -1300,6 +1434,17 @@ int32_t slg_segment_stats(const slg_index_t *ixc, uint32_t segment_ord, float *a
   if (live_docs) *live_docs = s->live_docs;
   if (min_doc_len) *min_doc_len = s->min_doc_len;
   if (n_postings) *n_postings = s->n_postings;
+  return SLG_OK;
+}
+
+int32_t slg_field_stats(const slg_index_t *ixc, uint32_t segment_ord, uint32_t field_index, float *avgdl, float *min_doc_len) {
+  slg_index *ix = const_cast<slg_index *>(ixc);
+  if (!ix) return SLG_ERR_INVALID;
+  Segment *s = ix->find(segment_ord);
+  if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
+  if (field_index >= s->f_avgdl.size()) return fail(ix, SLG_ERR_INVALID, "segment %u scores %zu field(s)", segment_ord, s->f_avgdl.size());
+  if (avgdl) *avgdl = s->f_avgdl[field_index];
+  if (min_doc_len) *min_doc_len = s->f_min_len[field_index];
   return SLG_OK;
 }
 

@@ -805,7 +805,7 @@ __global__ void slg_build_sweep_kernel(SegmentDev seg, BatchDev bt, uint32_t n_s
       } else {
         out[8 + p] = (uint32_t)seg.term_start[term];
         const float mtf = seg.term_max_tf[term];
-        ub = mtf > 0.0f ? __fmul_rn(bm25_contrib(mtf, seg.term_idf[term], seg.k1p1, seg.min_nk, 1.0f), w) : 0.0f;
+        ub = mtf > 0.0f ? __fmul_rn(bm25_contrib(mtf, seg.term_idf[term], seg.k1p1, seg_min_nk(seg, term), 1.0f), w) : 0.0f;
         ns++;
       }
       if (w != 1.0f) anyw = 1;
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(128) slg_score_postings_kernel(SegmentDev seg,
   uint32_t tf = seg.post_tf[base + i];
   const uint64_t wide = seg.term_wide[term];
   if (tf == 255u && wide != ~0ull) tf = seg.tf_wide[wide + i];
-  post_score[base + i] = bm25_contrib_fast(tf, seg.term_idf[term], seg.k1p1, seg.nk[doc], 1.0f);
+  post_score[base + i] = bm25_contrib_fast(tf, seg.term_idf[term], seg.k1p1, seg_nk(seg, term)[doc], 1.0f);
 }
 
 // (doc, score bits) of every posting side by side: one 8-byte copy per posting in the sweep

@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
           tc.fptr = seg.post_tf + q.base;
           tc.wptr = wide != ~0ull ? seg.tf_wide + wide : nullptr;
           tc.scored = scored;
+          tc.nk = seg_nk(seg, q.term);
           tc.idf = seg.term_idf[q.term];
           tc.w = q.weight;
           tc.gbit = MATCHER ? (uint8_t)(1u << ((q.flags >> 8) & 7u)) : 0;

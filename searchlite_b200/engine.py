@@ -102,7 +102,7 @@ EXPORTED_SYMBOLS = [
     "slg_get_counters", "slg_version", "slg_batch_copy_results_device", "slg_get_stream", "slg_selftest_div", "slg_batch_enable_stats",
     "slg_set_option", "slg_term_has_column",
     "slg_inspect_segment_files", "slg_load_segment_files", "slg_load_index_dir", "slg_load_vector_file", "slg_term_lookup",
-    "slg_column_lookup", "slg_load_positions", "slg_phrase_compile", "slg_phrase_compile_batch", "slg_filter_combine", "slg_filter_free",
+    "slg_column_lookup", "slg_field_stats", "slg_load_positions", "slg_phrase_compile", "slg_phrase_compile_batch", "slg_filter_combine", "slg_filter_free",
 ]
 
 
@@ -155,6 +155,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_load_vector_file": [vp, u32, vp, u64, i32, C.POINTER(i32)],
         "slg_term_lookup": [vp, C.c_char_p, C.POINTER(u32)],
         "slg_column_lookup": [vp, C.c_char_p],
+        "slg_field_stats": [vp, u32, u32, C.POINTER(f32), C.POINTER(f32)],
         "slg_load_positions": [vp, u32, vp, vp, vp, i32],
         "slg_phrase_compile": [vp, vp, u32, u32],
         "slg_phrase_compile_batch": [vp, vp, vp, vp, u32, vp],
@@ -554,6 +555,11 @@ class GpuIndex:
         a, l, m, n = C.c_float(), C.c_float(), C.c_float(), C.c_uint64()
         self._check(self.lib.slg_segment_stats(self.handle, segment_ord, C.byref(a), C.byref(l), C.byref(m), C.byref(n)))
         return {"avgdl": a.value, "live_docs": l.value, "min_doc_len": m.value, "n_postings": n.value}
+
+    def field_stats(self, segment_ord: int, field_index: int) -> dict:
+        a, m = C.c_float(), C.c_float()
+        self._check(self.lib.slg_field_stats(self.handle, segment_ord, field_index, C.byref(a), C.byref(m)))
+        return {"avgdl": a.value, "min_doc_len": m.value}
 
     # ---- filters ---------------------------------------------------------------------------
     def compile_filter(self, nodes: np.ndarray, strings: Sequence[str] = ()) -> int:

@@ -138,7 +138,7 @@ def test_index_dir_load_equals_csr_load_and_oracle(index_dir):
         gi.load_segment(csr[0])
     with pytest.raises(SearchliteGpuError, match="caller-assigned"):
         g2.load_index_dir(root, "body")
-    with pytest.raises(SearchliteGpuError, match="one text field per handle"):
+    with pytest.raises(SearchliteGpuError, match="same field list"):
         gi.load_index_dir(root, "title")
     for h in (gi, g2, ga):
         h.close()
@@ -354,3 +354,80 @@ def test_positions_can_be_dropped(tmp_path):
     with pytest.raises(SearchliteGpuError, match="no term positions"):
         gi.compile_phrase([0, 1], 0)
     gi.close()
+
+
+# ---- several text fields in one handle ----
+def test_multi_field_keys_use_their_own_norms(index_dir):
+    """QueryString over default fields [body, title] (query/planner.rs:284-312): per term one key per field; every key
+    is scored with its field's lengths / avgdl / min length (api/reader.rs:2990-2994).  Expected values: the oracle
+    scores each key alone in a single-field index of its field; the engine's sum is the f32 left fold in query order."""
+    root, segs = index_dir
+    from oracle import slo
+    gi = GpuIndex(0, kernel="warp")
+    assert gi.load_index_dir(root, "body,title") == 2
+    per_field = {}
+    for si, s in enumerate(segs):
+        for fi, field in enumerate(("body", "title")):
+            keys, toff, docs, tfs, poff, pos, lens = sw.csr_of(s, field)
+            sd = SegmentData(si, len(s.docs), toff, docs, tfs, lens, int(lens.sum()),
+                             deleted_docs=np.asarray(s.deleted, dtype=np.uint32) if s.deleted else None)
+            o = slo.OracleIndex(sd)
+            per_field[(si, field)] = (keys, o)
+            st = gi.field_stats(si, fi)
+            assert np.float32(st["avgdl"]).view(np.uint32) == np.float32(o.avgdl).view(np.uint32), (si, field)
+            assert np.float32(st["min_doc_len"]).view(np.uint32) == np.float32(o.min_doc_len).view(np.uint32), (si, field)
+
+    cache = {}
+
+    def key_scores(si, key):
+        """doc -> f32 score of one key alone in segment si (deleted docs absent)"""
+        if (si, key) not in cache:
+            cache[(si, key)] = _key_scores(si, key)
+        return cache[(si, key)]
+
+    def _key_scores(si, key):
+        keys, o = per_field[(si, key.split(":")[0])]
+        if key not in keys:
+            return {}
+        h, c = o.search_batch(QueryBatch.from_term_lists([[keys.index(key)]]), len(segs[si].docs) + 1, "bm25")
+        return {int(x["doc_id"]): np.float32(x["score"]) for x in h[0, : c[0]]}
+
+    rng = np.random.default_rng(12)
+    queries = []
+    for _ in range(40):
+        toks = rng.choice(np.arange(1, 60), size=int(rng.integers(1, 4)), replace=False)
+        queries.append([f"{f}:w{int(t)}" for t in toks for f in ("body", "title")])
+    queries.append(["title:w1", "body:nosuch", "title:w2"])
+    qb = QueryBatch.from_term_lists([[gi.term_lookup(k) for k in q] for q in queries])
+    k = 11
+    for exe in ("bm25", "bmw"):
+        got_h, got_c = gi.search_batch(qb, k, exe)
+        for qi, q in enumerate(queries):
+            rows = []
+            for si in range(len(segs)):
+                total = {}
+                for key in q:
+                    for d, sc in key_scores(si, key).items():
+                        total[d] = np.float32(total[d] + sc) if d in total else sc
+                rows += [(-float(sc), si, d, sc) for d, sc in total.items()]
+            rows.sort(key=lambda r: (r[0], r[1], r[2]))
+            want = rows[:k]
+            g = got_h[qi, : got_c[qi]]
+            assert len(g) == len(want), (exe, qi)
+            assert [(int(x["segment_ord"]), int(x["doc_id"])) for x in g] == [(r[1], r[2]) for r in want], (exe, qi, q)
+            assert g["score"].view(np.uint32).tolist() == [int(np.float32(r[3]).view(np.uint32)) for r in want], (exe, qi)
+    # the automatic kernel (column front end, resident scores) agrees within the rule
+    ga = GpuIndex(0)
+    ga.load_index_dir(root, "body,title")
+    a_h, a_c = ga.search_batch(qb, k, "bm25")
+    assert_parity(got_h, got_c, a_h, a_c, strict=False)
+    # in-place scoring (no resident scores) takes the same per-field norms
+    gp = GpuIndex(0, kernel="warp")
+    gp.set_option("resident_scores", 0)
+    gp.load_index_dir(root, "body,title")
+    p_h, p_c = gp.search_batch(qb, k, "bm25")
+    assert p_h.tobytes() == got_h.tobytes() and p_c.tobytes() == got_c.tobytes()
+    with pytest.raises(SearchliteGpuError, match="same field list"):
+        gi.load_index_dir(root, "body")
+    for h in (gi, ga, gp):
+        h.close()
