@@ -1212,7 +1212,14 @@ int32_t slg_load_segment_files(slg_index_t *ix, const slg_segment_files_t *f, co
   v.n_deleted = f->n_deleted;
   v.memory_space = SLG_MEM_HOST;
   int32_t rc = load_post_image(ix, &v, f->post, f->post_bytes, begin.data(), end.data(), &ps.avgdl[0], k1, b, &more, &term_field);
-  if (rc) return rc;
+  if (rc) {
+    if (ix->segs.empty()) {  // nothing loaded yet: a failed first load leaves no term space behind
+      ix->term_ids.clear();
+      ix->term_field_of.clear();
+      ix->term_field.clear();
+    }
+    return rc;
+  }
   // scalar fast-field columns, by name (the file's field order is HashMap order, index/fastfields.rs:414)
   Segment *s = ix->find(f->segment_ord);
   for (auto &c : ps.fast) {
