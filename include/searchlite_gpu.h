@@ -293,6 +293,8 @@ int32_t slg_phrase_compile_batch(slg_index_t *, const uint32_t *term_ids, const 
 enum { SLG_COMBINE_AND = 0, SLG_COMBINE_OR = 1, SLG_COMBINE_AND_NOT = 2 };
 /* new filter id = a op b, per segment */
 int32_t slg_filter_combine(slg_index_t *, uint32_t op, int32_t a, int32_t b);
+/* n combinations in one launch per segment (a query batch's phrase-and-filter conjunctions): out_ids[i] = a[i] op b[i] */
+int32_t slg_filter_combine_batch(slg_index_t *, uint32_t op, const int32_t *a, const int32_t *b, uint32_t n, int32_t *out_ids);
 /* release the bitmaps of a filter / phrase id (ids are not reused; a batch naming a freed id is rejected) */
 int32_t slg_filter_free(slg_index_t *, int32_t filter_id);
 

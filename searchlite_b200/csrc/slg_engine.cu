@@ -1640,6 +1640,33 @@ int32_t slg_filter_bitmap(slg_index_t *ix, int32_t filter_id, uint32_t segment_o
   return SLG_OK;
 }
 
+// n consecutive filter ids whose bitmaps are rows of one slab per segment
+static int32_t register_slabs(slg_index *ix, std::vector<std::shared_ptr<DevBuf>> &slabs, const std::vector<uint64_t> &stride,
+                              uint32_t n, int32_t *out_ids) {
+  const size_t id0 = ix->filters.size();
+  for (size_t si = 0; si < ix->segs.size(); si++) {
+    Segment *s = ix->segs[si].get();
+    s->filter_bits.resize(id0 + n);
+    s->filter_slabs.resize(id0 + n);
+    for (uint32_t i = 0; i < n; i++) {
+      s->filter_bits[id0 + i].view(slabs[si]->as<uint32_t>() + (uint64_t)i * stride[si], stride[si] * 4);
+      s->filter_slabs[id0 + i] = slabs[si];
+    }
+    std::vector<const uint32_t *> ptrs;
+    for (auto &fb : s->filter_bits) ptrs.push_back(fb.as<uint32_t>());
+    if (s->filter_ptrs.bytes < ptrs.size() * sizeof(void *)) {
+      SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));  // a running batch may still read the old table
+      SLG_CUDA(ix, s->filter_ptrs.alloc(std::max<size_t>(64, ptrs.size() * 2) * sizeof(void *)));
+    }
+    SLG_CUDA(ix, cudaMemcpy(s->filter_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice));
+  }
+  for (uint32_t i = 0; i < n; i++) {
+    ix->filters.push_back(FilterProg{});
+    out_ids[i] = (int32_t)(id0 + i);
+  }
+  return SLG_OK;
+}
+
 /* ---- phrases (query/phrase.rs:4-48) and bitmap algebra ---- */
 int32_t slg_phrase_compile_batch(slg_index_t *ix, const uint32_t *term_ids, const uint32_t *phrase_offsets, const uint32_t *slops,
                                  uint32_t n_phrases, int32_t *out_ids) {
@@ -1701,27 +1728,7 @@ int32_t slg_phrase_compile_batch(slg_index_t *ix, const uint32_t *term_ids, cons
     }
   }
   SLG_CUDA(ix, cudaStreamSynchronize(st));
-  // ids: consecutive; every segment's entry is a view into its slab
-  const size_t id0 = ix->filters.size();
-  for (size_t si = 0; si < ix->segs.size(); si++) {
-    Segment *s = ix->segs[si].get();
-    s->filter_bits.resize(id0 + n_phrases);
-    s->filter_slabs.resize(id0 + n_phrases);
-    for (uint32_t i = 0; i < n_phrases; i++) {
-      s->filter_bits[id0 + i].view(slabs[si]->as<uint32_t>() + (uint64_t)i * stride[si], stride[si] * 4);
-      s->filter_slabs[id0 + i] = slabs[si];
-    }
-    std::vector<const uint32_t *> ptrs;
-    for (auto &fb : s->filter_bits) ptrs.push_back(fb.as<uint32_t>());
-    if (s->filter_ptrs.bytes < ptrs.size() * sizeof(void *))
-      SLG_CUDA(ix, s->filter_ptrs.alloc(std::max<size_t>(64, ptrs.size() * 2) * sizeof(void *)));
-    SLG_CUDA(ix, cudaMemcpy(s->filter_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice));
-  }
-  for (uint32_t i = 0; i < n_phrases; i++) {
-    ix->filters.push_back(FilterProg{});
-    out_ids[i] = (int32_t)(id0 + i);
-  }
-  return SLG_OK;
+  return register_slabs(ix, slabs, stride, n_phrases, out_ids);
 }
 
 int32_t slg_phrase_compile(slg_index_t *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop) {
@@ -1754,6 +1761,46 @@ int32_t slg_filter_combine(slg_index_t *ix, uint32_t op, int32_t a, int32_t b) {
   SLG_CUDA(ix, cudaGetLastError());
   SLG_CUDA(ix, cudaStreamSynchronize(st));
   return register_filter(ix, FilterProg{}, per_seg);
+}
+
+int32_t slg_filter_combine_batch(slg_index_t *ix, uint32_t op, const int32_t *a, const int32_t *b, uint32_t n, int32_t *out_ids) {
+  if (!ix || !a || !b || !n || !out_ids) return SLG_ERR_INVALID;
+  if (op > SLG_COMBINE_AND_NOT) return fail(ix, SLG_ERR_INVALID, "unknown combine op %u", op);
+  if (n > 65535) return fail(ix, SLG_ERR_UNSUPPORTED, "at most 65535 combinations per call");
+  if (ix->segs.empty()) return fail(ix, SLG_ERR_INVALID, "no segment loaded");
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  cudaStream_t st = ix->stream;
+  std::vector<std::shared_ptr<DevBuf>> slabs(ix->segs.size());
+  std::vector<uint64_t> stride(ix->segs.size());
+  for (size_t si = 0; si < ix->segs.size(); si++) {
+    Segment *s = ix->segs[si].get();
+    std::vector<const uint32_t *> pa(n), pb(n);
+    for (uint32_t i = 0; i < n; i++) {
+      for (int32_t f : {a[i], b[i]})
+        if (f < 0 || (size_t)f >= s->filter_bits.size() || !s->filter_bits[f].p)
+          return fail(ix, SLG_ERR_INVALID, "filter %d is freed or not compiled for segment %u", f, s->ord);
+      pa[i] = s->filter_bits[a[i]].as<uint32_t>();
+      pb[i] = s->filter_bits[b[i]].as<uint32_t>();
+    }
+    const uint32_t words = (s->doc_count + 31) / 32;
+    stride[si] = align_up(std::max<uint64_t>(words, 1), 32);
+    slabs[si] = std::make_shared<DevBuf>();
+    SLG_CUDA(ix, slabs[si]->alloc(stride[si] * 4 * n));
+    SLG_CUDA(ix, cudaMemsetAsync(slabs[si]->p, 0, stride[si] * 4 * n, st));
+    if (words) {
+      DevBuf d_a, d_b;
+      SLG_CUDA(ix, d_a.alloc(n * sizeof(void *)));
+      SLG_CUDA(ix, d_b.alloc(n * sizeof(void *)));
+      SLG_CUDA(ix, cudaMemcpyAsync(d_a.p, pa.data(), n * sizeof(void *), cudaMemcpyHostToDevice, st));
+      SLG_CUDA(ix, cudaMemcpyAsync(d_b.p, pb.data(), n * sizeof(void *), cudaMemcpyHostToDevice, st));
+      slg_bitmap_combine_batch_kernel<<<dim3((words + 255) / 256, n), 256, 0, st>>>(
+          d_a.as<const uint32_t *>(), d_b.as<const uint32_t *>(), words, op, slabs[si]->as<uint32_t>(), stride[si]);
+      count_launch(ix);
+      SLG_CUDA(ix, cudaGetLastError());
+      SLG_CUDA(ix, cudaStreamSynchronize(st));  // the host tables go out of scope
+    }
+  }
+  return register_slabs(ix, slabs, stride, n, out_ids);
 }
 
 int32_t slg_filter_free(slg_index_t *ix, int32_t filter_id) {

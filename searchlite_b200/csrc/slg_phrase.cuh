@@ -207,4 +207,14 @@ __global__ void slg_bitmap_combine_kernel(const uint32_t *a, const uint32_t *b, 
   out[w] = op == 0 ? (x & y) : (op == 1 ? (x | y) : (x & ~y));
 }
 
+// the same for n pairs in one launch: row i of `out` = a[i] op b[i]
+__global__ void slg_bitmap_combine_batch_kernel(const uint32_t *const *a, const uint32_t *const *b, uint32_t words, uint32_t op,
+                                                uint32_t *out, uint64_t row_words) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = blockIdx.y;
+  if (w >= words) return;
+  const uint32_t x = a[i][w], y = b[i][w];
+  out[(uint64_t)i * row_words + w] = op == 0 ? (x & y) : (op == 1 ? (x | y) : (x & ~y));
+}
+
 }  // namespace slg

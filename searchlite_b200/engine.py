@@ -102,7 +102,7 @@ EXPORTED_SYMBOLS = [
     "slg_get_counters", "slg_version", "slg_batch_copy_results_device", "slg_get_stream", "slg_selftest_div", "slg_batch_enable_stats",
     "slg_set_option", "slg_term_has_column",
     "slg_inspect_segment_files", "slg_load_segment_files", "slg_load_index_dir", "slg_load_vector_file", "slg_term_lookup",
-    "slg_column_lookup", "slg_field_stats", "slg_load_positions", "slg_phrase_compile", "slg_phrase_compile_batch", "slg_filter_combine", "slg_filter_free",
+    "slg_column_lookup", "slg_field_stats", "slg_load_positions", "slg_phrase_compile", "slg_phrase_compile_batch", "slg_filter_combine", "slg_filter_combine_batch", "slg_filter_free",
 ]
 
 
@@ -160,6 +160,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_phrase_compile": [vp, vp, u32, u32],
         "slg_phrase_compile_batch": [vp, vp, vp, vp, u32, vp],
         "slg_filter_combine": [vp, u32, i32, i32],
+        "slg_filter_combine_batch": [vp, u32, vp, vp, u32, vp],
         "slg_filter_free": [vp, i32],
     }
     for name, args in sigs.items():
@@ -531,6 +532,14 @@ class GpuIndex:
 
     def combine_filters(self, op: str, a: int, b: int) -> int:
         return self._check(self.lib.slg_filter_combine(self.handle, COMBINE[op], a, b))
+
+    def combine_filters_batch(self, op: str, a: Sequence[int], b: Sequence[int]) -> np.ndarray:
+        """out[i] = a[i] op b[i], one launch per segment"""
+        aa, bb = np.ascontiguousarray(a, dtype=np.int32), np.ascontiguousarray(b, dtype=np.int32)
+        assert len(aa) == len(bb)
+        out = np.zeros(len(aa), dtype=np.int32)
+        self._check(self.lib.slg_filter_combine_batch(self.handle, COMBINE[op], _ptr(aa), _ptr(bb), len(aa), _ptr(out)))
+        return out
 
     def free_filter(self, filter_id: int) -> None:
         self._check(self.lib.slg_filter_free(self.handle, filter_id))

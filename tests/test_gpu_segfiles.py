@@ -322,6 +322,11 @@ def test_phrase_query_search_and_bitmap_algebra(tmp_path):
     assert np.array_equal(gi.filter_bitmap(both, 0, n), a & b)
     assert np.array_equal(gi.filter_bitmap(either, 0, n), a | b)
     assert np.array_equal(gi.filter_bitmap(minus, 0, n), b & ~a)
+    for op, expect in (("and", a & b), ("or", a | b), ("and_not", b & ~a)):
+        x, y = (flt, ph) if op == "and_not" else (ph, flt)
+        out = gi.combine_filters_batch(op, [x, x, either], [y, y, either])
+        assert np.array_equal(gi.filter_bitmap(int(out[0]), 0, n), expect) and np.array_equal(gi.filter_bitmap(int(out[1]), 0, n), expect)
+        assert np.array_equal(gi.filter_bitmap(int(out[2]), 0, n), (a | b) if op != "and_not" else np.zeros_like(a))
     want_bm = slo.phrase_bitmap(n, sd.term_offsets, sd.post_docs, g_poff, g_pos, [t1, t2], 1) & b
     # query: w1 w2 w3 scored, phrase "w1 w2"~1 required
     qb = QueryBatch.from_term_lists([[t1, t2, t3], [t3], [t1, t2]])
@@ -431,3 +436,73 @@ def test_multi_field_keys_use_their_own_norms(index_dir):
         gi.load_index_dir(root, "body")
     for h in (gi, ga, gp):
         h.close()
+
+
+def test_full_size_c4_phrase_properties():
+    """BASELINE.json configs[3] (phrase = 2-term adjacent, slop 0) at full size: the 10 M-doc C2 corpus with resident
+    positions.  Size-independent checks: phrase bitmaps equal a restatement that uses neither postings nor positions
+    (the corpus is a pure function token(seed, doc, position), so "a at p and b at p+1" is recomputed from the generator),
+    slop 1 is a superset of slop 0, the reversed phrase differs, every hit of a phrase query lies in its bitmap and holds
+    both terms, pruned == exhaustive bytes."""
+    import torch
+    from searchlite_b200 import synth
+    dev = "cuda:0"
+    spec = synth.CorpusSpec(n_docs=10_000_000, vocab=1_000_000, seed=20260101)
+    seg = synth.generate_segment(spec, dev)
+    positions = synth.generate_positions(spec, dev)
+    pos_off = torch.zeros(seg.post_tfs.shape[0] + 1, dtype=torch.int64, device=dev)
+    pos_off[1:] = torch.cumsum(seg.post_tfs.to(torch.int64), 0)
+    assert int(pos_off[-1]) == positions.shape[0] == seg.total_tokens
+    torch.cuda.empty_cache()
+    gi = GpuIndex(0)
+    gi.load_segment(seg)
+    gi.load_positions(0, seg.term_offsets, pos_off, positions)
+    del seg, positions, pos_off
+    torch.cuda.empty_cache()
+    cdf = synth.zipf_cdf(spec.vocab, spec.zipf_s).to(dev)
+    rng = np.random.default_rng(20260105)
+    phrases = []
+    while len(phrases) < 12:
+        d = int(rng.integers(0, spec.n_docs))
+        term, valid = synth.token_terms(spec, d, d + 1, cdf, dev)
+        t = term[0][valid[0]].cpu().numpy()
+        p = int(rng.integers(0, len(t) - 1))
+        a, b = int(t[p]), int(t[p + 1])
+        if a >= 9 and b >= 9 and a != b:
+            phrases.append((a, b))
+    n = spec.n_docs
+    ids = gi.compile_phrases([[a, b] for a, b in phrases] + [[a, b] for a, b in phrases[:4]] + [[b, a] for a, b in phrases[:4]],
+                             [0] * 12 + [1] * 4 + [0] * 4)
+    n_check = 4
+    want = [torch.zeros(n, dtype=torch.bool, device=dev) for _ in range(n_check)]
+    has_both = [torch.zeros(n, dtype=torch.bool, device=dev) for _ in range(n_check)]
+    chunk = 1 << 18
+    for d0 in range(0, n, chunk):
+        d1 = min(n, d0 + chunk)
+        term, valid = synth.token_terms(spec, d0, d1, cdf, dev)
+        for i in range(n_check):
+            a, b = phrases[i]
+            want[i][d0:d1] = ((term[:, :-1] == a) & (term[:, 1:] == b) & valid[:, 1:]).any(dim=1)
+            has_both[i][d0:d1] = ((term == a) & valid).any(dim=1) & ((term == b) & valid).any(dim=1)
+        del term, valid
+    unpack = lambda bits: np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
+    for i in range(n_check):
+        got = unpack(gi.filter_bitmap(int(ids[i]), 0, n))
+        w = want[i].cpu().numpy()
+        assert w.any() and np.array_equal(got, w), (phrases[i], int(got.sum()), int(w.sum()))
+        sloppy = unpack(gi.filter_bitmap(int(ids[12 + i]), 0, n))
+        assert not (got & ~sloppy).any() and not (sloppy & ~has_both[i].cpu().numpy()).any()  # slop 0 within slop 1 within "holds both"
+        rev = unpack(gi.filter_bitmap(int(ids[16 + i]), 0, n))
+        assert not np.array_equal(rev, got)
+    qb = QueryBatch.from_term_lists([[a, b] for a, b in phrases])
+    qb.filter_id = np.asarray(ids[:12], dtype=np.int32)
+    h, c = gi.search_batch(qb, 11, "bm25")
+    hp, cp = gi.search_batch(qb, 11, "bmw")
+    assert h.tobytes() == hp.tobytes() and c.tobytes() == cp.tobytes()
+    assert c.min() >= 1
+    for i in range(n_check):
+        docs = torch.from_numpy(h[i, : c[i]]["doc_id"].astype(np.int64)).to(dev)
+        assert bool(want[i][docs].all())
+        sc = h[i, : c[i]]["score"]
+        assert np.all(sc[:-1] >= sc[1:])
+    gi.close()
