@@ -246,6 +246,12 @@ int32_t slg_load_segment_files(slg_index_t *, const slg_segment_files_t *files, 
  * vector_field (nullable): also load seg_<id>_vectors/<vector_field>.bin of every segment. */
 int32_t slg_load_index_dir(slg_index_t *, const char *dir, const char *field, float k1, float b, const char *vector_field,
                            int32_t store_bf16, uint32_t *n_segments_out);
+/* One process per GPU: load only the manifest segments with position % shard_world == shard_rank (segment == shard;
+ * N, df, avgdl are per segment in the reference, so no statistics cross GPUs).  segment_ord stays the manifest
+ * position; every rank resolves query keys against its own term space (slg_term_lookup) and the local top-k lists
+ * meet in slg_merge_gathered.  *n_segments_out = segments this rank loaded. */
+int32_t slg_load_index_dir_shard(slg_index_t *, const char *dir, const char *field, float k1, float b, const char *vector_field,
+                                 int32_t store_bf16, uint32_t shard_rank, uint32_t shard_world, uint32_t *n_segments_out);
 /* <field>.bin image ("VCTR", index/segment.rs:1030-1119) -> slg_load_vectors.  metric_out nullable: 0 cosine, 1 l2 */
 int32_t slg_load_vector_file(slg_index_t *, uint32_t segment_ord, const uint8_t *bytes, uint64_t n_bytes, int32_t store_bf16,
                              int32_t *metric_out);

@@ -1309,15 +1309,25 @@ std::string in_dir(const std::string &dir, const std::string &stored) {
 
 int32_t slg_load_index_dir(slg_index_t *ix, const char *dir, const char *field, float k1, float b, const char *vector_field,
                            int32_t store_bf16, uint32_t *n_segments_out) {
+  return slg_load_index_dir_shard(ix, dir, field, k1, b, vector_field, store_bf16, 0, 1, n_segments_out);
+}
+
+int32_t slg_load_index_dir_shard(slg_index_t *ix, const char *dir, const char *field, float k1, float b, const char *vector_field,
+                                 int32_t store_bf16, uint32_t shard_rank, uint32_t shard_world, uint32_t *n_segments_out) {
   if (!ix || !dir || !field) return SLG_ERR_INVALID;
+  if (shard_world == 0 || shard_rank >= shard_world) return fail(ix, SLG_ERR_INVALID, "shard %u of %u", shard_rank, shard_world);
   MappedFile man;
   const std::string d(dir);
   if (!man.open(d + "/MANIFEST.json")) return fail(ix, SLG_ERR_INVALID, "cannot read %s/MANIFEST.json", dir);
   slgf::Json root = slgf::json_root(man.data(), man.size());
   std::vector<slgf::Json> segs;
   if (!slgf::json_elements(slgf::json_get(root, "segments"), segs)) return fail(ix, SLG_ERR_INVALID, "manifest has no segments array");
-  uint32_t ord = 0;
+  uint32_t ord = 0, loaded = 0;
   for (auto &sm : segs) {  // IndexReader::open keeps manifest order; segment_ord is that index (api/reader.rs:2670)
+    if (ord % shard_world != shard_rank) {  // another GPU's segment (segment == shard)
+      ord++;
+      continue;
+    }
     slgf::Json paths = slgf::json_get(sm, "paths");
     MappedFile terms, post, fast, meta;
     const char *names[4] = {"terms", "postings", "fast", "meta"};
@@ -1362,8 +1372,9 @@ int32_t slg_load_index_dir(slg_index_t *ix, const char *dir, const char *field, 
       if ((rc = slg_load_vector_file(ix, ord, vb.data(), vb.size(), store_bf16, nullptr))) return rc;
     }
     ord++;
+    loaded++;
   }
-  if (n_segments_out) *n_segments_out = ord;
+  if (n_segments_out) *n_segments_out = loaded;
   return SLG_OK;
 }
 

@@ -101,7 +101,7 @@ EXPORTED_SYMBOLS = [
     "slg_batch_device_results", "slg_batch_free", "slg_merge_gathered", "slg_load_vectors", "slg_rerank",
     "slg_get_counters", "slg_version", "slg_batch_copy_results_device", "slg_get_stream", "slg_selftest_div", "slg_batch_enable_stats",
     "slg_set_option", "slg_term_has_column",
-    "slg_inspect_segment_files", "slg_load_segment_files", "slg_load_index_dir", "slg_load_vector_file", "slg_term_lookup",
+    "slg_inspect_segment_files", "slg_load_segment_files", "slg_load_index_dir", "slg_load_index_dir_shard", "slg_load_vector_file", "slg_term_lookup",
     "slg_column_lookup", "slg_field_stats", "slg_load_positions", "slg_phrase_compile", "slg_phrase_compile_batch", "slg_filter_combine", "slg_filter_combine_batch", "slg_filter_free",
 ]
 
@@ -152,6 +152,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_inspect_segment_files": [C.POINTER(SegmentFiles), C.c_char_p, C.POINTER(SegmentInfo), C.c_char_p, u64],
         "slg_load_segment_files": [vp, C.POINTER(SegmentFiles), C.c_char_p, f32, f32],
         "slg_load_index_dir": [vp, C.c_char_p, C.c_char_p, f32, f32, C.c_char_p, i32, C.POINTER(u32)],
+        "slg_load_index_dir_shard": [vp, C.c_char_p, C.c_char_p, f32, f32, C.c_char_p, i32, u32, u32, C.POINTER(u32)],
         "slg_load_vector_file": [vp, u32, vp, u64, i32, C.POINTER(i32)],
         "slg_term_lookup": [vp, C.c_char_p, C.POINTER(u32)],
         "slg_column_lookup": [vp, C.c_char_p],
@@ -484,11 +485,13 @@ class GpuIndex:
         del keep
 
     def load_index_dir(self, path: str, field: str, k1: float = 0.9, b: float = 0.4, vector_field: Optional[str] = None,
-                       store_bf16: bool = False) -> int:
-        """Every segment of an index directory in MANIFEST.json order; returns the segment count."""
+                       store_bf16: bool = False, shard_rank: int = 0, shard_world: int = 1) -> int:
+        """Every segment of an index directory in MANIFEST.json order (or, one process per GPU, the segments with
+        position % shard_world == shard_rank); returns the number of segments loaded."""
         n = C.c_uint32()
         vf = vector_field.encode() if vector_field else None
-        self._check(self.lib.slg_load_index_dir(self.handle, path.encode(), field.encode(), k1, b, vf, int(store_bf16), C.byref(n)))
+        self._check(self.lib.slg_load_index_dir_shard(self.handle, path.encode(), field.encode(), k1, b, vf, int(store_bf16),
+                                                      shard_rank, shard_world, C.byref(n)))
         return n.value
 
     def term_lookup(self, key: str) -> int:

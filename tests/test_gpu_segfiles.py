@@ -144,6 +144,36 @@ def test_index_dir_load_equals_csr_load_and_oracle(index_dir):
         h.close()
 
 
+def test_sharded_index_dir_equals_whole(index_dir):
+    """one process per GPU loads the manifest segments of its rank (segment == shard); the merged local lists equal the
+    single-handle result — term ids differ per handle, keys are resolved by each"""
+    root, segs = index_dir
+    from oracle import slo
+    whole = GpuIndex(0, kernel="warp")
+    assert whole.load_index_dir(root, "body") == 2
+    parts = []
+    for r in range(2):
+        g = GpuIndex(0, kernel="warp")
+        assert g.load_index_dir(root, "body", shard_rank=r, shard_world=2) == 1
+        parts.append(g)
+    keys_all = sorted({k for s in segs for k in s.postings() if k.startswith("body:")})
+    rng = np.random.default_rng(14)
+    qkeys = [[keys_all[i] for i in rng.choice(len(keys_all), size=int(rng.integers(1, 5)), replace=False)] for _ in range(50)]
+    batch = lambda g: QueryBatch.from_term_lists([[g.term_lookup(k) for k in q] for q in qkeys])
+    wh, wc = whole.search_batch(batch(whole), 11, "bm25")
+    per = [g.search_batch(batch(g), 11, "bm25") for g in parts]
+    assert set(np.unique(per[1][0]["segment_ord"][per[1][1] > 0][:, 0]).tolist()) <= {1}
+    for q in range(len(qkeys)):
+        want = slo.merge_hits([h[q, : c[q]] for h, c in per], 11)
+        g = wh[q, : wc[q]]
+        assert len(g) == len(want) and np.array_equal(g["segment_ord"], want["segment_ord"]) and np.array_equal(g["doc_id"], want["doc_id"])
+        assert np.array_equal(g["score"].view(np.uint32), want["score"].view(np.uint32))
+    with pytest.raises(SearchliteGpuError, match="shard"):
+        GpuIndex(0).load_index_dir(root, "body", shard_rank=2, shard_world=2)
+    for h in [whole] + parts:
+        h.close()
+
+
 def test_file_columns_filter_like_the_oracle(index_dir):
     root, segs = index_dir
     from oracle import slo
