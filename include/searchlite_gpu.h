@@ -62,14 +62,32 @@ typedef struct {
   uint32_t flags;   /* SLG_TERM_SCORED if it contributes to the score */
 } slg_term_t;
 
+/* ScorePlan (query/planner.rs:113-164): the ScoreExpr tree in POSTFIX order, evaluated per doc on the
+ * per-leaf sums `leaves[term.leaf] += score_tf(..)` of query/wand.rs:470-497 (terms added in listed order):
+ *   LEAF   arg = leaf index                      -> leaves[arg]                      (planner.rs:134)
+ *   SUM    arg = number of children              -> ((0 + c0) + c1) + ..             (planner.rs:135)
+ *   DISMAX arg = number of children, tie_breaker -> max + tie_breaker * (sum - max)  (planner.rs:136-151)
+ * tie_breaker must lie in [0, 1] (validate_tie_breaker, planner.rs:850-858).  Every leaf of a scored
+ * term must be read by the plan (the planner guarantees it, planner.rs:284-460). */
+enum { SLG_PLAN_LEAF = 0, SLG_PLAN_SUM = 1, SLG_PLAN_DISMAX = 2 };
+#define SLG_MAX_PLAN_LEAVES 8u
+#define SLG_MAX_PLAN_NODES 32u
+typedef struct {
+  uint32_t op;
+  uint32_t arg;
+  float tie_breaker;
+} slg_plan_node_t;
+
 typedef struct {
   uint32_t n_terms;
   const slg_term_t *terms;
   uint32_t n_groups;         /* 0 = plain OR of the scored terms (QueryString, min_should 1) */
   const uint8_t *group_role; /* n_groups entries */
   uint32_t min_should;       /* resolved minimum_should_match */
-  uint32_t leaf_count;       /* informational; the plan is Sum of leaves */
+  uint32_t leaf_count;       /* number of ScorePlan leaves when `plan` is given (1..SLG_MAX_PLAN_LEAVES) */
   int32_t filter_id;         /* root filter from slg_filter_compile, -1 = none */
+  uint32_t n_plan_nodes;     /* 0 = no plan: the score is the running sum of the terms in listed order */
+  const slg_plan_node_t *plan; /* n_plan_nodes postfix nodes leaving exactly one value */
 } slg_query_t;
 
 /* RankedHit as merged by SortKey: score desc, segment_ord asc, doc_id asc */

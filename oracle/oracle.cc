@@ -641,8 +641,46 @@ struct SearchCtx {
 
 /* ---------------------------------------------------------------- execution */
 
-// query/wand.rs:459-566 brute_force (hash-map accumulation; leaf buffers when a ScorePlan is given;
-// the plan is Sum-of-leaves, query/planner.rs:354-360)
+// ScorePlan::evaluate, query/planner.rs:133-164, on the postfix form of the ScoreExpr tree.  Without
+// plan nodes the plan is Sum of all leaves (QueryString, query/planner.rs:354-360).
+float evaluate_plan(const slo_query_t *q, const std::vector<float> &leaves) {
+  if (!q->n_plan_nodes) {
+    float score = 0.0f;
+    for (float l : leaves) score += l;  // ScoreExpr::Sum, query/planner.rs:135
+    return score;
+  }
+  std::vector<float> st;
+  for (uint32_t i = 0; i < q->n_plan_nodes; i++) {
+    const slo_plan_node_t &n = q->plan[i];
+    if (n.op == SLO_PLAN_LEAF) {
+      st.push_back(n.arg < leaves.size() ? leaves[n.arg] : 0.0f);  // leaves.get(idx).unwrap_or(0.0), :134
+      continue;
+    }
+    size_t c = std::min<size_t>(n.arg, st.size());
+    size_t base = st.size() - c;
+    float r;
+    if (n.op == SLO_PLAN_SUM) {
+      r = 0.0f;
+      for (size_t j = base; j < st.size(); j++) r += st[j];
+    } else {  // DisMax, :136-151
+      if (c == 0) {
+        r = 0.0f;
+      } else {
+        float mx = -INFINITY, sum = 0.0f;
+        for (size_t j = base; j < st.size(); j++) {
+          mx = std::fmax(mx, st[j]);
+          sum += st[j];
+        }
+        r = mx + n.tie_breaker * (sum - mx);
+      }
+    }
+    st.resize(base);
+    st.push_back(r);
+  }
+  return st.empty() ? 0.0f : st.back();
+}
+
+// query/wand.rs:459-566 brute_force (hash-map accumulation; leaf buffers when a ScorePlan is given)
 std::vector<RankedDoc> brute_force(const std::vector<ScoredTerm> &terms, size_t k, uint32_t leaf_count,
                                    const SearchCtx &cx) {
   TopHeap heap{RankedLe{}};
@@ -665,8 +703,7 @@ std::vector<RankedDoc> brute_force(const std::vector<ScoredTerm> &terms, size_t 
       cx.stats->candidates_examined += scores.size();
     }
     for (auto &kv : scores) {
-      float score = 0.0f;
-      for (float l : kv.second) score += l;  // ScoreExpr::Sum, query/planner.rs:134
+      float score = evaluate_plan(cx.q, kv.second);  // plan.evaluate(&leaves), query/wand.rs:506
       if (!cx.accept(kv.first)) continue;
       push_top_k(heap, RankedDoc{kv.first, score}, k);
     }
@@ -799,8 +836,7 @@ std::vector<RankedDoc> wand_loop(std::vector<TermState> &states, size_t k, bool 
       }
       float score = score_sum;
       if (leaf_count) {
-        score = 0.0f;
-        for (float l : leaf_scores) score += l;
+        score = evaluate_plan(cx.q, leaf_scores);
         std::fill(leaf_scores.begin(), leaf_scores.end(), 0.0f);
       }
       if (cx.accept(doc_id)) {
@@ -1118,6 +1154,13 @@ int slo_max_threads(void) {
 
 // api/reader.rs:2777 hits.sort_by(SortKey) with query/sort.rs:80-136 for the `_score` desc plan:
 // score desc by total_cmp, then segment_ord asc, then doc_id asc; truncate to limit (:2838-2851).
+float slo_plan_evaluate(const slo_plan_node_t *plan, uint32_t n_nodes, const float *leaves, uint32_t n_leaves) {
+  slo_query_t q{};
+  q.plan = plan;
+  q.n_plan_nodes = n_nodes;
+  return evaluate_plan(&q, std::vector<float>(leaves, leaves + n_leaves));
+}
+
 uint32_t slo_merge_hits(const slo_hit_t *hits, uint32_t n, uint32_t limit, slo_hit_t *out) {
   std::vector<slo_hit_t> v(hits, hits + n);
   std::stable_sort(v.begin(), v.end(), [](const slo_hit_t &a, const slo_hit_t &b) {

@@ -50,6 +50,15 @@ typedef struct {
   uint32_t flags;   /* SLO_TERM_SCORED if it contributes to the score */
 } slo_term_t;
 
+/* ScoreExpr (query/planner.rs:113-153) flattened to postfix: LEAF arg = leaf index;
+ * SUM / DISMAX arg = number of children (the values on top of the evaluation stack). */
+enum { SLO_PLAN_LEAF = 0, SLO_PLAN_SUM = 1, SLO_PLAN_DISMAX = 2 };
+typedef struct {
+  uint32_t op;
+  uint32_t arg;
+  float tie_breaker;
+} slo_plan_node_t;
+
 typedef struct {
   uint32_t n_terms;
   const slo_term_t *terms;
@@ -58,6 +67,8 @@ typedef struct {
   uint32_t min_should;       /* resolved minimum_should_match */
   uint32_t leaf_count;       /* 0 => score_plan None: plain running sum */
   int32_t filter_id;         /* unused here (the root filter is a call argument); keeps the layout of slg_query_t */
+  uint32_t n_plan_nodes;     /* 0 with leaf_count > 0 => Sum of leaves (query/planner.rs:354-360) */
+  const slo_plan_node_t *plan; /* ScoreExpr in postfix order, query/planner.rs:113-153 */
 } slo_query_t;
 
 /* Filter AST, api/types.rs:670-680, evaluated as query/filters.rs:84-149.  Prefix
@@ -162,6 +173,9 @@ int32_t slo_search_batch(const slo_index_t *, const slo_query_t *qs, uint32_t n_
 
 /* merge per-segment hit lists as api/reader.rs:2777 (SortKey: score desc total_cmp, segment_ord asc,
  * doc_id asc, query/sort.rs:80-93) and truncate to limit. Returns count. */
+/* ScorePlan::evaluate (query/planner.rs:133-164) on a postfix plan and explicit leaf scores */
+float slo_plan_evaluate(const slo_plan_node_t *plan, uint32_t n_nodes, const float *leaves, uint32_t n_leaves);
+
 uint32_t slo_merge_hits(const slo_hit_t *hits, uint32_t n, uint32_t limit, slo_hit_t *out);
 
 /* evaluate the root filter for every doc into a bitmap (1 bit/doc, LSB first) — checker for the filter kernel */

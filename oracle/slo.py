@@ -59,6 +59,8 @@ def lib() -> C.CDLL:
     L.slo_postings_encode.restype = sz
     L.slo_postings_peek_df.argtypes = [vp, sz, C.POINTER(u32), C.POINTER(u32)]
     L.slo_postings_decode.argtypes = [vp, sz, C.c_int, vp, vp, C.POINTER(f32), C.POINTER(u32), vp, vp, C.POINTER(u32), C.POINTER(sz)]
+    L.slo_plan_evaluate.argtypes = [vp, u32, vp, u32]
+    L.slo_plan_evaluate.restype = f32
     L.slo_index_new.argtypes = [u32, u32, f32, f32]
     L.slo_index_new.restype = vp
     L.slo_index_free.argtypes = [vp]

@@ -232,6 +232,9 @@ struct slg_batch {
   bool staged = false;
   uint32_t max_terms = 0;
   bool use_warp = false, use_reg = false;
+  bool has_plan = false;     // some query carries a ScorePlan: CTA-per-item kernel with per-leaf accumulator planes
+  uint32_t max_leaves = 1;
+  size_t off_qt_leaf = 0, off_q_leaves = 0, off_q_plan_off = 0, off_plan_nodes = 0;
   uint32_t plan_docs = 0, reg_v = 8;
   uint32_t n_heavy = 0, n_light = 0;  // sweep: slots [0, n_heavy) of q_order are swept, the rest go to the warp kernel
   uint32_t n_rows = 0, n_light_u = 0; // rows of the sweep's range table; unique terms of the light queries
@@ -581,17 +584,17 @@ int32_t to_device(slg_index *ix, const T *src, size_t n, int space, DevBuf &tmp,
 
 // --------------------------------------------------------------------------------------------
 // search
-int32_t select_smem(slg_index *ix, uint32_t tile_docs, uint32_t cap, bool matcher, size_t *out) {
-  size_t smem = (size_t)tile_docs * 4 + (size_t)cap * 8 + (matcher ? tile_docs : 0);
+int32_t select_smem(slg_index *ix, uint32_t tile_docs, uint32_t cap, bool matcher, size_t *out, uint32_t planes = 1) {
+  size_t smem = (size_t)tile_docs * 4 * planes + (size_t)cap * 8 + (matcher ? tile_docs : 0);
   if (smem + 1024 > ix->smem_optin)
     return fail(ix, SLG_ERR_UNSUPPORTED, "tile of %u docs with k buffer %u needs %zu B shared memory", tile_docs, cap, smem);
   *out = smem;
   return SLG_OK;
 }
 
-template <bool M, bool P, bool S>
+template <bool M, bool P, bool S, bool PL = false>
 int32_t launch_score_t(slg_index *ix, const SegmentDev &sd, const BatchDev &bd, size_t smem, int grid) {
-  auto kern = slg_score_tiles_kernel<M, P, S>;
+  auto kern = slg_score_tiles_kernel<M, P, S, PL>;
   SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kThreads, smem, ix->stream>>>(sd, bd);
   SLG_CUDA(ix, cudaGetLastError());
@@ -599,8 +602,20 @@ int32_t launch_score_t(slg_index *ix, const SegmentDev &sd, const BatchDev &bd, 
 }
 
 int32_t launch_score(slg_index *ix, bool matcher, bool prune, bool stats, const SegmentDev &sd, const BatchDev &bd,
-                     size_t smem, int grid) {
+                     size_t smem, int grid, bool plan = false) {
   int sel = (matcher ? 4 : 0) | (prune ? 2 : 0) | (stats ? 1 : 0);
+  if (plan) {  // ScorePlan batches: the matcher form serves both (plain OR queries carry an empty group program)
+    switch (sel & 3) {
+      case 0: return matcher ? launch_score_t<true, false, false, true>(ix, sd, bd, smem, grid)
+                             : launch_score_t<false, false, false, true>(ix, sd, bd, smem, grid);
+      case 1: return matcher ? launch_score_t<true, false, true, true>(ix, sd, bd, smem, grid)
+                             : launch_score_t<false, false, true, true>(ix, sd, bd, smem, grid);
+      case 2: return matcher ? launch_score_t<true, true, false, true>(ix, sd, bd, smem, grid)
+                             : launch_score_t<false, true, false, true>(ix, sd, bd, smem, grid);
+      default: return matcher ? launch_score_t<true, true, true, true>(ix, sd, bd, smem, grid)
+                              : launch_score_t<false, true, true, true>(ix, sd, bd, smem, grid);
+    }
+  }
   switch (sel) {
     case 0: return launch_score_t<false, false, false>(ix, sd, bd, smem, grid);
     case 1: return launch_score_t<false, false, true>(ix, sd, bd, smem, grid);
@@ -1858,6 +1873,9 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   std::vector<uint8_t> qt_g, qt_f, q_must(n_queries, 0), q_not(n_queries, 0), q_should(n_queries, 0), q_min(n_queries, 0);
   std::vector<int32_t> q_filter(n_queries, -1);
   std::vector<uint64_t> q_cost(n_queries, 0);
+  std::vector<uint8_t> qt_leaf, q_leaves(n_queries, 0);
+  std::vector<uint32_t> q_plan_off(n_queries + 1, 0);
+  std::vector<PlanNodeDev> plan_nodes;
   q_off.assign(n_queries + 1, 0);
   bool matcher = false;
   for (uint32_t qi = 0; qi < n_queries; qi++) {
@@ -1867,6 +1885,35 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
     if (q.n_groups && !q.group_role) return fail(ix, SLG_ERR_INVALID, "query %u has no group roles", qi);
     if (q.filter_id >= (int32_t)ix->filters.size()) return fail(ix, SLG_ERR_INVALID, "query %u names unknown filter %d", qi, q.filter_id);
     q_filter[qi] = q.filter_id < 0 ? -1 : q.filter_id;
+    if (q.n_plan_nodes) {
+      // ScorePlan: a well-formed postfix program over leaves 0..leaf_count-1 (query/planner.rs:113-164)
+      if (!q.plan) return fail(ix, SLG_ERR_INVALID, "query %u has no plan pointer", qi);
+      if (q.leaf_count == 0 || q.leaf_count > SLG_MAX_PLAN_LEAVES)
+        return fail(ix, SLG_ERR_UNSUPPORTED, "query %u: a plan needs 1..%u leaves, got %u", qi, SLG_MAX_PLAN_LEAVES, q.leaf_count);
+      if (q.n_plan_nodes > SLG_MAX_PLAN_NODES)
+        return fail(ix, SLG_ERR_UNSUPPORTED, "query %u: plan of %u nodes; the maximum is %u", qi, q.n_plan_nodes, SLG_MAX_PLAN_NODES);
+      uint32_t depth = 0;
+      for (uint32_t n = 0; n < q.n_plan_nodes; n++) {
+        const slg_plan_node_t &pn = q.plan[n];
+        if (pn.op == SLG_PLAN_LEAF) {
+          if (pn.arg >= q.leaf_count) return fail(ix, SLG_ERR_INVALID, "query %u plan node %u: leaf %u out of range", qi, n, pn.arg);
+          depth++;
+        } else if (pn.op == SLG_PLAN_SUM || pn.op == SLG_PLAN_DISMAX) {
+          if (pn.arg > depth) return fail(ix, SLG_ERR_INVALID, "query %u plan node %u: %u children but %u values", qi, n, pn.arg, depth);
+          if (pn.op == SLG_PLAN_DISMAX && !(pn.tie_breaker >= 0.0f && pn.tie_breaker <= 1.0f))
+            return fail(ix, SLG_ERR_INVALID, "query %u plan node %u: tie_breaker must lie in [0, 1]", qi, n);  // planner.rs:850-858
+          depth = depth - pn.arg + 1;
+        } else {
+          return fail(ix, SLG_ERR_INVALID, "query %u plan node %u: unknown op %u", qi, n, pn.op);
+        }
+        plan_nodes.push_back(PlanNodeDev{pn.op, pn.arg, pn.tie_breaker});
+      }
+      if (depth != 1) return fail(ix, SLG_ERR_INVALID, "query %u: the plan leaves %u values instead of one", qi, depth);
+      q_leaves[qi] = (uint8_t)q.leaf_count;
+      bt->has_plan = true;
+      bt->max_leaves = std::max(bt->max_leaves, q.leaf_count);
+    }
+    q_plan_off[qi + 1] = (uint32_t)plan_nodes.size();
     if (q.filter_id >= 0)
       for (auto &sg : ix->segs)
         if ((size_t)q.filter_id >= sg->filter_bits.size() || !sg->filter_bits[q.filter_id].p)
@@ -1880,6 +1927,8 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
       if (scored && !(tm.weight > 0.0f && std::isfinite(tm.weight)))
         return fail(ix, SLG_ERR_UNSUPPORTED, "query %u term %u: weight must be finite and > 0", qi, t);
       if (q.n_groups && tm.group >= q.n_groups) return fail(ix, SLG_ERR_INVALID, "query %u term %u: group out of range", qi, t);
+      if (scored && q.n_plan_nodes && tm.leaf >= q.leaf_count)
+        return fail(ix, SLG_ERR_INVALID, "query %u term %u: leaf %u but the plan has %u leaves", qi, t, tm.leaf, q.leaf_count);  // wand.rs:489-494
       if (!scored) need_mask = true;
       auto it = umap.find(tm.term_id);
       uint32_t u;
@@ -1894,6 +1943,7 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
       qt_w.push_back(tm.weight);
       qt_g.push_back((uint8_t)(q.n_groups ? tm.group : 0));
       qt_f.push_back(scored ? 1 : 0);
+      qt_leaf.push_back((uint8_t)(scored && q.n_plan_nodes ? tm.leaf : 0));
       if (scored && tm.term_id < s0->n_terms) q_cost[qi] += s0->h_df[tm.term_id];
       kept++;
     }
@@ -1927,12 +1977,14 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   for (auto &s : ix->segs) sweepable = sweepable && (s->post_pair.p != nullptr || s->n_blocks == 0);
   // tile-sweep kernel: plain OR queries (no matcher), small k, few terms, resident scores
   // column front end: plain OR queries (no matcher), small k, few terms, resident scores and columns
-  bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && sweepable);
+  if (bt->has_plan && ix->kernel_choice >= 2)
+    return fail(ix, SLG_ERR_UNSUPPORTED, "ScorePlan queries run on the CTA-per-item kernel (kernel_choice 0 or 1)");
+  bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && sweepable && !bt->has_plan);
   if (bt->use_reg && !(small && !matcher && sweepable))
     return fail(ix, SLG_ERR_UNSUPPORTED,
                 "the sweep kernel handles plain OR queries, k <= %u, <= %u terms per query, resident scores, < 2^32 postings per segment",
                 kWarpMaxK, kWarpMaxTerms);
-  bt->use_warp = !bt->use_reg && (ix->kernel_choice == 2 || (ix->kernel_choice == 0 && small));
+  bt->use_warp = !bt->use_reg && (ix->kernel_choice == 2 || (ix->kernel_choice == 0 && small && !bt->has_plan));
   if (bt->use_warp && !small)
     return fail(ix, SLG_ERR_UNSUPPORTED, "the warp kernel handles k <= %u and <= %u terms per query", kWarpMaxK, kWarpMaxTerms);
 
@@ -1997,6 +2049,12 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bt->off_q_should = place(n_queries);
   bt->off_q_min = place(n_queries);
   bt->off_q_filter = place((size_t)n_queries * 4);
+  if (bt->has_plan) {
+    bt->off_qt_leaf = place(bt->T);
+    bt->off_q_leaves = place(n_queries);
+    bt->off_q_plan_off = place((size_t)(n_queries + 1) * 4);
+    bt->off_plan_nodes = place(plan_nodes.size() * sizeof(PlanNodeDev));
+  }
   bt->h_pack.assign(pos, 0);
   unsigned char *hp = bt->h_pack.data();
   auto put = [&](size_t off, const void *src, size_t bytes) {
@@ -2014,11 +2072,23 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   put(bt->off_q_should, q_should.data(), n_queries);
   put(bt->off_q_min, q_min.data(), n_queries);
   put(bt->off_q_filter, q_filter.data(), (size_t)n_queries * 4);
+  if (bt->has_plan) {
+    put(bt->off_qt_leaf, qt_leaf.data(), bt->T);
+    put(bt->off_q_leaves, q_leaves.data(), n_queries);
+    put(bt->off_q_plan_off, q_plan_off.data(), (size_t)(n_queries + 1) * 4);
+    put(bt->off_plan_nodes, plan_nodes.data(), plan_nodes.size() * sizeof(PlanNodeDev));
+  }
   SLG_CUDA(ix, bt->d_pack.alloc(pos));
   SLG_CUDA(ix, cudaMemcpyAsync(bt->d_pack.p, hp, pos, cudaMemcpyHostToDevice, ix->stream));
   ix->ctr.last_h2d_bytes = pos;
 
   bt->plan_docs = bt->use_reg ? ix->sub_docs : (bt->use_warp ? ix->sub_docs : ix->tile_docs);
+  if (bt->has_plan) {
+    // one accumulator plane per leaf: shrink the doc tile so that the planes together stay near the configured tile
+    uint32_t planes = 1;
+    while (planes < bt->max_leaves) planes <<= 1;
+    bt->plan_docs = std::max(1024u, (ix->tile_docs / planes) & ~1023u);
+  }
   const uint32_t plan_docs = bt->plan_docs;
   uint32_t max_tiles = 0;
   for (auto &s : ix->segs) max_tiles = std::max(max_tiles, (s->doc_count + plan_docs - 1) / plan_docs);
@@ -2142,7 +2212,8 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
   const uint32_t Q = bt->Q, k = bt->k;
   unsigned char *dp = bt->d_pack.as<unsigned char>();
   size_t smem = 0;
-  int32_t rc = select_smem(ix, ix->tile_docs, bt->cap, bt->matcher, &smem);
+  int32_t rc = bt->has_plan ? select_smem(ix, bt->plan_docs, bt->cap, bt->matcher, &smem, bt->max_leaves)
+                            : select_smem(ix, ix->tile_docs, bt->cap, bt->matcher, &smem);
   if (rc) return rc;
   uint32_t per_sm = (uint32_t)std::max<size_t>(1, (ix->smem_optin + 1024) / (smem + 1024));
   per_sm = std::min(per_sm, 8u);
@@ -2168,6 +2239,13 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
     bd.q_min_should = dp + bt->off_q_min;
     bd.q_filter = reinterpret_cast<const int32_t *>(dp + bt->off_q_filter);
     bd.filter_bits = reinterpret_cast<const uint32_t *const *>(s->filter_ptrs.p);
+    if (bt->has_plan) {
+      bd.qt_leaf = dp + bt->off_qt_leaf;
+      bd.q_leaves = dp + bt->off_q_leaves;
+      bd.q_plan_off = reinterpret_cast<const uint32_t *>(dp + bt->off_q_plan_off);
+      bd.plan_nodes = reinterpret_cast<const PlanNodeDev *>(dp + bt->off_plan_nodes);
+    }
+    bd.max_leaves = bt->max_leaves;
     bd.n_queries = Q;
     bd.n_uterms = bt->U;
     bd.k = k;
@@ -2328,7 +2406,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         if (!bt->use_reg || !bt->n_heavy) ix->ctr.score_launches++;
       } else if (!bt->use_reg && !bt->use_warp) {
         int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * per_sm, (uint64_t)bd.n_tiles * Q);
-        rc = launch_score(ix, bt->matcher, prune, bt->want_stats, s->dev, bd, smem, grid);
+        rc = launch_score(ix, bt->matcher, prune, bt->want_stats, s->dev, bd, smem, grid, bt->has_plan);
         if (rc) return rc;
         count_launch(ix);
         ix->ctr.score_launches++;

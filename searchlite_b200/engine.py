@@ -32,9 +32,26 @@ TERM_DTYPE = np.dtype(
     {"names": ["term_id", "weight", "leaf", "group", "flags"],
      "formats": ["<u4", "<f4", "<u4", "<u4", "<u4"], "itemsize": 20})
 QUERY_DTYPE = np.dtype(
-    {"names": ["n_terms", "terms", "n_groups", "group_role", "min_should", "leaf_count", "filter_id"],
-     "formats": ["<u4", "<u8", "<u4", "<u8", "<u4", "<u4", "<i4"],
-     "offsets": [0, 8, 16, 24, 32, 36, 40], "itemsize": 48})
+    {"names": ["n_terms", "terms", "n_groups", "group_role", "min_should", "leaf_count", "filter_id", "n_plan_nodes", "plan"],
+     "formats": ["<u4", "<u8", "<u4", "<u8", "<u4", "<u4", "<i4", "<u4", "<u8"],
+     "offsets": [0, 8, 16, 24, 32, 36, 40, 44, 48], "itemsize": 56})
+PLAN_DTYPE = np.dtype({"names": ["op", "arg", "tie_breaker"], "formats": ["<u4", "<u4", "<f4"], "itemsize": 12})
+PLAN_LEAF, PLAN_SUM, PLAN_DISMAX = 0, 1, 2
+
+
+def plan_postfix(expr) -> list:
+    """ScoreExpr (query/planner.rs:113-122) -> postfix slg_plan_node_t rows.  expr is
+    ("leaf", i) | ("sum", [children]) | ("dismax", [children], tie_breaker)."""
+    if expr[0] == "leaf":
+        return [(PLAN_LEAF, int(expr[1]), 0.0)]
+    rows = []
+    for c in expr[1]:
+        rows += plan_postfix(c)
+    if expr[0] == "sum":
+        return rows + [(PLAN_SUM, len(expr[1]), 0.0)]
+    if expr[0] == "dismax":
+        return rows + [(PLAN_DISMAX, len(expr[1]), float(expr[2]))]
+    raise ValueError(f"unknown score expression {expr[0]!r}")
 HIT_DTYPE = np.dtype({"names": ["segment_ord", "doc_id", "score"], "formats": ["<u4", "<u4", "<f4"], "itemsize": 12})
 STATS_DTYPE = np.dtype(
     {"names": ["scored_docs", "postings_advanced", "blocks_skipped", "candidates_examined"],
@@ -261,7 +278,25 @@ class QueryBatch:
     group_role: Optional[np.ndarray] = None  # u8 [G]
     min_should: Optional[np.ndarray] = None  # u32 [Q]
     filter_id: Optional[np.ndarray] = None   # i32 [Q]
+    plan_off: Optional[np.ndarray] = None    # [Q+1] into plan_nodes (ScorePlan per query; empty = running sum)
+    plan_nodes: Optional[np.ndarray] = None  # PLAN_DTYPE
+    leaf_count: Optional[np.ndarray] = None  # u32 [Q]
     _structs: Optional[np.ndarray] = None
+
+    def set_plans(self, exprs: Sequence) -> "QueryBatch":
+        """attach one ScoreExpr per query (None = no plan); leaf_count = 1 + the largest leaf of the query's terms"""
+        off, rows, leaves = [0], [], []
+        for qi, e in enumerate(exprs):
+            if e is not None:
+                rows += plan_postfix(e)
+            off.append(len(rows))
+            t = self.terms[int(self.term_off[qi]):int(self.term_off[qi + 1])]
+            leaves.append(0 if e is None else (int(t["leaf"].max()) + 1 if len(t) else 1))
+        self.plan_off = np.array(off, dtype=np.int64)
+        self.plan_nodes = np.array(rows, dtype=PLAN_DTYPE) if rows else np.zeros(0, dtype=PLAN_DTYPE)
+        self.leaf_count = np.array(leaves, dtype=np.uint32)
+        self._structs = None
+        return self
 
     @property
     def n_queries(self) -> int:
@@ -328,6 +363,12 @@ class QueryBatch:
             s["min_should"] = 1
         s["leaf_count"] = 0
         s["filter_id"] = -1 if self.filter_id is None else self.filter_id
+        if self.plan_off is not None:
+            self.plan_nodes = np.ascontiguousarray(self.plan_nodes)
+            n = (self.plan_off[1:] - self.plan_off[:-1]).astype(np.uint32)
+            s["n_plan_nodes"] = n
+            s["plan"] = np.where(n > 0, self.plan_nodes.ctypes.data + self.plan_off[:-1].astype(np.uint64) * np.uint64(PLAN_DTYPE.itemsize), 0)
+            s["leaf_count"] = self.leaf_count
         self._structs = s
         return s
 
@@ -341,6 +382,11 @@ class QueryBatch:
             qb.min_should = self.min_should[lo:hi].copy()
         if self.filter_id is not None:
             qb.filter_id = self.filter_id[lo:hi].copy()
+        if self.plan_off is not None:
+            p0, p1 = int(self.plan_off[lo]), int(self.plan_off[hi])
+            qb.plan_off = self.plan_off[lo:hi + 1] - p0
+            qb.plan_nodes = self.plan_nodes[p0:p1].copy()
+            qb.leaf_count = self.leaf_count[lo:hi].copy()
         return qb
 
 

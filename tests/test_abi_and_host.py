@@ -63,7 +63,8 @@ def test_null_arguments_are_errors_not_crashes(lib):
 def test_struct_layouts_match_the_header():
     # sizes the C compiler gives the header's structs (x86-64 SysV)
     assert engine.TERM_DTYPE.itemsize == 20
-    assert engine.QUERY_DTYPE.itemsize == 48
+    assert engine.QUERY_DTYPE.itemsize == 56
+    assert engine.PLAN_DTYPE.itemsize == 12
     assert engine.HIT_DTYPE.itemsize == 12
     assert engine.STATS_DTYPE.itemsize == 32
     assert engine.FILTER_DTYPE.itemsize == 56
@@ -72,9 +73,9 @@ def test_struct_layouts_match_the_header():
     src = r'''
     #include "include/searchlite_gpu.h"
     #include <stdio.h>
-    int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(slg_term_t), sizeof(slg_query_t), sizeof(slg_hit_t),
+    int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(slg_term_t), sizeof(slg_query_t), sizeof(slg_hit_t),
       sizeof(slg_stats_t), sizeof(slg_filter_node_t), sizeof(slg_segment_view_t), sizeof(slg_counters_t),
-      sizeof(slg_segment_files_t), sizeof(slg_segment_info_t));return 0;}
+      sizeof(slg_segment_files_t), sizeof(slg_segment_info_t), sizeof(slg_plan_node_t));return 0;}
     '''
     import subprocess
     import tempfile
@@ -84,7 +85,7 @@ def test_struct_layouts_match_the_header():
         exe = os.path.join(td, "s")
         subprocess.run(["gcc", "-std=c99", "-I", ROOT, "-o", exe, c], check=True, cwd=ROOT)  # the header is plain C
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [20, 48, 12, 32, 56, 80, 72, C.sizeof(engine.SegmentFiles), C.sizeof(engine.SegmentInfo)]
+    assert sizes == [20, 56, 12, 32, 56, 80, 72, C.sizeof(engine.SegmentFiles), C.sizeof(engine.SegmentInfo), 12]
 
 
 def test_query_batch_builders():
@@ -98,6 +99,13 @@ def test_query_batch_builders():
     assert bq.min_should.tolist() == [0, 1, 0]                        # api/reader.rs:1553-1561 defaults
     sub = bq.subset(1, 3)
     assert sub.n_queries == 2 and sub.terms["term_id"].tolist() == [9, 9] and sub.filter_id.tolist() == [-1, 0]
+    # ScorePlans: postfix rows of the ScoreExpr tree (query/planner.rs:113-122)
+    expr = ("sum", [("dismax", [("leaf", 0), ("leaf", 1)], 0.25), ("leaf", 2)])
+    assert engine.plan_postfix(expr) == [(0, 0, 0.0), (0, 1, 0.0), (2, 2, 0.25), (0, 2, 0.0), (1, 2, 0.0)]
+    pq = engine.QueryBatch.from_term_lists([[3, 5, 6], [7]]).set_plans([expr, None])
+    ps = pq.structs()
+    assert ps["n_plan_nodes"].tolist() == [5, 0] and ps["leaf_count"].tolist() == [3, 0] and ps["plan"][1] == 0
+    assert pq.subset(0, 1).structs()["n_plan_nodes"].tolist() == [5]
 
 
 def test_shard_ranges_cover_the_corpus():

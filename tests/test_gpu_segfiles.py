@@ -536,3 +536,73 @@ def test_full_size_c4_phrase_properties():
         sc = h[i, : c[i]]["score"]
         assert np.all(sc[:-1] >= sc[1:])
     gi.close()
+
+
+def test_multi_match_best_fields_score_plan(index_dir):
+    """MultiMatch best_fields over [body, title] (query/planner.rs:381-404): every query term has one key per field, all
+    keys of a field add into that field's leaf (query/wand.rs:470-497), the score is DisMax(tie_breaker) over the field
+    leaves (planner.rs:136-151).  Expected: per-key scores from single-field oracles, leaves folded in term order, the
+    plan evaluated by the oracle's evaluator; segments merged by (score desc, segment, doc)."""
+    root, segs = index_dir
+    from oracle import slo
+    from searchlite_b200.engine import PLAN_DTYPE, plan_postfix
+    gi = GpuIndex(0)
+    assert gi.load_index_dir(root, "body,title") == 2
+    per_field = {}
+    for si, s in enumerate(segs):
+        for field in ("body", "title"):
+            keys, toff, docs, tfs, poff, pos, lens = sw.csr_of(s, field)
+            sd = SegmentData(si, len(s.docs), toff, docs, tfs, lens, int(lens.sum()),
+                             deleted_docs=np.asarray(s.deleted, dtype=np.uint32) if s.deleted else None)
+            per_field[(si, field)] = (keys, slo.OracleIndex(sd))
+    cache = {}
+
+    def key_scores(si, key):
+        if (si, key) not in cache:
+            keys, o = per_field[(si, key.split(":")[0])]
+            if key not in keys:
+                cache[(si, key)] = {}
+            else:
+                h, c = o.search_batch(QueryBatch.from_term_lists([[keys.index(key)]]), len(segs[si].docs) + 1, "bm25")
+                cache[(si, key)] = {int(x["doc_id"]): np.float32(x["score"]) for x in h[0, : c[0]]}
+        return cache[(si, key)]
+
+    rng = np.random.default_rng(21)
+    queries, exprs = [], []
+    for qi in range(30):
+        toks = rng.choice(np.arange(1, 60), size=int(rng.integers(1, 4)), replace=False)
+        queries.append([f"{f}:w{int(t)}" for t in toks for f in ("body", "title")])
+        exprs.append(("dismax", [("leaf", 0), ("leaf", 1)], float(rng.choice([0.0, 0.3, 1.0]))))
+    qb = QueryBatch.from_term_lists([[gi.term_lookup(k) for k in q] for q in queries])
+    qb.terms["leaf"] = np.concatenate([[0 if k.startswith("body:") else 1 for k in q] for q in queries]).astype(np.uint32)
+    qb.set_plans(exprs)
+    qb.leaf_count[:] = 2
+    qb._structs = None
+    k = 11
+    L = slo.lib()
+    base = None
+    for exe in ("bm25", "bmw"):
+        got_h, got_c = gi.search_batch(qb, k, exe)
+        if base is None:
+            base = (got_h.tobytes(), got_c.tobytes())
+        else:
+            assert (got_h.tobytes(), got_c.tobytes()) == base
+        for qi, q in enumerate(queries):
+            nodes = np.array(plan_postfix(exprs[qi]), dtype=PLAN_DTYPE)
+            rows = []
+            for si in range(len(segs)):
+                leaves = {}
+                for key in q:
+                    leaf = 0 if key.startswith("body:") else 1
+                    for d, sc in key_scores(si, key).items():
+                        buf = leaves.setdefault(d, np.zeros(2, dtype=np.float32))
+                        buf[leaf] = np.float32(buf[leaf] + sc)
+                for d, buf in leaves.items():
+                    sc = np.float32(L.slo_plan_evaluate(nodes.ctypes.data, len(nodes), buf.ctypes.data, 2))
+                    rows.append((-float(sc), si, d, sc))
+            rows.sort(key=lambda r: (r[0], r[1], r[2]))
+            want = rows[:k]
+            g = got_h[qi, : got_c[qi]]
+            assert [(int(x["segment_ord"]), int(x["doc_id"])) for x in g] == [(r[1], r[2]) for r in want], (exe, qi, q)
+            assert g["score"].view(np.uint32).tolist() == [int(np.float32(r[3]).view(np.uint32)) for r in want], (exe, qi)
+    gi.close()
