@@ -62,6 +62,13 @@ typedef struct {
   uint32_t flags;   /* SLG_TERM_SCORED if it contributes to the score */
 } slg_term_t;
 
+/* RankedHit as merged by SortKey: score desc, segment_ord asc, doc_id asc */
+typedef struct {
+  uint32_t segment_ord;
+  uint32_t doc_id;
+  float score;
+} slg_hit_t;
+
 /* ScorePlan (query/planner.rs:113-164): the ScoreExpr tree in POSTFIX order, evaluated per doc on the
  * per-leaf sums `leaves[term.leaf] += score_tf(..)` of query/wand.rs:470-497 (terms added in listed order):
  *   LEAF   arg = leaf index                      -> leaves[arg]                      (planner.rs:134)
@@ -88,14 +95,12 @@ typedef struct {
   int32_t filter_id;         /* root filter from slg_filter_compile, -1 = none */
   uint32_t n_plan_nodes;     /* 0 = no plan: the score is the running sum of the terms in listed order */
   const slg_plan_node_t *plan; /* n_plan_nodes postfix nodes leaving exactly one value */
+  /* search-after cursor (SearchRequest.cursor, api/reader.rs:3019-3028): with has_cursor != 0 a doc is accepted only
+   * if its SortKey (score desc, segment_ord asc, doc_id asc; query/sort.rs:80-93) is strictly after `cursor`; the doc
+   * whose key equals the cursor is rejected and reported by slg_batch_cursor_seen (saw_cursor, api/reader.rs:2747). */
+  uint32_t has_cursor;
+  slg_hit_t cursor;
 } slg_query_t;
-
-/* RankedHit as merged by SortKey: score desc, segment_ord asc, doc_id asc */
-typedef struct {
-  uint32_t segment_ord;
-  uint32_t doc_id;
-  float score;
-} slg_hit_t;
 
 /* QueryStats, src/query/wand.rs:45-50 (+ pruning counters the example prints, examples/pruning.rs:198-203) */
 typedef struct {
@@ -345,7 +350,19 @@ int32_t slg_batch_device_results(slg_batch_t *, void **dev_hits, void **dev_coun
 /* device->device copy of the last run's results into caller buffers (e.g. the send buffer of an
  * allgather), asynchronous on the handle's stream */
 int32_t slg_batch_copy_results_device(slg_batch_t *, void *dst_dev_hits, void *dst_dev_counts);
+/* saw_cursor per query after slg_batch_run: 1 if the doc named by the query's cursor was met (and rejected) by accept.
+ * The reference fails the request with "stale or invalid cursor for this result set" when it was not (api/reader.rs:2747-2749).
+ * Queries without a cursor report 1 (api/reader.rs:2663). */
+int32_t slg_batch_cursor_seen(slg_batch_t *, uint8_t *out_seen);
 int32_t slg_batch_free(slg_batch_t *);
+
+/* PaginationCursor of the score-sorted fast path (api/reader.rs:614-691): 21 bytes — version 1, generation, score bits,
+ * segment_ord, doc_id, returned, all big-endian — as 42 lowercase hex characters.  encode writes 43 bytes (NUL included).
+ * decode checks length, hex digits, version, returned <= 50000 (MAX_CURSOR_ADVANCE, :55) and the manifest generation
+ * (decode_cursor, :821-841) and writes the reference's message into err on failure (returns SLG_ERR_INVALID). */
+int32_t slg_cursor_encode(uint32_t generation, uint32_t returned, const slg_hit_t *last_hit, char *out43);
+int32_t slg_cursor_decode(const char *raw, uint32_t manifest_generation, slg_hit_t *key, uint32_t *returned, char *err,
+                          uint64_t err_len);
 
 /* ---- shard merge (api/reader.rs:2777): gathered is n_shards x n_queries x k hits (DEVICE memory),
  * counts n_shards x n_queries (DEVICE).  Writes n_queries x k merged hits / counts to HOST buffers. */

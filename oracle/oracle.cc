@@ -626,13 +626,23 @@ struct SearchCtx {
   uint32_t n_filter;
   const char *const *strings;
   slo_stats_t *stats;
-  // accept closure api/reader.rs:3009-3036 (cursor / collector branches are not on this path)
-  bool accept(uint32_t doc) const {
+  // accept closure api/reader.rs:3009-3036 (the collector branch is not on this path)
+  bool accept(uint32_t doc, float score) const {
     if (doc < ix->deleted.size() && ix->deleted[doc]) return false;
     if (!matcher->matches(doc)) return false;
     if (filter && n_filter) {
       uint32_t pos = 0;
       if (!filter_eval(ix, doc, filter, n_filter, pos, strings)) return false;
+    }
+    if (q->has_cursor) {
+      // key.cmp(cur) for the `_score` desc plan, query/sort.rs:80-93: score desc (total_cmp), segment_ord asc, doc_id asc
+      int ord = total_cmp(q->cursor_score, score);
+      if (ord == 0) ord = ix->segment_ord < q->cursor_segment_ord ? -1 : (ix->segment_ord > q->cursor_segment_ord ? 1 : 0);
+      if (ord == 0) ord = doc < q->cursor_doc_id ? -1 : (doc > q->cursor_doc_id ? 1 : 0);
+      if (ord <= 0) {  // at or before the cursor: rejected (:3021-3027)
+        if (ord == 0 && stats) stats->saw_cursor = 1;
+        return false;
+      }
     }
     if (stats) stats->total_matches += 1;
     return true;
@@ -704,7 +714,7 @@ std::vector<RankedDoc> brute_force(const std::vector<ScoredTerm> &terms, size_t 
     }
     for (auto &kv : scores) {
       float score = evaluate_plan(cx.q, kv.second);  // plan.evaluate(&leaves), query/wand.rs:506
-      if (!cx.accept(kv.first)) continue;
+      if (!cx.accept(kv.first, score)) continue;
       push_top_k(heap, RankedDoc{kv.first, score}, k);
     }
     return finalize_heap(heap);
@@ -725,7 +735,7 @@ std::vector<RankedDoc> brute_force(const std::vector<ScoredTerm> &terms, size_t 
     cx.stats->candidates_examined += scores.size();
   }
   for (auto &kv : scores) {
-    if (!cx.accept(kv.first)) continue;
+    if (!cx.accept(kv.first, kv.second)) continue;
     push_top_k(heap, RankedDoc{kv.first, kv.second}, k);
   }
   return finalize_heap(heap);
@@ -765,7 +775,7 @@ std::vector<RankedDoc> brute_force_dense(const std::vector<ScoredTerm> &terms, s
       if (!touched[d]) continue;
       touched[d] = 0;
       float s = acc[d];
-      if (!cx.accept(d)) continue;
+      if (!cx.accept(d, s)) continue;
       push_top_k(heap, RankedDoc{d, s}, k);
     }
   return finalize_heap(heap);
@@ -839,7 +849,7 @@ std::vector<RankedDoc> wand_loop(std::vector<TermState> &states, size_t k, bool 
         score = evaluate_plan(cx.q, leaf_scores);
         std::fill(leaf_scores.begin(), leaf_scores.end(), 0.0f);
       }
-      if (cx.accept(doc_id)) {
+      if (cx.accept(doc_id, score)) {
         if (rank_hits && (heap.size() < k || score > heap_threshold)) push_top_k(heap, RankedDoc{doc_id, score}, k);
       }
     } else {

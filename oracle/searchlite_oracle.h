@@ -69,6 +69,9 @@ typedef struct {
   int32_t filter_id;         /* unused here (the root filter is a call argument); keeps the layout of slg_query_t */
   uint32_t n_plan_nodes;     /* 0 with leaf_count > 0 => Sum of leaves (query/planner.rs:354-360) */
   const slo_plan_node_t *plan; /* ScoreExpr in postfix order, query/planner.rs:113-153 */
+  uint32_t has_cursor;       /* search-after cursor, api/reader.rs:3019-3028 */
+  uint32_t cursor_segment_ord, cursor_doc_id;
+  float cursor_score;
 } slo_query_t;
 
 /* Filter AST, api/types.rs:670-680, evaluated as query/filters.rs:84-149.  Prefix
@@ -104,6 +107,7 @@ typedef struct {
   uint64_t candidates_examined;
   uint64_t postings_advanced;
   uint64_t total_matches;
+  uint64_t saw_cursor;       /* the cursor's own doc was met by accept (api/reader.rs:3022-3024) */
 } slo_stats_t;
 
 /* ---- scalar arithmetic (query/bm25.rs:1-6, query/wand.rs:269-303) ---- */

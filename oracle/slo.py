@@ -17,8 +17,8 @@ LIB_PATH = os.path.join(HERE, "libslo_oracle.so")
 EXEC = {"bm25": 0, "wand": 1, "bmw": 2, "bm25_dense": 3}
 
 HIT_DTYPE = np.dtype({"names": ["segment_ord", "doc_id", "score"], "formats": ["<u4", "<u4", "<f4"], "itemsize": 12})
-STATS_DTYPE = np.dtype({"names": ["scored_docs", "candidates_examined", "postings_advanced", "total_matches"],
-                        "formats": ["<u8"] * 4, "itemsize": 32})
+STATS_DTYPE = np.dtype({"names": ["scored_docs", "candidates_examined", "postings_advanced", "total_matches", "saw_cursor"],
+                        "formats": ["<u8"] * 5, "itemsize": 40})
 
 FILTER_DTYPE = np.dtype(
     {"names": ["op", "column", "i_min", "i_max", "f_min", "f_max", "n_children", "value_begin", "value_end"],

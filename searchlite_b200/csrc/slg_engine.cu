@@ -232,6 +232,11 @@ struct slg_batch {
   bool staged = false;
   uint32_t max_terms = 0;
   bool use_warp = false, use_reg = false;
+  bool has_cursor = false;   // some query carries a search-after cursor
+  std::vector<uint8_t> h_has_cursor;
+  DevBuf cursor_bounds;      // u64 [n_segs][Q]: exclusive upper key bound per segment
+  DevBuf cursor_saw;         // u32 [Q]
+  uint32_t n_cursor_segs = 0;
   bool has_plan = false;     // some query carries a ScorePlan: CTA-per-item kernel with per-leaf accumulator planes
   uint32_t max_leaves = 1;
   size_t off_qt_leaf = 0, off_q_leaves = 0, off_q_plan_off = 0, off_plan_nodes = 0;
@@ -1914,6 +1919,11 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
       bt->max_leaves = std::max(bt->max_leaves, q.leaf_count);
     }
     q_plan_off[qi + 1] = (uint32_t)plan_nodes.size();
+    if (q.has_cursor) {
+      if (!(q.cursor.score >= 0.0f) || !std::isfinite(q.cursor.score))
+        return fail(ix, SLG_ERR_INVALID, "query %u: the cursor score must be finite and >= 0", qi);
+      bt->has_cursor = true;
+    }
     if (q.filter_id >= 0)
       for (auto &sg : ix->segs)
         if ((size_t)q.filter_id >= sg->filter_bits.size() || !sg->filter_bits[q.filter_id].p)
@@ -1966,6 +1976,35 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
     }
     bt->posting_count += q_cost[qi];
   }
+  if (bt->has_cursor) {
+    if (ix->kernel_choice == 3 && ix->heavy_kernel == 1)
+      return fail(ix, SLG_ERR_UNSUPPORTED, "cursors are not handled by the tile-sweep kernel (heavy_kernel 1)");
+    // key.cmp(cursor) (query/sort.rs:80-93: score desc, segment_ord asc, doc_id asc) folded into one exclusive bound on
+    // the 64-bit keys of each segment: same segment (score, ~doc); an earlier segment loses ties; a later one wins them
+    const uint32_t n_segs = (uint32_t)ix->segs.size();
+    std::vector<unsigned long long> bounds((size_t)n_segs * n_queries, ~0ull);
+    bt->h_has_cursor.assign(n_queries, 0);
+    for (uint32_t qi = 0; qi < n_queries; qi++) {
+      const slg_query_t &q = queries[qi];
+      if (!q.has_cursor) continue;
+      bt->h_has_cursor[qi] = 1;
+      uint32_t sb;
+      std::memcpy(&sb, &q.cursor.score, 4);
+      for (uint32_t si = 0; si < n_segs; si++) {
+        const uint32_t ord = ix->segs[si]->ord;
+        unsigned long long b;
+        if (ord == q.cursor.segment_ord) b = ((unsigned long long)sb << 32) | (unsigned long long)(0xFFFFFFFFu - q.cursor.doc_id);
+        else if (ord < q.cursor.segment_ord) b = (unsigned long long)sb << 32;
+        else b = ((unsigned long long)sb + 1ull) << 32;
+        bounds[(size_t)si * n_queries + qi] = b;
+      }
+    }
+    bt->n_cursor_segs = n_segs;
+    SLG_CUDA(ix, bt->cursor_bounds.alloc(bounds.size() * 8));
+    SLG_CUDA(ix, bt->cursor_saw.alloc((size_t)n_queries * 4));
+    SLG_CUDA(ix, cudaMemcpyAsync(bt->cursor_bounds.p, bounds.data(), bounds.size() * 8, cudaMemcpyHostToDevice, ix->stream));
+    SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));  // bounds is a local
+  }
   bt->matcher = matcher;
   bt->U = (uint32_t)ut.size();
   bt->T = (uint32_t)qt_u.size();
@@ -2002,7 +2041,7 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
     uint64_t max_docs = 0;
     for (auto &sg : ix->segs) max_docs = std::max<uint64_t>(max_docs, sg->doc_count);
     bt->warp_cols = ix->sub_docs <= 4096;
-    for (uint32_t qi = 0; qi < n_queries && ix->heavy_kernel == 1; qi++) {
+    for (uint32_t qi = 0; qi < n_queries && ix->heavy_kernel == 1 && !bt->has_cursor; qi++) {
       bool h = q_cost[qi] >= (ix->sweep_min_postings ? ix->sweep_min_postings : std::max<uint64_t>(1, max_docs / 64));
       for (uint32_t t = q_off[qi]; t < q_off[qi + 1] && !h; t++) h = u_col[qt_u[t]] != 0;
       heavy[qi] = h;
@@ -2220,6 +2259,10 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
   if (ix->ctas_per_sm) per_sm = std::min(per_sm, ix->ctas_per_sm);
   SLG_CUDA(ix, cudaEventRecord(ix->ev[0], st));
   SLG_CUDA(ix, cudaMemsetAsync(bt->stats.p, 0, (size_t)Q * 32, st));
+  if (bt->has_cursor) {
+    if (bt->n_cursor_segs != ix->segs.size()) return fail(ix, SLG_ERR_INVALID, "a segment was loaded after the batch with cursors was prepared");
+    SLG_CUDA(ix, cudaMemsetAsync(bt->cursor_saw.p, 0, (size_t)Q * 4, st));
+  }
   uint32_t si = 0;
   for (auto &sp : ix->segs) {
     Segment *s = sp.get();
@@ -2246,6 +2289,10 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
       bd.plan_nodes = reinterpret_cast<const PlanNodeDev *>(dp + bt->off_plan_nodes);
     }
     bd.max_leaves = bt->max_leaves;
+    if (bt->has_cursor) {
+      bd.q_cursor = bt->cursor_bounds.as<unsigned long long>() + (size_t)si * Q;
+      bd.q_saw = bt->cursor_saw.as<uint32_t>();
+    }
     bd.n_queries = Q;
     bd.n_uterms = bt->U;
     bd.k = k;
@@ -2393,6 +2440,8 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         wb.topk_keys = bd.topk_keys;
         wb.work_counter = bd.work_counter;
         wb.stats = bd.stats;
+        wb.q_cursor = bd.q_cursor;
+        wb.q_saw = bd.q_saw;
         const int warps = kThreads / 32;
         size_t wsmem = (size_t)warps * warp_kernel_smem_per_warp(ix->sub_docs, bt->matcher, prune);
         if (wsmem + 1024 > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "sub_docs %u needs %zu B shared memory", ix->sub_docs, wsmem);
@@ -2506,6 +2555,76 @@ int32_t slg_batch_copy_results_device(slg_batch_t *bt, void *dst_hits, void *dst
   slg_batch_device_results(bt, &dh, &dc);
   SLG_CUDA(ix, cudaMemcpyAsync(dst_hits, dh, (size_t)bt->Q * bt->k * sizeof(HitDev), cudaMemcpyDeviceToDevice, ix->stream));
   SLG_CUDA(ix, cudaMemcpyAsync(dst_counts, dc, (size_t)bt->Q * 4, cudaMemcpyDeviceToDevice, ix->stream));
+  return SLG_OK;
+}
+
+int32_t slg_batch_cursor_seen(slg_batch_t *bt, uint8_t *out_seen) {
+  if (!bt || !out_seen) return SLG_ERR_INVALID;
+  slg_index *ix = bt->ix;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  for (uint32_t q = 0; q < bt->Q; q++) out_seen[q] = 1;  // no cursor: saw_cursor starts true (api/reader.rs:2663)
+  if (!bt->has_cursor) return SLG_OK;
+  std::vector<uint32_t> saw(bt->Q);
+  SLG_CUDA(ix, cudaMemcpyAsync(saw.data(), bt->cursor_saw.p, (size_t)bt->Q * 4, cudaMemcpyDeviceToHost, ix->stream));
+  SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));
+  for (uint32_t q = 0; q < bt->Q; q++)
+    if (bt->h_has_cursor[q]) out_seen[q] = saw[q] ? 1 : 0;
+  return SLG_OK;
+}
+
+// PaginationCursor::encode / decode, api/reader.rs:630-691, and the generation check of decode_cursor, :821-841
+int32_t slg_cursor_encode(uint32_t generation, uint32_t returned, const slg_hit_t *last_hit, char *out43) {
+  if (!last_hit || !out43) return SLG_ERR_INVALID;
+  uint32_t sb;
+  std::memcpy(&sb, &last_hit->score, 4);
+  unsigned char buf[21];
+  buf[0] = 1;  // CURSOR_VERSION
+  const uint32_t words[5] = {generation, sb, last_hit->segment_ord, last_hit->doc_id, returned};
+  for (int w = 0; w < 5; w++)
+    for (int b = 0; b < 4; b++) buf[1 + w * 4 + b] = (unsigned char)(words[w] >> (24 - 8 * b));
+  static const char HEX[] = "0123456789abcdef";
+  for (int i = 0; i < 21; i++) {
+    out43[2 * i] = HEX[buf[i] >> 4];
+    out43[2 * i + 1] = HEX[buf[i] & 15];
+  }
+  out43[42] = 0;
+  return SLG_OK;
+}
+
+int32_t slg_cursor_decode(const char *raw, uint32_t manifest_generation, slg_hit_t *key, uint32_t *returned, char *err,
+                          uint64_t err_len) {
+  auto bail = [&](const char *fmt, auto... a) {
+    if (err && err_len) std::snprintf(err, (size_t)err_len, fmt, a...);
+    return (int32_t)SLG_ERR_INVALID;
+  };
+  if (!raw || !key || !returned) return bail("%s", "null argument");
+  const size_t len = std::strlen(raw);
+  if (len != 42) return bail("invalid cursor length: expected 42 hex chars, got %zu", len);
+  unsigned char bytes[21];
+  for (int i = 0; i < 21; i++) {
+    int v = 0;
+    for (int h = 0; h < 2; h++) {
+      const char c = raw[2 * i + h];
+      int d;
+      if (c >= '0' && c <= '9') d = c - '0';
+      else if (c >= 'a' && c <= 'f') d = c - 'a' + 10;
+      else if (c >= 'A' && c <= 'F') d = c - 'A' + 10;  // u8::from_str_radix accepts both cases
+      else return bail("decoding cursor at byte index %d", i);
+      v = v * 16 + d;
+    }
+    bytes[i] = (unsigned char)v;
+  }
+  if (bytes[0] != 1) return bail("unsupported cursor version %u", (unsigned)bytes[0]);
+  uint32_t words[5];
+  for (int w = 0; w < 5; w++)
+    words[w] = ((uint32_t)bytes[1 + w * 4] << 24) | ((uint32_t)bytes[2 + w * 4] << 16) | ((uint32_t)bytes[3 + w * 4] << 8) | bytes[4 + w * 4];
+  if (words[4] > 50000u) return bail("cursor requests %u hits, which exceeds max supported 50000", words[4]);
+  if (words[0] != manifest_generation)
+    return bail("stale cursor for this index generation: expected %u, got %u", manifest_generation, words[0]);
+  std::memcpy(&key->score, &words[1], 4);
+  key->segment_ord = words[2];
+  key->doc_id = words[3];
+  *returned = words[4];
   return SLG_OK;
 }
 

@@ -67,6 +67,8 @@ struct WarpBatchDev {
   unsigned long long *topk_keys;
   uint32_t *work_counter;
   unsigned long long *stats;
+  const unsigned long long *q_cursor;  // as in BatchDev
+  uint32_t *q_saw;
 };
 
 // resolve the batch's query terms against one segment (runs once per segment per batch)
@@ -491,6 +493,7 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
         bool pass = have && key > thr;
         if (pass) pass = (seg.live_bits[doc >> 5] >> (doc & 31)) & 1u;
         if (pass && head.filter >= 0) pass = (wb.filter_bits[head.filter][doc >> 5] >> (doc & 31)) & 1u;
+        if (pass) pass = cursor_accepts(wb.q_cursor, wb.q_saw, head.qi, key);
         push_keys(pass, key);
       };
       // every parked doc (at most 64): read them all before the first push may reuse the buffer
@@ -543,6 +546,7 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
                 pass = ((mm & must) == must) && ((mm & nots) == 0u) && (__popc(mm & should) >= (int)(masks >> 24));
               }
               if (pass && head.filter >= 0) pass = (wb.filter_bits[head.filter][doc >> 5] >> (doc & 31)) & 1u;
+              if (pass) pass = cursor_accepts(wb.q_cursor, wb.q_saw, head.qi, key);
               push_keys(pass, key);
             }
           }

@@ -32,9 +32,10 @@ TERM_DTYPE = np.dtype(
     {"names": ["term_id", "weight", "leaf", "group", "flags"],
      "formats": ["<u4", "<f4", "<u4", "<u4", "<u4"], "itemsize": 20})
 QUERY_DTYPE = np.dtype(
-    {"names": ["n_terms", "terms", "n_groups", "group_role", "min_should", "leaf_count", "filter_id", "n_plan_nodes", "plan"],
-     "formats": ["<u4", "<u8", "<u4", "<u8", "<u4", "<u4", "<i4", "<u4", "<u8"],
-     "offsets": [0, 8, 16, 24, 32, 36, 40, 44, 48], "itemsize": 56})
+    {"names": ["n_terms", "terms", "n_groups", "group_role", "min_should", "leaf_count", "filter_id", "n_plan_nodes", "plan",
+               "has_cursor", "cursor_segment_ord", "cursor_doc_id", "cursor_score"],
+     "formats": ["<u4", "<u8", "<u4", "<u8", "<u4", "<u4", "<i4", "<u4", "<u8", "<u4", "<u4", "<u4", "<f4"],
+     "offsets": [0, 8, 16, 24, 32, 36, 40, 44, 48, 56, 60, 64, 68], "itemsize": 72})
 PLAN_DTYPE = np.dtype({"names": ["op", "arg", "tie_breaker"], "formats": ["<u4", "<u4", "<f4"], "itemsize": 12})
 PLAN_LEAF, PLAN_SUM, PLAN_DISMAX = 0, 1, 2
 
@@ -120,6 +121,7 @@ EXPORTED_SYMBOLS = [
     "slg_set_option", "slg_term_has_column",
     "slg_inspect_segment_files", "slg_load_segment_files", "slg_load_index_dir", "slg_load_index_dir_shard", "slg_load_vector_file", "slg_term_lookup",
     "slg_column_lookup", "slg_field_stats", "slg_load_positions", "slg_phrase_compile", "slg_phrase_compile_batch", "slg_filter_combine", "slg_filter_combine_batch", "slg_filter_free",
+    "slg_batch_cursor_seen", "slg_cursor_encode", "slg_cursor_decode",
 ]
 
 
@@ -156,6 +158,9 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_batch_fetch": [vp, vp, vp, vp],
         "slg_batch_device_results": [vp, C.POINTER(vp), C.POINTER(vp)],
         "slg_batch_free": [vp],
+        "slg_batch_cursor_seen": [vp, vp],
+        "slg_cursor_encode": [u32, u32, vp, C.c_char_p],
+        "slg_cursor_decode": [C.c_char_p, u32, vp, C.POINTER(u32), C.c_char_p, u64],
         "slg_merge_gathered": [vp, vp, vp, u32, u32, u32, vp, vp],
         "slg_load_vectors": [vp, u32, u32, vp, vp, u64, i32],
         "slg_rerank": [vp, vp, u32, u32, vp, vp, u32, f32, i32, vp, vp],
@@ -281,7 +286,20 @@ class QueryBatch:
     plan_off: Optional[np.ndarray] = None    # [Q+1] into plan_nodes (ScorePlan per query; empty = running sum)
     plan_nodes: Optional[np.ndarray] = None  # PLAN_DTYPE
     leaf_count: Optional[np.ndarray] = None  # u32 [Q]
+    cursor: Optional[np.ndarray] = None      # HIT_DTYPE [Q]: search-after keys (SearchRequest.cursor)
+    has_cursor: Optional[np.ndarray] = None  # u8 [Q]
     _structs: Optional[np.ndarray] = None
+
+    def set_cursors(self, cursors: Sequence) -> "QueryBatch":
+        """one (segment_ord, doc_id, score) triple or HIT_DTYPE row per query; None = no cursor"""
+        self.cursor = np.zeros(self.n_queries, dtype=HIT_DTYPE)
+        self.has_cursor = np.zeros(self.n_queries, dtype=np.uint8)
+        for qi, c in enumerate(cursors):
+            if c is not None:
+                self.cursor[qi] = (int(c[0]), int(c[1]), np.float32(c[2]))
+                self.has_cursor[qi] = 1
+        self._structs = None
+        return self
 
     def set_plans(self, exprs: Sequence) -> "QueryBatch":
         """attach one ScoreExpr per query (None = no plan); leaf_count = 1 + the largest leaf of the query's terms"""
@@ -369,6 +387,11 @@ class QueryBatch:
             s["n_plan_nodes"] = n
             s["plan"] = np.where(n > 0, self.plan_nodes.ctypes.data + self.plan_off[:-1].astype(np.uint64) * np.uint64(PLAN_DTYPE.itemsize), 0)
             s["leaf_count"] = self.leaf_count
+        if self.cursor is not None:
+            s["has_cursor"] = self.has_cursor
+            s["cursor_segment_ord"] = self.cursor["segment_ord"]
+            s["cursor_doc_id"] = self.cursor["doc_id"]
+            s["cursor_score"] = self.cursor["score"]
         self._structs = s
         return s
 
@@ -387,6 +410,9 @@ class QueryBatch:
             qb.plan_off = self.plan_off[lo:hi + 1] - p0
             qb.plan_nodes = self.plan_nodes[p0:p1].copy()
             qb.leaf_count = self.leaf_count[lo:hi].copy()
+        if self.cursor is not None:
+            qb.cursor = self.cursor[lo:hi].copy()
+            qb.has_cursor = self.has_cursor[lo:hi].copy()
         return qb
 
 
@@ -418,6 +444,13 @@ class PreparedBatch:
     def copy_results_to(self, dst_hits_ptr: int, dst_counts_ptr: int) -> None:
         self.index._check(self.index.lib.slg_batch_copy_results_device(self.handle, dst_hits_ptr, dst_counts_ptr))
 
+    def cursor_seen(self) -> np.ndarray:
+        """saw_cursor per query of the last run (api/reader.rs:2663, :3022-3024); False means the reference would fail
+        the request with 'stale or invalid cursor for this result set'"""
+        out = np.zeros(self.n_queries, dtype=np.uint8)
+        self.index._check(self.index.lib.slg_batch_cursor_seen(self.handle, _ptr(out)))
+        return out.astype(bool)
+
     def free(self) -> None:
         if self.handle:
             self.index.lib.slg_batch_free(self.handle)
@@ -428,6 +461,29 @@ class PreparedBatch:
             self.free()
         except Exception:
             pass
+
+
+def cursor_encode(generation: int, returned: int, hit) -> str:
+    """PaginationCursor::encode (api/reader.rs:630-650): hit = (segment_ord, doc_id, score) of the last returned hit"""
+    h = np.zeros(1, dtype=HIT_DTYPE)
+    h[0] = (int(hit[0]), int(hit[1]), np.float32(hit[2]))
+    buf = C.create_string_buffer(43)
+    rc = load_library().slg_cursor_encode(generation, returned, _ptr(h), buf)
+    if rc:
+        raise SearchliteGpuError(rc, "cursor encode failed")
+    return buf.value.decode()
+
+
+def cursor_decode(raw: str, manifest_generation: int):
+    """PaginationCursor::decode + the generation check of decode_cursor (api/reader.rs:652-691, :821-841) ->
+    ((segment_ord, doc_id, score), returned); raises with the reference's message"""
+    h = np.zeros(1, dtype=HIT_DTYPE)
+    ret = C.c_uint32()
+    err = C.create_string_buffer(256)
+    rc = load_library().slg_cursor_decode(raw.encode(), manifest_generation, _ptr(h), C.byref(ret), err, 256)
+    if rc:
+        raise SearchliteGpuError(rc, err.value.decode())
+    return (int(h[0]["segment_ord"]), int(h[0]["doc_id"]), np.float32(h[0]["score"])), int(ret.value)
 
 
 class GpuIndex:
