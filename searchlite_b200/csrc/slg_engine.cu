@@ -633,9 +633,9 @@ int32_t launch_score(slg_index *ix, bool matcher, bool prune, bool stats, const 
   }
 }
 
-template <bool M, bool P, bool S, bool G, bool C = false>
+template <bool M, bool P, bool S, bool G, bool C = false, bool PL = false>
 int32_t launch_warp_t(slg_index *ix, const SegmentDev &sd, const WarpBatchDev &wb, size_t smem, int grid) {
-  auto kern = slg_score_warp_kernel<M, P, S, G, C>;
+  auto kern = slg_score_warp_kernel<M, P, S, G, C, PL>;
   SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kThreads, smem, ix->stream>>>(sd, wb);
   SLG_CUDA(ix, cudaGetLastError());
@@ -643,8 +643,21 @@ int32_t launch_warp_t(slg_index *ix, const SegmentDev &sd, const WarpBatchDev &w
 }
 
 int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, bool staged, bool cols, const SegmentDev &sd,
-                    const WarpBatchDev &wb, size_t smem, int grid) {
+                    const WarpBatchDev &wb, size_t smem, int grid, bool plan = false) {
   int sel = (matcher ? 4 : 0) | (prune ? 2 : 0) | (stats ? 1 : 0);
+  if (plan) {  // ScorePlans: resident scores for plain OR queries, in-place scoring + group masks otherwise
+    const bool st = staged && !matcher;
+    switch (sel & 3) {
+      case 0: return st ? launch_warp_t<false, false, false, true, false, true>(ix, sd, wb, smem, grid)
+                        : launch_warp_t<true, false, false, false, false, true>(ix, sd, wb, smem, grid);
+      case 1: return st ? launch_warp_t<false, false, true, true, false, true>(ix, sd, wb, smem, grid)
+                        : launch_warp_t<true, false, true, false, false, true>(ix, sd, wb, smem, grid);
+      case 2: return st ? launch_warp_t<false, true, false, true, false, true>(ix, sd, wb, smem, grid)
+                        : launch_warp_t<true, true, false, false, false, true>(ix, sd, wb, smem, grid);
+      default: return st ? launch_warp_t<false, true, true, true, false, true>(ix, sd, wb, smem, grid)
+                         : launch_warp_t<true, true, true, false, false, true>(ix, sd, wb, smem, grid);
+    }
+  }
   if (staged && !matcher && cols) {
     switch (sel) {
       case 0: return launch_warp_t<false, false, false, true, true>(ix, sd, wb, smem, grid);
@@ -2016,14 +2029,14 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   for (auto &s : ix->segs) sweepable = sweepable && (s->post_pair.p != nullptr || s->n_blocks == 0);
   // tile-sweep kernel: plain OR queries (no matcher), small k, few terms, resident scores
   // column front end: plain OR queries (no matcher), small k, few terms, resident scores and columns
-  if (bt->has_plan && ix->kernel_choice >= 2)
-    return fail(ix, SLG_ERR_UNSUPPORTED, "ScorePlan queries run on the CTA-per-item kernel (kernel_choice 0 or 1)");
+  if (bt->has_plan && ix->kernel_choice == 3)
+    return fail(ix, SLG_ERR_UNSUPPORTED, "ScorePlan queries run on the warp or CTA-per-item kernel (kernel_choice 0, 1 or 2)");
   bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && sweepable && !bt->has_plan);
   if (bt->use_reg && !(small && !matcher && sweepable))
     return fail(ix, SLG_ERR_UNSUPPORTED,
                 "the sweep kernel handles plain OR queries, k <= %u, <= %u terms per query, resident scores, < 2^32 postings per segment",
                 kWarpMaxK, kWarpMaxTerms);
-  bt->use_warp = !bt->use_reg && (ix->kernel_choice == 2 || (ix->kernel_choice == 0 && small && !bt->has_plan));
+  bt->use_warp = !bt->use_reg && (ix->kernel_choice == 2 || (ix->kernel_choice == 0 && small));
   if (bt->use_warp && !small)
     return fail(ix, SLG_ERR_UNSUPPORTED, "the warp kernel handles k <= %u and <= %u terms per query", kWarpMaxK, kWarpMaxTerms);
 
@@ -2126,7 +2139,7 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
     // one accumulator plane per leaf: shrink the doc tile so that the planes together stay near the configured tile
     uint32_t planes = 1;
     while (planes < bt->max_leaves) planes <<= 1;
-    bt->plan_docs = std::max(1024u, (ix->tile_docs / planes) & ~1023u);
+    bt->plan_docs = bt->use_warp ? std::max(512u, (ix->sub_docs / planes) & ~127u) : std::max(1024u, (ix->tile_docs / planes) & ~1023u);
   }
   const uint32_t plan_docs = bt->plan_docs;
   uint32_t max_tiles = 0;
@@ -2430,7 +2443,11 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         wb.filter_bits = bd.filter_bits;
         wb.n_queries = bw.n_queries;
         wb.k = k;
-        wb.sub_docs = ix->sub_docs;
+        wb.sub_docs = bt->has_plan ? bt->plan_docs : ix->sub_docs;
+        wb.q_leaves = bd.q_leaves;
+        wb.q_plan_off = bd.q_plan_off;
+        wb.plan_nodes = bd.plan_nodes;
+        wb.max_leaves = bt->max_leaves;
         wb.n_sub = bd.n_tiles;
         wb.n_groups = (bd.n_tiles + kSubPerGroup - 1) / kSubPerGroup;
         wb.ms_frac = (float)ix->maxscore_pct / 100.0f;
@@ -2443,13 +2460,16 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         wb.q_cursor = bd.q_cursor;
         wb.q_saw = bd.q_saw;
         const int warps = kThreads / 32;
-        size_t wsmem = (size_t)warps * warp_kernel_smem_per_warp(ix->sub_docs, bt->matcher, prune);
+        // (plan batches: the matcher form of the kernel unless the staged plain-OR form applies — size for the larger)
+        size_t wsmem = (size_t)warps * warp_kernel_smem_per_warp(wb.sub_docs, bt->matcher || (bt->has_plan && !bt->staged), prune,
+                                                                 bt->has_plan ? bt->max_leaves : 1u);
         if (wsmem + 1024 > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "sub_docs %u needs %zu B shared memory", ix->sub_docs, wsmem);
         uint32_t wper = (uint32_t)std::max<size_t>(1, (ix->smem_optin + 1024) / (wsmem + 1024));
         wper = std::min(wper, 8u);
         if (ix->ctas_per_sm) wper = std::min(wper, ix->ctas_per_sm);
         int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * wper, ((uint64_t)wb.n_groups * wb.n_queries + warps - 1) / warps);
-        rc = launch_warp(ix, bt->matcher, prune, bt->want_stats, bt->staged, bt->use_reg && bt->warp_cols, s->dev, wb, wsmem, grid);
+        rc = launch_warp(ix, bt->matcher, prune, bt->want_stats, bt->staged, bt->use_reg && bt->warp_cols, s->dev, wb, wsmem, grid,
+                         bt->has_plan);
         if (rc) return rc;
         count_launch(ix);
         if (!bt->use_reg || !bt->n_heavy) ix->ctr.score_launches++;

@@ -69,6 +69,11 @@ struct WarpBatchDev {
   unsigned long long *stats;
   const unsigned long long *q_cursor;  // as in BatchDev
   uint32_t *q_saw;
+  // ScorePlans (PLAN kernels): as in BatchDev; a term's leaf travels in QTerm.flags bits 16..19
+  const uint8_t *q_leaves;
+  const uint32_t *q_plan_off;
+  const PlanNodeDev *plan_nodes;
+  uint32_t max_leaves;
 };
 
 // resolve the batch's query terms against one segment (runs once per segment per batch)
@@ -103,6 +108,7 @@ __global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qter
       r.uterm = u;
       r.weight = bt.qt_weight[t0 + t];
       r.flags = (bt.qt_flags[t0 + t] & 1u) | 2u | ((uint32_t)bt.qt_group[t0 + t] << 8);
+      if (bt.qt_leaf) r.flags |= (uint32_t)bt.qt_leaf[t0 + t] << 16;
       if (seg.term_col && term < seg.n_terms && seg.term_col[term] >= 0 && (r.flags & 1u)) {
         r.sc_base = (uint64_t)seg.term_col[term] * seg.col_stride;
         if (use_cols) r.flags |= 4u;
@@ -113,9 +119,9 @@ __global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qter
 }
 
 constexpr uint32_t kRbStride = 9;
-__host__ __device__ inline size_t warp_kernel_smem_per_warp(uint32_t sub_docs, bool matcher, bool prune) {
+__host__ __device__ inline size_t warp_kernel_smem_per_warp(uint32_t sub_docs, bool matcher, bool prune, uint32_t planes = 1) {
   // (every term is a multiple of 16 B)
-  return (size_t)sub_docs * 4 + kWarpCand * 8 + kWarpMaxTerms * sizeof(QTerm) + kWarpMaxTerms * kRbStride * 4 +
+  return (size_t)sub_docs * 4 * planes + kWarpCand * 8 + kWarpMaxTerms * sizeof(QTerm) + kWarpMaxTerms * kRbStride * 4 +
          (prune ? kWarpMaxTerms * 8 * 4 : 0) + (matcher ? sub_docs : 0);
 }
 
@@ -223,18 +229,25 @@ __device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ d
 // binary search inside the sub-tile's posting range otherwise — so the result is bit-identical to
 // the exhaustive run.  (TermState upper bounds: query/wand.rs:238-303; the reference's wand_loop
 // prunes document-at-a-time with the same bounds, query/wand.rs:659-903.)
-template <bool MATCHER, bool PRUNE, bool STATS, bool STAGED, bool COLS = false>
+//
+// PLAN (ScorePlans): the warp's accumulator holds wb.max_leaves planes of sub_docs floats; a scored
+// term scatters into the plane of its leaf, one pass per sub-tile evaluates the query's postfix ScoreExpr per
+// touched doc into plane 0 and clears the other planes, and the scan proceeds on plane 0.  MaxScore (partial
+// sums) and the written-maximum shortcut do not apply to plans; the tile skip does (a plan never exceeds the
+// sum of its terms' bounds).
+template <bool MATCHER, bool PRUNE, bool STATS, bool STAGED, bool COLS = false, bool PLAN = false>
 __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev seg, WarpBatchDev wb) {
-  constexpr bool MAXSCORE = PRUNE && !MATCHER && STAGED;
+  constexpr bool MAXSCORE = PRUNE && !MATCHER && STAGED && !PLAN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarps = kThreads / 32;
   const uint32_t sub_docs = wb.sub_docs;
   // per-warp layout: acc f32[sub_docs] | cand u64[64] | qt QTerm[8] | rb u32[8][9] | ub f32[8][8] (PRUNE) | gmask u8[sub_docs] (MATCHER)
-  const size_t per_warp = warp_kernel_smem_per_warp(sub_docs, MATCHER, PRUNE);
+  const uint32_t n_planes = PLAN ? wb.max_leaves : 1u;
+  const size_t per_warp = warp_kernel_smem_per_warp(sub_docs, MATCHER, PRUNE, n_planes);
   unsigned char *mine = smem_raw + (size_t)warp * per_warp;
   float *acc = reinterpret_cast<float *>(mine);
-  unsigned long long *cand = reinterpret_cast<unsigned long long *>(mine + (size_t)sub_docs * 4);
+  unsigned long long *cand = reinterpret_cast<unsigned long long *>(mine + (size_t)sub_docs * 4 * n_planes);
   QTerm *qt = reinterpret_cast<QTerm *>(cand + kWarpCand);
   uint32_t *rb = reinterpret_cast<uint32_t *>(qt + kWarpMaxTerms);   // [t][9], boundary j at rb[t*9 + j]
   float *ubs = reinterpret_cast<float *>(rb + kWarpMaxTerms * kRbStride);   // [t][8]
@@ -249,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
   const uint32_t total_items = wb.n_groups * wb.n_queries;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
-  for (uint32_t i = lane * 4; i < sub_docs; i += 128) *reinterpret_cast<float4 *>(acc + i) = make_float4(0, 0, 0, 0);
+  for (uint32_t i = lane * 4; i < sub_docs * n_planes; i += 128) *reinterpret_cast<float4 *>(acc + i) = make_float4(0, 0, 0, 0);
   if (MATCHER)
     for (uint32_t i = lane * 4; i < sub_docs; i += 128) *reinterpret_cast<uint32_t *>(gmask + i) = 0u;
   __syncwarp();
@@ -268,6 +281,16 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
     const uint32_t qslot = item - tg * wb.n_queries;
     const QHead head = wb.qheads[qslot];
     const uint32_t nt = head.nt;
+    uint32_t n_leaves = 0, n_nodes = 0;  // PLAN: 0 leaves = this query has no plan (running sum in plane 0)
+    const PlanNodeDev *nodes = nullptr;
+    if (PLAN) {
+      n_leaves = wb.q_leaves[head.qi];
+      const uint32_t p0 = wb.q_plan_off[head.qi];
+      n_nodes = wb.q_plan_off[head.qi + 1] - p0;
+      nodes = wb.plan_nodes + p0;
+    }
+    (void)n_nodes;
+    (void)nodes;
     // stage the query's term records: 8 records x 32 B = 16 lanes x 16 B
     if (lane < 16) {
       const uint4 v = __ldg(reinterpret_cast<const uint4 *>(wb.qterms + (uint64_t)qslot * kWarpMaxTerms) + lane);
@@ -395,15 +418,18 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
         if (MAXSCORE && ((nmask >> t) & 1u)) continue;
         const QTerm q = qt[t];
         const bool scored = q.flags & 1u;
+        float *plane = acc;
+        if (PLAN && n_leaves) plane += (size_t)((q.flags >> 16) & 15u) * sub_docs;
+        if (PLAN) first = false;  // planes: always add (0 + s == s)
         if (STAGED && !MATCHER) {
           const uint32_t *dptr = seg.post_doc + q.base;
           const float *sptr = wb.scores + q.base;
           if (q.weight == 1.0f) {
-            if (first) accumulate_staged<true, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, acc, lane, wmax);
-            else accumulate_staged<false, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, acc, lane, wmax);
+            if (first) accumulate_staged<true, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, plane, lane, wmax);
+            else accumulate_staged<false, true>(dptr, sptr, lo, hi, tile_lo, 1.0f, plane, lane, wmax);
           } else {
-            if (first) accumulate_staged<true, false>(dptr, sptr, lo, hi, tile_lo, q.weight, acc, lane, wmax);
-            else accumulate_staged<false, false>(dptr, sptr, lo, hi, tile_lo, q.weight, acc, lane, wmax);
+            if (first) accumulate_staged<true, false>(dptr, sptr, lo, hi, tile_lo, q.weight, plane, lane, wmax);
+            else accumulate_staged<false, false>(dptr, sptr, lo, hi, tile_lo, q.weight, plane, lane, wmax);
           }
         } else {
           TermCtx tc;
@@ -416,14 +442,38 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
           tc.idf = seg.term_idf[q.term];
           tc.w = q.weight;
           tc.gbit = MATCHER ? (uint8_t)(1u << ((q.flags >> 8) & 7u)) : 0;
-          if (first && scored && !MATCHER) accumulate_term<MATCHER, true, 32>(seg, tc, lo, hi, tile_lo, acc, gmask, lane);
-          else accumulate_term<MATCHER, false, 32>(seg, tc, lo, hi, tile_lo, acc, gmask, lane);
+          if (first && scored && !MATCHER) accumulate_term<MATCHER, true, 32>(seg, tc, lo, hi, tile_lo, plane, gmask, lane);
+          else accumulate_term<MATCHER, false, 32>(seg, tc, lo, hi, tile_lo, plane, gmask, lane);
           wmax = 0xFFFFFFFFu;  // not tracked on this path
         }
         if (scored) first = false;
         __syncwarp();
       }
 
+      if (PLAN) {
+        wmax = 0xFFFFFFFFu;  // a plan's score can exceed every value written to a plane
+        if (n_leaves) {
+          // ---- ScorePlan: leaves -> score in plane 0, other planes cleared (plan.evaluate, query/wand.rs:506) ----
+#pragma unroll 1
+          for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) {
+            const uint32_t i = i0 + lane * 4;
+            uint32_t m = 0;
+            for (uint32_t l = 0; l < n_leaves; l++) {
+              const uint4 v = *reinterpret_cast<const uint4 *>(acc + (size_t)l * sub_docs + i);
+              m |= v.x | v.y | v.z | v.w;
+            }
+            if (m == 0u) continue;
+            float4 r;
+            r.x = plan_evaluate(nodes, n_nodes, acc, sub_docs, i);
+            r.y = plan_evaluate(nodes, n_nodes, acc, sub_docs, i + 1);
+            r.z = plan_evaluate(nodes, n_nodes, acc, sub_docs, i + 2);
+            r.w = plan_evaluate(nodes, n_nodes, acc, sub_docs, i + 3);
+            for (uint32_t l = 1; l < n_leaves; l++) *reinterpret_cast<float4 *>(acc + (size_t)l * sub_docs + i) = make_float4(0, 0, 0, 0);
+            *reinterpret_cast<float4 *>(acc + i) = r;
+          }
+          __syncwarp();
+        }
+      }
       // ---- scan + clear; collect keys that beat the threshold ----
       uint32_t thr_hi = (uint32_t)(thr >> 32);
       if (MAXSCORE && nmask) {

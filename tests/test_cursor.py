@@ -141,8 +141,8 @@ def test_gpu_pagination_matches_full_ranking_and_oracle(kernel, exe):
     for s in segs:
         gi.load_segment(s)
     qb = QueryBatch.from_term_lists([rng.choice(25, size=int(rng.integers(1, 4)), replace=False).tolist() for _ in range(24)])
-    limit = 10
-    n_pages = 6
+    limit = 5
+    n_pages = 6  # k = 31 for the un-paged ranking: within the warp kernels' k <= 32
     full_h, full_c = gi.search_batch(qb, limit * n_pages + 1, exe)
 
     def search(batch, k):

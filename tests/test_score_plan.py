@@ -3,8 +3,8 @@
 
 CPU part: the oracle's postfix evaluator against a tree-recursive restatement of planner.rs:133-153 in numpy
 f32, the reference's own multi-field ordering tests (searchlite-core/tests/multi_field.rs:105-192) restated on
-the literal 5-doc corpus, and bm25 == wand under plans.  GPU part: the CTA-per-item kernel with one accumulator
-plane per leaf, bit-exact against the oracle's `bm25` execution."""
+the literal 5-doc corpus, and bm25 == wand under plans.  GPU part: the warp and CTA-per-item kernels with one
+accumulator plane per leaf, bit-exact against the oracle's `bm25` execution."""
 import ctypes as C
 
 import numpy as np
@@ -205,10 +205,13 @@ def test_oracle_wand_agrees_with_bm25_under_plans():
 
 # ---- GPU ------------------------------------------------------------------------------------------
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["auto", "cta", "warp", "warp-inplace"])  # auto: warp kernel for k <= 32, CTA kernel above
 @pytest.mark.parametrize("k", [11, 101])
 @pytest.mark.parametrize("deleted", [False, True])
-def test_gpu_plans_bit_exact(k, deleted):
+def test_gpu_plans_bit_exact(k, deleted, kernel):
     from searchlite_b200 import GpuIndex
+    if k > 32 and kernel.startswith("warp"):
+        pytest.skip("the warp kernel handles k <= 32")
     slo = _slo()
     rng = np.random.default_rng(100 + k + int(deleted))
     seg, tl, ll, ex = _random_case(rng, n_docs=6000, vocab=40, n_queries=64, max_leaves=6, deleted=deleted)
@@ -216,7 +219,7 @@ def test_gpu_plans_bit_exact(k, deleted):
     qb = _plan_batch(tl, ll, ex, weights)
     ora = slo.OracleIndex(seg)
     ref = ora.search_batch(qb, k, "bm25")
-    gi = GpuIndex(0)
+    gi = GpuIndex(0, kernel=kernel)
     gi.load_segment(seg)
     got = gi.search_batch(qb, k, "bm25")
     assert_parity(*ref, *got, strict=True)
@@ -224,7 +227,7 @@ def test_gpu_plans_bit_exact(k, deleted):
         h, c = gi.search_batch(qb, k, exe)
         assert h.tobytes() == got[0].tobytes() and c.tobytes() == got[1].tobytes(), exe
     gi.close()
-    gt = GpuIndex(0, tile_docs=1024)  # many tiles per query: plans across tile boundaries
+    gt = GpuIndex(0, tile_docs=1024, kernel=kernel)  # many tiles per query: plans across tile boundaries
     gt.load_segment(seg)
     h, c = gt.search_batch(qb, k, "bm25")
     assert h.tobytes() == got[0].tobytes() and c.tobytes() == got[1].tobytes()
@@ -232,7 +235,8 @@ def test_gpu_plans_bit_exact(k, deleted):
 
 
 @pytest.mark.gpu
-def test_gpu_plans_with_bool_matcher_and_segments():
+@pytest.mark.parametrize("kernel", ["auto", "cta", "warp"])
+def test_gpu_plans_with_bool_matcher_and_segments(kernel):
     from searchlite_b200 import GpuIndex
     slo = _slo()
     rng = np.random.default_rng(5)
@@ -249,7 +253,7 @@ def test_gpu_plans_with_bool_matcher_and_segments():
         exprs.append(("sum", [("leaf", 0), ("dismax", [("leaf", 1), ("leaf", 2), ("leaf", 3)], 0.25)]) if qi % 5 else None)
     qb = QueryBatch.from_bool(queries).set_plans(exprs)
     k = 21
-    gi = GpuIndex(0)
+    gi = GpuIndex(0, kernel=kernel)
     for s in segs:
         gi.load_segment(s)
     got = gi.search_batch(qb, k, "bm25")
@@ -296,9 +300,9 @@ def test_gpu_plan_validation():
     with pytest.raises(SearchliteGpuError, match="instead of one"):
         run(("leaf", 0), fix=two_values)
     gi.close()
-    gw = GpuIndex(0, kernel="warp")
+    gw = GpuIndex(0, kernel="reg")
     gw.load_segment(seg)
     qb = QueryBatch.from_term_lists([[0, 1]]).set_plans([("sum", [("leaf", 0), ("leaf", 1)])])
-    with pytest.raises(SearchliteGpuError, match="CTA-per-item"):
+    with pytest.raises(SearchliteGpuError, match="warp or CTA-per-item"):
         gw.search_batch(qb, 3, "bm25")
     gw.close()

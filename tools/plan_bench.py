@@ -1,7 +1,7 @@
 """Bounded timing of ScorePlan queries at C2 size (a parity-test shape, not a bench line):
 the C2 corpus and its 4096 two-to-five-term OR queries, each query's terms dealt onto two leaves under
-DisMax(tie_breaker 0.3) — the shape of a `multi_match best_fields` — on the CTA-per-item kernel with
-accumulator planes, next to the same queries without a plan on the same kernel and on the automatic one.
+DisMax(tie_breaker 0.3) — the shape of a `multi_match best_fields` — on the warp kernel with accumulator
+planes (the automatic choice) and on the CTA-per-item kernel with planes, next to the same queries without a plan.
 A sample of the plan results is compared with the oracle.  Usage: python tools/plan_bench.py [n_docs]"""
 import sys
 import time
@@ -35,8 +35,9 @@ plan_qb.set_plans([("dismax", [("leaf", 0), ("leaf", 1)], 0.3)] * qb.n_queries)
 plan_qb.leaf_count[:] = 2
 plan_qb._structs = None
 
-for label, kernel, batch in (("no plan, automatic kernel", "auto", qb), ("no plan, CTA-per-item kernel", "cta", qb),
-                             ("DisMax over 2 leaves, CTA-per-item kernel with planes", "auto", plan_qb)):
+for label, kernel, batch in (("no plan, automatic kernel", "auto", qb), ("no plan, warp kernel (query order)", "warp", qb),
+                             ("DisMax over 2 leaves, warp kernel with planes (automatic)", "auto", plan_qb),
+                             ("DisMax over 2 leaves, CTA-per-item kernel with planes", "cta", plan_qb)):
     gi = GpuIndex(0, kernel=kernel)
     gi.load_segment(seg)
     for exe in ("bm25", "bmw"):
@@ -44,7 +45,7 @@ for label, kernel, batch in (("no plan, automatic kernel", "auto", qb), ("no pla
         ms = timed(lambda: p.run(sync=True))
         print(f"{label}, {exe}: {ms:.1f} ms/batch, {4096 / ms * 1e3:.0f} q/s", flush=True)
         p.free()
-    if batch is plan_qb:
+    if batch is plan_qb and kernel == "auto":
         from oracle import slo  # checker only
         from tests.parity import parity_report
         host = seg.to_host() if hasattr(seg, "to_host") else seg
