@@ -108,6 +108,9 @@ typedef struct {
   uint64_t postings_advanced; /* postings decoded and scored */
   uint64_t blocks_skipped;    /* (query, tile) items skipped by the block-max bound */
   uint64_t candidates_examined;
+  uint64_t total_matches;     /* docs accepted by the accept closure (match counter, api/reader.rs:3029-3031): exact under
+                               * BM25; under WAND/BMW an estimate, as the reference's total_hits_estimate is (skipped
+                               * tiles and MaxScore-skipped terms are not visited).  Not counted by the tile-sweep kernel. */
 } slg_stats_t;
 
 /* Where the arrays of a view live. */

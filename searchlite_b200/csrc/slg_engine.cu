@@ -2235,14 +2235,14 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   SLG_CUDA(ix, bt->lock.alloc((size_t)n_queries * 4));
   SLG_CUDA(ix, bt->topk_keys.alloc((size_t)n_queries * k * 8));
   SLG_CUDA(ix, bt->work_counter.alloc(64 * 4));
-  SLG_CUDA(ix, bt->stats.alloc((size_t)n_queries * 4 * 8));
+  SLG_CUDA(ix, bt->stats.alloc((size_t)n_queries * 5 * 8));  // [Q][4] counters, then [Q] accepted docs
   SLG_CUDA(ix, bt->seg_hits.alloc(S * n_queries * k * sizeof(HitDev)));
   SLG_CUDA(ix, bt->seg_counts.alloc(S * n_queries * 4));
   if (S > 1) {
     SLG_CUDA(ix, bt->out_hits.alloc((size_t)n_queries * k * sizeof(HitDev)));
     SLG_CUDA(ix, bt->out_counts.alloc((size_t)n_queries * 4));
   }
-  bt->pinned_bytes = (size_t)n_queries * k * sizeof(slg_hit_t) + (size_t)n_queries * 4 + (size_t)n_queries * 32;
+  bt->pinned_bytes = (size_t)n_queries * k * sizeof(slg_hit_t) + (size_t)n_queries * 4 + (size_t)n_queries * 40;
   if (!ix->pinned_busy && ix->pinned && ix->pinned_bytes >= bt->pinned_bytes) {
     bt->pinned = ix->pinned;
     bt->pinned_from_index = true;
@@ -2271,7 +2271,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
   per_sm = std::min(per_sm, 8u);
   if (ix->ctas_per_sm) per_sm = std::min(per_sm, ix->ctas_per_sm);
   SLG_CUDA(ix, cudaEventRecord(ix->ev[0], st));
-  SLG_CUDA(ix, cudaMemsetAsync(bt->stats.p, 0, (size_t)Q * 32, st));
+  SLG_CUDA(ix, cudaMemsetAsync(bt->stats.p, 0, (size_t)Q * 40, st));
   if (bt->has_cursor) {
     if (bt->n_cursor_segs != ix->segs.size()) return fail(ix, SLG_ERR_INVALID, "a segment was loaded after the batch with cursors was prepared");
     SLG_CUDA(ix, cudaMemsetAsync(bt->cursor_saw.p, 0, (size_t)Q * 4, st));
@@ -2319,6 +2319,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
     bd.topk_keys = bt->topk_keys.as<unsigned long long>();
     bd.work_counter = bt->work_counter.as<uint32_t>();
     bd.stats = bt->stats.as<unsigned long long>();
+    bd.match_count = bd.stats + (size_t)Q * 4;
     // queries that name a filter need its bitmap on every segment
     if (!ix->filters.empty() && s->filter_bits.size() < ix->filters.size())
       return fail(ix, SLG_ERR_INVALID, "segment %u was loaded after its filters were compiled", s->ord);
@@ -2457,6 +2458,7 @@ int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
         wb.topk_keys = bd.topk_keys;
         wb.work_counter = bd.work_counter;
         wb.stats = bd.stats;
+        wb.match_count = bd.match_count;
         wb.q_cursor = bd.q_cursor;
         wb.q_saw = bd.q_saw;
         const int warps = kThreads / 32;
@@ -2546,7 +2548,7 @@ int32_t slg_batch_fetch(slg_batch_t *bt, slg_hit_t *out_hits, uint32_t *out_coun
   void *dh, *dc;
   slg_batch_device_results(bt, &dh, &dc);
   static_assert(sizeof(slg_hit_t) == sizeof(HitDev), "hit layout");
-  size_t hb = (size_t)bt->Q * bt->k * sizeof(slg_hit_t), cb = (size_t)bt->Q * 4, sb = (size_t)bt->Q * 32;
+  size_t hb = (size_t)bt->Q * bt->k * sizeof(slg_hit_t), cb = (size_t)bt->Q * 4, sb = (size_t)bt->Q * 40;
   unsigned char *pin = static_cast<unsigned char *>(bt->pinned);
   SLG_CUDA(ix, cudaMemcpyAsync(pin, dh, hb, cudaMemcpyDeviceToHost, st));
   SLG_CUDA(ix, cudaMemcpyAsync(pin + hb, dc, cb, cudaMemcpyDeviceToHost, st));
@@ -2562,6 +2564,7 @@ int32_t slg_batch_fetch(slg_batch_t *bt, slg_hit_t *out_hits, uint32_t *out_coun
       out_stats[q].postings_advanced = sv[q * 4 + 1];
       out_stats[q].blocks_skipped = sv[q * 4 + 2];
       out_stats[q].candidates_examined = sv[q * 4 + 3];
+      out_stats[q].total_matches = sv[(size_t)bt->Q * 4 + q];
     }
   }
   return SLG_OK;

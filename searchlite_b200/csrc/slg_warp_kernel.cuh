@@ -74,6 +74,7 @@ struct WarpBatchDev {
   const uint32_t *q_plan_off;
   const PlanNodeDev *plan_nodes;
   uint32_t max_leaves;
+  unsigned long long *match_count;  // [Q] accepted docs (STATS)
 };
 
 // resolve the batch's query terms against one segment (runs once per segment per batch)
@@ -289,8 +290,8 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
       n_nodes = wb.q_plan_off[head.qi + 1] - p0;
       nodes = wb.plan_nodes + p0;
     }
-    (void)n_nodes;
-    (void)nodes;
+    const PlanInfo pinfo = plan_info(nodes, n_nodes, n_leaves);
+    (void)pinfo;
     // stage the query's term records: 8 records x 32 B = 16 lanes x 16 B
     if (lane < 16) {
       const uint4 v = __ldg(reinterpret_cast<const uint4 *>(wb.qterms + (uint64_t)qslot * kWarpMaxTerms) + lane);
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
     __syncwarp();
 
     uint32_t cnt = 0;  // pending candidates in cand[]
-    uint32_t n_touched = 0, n_post = 0, n_skipped = 0;
+    uint32_t n_touched = 0, n_post = 0, n_skipped = 0, n_match = 0;
     const uint32_t masks = head.masks;
 
 #pragma unroll 1
@@ -455,22 +456,7 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
         if (n_leaves) {
           // ---- ScorePlan: leaves -> score in plane 0, other planes cleared (plan.evaluate, query/wand.rs:506) ----
 #pragma unroll 1
-          for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) {
-            const uint32_t i = i0 + lane * 4;
-            uint32_t m = 0;
-            for (uint32_t l = 0; l < n_leaves; l++) {
-              const uint4 v = *reinterpret_cast<const uint4 *>(acc + (size_t)l * sub_docs + i);
-              m |= v.x | v.y | v.z | v.w;
-            }
-            if (m == 0u) continue;
-            float4 r;
-            r.x = plan_evaluate(nodes, n_nodes, acc, sub_docs, i);
-            r.y = plan_evaluate(nodes, n_nodes, acc, sub_docs, i + 1);
-            r.z = plan_evaluate(nodes, n_nodes, acc, sub_docs, i + 2);
-            r.w = plan_evaluate(nodes, n_nodes, acc, sub_docs, i + 3);
-            for (uint32_t l = 1; l < n_leaves; l++) *reinterpret_cast<float4 *>(acc + (size_t)l * sub_docs + i) = make_float4(0, 0, 0, 0);
-            *reinterpret_cast<float4 *>(acc + i) = r;
-          }
+          for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) plan_combine_quad(pinfo, acc, sub_docs, i0 + lane * 4);
           __syncwarp();
         }
       }
@@ -569,6 +555,27 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
           gm = *reinterpret_cast<const uint32_t *>(gmask + i);
           if (gm) *reinterpret_cast<uint32_t *>(gmask + i) = 0u;
         }
+        if (STATS && m != 0u) {
+          // the accept closure for every scored doc (api/reader.rs:3009-3031): the match counter behind
+          // total_hits_estimate.  Under MaxScore the scores seen here are partial and skipped terms' docs are
+          // absent, so — as in the reference under pruning — the count is an estimate.
+          const uint32_t sb[4] = {b0, b1, b2, b3};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            if (sb[e] == 0u) continue;
+            const uint32_t doc = tile_lo + i + e;
+            bool pass = (seg.live_bits[doc >> 5] >> (doc & 31)) & 1u;
+            if (pass && MATCHER) {
+              const uint32_t mm = (gm >> (8 * e)) & 255u;
+              const uint32_t must = masks & 255u, nots = (masks >> 8) & 255u, should = (masks >> 16) & 255u;
+              pass = ((mm & must) == must) && ((mm & nots) == 0u) && (__popc(mm & should) >= (int)(masks >> 24));
+            }
+            if (pass && head.filter >= 0) pass = (wb.filter_bits[head.filter][doc >> 5] >> (doc & 31)) & 1u;
+            if (pass && wb.q_cursor)
+              pass = (((unsigned long long)sb[e] << 32) | (unsigned long long)(0xFFFFFFFFu - doc)) < __ldg(wb.q_cursor + head.qi);
+            n_match += pass ? 1u : 0u;
+          }
+        }
         if (__any_sync(0xFFFFFFFFu, m >= thr_hi && m != 0u)) {
           const uint32_t bits[4] = {b0, b1, b2, b3};
           if (MAXSCORE && nmask) {
@@ -610,8 +617,10 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
       for (int o = 16; o > 0; o >>= 1) {
         n_touched += __shfl_xor_sync(0xFFFFFFFFu, n_touched, o);
         n_post += __shfl_xor_sync(0xFFFFFFFFu, n_post, o);
+        n_match += __shfl_xor_sync(0xFFFFFFFFu, n_match, o);
       }
       if (lane == 0) {
+        if (n_match) atomicAdd(wb.match_count + head.qi, (unsigned long long)n_match);
         if (n_touched) atomicAdd(wb.stats + (uint64_t)head.qi * 4 + 0, (unsigned long long)n_touched);
         if (n_post) atomicAdd(wb.stats + (uint64_t)head.qi * 4 + 1, (unsigned long long)n_post);
         if (n_skipped) atomicAdd(wb.stats + (uint64_t)head.qi * 4 + 2, (unsigned long long)n_skipped);

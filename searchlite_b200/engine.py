@@ -55,8 +55,8 @@ def plan_postfix(expr) -> list:
     raise ValueError(f"unknown score expression {expr[0]!r}")
 HIT_DTYPE = np.dtype({"names": ["segment_ord", "doc_id", "score"], "formats": ["<u4", "<u4", "<f4"], "itemsize": 12})
 STATS_DTYPE = np.dtype(
-    {"names": ["scored_docs", "postings_advanced", "blocks_skipped", "candidates_examined"],
-     "formats": ["<u8"] * 4, "itemsize": 32})
+    {"names": ["scored_docs", "postings_advanced", "blocks_skipped", "candidates_examined", "total_matches"],
+     "formats": ["<u8"] * 5, "itemsize": 40})
 FILTER_DTYPE = np.dtype(
     {"names": ["op", "column", "i_min", "i_max", "f_min", "f_max", "n_children", "value_begin", "value_end"],
      "formats": ["<u4", "<i4", "<i8", "<i8", "<f8", "<f8", "<u4", "<u4", "<u4"],

@@ -210,3 +210,53 @@ def test_gpu_cursor_with_matcher_filter_and_plan():
             lo = 0 if cursors[qi] is None else 7
             assert h[qi, : c[qi]].tobytes() == full_h[qi, lo: min(int(full_c[qi]), lo + 11)].tobytes(), (exe, qi)
     gi.close()
+
+
+# ---- match counter (total_hits_estimate, api/reader.rs:3029-3031, :2825) ----------------------------
+def test_oracle_total_hits_counts_across_pages():
+    """smoke.rs:594-616 total_hits_estimate_counts_across_pages: 3 matching docs, limit 2 -> the second page still
+    reports 3 = total_matches (docs after the cursor) + cursor.returned"""
+    slo = _slo()
+    seg = segment_from_postings([([0, 1, 2], [1, 1, 1])], [2, 3, 3])
+    ora = slo.OracleIndex(seg)
+    qb = QueryBatch.from_term_lists([[0]])
+    h, c, st = ora.search_batch(qb, 3, "bm25", want_stats=True)
+    assert st["total_matches"][0] == 3 and c[0] == 3
+    cur = (0, int(h[0, 1]["doc_id"]), h[0, 1]["score"])
+    h2, c2, st2 = ora.search_batch(qb.subset(0, 1).set_cursors([cur]), 3, "bm25", want_stats=True)
+    assert c2[0] == 1 and st2["total_matches"][0] + 2 == 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["auto", "cta", "warp"])
+def test_gpu_total_matches_equal_the_oracle_counter(kernel):
+    from searchlite_b200 import GpuIndex
+    slo = _slo()
+    rng = np.random.default_rng(31)
+    toks = [rng.integers(0, 30, size=int(rng.integers(2, 9))).tolist() for _ in range(5000)]
+    seg = token_corpus(toks, 30)
+    seg.deleted_docs = np.sort(rng.choice(5000, size=400, replace=False)).astype(np.uint32)
+    ora = slo.OracleIndex(seg)
+    gi = GpuIndex(0, kernel=kernel)
+    gi.load_segment(seg)
+    plain = QueryBatch.from_term_lists([rng.choice(30, size=int(rng.integers(1, 5)), replace=False).tolist() for _ in range(20)])
+    boolq = QueryBatch.from_bool([{"must": [int(a)], "should": [int(b), int(c)], "must_not": [int(d)], "min_should": int(m)}
+                                  for a, b, c, d, m in ((*rng.choice(30, size=4, replace=False), rng.integers(0, 2)) for _ in range(20))])
+    for qb in (plain, boolq):
+        h, c, st = gi.search_batch(qb, 11, "bm25", want_stats=True)
+        oh, oc, ost = ora.search_batch(qb, 11, "bm25", want_stats=True)
+        assert st["total_matches"].tolist() == ost["total_matches"].tolist()
+        # second page: the counter only sees docs after the cursor; + cursor.returned gives the same total (:2825)
+        cursors = [None if c[q] < 6 else (0, int(h[q, 4]["doc_id"]), h[q, 4]["score"]) for q in range(qb.n_queries)]
+        page2 = qb.subset(0, qb.n_queries).set_cursors(cursors)
+        h2, c2, st2 = gi.search_batch(page2, 11, "bm25", want_stats=True)
+        oh2, oc2, ost2 = ora.search_batch(page2, 11, "bm25", want_stats=True)
+        assert st2["total_matches"].tolist() == ost2["total_matches"].tolist()
+        for q in range(qb.n_queries):
+            if cursors[q] is not None:
+                assert st2["total_matches"][q] + 5 == st["total_matches"][q]
+        # pruned execution: an estimate from below, exact hits
+        hp, cp, stp = gi.search_batch(qb, 11, "bmw", want_stats=True)
+        assert hp.tobytes() == h.tobytes()
+        assert (stp["total_matches"] <= st["total_matches"]).all() and (stp["total_matches"] >= cp).all()
+    gi.close()
