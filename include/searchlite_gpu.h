@@ -195,7 +195,7 @@ int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, u
  *   "keep_positions"   1/0  keep term positions resident when a posting image carries them (default 1)
  *   "heavy_kernel"     0|1  column front end (kernel_choice 3): 0 = warp kernel that sums a query's column
  *                           terms from their dense columns (default), 1 = tile-sweep kernel
- *   "reg_tile_v"       4|8     tile-sweep kernel: 128 * v docs per register tile (default 8)
+ *   "reg_tile_v"       8       tile-sweep kernel: 128 * v docs per register tile (4 is refused: known intermittent fault)
  *   "sweep_min_postings" n  tile-sweep kernel: a query without a column term whose terms hold fewer than
  *                           n postings is scored posting-driven by the warp kernel instead of being swept
  *                           over every tile (default 0 = doc_count / 64; 1 = sweep every query)
