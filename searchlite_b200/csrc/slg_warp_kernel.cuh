@@ -451,9 +451,21 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
         __syncwarp();
       }
 
-      if (PLAN) {
-        wmax = 0xFFFFFFFFu;  // a plan's score can exceed every value written to a plane
-        if (n_leaves) {
+      if (PLAN && n_leaves) {
+        // a plan's score is at most the sum of its leaves (tie_breaker <= 1), and every leaf is at most the largest value
+        // written to a plane: if n_leaves x that maximum cannot reach the threshold, the sub-tile is cleared unread
+        if (STAGED && !MATCHER && !STATS && thr != kThrInit) {
+          const float top = __uint_as_float(__reduce_max_sync(0xFFFFFFFFu, wmax));
+          if (top * (float)n_leaves * 1.00001f < __uint_as_float((uint32_t)(thr >> 32))) {
+            for (uint32_t l = 0; l < n_leaves; l++)
+#pragma unroll 4
+              for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) *reinterpret_cast<float4 *>(acc + (size_t)l * sub_docs + i0 + lane * 4) = make_float4(0, 0, 0, 0);
+            __syncwarp();
+            continue;
+          }
+        }
+        wmax = 0xFFFFFFFFu;  // the scan's own shortcut compares single written values: not valid for a plan
+        {
           // ---- ScorePlan: leaves -> score in plane 0, other planes cleared (plan.evaluate, query/wand.rs:506) ----
 #pragma unroll 1
           for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) plan_combine_quad(pinfo, acc, sub_docs, i0 + lane * 4);
