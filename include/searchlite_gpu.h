@@ -50,7 +50,7 @@ typedef enum { SLG_EXEC_BM25 = 0, SLG_EXEC_WAND = 1, SLG_EXEC_BMW = 2 } slg_exec
 enum { SLG_ROLE_SHOULD = 0, SLG_ROLE_MUST = 1, SLG_ROLE_MUST_NOT = 2 };
 enum { SLG_TERM_SCORED = 1u };
 #define SLG_MAX_QUERY_TERMS 64u
-#define SLG_MAX_GROUPS 32u
+#define SLG_MAX_GROUPS 8u
 #define SLG_MAX_K 2048u
 
 /* One "field:term" key of a query after search_segment's weight merge (api/reader.rs:2971-2983). */
@@ -167,6 +167,11 @@ typedef struct {
   uint64_t resident_bytes;     /* device bytes held by loaded segments */
   uint64_t last_h2d_bytes;     /* host->device bytes of the last slg_batch_prepare */
   uint64_t last_d2h_bytes;     /* device->host bytes of the last slg_batch_fetch / slg_merge_gathered */
+  /* work of the last fetched run of the items kernel (whole batch, all segments): */
+  uint64_t last_postings_scattered;     /* postings read and accumulated (compare with last_posting_count) */
+  uint64_t last_subtiles_skipped;       /* (query, sub-tile) pairs dropped inside the sweep by the bound */
+  uint64_t last_column_blocks_streamed; /* 512-doc blocks of dense columns read */
+  uint64_t last_items;                  /* (query, doc-range) items scored, seeds included */
 } slg_counters_t;
 
 /* ---- lifetime ---- */
@@ -346,10 +351,24 @@ int32_t slg_batch_prepare(slg_index_t *, const slg_query_t *queries, uint32_t n_
 /* collect slg_stats_t counters in later runs (off by default: the counting costs a few percent) */
 int32_t slg_batch_enable_stats(slg_batch_t *, int32_t on);
 int32_t slg_batch_run(slg_batch_t *, int32_t sync);
+/* The pruned run in two steps for one-segment-per-GPU sharding: seeds give every query a local k-th
+ * key; the caller max-reduces the keys over the shards (e.g. ncclAllReduce(max) on the uint64 array of
+ * slg_batch_threshold_keys, n_queries entries in query order, on the handle's stream) and hands the result to
+ * slg_batch_import_thresholds, which keeps the score part (a global k-th score is a safe bound for every shard; an
+ * equal score may still win on segment order, query/sort.rs:80-93); the sweep then prunes against the global bound.
+ * The merged result over all shards is exact; a shard's own list may lack docs that cannot reach the global top k.
+ * Needs one segment in the handle, execution wand/bmw and a batch the items kernel handles. */
+int32_t slg_batch_run_seeds(slg_batch_t *);
+int32_t slg_batch_threshold_keys(slg_batch_t *, void **dev_keys);
+int32_t slg_batch_import_thresholds(slg_batch_t *, const void *dev_keys);
+int32_t slg_batch_run_sweep(slg_batch_t *, int32_t sync);
 int32_t slg_batch_fetch(slg_batch_t *, slg_hit_t *out_hits, uint32_t *out_counts, slg_stats_t *out_stats);
 /* device pointers of the last run's results (n_queries*k slg_hit_t, n_queries u32) for an
  * allgather by the caller; valid until the batch is re-run or freed */
 int32_t slg_batch_device_results(slg_batch_t *, void **dev_hits, void **dev_counts);
+/* the same as ONE block — n_queries*k hits followed by n_queries counts, *n_bytes long — the send buffer of a single
+ * allgather (slg_merge_gathered_packed takes the gathered blocks) */
+int32_t slg_batch_packed_results(slg_batch_t *, void **dev_block, uint64_t *n_bytes);
 /* device->device copy of the last run's results into caller buffers (e.g. the send buffer of an
  * allgather), asynchronous on the handle's stream */
 int32_t slg_batch_copy_results_device(slg_batch_t *, void *dst_dev_hits, void *dst_dev_counts);
@@ -372,6 +391,10 @@ int32_t slg_cursor_decode(const char *raw, uint32_t manifest_generation, slg_hit
 int32_t slg_merge_gathered(slg_index_t *, const void *dev_gathered_hits, const void *dev_gathered_counts,
                            uint32_t n_shards, uint32_t n_queries, uint32_t k, slg_hit_t *out_hits,
                            uint32_t *out_counts);
+
+/* gathered blocks of slg_batch_packed_results, shard_stride bytes apart (0 = tightly packed), DEVICE memory */
+int32_t slg_merge_gathered_packed(slg_index_t *, const void *dev_gathered, uint64_t shard_stride, uint32_t n_shards,
+                                  uint32_t n_queries, uint32_t k, slg_hit_t *out_hits, uint32_t *out_counts);
 
 /* ---- vectors + rerank (what gpu::rerank should have been; vectors/mod.rs:63-129, api/reader.rs:218-254) ----
  * offsets: doc -> row in values or UINT32_MAX (VectorStore, index/segment.rs:1030-1053).

@@ -7,318 +7,38 @@
 //   execute_top_k_with_stats_and_mode_internal            src/query/wand.rs:398-456
 //   hits.sort_by(SortKey)                                 src/api/reader.rs:2777
 // There is no CPU fallback anywhere in this file: every search runs the CUDA kernels or fails.
-#include "../../include/searchlite_gpu.h"
+#include "slg_host.h"
 
-#include <algorithm>
-#include <chrono>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
 #include <cub/cub.cuh>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
-#include <limits>
-#include <memory>
-#include <string>
-#include <unordered_map>
-#include <vector>
 
 #include "slg_filter.cuh"
-#include "slg_kernels.cuh"
 #include "slg_phrase.cuh"
 #include "slg_postimage.cuh"
-#include "slg_segfiles.h"
 #include "slg_rerank.cuh"
-#include "slg_sweep_kernel.cuh"
-#include "slg_warp_kernel.cuh"
+#include "slg_residency.cuh"
+#include "slg_segfiles.h"
 
 using namespace slg;
 
+namespace slg {
+std::string &open_error() {
+  thread_local std::string e;
+  return e;
+}
+cudaStream_t &pool_stream() {
+  thread_local cudaStream_t s = nullptr;
+  return s;
+}
+}  // namespace slg
+
 namespace {
-
-thread_local std::string g_open_error;
-
-// Per-batch buffers come from the device's stream-ordered pool (cudaMallocAsync): a prepare/free pair
-// per batch then costs microseconds instead of a cudaMalloc/cudaFree round trip per buffer.  The scope
-// guard names the stream; everything else (segment residency) uses plain cudaMalloc.
-thread_local cudaStream_t g_pool_stream = nullptr;
-struct PoolScope {
-  cudaStream_t prev;
-  explicit PoolScope(cudaStream_t s) : prev(g_pool_stream) { g_pool_stream = s; }
-  ~PoolScope() { g_pool_stream = prev; }
-};
-
-struct DevBuf {
-  void *p = nullptr;
-  size_t bytes = 0;
-  cudaStream_t pool = nullptr;  // non-null: allocated with cudaMallocAsync on this stream
-  bool borrowed = false;        // a view into another DevBuf's allocation: never freed here
-  DevBuf() = default;
-  DevBuf(const DevBuf &) = delete;
-  DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), pool(o.pool), borrowed(o.borrowed) { o.p = nullptr; o.bytes = 0; }
-  DevBuf &operator=(DevBuf &&o) noexcept {
-    if (this != &o) {
-      release();
-      p = o.p;
-      bytes = o.bytes;
-      pool = o.pool;
-      borrowed = o.borrowed;
-      o.p = nullptr;
-      o.bytes = 0;
-    }
-    return *this;
-  }
-  ~DevBuf() { release(); }
-  void view(void *ptr, size_t n) {  // borrow [ptr, ptr + n) from a slab that outlives this view
-    release();
-    p = ptr;
-    bytes = n;
-    borrowed = true;
-  }
-  void release() {
-    if (p && !borrowed) {
-      if (pool) cudaFreeAsync(p, pool);
-      else cudaFree(p);
-    }
-    p = nullptr;
-    bytes = 0;
-    borrowed = false;
-  }
-  cudaError_t alloc(size_t n) {
-    release();
-    if (n == 0) n = 16;
-    borrowed = false;
-    pool = g_pool_stream;
-    cudaError_t e = pool ? cudaMallocAsync(&p, n, pool) : cudaMalloc(&p, n);
-    if (e == cudaSuccess) bytes = n;
-    else p = nullptr;
-    return e;
-  }
-  template <class T>
-  T *as() const { return reinterpret_cast<T *>(p); }
-};
 
 struct CastU64 {
   __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; }
-};
-
-struct Column {
-  int kind = -1;  // 0 i64, 1 f64, 2 str; -1 = the segment lacks this column (predicates on it are false)
-  DevBuf values; // i64 / f64 / u32 ords
-  DevBuf present;
-  std::vector<std::string> dict;
-};
-
-struct Vectors {
-  uint32_t dim = 0;
-  uint64_t n_rows = 0;
-  bool bf16 = false;
-  DevBuf offsets;  // u32[doc_count]
-  DevBuf values;   // f32 or bf16 [n_rows][dim]
-};
-
-struct Segment {
-  uint32_t ord = 0, doc_count = 0;
-  uint64_t n_terms = 0, n_postings = 0, n_post_padded = 0;
-  uint32_t n_blocks = 0, n_deleted = 0;
-  float k1 = 0.9f, b = 0.4f, avgdl = 0, live_docs = 0, min_doc_len = 1;
-  std::vector<uint32_t> h_df;  // host copy (query ordering, validation)
-  DevBuf post_doc, post_tf, term_start, term_df, term_idf, term_max_tf, term_wide, tf_wide, term_blk, blk_max_doc,
-      blk_max_tf, nk, live_bits, post_score, post_pair, cols, term_col, col_tmax;
-  uint32_t n_cols = 0, tmax_stride = 0;
-  uint64_t col_stride = 0;
-  std::vector<int32_t> h_term_col;  // host copy (tests, introspection); empty = no columns
-  SegmentDev dev{};
-  std::vector<Column> columns;
-  std::vector<DevBuf> filter_bits;  // per filter id (owning, or a view into one of filter_slabs)
-  std::vector<std::shared_ptr<DevBuf>> filter_slabs;  // per filter id: the slab a view borrows from (or null)
-  std::vector<uint64_t> h_start;    // host copy of term_start
-  DevBuf filter_ptrs;               // device array of pointers into filter_bits
-  Vectors vec;
-  // term positions (index/postings.rs:117-125), kept for phrase matching: positions of padded posting slot i are
-  // pos[pos_begin[i] .. pos_begin[i+1])
-  DevBuf pos_begin, pos;
-  uint64_t n_positions = 0;
-  bool has_positions = false;
-  bool avgdl_given = false;  // avgdl comes from the segment's .meta file instead of total_tokens / doc_count
-  // further text fields of a handle that scores several ("title:..." next to "body:..."): field 0 is the one the
-  // load call passes directly; these are set before finish_segment, which consumes the device copies
-  struct ExtraField {
-    DevBuf d_lens, d_present;
-    float avgdl = 0.0f;
-  };
-  std::vector<ExtraField> extra_fields;
-  std::vector<uint8_t> h_term_field;      // per term, empty = single field
-  std::vector<float> f_avgdl, f_min_len;  // per field (index 0 = avgdl / min_doc_len)
-  DevBuf term_field;
-  size_t resident() const {
-    return post_doc.bytes + post_tf.bytes + term_start.bytes + term_df.bytes + term_idf.bytes + term_max_tf.bytes +
-           term_wide.bytes + tf_wide.bytes + term_blk.bytes + blk_max_doc.bytes + blk_max_tf.bytes + nk.bytes + term_field.bytes +
-           live_bits.bytes + post_score.bytes + post_pair.bytes + cols.bytes + term_col.bytes + col_tmax.bytes +
-           pos_begin.bytes + pos.bytes;
-  }
-};
-
-struct FilterProg {
-  std::vector<slg_filter_node_t> nodes;
-  std::vector<std::string> strings;
-};
-
-}  // namespace
-
-struct slg_index {
-  int device = 0;
-  int n_sm = 148;
-  size_t smem_optin = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  std::vector<std::unique_ptr<Segment>> segs;
-  std::vector<FilterProg> filters;
-  std::string err;
-  slg_counters_t ctr{};
-  void *pinned = nullptr;        // host staging buffer kept between batches (one batch at a time uses it)
-  size_t pinned_bytes = 0;
-  bool pinned_busy = false;
-  uint32_t tile_docs = 16384;
-  uint32_t ctas_per_sm = 0;  // 0 = as many as shared memory allows
-  uint32_t sub_docs = 2048;  // warp kernel: docs per warp-private accumulator
-  uint32_t kernel_choice = 0;  // 0 auto, 1 CTA-per-item kernel, 2 warp-per-item kernel, 3 register-tile kernel
-  bool staging = true;         // use the resident per-posting scores (seg.post_score) where a kernel can
-  // residency options (slg_set_option), applied to segments loaded afterwards
-  bool resident_scores = true;   // build seg.post_score at load
-  uint32_t dense_den = 8;        // a term gets a dense column when df * dense_den >= doc_count; 0 = no columns
-  uint32_t dense_min_df = 256;   // ... and df >= this
-  uint64_t max_column_bytes = 24ull << 30;
-  uint32_t reg_tile_v = 8;       // sweep kernel: 128 * V docs per tile (4 or 8)
-  uint64_t sweep_min_postings = 0;  // sweep: a query without column terms and sum(df) below this goes to the warp kernel (0 = doc_count / 64)
-  uint32_t seed_docs = 16384;    // sweep: docs of the seed pass
-  uint32_t part_tiles = 0;       // sweep: tiles per unit of work (0 = automatic)
-  uint32_t maxscore_pct = 35;    // pruned warp kernel: non-essential bounds may sum to this % of the k-th score (0 = tile skip only)
-  uint32_t heavy_kernel = 0;     // column front end: 0 = warp kernel summing column terms from their columns, 1 = tile-sweep kernel
-  bool keep_positions = true;    // keep term positions resident when a posting image carries them (SegmentReader keep_positions)
-  // term space of segments loaded from the reference's files: "field:token" key -> term id, in order of first appearance
-  std::unordered_map<std::string, uint32_t> term_ids;
-  std::string term_field;        // the text field(s) those keys belong to, as named at load ("body" or "title,body")
-  std::vector<uint8_t> term_field_of;  // term id -> index of its field in that list
-  // fast-field columns by name (handles are indices into every segment's `columns`)
-  std::vector<std::string> column_names;
-  Segment *find(uint32_t ord) {
-    for (auto &s : segs)
-      if (s->ord == ord) return s.get();
-    return nullptr;
-  }
-};
-
-struct slg_batch {
-  slg_index *ix = nullptr;
-  uint32_t Q = 0, k = 0, cap = 0, U = 0, T = 0;
-  slg_exec_t exec = SLG_EXEC_BM25;
-  bool matcher = false;
-  bool want_stats = false;
-  uint64_t posting_count = 0;
-  // packed inputs
-  std::vector<unsigned char> h_pack;
-  DevBuf d_pack;
-  size_t off_ut_term = 0, off_q_term_off = 0, off_qt_uterm = 0, off_qt_weight = 0, off_qt_group = 0, off_qt_flags = 0,
-         off_q_order = 0, off_q_must = 0, off_q_not = 0, off_q_should = 0, off_q_min = 0, off_q_filter = 0;
-  std::vector<uint32_t> h_ut_term, h_qt_uterm, h_q_term_off;
-  // state + outputs
-  DevBuf ut_rng, ut_tile_ub, thr_key, topk_count, lock, topk_keys, work_counter, stats;
-  DevBuf qterms, qheads;  // warp / register kernel term tables
-  bool staged = false;
-  uint32_t max_terms = 0;
-  bool use_warp = false, use_reg = false;
-  bool has_cursor = false;   // some query carries a search-after cursor
-  std::vector<uint8_t> h_has_cursor;
-  DevBuf cursor_bounds;      // u64 [n_segs][Q]: exclusive upper key bound per segment
-  DevBuf cursor_saw;         // u32 [Q]
-  uint32_t n_cursor_segs = 0;
-  bool has_plan = false;     // some query carries a ScorePlan: CTA-per-item kernel with per-leaf accumulator planes
-  uint32_t max_leaves = 1;
-  size_t off_qt_leaf = 0, off_q_leaves = 0, off_q_plan_off = 0, off_plan_nodes = 0;
-  uint32_t plan_docs = 0, reg_v = 8;
-  uint32_t n_heavy = 0, n_light = 0;  // sweep: slots [0, n_heavy) of q_order are swept, the rest go to the warp kernel
-  uint32_t n_rows = 0, n_light_u = 0; // rows of the sweep's range table; unique terms of the light queries
-  uint32_t sweep_tiles_max = 0, sub_tiles_max = 0;
-  DevBuf d_u_row, d_row_u, d_light_u; // [U] row or ~0; [n_rows] unique term; [n_light_u] unique term
-  DevBuf sw_sstat, sw_weights, sw_ubw, sw_rng, sw_records, d_chunk_cols;  // d_chunk_cols: [S][n_chunks][kSweepStage]
-  uint32_t n_chunks = 0;
-  bool any_weight = false;             // some scored term has weight != 1
-  bool warp_cols = false;              // the warp kernel sums column terms from their dense columns
-  DevBuf seg_hits, seg_counts;  // [S][Q][k], [S][Q]
-  DevBuf out_hits, out_counts;  // merged (aliases seg buffers when S == 1)
-  uint32_t n_segs_run = 0;
-  void *pinned = nullptr;
-  size_t pinned_bytes = 0;
-  bool pinned_from_index = false;
-  ~slg_batch() {
-    if (pinned_from_index) ix->pinned_busy = false;
-    else if (pinned) {
-      if (!ix->pinned_busy && pinned_bytes > ix->pinned_bytes) {  // keep the larger buffer for the next batch
-        if (ix->pinned) cudaFreeHost(ix->pinned);
-        ix->pinned = pinned;
-        ix->pinned_bytes = pinned_bytes;
-      } else {
-        cudaFreeHost(pinned);
-      }
-    }
-  }
-};
-
-namespace {
-
-int32_t fail(slg_index *ix, int32_t code, const char *fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  if (ix) ix->err = buf;
-  else g_open_error = buf;
-  return code;
-}
-
-#define SLG_CUDA(ix, call)                                                                         \
-  do {                                                                                             \
-    cudaError_t e__ = (call);                                                                      \
-    if (e__ != cudaSuccess)                                                                        \
-      return fail((ix), e__ == cudaErrorMemoryAllocation ? SLG_ERR_OOM : SLG_ERR_CUDA, "%s: %s (%s:%d)", #call, \
-                  cudaGetErrorString(e__), __FILE__, __LINE__);                                    \
-  } while (0)
-
-inline void count_launch(slg_index *ix, uint64_t n = 1) { ix->ctr.kernel_launches += n; }
-
-// idf exactly as query/bm25.rs:2 with docs = live docs (api/reader.rs:2985) and df = list length
-// f32::max returns the non-NaN operand (ln of a negative ratio when df > N + 0.5 after deletions): fmaxf
-inline float host_idf(float df, float docs) { return fmaxf(logf((docs - df + 0.5f) / (df + 0.5f)), 0.0f) + 1.0f; }
-inline float host_nk(float dl, float avgdl, float k1, float b) {
-  volatile float norm = avgdl > 0.0f ? dl / avgdl : 1.0f;
-  volatile float bn = b * norm;
-  volatile float omb = 1.0f - b;
-  volatile float s = omb + bn;
-  volatile float r = k1 * s;
-  return r;
-}
-
-size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// SLG_LOAD_TRACE=1: wall-clock time of every residency stage on stderr (the stream is synchronised at each mark)
-struct StageTimer {
-  bool on;
-  cudaStream_t st;
-  std::chrono::steady_clock::time_point t0;
-  explicit StageTimer(cudaStream_t s) : on(getenv("SLG_LOAD_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
-  void mark(const char *what) {
-    if (!on) return;
-    cudaStreamSynchronize(st);
-    const auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[slg load] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
-  }
 };
 
 // --------------------------------------------------------------------------------------------
@@ -401,6 +121,7 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
   d.nk = s->nk.as<float>();
   d.live_bits = s->live_bits.as<uint32_t>();
   d.post_score = nullptr;
+  d.mb_max = nullptr;
   d.cols = nullptr;
   d.term_col = nullptr;
   d.col_tmax = nullptr;
@@ -418,17 +139,13 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
   if (ix->resident_scores && s->n_blocks) {
     SLG_CUDA(ix, s->post_score.alloc(s->n_post_padded * 4));
     SLG_CUDA(ix, cudaMemsetAsync(s->post_score.p, 0, s->n_post_padded * 4, st));
-    slg_score_postings_kernel<<<s->n_blocks, 128, 0, st>>>(d, s->n_blocks, s->post_score.as<float>());
+    SLG_CUDA(ix, s->mb_max.alloc((s->n_post_padded / 32 + 1) * 4));
+    SLG_CUDA(ix, cudaMemsetAsync(s->mb_max.p, 0, (s->n_post_padded / 32 + 1) * 4, st));
+    slg_score_postings_kernel<<<s->n_blocks, 128, 0, st>>>(d, s->n_blocks, s->post_score.as<float>(), s->mb_max.as<float>());
     count_launch(ix);
     SLG_CUDA(ix, cudaGetLastError());
     d.post_score = s->post_score.as<float>();
-    if (s->n_post_padded < (1ull << 32)) {  // the sweep kernel's posting stream (32-bit posting indices)
-      SLG_CUDA(ix, s->post_pair.alloc(s->n_post_padded * 8));
-      slg_pair_postings_kernel<<<ix->n_sm * 8, 256, 0, st>>>(s->post_doc.as<uint32_t>(), s->post_score.as<float>(), s->n_post_padded,
-                                                             s->post_pair.as<uint2>());
-      count_launch(ix);
-      SLG_CUDA(ix, cudaGetLastError());
-    }
+    d.mb_max = s->mb_max.as<float>();
     // dense columns for the high-df terms, largest df first until the byte budget is spent
     if (ix->dense_den && s->doc_count) {
       const uint64_t stride = align_up((uint64_t)s->doc_count, 4096) + 4096;  // a whole staged block past the end stays in bounds and zero
@@ -438,7 +155,7 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
         if (df >= ix->dense_min_df && df * ix->dense_den >= s->doc_count) cand.push_back((uint32_t)t);
       }
       std::sort(cand.begin(), cand.end(), [&](uint32_t a, uint32_t b2) { return s->h_df[a] != s->h_df[b2] ? s->h_df[a] > s->h_df[b2] : a < b2; });
-      const uint64_t max_cols = std::min<uint64_t>(65535, ix->max_column_bytes / (stride * 4));  // 16-bit column ids in the sweep records
+      const uint64_t max_cols = std::min<uint64_t>(65535, ix->max_column_bytes / (stride * 4));
       if (cand.size() > max_cols) cand.resize(max_cols);
       if (!cand.empty()) {
         std::vector<int32_t> tcol(s->n_terms, -1);
@@ -587,137 +304,6 @@ int32_t to_device(slg_index *ix, const T *src, size_t n, int space, DevBuf &tmp,
   return SLG_OK;
 }
 
-// --------------------------------------------------------------------------------------------
-// search
-int32_t select_smem(slg_index *ix, uint32_t tile_docs, uint32_t cap, bool matcher, size_t *out, uint32_t planes = 1) {
-  size_t smem = (size_t)tile_docs * 4 * planes + (size_t)cap * 8 + (matcher ? tile_docs : 0);
-  if (smem + 1024 > ix->smem_optin)
-    return fail(ix, SLG_ERR_UNSUPPORTED, "tile of %u docs with k buffer %u needs %zu B shared memory", tile_docs, cap, smem);
-  *out = smem;
-  return SLG_OK;
-}
-
-template <bool M, bool P, bool S, bool PL = false>
-int32_t launch_score_t(slg_index *ix, const SegmentDev &sd, const BatchDev &bd, size_t smem, int grid) {
-  auto kern = slg_score_tiles_kernel<M, P, S, PL>;
-  SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kThreads, smem, ix->stream>>>(sd, bd);
-  SLG_CUDA(ix, cudaGetLastError());
-  return SLG_OK;
-}
-
-int32_t launch_score(slg_index *ix, bool matcher, bool prune, bool stats, const SegmentDev &sd, const BatchDev &bd,
-                     size_t smem, int grid, bool plan = false) {
-  int sel = (matcher ? 4 : 0) | (prune ? 2 : 0) | (stats ? 1 : 0);
-  if (plan) {  // ScorePlan batches: the matcher form serves both (plain OR queries carry an empty group program)
-    switch (sel & 3) {
-      case 0: return matcher ? launch_score_t<true, false, false, true>(ix, sd, bd, smem, grid)
-                             : launch_score_t<false, false, false, true>(ix, sd, bd, smem, grid);
-      case 1: return matcher ? launch_score_t<true, false, true, true>(ix, sd, bd, smem, grid)
-                             : launch_score_t<false, false, true, true>(ix, sd, bd, smem, grid);
-      case 2: return matcher ? launch_score_t<true, true, false, true>(ix, sd, bd, smem, grid)
-                             : launch_score_t<false, true, false, true>(ix, sd, bd, smem, grid);
-      default: return matcher ? launch_score_t<true, true, true, true>(ix, sd, bd, smem, grid)
-                              : launch_score_t<false, true, true, true>(ix, sd, bd, smem, grid);
-    }
-  }
-  switch (sel) {
-    case 0: return launch_score_t<false, false, false>(ix, sd, bd, smem, grid);
-    case 1: return launch_score_t<false, false, true>(ix, sd, bd, smem, grid);
-    case 2: return launch_score_t<false, true, false>(ix, sd, bd, smem, grid);
-    case 3: return launch_score_t<false, true, true>(ix, sd, bd, smem, grid);
-    case 4: return launch_score_t<true, false, false>(ix, sd, bd, smem, grid);
-    case 5: return launch_score_t<true, false, true>(ix, sd, bd, smem, grid);
-    case 6: return launch_score_t<true, true, false>(ix, sd, bd, smem, grid);
-    default: return launch_score_t<true, true, true>(ix, sd, bd, smem, grid);
-  }
-}
-
-template <bool M, bool P, bool S, bool G, bool C = false, bool PL = false>
-int32_t launch_warp_t(slg_index *ix, const SegmentDev &sd, const WarpBatchDev &wb, size_t smem, int grid) {
-  auto kern = slg_score_warp_kernel<M, P, S, G, C, PL>;
-  SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kThreads, smem, ix->stream>>>(sd, wb);
-  SLG_CUDA(ix, cudaGetLastError());
-  return SLG_OK;
-}
-
-int32_t launch_warp(slg_index *ix, bool matcher, bool prune, bool stats, bool staged, bool cols, const SegmentDev &sd,
-                    const WarpBatchDev &wb, size_t smem, int grid, bool plan = false) {
-  int sel = (matcher ? 4 : 0) | (prune ? 2 : 0) | (stats ? 1 : 0);
-  if (plan) {  // ScorePlans: resident scores for plain OR queries, in-place scoring + group masks otherwise
-    const bool st = staged && !matcher;
-    switch (sel & 3) {
-      case 0: return st ? launch_warp_t<false, false, false, true, false, true>(ix, sd, wb, smem, grid)
-                        : launch_warp_t<true, false, false, false, false, true>(ix, sd, wb, smem, grid);
-      case 1: return st ? launch_warp_t<false, false, true, true, false, true>(ix, sd, wb, smem, grid)
-                        : launch_warp_t<true, false, true, false, false, true>(ix, sd, wb, smem, grid);
-      case 2: return st ? launch_warp_t<false, true, false, true, false, true>(ix, sd, wb, smem, grid)
-                        : launch_warp_t<true, true, false, false, false, true>(ix, sd, wb, smem, grid);
-      default: return st ? launch_warp_t<false, true, true, true, false, true>(ix, sd, wb, smem, grid)
-                         : launch_warp_t<true, true, true, false, false, true>(ix, sd, wb, smem, grid);
-    }
-  }
-  if (staged && !matcher && cols) {
-    switch (sel) {
-      case 0: return launch_warp_t<false, false, false, true, true>(ix, sd, wb, smem, grid);
-      case 1: return launch_warp_t<false, false, true, true, true>(ix, sd, wb, smem, grid);
-      case 2: return launch_warp_t<false, true, false, true, true>(ix, sd, wb, smem, grid);
-      default: return launch_warp_t<false, true, true, true, true>(ix, sd, wb, smem, grid);
-    }
-  }
-  if (staged && !matcher) {
-    switch (sel) {
-      case 0: return launch_warp_t<false, false, false, true>(ix, sd, wb, smem, grid);
-      case 1: return launch_warp_t<false, false, true, true>(ix, sd, wb, smem, grid);
-      case 2: return launch_warp_t<false, true, false, true>(ix, sd, wb, smem, grid);
-      default: return launch_warp_t<false, true, true, true>(ix, sd, wb, smem, grid);
-    }
-  }
-  switch (sel) {
-    case 0: return launch_warp_t<false, false, false, false>(ix, sd, wb, smem, grid);
-    case 1: return launch_warp_t<false, false, true, false>(ix, sd, wb, smem, grid);
-    case 2: return launch_warp_t<false, true, false, false>(ix, sd, wb, smem, grid);
-    case 3: return launch_warp_t<false, true, true, false>(ix, sd, wb, smem, grid);
-    case 4: return launch_warp_t<true, false, false, false>(ix, sd, wb, smem, grid);
-    case 5: return launch_warp_t<true, false, true, false>(ix, sd, wb, smem, grid);
-    case 6: return launch_warp_t<true, true, false, false>(ix, sd, wb, smem, grid);
-    default: return launch_warp_t<true, true, true, false>(ix, sd, wb, smem, grid);
-  }
-}
-
-template <int V, bool P, bool S, bool W>
-int32_t launch_sweep_t(slg_index *ix, const SegmentDev &sd, const SweepDev &sw, int grid) {
-  auto kern = slg_score_sweep_kernel<V, P, S, W>;
-  const size_t smem = sweep_smem_bytes<V>();
-  if (smem + 1024 > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "sweep kernel needs %zu B shared memory", smem);
-  SLG_CUDA(ix, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kSweepThreads, smem, ix->stream>>>(sd, sw);
-  SLG_CUDA(ix, cudaGetLastError());
-  return SLG_OK;
-}
-
-template <int V>
-int32_t launch_sweep_v(slg_index *ix, bool prune, bool stats, bool weights, const SegmentDev &sd, const SweepDev &sw, int grid) {
-  switch ((prune ? 4 : 0) | (stats ? 2 : 0) | (weights ? 1 : 0)) {
-    case 0: return launch_sweep_t<V, false, false, false>(ix, sd, sw, grid);
-    case 1: return launch_sweep_t<V, false, false, true>(ix, sd, sw, grid);
-    case 2: return launch_sweep_t<V, false, true, false>(ix, sd, sw, grid);
-    case 3: return launch_sweep_t<V, false, true, true>(ix, sd, sw, grid);
-    case 4: return launch_sweep_t<V, true, false, false>(ix, sd, sw, grid);
-    case 5: return launch_sweep_t<V, true, false, true>(ix, sd, sw, grid);
-    case 6: return launch_sweep_t<V, true, true, false>(ix, sd, sw, grid);
-    default: return launch_sweep_t<V, true, true, true>(ix, sd, sw, grid);
-  }
-}
-
-int32_t launch_sweep(slg_index *ix, uint32_t v, bool prune, bool stats, bool weights, const SegmentDev &sd, const SweepDev &sw, int grid) {
-  switch (v) {
-    case 4: return launch_sweep_v<4>(ix, prune, stats, weights, sd, sw, grid);
-    default: return launch_sweep_v<8>(ix, prune, stats, weights, sd, sw, grid);
-  }
-}
-
 }  // namespace
 
 /* ================================================================================================ C ABI */
@@ -725,7 +311,7 @@ extern "C" {
 
 const char *slg_version(void) { return "searchlite-b200 0.1 (sm_100a)"; }
 
-const char *slg_last_error(const slg_index_t *ix) { return ix ? ix->err.c_str() : g_open_error.c_str(); }
+const char *slg_last_error(const slg_index_t *ix) { return ix ? ix->err.c_str() : open_error().c_str(); }
 
 int32_t slg_open(int32_t device, slg_index_t **out) {
   if (!out) return fail(nullptr, SLG_ERR_INVALID, "out is NULL");
@@ -804,18 +390,9 @@ int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
   else if (n == "dense_den") ix->dense_den = (uint32_t)value;
   else if (n == "dense_min_df") ix->dense_min_df = (uint32_t)value;
   else if (n == "max_column_bytes") ix->max_column_bytes = value;
-  else if (n == "reg_tile_v") {
-    if (value == 4)  // known issue: the 4-wide variant faulted intermittently on the B200 boxes, ~1 batch in 40
-      return fail(ix, SLG_ERR_UNSUPPORTED, "reg_tile_v 4 is disabled: intermittent illegal memory access in the 4-wide tile-sweep variant");
-    if (value != 8) return fail(ix, SLG_ERR_INVALID, "reg_tile_v must be 8");
-    ix->reg_tile_v = (uint32_t)value;
-  } else if (n == "sweep_min_postings") ix->sweep_min_postings = value;
-  else if (n == "seed_docs") ix->seed_docs = (uint32_t)value;
-  else if (n == "part_tiles") ix->part_tiles = (uint32_t)value;
   else if (n == "maxscore_pct") ix->maxscore_pct = (uint32_t)std::min<uint64_t>(value, 100);
-  else if (n == "heavy_kernel") {
-    if (value > 1) return fail(ix, SLG_ERR_INVALID, "heavy_kernel must be 0 (warp kernel + columns) or 1 (tile sweep)");
-    ix->heavy_kernel = (uint32_t)value;
+  else if (n == "heavy_kernel") {  // the tile-sweep front end of round 1 is gone (it carried an unlocalised intermittent fault)
+    if (value != 0) return fail(ix, SLG_ERR_UNSUPPORTED, "heavy_kernel 1 (tile-sweep kernel) was removed; the column path is the items kernel");
   }
   else if (n == "keep_positions") ix->keep_positions = value != 0;
   else return fail(ix, SLG_ERR_INVALID, "unknown option '%s'", name);
@@ -1862,741 +1439,6 @@ int32_t slg_filter_free(slg_index_t *ix, int32_t filter_id) {
   return SLG_OK;
 }
 
-/* ---- batched search ---- */
-int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t n_queries, uint32_t k, slg_exec_t exec,
-                          uint32_t bmw_block_size, slg_batch_t **out) {
-  if (!ix || !out) return SLG_ERR_INVALID;
-  *out = nullptr;
-  if (!queries || n_queries == 0) return fail(ix, SLG_ERR_INVALID, "empty query batch");
-  if (k == 0) return fail(ix, SLG_ERR_INVALID, "k must be > 0 (the reference bails on limit == 0, api/reader.rs:2540)");
-  if (k > SLG_MAX_K) return fail(ix, SLG_ERR_UNSUPPORTED, "k = %u exceeds the built maximum %u", k, SLG_MAX_K);
-  if (exec != SLG_EXEC_BM25 && exec != SLG_EXEC_WAND && exec != SLG_EXEC_BMW) return fail(ix, SLG_ERR_INVALID, "unknown execution strategy");
-  if (ix->segs.empty()) return fail(ix, SLG_ERR_INVALID, "no segment loaded");
-  (void)bmw_block_size;  // bounds are taken over the stored 128-posting blocks; any block size gives the same (exact) result
-  SLG_CUDA(ix, cudaSetDevice(ix->device));
-  PoolScope pool_scope(ix->stream);
-  auto bt = std::make_unique<slg_batch>();
-  bt->ix = ix;
-  bt->Q = n_queries;
-  bt->k = k;
-  bt->exec = exec;
-  bt->cap = std::max(1024u, 1u << (32 - __builtin_clz(4 * k - 1)));
-  const Segment *s0 = ix->segs[0].get();
-  uint64_t n_terms_space = 0;
-  for (auto &s : ix->segs) n_terms_space = std::max(n_terms_space, s->n_terms);
-
-  std::unordered_map<uint32_t, uint32_t> umap;
-  std::vector<uint32_t> &ut = bt->h_ut_term;
-  std::vector<uint32_t> &q_off = bt->h_q_term_off;
-  std::vector<uint32_t> &qt_u = bt->h_qt_uterm;
-  std::vector<float> qt_w;
-  std::vector<uint8_t> qt_g, qt_f, q_must(n_queries, 0), q_not(n_queries, 0), q_should(n_queries, 0), q_min(n_queries, 0);
-  std::vector<int32_t> q_filter(n_queries, -1);
-  std::vector<uint64_t> q_cost(n_queries, 0);
-  std::vector<uint8_t> qt_leaf, q_leaves(n_queries, 0);
-  std::vector<uint32_t> q_plan_off(n_queries + 1, 0);
-  std::vector<PlanNodeDev> plan_nodes;
-  q_off.assign(n_queries + 1, 0);
-  bool matcher = false;
-  for (uint32_t qi = 0; qi < n_queries; qi++) {
-    const slg_query_t &q = queries[qi];
-    if (q.n_terms && !q.terms) return fail(ix, SLG_ERR_INVALID, "query %u has no terms pointer", qi);
-    if (q.n_groups > 8) return fail(ix, SLG_ERR_UNSUPPORTED, "query %u has %u term groups; this build supports 8", qi, q.n_groups);
-    if (q.n_groups && !q.group_role) return fail(ix, SLG_ERR_INVALID, "query %u has no group roles", qi);
-    if (q.filter_id >= (int32_t)ix->filters.size()) return fail(ix, SLG_ERR_INVALID, "query %u names unknown filter %d", qi, q.filter_id);
-    q_filter[qi] = q.filter_id < 0 ? -1 : q.filter_id;
-    if (q.n_plan_nodes) {
-      // ScorePlan: a well-formed postfix program over leaves 0..leaf_count-1 (query/planner.rs:113-164)
-      if (!q.plan) return fail(ix, SLG_ERR_INVALID, "query %u has no plan pointer", qi);
-      if (q.leaf_count == 0 || q.leaf_count > SLG_MAX_PLAN_LEAVES)
-        return fail(ix, SLG_ERR_UNSUPPORTED, "query %u: a plan needs 1..%u leaves, got %u", qi, SLG_MAX_PLAN_LEAVES, q.leaf_count);
-      if (q.n_plan_nodes > SLG_MAX_PLAN_NODES)
-        return fail(ix, SLG_ERR_UNSUPPORTED, "query %u: plan of %u nodes; the maximum is %u", qi, q.n_plan_nodes, SLG_MAX_PLAN_NODES);
-      uint32_t depth = 0;
-      for (uint32_t n = 0; n < q.n_plan_nodes; n++) {
-        const slg_plan_node_t &pn = q.plan[n];
-        if (pn.op == SLG_PLAN_LEAF) {
-          if (pn.arg >= q.leaf_count) return fail(ix, SLG_ERR_INVALID, "query %u plan node %u: leaf %u out of range", qi, n, pn.arg);
-          depth++;
-        } else if (pn.op == SLG_PLAN_SUM || pn.op == SLG_PLAN_DISMAX) {
-          if (pn.arg > depth) return fail(ix, SLG_ERR_INVALID, "query %u plan node %u: %u children but %u values", qi, n, pn.arg, depth);
-          if (pn.op == SLG_PLAN_DISMAX && !(pn.tie_breaker >= 0.0f && pn.tie_breaker <= 1.0f))
-            return fail(ix, SLG_ERR_INVALID, "query %u plan node %u: tie_breaker must lie in [0, 1]", qi, n);  // planner.rs:850-858
-          depth = depth - pn.arg + 1;
-        } else {
-          return fail(ix, SLG_ERR_INVALID, "query %u plan node %u: unknown op %u", qi, n, pn.op);
-        }
-        plan_nodes.push_back(PlanNodeDev{pn.op, pn.arg, pn.tie_breaker});
-      }
-      if (depth != 1) return fail(ix, SLG_ERR_INVALID, "query %u: the plan leaves %u values instead of one", qi, depth);
-      q_leaves[qi] = (uint8_t)q.leaf_count;
-      bt->has_plan = true;
-      bt->max_leaves = std::max(bt->max_leaves, q.leaf_count);
-    }
-    q_plan_off[qi + 1] = (uint32_t)plan_nodes.size();
-    if (q.has_cursor) {
-      if (!(q.cursor.score >= 0.0f) || !std::isfinite(q.cursor.score))
-        return fail(ix, SLG_ERR_INVALID, "query %u: the cursor score must be finite and >= 0", qi);
-      bt->has_cursor = true;
-    }
-    if (q.filter_id >= 0)
-      for (auto &sg : ix->segs)
-        if ((size_t)q.filter_id >= sg->filter_bits.size() || !sg->filter_bits[q.filter_id].p)
-          return fail(ix, SLG_ERR_INVALID, "query %u names filter %d, which is freed or not compiled for segment %u", qi, q.filter_id, sg->ord);
-    uint32_t kept = 0;
-    bool need_mask = q.n_groups > 0;
-    for (uint32_t t = 0; t < q.n_terms; t++) {
-      const slg_term_t &tm = q.terms[t];
-      if (tm.term_id == 0xFFFFFFFFu || tm.term_id >= n_terms_space) continue;  // seg.postings(key) == None
-      bool scored = tm.flags & SLG_TERM_SCORED;
-      if (scored && !(tm.weight > 0.0f && std::isfinite(tm.weight)))
-        return fail(ix, SLG_ERR_UNSUPPORTED, "query %u term %u: weight must be finite and > 0", qi, t);
-      if (q.n_groups && tm.group >= q.n_groups) return fail(ix, SLG_ERR_INVALID, "query %u term %u: group out of range", qi, t);
-      if (scored && q.n_plan_nodes && tm.leaf >= q.leaf_count)
-        return fail(ix, SLG_ERR_INVALID, "query %u term %u: leaf %u but the plan has %u leaves", qi, t, tm.leaf, q.leaf_count);  // wand.rs:489-494
-      if (!scored) need_mask = true;
-      auto it = umap.find(tm.term_id);
-      uint32_t u;
-      if (it == umap.end()) {
-        u = (uint32_t)ut.size();
-        umap.emplace(tm.term_id, u);
-        ut.push_back(tm.term_id);
-      } else {
-        u = it->second;
-      }
-      qt_u.push_back(u);
-      qt_w.push_back(tm.weight);
-      qt_g.push_back((uint8_t)(q.n_groups ? tm.group : 0));
-      qt_f.push_back(scored ? 1 : 0);
-      qt_leaf.push_back((uint8_t)(scored && q.n_plan_nodes ? tm.leaf : 0));
-      if (scored && tm.term_id < s0->n_terms) q_cost[qi] += s0->h_df[tm.term_id];
-      kept++;
-    }
-    if (kept > SLG_MAX_QUERY_TERMS) return fail(ix, SLG_ERR_UNSUPPORTED, "query %u has %u terms; the maximum is %u", qi, kept, SLG_MAX_QUERY_TERMS);
-    q_off[qi + 1] = q_off[qi] + kept;
-    bt->max_terms = std::max(bt->max_terms, kept);
-    if (need_mask) {
-      matcher = true;
-      if (q.n_groups == 0) {  // non-scored terms without groups: plain OR over group 0
-        q_should[qi] = 1;
-        q_min[qi] = 1;
-      }
-      for (uint32_t g = 0; g < q.n_groups; g++) {
-        uint8_t bit = (uint8_t)(1u << g);
-        if (q.group_role[g] == SLG_ROLE_MUST) q_must[qi] |= bit;
-        else if (q.group_role[g] == SLG_ROLE_MUST_NOT) q_not[qi] |= bit;
-        else q_should[qi] |= bit;
-      }
-      if (q.n_groups) q_min[qi] = (uint8_t)std::min<uint32_t>(q.min_should, 255);
-    }
-    bt->posting_count += q_cost[qi];
-  }
-  if (bt->has_cursor) {
-    if (ix->kernel_choice == 3 && ix->heavy_kernel == 1)
-      return fail(ix, SLG_ERR_UNSUPPORTED, "cursors are not handled by the tile-sweep kernel (heavy_kernel 1)");
-    // key.cmp(cursor) (query/sort.rs:80-93: score desc, segment_ord asc, doc_id asc) folded into one exclusive bound on
-    // the 64-bit keys of each segment: same segment (score, ~doc); an earlier segment loses ties; a later one wins them
-    const uint32_t n_segs = (uint32_t)ix->segs.size();
-    std::vector<unsigned long long> bounds((size_t)n_segs * n_queries, ~0ull);
-    bt->h_has_cursor.assign(n_queries, 0);
-    for (uint32_t qi = 0; qi < n_queries; qi++) {
-      const slg_query_t &q = queries[qi];
-      if (!q.has_cursor) continue;
-      bt->h_has_cursor[qi] = 1;
-      uint32_t sb;
-      std::memcpy(&sb, &q.cursor.score, 4);
-      for (uint32_t si = 0; si < n_segs; si++) {
-        const uint32_t ord = ix->segs[si]->ord;
-        unsigned long long b;
-        if (ord == q.cursor.segment_ord) b = ((unsigned long long)sb << 32) | (unsigned long long)(0xFFFFFFFFu - q.cursor.doc_id);
-        else if (ord < q.cursor.segment_ord) b = (unsigned long long)sb << 32;
-        else b = ((unsigned long long)sb + 1ull) << 32;
-        bounds[(size_t)si * n_queries + qi] = b;
-      }
-    }
-    bt->n_cursor_segs = n_segs;
-    SLG_CUDA(ix, bt->cursor_bounds.alloc(bounds.size() * 8));
-    SLG_CUDA(ix, bt->cursor_saw.alloc((size_t)n_queries * 4));
-    SLG_CUDA(ix, cudaMemcpyAsync(bt->cursor_bounds.p, bounds.data(), bounds.size() * 8, cudaMemcpyHostToDevice, ix->stream));
-    SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));  // bounds is a local
-  }
-  bt->matcher = matcher;
-  bt->U = (uint32_t)ut.size();
-  bt->T = (uint32_t)qt_u.size();
-  // kernel selection
-  const bool small = k <= kWarpMaxK && bt->max_terms <= kWarpMaxTerms;
-  bool all_scores = ix->staging;
-  for (auto &s : ix->segs) all_scores = all_scores && (s->post_score.p != nullptr || s->n_blocks == 0);
-  bool sweepable = all_scores;  // the sweep addresses postings with 32-bit indices
-  for (auto &s : ix->segs) sweepable = sweepable && (s->post_pair.p != nullptr || s->n_blocks == 0);
-  // tile-sweep kernel: plain OR queries (no matcher), small k, few terms, resident scores
-  // column front end: plain OR queries (no matcher), small k, few terms, resident scores and columns
-  if (bt->has_plan && ix->kernel_choice == 3)
-    return fail(ix, SLG_ERR_UNSUPPORTED, "ScorePlan queries run on the warp or CTA-per-item kernel (kernel_choice 0, 1 or 2)");
-  bt->use_reg = ix->kernel_choice == 3 || (ix->kernel_choice == 0 && small && !matcher && sweepable && !bt->has_plan);
-  if (bt->use_reg && !(small && !matcher && sweepable))
-    return fail(ix, SLG_ERR_UNSUPPORTED,
-                "the sweep kernel handles plain OR queries, k <= %u, <= %u terms per query, resident scores, < 2^32 postings per segment",
-                kWarpMaxK, kWarpMaxTerms);
-  bt->use_warp = !bt->use_reg && (ix->kernel_choice == 2 || (ix->kernel_choice == 0 && small));
-  if (bt->use_warp && !small)
-    return fail(ix, SLG_ERR_UNSUPPORTED, "the warp kernel handles k <= %u and <= %u terms per query", kWarpMaxK, kWarpMaxTerms);
-
-  // processing order inside a tile: most expensive queries first.  Sweep kernel: the "heavy" queries
-  // (a column term in any segment, or enough postings that most tiles hold some) come first and are
-  // swept; the "light" rest is scored posting-driven by the warp kernel.
-  std::vector<uint32_t> order(n_queries);
-  for (uint32_t i = 0; i < n_queries; i++) order[i] = i;
-  std::vector<uint8_t> heavy(n_queries, 0);
-  if (bt->use_reg) {
-    std::vector<uint8_t> u_col(bt->U, 0);
-    for (uint32_t u = 0; u < bt->U; u++)
-      for (auto &sg : ix->segs)
-        if (ut[u] < sg->h_term_col.size() && sg->h_term_col[ut[u]] >= 0) u_col[u] = 1;
-    uint64_t max_docs = 0;
-    for (auto &sg : ix->segs) max_docs = std::max<uint64_t>(max_docs, sg->doc_count);
-    bt->warp_cols = ix->sub_docs <= 4096;
-    for (uint32_t qi = 0; qi < n_queries && ix->heavy_kernel == 1 && !bt->has_cursor; qi++) {
-      bool h = q_cost[qi] >= (ix->sweep_min_postings ? ix->sweep_min_postings : std::max<uint64_t>(1, max_docs / 64));
-      for (uint32_t t = q_off[qi]; t < q_off[qi + 1] && !h; t++) h = u_col[qt_u[t]] != 0;
-      heavy[qi] = h;
-      bt->n_heavy += h;
-    }
-    bt->n_light = n_queries - bt->n_heavy;
-  }
-  // swept queries are ordered by their first column term (segment 0): the warps of a CTA walk
-  // neighbouring slots at the same time and share that column's tile slice through L1
-  std::vector<uint32_t> q_col(n_queries, 0xFFFFFFFFu);
-  if (bt->use_reg && !ix->segs.empty()) {
-    const Segment *sg0 = ix->segs[0].get();
-    for (uint32_t qi = 0; qi < n_queries; qi++)
-      for (uint32_t t = q_off[qi]; t < q_off[qi + 1]; t++) {
-        const uint32_t term = ut[qt_u[t]];
-        if (term < sg0->h_term_col.size() && sg0->h_term_col[term] >= 0) {
-          q_col[qi] = (uint32_t)sg0->h_term_col[term];
-          break;
-        }
-      }
-  }
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b2) {
-    if (heavy[a] != heavy[b2]) return heavy[a] > heavy[b2];
-    if (q_col[a] != q_col[b2]) return q_col[a] < q_col[b2];
-    return q_cost[a] > q_cost[b2];
-  });
-
-  // pack all inputs into one buffer: one H2D copy per batch
-  size_t pos = 0;
-  auto place = [&](size_t bytes) {
-    size_t o = pos;
-    pos = align_up(pos + std::max<size_t>(bytes, 4), 256);
-    return o;
-  };
-  bt->off_ut_term = place((size_t)bt->U * 4);
-  bt->off_q_term_off = place((size_t)(n_queries + 1) * 4);
-  bt->off_qt_uterm = place((size_t)bt->T * 4);
-  bt->off_qt_weight = place((size_t)bt->T * 4);
-  bt->off_qt_group = place(bt->T);
-  bt->off_qt_flags = place(bt->T);
-  bt->off_q_order = place((size_t)n_queries * 4);
-  bt->off_q_must = place(n_queries);
-  bt->off_q_not = place(n_queries);
-  bt->off_q_should = place(n_queries);
-  bt->off_q_min = place(n_queries);
-  bt->off_q_filter = place((size_t)n_queries * 4);
-  if (bt->has_plan) {
-    bt->off_qt_leaf = place(bt->T);
-    bt->off_q_leaves = place(n_queries);
-    bt->off_q_plan_off = place((size_t)(n_queries + 1) * 4);
-    bt->off_plan_nodes = place(plan_nodes.size() * sizeof(PlanNodeDev));
-  }
-  bt->h_pack.assign(pos, 0);
-  unsigned char *hp = bt->h_pack.data();
-  auto put = [&](size_t off, const void *src, size_t bytes) {
-    if (bytes) std::memcpy(hp + off, src, bytes);
-  };
-  put(bt->off_ut_term, ut.data(), (size_t)bt->U * 4);
-  put(bt->off_q_term_off, q_off.data(), (size_t)(n_queries + 1) * 4);
-  put(bt->off_qt_uterm, qt_u.data(), (size_t)bt->T * 4);
-  put(bt->off_qt_weight, qt_w.data(), (size_t)bt->T * 4);
-  put(bt->off_qt_group, qt_g.data(), bt->T);
-  put(bt->off_qt_flags, qt_f.data(), bt->T);
-  put(bt->off_q_order, order.data(), (size_t)n_queries * 4);
-  put(bt->off_q_must, q_must.data(), n_queries);
-  put(bt->off_q_not, q_not.data(), n_queries);
-  put(bt->off_q_should, q_should.data(), n_queries);
-  put(bt->off_q_min, q_min.data(), n_queries);
-  put(bt->off_q_filter, q_filter.data(), (size_t)n_queries * 4);
-  if (bt->has_plan) {
-    put(bt->off_qt_leaf, qt_leaf.data(), bt->T);
-    put(bt->off_q_leaves, q_leaves.data(), n_queries);
-    put(bt->off_q_plan_off, q_plan_off.data(), (size_t)(n_queries + 1) * 4);
-    put(bt->off_plan_nodes, plan_nodes.data(), plan_nodes.size() * sizeof(PlanNodeDev));
-  }
-  SLG_CUDA(ix, bt->d_pack.alloc(pos));
-  SLG_CUDA(ix, cudaMemcpyAsync(bt->d_pack.p, hp, pos, cudaMemcpyHostToDevice, ix->stream));
-  ix->ctr.last_h2d_bytes = pos;
-
-  bt->plan_docs = bt->use_reg ? ix->sub_docs : (bt->use_warp ? ix->sub_docs : ix->tile_docs);
-  if (bt->has_plan) {
-    // one accumulator plane per leaf: shrink the doc tile so that the planes together stay near the configured tile
-    uint32_t planes = 1;
-    while (planes < bt->max_leaves) planes <<= 1;
-    bt->plan_docs = bt->use_warp ? std::max(512u, (ix->sub_docs / planes) & ~127u) : std::max(1024u, (ix->tile_docs / planes) & ~1023u);
-  }
-  const uint32_t plan_docs = bt->plan_docs;
-  uint32_t max_tiles = 0;
-  for (auto &s : ix->segs) max_tiles = std::max(max_tiles, (s->doc_count + plan_docs - 1) / plan_docs);
-  max_tiles = std::max(max_tiles, 1u);
-  const uint32_t n_warp_slots = bt->use_reg ? bt->n_light : n_queries;
-  if (bt->use_warp || (bt->use_reg && bt->n_light)) {
-    SLG_CUDA(ix, bt->qterms.alloc((size_t)n_warp_slots * kWarpMaxTerms * sizeof(QTerm)));
-    SLG_CUDA(ix, bt->qheads.alloc((size_t)n_warp_slots * sizeof(QHead)));
-    // the (doc, score) stream form of the warp kernel: no matcher, resident scores
-    bt->staged = all_scores && !matcher && bt->U > 0;
-  }
-  if (bt->use_reg) {
-    bt->reg_v = ix->reg_tile_v;
-    const size_t nseg = ix->segs.size();
-    // rows of the sweep's range table: the unique terms of the heavy queries; the light queries'
-    // unique terms get rows of the warp kernel's table
-    std::vector<uint32_t> u_row(std::max(bt->U, 1u), 0xFFFFFFFFu), row_u, light_u;
-    std::vector<uint8_t> u_light(bt->U, 0);
-    std::vector<uint32_t> inst(bt->U, 0);
-    for (uint32_t qi = 0; qi < n_queries; qi++)
-      for (uint32_t t = q_off[qi]; t < q_off[qi + 1]; t++) {
-        const uint32_t u = qt_u[t];
-        if (heavy[qi]) {
-          inst[u]++;
-          if (u_row[u] == 0xFFFFFFFFu) {
-            u_row[u] = (uint32_t)row_u.size();
-            row_u.push_back(u);
-          }
-        } else if (!u_light[u]) {
-          u_light[u] = 1;
-          light_u.push_back(u);
-        }
-      }
-    bt->n_rows = (uint32_t)row_u.size();
-    bt->n_light_u = (uint32_t)light_u.size();
-    for (auto &sg : ix->segs) {
-      const uint32_t tile = 128u * bt->reg_v;
-      bt->sweep_tiles_max = std::max(bt->sweep_tiles_max, std::max(1u, (sg->doc_count + tile - 1) / tile));
-    }
-    // per segment and chunk of kSweepChunk swept slots: the columns staged in shared memory — the ones
-    // the chunk's queries name most
-    bt->n_chunks = (bt->n_heavy + kSweepChunk - 1) / kSweepChunk;
-    std::vector<uint32_t> chunk_cols(std::max<size_t>(1, nseg * bt->n_chunks * kSweepStage), 0xFFFFFFFFu);
-    for (size_t si = 0; si < nseg; si++) {
-      const Segment *sg = ix->segs[si].get();
-      if (sg->h_term_col.empty()) continue;
-      for (uint32_t ch = 0; ch < bt->n_chunks; ch++) {
-        std::vector<std::pair<uint32_t, uint32_t>> cnt;  // (column, uses)
-        for (uint32_t sl = ch * kSweepChunk; sl < std::min(bt->n_heavy, (ch + 1) * kSweepChunk); sl++) {
-          const uint32_t qi = order[sl];
-          for (uint32_t t = q_off[qi]; t < q_off[qi + 1]; t++) {
-            const uint32_t term = ut[qt_u[t]];
-            if (term >= sg->h_term_col.size() || sg->h_term_col[term] < 0) continue;
-            const uint32_t col = (uint32_t)sg->h_term_col[term];
-            auto it = std::find_if(cnt.begin(), cnt.end(), [&](const auto &p2) { return p2.first == col; });
-            if (it == cnt.end()) cnt.emplace_back(col, 1u);
-            else it->second++;
-          }
-        }
-        std::stable_sort(cnt.begin(), cnt.end(), [](const auto &a, const auto &b2) { return a.second > b2.second; });
-        for (size_t i = 0; i < cnt.size() && i < kSweepStage; i++) chunk_cols[(si * bt->n_chunks + ch) * kSweepStage + i] = cnt[i].first;
-      }
-    }
-    auto upload = [&](DevBuf &d, const void *src, size_t bytes) -> cudaError_t {
-      cudaError_t e = d.alloc(bytes);
-      if (e != cudaSuccess || !bytes) return e;
-      ix->ctr.last_h2d_bytes += bytes;
-      return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, ix->stream);
-    };
-    SLG_CUDA(ix, upload(bt->d_chunk_cols, chunk_cols.data(), chunk_cols.size() * 4));
-    SLG_CUDA(ix, upload(bt->d_u_row, u_row.data(), u_row.size() * 4));
-    SLG_CUDA(ix, upload(bt->d_row_u, row_u.data(), row_u.size() * 4));
-    SLG_CUDA(ix, upload(bt->d_light_u, light_u.data(), light_u.size() * 4));
-    SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));  // host vectors go out of scope
-    if (bt->n_heavy) {
-      for (float w : qt_w) bt->any_weight = bt->any_weight || w != 1.0f;
-      SLG_CUDA(ix, bt->sw_sstat.alloc((size_t)bt->n_heavy * kSweepSlotWords * 4));
-      SLG_CUDA(ix, bt->sw_weights.alloc((size_t)bt->n_heavy * 8 * 4));
-      SLG_CUDA(ix, bt->sw_ubw.alloc((size_t)bt->n_heavy * 8 * 4));
-      SLG_CUDA(ix, bt->sw_records.alloc((size_t)bt->sweep_tiles_max * std::min(bt->n_heavy, kSweepMaxSlots) * kSweepRecWords * 4));
-      SLG_CUDA(ix, bt->sw_rng.alloc((size_t)std::max(bt->n_rows, 1u) * (bt->sweep_tiles_max + 1) * 4));
-    }
-  }
-  size_t S = ix->segs.size();
-  bt->sub_tiles_max = max_tiles;
-  if (!bt->use_reg || bt->n_light) {
-    SLG_CUDA(ix, bt->ut_rng.alloc((size_t)std::max(bt->U, 1u) * (max_tiles + 1) * 4));
-    if (exec != SLG_EXEC_BM25) SLG_CUDA(ix, bt->ut_tile_ub.alloc((size_t)std::max(bt->U, 1u) * max_tiles * 4));
-  }
-  SLG_CUDA(ix, bt->thr_key.alloc((size_t)n_queries * 8));
-  SLG_CUDA(ix, bt->topk_count.alloc((size_t)n_queries * 4));
-  SLG_CUDA(ix, bt->lock.alloc((size_t)n_queries * 4));
-  SLG_CUDA(ix, bt->topk_keys.alloc((size_t)n_queries * k * 8));
-  SLG_CUDA(ix, bt->work_counter.alloc(64 * 4));
-  SLG_CUDA(ix, bt->stats.alloc((size_t)n_queries * 5 * 8));  // [Q][4] counters, then [Q] accepted docs
-  SLG_CUDA(ix, bt->seg_hits.alloc(S * n_queries * k * sizeof(HitDev)));
-  SLG_CUDA(ix, bt->seg_counts.alloc(S * n_queries * 4));
-  if (S > 1) {
-    SLG_CUDA(ix, bt->out_hits.alloc((size_t)n_queries * k * sizeof(HitDev)));
-    SLG_CUDA(ix, bt->out_counts.alloc((size_t)n_queries * 4));
-  }
-  bt->pinned_bytes = (size_t)n_queries * k * sizeof(slg_hit_t) + (size_t)n_queries * 4 + (size_t)n_queries * 40;
-  if (!ix->pinned_busy && ix->pinned && ix->pinned_bytes >= bt->pinned_bytes) {
-    bt->pinned = ix->pinned;
-    bt->pinned_from_index = true;
-    ix->pinned_busy = true;
-  } else {
-    SLG_CUDA(ix, cudaMallocHost(&bt->pinned, bt->pinned_bytes));
-  }
-  SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));
-  *out = bt.release();
-  return SLG_OK;
-}
-
-int32_t slg_batch_run(slg_batch_t *bt, int32_t sync) {
-  if (!bt) return SLG_ERR_INVALID;
-  slg_index *ix = bt->ix;
-  SLG_CUDA(ix, cudaSetDevice(ix->device));
-  cudaStream_t st = ix->stream;
-  const bool prune = bt->exec != SLG_EXEC_BM25;
-  const uint32_t Q = bt->Q, k = bt->k;
-  unsigned char *dp = bt->d_pack.as<unsigned char>();
-  size_t smem = 0;
-  int32_t rc = bt->has_plan ? select_smem(ix, bt->plan_docs, bt->cap, bt->matcher, &smem, bt->max_leaves)
-                            : select_smem(ix, ix->tile_docs, bt->cap, bt->matcher, &smem);
-  if (rc) return rc;
-  uint32_t per_sm = (uint32_t)std::max<size_t>(1, (ix->smem_optin + 1024) / (smem + 1024));
-  per_sm = std::min(per_sm, 8u);
-  if (ix->ctas_per_sm) per_sm = std::min(per_sm, ix->ctas_per_sm);
-  SLG_CUDA(ix, cudaEventRecord(ix->ev[0], st));
-  SLG_CUDA(ix, cudaMemsetAsync(bt->stats.p, 0, (size_t)Q * 40, st));
-  if (bt->has_cursor) {
-    if (bt->n_cursor_segs != ix->segs.size()) return fail(ix, SLG_ERR_INVALID, "a segment was loaded after the batch with cursors was prepared");
-    SLG_CUDA(ix, cudaMemsetAsync(bt->cursor_saw.p, 0, (size_t)Q * 4, st));
-  }
-  uint32_t si = 0;
-  for (auto &sp : ix->segs) {
-    Segment *s = sp.get();
-    BatchDev bd{};
-    bd.ut_term = reinterpret_cast<const uint32_t *>(dp + bt->off_ut_term);
-    bd.ut_rng = bt->ut_rng.as<uint32_t>();
-    bd.ut_tile_ub = bt->ut_tile_ub.as<float>();
-    bd.q_term_off = reinterpret_cast<const uint32_t *>(dp + bt->off_q_term_off);
-    bd.qt_uterm = reinterpret_cast<const uint32_t *>(dp + bt->off_qt_uterm);
-    bd.qt_weight = reinterpret_cast<const float *>(dp + bt->off_qt_weight);
-    bd.qt_group = dp + bt->off_qt_group;
-    bd.qt_flags = dp + bt->off_qt_flags;
-    bd.q_order = reinterpret_cast<const uint32_t *>(dp + bt->off_q_order);
-    bd.q_must = dp + bt->off_q_must;
-    bd.q_not = dp + bt->off_q_not;
-    bd.q_should = dp + bt->off_q_should;
-    bd.q_min_should = dp + bt->off_q_min;
-    bd.q_filter = reinterpret_cast<const int32_t *>(dp + bt->off_q_filter);
-    bd.filter_bits = reinterpret_cast<const uint32_t *const *>(s->filter_ptrs.p);
-    if (bt->has_plan) {
-      bd.qt_leaf = dp + bt->off_qt_leaf;
-      bd.q_leaves = dp + bt->off_q_leaves;
-      bd.q_plan_off = reinterpret_cast<const uint32_t *>(dp + bt->off_q_plan_off);
-      bd.plan_nodes = reinterpret_cast<const PlanNodeDev *>(dp + bt->off_plan_nodes);
-    }
-    bd.max_leaves = bt->max_leaves;
-    if (bt->has_cursor) {
-      bd.q_cursor = bt->cursor_bounds.as<unsigned long long>() + (size_t)si * Q;
-      bd.q_saw = bt->cursor_saw.as<uint32_t>();
-    }
-    bd.n_queries = Q;
-    bd.n_uterms = bt->U;
-    bd.k = k;
-    bd.cap = bt->cap;
-    const uint32_t plan_docs = bt->plan_docs;
-    bd.tile_docs = plan_docs;
-    bd.n_tiles = std::max(1u, (s->doc_count + plan_docs - 1) / plan_docs);
-    bd.thr_key = bt->thr_key.as<unsigned long long>();
-    bd.topk_count = bt->topk_count.as<uint32_t>();
-    bd.lock = bt->lock.as<uint32_t>();
-    bd.topk_keys = bt->topk_keys.as<unsigned long long>();
-    bd.work_counter = bt->work_counter.as<uint32_t>();
-    bd.stats = bt->stats.as<unsigned long long>();
-    bd.match_count = bd.stats + (size_t)Q * 4;
-    // queries that name a filter need its bitmap on every segment
-    if (!ix->filters.empty() && s->filter_bits.size() < ix->filters.size())
-      return fail(ix, SLG_ERR_INVALID, "segment %u was loaded after its filters were compiled", s->ord);
-
-    slg_fill_u64_kernel<<<(Q + 255) / 256, 256, 0, st>>>(bd.thr_key, kThrInit, Q);
-    count_launch(ix);
-    SLG_CUDA(ix, cudaMemsetAsync(bd.topk_count, 0, (size_t)Q * 4, st));
-    SLG_CUDA(ix, cudaMemsetAsync(bd.lock, 0, (size_t)Q * 4, st));
-    SLG_CUDA(ix, cudaMemsetAsync(bd.work_counter, 0, 64 * 4, st));
-    if (bt->U && s->doc_count) {
-      // ---- plans and per-segment query tables ----
-      BatchDev bw = bd;  // the view of the warp kernel: all queries, or the light ones behind the heavy slots
-      uint32_t n_warp_rows = bt->U;
-      const uint32_t *warp_rows = nullptr;
-      if (bt->use_reg && bt->n_heavy) {  // only the light queries' terms behind the swept slots
-        bw.q_order = bd.q_order + bt->n_heavy;
-        bw.n_queries = bt->n_light;
-        n_warp_rows = bt->n_light_u;
-        warp_rows = bt->d_light_u.as<uint32_t>();
-      }
-      const bool run_warp_side = !bt->use_reg || bt->n_light;
-      if (run_warp_side && n_warp_rows) {
-        uint64_t n = (uint64_t)n_warp_rows * (bd.n_tiles + 1);
-        uint64_t n2 = (uint64_t)n_warp_rows * bd.n_tiles;
-        if (warp_rows) {
-          slg_plan_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, bd, warp_rows, n_warp_rows);
-        } else {
-          // every unique term: short lists are walked once, long lists take one binary search per boundary
-          slg_sweep_plan_kernel<<<dim3(n_warp_rows, 8), 256, 0, st>>>(s->dev, bd.ut_term, nullptr, n_warp_rows, bd.tile_docs, bd.n_tiles,
-                                                                     true, bd.ut_rng);
-        }
-        count_launch(ix);
-        if (prune) {
-          slg_plan_bounds_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(s->dev, bd, warp_rows, n_warp_rows);
-          count_launch(ix);
-        }
-      }
-      if ((bt->use_warp || (bt->use_reg && bt->n_light)) && bw.n_queries) {
-        slg_build_qterms_kernel<<<(bw.n_queries + 127) / 128, 128, 0, st>>>(s->dev, bw, bt->qterms.as<QTerm>(), bt->qheads.as<QHead>(),
-                                                                            bt->use_reg && bt->warp_cols && bt->staged);
-        count_launch(ix);
-      }
-      const uint32_t sw_tile = 128u * bt->reg_v;
-      const uint32_t sw_tiles = std::max(1u, (s->doc_count + sw_tile - 1) / sw_tile);
-      if (bt->use_reg && bt->n_heavy) {
-        if (bt->n_rows) {
-          slg_sweep_plan_kernel<<<dim3(bt->n_rows, 8), 256, 0, st>>>(s->dev, bd.ut_term, bt->d_row_u.as<uint32_t>(), bt->n_rows, sw_tile,
-                                                                      sw_tiles, bt->want_stats, bt->sw_rng.as<uint32_t>());
-          count_launch(ix);
-        }
-        slg_build_sweep_kernel<<<(bt->n_heavy + 127) / 128, 128, 0, st>>>(
-            s->dev, bd, bt->n_heavy, bt->d_u_row.as<uint32_t>(), bt->d_chunk_cols.as<uint32_t>() + (size_t)si * bt->n_chunks * kSweepStage,
-            bt->sw_sstat.as<uint4>(), bt->sw_weights.as<float>(), bt->sw_ubw.as<float>());
-        count_launch(ix);
-      }
-      SLG_CUDA(ix, cudaGetLastError());
-      SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));
-      // ---- scoring ----
-      if (bt->use_reg && bt->n_heavy) {
-        // seed pass over the first tiles (gives every query a threshold), then the rest in ranges of tiles
-        const uint32_t seed_tiles = std::min(sw_tiles, std::max(1u, std::min(sw_tiles / 4, ix->seed_docs / sw_tile)));
-        uint32_t launch_id = 0;
-        for (uint32_t c0 = 0; c0 < bt->n_heavy; c0 += kSweepMaxSlots) {
-          if (launch_id + 3 >= 64) return fail(ix, SLG_ERR_UNSUPPORTED, "more than %u swept queries in one batch", 30 * kSweepMaxSlots);
-          SweepDev sw{};
-          sw.sstat = bt->sw_sstat.as<uint4>() + (size_t)c0 * (kSweepSlotWords / 4);
-          sw.weights = bt->sw_weights.as<float>() + (size_t)c0 * 8;
-          sw.ubw = bt->sw_ubw.as<float>() + (size_t)c0 * 8;
-          sw.records = bt->sw_records.as<uint32_t>();
-          sw.rng = bt->sw_rng.as<uint32_t>();
-          sw.post_pair = s->post_pair.as<uint2>();
-          sw.col_tmax = s->col_tmax.as<float>();
-          sw.chunk_cols = bt->d_chunk_cols.as<uint32_t>() + ((size_t)si * bt->n_chunks + c0 / kSweepChunk) * kSweepStage;
-          sw.filter_bits = bd.filter_bits;
-          sw.n_slots = std::min(kSweepMaxSlots, bt->n_heavy - c0);
-          sw.n_chunks = (sw.n_slots + kSweepChunk - 1) / kSweepChunk;
-          sw.k = k;
-          sw.n_tiles = sw_tiles;
-          sw.tmax_stride = s->tmax_stride;
-          sw.thr_key = bd.thr_key;
-          sw.topk_count = bd.topk_count;
-          sw.lock = bd.lock;
-          sw.topk_keys = bd.topk_keys;
-          sw.stats = bd.stats;
-          {
-            const dim3 rgrid((sw.n_slots + 127) / 128, (sw_tiles + kSweepTileGroup - 1) / kSweepTileGroup);
-            if (prune) slg_sweep_records_kernel<true><<<rgrid, 128, 0, st>>>(sw, bt->reg_v, bt->want_stats);
-            else slg_sweep_records_kernel<false><<<rgrid, 128, 0, st>>>(sw, bt->reg_v, bt->want_stats);
-            SLG_CUDA(ix, cudaGetLastError());
-            count_launch(ix);
-          }
-          sw.work_counter = bd.work_counter + 1 + launch_id++;
-          sw.tile_begin = 0;
-          sw.tile_end = seed_tiles;
-          sw.part_tiles = seed_tiles;
-          rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, bt->any_weight, s->dev, sw, (int)std::min<uint32_t>((uint32_t)ix->n_sm, sw.n_chunks));
-          if (rc) return rc;
-          count_launch(ix);
-          if (seed_tiles < sw_tiles) {
-            sw.work_counter = bd.work_counter + 1 + launch_id++;
-            sw.tile_begin = seed_tiles;
-            sw.tile_end = sw_tiles;
-            // enough units for an even finish: about 24 per SM
-            const uint32_t want_parts = std::max(1u, (24u * (uint32_t)ix->n_sm + sw.n_chunks - 1) / sw.n_chunks);
-            sw.part_tiles = ix->part_tiles ? ix->part_tiles : std::max(32u, (sw_tiles - seed_tiles + want_parts - 1) / want_parts);
-            sw.part_tiles = (sw.part_tiles + 31u) & ~31u;  // whole staged blocks
-            const uint64_t units = (uint64_t)sw.n_chunks * ((sw_tiles - seed_tiles + sw.part_tiles - 1) / sw.part_tiles);
-            rc = launch_sweep(ix, bt->reg_v, prune, bt->want_stats, bt->any_weight, s->dev, sw, (int)std::min<uint64_t>((uint64_t)ix->n_sm, units));
-            if (rc) return rc;
-            count_launch(ix);
-          }
-        }
-        ix->ctr.score_launches++;
-      }
-      if ((bt->use_warp || (bt->use_reg && bt->n_light)) && bw.n_queries) {
-        WarpBatchDev wb{};
-        wb.qterms = bt->qterms.as<QTerm>();
-        wb.qheads = bt->qheads.as<QHead>();
-        wb.rng = bd.ut_rng;
-        wb.sub_ub = bd.ut_tile_ub;
-        wb.scores = s->dev.post_score;
-        wb.filter_bits = bd.filter_bits;
-        wb.n_queries = bw.n_queries;
-        wb.k = k;
-        wb.sub_docs = bt->has_plan ? bt->plan_docs : ix->sub_docs;
-        wb.q_leaves = bd.q_leaves;
-        wb.q_plan_off = bd.q_plan_off;
-        wb.plan_nodes = bd.plan_nodes;
-        wb.max_leaves = bt->max_leaves;
-        wb.n_sub = bd.n_tiles;
-        wb.n_groups = (bd.n_tiles + kSubPerGroup - 1) / kSubPerGroup;
-        wb.ms_frac = (float)ix->maxscore_pct / 100.0f;
-        wb.thr_key = bd.thr_key;
-        wb.topk_count = bd.topk_count;
-        wb.lock = bd.lock;
-        wb.topk_keys = bd.topk_keys;
-        wb.work_counter = bd.work_counter;
-        wb.stats = bd.stats;
-        wb.match_count = bd.match_count;
-        wb.q_cursor = bd.q_cursor;
-        wb.q_saw = bd.q_saw;
-        const int warps = kThreads / 32;
-        // (plan batches: the matcher form of the kernel unless the staged plain-OR form applies — size for the larger)
-        size_t wsmem = (size_t)warps * warp_kernel_smem_per_warp(wb.sub_docs, bt->matcher || (bt->has_plan && !bt->staged), prune,
-                                                                 bt->has_plan ? bt->max_leaves : 1u);
-        if (wsmem + 1024 > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "sub_docs %u needs %zu B shared memory", ix->sub_docs, wsmem);
-        uint32_t wper = (uint32_t)std::max<size_t>(1, (ix->smem_optin + 1024) / (wsmem + 1024));
-        wper = std::min(wper, 8u);
-        if (ix->ctas_per_sm) wper = std::min(wper, ix->ctas_per_sm);
-        int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * wper, ((uint64_t)wb.n_groups * wb.n_queries + warps - 1) / warps);
-        rc = launch_warp(ix, bt->matcher, prune, bt->want_stats, bt->staged, bt->use_reg && bt->warp_cols, s->dev, wb, wsmem, grid,
-                         bt->has_plan);
-        if (rc) return rc;
-        count_launch(ix);
-        if (!bt->use_reg || !bt->n_heavy) ix->ctr.score_launches++;
-      } else if (!bt->use_reg && !bt->use_warp) {
-        int grid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * per_sm, (uint64_t)bd.n_tiles * Q);
-        rc = launch_score(ix, bt->matcher, prune, bt->want_stats, s->dev, bd, smem, grid, bt->has_plan);
-        if (rc) return rc;
-        count_launch(ix);
-        ix->ctr.score_launches++;
-      }
-      SLG_CUDA(ix, cudaEventRecord(ix->ev[3], st));
-    }
-    HitDev *hits = bt->seg_hits.as<HitDev>() + (size_t)si * Q * k;
-    uint32_t *cnts = bt->seg_counts.as<uint32_t>() + (size_t)si * Q;
-    size_t fsmem = (size_t)(1u << (32 - __builtin_clz(std::max(k, 2u) - 1))) * 8;
-    slg_finalize_kernel<<<Q, kThreads, fsmem, st>>>(bd, s->ord, hits, cnts);
-    count_launch(ix);
-    SLG_CUDA(ix, cudaGetLastError());
-    if (ix->segs.size() > 1 && bt->U && s->doc_count) {
-      // per-segment score time must be read before the events are reused
-      SLG_CUDA(ix, cudaEventSynchronize(ix->ev[3]));
-      float ms = 0;
-      SLG_CUDA(ix, cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3]));
-      ix->ctr.score_ms_total += ms;
-      ix->ctr.last_score_ms = ms;
-    }
-    si++;
-  }
-  bt->n_segs_run = si;
-  if (si > 1) {
-    size_t msmem = (size_t)si * k * sizeof(HitDev);
-    if (msmem > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "merge of %u segments x k=%u does not fit shared memory", si, k);
-    SLG_CUDA(ix, cudaFuncSetAttribute(slg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    slg_merge_kernel<<<Q, kThreads, msmem, st>>>(bt->seg_hits.as<HitDev>(), bt->seg_counts.as<uint32_t>(), si, Q, k,
-                                                 bt->out_hits.as<HitDev>(), bt->out_counts.as<uint32_t>());
-    count_launch(ix);
-    SLG_CUDA(ix, cudaGetLastError());
-  }
-  SLG_CUDA(ix, cudaEventRecord(ix->ev[1], st));
-  ix->ctr.last_posting_count = bt->posting_count;
-  if (sync) {
-    SLG_CUDA(ix, cudaStreamSynchronize(st));
-    float ms = 0;
-    SLG_CUDA(ix, cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[1]));
-    ix->ctr.last_batch_ms = ms;
-    if (ix->segs.size() == 1 && bt->U) {
-      SLG_CUDA(ix, cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3]));
-      ix->ctr.score_ms_total += ms;
-      ix->ctr.last_score_ms = ms;
-    }
-  }
-  return SLG_OK;
-}
-
-int32_t slg_batch_enable_stats(slg_batch_t *bt, int32_t on) {
-  if (!bt) return SLG_ERR_INVALID;
-  bt->want_stats = on != 0;
-  return SLG_OK;
-}
-
-int32_t slg_batch_device_results(slg_batch_t *bt, void **dev_hits, void **dev_counts) {
-  if (!bt || !dev_hits || !dev_counts) return SLG_ERR_INVALID;
-  bool merged = bt->n_segs_run > 1;
-  *dev_hits = merged ? bt->out_hits.p : bt->seg_hits.p;
-  *dev_counts = merged ? bt->out_counts.p : bt->seg_counts.p;
-  return SLG_OK;
-}
-
-int32_t slg_batch_fetch(slg_batch_t *bt, slg_hit_t *out_hits, uint32_t *out_counts, slg_stats_t *out_stats) {
-  if (!bt || !out_hits || !out_counts) return SLG_ERR_INVALID;
-  slg_index *ix = bt->ix;
-  SLG_CUDA(ix, cudaSetDevice(ix->device));
-  cudaStream_t st = ix->stream;
-  void *dh, *dc;
-  slg_batch_device_results(bt, &dh, &dc);
-  static_assert(sizeof(slg_hit_t) == sizeof(HitDev), "hit layout");
-  size_t hb = (size_t)bt->Q * bt->k * sizeof(slg_hit_t), cb = (size_t)bt->Q * 4, sb = (size_t)bt->Q * 40;
-  unsigned char *pin = static_cast<unsigned char *>(bt->pinned);
-  SLG_CUDA(ix, cudaMemcpyAsync(pin, dh, hb, cudaMemcpyDeviceToHost, st));
-  SLG_CUDA(ix, cudaMemcpyAsync(pin + hb, dc, cb, cudaMemcpyDeviceToHost, st));
-  if (out_stats) SLG_CUDA(ix, cudaMemcpyAsync(pin + hb + cb, bt->stats.p, sb, cudaMemcpyDeviceToHost, st));
-  SLG_CUDA(ix, cudaStreamSynchronize(st));
-  ix->ctr.last_d2h_bytes = hb + cb + (out_stats ? sb : 0);
-  std::memcpy(out_hits, pin, hb);
-  std::memcpy(out_counts, pin + hb, cb);
-  if (out_stats) {
-    const unsigned long long *sv = reinterpret_cast<const unsigned long long *>(pin + hb + cb);
-    for (uint32_t q = 0; q < bt->Q; q++) {
-      out_stats[q].scored_docs = sv[q * 4 + 0];
-      out_stats[q].postings_advanced = sv[q * 4 + 1];
-      out_stats[q].blocks_skipped = sv[q * 4 + 2];
-      out_stats[q].candidates_examined = sv[q * 4 + 3];
-      out_stats[q].total_matches = sv[(size_t)bt->Q * 4 + q];
-    }
-  }
-  return SLG_OK;
-}
-
-int32_t slg_batch_copy_results_device(slg_batch_t *bt, void *dst_hits, void *dst_counts) {
-  if (!bt || !dst_hits || !dst_counts) return SLG_ERR_INVALID;
-  slg_index *ix = bt->ix;
-  SLG_CUDA(ix, cudaSetDevice(ix->device));
-  void *dh, *dc;
-  slg_batch_device_results(bt, &dh, &dc);
-  SLG_CUDA(ix, cudaMemcpyAsync(dst_hits, dh, (size_t)bt->Q * bt->k * sizeof(HitDev), cudaMemcpyDeviceToDevice, ix->stream));
-  SLG_CUDA(ix, cudaMemcpyAsync(dst_counts, dc, (size_t)bt->Q * 4, cudaMemcpyDeviceToDevice, ix->stream));
-  return SLG_OK;
-}
-
-int32_t slg_batch_cursor_seen(slg_batch_t *bt, uint8_t *out_seen) {
-  if (!bt || !out_seen) return SLG_ERR_INVALID;
-  slg_index *ix = bt->ix;
-  SLG_CUDA(ix, cudaSetDevice(ix->device));
-  for (uint32_t q = 0; q < bt->Q; q++) out_seen[q] = 1;  // no cursor: saw_cursor starts true (api/reader.rs:2663)
-  if (!bt->has_cursor) return SLG_OK;
-  std::vector<uint32_t> saw(bt->Q);
-  SLG_CUDA(ix, cudaMemcpyAsync(saw.data(), bt->cursor_saw.p, (size_t)bt->Q * 4, cudaMemcpyDeviceToHost, ix->stream));
-  SLG_CUDA(ix, cudaStreamSynchronize(ix->stream));
-  for (uint32_t q = 0; q < bt->Q; q++)
-    if (bt->h_has_cursor[q]) out_seen[q] = saw[q] ? 1 : 0;
-  return SLG_OK;
-}
-
 // PaginationCursor::encode / decode, api/reader.rs:630-691, and the generation check of decode_cursor, :821-841
 int32_t slg_cursor_encode(uint32_t generation, uint32_t returned, const slg_hit_t *last_hit, char *out43) {
   if (!last_hit || !out43) return SLG_ERR_INVALID;
@@ -2650,59 +1492,6 @@ int32_t slg_cursor_decode(const char *raw, uint32_t manifest_generation, slg_hit
   key->segment_ord = words[2];
   key->doc_id = words[3];
   *returned = words[4];
-  return SLG_OK;
-}
-
-int32_t slg_batch_free(slg_batch_t *bt) {
-  if (!bt) return SLG_OK;
-  cudaSetDevice(bt->ix->device);
-  cudaStreamSynchronize(bt->ix->stream);
-  delete bt;
-  return SLG_OK;
-}
-
-int32_t slg_search_batch(slg_index_t *ix, const slg_query_t *queries, uint32_t n_queries, uint32_t k, slg_exec_t exec,
-                         uint32_t bmw_block_size, slg_hit_t *out_hits, uint32_t *out_counts, slg_stats_t *out_stats) {
-  if (!ix) return SLG_ERR_INVALID;
-  if (!out_hits || !out_counts) return fail(ix, SLG_ERR_INVALID, "output buffers are NULL");
-  slg_batch_t *bt = nullptr;
-  int32_t rc = slg_batch_prepare(ix, queries, n_queries, k, exec, bmw_block_size, &bt);
-  if (rc) return rc;
-  bt->want_stats = out_stats != nullptr;
-  rc = slg_batch_run(bt, 0);
-  if (rc == SLG_OK) rc = slg_batch_fetch(bt, out_hits, out_counts, out_stats);
-  if (rc == SLG_OK && ix->segs.size() == 1 && bt->U) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3]) == cudaSuccess) {
-      ix->ctr.score_ms_total += ms;
-      ix->ctr.last_score_ms = ms;
-    }
-    if (cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[1]) == cudaSuccess) ix->ctr.last_batch_ms = ms;
-  }
-  slg_batch_free(bt);
-  return rc;
-}
-
-int32_t slg_merge_gathered(slg_index_t *ix, const void *dev_hits, const void *dev_counts, uint32_t n_shards,
-                           uint32_t n_queries, uint32_t k, slg_hit_t *out_hits, uint32_t *out_counts) {
-  if (!ix || !dev_hits || !dev_counts || !out_hits || !out_counts || !n_shards || !n_queries || !k) return SLG_ERR_INVALID;
-  SLG_CUDA(ix, cudaSetDevice(ix->device));
-  cudaStream_t st = ix->stream;
-  size_t msmem = (size_t)n_shards * k * sizeof(HitDev);
-  if (msmem > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "merge of %u shards x k=%u does not fit shared memory", n_shards, k);
-  PoolScope pool_scope(st);  // per-call buffers from the stream-ordered pool
-  DevBuf oh, oc;
-  SLG_CUDA(ix, oh.alloc((size_t)n_queries * k * sizeof(HitDev)));
-  SLG_CUDA(ix, oc.alloc((size_t)n_queries * 4));
-  SLG_CUDA(ix, cudaFuncSetAttribute(slg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-  slg_merge_kernel<<<n_queries, kThreads, msmem, st>>>(static_cast<const HitDev *>(dev_hits), static_cast<const uint32_t *>(dev_counts),
-                                                       n_shards, n_queries, k, oh.as<HitDev>(), oc.as<uint32_t>());
-  count_launch(ix);
-  SLG_CUDA(ix, cudaGetLastError());
-  SLG_CUDA(ix, cudaMemcpyAsync(out_hits, oh.p, (size_t)n_queries * k * sizeof(HitDev), cudaMemcpyDeviceToHost, st));
-  SLG_CUDA(ix, cudaMemcpyAsync(out_counts, oc.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, st));
-  SLG_CUDA(ix, cudaStreamSynchronize(st));
-  ix->ctr.last_d2h_bytes = (size_t)n_queries * k * sizeof(HitDev) + (size_t)n_queries * 4;
   return SLG_OK;
 }
 

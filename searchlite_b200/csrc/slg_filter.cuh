@@ -28,7 +28,7 @@ struct FilterNodeDev {
 
 // The program is in prefix order; walking it backwards with a value stack evaluates every
 // node after its children (And/Or are commutative, so the reversed child order is immaterial).
-__global__ void slg_filter_bitmap_kernel(const FilterNodeDev *nodes, uint32_t n_nodes, const uint32_t *ordsets,
+static __global__ void slg_filter_bitmap_kernel(const FilterNodeDev *nodes, uint32_t n_nodes, const uint32_t *ordsets,
                                          uint32_t doc_count, uint32_t *bits) {
   const uint32_t doc = blockIdx.x * blockDim.x + threadIdx.x;
   bool result = false;

@@ -1,0 +1,22 @@
+// slg_launch_items.cu — instantiations of the posting-driven items kernel (plain OR queries, k <= 32, <= 8 terms)
+#include "slg_launch.h"
+
+namespace slg {
+namespace {
+template <class K, class... A>
+cudaError_t go(K kern, size_t smem, int grid, cudaStream_t st, A... args) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, smem, st>>>(args...);
+  return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t launch_score_items(bool prune, const SegmentDev &sd, const WarpBatchDev &wb, const ItemsDev &it, size_t smem, int grid,
+                               cudaStream_t st) {
+  return prune ? go(slg_score_items_kernel<true>, smem, grid, st, sd, wb, it) : go(slg_score_items_kernel<false>, smem, grid, st, sd, wb, it);
+}
+cudaError_t launch_seed_items(const SegmentDev &sd, const WarpBatchDev &wb, const ItemsDev &it, size_t smem, int grid, cudaStream_t st) {
+  return go(slg_seed_items_kernel<0>, smem, grid, st, sd, wb, it);
+}
+}  // namespace slg

@@ -35,7 +35,7 @@ struct PhraseDev {
 
 // Positions of the postings of a `.post` image: one CTA per 128-posting block, one thread per posting.
 // post_posbyte / post_npos were recorded by slg_decode_post_image_kernel's walk.
-__global__ void __launch_bounds__(128) slg_decode_positions_kernel(const uint8_t *img, const PostTermHeader *hdr, uint64_t n_terms,
+static __global__ void __launch_bounds__(128) slg_decode_positions_kernel(const uint8_t *img, const PostTermHeader *hdr, uint64_t n_terms,
                                                                     const uint64_t *term_start, const uint32_t *term_blk,
                                                                     const uint32_t *term_df, uint32_t n_blocks,
                                                                     const uint32_t *post_posbyte, const uint64_t *pos_begin,
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) slg_decode_positions_kernel(const uint8_t
 }
 
 // Positions handed over as CSR (slg_load_positions): counts per padded posting slot.
-__global__ void __launch_bounds__(128) slg_csr_position_counts_kernel(const uint64_t *csr_off, const uint64_t *csr_pos_off,
+static __global__ void __launch_bounds__(128) slg_csr_position_counts_kernel(const uint64_t *csr_off, const uint64_t *csr_pos_off,
                                                                        uint64_t n_terms, const uint64_t *term_start,
                                                                        const uint32_t *term_blk, uint32_t n_blocks,
                                                                        uint32_t *post_npos) {
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(128) slg_csr_position_counts_kernel(const uint
   post_npos[term_start[term] + i] = (uint32_t)(csr_pos_off[src0 + i + 1] - csr_pos_off[src0 + i]);
 }
 
-__global__ void __launch_bounds__(128) slg_csr_position_copy_kernel(const uint64_t *csr_off, const uint64_t *csr_pos_off,
+static __global__ void __launch_bounds__(128) slg_csr_position_copy_kernel(const uint64_t *csr_off, const uint64_t *csr_pos_off,
                                                                      const uint32_t *csr_pos, uint64_t n_terms,
                                                                      const uint64_t *term_start, const uint32_t *term_blk,
                                                                      uint32_t n_blocks, const uint64_t *pos_begin, uint32_t *pos) {
@@ -139,7 +139,7 @@ __device__ __forceinline__ uint32_t phrase_lower_bound(const uint32_t *docs, uin
 // One thread per posting of a phrase's driver term; a batch of phrases shares one launch: CTA b serves
 // phrase i with blk_off[i] <= b < blk_off[i+1] and writes row i (row_words words) of `bits`, which must be
 // zeroed.  Live / deleted docs are not consulted here (accept() checks them separately, api/reader.rs:3010).
-__global__ void __launch_bounds__(256) slg_phrase_bitmap_kernel(const PhraseDev *phrases, const uint32_t *blk_off, uint32_t n_phrases,
+static __global__ void __launch_bounds__(256) slg_phrase_bitmap_kernel(const PhraseDev *phrases, const uint32_t *blk_off, uint32_t n_phrases,
                                                                  const uint32_t *post_doc, const uint64_t *pos_begin,
                                                                  const uint32_t *pos, uint32_t doc_count, uint32_t *bits,
                                                                  uint64_t row_words) {
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) slg_phrase_bitmap_kernel(const PhraseDev 
 }
 
 // out = a op b over bitmap words: 0 and, 1 or, 2 and-not.  Tail bits of a and b are zero, so are out's.
-__global__ void slg_bitmap_combine_kernel(const uint32_t *a, const uint32_t *b, uint32_t words, uint32_t op, uint32_t *out) {
+static __global__ void slg_bitmap_combine_kernel(const uint32_t *a, const uint32_t *b, uint32_t words, uint32_t op, uint32_t *out) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= words) return;
   const uint32_t x = a[w], y = b[w];
@@ -208,7 +208,7 @@ __global__ void slg_bitmap_combine_kernel(const uint32_t *a, const uint32_t *b, 
 }
 
 // the same for n pairs in one launch: row i of `out` = a[i] op b[i]
-__global__ void slg_bitmap_combine_batch_kernel(const uint32_t *const *a, const uint32_t *const *b, uint32_t words, uint32_t op,
+static __global__ void slg_bitmap_combine_batch_kernel(const uint32_t *const *a, const uint32_t *const *b, uint32_t words, uint32_t op,
                                                 uint32_t *out, uint64_t row_words) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = blockIdx.y;

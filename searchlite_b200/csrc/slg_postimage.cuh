@@ -77,7 +77,7 @@ __device__ __forceinline__ bool window_varint(uint64_t w, uint32_t avail, uint32
   return true;
 }
 
-__global__ void __launch_bounds__(128) slg_decode_post_image_kernel(const uint8_t *img, uint64_t img_bytes,
+static __global__ void __launch_bounds__(128) slg_decode_post_image_kernel(const uint8_t *img, uint64_t img_bytes,
                                                                      const PostTermHeader *hdr, uint64_t n_terms,
                                                                      const uint64_t *term_start, const uint32_t *term_blk,
                                                                      uint32_t *post_doc, uint8_t *post_tf,

@@ -26,12 +26,12 @@ struct RerankSegDev {
   uint32_t dim;
 };
 
-__global__ void slg_f32_to_bf16_kernel(const float *in, __nv_bfloat16 *out, size_t n) {
+static __global__ void slg_f32_to_bf16_kernel(const float *in, __nv_bfloat16 *out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
 }
 
-__global__ void __launch_bounds__(256) slg_rerank_kernel(const RerankSegDev *segs, uint32_t n_segs, const float *query_vecs,
+static __global__ void __launch_bounds__(256) slg_rerank_kernel(const RerankSegDev *segs, uint32_t n_segs, const float *query_vecs,
                                                           uint32_t dim, const HitDev *cands, const uint32_t *cand_counts,
                                                           uint32_t stride, float alpha, int metric, HitDev *out_hits,
                                                           float *out_vs) {

@@ -1,5 +1,6 @@
-// slg_warp_kernel.cuh — K2/K3, warp-autonomous variant (the default for k <= 32 and <= 8 terms
-// per query; with COLS for plain OR queries, without for Bool queries and kernel choice 2).
+// slg_warp_kernel.cuh — K2/K3, warp-autonomous variant with one accumulator slot per doc of a sub-tile: Bool
+// queries, ScorePlans, per-query statistics and kernel choice 2 (the reference's summation order) for k <= 32
+// and <= 8 terms per query.  Plain OR queries run on the posting-driven kernel of slg_items_kernel.cuh.
 //
 // Same arithmetic, same key order and same per-query global top-k protocol as
 // slg_score_tiles_kernel, but the unit of cooperation is one WARP instead of one CTA, so no block
@@ -21,12 +22,10 @@
 // adds them.  The per-query weight is applied at accumulate time (score_tf: base * weight,
 // query/wand.rs:284-285), so results are bit-identical to computing the contribution in place.
 //
-// The kernel is bound by the shared-memory pipe (profiles/r1_v7_warp_kernel_summary.txt); three things
-// keep that traffic down: one shared-memory instruction touches 32 consecutive postings (fewer bank
-// conflicts on dense lists), every lane tracks the largest value it wrote so that a sub-tile whose best
-// score is below the query's threshold is cleared without being read back, and — template flag COLS,
-// the automatic choice for plain OR queries — terms with a dense column are summed from it with
-// 128-bit loads instead of being scattered, which also removes the clearing between sub-tiles.
+// The kernel is bound by the shared-memory pipe (profiles/r1_v7_warp_kernel_summary.txt); two things keep that
+// traffic down: one shared-memory instruction touches 32 consecutive postings (fewer bank conflicts on dense
+// lists), and every lane tracks the largest value it wrote so that a sub-tile whose best score is below the
+// query's threshold is cleared without being read back.
 #pragma once
 #include "slg_kernels.cuh"
 
@@ -43,7 +42,7 @@ struct __align__(16) QTerm {  // one query term resolved against one segment (32
   uint32_t term;      // term id in the segment
   uint32_t uterm;     // row of the range / bound tables
   float weight;
-  uint32_t flags;     // bit0 scored, bit1 valid, bit2 summed from its dense column (COLS), bits 8..15 group
+  uint32_t flags;     // bit0 scored, bit1 valid, bit2 streamed from its dense column (items kernel), bits 8..15 group, 16..19 leaf
 };
 
 struct __align__(16) QHead {  // 16 B per query slot (processing order)
@@ -77,10 +76,12 @@ struct WarpBatchDev {
   unsigned long long *match_count;  // [Q] accepted docs (STATS)
 };
 
-// resolve the batch's query terms against one segment (runs once per segment per batch)
-// use_cols: terms with a dense column (seg.term_col) are flagged; the kernel then sums them from the
-// column, before the query's other terms (the float contract of the column path, see slg_score_warp_kernel)
-__global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qterms, QHead *qheads, bool use_cols) {
+// resolve the batch's query terms against one segment (runs once per segment per batch).
+// canonical: the term slots of a query are laid out in the DECLARED summation order of the column path
+// (include/searchlite_gpu.h): terms without a dense column first, then the terms with one, each group in query
+// order — every kernel that walks the slots in order then sums in that order.  use_cols: the terms with a column
+// are flagged (bit2) and the items kernel streams them from seg.cols.
+static __global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qterms, QHead *qheads, bool canonical, bool use_cols) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= bt.n_queries) return;
   const uint32_t qi = bt.q_order[slot];
@@ -92,7 +93,27 @@ __global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qter
             ((uint32_t)bt.q_min_should[qi] << 24);
   h.filter = bt.q_filter[qi];
   qheads[slot] = h;
-  for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
+  uint32_t out = 0;
+  for (int pass = 0; pass < (canonical ? 2 : 1); pass++) {
+    for (uint32_t t = 0; t < nt && t < kWarpMaxTerms; t++) {
+      const uint32_t u = bt.qt_uterm[t0 + t];
+      const uint32_t term = bt.ut_term[u];
+      const bool scored = bt.qt_flags[t0 + t] & 1u;
+      const bool has_col = seg.term_col && term < seg.n_terms && seg.term_col[term] >= 0 && scored;
+      if (canonical && has_col != (pass == 1)) continue;
+      QTerm r;
+      r.base = term < seg.n_terms ? seg.term_start[term] : 0;  // seg.post_score is laid out like seg.post_doc
+      r.sc_base = has_col ? (uint64_t)seg.term_col[term] * seg.col_stride : ~0ull;
+      r.term = term;
+      r.uterm = u;
+      r.weight = bt.qt_weight[t0 + t];
+      r.flags = (scored ? 1u : 0u) | 2u | ((uint32_t)bt.qt_group[t0 + t] << 8);
+      if (bt.qt_leaf) r.flags |= (uint32_t)bt.qt_leaf[t0 + t] << 16;
+      if (has_col && use_cols) r.flags |= 4u;
+      qterms[(uint64_t)slot * kWarpMaxTerms + out++] = r;
+    }
+  }
+  for (; out < kWarpMaxTerms; out++) {
     QTerm r;
     r.base = 0;
     r.sc_base = 0;
@@ -100,22 +121,7 @@ __global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTerm *qter
     r.uterm = 0;
     r.weight = 0.0f;
     r.flags = 0;
-    if (t < nt) {
-      const uint32_t u = bt.qt_uterm[t0 + t];
-      const uint32_t term = bt.ut_term[u];
-      r.base = term < seg.n_terms ? seg.term_start[term] : 0;  // seg.post_score is laid out like seg.post_doc
-      r.sc_base = ~0ull;
-      r.term = term;
-      r.uterm = u;
-      r.weight = bt.qt_weight[t0 + t];
-      r.flags = (bt.qt_flags[t0 + t] & 1u) | 2u | ((uint32_t)bt.qt_group[t0 + t] << 8);
-      if (bt.qt_leaf) r.flags |= (uint32_t)bt.qt_leaf[t0 + t] << 16;
-      if (seg.term_col && term < seg.n_terms && seg.term_col[term] >= 0 && (r.flags & 1u)) {
-        r.sc_base = (uint64_t)seg.term_col[term] * seg.col_stride;
-        if (use_cols) r.flags |= 4u;
-      }
-    }
-    qterms[(uint64_t)slot * kWarpMaxTerms + t] = r;
+    qterms[(uint64_t)slot * kWarpMaxTerms + out] = r;
   }
 }
 
@@ -214,11 +220,6 @@ __device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ d
   }
 }
 
-// COLS (plain OR queries with resident scores): a term with a dense column is not scattered posting by
-// posting; the warp first fills its accumulator with the sum of the query's column slices (128-bit
-// loads, query order), then scatters the remaining terms on top.  Float contract of that path: the
-// terms WITH a column in query order, then the terms WITHOUT one in query order, one left fold.
-//
 // PRUNE on plain OR queries with resident scores adds MaxScore on top of the tile skip.  Per (query,
 // sub-tile) the terms are ranked by their bound inside the sub-tile; the longest prefix whose bounds
 // sum to less than the running k-th score is "non-essential": a doc that holds only such terms cannot
@@ -226,7 +227,7 @@ __device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ d
 // of the threshold, ms_frac: with loose bounds too many docs would need the exact rescoring below).
 // A doc touched by the other terms is a
 // candidate if its partial score plus the non-essential bounds can still reach the threshold; its
-// exact score is then recomputed over ALL terms in query order — dense-column lookup for column terms,
+// exact score is then recomputed over ALL terms in slot order — dense-column lookup for column terms,
 // binary search inside the sub-tile's posting range otherwise — so the result is bit-identical to
 // the exhaustive run.  (TermState upper bounds: query/wand.rs:238-303; the reference's wand_loop
 // prunes document-at-a-time with the same bounds, query/wand.rs:659-903.)
@@ -236,7 +237,7 @@ __device__ __forceinline__ void accumulate_staged(const uint32_t *__restrict__ d
 // touched doc into plane 0 and clears the other planes, and the scan proceeds on plane 0.  MaxScore (partial
 // sums) and the written-maximum shortcut do not apply to plans; the tile skip does (a plan never exceeds the
 // sum of its terms' bounds).
-template <bool MATCHER, bool PRUNE, bool STATS, bool STAGED, bool COLS = false, bool PLAN = false>
+template <bool MATCHER, bool PRUNE, bool STATS, bool STAGED, bool PLAN = false>
 __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev seg, WarpBatchDev wb) {
   constexpr bool MAXSCORE = PRUNE && !MATCHER && STAGED && !PLAN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -268,8 +269,6 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
     for (uint32_t i = lane * 4; i < sub_docs; i += 128) *reinterpret_cast<uint32_t *>(gmask + i) = 0u;
   __syncwarp();
 
-  bool dirty = false;  // COLS: the accumulator still holds the scores of the last column sub-tile
-  (void)dirty;
   uint32_t item = 0;
   if (lane == 0) item = atomicAdd(wb.work_counter, 1u);
   item = __shfl_sync(0xFFFFFFFFu, item, 0);
@@ -333,8 +332,6 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
       }
       const uint32_t any = __ballot_sync(0xFFFFFFFFu, mine_n != 0u);
       if (any == 0u) continue;
-      uint32_t colmask = 0;  // term slots summed from a column
-      if (COLS) colmask = __ballot_sync(0xFFFFFFFFu, lane < (int)nt && (qt[lane].flags & 5u) == 5u);
       if (PRUNE) {
         float ub = mine_ub;
 #pragma unroll
@@ -364,58 +361,15 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
         for (int o = 4; o > 0; o >>= 1) sn = fmaxf(sn, __shfl_xor_sync(0xFFFFFFFFu, sn, o));
         sum_n = __shfl_sync(0xFFFFFFFFu, sn, 0);
       }
-      if (COLS) colmask &= ~nmask;  // a non-essential column term is looked up for the parked docs only
       if (STATS) n_post += ((nmask >> lane) & 1u) ? 0u : mine_n;
 
       // ---- accumulate ----
       bool first = true;
       uint32_t wmax = 0;  // largest value written to the accumulator by this lane (bits)
-      if (COLS && !colmask && dirty) {
-        // no column term this time: the scores the last column sub-tile left behind have to go
-#pragma unroll 4
-        for (uint32_t i0 = 0; i0 < sub_docs; i0 += 128) *reinterpret_cast<float4 *>(acc + i0 + lane * 4) = make_float4(0, 0, 0, 0);
-        dirty = false;
-        __syncwarp();
-      }
-      if (COLS && colmask) {
-        // column terms: accumulator = sum of the column slices, query order; four rows of 128 docs per
-        // step so that four 128-bit loads per column are in flight.  Every slot is overwritten, so a
-        // dirty accumulator needs no clearing first.
-#pragma unroll 1
-        for (uint32_t i0 = 0; i0 < sub_docs; i0 += 512) {
-          float4 v[4];
-#pragma unroll
-          for (int r = 0; r < 4; r++) v[r] = make_float4(0, 0, 0, 0);
-          for (uint32_t m = colmask; m; m &= m - 1) {
-            const uint32_t t = __ffs(m) - 1;
-            const float4 *cp = reinterpret_cast<const float4 *>(seg.cols + qt[t].sc_base + tile_lo + i0) + lane;
-            const float w = qt[t].weight;
-            float4 c[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) c[r] = (i0 + r * 128 < sub_docs) ? __ldg(cp + r * 32) : make_float4(0, 0, 0, 0);
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-              v[r].x = __fadd_rn(v[r].x, __fmul_rn(c[r].x, w));
-              v[r].y = __fadd_rn(v[r].y, __fmul_rn(c[r].y, w));
-              v[r].z = __fadd_rn(v[r].z, __fmul_rn(c[r].z, w));
-              v[r].w = __fadd_rn(v[r].w, __fmul_rn(c[r].w, w));
-            }
-          }
-#pragma unroll
-          for (int r = 0; r < 4; r++) {
-            if (i0 + r * 128 < sub_docs) *reinterpret_cast<float4 *>(acc + i0 + r * 128 + lane * 4) = v[r];
-            wmax = max(wmax, max(max(__float_as_uint(v[r].x), __float_as_uint(v[r].y)), max(__float_as_uint(v[r].z), __float_as_uint(v[r].w))));
-          }
-        }
-        first = false;
-        dirty = false;
-        __syncwarp();
-      }
 #pragma unroll 1
       for (uint32_t t = 0; t < nt; t++) {
         const uint32_t lo = rb[t * kRbStride + j], hi = rb[t * kRbStride + j + 1];
         if (hi <= lo) continue;
-        if (COLS && ((colmask >> t) & 1u)) continue;
         if (MAXSCORE && ((nmask >> t) & 1u)) continue;
         const QTerm q = qt[t];
         const bool scored = q.flags & 1u;
@@ -480,14 +434,9 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
         thr_hi = cut > 0.0f ? __float_as_uint(cut) : 0u;
       }
       if (!STATS && !MATCHER && __reduce_max_sync(0xFFFFFFFFu, wmax) < thr_hi) {
-        // no score of this sub-tile reaches the threshold: nothing to collect, only clear — and not even
-        // that after a column fill: the next column fill overwrites every slot
-        if (COLS && colmask) {
-          dirty = true;
-        } else {
+        // no score of this sub-tile reaches the threshold: nothing to collect, only clear
 #pragma unroll 4
-          for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) *reinterpret_cast<float4 *>(acc + i0 + lane * 4) = make_float4(0, 0, 0, 0);
-        }
+        for (uint32_t i0 = 0; i0 < tile_n; i0 += 128) *reinterpret_cast<float4 *>(acc + i0 + lane * 4) = make_float4(0, 0, 0, 0);
         __syncwarp();
         continue;
       }
@@ -514,12 +463,9 @@ __global__ void __launch_bounds__(kThreads, 3) slg_score_warp_kernel(SegmentDev 
       auto rescore = [&](bool have, uint32_t doc) {
         float s = 0.0f;
         if (have) {
-          for (uint32_t tt = 0; tt < (COLS ? 2u * nt : nt); tt++) {
-            // COLS: the kernel's order — the terms summed from columns first, then the others
-            const uint32_t t = tt < nt ? tt : tt - nt;
+          for (uint32_t t = 0; t < nt; t++) {
             const QTerm &q = qt[t];
             if (!(q.flags & 1u)) continue;
-            if (COLS && (((q.flags >> 2) & 1u) != 0u) != (tt < nt)) continue;
             float c = 0.0f;
             if (q.sc_base != ~0ull) {
               c = __ldg(seg.cols + q.sc_base + doc);

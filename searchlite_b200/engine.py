@@ -100,6 +100,8 @@ class Counters(C.Structure):
         ("kernel_launches", C.c_uint64), ("score_launches", C.c_uint64), ("score_ms_total", C.c_double),
         ("last_score_ms", C.c_double), ("last_batch_ms", C.c_double), ("last_posting_count", C.c_uint64),
         ("resident_bytes", C.c_uint64), ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64),
+        ("last_postings_scattered", C.c_uint64), ("last_subtiles_skipped", C.c_uint64),
+        ("last_column_blocks_streamed", C.c_uint64), ("last_items", C.c_uint64),
     ]
 
 
@@ -122,6 +124,8 @@ EXPORTED_SYMBOLS = [
     "slg_inspect_segment_files", "slg_load_segment_files", "slg_load_index_dir", "slg_load_index_dir_shard", "slg_load_vector_file", "slg_term_lookup",
     "slg_column_lookup", "slg_field_stats", "slg_load_positions", "slg_phrase_compile", "slg_phrase_compile_batch", "slg_filter_combine", "slg_filter_combine_batch", "slg_filter_free",
     "slg_batch_cursor_seen", "slg_cursor_encode", "slg_cursor_decode",
+    "slg_batch_run_seeds", "slg_batch_threshold_keys", "slg_batch_import_thresholds", "slg_batch_run_sweep",
+    "slg_batch_packed_results", "slg_merge_gathered_packed",
 ]
 
 
@@ -185,6 +189,12 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_filter_combine": [vp, u32, i32, i32],
         "slg_filter_combine_batch": [vp, u32, vp, vp, u32, vp],
         "slg_filter_free": [vp, i32],
+        "slg_batch_run_seeds": [vp],
+        "slg_batch_threshold_keys": [vp, C.POINTER(vp)],
+        "slg_batch_import_thresholds": [vp, vp],
+        "slg_batch_run_sweep": [vp, i32],
+        "slg_batch_packed_results": [vp, C.POINTER(vp), C.POINTER(u64)],
+        "slg_merge_gathered_packed": [vp, vp, u64, u32, u32, u32, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -419,9 +429,13 @@ class QueryBatch:
 class PreparedBatch:
     """A query batch resident on the device (slg_batch_prepare)."""
 
-    def __init__(self, index: "GpuIndex", handle: int, n_queries: int, k: int, keepalive):
+    def __init__(self, index: "GpuIndex", handle: int, n_queries: int, k: int, keepalive, execution: str = "bm25"):
         self.index, self.handle, self.n_queries, self.k = index, handle, n_queries, k
         self._keepalive = keepalive
+        self.execution = execution
+        # pruned executions can run in two steps (seeds / threshold exchange / sweep) when the engine's items kernel
+        # takes the batch; the first refusal (SLG_ERR_UNSUPPORTED) switches this off
+        self.two_step_ok = execution != "bm25"
 
     def enable_stats(self, on: bool = True) -> None:
         self.index._check(self.index.lib.slg_batch_enable_stats(self.handle, 1 if on else 0))
@@ -435,6 +449,33 @@ class PreparedBatch:
         stats = np.zeros(self.n_queries, dtype=STATS_DTYPE) if want_stats else None
         self.index._check(self.index.lib.slg_batch_fetch(self.handle, _ptr(hits), _ptr(counts), _ptr(stats)))
         return (hits, counts, stats) if want_stats else (hits, counts)
+
+    # two-step pruned run for one-segment-per-GPU sharding: seeds -> threshold exchange -> sweep
+    def run_seeds(self) -> bool:
+        """False (and nothing was run) when this batch cannot run in two steps"""
+        rc = self.index.lib.slg_batch_run_seeds(self.handle)
+        if rc == -4:  # SLG_ERR_UNSUPPORTED
+            self.two_step_ok = False
+            return False
+        self.index._check(rc)
+        return True
+
+    def threshold_keys_ptr(self) -> int:
+        p = C.c_void_p()
+        self.index._check(self.index.lib.slg_batch_threshold_keys(self.handle, C.byref(p)))
+        return p.value
+
+    def import_thresholds(self, dev_keys_ptr: int) -> None:
+        self.index._check(self.index.lib.slg_batch_import_thresholds(self.handle, dev_keys_ptr))
+
+    def run_sweep(self, sync: bool = True) -> None:
+        self.index._check(self.index.lib.slg_batch_run_sweep(self.handle, 1 if sync else 0))
+
+    def packed_results(self):
+        """(device pointer, bytes) of the last run's result block: n_queries*k hits, then n_queries counts"""
+        p, n = C.c_void_p(), C.c_uint64()
+        self.index._check(self.index.lib.slg_batch_packed_results(self.handle, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def device_results(self):
         dh, dc = C.c_void_p(), C.c_void_p()
@@ -490,7 +531,9 @@ class GpuIndex:
     """Device-resident index: the GPU stand-in for Index::reader() + IndexReader::search on the
     BM25 top-k path.  One instance owns one CUDA device/stream."""
 
-    KERNEL = {"auto": 0, "cta": 1, "warp": 2, "reg": 3, "warp-inplace": 2 + 256, "auto-inplace": 256}
+    # "items": the posting-driven kernel is required (an unsupported batch is an error instead of a fallback);
+    # "reg" is its round-1 name
+    KERNEL = {"auto": 0, "cta": 1, "warp": 2, "items": 3, "reg": 3, "warp-inplace": 2 + 256, "auto-inplace": 256}
 
     def __init__(self, device: int = 0, tile_docs: int = 0, ctas_per_sm: int = 0, sub_docs: int = 0, kernel: str = "auto",
                  options: Optional[dict] = None):
@@ -703,13 +746,20 @@ class GpuIndex:
         h = C.c_void_p()
         self._check(self.lib.slg_batch_prepare(self.handle, _ptr(s), batch.n_queries, k, EXECUTION[execution],
                                                bmw_block_size, C.byref(h)))
-        return PreparedBatch(self, h, batch.n_queries, k, batch)
+        return PreparedBatch(self, h, batch.n_queries, k, batch, execution)
 
     def merge_gathered(self, dev_hits_ptr: int, dev_counts_ptr: int, n_shards: int, n_queries: int, k: int):
         hits = np.zeros((n_queries, k), dtype=HIT_DTYPE)
         counts = np.zeros(n_queries, dtype=np.uint32)
         self._check(self.lib.slg_merge_gathered(self.handle, dev_hits_ptr, dev_counts_ptr, n_shards, n_queries, k,
                                                 _ptr(hits), _ptr(counts)))
+        return hits, counts
+
+    def merge_gathered_packed(self, dev_blocks_ptr: int, n_shards: int, n_queries: int, k: int, shard_stride: int = 0):
+        hits = np.zeros((n_queries, k), dtype=HIT_DTYPE)
+        counts = np.zeros(n_queries, dtype=np.uint32)
+        self._check(self.lib.slg_merge_gathered_packed(self.handle, dev_blocks_ptr, shard_stride, n_shards, n_queries, k,
+                                                       _ptr(hits), _ptr(counts)))
         return hits, counts
 
     # ---- vectors ---------------------------------------------------------------------------

@@ -1,8 +1,8 @@
 """Doc-range / segment sharding across the GPUs of one box.
 
 One process per GPU, each holding one segment (== shard).  Per batch every rank scores all
-queries against its own segment, the per-rank top-k lists (Q x k x 12 B) are exchanged with ONE
-all-gather over NCCL/NVLink, and every rank merges the gathered lists with the device merge
+queries against its own segment, the per-rank result blocks (Q x k x 12 B of hits + Q x 4 B of counts)
+are exchanged with ONE all-gather over NCCL/NVLink, and every rank merges the gathered lists with the device merge
 kernel (slg_merge_gathered) in the reference's SortKey order — score desc, segment_ord asc,
 doc_id asc (searchlite-core/src/api/reader.rs:2777, src/query/sort.rs:80-93).  Because N, df
 and avgdl are per segment in the reference (api/reader.rs:2985,2994), the N-GPU result equals
@@ -35,16 +35,13 @@ def shard_ranges(n_docs: int, world: int) -> list:
     return out
 
 
-def gather_hits(local_hits: torch.Tensor, local_counts: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """all-gather of per-rank results.  local_hits: uint8 [Q*k*12], local_counts: int32 [Q].
-    Returns ([world, Q*k*12] uint8, [world, Q] int32), rank-major."""
+def gather_blocks(local_block: torch.Tensor, group=None) -> torch.Tensor:
+    """ONE all-gather of the per-rank result blocks (uint8, Q*k*12 bytes of hits followed by Q*4 bytes of counts — the
+    layout of slg_batch_packed_results).  Returns [world, block bytes], rank-major."""
     world = dist.get_world_size(group)
-    # flat outputs (rank-major concatenation): the form both NCCL and gloo accept
-    hits = torch.empty(world * local_hits.numel(), dtype=local_hits.dtype, device=local_hits.device)
-    counts = torch.empty(world * local_counts.numel(), dtype=local_counts.dtype, device=local_counts.device)
-    dist.all_gather_into_tensor(hits, local_hits.reshape(-1), group=group)
-    dist.all_gather_into_tensor(counts, local_counts.reshape(-1), group=group)
-    return hits.view(world, -1), counts.view(world, -1)
+    out = torch.empty(world * local_block.numel(), dtype=local_block.dtype, device=local_block.device)
+    dist.all_gather_into_tensor(out, local_block.reshape(-1), group=group)
+    return out.view(world, -1)
 
 
 class ShardedSearcher:
@@ -55,29 +52,63 @@ class ShardedSearcher:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.host_merge = host_merge
         self.stream = None
+        self.block_bytes = n_queries * k * HIT_BYTES + n_queries * 4
         if index is not None:
-            dev = torch.device("cuda", index.device)
-            self.stream = torch.cuda.ExternalStream(index.stream_ptr(), device=dev)
-            self.send_hits = torch.empty(n_queries * k * HIT_BYTES, dtype=torch.uint8, device=dev)
-            self.send_counts = torch.empty(n_queries, dtype=torch.int32, device=dev)
+            self.dev = torch.device("cuda", index.device)
+            self.stream = torch.cuda.ExternalStream(index.stream_ptr(), device=self.dev)
+
+    def _as_tensor(self, ptr: int, nbytes: int, dtype=torch.uint8) -> torch.Tensor:
+        """zero-copy view of device memory the engine owns (valid until the batch is re-run or freed)"""
+        itemsize = torch.empty((), dtype=dtype).element_size()
+
+        class _Arr:  # __cuda_array_interface__ v3
+            pass
+        a = _Arr()
+        typestr = {torch.uint8: "|u1", torch.int64: "<i8"}[dtype]
+        a.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                      "strides": None}
+        return torch.as_tensor(a, device=self.dev)
+
+    def run(self, prepared, exchange_thresholds: bool = True):
+        """one sharded search: local scoring (asynchronous), the exchange, the merge.  Pruned executions run in two steps
+        with an all-reduce(max) of the per-query k-th keys after the seeds, so every shard prunes against the global
+        bound."""
+        if self.world == 1:
+            prepared.run(sync=False)
+            return prepared.fetch()
+        with torch.cuda.stream(self.stream):
+            if exchange_thresholds and prepared.two_step_ok and prepared.run_seeds():
+                keys = self._as_tensor(prepared.threshold_keys_ptr(), self.q * 8, torch.int64)  # positive-score keys: top bit clear
+                glob = keys.clone()
+                dist.all_reduce(glob, op=dist.ReduceOp.MAX, group=self.group)
+                prepared.import_thresholds(glob.data_ptr())
+                prepared.run_sweep(sync=False)
+            else:
+                prepared.run(sync=False)
+            return self._exchange(prepared)
+
+    def _exchange(self, prepared):
+        ptr, nbytes = prepared.packed_results()
+        assert nbytes == self.block_bytes
+        blocks = gather_blocks(self._as_tensor(ptr, nbytes), self.group)
+        # NCCL work is ordered after the current (= the handle's) stream and the stream waits for it
+        return self.index.merge_gathered_packed(blocks.data_ptr(), self.world, self.q, self.k)
 
     def exchange_and_merge(self, prepared) -> Tuple[np.ndarray, np.ndarray]:
-        """after prepared.run(): gather every rank's top-k and merge on the device"""
+        """after prepared.run(): gather every rank's top-k with one all-gather and merge on the device"""
         if self.world == 1:
             return prepared.fetch()
         with torch.cuda.stream(self.stream):
-            prepared.copy_results_to(self.send_hits.data_ptr(), self.send_counts.data_ptr())
-            hits, counts = gather_hits(self.send_hits, self.send_counts, self.group)
-            # NCCL work is ordered after the current (= the handle's) stream and the stream waits for it
-            return self.index.merge_gathered(hits.data_ptr(), counts.data_ptr(), self.world, self.q, self.k)
+            return self._exchange(prepared)
 
     def merge_cpu(self, local_hits: np.ndarray, local_counts: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-        """gloo path used by the CPU tests: same exchange, merge by `host_merge`"""
-        lh = torch.from_numpy(np.ascontiguousarray(local_hits).view(np.uint8).reshape(-1))
-        lc = torch.from_numpy(np.ascontiguousarray(local_counts).astype(np.int32))
-        hits, counts = gather_hits(lh, lc, self.group)
-        hits = hits.numpy().view(HIT_DTYPE).reshape(self.world, self.q, self.k)
-        counts = counts.numpy().astype(np.uint32)
+        """gloo path used by the CPU tests: same single-block exchange, merge by `host_merge`"""
+        lh = np.ascontiguousarray(local_hits).view(np.uint8).reshape(-1)
+        lc = np.ascontiguousarray(local_counts).astype(np.uint32).view(np.uint8).reshape(-1)
+        blocks = gather_blocks(torch.from_numpy(np.concatenate([lh, lc])), self.group).numpy()
+        hb = self.q * self.k * HIT_BYTES
+        hits = np.ascontiguousarray(blocks[:, :hb]).view(HIT_DTYPE).reshape(self.world, self.q, self.k)
+        counts = np.ascontiguousarray(blocks[:, hb:]).view(np.uint32).reshape(self.world, self.q)
         out_h = np.zeros((self.q, self.k), dtype=HIT_DTYPE)
         out_c = np.zeros(self.q, dtype=np.uint32)
         for qi in range(self.q):

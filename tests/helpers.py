@@ -59,9 +59,9 @@ def hits_to_list(hits, counts, q: int = 0):
 
 
 def canonical_batch(gi, qb: QueryBatch, segment_ord: int = 0) -> QueryBatch:
-    """The tile-sweep kernel's summation order (include/searchlite_gpu.h, slg_set_option): per query
-    the terms WITH a dense column first, then the terms WITHOUT one, both in query order.  The oracle's
-    `bm25` mode on this permuted batch is what that kernel must reproduce bit for bit."""
+    """The column path's declared summation order (include/searchlite_gpu.h, slg_set_option): per query
+    the terms WITHOUT a dense column first, then the terms WITH one, both in query order.  The oracle's
+    `bm25` mode on this permuted batch is what the items kernel must reproduce bit for bit."""
     terms = qb.terms.copy()
     cache = {}
     for q in range(qb.n_queries):
@@ -72,7 +72,7 @@ def canonical_batch(gi, qb: QueryBatch, segment_ord: int = 0) -> QueryBatch:
             if t not in cache:
                 cache[t] = False if t == 0xFFFFFFFF else gi.term_has_column(segment_ord, t)
             has.append(cache[t])
-        order = [i for i, h in enumerate(has) if h] + [i for i, h in enumerate(has) if not h]
+        order = [i for i, h in enumerate(has) if not h] + [i for i, h in enumerate(has) if h]
         terms[a:b] = rows[order]
     out = QueryBatch(qb.term_off.copy(), terms)
     out.filter_id = None if qb.filter_id is None else qb.filter_id.copy()

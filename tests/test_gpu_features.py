@@ -15,15 +15,14 @@ from tests.parity import assert_parity
 pytestmark = pytest.mark.gpu
 
 MATCHER_KERNELS = ["cta", "warp", "warp-inplace"]      # Bool queries: query-order kernels
-KERNELS = MATCHER_KERNELS + ["reg", "reg-dense", "reg-sweep", "reg-sweep-dense", "reg-light"]  # plain OR queries: also the column front end
-# "reg" = the automatic choice for plain OR queries: the warp kernel summing column terms from their dense columns.
+KERNELS = MATCHER_KERNELS + ["reg", "reg-dense", "reg-nocol", "reg-small"]  # plain OR queries: also the items kernel
+# "reg" = the automatic choice for plain OR queries: the posting-driven items kernel (column terms streamed from their columns).
 # reg-dense: every term with >= 2 postings and df >= N/64 gets a column (exercises the column path on tiny corpora)
-# reg-sweep*: the tile-sweep kernel (heavy_kernel 1), every query swept, without / with columns
-# reg-light: the tile-sweep front end with every query handed to the warp kernel
+# reg-nocol: the items kernel without columns; reg-small: 128-doc sub-tiles, so tiny corpora span several items
 REG_OPTIONS = {"reg-dense": {"dense_min_df": 2, "dense_den": 64},
-               "reg-sweep": {"heavy_kernel": 1, "dense_den": 0, "sweep_min_postings": 1},
-               "reg-sweep-dense": {"heavy_kernel": 1, "dense_min_df": 2, "dense_den": 64, "sweep_min_postings": 1},
-               "reg-light": {"heavy_kernel": 1, "dense_den": 0, "sweep_min_postings": 1 << 40}}
+               "reg-nocol": {"dense_den": 0},
+               "reg-small": {"dense_min_df": 2, "dense_den": 16}}
+REG_KW = {"reg-small": {"sub_docs": 128}}
 
 
 def _oracle(seg, **kw):
@@ -33,7 +32,7 @@ def _oracle(seg, **kw):
 
 def _gpu(seg, kernel="auto", k1=0.9, b=0.4, **kw):
     if kernel in REG_OPTIONS:
-        gi = GpuIndex(0, kernel="reg", options=REG_OPTIONS[kernel], **kw)
+        gi = GpuIndex(0, kernel="reg", options=REG_OPTIONS[kernel], **{**REG_KW.get(kernel, {}), **kw})
     else:
         gi = GpuIndex(0, kernel=kernel, **kw)
     cols = gi.load_segment(seg, k1=k1, b=b)
@@ -363,9 +362,10 @@ def test_post_image_load_equals_csr_load():
     for mode in ("bm25", "bmw"):
         assert_engine_parity(gi, ora, qb, 11, gi.search_batch(qb, 11, mode))
     gi.close()
-    gi = GpuIndex(0, kernel="reg", options={"heavy_kernel": 1})
+    gi = GpuIndex(0, kernel="items", sub_docs=512, options={"dense_min_df": 64})
     gi.load_segment_post_image(seg, img, off)
-    assert_engine_parity(gi, ora, qb, 11, gi.search_batch(qb, 11, "bm25"))
+    for mode in ("bm25", "bmw"):
+        assert_engine_parity(gi, ora, qb, 11, gi.search_batch(qb, 11, mode))
     gi.close()
     gi = GpuIndex(0, kernel="warp")
     gi.load_segment_post_image(seg, img, off)
@@ -379,14 +379,14 @@ def test_post_image_load_equals_csr_load():
 
 
 # ---- several segments in one handle: api/reader.rs:2670-2777 ----------------------------------------------
-@pytest.mark.parametrize("kernel", ["cta", "warp", "reg", "reg-dense", "reg-sweep", "reg-sweep-dense"])
+@pytest.mark.parametrize("kernel", ["cta", "warp", "reg", "reg-dense", "reg-nocol", "reg-small"])
 def test_multi_segment_merge_order(kernel):
     from oracle import slo
     from searchlite_b200.shard import shard_ranges
     from tests.helpers import canonical_batch
     n_docs, vocab, world = 24_000, 1_500, 3
     qb = synth.generate_queries(70, vocab, seed=72, min_rank=2)
-    gi = GpuIndex(0, kernel="reg", options=REG_OPTIONS[kernel]) if kernel in REG_OPTIONS else GpuIndex(0, kernel=kernel)
+    gi = GpuIndex(0, kernel="reg", options=REG_OPTIONS[kernel], **REG_KW.get(kernel, {})) if kernel in REG_OPTIONS else GpuIndex(0, kernel=kernel)
     per_seg = []
     for r, (lo, hi) in enumerate(shard_ranges(n_docs, world)):
         spec = synth.CorpusSpec(n_docs=hi - lo, vocab=vocab, seed=71, len_lo=10, len_hi=60, segment_ord=r, doc_base=lo)
@@ -496,7 +496,7 @@ def test_rerank_matches_oracle_formulae(metric, bf16):
 
 
 # ---- statistics (QueryStats, query/wand.rs:45-50) -----------------------------------------------------------
-@pytest.mark.parametrize("kernel", ["cta", "warp", "warp-inplace", "reg", "reg-dense", "reg-sweep", "reg-sweep-dense", "reg-light"])
+@pytest.mark.parametrize("kernel", ["cta", "warp", "warp-inplace", "reg", "reg-dense", "reg-nocol", "reg-small"])
 def test_stats_count_scored_docs_and_postings(kernel):
     spec = synth.CorpusSpec(n_docs=15_000, vocab=1_200, seed=91, len_lo=10, len_hi=50)
     seg = synth.generate_segment(spec, "cpu")

@@ -3,9 +3,9 @@
 
 Float contract (include/searchlite_gpu.h): the CTA and warp kernels sum a doc's contributions in query
 term order — bit-identical to the oracle's `bm25` mode (brute_force, query/wand.rs:527-548); the
-tile-sweep kernel sums the terms with a dense column first, then the terms without one —
-bit-identical to the oracle on that permutation of the query and within the north-star 1e-5 rule of
-the query order."""
+items kernel (the automatic choice for plain OR queries) sums the terms without a dense column first,
+then the terms with one — bit-identical to the oracle on that permutation of the query and within the
+north-star 1e-5 rule of the query order."""
 import numpy as np
 import pytest
 
@@ -52,59 +52,87 @@ def test_bm25_bit_exact_vs_oracle(small, kernel, tile_docs, sub_docs, k):
 
 @pytest.mark.parametrize("k", [1, 11, 32])
 @pytest.mark.parametrize("dense_den", [0, 8, 64])
-@pytest.mark.parametrize("sub_docs", [256, 2048])
-def test_column_front_end_vs_oracle(small, k, dense_den, sub_docs):
-    """column front end 0: warp kernel, column terms summed from their dense columns.
-    dense_den 0: no columns (query order); 8: default; 64: most query terms are columns"""
+@pytest.mark.parametrize("sub_docs", [128, 256, 2048, 4096])
+def test_items_kernel_vs_oracle(small, k, dense_den, sub_docs):
+    """the posting-driven items kernel.  dense_den 0: no columns (query order); 8: default; 64: most query terms
+    are columns.  bm25 / wand / bmw return the same bytes, and so does the statistics run (warp kernel on the same
+    term layout)."""
     seg, qb = small
     ora = _oracle(seg)
-    gi = GpuIndex(0, kernel="reg", sub_docs=sub_docs, options={**DENSE, "dense_den": dense_den})
+    gi = GpuIndex(0, kernel="items", sub_docs=sub_docs, options={**DENSE, "dense_den": dense_den})
     gi.load_segment(seg)
     n_col = sum(gi.term_has_column(0, int(t)) for t in np.unique(qb.terms["term_id"]))
     assert (n_col == 0) == (dense_den == 0)
+    first = None
     for mode in ("bm25", "wand", "bmw"):
         got = gi.search_batch(qb, k, mode)
         assert_engine_parity(gi, ora, qb, k, got, exact_order=(dense_den == 0))
+        if first is None:
+            first = got
+        assert got[0].tobytes() == first[0].tobytes() and got[1].tobytes() == first[1].tobytes(), mode
+    with_stats = gi.search_batch(qb, k, "bm25", want_stats=True)
+    assert with_stats[0].tobytes() == first[0].tobytes() and with_stats[1].tobytes() == first[1].tobytes()
     gi.close()
 
 
-@pytest.mark.parametrize("v", [8])  # the 4-wide variant is disabled (intermittent illegal memory access, DESIGN.md §6)
-@pytest.mark.parametrize("k", [1, 11, 32])
-@pytest.mark.parametrize("dense_den", [0, 8, 64])
-@pytest.mark.parametrize("min_postings", [0, 1])
-def test_sweep_kernel_vs_oracle(small, v, k, dense_den, min_postings):
-    """the tile-sweep kernel (heavy_kernel 1).  dense_den 0: no columns (pure sparse path, query order); 8:
-    default; 64: most query terms are columns.  min_postings 0: queries with few postings go to the warp
-    kernel; 1: every query is swept"""
+@pytest.mark.parametrize("maxscore_pct", [0, 35, 100])
+def test_items_kernel_maxscore_settings_are_exact(small, maxscore_pct):
+    """the MaxScore cap only moves work between scattering and exact rescoring: the bytes never change"""
     seg, qb = small
     ora = _oracle(seg)
-    gi = GpuIndex(0, kernel="reg", options={**DENSE, "heavy_kernel": 1, "dense_den": dense_den, "reg_tile_v": v,
-                                            "sweep_min_postings": min_postings, "seed_docs": 4096 if k == 11 else 16384})
+    gi = GpuIndex(0, kernel="items", sub_docs=512, options={**DENSE, "dense_den": 32, "maxscore_pct": maxscore_pct})
     gi.load_segment(seg)
-    n_col = sum(gi.term_has_column(0, int(t)) for t in np.unique(qb.terms["term_id"]))
-    assert (n_col == 0) == (dense_den == 0)
-    for mode in ("bm25", "wand", "bmw"):
-        got = gi.search_batch(qb, k, mode)
-        assert_engine_parity(gi, ora, qb, k, got, exact_order=(dense_den == 0))
+    full = gi.search_batch(qb, 11, "bm25")
+    got = gi.search_batch(qb, 11, "bmw")
+    assert got[0].tobytes() == full[0].tobytes() and got[1].tobytes() == full[1].tobytes()
+    assert_engine_parity(gi, ora, qb, 11, got)
     gi.close()
 
 
-def test_automatic_kernel_is_the_column_front_end(small):
+def test_items_kernel_weights_and_filters(small):
+    """weights != 1 (score_tf multiplies by the merged weight, query/wand.rs:284-285), deleted docs and a root
+    filter on the items kernel, every execution"""
+    seg, qb = small
+    import copy
+    seg2 = copy.copy(seg)
+    seg2.deleted_docs = np.arange(0, seg.doc_count, 7, dtype=np.uint32)
+    year = (np.arange(seg.doc_count) % 26 + 2000).astype(np.int64)
+    seg2.fast_i64 = {"year": (year, None)}
+    rng = np.random.default_rng(5)
+    tl = [qb.terms["term_id"][int(qb.term_off[q]):int(qb.term_off[q + 1])].tolist() for q in range(qb.n_queries)]
+    wq = QueryBatch.from_term_lists(tl, [[float(np.float32(rng.uniform(0.25, 3.0))) for _ in t] for t in tl])
+    ora = _oracle(seg2)
+    gi = GpuIndex(0, kernel="items", sub_docs=1024, options=DENSE)
+    cols = gi.load_segment(seg2)
+    from searchlite_b200.engine import FILTER_DTYPE, F_I64_RANGE
+    from tests.helpers import canonical_batch
+
+    def prog(c):
+        node = np.zeros(1, dtype=FILTER_DTYPE)
+        node[0]["op"], node[0]["column"], node[0]["i_min"], node[0]["i_max"] = F_I64_RANGE, c["year"], 2003, 2011
+        return node
+    fid = gi.compile_filter(prog(cols))
+    wq.filter_id = np.full(wq.n_queries, fid, dtype=np.int32)
+    for mode in ("bm25", "bmw", "wand"):
+        got = gi.search_batch(wq, 11, mode)
+        assert_parity(*ora.search_batch(canonical_batch(gi, wq), 11, "bm25", filter_nodes=prog(ora.columns)), *got, strict=True)
+        assert_parity(*ora.search_batch(wq, 11, "bm25", filter_nodes=prog(ora.columns)), *got, strict=False)
+    gi.close()
+
+
+def test_automatic_kernel_is_the_items_kernel(small):
     seg, qb = small
     ora = _oracle(seg)
     ref = ora.search_batch(qb, 11, "bm25")
-    # automatic choice for plain OR queries: the warp kernel summing column terms from their columns
+    # automatic choice for plain OR queries: the items kernel (column terms streamed from their columns)
     gi = GpuIndex(0, options=DENSE)
     gi.load_segment(seg)
     auto = gi.search_batch(qb, 11, "bm25")
     assert_engine_parity(gi, ora, qb, 11, auto)
-    # both column front ends share one float contract
-    r0 = GpuIndex(0, kernel="reg", options={**DENSE, "heavy_kernel": 0})
+    assert gi.counters()["last_items"] > 0
+    r0 = GpuIndex(0, kernel="items", options=DENSE)
     r0.load_segment(seg)
-    r1 = GpuIndex(0, kernel="reg", options={**DENSE, "heavy_kernel": 1})
-    r1.load_segment(seg)
-    a, b = r0.search_batch(qb, 11, "bm25"), r1.search_batch(qb, 11, "bm25")
-    assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
+    a = r0.search_batch(qb, 11, "bm25")
     assert auto[0].tobytes() == a[0].tobytes() and auto[1].tobytes() == a[1].tobytes()
     # the explicit warp kernel keeps the reference's summation order, bit for bit
     warp = GpuIndex(0, kernel="warp", options=DENSE)
@@ -115,7 +143,12 @@ def test_automatic_kernel_is_the_column_front_end(small):
     capped.load_segment(seg)
     assert sum(capped.term_has_column(0, t) for t in range(200)) == 3
     assert_engine_parity(capped, ora, qb, 11, capped.search_batch(qb, 11, "bm25"))
-    for g in (gi, warp, r0, r1, capped):
+    # a batch the items kernel cannot take is an error when it is required, a fallback when it is not
+    bq = QueryBatch.from_bool([{"must": [3, 5]}])
+    with pytest.raises(SearchliteGpuError, match="items kernel handles plain OR"):
+        r0.search_batch(bq, 11, "bm25")
+    gi.search_batch(bq, 11, "bm25")
+    for g in (gi, warp, r0, capped):
         g.close()
 
 
@@ -136,29 +169,34 @@ def test_pruned_modes_are_exact(small, execution, kernel):
 
 
 @pytest.mark.parametrize("execution", ["wand", "bmw"])
-@pytest.mark.parametrize("heavy_kernel", [0, 1])
-def test_column_paths_pruning_skips_work_and_stays_exact(small, execution, heavy_kernel):
+def test_items_kernel_pruning_skips_work_and_stays_exact(small, execution):
     seg, qb = small
     ora = _oracle(seg)
-    gi = GpuIndex(0, kernel="reg", sub_docs=256, options={**DENSE, "heavy_kernel": heavy_kernel})
+    gi = GpuIndex(0, kernel="items", sub_docs=256, options=DENSE)
     gi.load_segment(seg)
-    full_h, full_c, full_st = gi.search_batch(qb, 11, "bm25", want_stats=True)
-    got_h, got_c, st = gi.search_batch(qb, 11, execution, want_stats=True)
+    full_h, full_c = gi.search_batch(qb, 11, "bm25")
+    full_ctr = gi.counters()
+    got_h, got_c = gi.search_batch(qb, 11, execution)
+    ctr = gi.counters()
     assert got_h.tobytes() == full_h.tobytes() and got_c.tobytes() == full_c.tobytes()  # pruning never changes the result
     assert_engine_parity(gi, ora, qb, 11, (got_h, got_c))
     wand = ora.search_batch(qb, 11, "wand")
     assert_parity(*wand, got_h, got_c, strict=False)
-    if heavy_kernel == 0:  # (the tile-sweep front end prunes per 1024-doc register tile; its savings are not asserted here)
-        assert st["blocks_skipped"].sum() > 0
-        assert st["scored_docs"].sum() < full_st["scored_docs"].sum()
-    else:
-        assert st["scored_docs"].sum() <= full_st["scored_docs"].sum()
+    assert ctr["last_items"] < full_ctr["last_items"]                                  # the filter drops (query, doc range) items
+    assert ctr["last_postings_scattered"] < full_ctr["last_postings_scattered"]
+    assert ctr["last_column_blocks_streamed"] < full_ctr["last_column_blocks_streamed"]
+    # per-query statistics come from the warp kernel on the same term layout: same bytes, counted skips
+    st_h, st_c, st = gi.search_batch(qb, 11, execution, want_stats=True)
+    assert st_h.tobytes() == full_h.tobytes() and st_c.tobytes() == full_c.tobytes()
+    assert st["blocks_skipped"].sum() > 0
     gi.close()
 
 
-def test_disabled_sweep_variant_is_refused():
-    with pytest.raises(SearchliteGpuError, match="reg_tile_v 4 is disabled"):
-        GpuIndex(0, kernel="reg", options={"reg_tile_v": 4})
+def test_removed_sweep_kernel_is_refused():
+    with pytest.raises(SearchliteGpuError, match="heavy_kernel 1 .* was removed"):
+        GpuIndex(0, options={"heavy_kernel": 1})
+    with pytest.raises(SearchliteGpuError, match="unknown option"):
+        GpuIndex(0, options={"reg_tile_v": 8})
 
 
 def test_division_sequence_is_ieee_exact():
@@ -180,7 +218,7 @@ def test_full_size_c2_properties():
     k = 11
     results = {}
     canon = None
-    for kernel, mode, opts in (("auto", "bm25", {}), ("auto", "bmw", {}), ("reg", "bm25", {"heavy_kernel": 1}), ("warp", "bm25", {}),
+    for kernel, mode, opts in (("auto", "bm25", {}), ("auto", "bmw", {}), ("auto", "wand", {}), ("warp", "bm25", {}),
                                ("warp", "bmw", {}), ("warp-inplace", "bm25", {}), ("cta", "bm25", {})):
         gi = GpuIndex(0, kernel=kernel, options=opts)
         gi.load_segment(seg)
@@ -190,7 +228,7 @@ def test_full_size_c2_properties():
         p.run()
         again = p.fetch()
         assert first[0].tobytes() == again[0].tobytes() and first[1].tobytes() == again[1].tobytes()  # re-runnable
-        results[(kernel, mode, opts.get("heavy_kernel"))] = first
+        results[(kernel, mode, None)] = first
         if kernel == "auto" and canon is None:
             from tests.helpers import canonical_batch
             canon = canonical_batch(gi, qb.subset(0, 48))
@@ -201,7 +239,7 @@ def test_full_size_c2_properties():
     w_h, w_c = results[("warp", "bm25", None)]                     # query order
     assert results[("auto", "bmw", None)][0].tobytes() == base_h.tobytes()
     assert results[("warp", "bmw", None)][0].tobytes() == w_h.tobytes()
-    assert results[("reg", "bm25", 1)][0].tobytes() == base_h.tobytes() and results[("reg", "bm25", 1)][1].tobytes() == base_c.tobytes()
+    assert results[("auto", "wand", None)][0].tobytes() == base_h.tobytes() and results[("auto", "wand", None)][1].tobytes() == base_c.tobytes()
     for key in (("warp-inplace", "bm25", None), ("cta", "bm25", None)):
         assert results[key][0].tobytes() == w_h.tobytes() and results[key][1].tobytes() == w_c.tobytes(), key
     assert_parity(w_h, w_c, base_h, base_c, strict=False)

@@ -303,6 +303,6 @@ def test_gpu_plan_validation():
     gw = GpuIndex(0, kernel="reg")
     gw.load_segment(seg)
     qb = QueryBatch.from_term_lists([[0, 1]]).set_plans([("sum", [("leaf", 0), ("leaf", 1)])])
-    with pytest.raises(SearchliteGpuError, match="warp or CTA-per-item"):
+    with pytest.raises(SearchliteGpuError, match="items kernel handles plain OR"):
         gw.search_batch(qb, 3, "bm25")
     gw.close()
