@@ -390,6 +390,11 @@ int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
   else if (n == "dense_den") ix->dense_den = (uint32_t)value;
   else if (n == "dense_min_df") ix->dense_min_df = (uint32_t)value;
   else if (n == "max_column_bytes") ix->max_column_bytes = value;
+  else if (n == "stage_cap") {
+    if (value < 64 || value > 8192 || value % 4) return fail(ix, SLG_ERR_INVALID, "stage_cap must be a multiple of 4 in [64, 8192]");
+    ix->stage_cap = (uint32_t)value;
+  }
+  else if (n == "stream_kernels") ix->stream_kernels = value != 0;
   else if (n == "maxscore_pct") ix->maxscore_pct = (uint32_t)std::min<uint64_t>(value, 100);
   else if (n == "heavy_kernel") {  // the tile-sweep front end of round 1 is gone (it carried an unlocalised intermittent fault)
     if (value != 0) return fail(ix, SLG_ERR_UNSUPPORTED, "heavy_kernel 1 (tile-sweep kernel) was removed; the column path is the items kernel");

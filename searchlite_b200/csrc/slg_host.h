@@ -178,6 +178,8 @@ struct slg_index {
   uint32_t dense_den = 8;        // a term gets a dense column when df * dense_den >= doc_count; 0 = no columns
   uint32_t dense_min_df = 256;   // ... and df >= this
   uint64_t max_column_bytes = 24ull << 30;
+  uint32_t stage_cap = 1024;     // sparse pass: postings a warp stages in shared memory per span (slg_stream_kernel.cuh)
+  uint32_t stream_kernels = 1;   // exhaustive plain OR batches: 1 = sparse pass + column pass, 0 = the items kernel
   uint32_t maxscore_pct = 35;    // pruned warp kernel: non-essential bounds may sum to this % of the k-th score (0 = tile skip only)
   bool keep_positions = true;    // keep term positions resident when a posting image carries them (SegmentReader keep_positions)
   // term space of segments loaded from the reference's files: "field:token" key -> term id, in order of first appearance
@@ -273,6 +275,10 @@ struct slg_batch {
   slg::QTerm *qterms = nullptr;
   slg::QHead *qheads = nullptr;
   uint2 *items = nullptr;
+  slg::ColQ *colq = nullptr;          // exhaustive two-pass path: queries grouped by their first column, chunk list, scratch
+  slg::ColChunk *chunks = nullptr;
+  uint32_t *col_count = nullptr;
+  uint32_t max_cols = 0;
   uint8_t *done = nullptr;
   size_t done_bytes = 0;
   uint32_t items_cap = 0;

@@ -2,7 +2,7 @@
 // translation unit (slg_launch_tiles.cu, slg_launch_warp.cu, slg_launch_items.cu) so that the library builds in
 // parallel; the host code selects a variant by flags.
 #pragma once
-#include "slg_items_kernel.cuh"
+#include "slg_stream_kernel.cuh"
 
 namespace slg {
 
@@ -12,6 +12,8 @@ cudaError_t launch_score_warp(bool matcher, bool prune, bool stats, bool staged,
                               size_t smem, int grid, cudaStream_t st);
 cudaError_t launch_score_items(bool prune, const SegmentDev &sd, const WarpBatchDev &wb, const ItemsDev &it, size_t smem, int grid,
                                cudaStream_t st);
+cudaError_t launch_score_sparse(const SegmentDev &sd, const WarpBatchDev &wb, const StreamDev &st_dev, size_t smem, int grid, cudaStream_t st);
+cudaError_t launch_score_colgroups(const SegmentDev &sd, const WarpBatchDev &wb, const StreamDev &st_dev, int grid, cudaStream_t st);
 cudaError_t launch_seed_items(const SegmentDev &sd, const WarpBatchDev &wb, const ItemsDev &it, size_t smem, int grid, cudaStream_t st);
 
 }  // namespace slg

@@ -16,6 +16,16 @@ cudaError_t launch_score_items(bool prune, const SegmentDev &sd, const WarpBatch
                                cudaStream_t st) {
   return prune ? go(slg_score_items_kernel<true>, smem, grid, st, sd, wb, it) : go(slg_score_items_kernel<false>, smem, grid, st, sd, wb, it);
 }
+cudaError_t launch_score_sparse(const SegmentDev &sd, const WarpBatchDev &wb, const StreamDev &st_dev, size_t smem, int grid, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(slg_score_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  slg_score_sparse_kernel<false><<<grid, kSparseWarps * 32, smem, st>>>(sd, wb, st_dev);
+  return cudaGetLastError();
+}
+cudaError_t launch_score_colgroups(const SegmentDev &sd, const WarpBatchDev &wb, const StreamDev &st_dev, int grid, cudaStream_t st) {
+  slg_score_colgroups_kernel<false><<<grid, kColWarps * 32, 0, st>>>(sd, wb, st_dev);
+  return cudaGetLastError();
+}
 cudaError_t launch_seed_items(const SegmentDev &sd, const WarpBatchDev &wb, const ItemsDev &it, size_t smem, int grid, cudaStream_t st) {
   return go(slg_seed_items_kernel<0>, smem, grid, st, sd, wb, it);
 }

@@ -302,6 +302,11 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bt->items_cap = want_items ? max_groups * n_queries : 0;
   bt->done_bytes = want_items ? (size_t)max_groups * n_queries : 0;
   const size_t o_items = want_items ? carve((size_t)bt->items_cap * sizeof(uint2)) : 0;
+  const bool want_stream = bt->can_items && exec == SLG_EXEC_BM25 && ix->stream_kernels;
+  for (auto &s : ix->segs) bt->max_cols = std::max(bt->max_cols, s->n_cols);
+  const size_t o_colq = want_stream ? carve((size_t)n_queries * sizeof(ColQ)) : 0;
+  const size_t o_chunks = want_stream ? carve((size_t)n_queries * sizeof(ColChunk)) : 0;
+  const size_t o_colcount = want_stream ? carve((size_t)(bt->max_cols + 2) * 4) : 0;
   const size_t o_done = want_items ? carve(bt->done_bytes) : 0;
   bt->result_stride = align_up((size_t)n_queries * k * sizeof(HitDev) + (size_t)n_queries * 4, 256);
   const size_t o_results = carve(bt->result_stride * (S + (S > 1 ? 1 : 0)));
@@ -325,6 +330,9 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bt->qheads = bt->use_warp ? reinterpret_cast<QHead *>(base + o_qheads) : nullptr;
   bt->items = want_items ? reinterpret_cast<uint2 *>(base + o_items) : nullptr;
   bt->done = want_items ? base + o_done : nullptr;
+  bt->colq = want_stream ? reinterpret_cast<ColQ *>(base + o_colq) : nullptr;
+  bt->chunks = want_stream ? reinterpret_cast<ColChunk *>(base + o_chunks) : nullptr;
+  bt->col_count = want_stream ? reinterpret_cast<uint32_t *>(base + o_colcount) : nullptr;
   bt->results = base + o_results;
 
   // ---- pinned staging: [pack | results | per-query stats + items counters] ----
@@ -533,9 +541,37 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
         count_launch(ix);
       }
     }
+    const bool run_stream = run_items && !prune && bt->colq != nullptr;
     if (do_sweep) {
       // ---- scoring ----
-      if (score && run_items) {
+      if (score && run_stream) {
+        // exhaustive: sparse pass (staged posting runs), then column pass (queries grouped by their first column)
+        StreamDev sdv{};
+        sdv.colq = bt->colq;
+        sdv.chunks = bt->chunks;
+        sdv.n_chunks = bt->work_counter + 3;
+        sdv.col_count = bt->col_count;
+        sdv.sparse_counter = bt->work_counter + 1;
+        sdv.col_counter = bt->work_counter + 2;
+        sdv.stage_cap = ix->stage_cap;
+        sdv.counters = bt->item_counters;
+        const size_t ssmem = (size_t)kSparseWarps * sparse_smem_per_warp(wb.sub_docs, sdv.stage_cap);
+        if (ssmem + 1024 > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "sub_docs %u with stage_cap %u needs %zu B shared memory", wb.sub_docs, sdv.stage_cap, ssmem);
+        uint32_t sper = (uint32_t)std::max<size_t>(1, (ix->smem_optin + 1024) / (ssmem + 1024));
+        sper = std::min(sper, 2048u / (kSparseWarps * 32u));
+        if (ix->ctas_per_sm) sper = std::min(sper, ix->ctas_per_sm);
+        const int sgrid = (int)std::min<uint64_t>((uint64_t)ix->n_sm * sper, ((uint64_t)wb.n_groups * Q + kSparseWarps - 1) / kSparseWarps);
+        SLG_CUDA(ix, launch_score_sparse(s->dev, wb, sdv, ssmem, sgrid, st));
+        count_launch(ix);
+        if (s->n_cols) {
+          slg_colgroups_kernel<<<1, 1024, 0, st>>>(s->dev, wb, sdv, s->n_cols);
+          count_launch(ix);
+          SLG_CUDA(ix, cudaGetLastError());
+          SLG_CUDA(ix, launch_score_colgroups(s->dev, wb, sdv, ix->n_sm * 4, st));
+          count_launch(ix);
+        }
+        ix->ctr.score_launches++;
+      } else if (score && run_items) {
         if (prune) {
           const uint32_t total = wb.n_groups * Q;
           slg_filter_items_kernel<<<(total + 255) / 256, 256, 0, st>>>(wb, it);

@@ -174,11 +174,19 @@ inline bool parse_terms(const uint8_t *buf, uint64_t n, std::vector<TermEntry> &
 // ---- .fast ----
 struct FastColumn {
   std::string name;
-  int type = -1;  // FieldType code, index/fastfields.rs:41-56: 0 I64, 1 F64, 2 Str, 3.. lists / nested (skipped)
+  int type = -1;  // FieldType code, index/fastfields.rs:41-56: 0 I64, 1 F64, 2 Str, 3 I64List, 4 F64List, 5 StrList,
+                  // 6 I64Nested, 7 F64Nested, 8 StrNested, 9 / 10 nested bookkeeping (walked over)
   uint32_t doc_len = 0;
   const uint8_t *presence = nullptr;  // I64 / F64: doc_len bytes
-  const uint8_t *values = nullptr;    // I64 / F64: doc_len x 8 bytes (unaligned); Str: doc_len x u32 ords
-  std::vector<std::string> dict;      // Str
+  const uint8_t *values = nullptr;    // I64 / F64: doc_len x 8 bytes (unaligned); Str: doc_len x u32 ords;
+                                      // lists / nested: n_values x (8 | 4) bytes
+  std::vector<std::string> dict;      // Str / StrList / StrNested
+  // lists and nested columns: the values of doc d are values[list_offsets[d] .. list_offsets[d+1]).  A nested column
+  // (doc -> objects -> values) is flattened here: "any value of any object" (fastfields.rs:510-527, 597-610) is
+  // "any value of the doc" because the object offsets are running sums (write_field, fastfields.rs:939-965).
+  std::vector<uint32_t> list_offsets;  // doc_len + 1 entries
+  uint64_t n_values = 0;
+  int kind() const { return type <= 2 ? type : (type <= 8 ? 3 + (type - 3) % 3 : -1); }  // 0..2 scalar, 3..5 list forms
 };
 
 struct Cursor {
@@ -196,11 +204,15 @@ struct Cursor {
     return true;
   }
   // u32 array of `count` entries; returns its last element (0 when empty) — the writer's running offsets
-  bool offsets(uint64_t count, uint32_t &last) {
+  bool offsets(uint64_t count, uint32_t &last, std::vector<uint32_t> *keep = nullptr) {
     last = 0;
     if (count == 0) return true;
-    if (count * 4 > n - pos) return false;
+    if (count > (n - pos) / 4) return false;
     std::memcpy(&last, p + pos + (count - 1) * 4, 4);
+    if (keep) {
+      keep->resize(count);
+      std::memcpy(keep->data(), p + pos, count * 4);
+    }
     pos += count * 4;
     return true;
   }
@@ -244,6 +256,12 @@ inline bool parse_fast(const uint8_t *buf, uint64_t n, std::vector<FastColumn> &
       }
       return true;
     };
+    // running offsets: ascending and ending at `last` (every entry then indexes inside the values / the next table)
+    auto monotone = [](const std::vector<uint32_t> &o, uint32_t last_v) {
+      for (size_t i = 1; i < o.size(); i++)
+        if (o[i] < o[i - 1]) return false;
+      return o.empty() || o.back() == last_v;
+    };
     switch (col.type) {
       case 0:
       case 1:
@@ -259,22 +277,35 @@ inline bool parse_fast(const uint8_t *buf, uint64_t n, std::vector<FastColumn> &
         break;
       case 3:
       case 4:
-        if (!c.offsets(dl + 1, last) || !c.skip((uint64_t)last * 8)) return bad("a numeric list column");
+      case 5: {
+        if (col.type == 5 && !read_dict()) return bad("a keyword dictionary");
+        if (!c.offsets(dl + 1, last, &col.list_offsets)) return bad("a list column's offsets");
+        col.values = buf + c.pos;
+        col.n_values = last;
+        if (!c.skip((uint64_t)last * (col.type == 5 ? 4 : 8))) return bad("a list column");
+        if (!monotone(col.list_offsets, last)) {
+          err = "fast-field list column '" + col.name + "' has descending offsets";
+          return false;
+        }
         break;
-      case 5:
-        if (!read_dict() || !c.offsets(dl + 1, last) || !c.skip((uint64_t)last * 4)) return bad("a keyword list column");
-        col.dict.clear();
-        break;
+      }
       case 6:
       case 7:
-        if (!c.offsets(dl + 1, last) || !c.offsets((uint64_t)last + 1, last2) || !c.skip((uint64_t)last2 * 8))
-          return bad("a nested numeric column");
+      case 8: {
+        std::vector<uint32_t> doc_off, obj_off;
+        if (col.type == 8 && !read_dict()) return bad("a keyword dictionary");
+        if (!c.offsets(dl + 1, last, &doc_off) || !c.offsets((uint64_t)last + 1, last2, &obj_off)) return bad("a nested column's offsets");
+        col.values = buf + c.pos;
+        col.n_values = last2;
+        if (!c.skip((uint64_t)last2 * (col.type == 8 ? 4 : 8))) return bad("a nested column");
+        if (!monotone(doc_off, last) || !monotone(obj_off, last2)) {
+          err = "fast-field nested column '" + col.name + "' has descending offsets";
+          return false;
+        }
+        col.list_offsets.resize(doc_off.size());
+        for (size_t d = 0; d < doc_off.size(); d++) col.list_offsets[d] = obj_off[doc_off[d]];
         break;
-      case 8:
-        if (!read_dict() || !c.offsets(dl + 1, last) || !c.offsets((uint64_t)last + 1, last2) || !c.skip((uint64_t)last2 * 4))
-          return bad("a nested keyword column");
-        col.dict.clear();
-        break;
+      }
       case 9:
         if (!c.skip(dl * 4)) return bad("a nested count column");
         break;
