@@ -254,6 +254,8 @@ typedef struct {
   uint32_t has_length_column; /* `_len:<field>` is present in .fast */
   uint32_t n_fast_columns, n_scalar_columns;
   uint32_t crc_terms, crc_postings, crc_fast, crc_meta; /* crc32 of the images as given */
+  uint32_t n_list_columns;    /* list and nested value columns (types 3..8), loaded with "any value" semantics */
+  uint32_t reserved;
 } slg_segment_info_t;
 
 /* Host-only: parse + validate the files (checksums, crc of .terms, structure of .fast, .meta JSON) without
@@ -269,8 +271,10 @@ int32_t slg_inspect_segment_files(const slg_segment_files_t *files, const char *
  * are handed out per "field:token" key in order of first appearance across the loaded segments —
  * slg_term_lookup resolves a key; a segment that lacks a key treats it as an empty list
  * (seg.postings(key) == None, api/reader.rs:2986-2988).  avgdl is the .meta value, N/df/min_doc_len are
- * per segment as in the reference; postings are decoded on the device; scalar I64/F64/Str fast fields
- * become filter columns addressed by name (slg_column_lookup); list and nested columns are skipped.
+ * per segment as in the reference; postings are decoded on the device; I64/F64/Str fast fields, their list forms
+ * (I64List / F64List / StrList) and their nested forms (flattened: any value of any object) become filter columns
+ * addressed by name (slg_column_lookup); a predicate on a list column holds when ANY value of the doc satisfies it
+ * (index/fastfields.rs:490-657).
  * Positions stay resident for slg_phrase_compile unless option "keep_positions" is 0. */
 int32_t slg_load_segment_files(slg_index_t *, const slg_segment_files_t *files, const char *field, float k1, float b);
 /* The same for every segment of an index directory, in MANIFEST.json order (segment_ord = position).
@@ -302,6 +306,13 @@ int32_t slg_add_i64_column(slg_index_t *, uint32_t segment_ord, const int64_t *v
 int32_t slg_add_f64_column(slg_index_t *, uint32_t segment_ord, const double *values, const uint8_t *present);
 int32_t slg_add_str_column(slg_index_t *, uint32_t segment_ord, const char *const *dict, uint32_t n_dict,
                            const uint32_t *ords /* UINT32_MAX = missing */);
+/* list columns (I64List / F64List / StrList, index/fastfields.rs:926-940, 1045-1068): offsets[doc_count + 1] are running
+ * sums starting at 0, the values of doc d are values[offsets[d] .. offsets[d + 1]); a filter leaf on such a column holds
+ * when any value of the doc satisfies it (matches_keyword / matches_i64_range / ..., index/fastfields.rs:490-657) */
+int32_t slg_add_i64_list_column(slg_index_t *, uint32_t segment_ord, const uint32_t *offsets, const int64_t *values);
+int32_t slg_add_f64_list_column(slg_index_t *, uint32_t segment_ord, const uint32_t *offsets, const double *values);
+int32_t slg_add_str_list_column(slg_index_t *, uint32_t segment_ord, const char *const *dict, uint32_t n_dict,
+                                const uint32_t *offsets, const uint32_t *ords);
 /* segment statistics as the reference derives them (for the host shim and for tests) */
 int32_t slg_segment_stats(const slg_index_t *, uint32_t segment_ord, float *avgdl, float *live_docs,
                           float *min_doc_len, uint64_t *n_postings);

@@ -331,12 +331,20 @@ size_t decode_postings(const uint8_t *buf, size_t len, bool keep_positions, Deco
 /* ---------------------------------------------------------------- index */
 
 struct Column {
-  int kind;  // 0 i64, 1 f64, 2 str
+  int kind;  // 0 i64, 1 f64, 2 str; 3 i64 list, 4 f64 list, 5 str list (index/fastfields.rs: Column::I64List / F64List / StrList)
   std::vector<int64_t> i64;
   std::vector<double> f64;
   std::vector<uint8_t> present;
   std::vector<std::string> dict;
   std::vector<uint32_t> ords;
+  std::vector<uint32_t> offsets;  // list kinds: doc_count + 1 running sums
+  // doc_range, index/fastfields.rs:1136-1143
+  bool doc_range(uint32_t doc, size_t &start, size_t &end) const {
+    if (offsets.size() < (size_t)doc + 2) return false;
+    start = offsets[doc];
+    end = offsets[doc + 1];
+    return true;
+  }
 };
 
 }  // namespace
@@ -554,6 +562,17 @@ bool filter_eval(const slo_index *ix, uint32_t doc, const slo_filter_node_t *nod
   switch (nd.op) {
     case SLO_F_KEYWORD_EQ:
     case SLO_F_KEYWORD_IN: {
+      if (col && col->kind == 5) {  // matches_keyword / matches_keyword_in over Column::StrList: any value, fastfields.rs:497-509, 548-562
+        size_t s0, e0;
+        if (!col->doc_range(doc, s0, e0)) return false;
+        for (size_t i = s0; i < e0 && i < col->ords.size(); i++) {
+          uint32_t o = col->ords[i];
+          if (o >= col->dict.size()) continue;
+          for (uint32_t v = nd.value_begin; v < nd.value_end; v++)
+            if (case_insensitive_equals(col->dict[o], strings[v])) return true;
+        }
+        return false;
+      }
       if (!col || col->kind != 2 || doc >= col->ords.size()) return false;
       uint32_t o = col->ords[doc];
       if (o == 0xFFFFFFFFu || o >= col->dict.size()) return false;
@@ -562,11 +581,25 @@ bool filter_eval(const slo_index *ix, uint32_t doc, const slo_filter_node_t *nod
       return false;
     }
     case SLO_F_I64_RANGE: {
+      if (col && col->kind == 3) {  // Column::I64List, fastfields.rs:602-609
+        size_t s0, e0;
+        if (!col->doc_range(doc, s0, e0)) return false;
+        for (size_t i = s0; i < e0 && i < col->i64.size(); i++)
+          if (col->i64[i] >= nd.i_min && col->i64[i] <= nd.i_max) return true;
+        return false;
+      }
       if (!col || col->kind != 0 || doc >= col->i64.size() || !col->present[doc]) return false;
       int64_t v = col->i64[doc];
       return v >= nd.i_min && v <= nd.i_max;
     }
     case SLO_F_F64_RANGE: {
+      if (col && col->kind == 4) {  // Column::F64List, fastfields.rs:632-639
+        size_t s0, e0;
+        if (!col->doc_range(doc, s0, e0)) return false;
+        for (size_t i = s0; i < e0 && i < col->f64.size(); i++)
+          if (col->f64[i] >= nd.f_min && col->f64[i] <= nd.f_max) return true;
+        return false;
+      }
       if (!col || col->kind != 1 || doc >= col->f64.size() || !col->present[doc]) return false;
       double v = col->f64[doc];
       return v >= nd.f_min && v <= nd.f_max;
@@ -1113,6 +1146,33 @@ int32_t slo_index_add_str_column(slo_index_t *ix, const char *const *dict, uint3
   c.kind = 2;
   for (uint32_t i = 0; i < n_dict; i++) c.dict.emplace_back(dict[i]);
   c.ords.assign(ords, ords + ix->doc_count);
+  ix->columns.push_back(std::move(c));
+  return (int32_t)ix->columns.size() - 1;
+}
+
+int32_t slo_index_add_i64_list_column(slo_index_t *ix, const uint32_t *offsets, const int64_t *values) {
+  Column c;
+  c.kind = 3;
+  c.offsets.assign(offsets, offsets + ix->doc_count + 1);
+  c.i64.assign(values, values + c.offsets.back());
+  ix->columns.push_back(std::move(c));
+  return (int32_t)ix->columns.size() - 1;
+}
+int32_t slo_index_add_f64_list_column(slo_index_t *ix, const uint32_t *offsets, const double *values) {
+  Column c;
+  c.kind = 4;
+  c.offsets.assign(offsets, offsets + ix->doc_count + 1);
+  c.f64.assign(values, values + c.offsets.back());
+  ix->columns.push_back(std::move(c));
+  return (int32_t)ix->columns.size() - 1;
+}
+int32_t slo_index_add_str_list_column(slo_index_t *ix, const char *const *dict, uint32_t n_dict, const uint32_t *offsets,
+                                      const uint32_t *ords) {
+  Column c;
+  c.kind = 5;
+  for (uint32_t i = 0; i < n_dict; i++) c.dict.emplace_back(dict[i]);
+  c.offsets.assign(offsets, offsets + ix->doc_count + 1);
+  c.ords.assign(ords, ords + c.offsets.back());
   ix->columns.push_back(std::move(c));
   return (int32_t)ix->columns.size() - 1;
 }

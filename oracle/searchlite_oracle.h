@@ -157,6 +157,11 @@ int32_t slo_index_add_i64_column(slo_index_t *, const int64_t *values, const uin
 int32_t slo_index_add_f64_column(slo_index_t *, const double *values, const uint8_t *present);
 /* ords: UINT32_MAX = missing */
 int32_t slo_index_add_str_column(slo_index_t *, const char *const *dict, uint32_t n_dict, const uint32_t *ords);
+/* list columns (Column::I64List / F64List / StrList): offsets[doc_count + 1], "any value" semantics (fastfields.rs:490-657) */
+int32_t slo_index_add_i64_list_column(slo_index_t *, const uint32_t *offsets, const int64_t *values);
+int32_t slo_index_add_f64_list_column(slo_index_t *, const uint32_t *offsets, const double *values);
+int32_t slo_index_add_str_list_column(slo_index_t *, const char *const *dict, uint32_t n_dict, const uint32_t *offsets,
+                                      const uint32_t *ords);
 
 /* ---- search (api/reader.rs:2908-3128 search_segment + query/wand.rs:398-456) ----
  * k is the internal k (limit+1 semantics are the caller's).  block_size 0 => 128.

@@ -81,6 +81,9 @@ def lib() -> C.CDLL:
     L.slo_index_add_i64_column.argtypes = [vp, vp, vp]
     L.slo_index_add_f64_column.argtypes = [vp, vp, vp]
     L.slo_index_add_str_column.argtypes = [vp, C.POINTER(C.c_char_p), u32, vp]
+    L.slo_index_add_i64_list_column.argtypes = [vp, vp, vp]
+    L.slo_index_add_f64_list_column.argtypes = [vp, vp, vp]
+    L.slo_index_add_str_list_column.argtypes = [vp, C.POINTER(C.c_char_p), u32, vp, vp]
     L.slo_search.argtypes = [vp, vp, u32, C.c_int, u32, vp, u32, C.POINTER(C.c_char_p), C.c_int, vp, vp]
     L.slo_search.restype = i32
     L.slo_search_batch.argtypes = [vp, vp, u32, u32, C.c_int, u32, vp, u32, C.POINTER(C.c_char_p), C.c_int, C.c_int, vp, vp, vp]
@@ -141,6 +144,16 @@ class OracleIndex:
             o = np.ascontiguousarray(ords, dtype=np.uint32)
             arr = (C.c_char_p * len(dic))(*[s.encode() for s in dic])
             self.columns[name] = L.slo_index_add_str_column(self.h, arr, len(dic), _p(o))
+        for name, (offs, vals) in getattr(seg, "fast_i64_list", {}).items():
+            o, v = np.ascontiguousarray(offs, dtype=np.uint32), np.ascontiguousarray(vals, dtype=np.int64)
+            self.columns[name] = L.slo_index_add_i64_list_column(self.h, _p(o), _p(v))
+        for name, (offs, vals) in getattr(seg, "fast_f64_list", {}).items():
+            o, v = np.ascontiguousarray(offs, dtype=np.uint32), np.ascontiguousarray(vals, dtype=np.float64)
+            self.columns[name] = L.slo_index_add_f64_list_column(self.h, _p(o), _p(v))
+        for name, (dic, offs, ords) in getattr(seg, "fast_str_list", {}).items():
+            o, v = np.ascontiguousarray(offs, dtype=np.uint32), np.ascontiguousarray(ords, dtype=np.uint32)
+            arr = (C.c_char_p * len(dic))(*[s.encode() for s in dic])
+            self.columns[name] = L.slo_index_add_str_list_column(self.h, arr, len(dic), _p(o), _p(v))
         self._has_image = False
 
     def __del__(self):

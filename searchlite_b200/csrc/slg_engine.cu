@@ -693,7 +693,7 @@ bool parse_segment_files(const slg_segment_files_t *f, const char *field_spec, P
     return false;
   }
   for (auto &c : out.fast)
-    if (c.type <= 2 && c.doc_len != f->doc_count) {
+    if (c.kind() >= 0 && c.doc_len != f->doc_count) {
       err = "fast-field column '" + c.name + "' has " + std::to_string(c.doc_len) + " rows, the segment " + std::to_string(f->doc_count) + " docs";
       return false;
     }
@@ -753,6 +753,7 @@ int32_t slg_inspect_segment_files(const slg_segment_files_t *files, const char *
   out->has_length_column = ps.len_col[0] != nullptr;
   out->n_fast_columns = (uint32_t)ps.fast.size();
   for (auto &c : ps.fast) out->n_scalar_columns += c.type <= 2;
+  for (auto &c : ps.fast) out->n_list_columns += c.kind() >= 3;
   out->crc_terms = slgf::crc32_parallel(files->terms, files->terms_bytes);
   out->crc_postings = slgf::crc32_parallel(files->post, files->post_bytes);
   out->crc_fast = slgf::crc32_parallel(files->fast, files->fast_bytes);
@@ -840,14 +841,25 @@ int32_t slg_load_segment_files(slg_index_t *ix, const slg_segment_files_t *f, co
   // scalar fast-field columns, by name (the file's field order is HashMap order, index/fastfields.rs:414)
   Segment *s = ix->find(f->segment_ord);
   for (auto &c : ps.fast) {
-    if (c.type > 2 || c.name.compare(0, 5, "_len:") == 0) continue;
+    if (c.kind() < 0 || c.name.compare(0, 5, "_len:") == 0) continue;  // nested bookkeeping (types 9, 10) is not filterable
     size_t h = 0;
     while (h < ix->column_names.size() && ix->column_names[h] != c.name) h++;
     if (h == ix->column_names.size()) ix->column_names.push_back(c.name);
     if (s->columns.size() <= h) s->columns.resize(h + 1);
     Column col;
-    col.kind = c.type;
-    const size_t elem = c.type == 2 ? 4 : 8;
+    col.kind = c.kind();
+    const size_t elem = (col.kind == 2 || col.kind == 5) ? 4 : 8;
+    if (col.kind >= 3) {
+      // list and (flattened) nested columns: offsets + values, "any value" semantics in the filter kernel
+      col.n_values = c.n_values;
+      SLG_CUDA(ix, col.offsets.alloc(c.list_offsets.size() * 4));
+      SLG_CUDA(ix, cudaMemcpy(col.offsets.p, c.list_offsets.data(), c.list_offsets.size() * 4, cudaMemcpyHostToDevice));
+      SLG_CUDA(ix, col.values.alloc(std::max<size_t>((size_t)c.n_values * elem, 16)));
+      if (c.n_values) SLG_CUDA(ix, cudaMemcpy(col.values.p, c.values, (size_t)c.n_values * elem, cudaMemcpyHostToDevice));
+      col.dict = c.dict;
+      s->columns[h] = std::move(col);
+      continue;
+    }
     SLG_CUDA(ix, col.values.alloc(std::max<size_t>((size_t)s->doc_count * elem, 1)));
     SLG_CUDA(ix, cudaMemcpy(col.values.p, c.values, (size_t)s->doc_count * elem, cudaMemcpyHostToDevice));
     if (c.type != 2) {
@@ -1124,6 +1136,43 @@ int32_t slg_add_str_column(slg_index_t *ix, uint32_t segment_ord, const char *co
   return add_column(ix, segment_ord, 2, ords, 4, nullptr, dict, n_dict);
 }
 
+// list columns (I64List / F64List / StrList, index/fastfields.rs:926-940, 1000-1010, 1045-1068): offsets[doc_count + 1]
+// running sums, values[offsets[doc_count]]
+static int32_t add_list_column(slg_index *ix, uint32_t segment_ord, int kind, const uint32_t *offsets, const void *values, size_t elem,
+                               const char *const *dict, uint32_t n_dict) {
+  if (!ix || !offsets) return SLG_ERR_INVALID;
+  SLG_CUDA(ix, cudaSetDevice(ix->device));
+  Segment *s = ix->find(segment_ord);
+  if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
+  if (offsets[0] != 0) return fail(ix, SLG_ERR_INVALID, "list column offsets must start at 0");
+  for (uint32_t d = 0; d < s->doc_count; d++)
+    if (offsets[d + 1] < offsets[d]) return fail(ix, SLG_ERR_INVALID, "list column offsets descend at doc %u", d);
+  const uint64_t nv = offsets[s->doc_count];
+  if (nv && !values) return SLG_ERR_INVALID;
+  Column c;
+  c.kind = kind;
+  c.n_values = nv;
+  SLG_CUDA(ix, c.offsets.alloc(((size_t)s->doc_count + 1) * 4));
+  SLG_CUDA(ix, cudaMemcpy(c.offsets.p, offsets, ((size_t)s->doc_count + 1) * 4, cudaMemcpyHostToDevice));
+  SLG_CUDA(ix, c.values.alloc(std::max<size_t>(nv * elem, 16)));
+  if (nv) SLG_CUDA(ix, cudaMemcpy(c.values.p, values, nv * elem, cudaMemcpyHostToDevice));
+  for (uint32_t i = 0; i < n_dict; i++) c.dict.emplace_back(dict[i]);
+  s->columns.push_back(std::move(c));
+  return (int32_t)s->columns.size() - 1;
+}
+
+int32_t slg_add_i64_list_column(slg_index_t *ix, uint32_t segment_ord, const uint32_t *offsets, const int64_t *values) {
+  return add_list_column(ix, segment_ord, 3, offsets, values, 8, nullptr, 0);
+}
+int32_t slg_add_f64_list_column(slg_index_t *ix, uint32_t segment_ord, const uint32_t *offsets, const double *values) {
+  return add_list_column(ix, segment_ord, 4, offsets, values, 8, nullptr, 0);
+}
+int32_t slg_add_str_list_column(slg_index_t *ix, uint32_t segment_ord, const char *const *dict, uint32_t n_dict, const uint32_t *offsets,
+                                const uint32_t *ords) {
+  if (n_dict && !dict) return SLG_ERR_INVALID;
+  return add_list_column(ix, segment_ord, 5, offsets, ords, 4, dict, n_dict);
+}
+
 // index/fastfields.rs:475-481, ASCII path
 static bool ci_equals(const std::string &a, const std::string &b) {
   if (a.size() != b.size()) return false;
@@ -1173,18 +1222,21 @@ static int32_t compile_filter_for_segment(slg_index *ix, Segment *s, const Filte
     d.f_max = n.f_max;
     d.values = nullptr;
     d.present = nullptr;
+    d.offsets = nullptr;
     d.set_off = 0;
     d.set_words = 0;
     const Column *c = (n.column >= 0 && (size_t)n.column < s->columns.size()) ? &s->columns[n.column] : nullptr;
     bool leaf = n.op <= SLG_F_F64_RANGE;
     if (!leaf) continue;
     int want = (n.op == SLG_F_I64_RANGE) ? 0 : (n.op == SLG_F_F64_RANGE ? 1 : 2);
-    if (!c || c->kind != want) {
+    if (!c || (c->kind != want && c->kind != want + 3)) {
       d.op = FOP_FALSE;  // unknown field or wrong column type: predicate is false (fastfields.rs `_ => false`)
       continue;
     }
     d.values = c->values.p;
     d.present = c->present.as<uint8_t>();
+    d.offsets = c->offsets.as<uint32_t>();
+    if (c->kind == want + 3) d.op = want == 0 ? FOP_I64_LIST : (want == 1 ? FOP_F64_LIST : FOP_KEYWORD_LIST);  // "any value", fastfields.rs:497-509, 548-562, 602-609, 632-639
     if (want == 2) {
       uint32_t words = ((uint32_t)c->dict.size() + 31) / 32;
       d.set_off = (uint32_t)ordset.size();

@@ -91,9 +91,11 @@ struct CastU64 {
 };
 
 struct Column {
-  int kind = -1;  // 0 i64, 1 f64, 2 str; -1 = the segment lacks this column (predicates on it are false)
-  DevBuf values; // i64 / f64 / u32 ords
+  int kind = -1;  // 0 i64, 1 f64, 2 str, 3 i64 list, 4 f64 list, 5 str list; -1 = the segment lacks this column (predicates on it are false)
+  DevBuf values; // i64 / f64 / u32 ords: one per doc (scalar kinds) or n_values of them (list kinds)
   DevBuf present;
+  DevBuf offsets;  // list kinds: u32[doc_count + 1], the values of doc d are values[offsets[d] .. offsets[d + 1])
+  uint64_t n_values = 0;
   std::vector<std::string> dict;
 };
 

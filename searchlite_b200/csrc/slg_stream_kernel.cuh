@@ -63,7 +63,7 @@ struct StreamDev {
   uint32_t *col_count;   // [n_cols + 1] scratch of slg_colgroups_kernel
   uint32_t *sparse_counter, *col_counter;  // work counters of the two passes
   uint32_t stage_cap;    // postings a warp of the sparse pass can stage per span (multiple of 4)
-  unsigned long long *counters;  // [4] postings scattered / streamed from staging, (query, block) column tests, column blocks looked at per doc, items
+  unsigned long long *counters;  // [4] sparse postings visited, (query, column block) pairs looked at per doc, (query, column block) pairs streamed, sparse items
 };
 
 // ---- grouping of the batch's queries by their first column term (one CTA) ------------------------------------
@@ -643,8 +643,8 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_colgroups_kernel(Seg
     item = __shfl_sync(0xFFFFFFFFu, next_item, 0);
   }
   if (sd.counters && lane == 0) {
-    if (n_tests) atomicAdd(sd.counters + 1, n_tests);
-    if (n_looked) atomicAdd(sd.counters + 2, n_looked);
+    if (n_looked) atomicAdd(sd.counters + 1, n_looked);
+    if (n_tests) atomicAdd(sd.counters + 2, n_tests);
   }
 }
 

@@ -88,7 +88,7 @@ class SegmentInfo(C.Structure):
         ("n_terms_total", C.c_uint64), ("n_terms_field", C.c_uint64), ("n_postings", C.c_uint64), ("avgdl", C.c_float),
         ("has_positions", C.c_uint32), ("has_length_column", C.c_uint32), ("n_fast_columns", C.c_uint32),
         ("n_scalar_columns", C.c_uint32), ("crc_terms", C.c_uint32), ("crc_postings", C.c_uint32), ("crc_fast", C.c_uint32),
-        ("crc_meta", C.c_uint32),
+        ("crc_meta", C.c_uint32), ("n_list_columns", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -116,7 +116,7 @@ _LIB = None
 # every symbol include/searchlite_gpu.h declares
 EXPORTED_SYMBOLS = [
     "slg_open", "slg_close", "slg_last_error", "slg_configure", "slg_load_segment", "slg_load_segment_post_image",
-    "slg_add_i64_column", "slg_add_f64_column", "slg_add_str_column", "slg_segment_stats", "slg_filter_compile",
+    "slg_add_i64_column", "slg_add_f64_column", "slg_add_str_column", "slg_add_i64_list_column", "slg_add_f64_list_column", "slg_add_str_list_column", "slg_segment_stats", "slg_filter_compile",
     "slg_filter_bitmap", "slg_search_batch", "slg_batch_prepare", "slg_batch_run", "slg_batch_fetch",
     "slg_batch_device_results", "slg_batch_free", "slg_merge_gathered", "slg_load_vectors", "slg_rerank",
     "slg_get_counters", "slg_version", "slg_batch_copy_results_device", "slg_get_stream", "slg_selftest_div", "slg_batch_enable_stats",
@@ -153,6 +153,9 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_add_i64_column": [vp, u32, vp, vp],
         "slg_add_f64_column": [vp, u32, vp, vp],
         "slg_add_str_column": [vp, u32, C.POINTER(C.c_char_p), u32, vp],
+        "slg_add_i64_list_column": [vp, u32, vp, vp],
+        "slg_add_f64_list_column": [vp, u32, vp, vp],
+        "slg_add_str_list_column": [vp, u32, C.POINTER(C.c_char_p), u32, vp, vp],
         "slg_segment_stats": [vp, u32, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), C.POINTER(u64)],
         "slg_filter_compile": [vp, vp, u32, C.POINTER(C.c_char_p)],
         "slg_filter_bitmap": [vp, i32, u32, vp],
@@ -265,6 +268,10 @@ class SegmentData:
     fast_i64: dict = field(default_factory=dict)   # name -> (values int64, present u8|None)
     fast_f64: dict = field(default_factory=dict)
     fast_str: dict = field(default_factory=dict)   # name -> (dict list[str], ords u32)
+    # list columns (I64List / F64List / StrList, index/fastfields.rs:926-1068): offsets u32 [doc_count+1], values
+    fast_i64_list: dict = field(default_factory=dict)   # name -> (offsets, values int64)
+    fast_f64_list: dict = field(default_factory=dict)   # name -> (offsets, values float64)
+    fast_str_list: dict = field(default_factory=dict)   # name -> (dict list[str], offsets, ords u32)
 
     @property
     def n_terms(self) -> int:
@@ -279,7 +286,7 @@ class SegmentData:
         cv = lambda t: None if t is None else t.cpu().numpy()
         return SegmentData(self.segment_ord, self.doc_count, cv(self.term_offsets), cv(self.post_docs), cv(self.post_tfs),
                            cv(self.field_lengths), self.total_tokens, cv(self.field_length_present), self.deleted_docs,
-                           self.fast_i64, self.fast_f64, self.fast_str)
+                           self.fast_i64, self.fast_f64, self.fast_str, self.fast_i64_list, self.fast_f64_list, self.fast_str_list)
 
 
 @dataclass
@@ -706,6 +713,19 @@ class GpuIndex:
             ords = np.ascontiguousarray(ords, dtype=np.uint32)
             arr = (C.c_char_p * len(dic))(*[s.encode() for s in dic])
             handles[name] = self._check(self.lib.slg_add_str_column(self.handle, seg.segment_ord, arr, len(dic), _ptr(ords)))
+        for name, (offs, vals) in seg.fast_i64_list.items():
+            offs = np.ascontiguousarray(offs, dtype=np.uint32)
+            vals = np.ascontiguousarray(vals, dtype=np.int64)
+            handles[name] = self._check(self.lib.slg_add_i64_list_column(self.handle, seg.segment_ord, _ptr(offs), _ptr(vals)))
+        for name, (offs, vals) in seg.fast_f64_list.items():
+            offs = np.ascontiguousarray(offs, dtype=np.uint32)
+            vals = np.ascontiguousarray(vals, dtype=np.float64)
+            handles[name] = self._check(self.lib.slg_add_f64_list_column(self.handle, seg.segment_ord, _ptr(offs), _ptr(vals)))
+        for name, (dic, offs, ords) in seg.fast_str_list.items():
+            offs = np.ascontiguousarray(offs, dtype=np.uint32)
+            ords = np.ascontiguousarray(ords, dtype=np.uint32)
+            arr = (C.c_char_p * len(dic))(*[s.encode() for s in dic])
+            handles[name] = self._check(self.lib.slg_add_str_list_column(self.handle, seg.segment_ord, arr, len(dic), _ptr(offs), _ptr(ords)))
         return handles
 
     def segment_stats(self, segment_ord: int) -> dict:

@@ -77,6 +77,10 @@ class Segment:
                  i64s: Optional[Dict[str, List[Optional[int]]]] = None,
                  f64s: Optional[Dict[str, List[Optional[float]]]] = None,
                  i64_lists: Optional[Dict[str, List[List[int]]]] = None,
+                 f64_lists: Optional[Dict[str, List[List[float]]]] = None,
+                 keyword_lists: Optional[Dict[str, List[List[str]]]] = None,
+                 i64_nested: Optional[Dict[str, List[List[List[int]]]]] = None,
+                 keyword_nested: Optional[Dict[str, List[List[List[str]]]]] = None,
                  vectors: Optional[Dict[str, tuple]] = None,  # field -> (metric "cosine"|"l2", [vec or None per doc])
                  deleted: Sequence[int] = (), keep_positions: bool = True):
         self.id = seg_id
@@ -86,6 +90,10 @@ class Segment:
         self.i64s = i64s or {}
         self.f64s = f64s or {}
         self.i64_lists = i64_lists or {}
+        self.f64_lists = f64_lists or {}
+        self.keyword_lists = keyword_lists or {}
+        self.i64_nested = i64_nested or {}
+        self.keyword_nested = keyword_nested or {}
         self.vectors = vectors or {}
         self.deleted = list(deleted)
         self.keep_positions = keep_positions
@@ -158,12 +166,40 @@ class Segment:
                 sb = s.encode()
                 b += struct.pack("<I", len(sb)) + sb
             fields.append(b + b"".join(struct.pack("<I", o) for o in ords))
-        for name, lists in self.i64_lists.items():  # a column type the engine skips
+        def running(lists):
             offs = [0]
             for l in lists:
                 offs.append(offs[-1] + len(l))
-            fields.append(name_hdr(name, 3) + b"".join(struct.pack("<I", o) for o in offs) +
-                          b"".join(struct.pack("<q", v) for l in lists for v in l))
+            return b"".join(struct.pack("<I", o) for o in offs)
+
+        def dictionary(values):
+            dic: List[str] = []
+            for v in values:
+                if v not in dic:
+                    dic.append(v)
+            b = struct.pack("<I", len(dic))
+            for s in dic:
+                sb = s.encode()
+                b += struct.pack("<I", len(sb)) + sb
+            return dic, b
+
+        # write_field, index/fastfields.rs:926-1110: list columns are running offsets + values, nested columns doc -> object
+        # offsets, object -> value offsets, values
+        for name, lists in self.i64_lists.items():
+            fields.append(name_hdr(name, 3) + running(lists) + b"".join(struct.pack("<q", v) for l in lists for v in l))
+        for name, lists in self.f64_lists.items():
+            fields.append(name_hdr(name, 4) + running(lists) + b"".join(struct.pack("<d", v) for l in lists for v in l))
+        for name, lists in self.keyword_lists.items():
+            dic, db = dictionary([v for l in lists for v in l])
+            fields.append(name_hdr(name, 5) + db + running(lists) + b"".join(struct.pack("<I", dic.index(v)) for l in lists for v in l))
+        for name, docs in self.i64_nested.items():
+            objs = [o for d in docs for o in d]
+            fields.append(name_hdr(name, 6) + running(docs) + running(objs) + b"".join(struct.pack("<q", v) for o in objs for v in o))
+        for name, docs in self.keyword_nested.items():
+            objs = [o for d in docs for o in d]
+            dic, db = dictionary([v for o in objs for v in o])
+            fields.append(name_hdr(name, 8) + db + running(docs) + running(objs) +
+                          b"".join(struct.pack("<I", dic.index(v)) for o in objs for v in o))
         # HashMap order in the reference: any order; rotate so that `_len:` is not first
         fields = fields[1:] + fields[:1]
         return b"FFV1" + struct.pack("<I", len(fields)) + b"".join(fields)

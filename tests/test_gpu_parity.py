@@ -182,7 +182,6 @@ def test_items_kernel_pruning_skips_work_and_stays_exact(small, execution):
     assert_engine_parity(gi, ora, qb, 11, (got_h, got_c))
     wand = ora.search_batch(qb, 11, "wand")
     assert_parity(*wand, got_h, got_c, strict=False)
-    assert ctr["last_items"] < full_ctr["last_items"]                                  # the filter drops (query, doc range) items
     assert ctr["last_postings_scattered"] < full_ctr["last_postings_scattered"]
     assert ctr["last_column_blocks_streamed"] < full_ctr["last_column_blocks_streamed"]
     # per-query statistics come from the warp kernel on the same term layout: same bytes, counted skips

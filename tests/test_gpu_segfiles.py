@@ -37,7 +37,11 @@ def two_segments(seed=21, n0=1800, n1=1300, vocab=220):
                 v = rng.standard_normal(16).astype(np.float32)
                 vecs.append(v / np.linalg.norm(v))
         segs.append(sw.Segment(sid, docs, ["body", "title"], keywords={"lang": langs}, i64s={"year": years},
-                               i64_lists={"tags": [[1] * (i % 2) for i in range(n)]}, vectors={"emb": ("cosine", vecs)},
+                               i64_lists={"tags": [[i % 7, (i * 3) % 11][: i % 3] for i in range(n)]},
+                               keyword_lists={"labels": [["Red", "green", "BLUE", "red"][i % 2: i % 2 + i % 4] for i in range(n)]},
+                               i64_nested={"sizes": [[[(i + j) % 9, 40 + j][: 1 + (i + j) % 2] for j in range(i % 3)] for i in range(n)]},
+                               keyword_nested={"owners": [[["ann", "Bob"][: 1 + j] for j in range(i % 3)] for i in range(n)]},
+                               vectors={"emb": ("cosine", vecs)},
                                deleted=[5, 77, n - 1] if sid == "s1" else []))
     return segs
 
@@ -180,7 +184,25 @@ def test_file_columns_filter_like_the_oracle(index_dir):
     gi = GpuIndex(0, kernel="warp")
     gi.load_index_dir(root, "body")
     lang, year = gi.column_lookup("lang"), gi.column_lookup("year")
-    assert lang >= 0 and year >= 0 and gi.column_lookup("tags") == -1 and gi.column_lookup("_len:body") == -1
+    assert lang >= 0 and year >= 0 and gi.column_lookup("_len:body") == -1
+    # list and nested columns of the files: any value of the doc (index/fastfields.rs:490-657)
+    tagc, labc, sizc, ownc = (gi.column_lookup(x) for x in ("tags", "labels", "sizes", "owners"))
+    assert min(tagc, labc, sizc, ownc) >= 0
+    lnodes = np.zeros(1, dtype=FILTER_DTYPE)
+    checks = [
+        ((F_I64_RANGE, tagc, 5, 6, 0, 0, 0, 0, 0), [], lambda s, d: any(5 <= v <= 6 for v in s.i64_lists["tags"][d])),
+        ((F_KEYWORD_EQ, labc, 0, 0, 0, 0, 0, 0, 1), ["RED"], lambda s, d: any(v.lower() == "red" for v in s.keyword_lists["labels"][d])),
+        ((F_I64_RANGE, sizc, 40, 40, 0, 0, 0, 0, 0), [], lambda s, d: any(v == 40 for o in s.i64_nested["sizes"][d] for v in o)),
+        ((F_KEYWORD_EQ, ownc, 0, 0, 0, 0, 0, 0, 1), ["bob"], lambda s, d: any(v.lower() == "bob" for o in s.keyword_nested["owners"][d] for v in o)),
+    ]
+    for row, strings, want in checks:
+        lnodes[0] = row
+        lf = gi.compile_filter(lnodes, strings)
+        for i, s in enumerate(segs):
+            bm = gi.filter_bitmap(lf, i, len(s.docs))
+            got = [bool((bm[d >> 5] >> (d & 31)) & 1) for d in range(len(s.docs))]
+            exp = [want(s, d) for d in range(len(s.docs))]
+            assert got == exp and 0 < sum(exp) < len(exp), row
     nodes = np.zeros(3, dtype=FILTER_DTYPE)
     nodes[0] = (F_AND, -1, 0, 0, 0, 0, 2, 0, 0)
     nodes[1] = (F_KEYWORD_EQ, lang, 0, 0, 0, 0, 0, 0, 1)

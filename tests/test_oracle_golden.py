@@ -325,3 +325,41 @@ def test_vector_functions_match_golden(L):
     v = np.array([3.0, 4.0], dtype=np.float32)
     L.slo_normalize_in_place(v.ctypes.data, 2)
     assert v.tolist() == [np.float32(3.0) / np.float32(5.0), np.float32(4.0) / np.float32(5.0)]
+
+
+# ---- list fast-field columns: "any value" semantics, index/fastfields.rs:490-657 ---------------------------------
+def test_list_columns_match_any_value():
+    """matches_keyword / matches_keyword_in / matches_i64_range / matches_f64_range over StrList / I64List / F64List
+    columns restated directly (any value of the doc; a doc without values fails; Not inverts that) against the
+    oracle's filter evaluation"""
+    import numpy as np
+    from oracle import slo
+    from searchlite_b200.engine import FILTER_DTYPE
+    from tests.helpers import token_corpus
+    rng = np.random.default_rng(17)
+    n = 257
+    seg = token_corpus([[0]] * n, 1)
+    dic = ["Rust", "go", "ZIG", "c"]
+    tags = [[dic[j] for j in rng.choice(4, size=int(rng.integers(0, 4)), replace=False)] for _ in range(n)]
+    nums = [[int(v) for v in rng.integers(0, 50, size=int(rng.integers(0, 5)))] for _ in range(n)]
+    flts = [[float(v) for v in rng.random(int(rng.integers(0, 3)))] for _ in range(n)]
+
+    def offs(ls):
+        return np.cumsum([0] + [len(l) for l in ls]).astype(np.uint32)
+    seg.fast_str_list["tags"] = (dic, offs(tags), np.array([dic.index(v) for l in tags for v in l], dtype=np.uint32))
+    seg.fast_i64_list["nums"] = (offs(nums), np.array([v for l in nums for v in l], dtype=np.int64))
+    seg.fast_f64_list["flts"] = (offs(flts), np.array([v for l in flts for v in l], dtype=np.float64))
+    ora = slo.OracleIndex(seg)
+    c = ora.columns
+
+    def bits(nodes, strings=()):
+        bm = ora.filter_bitmap(np.array(nodes, dtype=FILTER_DTYPE), list(strings))
+        return [bool((bm[d >> 5] >> (d & 31)) & 1) for d in range(n)]
+    F_EQ, F_IN, F_I64, F_F64, F_AND, F_OR, F_NOT = range(7)
+    assert bits([(F_EQ, c["tags"], 0, 0, 0, 0, 0, 0, 1)], ["rust"]) == [any(v.lower() == "rust" for v in l) for l in tags]
+    assert bits([(F_IN, c["tags"], 0, 0, 0, 0, 0, 0, 2)], ["GO", "zig"]) == [any(v.lower() in ("go", "zig") for v in l) for l in tags]
+    assert bits([(F_I64, c["nums"], 10, 20, 0, 0, 0, 0, 0)]) == [any(10 <= v <= 20 for v in l) for l in nums]
+    assert bits([(F_F64, c["flts"], 0, 0, 0.25, 0.5, 0, 0, 0)]) == [any(0.25 <= v <= 0.5 for v in l) for l in flts]
+    assert bits([(F_NOT, -1, 0, 0, 0, 0, 1, 0, 0), (F_I64, c["nums"], 0, 100, 0, 0, 0, 0, 0)]) == [len(l) == 0 for l in nums]
+    # a numeric predicate on a keyword list (wrong column type) is false, as `_ => false`
+    assert not any(bits([(F_I64, c["tags"], 0, 100, 0, 0, 0, 0, 0)]))

@@ -28,7 +28,9 @@ def small_segment(seed: int = 3, n_docs: int = 300, vocab: int = 60):
     years = [None if i % 13 == 0 else 2000 + (i * 7) % 26 for i in range(n_docs)]
     return sw.Segment("a1", docs, ["body", "title"], keywords={"lang": langs}, i64s={"year": years},
                       f64s={"price": [float(i) * 0.5 for i in range(n_docs)]},
-                      i64_lists={"tags": [[i, i + 1][: i % 3] for i in range(n_docs)]})
+                      i64_lists={"tags": [[i, i + 1][: i % 3] for i in range(n_docs)]},
+                      keyword_lists={"labels": [["Red", "green", "BLUE"][: i % 4] for i in range(n_docs)]},
+                      i64_nested={"sizes": [[[i % 5, 9][: j + 1] for j in range(i % 3)] for i in range(n_docs)]})
 
 
 def files_of(seg):
@@ -48,7 +50,8 @@ def test_inspect_reports_what_the_writer_wrote():
     assert info["n_postings"] == sum(len(v) for v in body.values())
     assert f32_bits(info["avgdl"]) == f32_bits(np.float32(seg.avg_field_lengths()["body"]))
     assert info["has_positions"] == 1 and info["has_length_column"] == 1
-    assert info["n_fast_columns"] == 6 and info["n_scalar_columns"] == 5  # _len:body, _len:title, year, price, lang; tags skipped
+    assert info["n_fast_columns"] == 8 and info["n_scalar_columns"] == 5  # _len:body, _len:title, year, price, lang
+    assert info["n_list_columns"] == 3  # tags (I64List), labels (StrList), sizes (I64Nested)
     # crc32 == crc32fast (IEEE): util/checksum.rs:3-7
     assert [info["crc_terms"], info["crc_postings"], info["crc_fast"], info["crc_meta"]] == crcs
     other = inspect_segment_files(len(seg.docs), terms, post, fast, meta, "nosuchfield")
