@@ -278,8 +278,7 @@ struct slg_batch {
   slg::QHead *qheads = nullptr;
   uint2 *items = nullptr;
   slg::ColQ *colq = nullptr;          // exhaustive two-pass path: queries grouped by their first column, chunk list, scratch
-  slg::ColChunk *chunks = nullptr;
-  uint32_t *col_count = nullptr;
+  uint32_t *ucol = nullptr, *col_slot = nullptr;
   uint32_t max_cols = 0;
   uint8_t *done = nullptr;
   size_t done_bytes = 0;

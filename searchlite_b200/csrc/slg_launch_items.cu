@@ -10,6 +10,13 @@ cudaError_t go(K kern, size_t smem, int grid, cudaStream_t st, A... args) {
   kern<<<grid, kThreads, smem, st>>>(args...);
   return cudaGetLastError();
 }
+template <class K, class... A>
+cudaError_t go_n(K kern, int threads, size_t smem, int grid, cudaStream_t st, A... args) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, threads, smem, st>>>(args...);
+  return cudaGetLastError();
+}
 }  // namespace
 
 cudaError_t launch_score_items(bool prune, const SegmentDev &sd, const WarpBatchDev &wb, const ItemsDev &it, size_t smem, int grid,
@@ -22,9 +29,9 @@ cudaError_t launch_score_sparse(const SegmentDev &sd, const WarpBatchDev &wb, co
   slg_score_sparse_kernel<false><<<grid, kSparseWarps * 32, smem, st>>>(sd, wb, st_dev);
   return cudaGetLastError();
 }
-cudaError_t launch_score_colgroups(const SegmentDev &sd, const WarpBatchDev &wb, const StreamDev &st_dev, int grid, cudaStream_t st) {
-  slg_score_colgroups_kernel<false><<<grid, kColWarps * 32, 0, st>>>(sd, wb, st_dev);
-  return cudaGetLastError();
+cudaError_t launch_score_columns(bool prune, const SegmentDev &sd, const WarpBatchDev &wb, const StreamDev &st_dev, size_t smem, int grid, cudaStream_t st) {
+  return prune ? go_n(slg_score_columns_kernel<true>, kColWarps * 32, smem, grid, st, sd, wb, st_dev)
+               : go_n(slg_score_columns_kernel<false>, kColWarps * 32, smem, grid, st, sd, wb, st_dev);
 }
 cudaError_t launch_seed_items(const SegmentDev &sd, const WarpBatchDev &wb, const ItemsDev &it, size_t smem, int grid, cudaStream_t st) {
   return go(slg_seed_items_kernel<0>, smem, grid, st, sd, wb, it);

@@ -305,8 +305,8 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   const bool want_stream = bt->can_items && exec == SLG_EXEC_BM25 && ix->stream_kernels;
   for (auto &s : ix->segs) bt->max_cols = std::max(bt->max_cols, s->n_cols);
   const size_t o_colq = want_stream ? carve((size_t)n_queries * sizeof(ColQ)) : 0;
-  const size_t o_chunks = want_stream ? carve((size_t)n_queries * sizeof(ColChunk)) : 0;
-  const size_t o_colcount = want_stream ? carve((size_t)(bt->max_cols + 2) * 4) : 0;
+  const size_t o_ucol = want_stream ? carve((size_t)(bt->max_cols + 1) * 4) : 0;
+  const size_t o_colslot = want_stream ? carve((size_t)(bt->max_cols + 1) * 4) : 0;
   const size_t o_done = want_items ? carve(bt->done_bytes) : 0;
   bt->result_stride = align_up((size_t)n_queries * k * sizeof(HitDev) + (size_t)n_queries * 4, 256);
   const size_t o_results = carve(bt->result_stride * (S + (S > 1 ? 1 : 0)));
@@ -331,8 +331,8 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bt->items = want_items ? reinterpret_cast<uint2 *>(base + o_items) : nullptr;
   bt->done = want_items ? base + o_done : nullptr;
   bt->colq = want_stream ? reinterpret_cast<ColQ *>(base + o_colq) : nullptr;
-  bt->chunks = want_stream ? reinterpret_cast<ColChunk *>(base + o_chunks) : nullptr;
-  bt->col_count = want_stream ? reinterpret_cast<uint32_t *>(base + o_colcount) : nullptr;
+  bt->ucol = want_stream ? reinterpret_cast<uint32_t *>(base + o_ucol) : nullptr;
+  bt->col_slot = want_stream ? reinterpret_cast<uint32_t *>(base + o_colslot) : nullptr;
   bt->results = base + o_results;
 
   // ---- pinned staging: [pack | results | per-query stats + items counters] ----
@@ -548,9 +548,10 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
         // exhaustive: sparse pass (staged posting runs), then column pass (queries grouped by their first column)
         StreamDev sdv{};
         sdv.colq = bt->colq;
-        sdv.chunks = bt->chunks;
-        sdv.n_chunks = bt->work_counter + 3;
-        sdv.col_count = bt->col_count;
+        sdv.n_colq = bt->work_counter + 3;
+        sdv.ucol = bt->ucol;
+        sdv.n_ucol = bt->work_counter + 4;
+        sdv.col_slot = bt->col_slot;
         sdv.sparse_counter = bt->work_counter + 1;
         sdv.col_counter = bt->work_counter + 2;
         sdv.stage_cap = ix->stage_cap;
@@ -567,7 +568,14 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
           slg_colgroups_kernel<<<1, 1024, 0, st>>>(s->dev, wb, sdv, s->n_cols);
           count_launch(ix);
           SLG_CUDA(ix, cudaGetLastError());
-          SLG_CUDA(ix, launch_score_colgroups(s->dev, wb, sdv, ix->n_sm * 4, st));
+          // one CTA per SM: as many columns of a block resident in shared memory (double buffered) as fit
+          sdv.n_smax = std::min(s->n_cols, kColMaxSlots);
+          const size_t fixed = column_smem(0, sdv.n_smax);
+          const size_t budget = ix->smem_optin > fixed + 2048 ? ix->smem_optin - fixed - 2048 : 0;
+          sdv.col_resident = (uint32_t)std::min<size_t>(s->n_cols, budget / (2 * kColBlock * 4));
+          const size_t csmem = column_smem(sdv.col_resident, sdv.n_smax);
+          const uint32_t n_cblocks = (s->doc_count + kColBlock - 1) / kColBlock;
+          SLG_CUDA(ix, launch_score_columns(false, s->dev, wb, sdv, csmem, (int)std::min<uint32_t>((uint32_t)ix->n_sm, n_cblocks), st));
           count_launch(ix);
         }
         ix->ctr.score_launches++;

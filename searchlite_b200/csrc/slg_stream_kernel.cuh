@@ -13,16 +13,18 @@
 //                 and a partial that can still reach the query's k-th score completes its score with one 4-byte
 //                 gather per column term and is offered.  A query with a single sparse term needs no accumulator:
 //                 its staged scores are compared as they are.
-//   COLUMN PASS   slg_score_colgroups_kernel — terms with a doc-indexed f32 column (df >= N / dense_den).  Queries
-//                 are grouped by their first column term (slg_colgroups_kernel); a warp takes a (chunk of <= 32
-//                 queries of one group, range of 512-doc blocks) item and reads each block of the shared column
-//                 ONCE for the whole chunk, 16 docs per lane in registers.  A query whose only column is the shared
-//                 one sees v = c * w for every doc of the block, and max(v) = max(c) * w (f32 multiplication by a
-//                 positive weight is monotone), so its 512 comparisons against the k-th score collapse into one
-//                 against the block maximum taken from the streamed values; a query with further columns adds
-//                 their blocks in slot order first.  Only where a doc can enter the top k is the block looked at
-//                 per doc.  A doc that also sits in one of the query's sparse lists belongs to the sparse pass (its
-//                 partial is in A there) and is left alone here.
+//   COLUMN PASS   slg_score_columns_kernel — terms with a doc-indexed f32 column (df >= N / dense_den).  Doc-block
+//                 major: a CTA takes a block of kColBlock docs, brings that block of EVERY column the batch
+//                 names into shared memory with one bulk asynchronous copy per column (double buffered: the next
+//                 block lands while this one is scored) — each column block leaves HBM/L2 once per batch instead of
+//                 once per query — and then scores all the batch's queries that have a column term against it, 32
+//                 queries per warp step.  A query whose only column term is c sees v = c[d] * w for every doc of the
+//                 block, and max(v) = max(c) * w (f32 multiplication by a positive weight is monotone), so its
+//                 comparisons against the k-th score collapse into one against the block maximum the CTA took from
+//                 the values it has just read; a query with several columns sums their blocks per doc, slot order,
+//                 from shared memory.  Only where a doc can enter the top k is a block looked at per doc.  A doc
+//                 that also sits in one of the query's sparse lists belongs to the sparse pass (its partial is in A
+//                 there) and is left alone here.
 //
 // Every posting of every query term is read and takes part in the comparison that decides its doc; what is
 // shared is the READ of a column block between the queries that name the column, and what is skipped is only the
@@ -38,108 +40,83 @@
 
 namespace slg {
 
-constexpr uint32_t kColChunk = 32;       // queries per column-pass chunk: one per lane
-constexpr uint32_t kColItemBlocks = 8;   // 512-doc blocks per column-pass item
+constexpr uint32_t kColBlock = 256;      // docs per column-pass block (1 KB of every column)
 constexpr int kSparseWarps = 4;          // warps per CTA of the sparse pass
 constexpr int kColWarps = 8;             // warps per CTA of the column pass
+constexpr uint32_t kColMaxSlots = 4096;  // used columns whose block maximum is kept (beyond: always looked at per doc)
 
-struct __align__(16) ColQ {  // one query of a column group (32 B)
+struct __align__(16) ColQ {  // one query with >= 1 column term (32 B)
   uint32_t qslot, qi;
-  float w;             // weight of the group's column in this query
-  uint32_t ncol, nsp;  // column terms / sparse terms of the query (slots [0, nsp) sparse, [nsp, nsp + ncol) columns)
   int32_t filter;
-  uint64_t pad;
-};
-
-struct __align__(16) ColChunk {  // <= kColChunk queries that share their first column (16 B)
-  uint64_t sc_base;  // element offset of the column in seg.cols
-  uint32_t begin, count;
+  uint8_t nsp, ncol, unit_w, pad;  // slots [0, nsp) sparse, [nsp, nsp + ncol) columns; unit_w: every column weight is 1.0
+  uint16_t slot[8];                // used-column slots of the column terms, slot order
 };
 
 struct StreamDev {
-  ColQ *colq;            // [Q] queries with >= 1 column term, grouped by their first column
-  ColChunk *chunks;      // [<= Q]
-  uint32_t *n_chunks;    // device counter
-  uint32_t *col_count;   // [n_cols + 1] scratch of slg_colgroups_kernel
+  ColQ *colq;            // [Q] the batch's queries with >= 1 column term
+  uint32_t *n_colq;      // device counters
+  uint32_t *ucol;        // [n_cols] slot -> column (the columns the batch names, densest first)
+  uint32_t *n_ucol;
+  uint32_t *col_slot;    // [n_cols] column -> slot (scratch of slg_colgroups_kernel)
   uint32_t *sparse_counter, *col_counter;  // work counters of the two passes
   uint32_t stage_cap;    // postings a warp of the sparse pass can stage per span (multiple of 4)
-  unsigned long long *counters;  // [4] sparse postings visited, (query, column block) pairs looked at per doc, (query, column block) pairs streamed, sparse items
+  uint32_t col_resident; // columns of a block the column pass keeps in shared memory (per buffer)
+  uint32_t n_smax;       // block maxima kept in shared memory (min(columns of the segment, kColMaxSlots))
+  unsigned long long *counters;  // [4] sparse postings visited, (query, column block) pairs looked at per doc, (query, column block) pairs scored, sparse items
 };
 
-// ---- grouping of the batch's queries by their first column term (one CTA) ------------------------------------
+// ---- the batch's column terms: used columns -> slots, queries with a column term -> ColQ (one CTA) -------------
 static __global__ void __launch_bounds__(1024) slg_colgroups_kernel(SegmentDev seg, WarpBatchDev wb, StreamDev sd, uint32_t n_cols) {
-  __shared__ uint32_t s_total;
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-  for (uint32_t c = tid; c <= n_cols; c += nthr) sd.col_count[c] = 0u;
-  if (tid == 0) *sd.n_chunks = 0u;
-  __syncthreads();
-  // pass 1: histogram
-  for (uint32_t slot = tid; slot < wb.n_queries; slot += nthr) {
-    const QHead h = wb.qheads[slot];
-    for (uint32_t t = 0; t < h.nt; t++) {
-      const QTerm &q = wb.qterms[(uint64_t)slot * kWarpMaxTerms + t];
-      if ((q.flags & 5u) == 5u) {
-        atomicAdd(sd.col_count + (uint32_t)(q.sc_base / seg.col_stride), 1u);
-        break;
-      }
-    }
-  }
-  __syncthreads();
-  // exclusive scan (n_cols is small: tens to a few thousand) — thread 0, then the chunk list per column
+  for (uint32_t c = tid; c < n_cols; c += nthr) sd.col_slot[c] = 0u;
   if (tid == 0) {
-    uint32_t run = 0;
-    for (uint32_t c = 0; c < n_cols; c++) {
-      const uint32_t n = sd.col_count[c];
-      sd.col_count[c] = run;
-      run += n;
-    }
-    sd.col_count[n_cols] = run;
-    s_total = run;
+    *sd.n_colq = 0u;
+    *sd.n_ucol = 0u;
   }
   __syncthreads();
-  for (uint32_t c = tid; c < n_cols; c += nthr) {
-    const uint32_t b = sd.col_count[c], e = (c + 1 < n_cols) ? sd.col_count[c + 1] : s_total;
-    // (col_count[c + 1] is still the untouched prefix here: pass 2 below only advances entries it owns)
-    const uint32_t n = e - b;
-    if (n) {
-      const uint32_t nch = (n + kColChunk - 1) / kColChunk;
-      const uint32_t at = atomicAdd(sd.n_chunks, nch);
-      for (uint32_t i = 0; i < nch; i++) {
-        ColChunk ch;
-        ch.sc_base = (uint64_t)c * seg.col_stride;
-        ch.begin = b + i * kColChunk;
-        ch.count = min(kColChunk, n - i * kColChunk);
-        sd.chunks[at + i] = ch;
+  for (uint32_t slot = tid; slot < wb.n_queries; slot += nthr) {
+    const uint32_t nt = wb.qheads[slot].nt;
+    for (uint32_t t = 0; t < nt; t++) {
+      const QTerm &q = wb.qterms[(uint64_t)slot * kWarpMaxTerms + t];
+      if ((q.flags & 5u) == 5u) sd.col_slot[q.term] = 1u;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {  // slots in column order: column 0 is the densest term (n_cols is tens to a few thousand)
+    uint32_t n = 0;
+    for (uint32_t c = 0; c < n_cols; c++) {
+      if (sd.col_slot[c]) {
+        sd.ucol[n] = c;
+        sd.col_slot[c] = n++;
+      } else {
+        sd.col_slot[c] = 0xFFFFFFFFu;
       }
     }
+    *sd.n_ucol = n;
   }
   __syncthreads();
-  // pass 2: fill (the running prefix of a column doubles as its fill cursor; order inside a group is immaterial)
   for (uint32_t slot = tid; slot < wb.n_queries; slot += nthr) {
     const QHead h = wb.qheads[slot];
-    uint32_t nsp = 0, ncol = 0, first = 0xFFFFFFFFu;
+    ColQ r;
+    r.qslot = slot;
+    r.qi = h.qi;
+    r.filter = h.filter;
+    r.nsp = 0;
+    r.ncol = 0;
+    r.unit_w = 1;
+    r.pad = 0;
+    for (int i = 0; i < 8; i++) r.slot[i] = 0;
     for (uint32_t t = 0; t < h.nt; t++) {
       const QTerm &q = wb.qterms[(uint64_t)slot * kWarpMaxTerms + t];
       if (!(q.flags & 1u)) continue;
       if (q.flags & 4u) {
-        if (first == 0xFFFFFFFFu) first = t;
-        ncol++;
+        r.slot[r.ncol++] = (uint16_t)sd.col_slot[q.term];
+        if (q.weight != 1.0f) r.unit_w = 0;
       } else {
-        nsp++;
+        r.nsp++;
       }
     }
-    if (first == 0xFFFFFFFFu) continue;
-    const QTerm &q = wb.qterms[(uint64_t)slot * kWarpMaxTerms + first];
-    const uint32_t pos = atomicAdd(sd.col_count + (uint32_t)(q.sc_base / seg.col_stride), 1u);
-    ColQ r;
-    r.qslot = slot;
-    r.qi = h.qi;
-    r.w = q.weight;
-    r.ncol = ncol;
-    r.nsp = nsp;
-    r.filter = h.filter;
-    r.pad = 0;
-    sd.colq[pos] = r;
+    if (r.ncol) sd.colq[atomicAdd(sd.n_colq, 1u)] = r;
   }
 }
 
@@ -223,37 +200,101 @@ struct WarpCand {
 
 // shared memory of one warp of the sparse pass
 __host__ __device__ inline size_t sparse_smem_per_warp(uint32_t sub_docs, uint32_t stage_cap) {
-  // acc f32[sub_docs] | sdoc u32[cap] | ssc f32[cap] | cand u64[64] | qt QTerm[8] | rb u32[8][9] | ubs f32[8][8] | soff u32[8] | slo u32[8] | bar u64 (+ pad to 16)
+  // acc f32[sub_docs] | sdoc u32[cap] | ssc f32[cap] | cand u64[64] | qt QTerm[8] | rb u32[8][9] | runs u32[8][8] | rest f32[8] | soff u32[8] | slo u32[8] | bar u64 (+ pad)
   return (size_t)sub_docs * 4 + (size_t)stage_cap * 8 + kWarpCand * 8 + kWarpMaxTerms * sizeof(QTerm) + kWarpMaxTerms * kRbStride * 4 +
-         kWarpMaxTerms * 8 * 4 + kWarpMaxTerms * 4 * 2 + 16;
+         kSubPerGroup * kWarpMaxTerms * 4 + kSubPerGroup * 4 + kWarpMaxTerms * 4 * 2 + 16;
 }
 
-// scatter [i0, i1) of the staged (doc, score) stream into the accumulator
-template <bool FIRST>
-__device__ __forceinline__ void scatter_staged(const uint32_t *sdoc, const float *ssc, uint32_t i0, uint32_t i1, uint32_t tile_lo, float w,
-                                               float *acc, int lane, uint32_t &wmax) {
-  uint32_t i = i0 + lane;
+// One sub-tile of the sparse pass.  Lane t < nsp holds the run [r0, r1) of sparse term t inside the sub-tile: indices into the
+// staged stream (STAGED) or into the term's posting list in global memory (a sub-tile whose runs do not fit the staging area).
+template <bool STAGED>
+__device__ __forceinline__ void sparse_sub(const SegmentDev &seg, const WarpBatchDev &wb, const QHead &head, const QTerm *qt, const uint32_t r0,
+                                           const uint32_t r1, const uint32_t colmask, const float rest, const uint32_t tile_lo, float *acc,
+                                           const uint32_t *sdoc, const float *ssc, WarpCand &wc, const int lane) {
+  const uint32_t ne = __ballot_sync(0xFFFFFFFFu, r1 > r0);
+  if (!ne) return;
+  auto cut_now = [&]() {
+    if (wc.thr == kThrInit) return 0u;
+    const float cf = __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f - rest * 1.00002f;
+    return cf > 0.0f ? __float_as_uint(cf) : 0u;
+  };
+  // a doc of the sparse lists whose partial is v: add the column terms of exactly this doc, slot order
+  auto complete = [&](bool pass, uint32_t doc, float v) {
+    float s = v;
+    if (pass)
+      for (uint32_t cm = colmask; cm; cm &= cm - 1) {
+        const uint32_t ct = __ffs(cm) - 1;
+        const float c = __ldg(seg.cols + qt[ct].sc_base + doc);
+        s = __fadd_rn(s, __fmul_rn(c, qt[ct].weight));
+      }
+    wc.offer(seg, wb, head.qi, head.filter, pass, doc, s);
+  };
+  uint32_t cut = cut_now();
+  if ((ne & (ne - 1u)) == 0u) {
+    // one term has postings here: its contributions are the partials, nothing to accumulate
+    const uint32_t t = __ffs(ne) - 1;
+    const uint32_t i0 = __shfl_sync(0xFFFFFFFFu, r0, t), i1 = __shfl_sync(0xFFFFFFFFu, r1, t);
+    const float w = qt[t].weight;
+    const uint32_t *dp = STAGED ? sdoc : seg.post_doc + qt[t].base;
+    const float *sp = STAGED ? ssc : wb.scores + qt[t].base;
 #pragma unroll 1
-  for (; i + 32 < i1; i += 64) {  // two steps in flight
-    const uint32_t d0 = sdoc[i], d1 = sdoc[i + 32];
-    const float s0 = ssc[i], s1 = ssc[i + 32];
-    float v0 = __fmul_rn(s0, w), v1 = __fmul_rn(s1, w);
-    float *p0 = acc + (d0 - tile_lo), *p1 = acc + (d1 - tile_lo);
-    if (!FIRST) {
-      const float a0 = *p0, a1 = *p1;
-      v0 = __fadd_rn(a0, v0);
-      v1 = __fadd_rn(a1, v1);
+    for (uint32_t b = i0; b < i1; b += 32) {
+      const uint32_t i = b + lane;
+      const bool in = i < i1;
+      float v = 0.0f;
+      if (in) v = __fmul_rn(sp[i], w);
+      const bool pass = in && __float_as_uint(v) >= cut;
+      if (!__any_sync(0xFFFFFFFFu, pass)) continue;
+      const uint32_t doc = pass ? dp[i] : 0u;
+      complete(pass, doc, v);
+      cut = cut_now();
     }
-    *p0 = v0;
-    *p1 = v1;
-    wmax = max(wmax, max(__float_as_uint(v0), __float_as_uint(v1)));
+    return;
   }
-  if (i < i1) {
-    float v = __fmul_rn(ssc[i], w);
-    float *p = acc + (sdoc[i] - tile_lo);
-    if (!FIRST) v = __fadd_rn(*p, v);
-    *p = v;
-    wmax = max(wmax, __float_as_uint(v));
+  // ---- several terms: accumulate in slot order, then visit the same runs again: collect or just restore the zeros ----
+  uint32_t wmax = 0;
+  for (uint32_t m = ne; m; m &= m - 1) {
+    const uint32_t t = __ffs(m) - 1;
+    const uint32_t i0 = __shfl_sync(0xFFFFFFFFu, r0, t), i1 = __shfl_sync(0xFFFFFFFFu, r1, t);
+    const float w = qt[t].weight;
+    const uint32_t *dp = STAGED ? sdoc : seg.post_doc + qt[t].base;
+    const float *sp = STAGED ? ssc : wb.scores + qt[t].base;
+#pragma unroll 1
+    for (uint32_t i = i0 + lane; i < i1; i += 32) {
+      const uint32_t slot = dp[i] - tile_lo;
+      const float v = __fadd_rn(acc[slot], __fmul_rn(sp[i], w));  // distinct docs inside a list: no aliasing between lanes
+      acc[slot] = v;
+      wmax = max(wmax, __float_as_uint(v));
+    }
+    __syncwarp();
+  }
+  const bool collect = __reduce_max_sync(0xFFFFFFFFu, wmax) >= cut;
+  for (uint32_t m = ne; m; m &= m - 1) {
+    const uint32_t t = __ffs(m) - 1;
+    const uint32_t i0 = __shfl_sync(0xFFFFFFFFu, r0, t), i1 = __shfl_sync(0xFFFFFFFFu, r1, t);
+    const uint32_t *dp = STAGED ? sdoc : seg.post_doc + qt[t].base;
+    if (!collect) {
+#pragma unroll 1
+      for (uint32_t i = i0 + lane; i < i1; i += 32) acc[dp[i] - tile_lo] = 0.0f;
+    } else {
+#pragma unroll 1
+      for (uint32_t b = i0; b < i1; b += 32) {
+        const uint32_t i = b + lane;
+        const bool in = i < i1;
+        uint32_t slot = 0;
+        float v = 0.0f;
+        if (in) {
+          slot = dp[i] - tile_lo;
+          v = acc[slot];
+          acc[slot] = 0.0f;
+        }
+        const bool pass = in && __float_as_uint(v) >= cut && v != 0.0f;  // v == 0: an earlier run already took this doc
+        if (!__any_sync(0xFFFFFFFFu, pass)) continue;
+        complete(pass, tile_lo + slot, v);
+        cut = cut_now();
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -270,8 +311,9 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
   unsigned long long *cand = reinterpret_cast<unsigned long long *>(ssc + cap);
   QTerm *qt = reinterpret_cast<QTerm *>(cand + kWarpCand);
   uint32_t *rb = reinterpret_cast<uint32_t *>(qt + kWarpMaxTerms);
-  float *ubs = reinterpret_cast<float *>(rb + kWarpMaxTerms * kRbStride);
-  uint32_t *soff = reinterpret_cast<uint32_t *>(ubs + kWarpMaxTerms * 8);
+  uint32_t *runs = rb + kWarpMaxTerms * kRbStride;                                   // [jj][t] = i0 | i1 << 16, staged indices
+  float *rest = reinterpret_cast<float *>(runs + kSubPerGroup * kWarpMaxTerms);      // [jj] what the column terms can add
+  uint32_t *soff = reinterpret_cast<uint32_t *>(rest + kSubPerGroup);
   uint32_t *slo = soff + kWarpMaxTerms;
   unsigned long long *bar = reinterpret_cast<unsigned long long *>(slo + kWarpMaxTerms);
   for (uint32_t i = lane * 4; i < sub_docs; i += 128) *reinterpret_cast<float4 *>(acc + i) = make_float4(0, 0, 0, 0);
@@ -283,7 +325,8 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
   __syncwarp();
   uint32_t parity = 0;
   const uint32_t total_items = wb.n_groups * wb.n_queries;
-  unsigned long long n_post = 0;
+  uint32_t n_post = 0;  // per lane
+  unsigned long long n_post_total = 0;
   uint32_t n_items = 0;
   WarpCand wc;
 
@@ -299,153 +342,39 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
     if (lane < 16) reinterpret_cast<uint4 *>(qt)[lane] = __ldg(reinterpret_cast<const uint4 *>(wb.qterms + (uint64_t)qslot * kWarpMaxTerms) + lane);
     const unsigned long long thr0 = ld_cg_u64(wb.thr_key + head.qi);
     __syncwarp();
-    uint32_t myflags = lane < (int)nt ? qt[lane].flags : 0u;
-    const uint32_t spmask = __ballot_sync(0xFFFFFFFFu, (myflags & 5u) == 1u);
+    const uint32_t myflags = lane < (int)nt ? qt[lane].flags : 0u;
+    const uint32_t spmask = __ballot_sync(0xFFFFFFFFu, (myflags & 5u) == 1u);  // canonical layout: the low nsp slots
     const uint32_t colmask = __ballot_sync(0xFFFFFFFFu, (myflags & 5u) == 5u);
     if (spmask) {
       n_items++;
+      const uint32_t nsp = __popc(spmask);
       const uint32_t sub0 = tg * kSubPerGroup;
+      const uint32_t jmax = min(kSubPerGroup, wb.n_sub - sub0);
       {
-        // posting boundaries of the sparse terms (lane = t*4 + c) and, per column term, the exact column maximum
-        // inside each sub-tile (seg.col_tmax per 512 docs): what a scattered partial can still gain
+        // posting boundaries of the sparse terms: lane = t*4 + c
         const uint32_t t = lane >> 2, c = lane & 3;
-        if ((spmask >> t) & 1u) {
+        if (t < nsp) {
           const uint32_t *row = wb.rng + (uint64_t)qt[t].uterm * (wb.n_sub + 1);
           for (uint32_t j = c; j <= kSubPerGroup; j += 4) rb[t * kRbStride + j] = __ldg(row + min(sub0 + j, wb.n_sub));
-        } else if ((colmask >> t) & 1u) {
-          const float *tm = seg.col_tmax + (qt[t].sc_base / seg.col_stride) * seg.tmax_stride;
-          for (uint32_t j = c; j < kSubPerGroup; j += 4) {
-            float b = 0.0f;
-            const uint32_t d0 = (sub0 + j) * sub_docs;
-            if (sub0 + j < wb.n_sub) {
-              const uint32_t d1 = min(d0 + sub_docs, seg.doc_count) - 1u;
+        }
+        // what the column terms can add to a partial inside each sub-tile: their exact maxima per 512 docs (seg.col_tmax)
+        if (lane < (int)kSubPerGroup) {
+          float r = 0.0f;
+          if (lane < (int)jmax) {
+            const uint32_t d0 = (sub0 + lane) * sub_docs, d1 = min(d0 + sub_docs, seg.doc_count) - 1u;
+            for (uint32_t cm = colmask; cm; cm &= cm - 1) {
+              const uint32_t ct = __ffs(cm) - 1;
+              const float *tm = seg.col_tmax + (uint64_t)qt[ct].term * seg.tmax_stride;
+              float b = 0.0f;
               for (uint32_t blk = d0 >> 9; blk <= (d1 >> 9); blk++) b = fmaxf(b, __ldg(tm + blk));
+              r = __fadd_rn(r, __fmul_rn(b, qt[ct].weight));
             }
-            ubs[t * 8 + j] = __fmul_rn(b, qt[t].weight) ;
           }
+          rest[lane] = r;
         }
       }
       __syncwarp();
       wc.begin(cand, thr0, k, lane);
-      const uint32_t nsp = __popc(spmask);
-      const uint32_t jmax = min(kSubPerGroup, wb.n_sub - sub0);
-
-      // one sub-tile: scatter + walk from the staged stream (staged) or from global memory (a sub-tile whose runs do not fit)
-      auto process_sub = [&](const uint32_t j, const bool staged) {
-        const uint32_t tile_lo = (sub0 + j) * sub_docs;
-        // bound of what a partial lacks: the column terms inside this sub-tile
-        float rest = (lane < (int)nt && ((colmask >> lane) & 1u)) ? ubs[lane * 8 + j] : 0.0f;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) rest += __shfl_xor_sync(0xFFFFFFFFu, rest, o);
-        rest = __shfl_sync(0xFFFFFFFFu, rest, 0);
-        auto cut_now = [&]() {
-          if (wc.thr == kThrInit) return 0u;
-          const float cf = __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f - rest * 1.00002f;
-          return cf > 0.0f ? __float_as_uint(cf) : 0u;
-        };
-        // a doc of the sparse lists whose partial is v: add the column terms of exactly this doc, slot order
-        auto complete = [&](bool pass, uint32_t doc, float v) {
-          float s = v;
-          if (pass)
-            for (uint32_t cm = colmask; cm; cm &= cm - 1) {
-              const uint32_t ct = __ffs(cm) - 1;
-              const float c = __ldg(seg.cols + qt[ct].sc_base + doc);
-              s = __fadd_rn(s, __fmul_rn(c, qt[ct].weight));
-            }
-          wc.offer(seg, wb, head.qi, head.filter, pass, doc, s);
-        };
-        if (nsp == 1) {
-          // one sparse term: its contributions are the partials
-          const uint32_t t = __ffs(spmask) - 1;
-          const float w = qt[t].weight;
-          uint32_t i0 = rb[t * kRbStride + j], i1 = rb[t * kRbStride + j + 1];
-          if (i1 <= i0) return;
-          n_post += i1 - i0;
-          const uint32_t *dp;
-          const float *sp;
-          if (staged) {
-            const uint32_t sh = soff[t] - slo[t];
-            i0 += sh;
-            i1 += sh;
-            dp = sdoc;
-            sp = ssc;
-          } else {
-            dp = seg.post_doc + qt[t].base;
-            sp = wb.scores + qt[t].base;
-          }
-          uint32_t cut = cut_now();
-#pragma unroll 1
-          for (uint32_t i = i0; i < i1; i += 32) {
-            const bool in = i + lane < i1;
-            float v = 0.0f;
-            if (in) v = __fmul_rn(sp[i + lane], w);
-            const bool pass = in && __float_as_uint(v) >= cut;
-            if (!__any_sync(0xFFFFFFFFu, pass)) continue;
-            const uint32_t doc = pass ? dp[i + lane] : 0u;
-            complete(pass, doc, v);
-            cut = cut_now();
-          }
-          return;
-        }
-        // ---- several sparse terms: scatter in slot order, then walk the same runs ----
-        uint32_t wmax = 0;
-        bool first = true, any = false;
-        for (uint32_t m = spmask; m; m &= m - 1) {
-          const uint32_t t = __ffs(m) - 1;
-          uint32_t i0 = rb[t * kRbStride + j], i1 = rb[t * kRbStride + j + 1];
-          if (i1 <= i0) continue;
-          any = true;
-          n_post += i1 - i0;
-          const float w = qt[t].weight;
-          if (staged) {
-            const uint32_t sh = soff[t] - slo[t];
-            if (first) scatter_staged<true>(sdoc, ssc, i0 + sh, i1 + sh, tile_lo, w, acc, lane, wmax);
-            else scatter_staged<false>(sdoc, ssc, i0 + sh, i1 + sh, tile_lo, w, acc, lane, wmax);
-          } else {
-            const uint32_t *dptr = seg.post_doc + qt[t].base;
-            const float *sptr = wb.scores + qt[t].base;
-            if (first) accumulate_staged<true, false>(dptr, sptr, i0, i1, tile_lo, w, acc, lane, wmax);
-            else accumulate_staged<false, false>(dptr, sptr, i0, i1, tile_lo, w, acc, lane, wmax);
-          }
-          first = false;
-          __syncwarp();
-        }
-        if (!any) return;
-        uint32_t cut = cut_now();
-        const bool collect = __reduce_max_sync(0xFFFFFFFFu, wmax) >= cut;
-        for (uint32_t m = spmask; m; m &= m - 1) {
-          const uint32_t t = __ffs(m) - 1;
-          uint32_t i0 = rb[t * kRbStride + j], i1 = rb[t * kRbStride + j + 1];
-          if (i1 <= i0) continue;
-          const uint32_t *dp = seg.post_doc + qt[t].base;
-          if (staged) {
-            const uint32_t sh = soff[t] - slo[t];
-            i0 += sh;
-            i1 += sh;
-            dp = sdoc;
-          }
-#pragma unroll 1
-          for (uint32_t i = i0; i < i1; i += 32) {
-            const bool in = i + lane < i1;
-            uint32_t slot = 0;
-            if (in) slot = dp[i + lane] - tile_lo;
-            if (!collect) {
-              if (in) acc[slot] = 0.0f;
-              continue;
-            }
-            float v = 0.0f;
-            if (in) {
-              v = acc[slot];
-              acc[slot] = 0.0f;
-            }
-            const bool pass = in && __float_as_uint(v) >= cut && v != 0.0f;  // v == 0: an earlier run already took this doc
-            if (!__any_sync(0xFFFFFFFFu, pass)) continue;
-            complete(pass, tile_lo + slot, v);
-            cut = cut_now();
-          }
-          __syncwarp();
-        }
-      };
 
       uint32_t j0 = 0;
       while (j0 < jmax) {
@@ -453,14 +382,19 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
         uint32_t tot = 0;
         const uint32_t jc = j0 + 1 + lane;  // lanes 0..7 try j1 = j0+1 .. j0+8
         if (jc <= jmax)
-          for (uint32_t m = spmask; m; m &= m - 1) {
-            const uint32_t t = __ffs(m) - 1;
+          for (uint32_t t = 0; t < nsp; t++) {
             const uint32_t lo = rb[t * kRbStride + j0], hi = rb[t * kRbStride + jc];
             if (hi > lo) tot += ((hi + 3u) & ~3u) - (lo & ~3u);
           }
         const uint32_t fits = __ballot_sync(0xFFFFFFFFu, jc <= jmax && tot <= cap);
         if (!(fits & 1u)) {  // a single sub-tile does not fit: straight from global memory
-          process_sub(j0, false);
+          uint32_t r0 = 0, r1 = 0;
+          if (lane < (int)nsp) {
+            r0 = rb[lane * kRbStride + j0];
+            r1 = rb[lane * kRbStride + j0 + 1];
+            n_post += r1 - r0;
+          }
+          sparse_sub<false>(seg, wb, head, qt, r0, r1, colmask, rest[j0], (sub0 + j0) * sub_docs, acc, sdoc, ssc, wc, lane);
           j0++;
           continue;
         }
@@ -474,11 +408,12 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
         // ---- stage: lanes 0..7 lay the terms out, lanes 0..15 issue one bulk copy each (docs / scores per term) ----
         {
           uint32_t len = 0, lo_al = 0;
-          if (lane < (int)kWarpMaxTerms && ((spmask >> lane) & 1u)) {
+          if (lane < (int)nsp) {
             const uint32_t lo = rb[lane * kRbStride + j0], hi = rb[lane * kRbStride + j1];
             if (hi > lo) {
               lo_al = lo & ~3u;
               len = ((hi + 3u) & ~3u) - lo_al;
+              n_post += hi - lo;
             }
           }
           uint32_t off = len;  // inclusive scan over lanes 0..7
@@ -495,126 +430,210 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
           __syncwarp();  // every lane is done reading the staging area of the previous span
           if (lane == 0) mbar_arrive_expect_tx(bar, span_tot * 8u);
           __syncwarp();
-          const uint32_t t = lane >> 1;
-          const uint32_t tlen = __shfl_sync(0xFFFFFFFFu, len, t & 7), tlo = __shfl_sync(0xFFFFFFFFu, lo_al, t & 7),
-                         toff = __shfl_sync(0xFFFFFFFFu, off, t & 7);
+          const uint32_t t = (lane >> 1) & 7;
+          const uint32_t tlen = __shfl_sync(0xFFFFFFFFu, len, t), tlo = __shfl_sync(0xFFFFFFFFu, lo_al, t), toff = __shfl_sync(0xFFFFFFFFu, off, t);
           if (lane < 16 && tlen) {
             if (lane & 1) bulk_copy_g2s(ssc + toff, wb.scores + qt[t].base + tlo, tlen * 4u, bar);
             else bulk_copy_g2s(sdoc + toff, seg.post_doc + qt[t].base + tlo, tlen * 4u, bar);
           }
+          // run table of the span while the copies fly: entry e = jj*8 + t, two per lane
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const uint32_t e = lane + 32 * h, et = e & 7, ej = e >> 3;
+            uint32_t v = 0;
+            if (et < nsp && j0 + ej < j1) {
+              const uint32_t sh = soff[et] - slo[et];
+              v = (rb[et * kRbStride + j0 + ej] + sh) | ((rb[et * kRbStride + j0 + ej + 1] + sh) << 16);
+            }
+            runs[e] = v;
+          }
+          __syncwarp();
           mbar_wait(bar, parity);
           parity ^= 1u;
         }
-        for (uint32_t j = j0; j < j1; j++) process_sub(j, true);
+        for (uint32_t j = j0; j < j1; j++) {
+          const uint32_t r = lane < (int)kWarpMaxTerms ? runs[(j - j0) * kWarpMaxTerms + lane] : 0u;
+          sparse_sub<true>(seg, wb, head, qt, r & 0xFFFFu, r >> 16, colmask, rest[j], (sub0 + j) * sub_docs, acc, sdoc, ssc, wc, lane);
+        }
         j0 = j1;
       }
       wc.merge(wb, head.qi);
     }
+    if (n_post > 0x40000000u) {
+      n_post_total += n_post;
+      n_post = 0;
+    }
     item = __shfl_sync(0xFFFFFFFFu, next_item, 0);
   }
-  if (sd.counters && lane == 0) {
-    if (n_post) atomicAdd(sd.counters + 0, n_post);
-    if (n_items) atomicAdd(sd.counters + 3, (unsigned long long)n_items);
+  if (sd.counters) {
+    n_post_total += n_post;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_post_total += __shfl_xor_sync(0xFFFFFFFFu, n_post_total, o);
+    if (lane == 0) {
+      if (n_post_total) atomicAdd(sd.counters + 0, n_post_total);
+      if (n_items) atomicAdd(sd.counters + 3, (unsigned long long)n_items);
+    }
   }
 }
 
 // ---- column pass -----------------------------------------------------------------------------------------------
-template <bool UNUSED>
-__global__ void __launch_bounds__(kColWarps * 32) slg_score_colgroups_kernel(SegmentDev seg, WarpBatchDev wb, StreamDev sd) {
-  __shared__ __align__(16) unsigned long long s_cand[kColWarps][kWarpCand];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned long long *cand = s_cand[warp];
+// shared memory: buf f32[2][resident][kColBlock] | smax f32[n_smax] | cand u64[kColWarps][64] | bar u64[2]
+__host__ __device__ inline size_t column_smem(uint32_t resident, uint32_t n_smax) {
+  return (size_t)2 * resident * kColBlock * 4 + (((size_t)n_smax * 4 + 15) & ~(size_t)15) + (size_t)kColWarps * kWarpCand * 8 + 16;
+}
+
+template <bool PRUNE>
+__global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(SegmentDev seg, WarpBatchDev wb, StreamDev sd) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n_used = *sd.n_ucol, n_colq = *sd.n_colq;
+  const uint32_t resident = min(sd.col_resident, n_used), n_smax = min(n_used, sd.n_smax);
+  float *buf = reinterpret_cast<float *>(smem_raw);
+  float *smax = buf + (size_t)2 * sd.col_resident * kColBlock;
+  unsigned long long *cand = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(smax) + (((size_t)sd.n_smax * 4 + 15) & ~(size_t)15)) +
+                             (size_t)warp * kWarpCand;
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw + column_smem(sd.col_resident, sd.n_smax) - 16);
   const uint32_t k = wb.k;
-  const uint32_t n_chunks = *sd.n_chunks;
-  const uint32_t n_blocks = (seg.doc_count + 511u) >> 9;
-  const uint32_t n_ranges = (n_blocks + kColItemBlocks - 1) / kColItemBlocks;
-  const uint64_t total_items = (uint64_t)n_chunks * n_ranges;
+  const uint32_t n_blocks = (seg.doc_count + kColBlock - 1) / kColBlock;
+  if (n_colq == 0 || n_used == 0) return;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
   unsigned long long n_tests = 0, n_looked = 0;
   WarpCand wc;
-
-  uint32_t item = 0;
-  if (lane == 0) item = atomicAdd(sd.col_counter, 1u);
-  item = __shfl_sync(0xFFFFFFFFu, item, 0);
-  while (item < total_items) {
-    uint32_t next_item = 0;
-    if (lane == 0) next_item = atomicAdd(sd.col_counter, 1u);
-    const uint32_t r = item / n_chunks, ci = item - r * n_chunks;  // range-major: the chunks of a column meet in L2
-    const ColChunk ch = sd.chunks[ci];
-    ColQ cq;
-    cq.qslot = 0;
-    cq.qi = 0;
-    cq.w = 0.0f;
-    cq.ncol = 0;
-    cq.nsp = 0;
-    cq.filter = -1;
-    unsigned long long thr = ~0ull;
-    if (lane < (int)ch.count) {
-      cq = sd.colq[ch.begin + lane];
-      thr = ld_cg_u64(wb.thr_key + cq.qi);
+  // one bulk copy per resident column; the column stride keeps a whole block past doc_count in bounds and zero
+  auto fetch = [&](uint32_t blk, uint32_t b) {
+    if (warp == 0) {
+      if (lane == 0) mbar_arrive_expect_tx(bar + b, resident * kColBlock * 4u);
+      __syncwarp();
+      for (uint32_t s = lane; s < resident; s += 32)
+        bulk_copy_g2s(buf + ((size_t)b * sd.col_resident + s) * kColBlock, seg.cols + (uint64_t)sd.ucol[s] * seg.col_stride + (uint64_t)blk * kColBlock,
+                      kColBlock * 4u, bar + b);
     }
-    const float4 *col = reinterpret_cast<const float4 *>(seg.cols + ch.sc_base);
-#pragma unroll 1
-    for (uint32_t b = r * kColItemBlocks; b < min((r + 1) * kColItemBlocks, n_blocks); b++) {
-      const uint32_t d0 = b << 9;
-      float4 p[4];
-#pragma unroll
-      for (int x = 0; x < 4; x++) p[x] = __ldg(col + (d0 >> 2) + x * 32 + lane);
+  };
+  uint32_t parity[2] = {0u, 0u};
+  uint32_t blk = blockIdx.x;
+  if (blk < n_blocks) fetch(blk, 0);
+  uint32_t b = 0;
+  for (; blk < n_blocks; blk += gridDim.x, b ^= 1u) {
+    const uint32_t nxt = blk + gridDim.x;
+    if (nxt < n_blocks) fetch(nxt, b ^ 1u);  // the other buffer was released by the barrier that ended the previous block
+    mbar_wait(bar + b, parity[b]);
+    parity[b] ^= 1u;
+    const float *cb = buf + (size_t)b * sd.col_resident * kColBlock;
+    const uint32_t d0 = blk * kColBlock;
+    // block maximum of every used column (non-resident columns: from global memory)
+    for (uint32_t s = warp; s < n_smax; s += kColWarps) {
+      const float4 *p = s < resident ? reinterpret_cast<const float4 *>(cb + (size_t)s * kColBlock)
+                                     : reinterpret_cast<const float4 *>(seg.cols + (uint64_t)sd.ucol[s] * seg.col_stride + d0);
       uint32_t top = 0u;
 #pragma unroll
-      for (int x = 0; x < 4; x++)
-        top = max(top, max(max(__float_as_uint(p[x].x), __float_as_uint(p[x].y)), max(__float_as_uint(p[x].z), __float_as_uint(p[x].w))));
+      for (uint32_t x = 0; x < kColBlock / 128; x++) {
+        const float4 v = p[x * 32 + lane];
+        top = max(top, max(max(__float_as_uint(v.x), __float_as_uint(v.y)), max(__float_as_uint(v.z), __float_as_uint(v.w))));
+      }
       top = __reduce_max_sync(0xFFFFFFFFu, top);
-      if (top == 0u) continue;  // the column is empty here
-      // lane g = query g of the chunk.  One column: max over the block of c * w is max(c) * w.  More columns: the
-      // other columns only add, so the block is summed per doc below.
-      const uint32_t thr_bits = thr == kThrInit ? 0u : (uint32_t)(thr >> 32);
-      const bool live = lane < (int)ch.count;
-      const bool look = live && (cq.ncol > 1u || __float_as_uint(__fmul_rn(__uint_as_float(top), cq.w)) >= thr_bits);
-      n_tests += live ? 1u : 0u;
+      if (lane == 0) smax[s] = __uint_as_float(top);
+    }
+    __syncthreads();
+    // ---- every query with a column term against this block: lane g = one query ----
+    for (uint32_t c0 = warp * 32; c0 < n_colq; c0 += kColWarps * 32) {
+      ColQ cq;
+      cq.ncol = 0;
+      unsigned long long thr = ~0ull;
+      const bool live = c0 + lane < n_colq;
+      if (live) {
+        cq = sd.colq[c0 + lane];
+        thr = ld_cg_u64(wb.thr_key + cq.qi);
+      }
+      bool look = false;
+      if (live) {
+        n_tests++;
+        // one column: the maximum over the block of c * w is max(c) * w, the comparison of every doc collapses into one.
+        // Several columns: the exhaustive execution sums them per doc; a pruned one first asks the sum of the maxima
+        // (same slot order, every operation monotone: it dominates every doc's sum).
+        float bound = 0.0f;
+        bool known = true;
+        if (PRUNE || cq.ncol == 1)
+          for (uint32_t i = 0; i < cq.ncol; i++) {
+            const uint32_t s = cq.slot[i];
+            if (s >= n_smax) known = false;
+            else bound = __fadd_rn(bound, __fmul_rn(smax[s], cq.unit_w ? 1.0f : __ldg(&wb.qterms[(uint64_t)cq.qslot * kWarpMaxTerms + cq.nsp + i].weight)));
+          }
+        else known = false;
+        const uint32_t thr_bits = thr == kThrInit ? 0u : (uint32_t)(thr >> 32);
+        look = !known || (bound != 0.0f && __float_as_uint(bound) >= thr_bits);
+      }
       uint32_t hits = __ballot_sync(0xFFFFFFFFu, look);
       while (hits) {
         const int g = __ffs(hits) - 1;
         hits &= hits - 1;
         const uint32_t qslot = __shfl_sync(0xFFFFFFFFu, cq.qslot, g), qi = __shfl_sync(0xFFFFFFFFu, cq.qi, g);
-        const uint32_t ncol = __shfl_sync(0xFFFFFFFFu, cq.ncol, g), nsp = __shfl_sync(0xFFFFFFFFu, cq.nsp, g);
+        const uint32_t ncol = __shfl_sync(0xFFFFFFFFu, (uint32_t)cq.ncol, g), nsp = __shfl_sync(0xFFFFFFFFu, (uint32_t)cq.nsp, g);
+        const uint32_t unit_w = __shfl_sync(0xFFFFFFFFu, (uint32_t)cq.unit_w, g);
         const int32_t filter = __shfl_sync(0xFFFFFFFFu, cq.filter, g);
-        const float w = __shfl_sync(0xFFFFFFFFu, cq.w, g);
         const unsigned long long qthr = __shfl_sync(0xFFFFFFFFu, thr, g);
+        const uint32_t s01 = __shfl_sync(0xFFFFFFFFu, (uint32_t)cq.slot[0] | ((uint32_t)cq.slot[1] << 16), g);
+        const uint32_t s23 = __shfl_sync(0xFFFFFFFFu, (uint32_t)cq.slot[2] | ((uint32_t)cq.slot[3] << 16), g);
+        const uint32_t s45 = __shfl_sync(0xFFFFFFFFu, (uint32_t)cq.slot[4] | ((uint32_t)cq.slot[5] << 16), g);
+        const uint32_t s67 = __shfl_sync(0xFFFFFFFFu, (uint32_t)cq.slot[6] | ((uint32_t)cq.slot[7] << 16), g);
         const QTerm *qts = wb.qterms + (uint64_t)qslot * kWarpMaxTerms;
         n_looked++;
-        float4 v[4];
+        // v = sum of the query's columns over the block, slot order (the first product is the exact value of 0 + c * w)
+        float4 v[kColBlock / 128];
 #pragma unroll
-        for (int x = 0; x < 4; x++) v[x] = make_float4(__fmul_rn(p[x].x, w), __fmul_rn(p[x].y, w), __fmul_rn(p[x].z, w), __fmul_rn(p[x].w, w));
-        for (uint32_t t = nsp + 1; t < nsp + ncol; t++) {  // the query's further columns, slot order
-          const float4 *c2 = reinterpret_cast<const float4 *>(seg.cols + __ldg(&qts[t].sc_base)) + (d0 >> 2) + lane;
-          const float w2 = __ldg(&qts[t].weight);
-          float4 c[4];
+        for (uint32_t x = 0; x < kColBlock / 128; x++) v[x] = make_float4(0, 0, 0, 0);
+        for (uint32_t i = 0; i < ncol; i++) {
+          const uint32_t pair = i < 2 ? s01 : (i < 4 ? s23 : (i < 6 ? s45 : s67));
+          const uint32_t s = (i & 1u) ? pair >> 16 : pair & 0xFFFFu;
+          const float w = unit_w ? 1.0f : __ldg(&qts[nsp + i].weight);
+          const float4 *p = s < resident ? reinterpret_cast<const float4 *>(cb + (size_t)s * kColBlock)
+                                         : reinterpret_cast<const float4 *>(seg.cols + (uint64_t)sd.ucol[s] * seg.col_stride + d0);
 #pragma unroll
-          for (int x = 0; x < 4; x++) c[x] = __ldg(c2 + x * 32);
-#pragma unroll
-          for (int x = 0; x < 4; x++) {
-            v[x].x = __fadd_rn(v[x].x, __fmul_rn(c[x].x, w2));
-            v[x].y = __fadd_rn(v[x].y, __fmul_rn(c[x].y, w2));
-            v[x].z = __fadd_rn(v[x].z, __fmul_rn(c[x].z, w2));
-            v[x].w = __fadd_rn(v[x].w, __fmul_rn(c[x].w, w2));
+          for (uint32_t x = 0; x < kColBlock / 128; x++) {
+            const float4 c = p[x * 32 + lane];
+            v[x].x = __fadd_rn(v[x].x, __fmul_rn(c.x, w));
+            v[x].y = __fadd_rn(v[x].y, __fmul_rn(c.y, w));
+            v[x].z = __fadd_rn(v[x].z, __fmul_rn(c.z, w));
+            v[x].w = __fadd_rn(v[x].w, __fmul_rn(c.w, w));
           }
         }
         uint32_t cut = qthr == kThrInit ? 0u : (uint32_t)(qthr >> 32);
         uint32_t mx = 0u;
 #pragma unroll
-        for (int x = 0; x < 4; x++)
+        for (uint32_t x = 0; x < kColBlock / 128; x++)
           mx = max(mx, max(max(__float_as_uint(v[x].x), __float_as_uint(v[x].y)), max(__float_as_uint(v[x].z), __float_as_uint(v[x].w))));
         if (!__any_sync(0xFFFFFFFFu, mx >= cut && mx != 0u)) continue;
-        // ---- per doc: the docs that can enter the top k ----
+        // ---- per doc: the docs that can enter the top k, one per lane and round ----
         wc.begin(cand, qthr, k, lane);
-#pragma unroll 1
-        for (int x = 0; x < 4; x++) {
-          const uint32_t bits[4] = {__float_as_uint(v[x].x), __float_as_uint(v[x].y), __float_as_uint(v[x].z), __float_as_uint(v[x].w)};
+        uint32_t todo = 0u;
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const uint32_t doc = d0 + x * 128 + lane * 4 + e;
+        for (uint32_t x = 0; x < kColBlock / 128; x++) {
+          const uint32_t bx[4] = {__float_as_uint(v[x].x), __float_as_uint(v[x].y), __float_as_uint(v[x].z), __float_as_uint(v[x].w)};
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            if (bx[e] >= cut && bx[e] != 0u && d0 + x * 128 + lane * 4 + e < seg.doc_count) todo |= 1u << (x * 4 + e);
+        }
+        while (__any_sync(0xFFFFFFFFu, todo != 0u)) {
+          {
+            const uint32_t el = todo ? __ffs(todo) - 1 : 0u;
+            const bool had = todo != 0u;
+            todo &= todo - 1u;
+            uint32_t bits = 0u;
+#pragma unroll
+            for (uint32_t x = 0; x < kColBlock / 128; x++) {
+              if (el == x * 4 + 0) bits = __float_as_uint(v[x].x);
+              if (el == x * 4 + 1) bits = __float_as_uint(v[x].y);
+              if (el == x * 4 + 2) bits = __float_as_uint(v[x].z);
+              if (el == x * 4 + 3) bits = __float_as_uint(v[x].w);
+            }
+            const uint32_t doc = d0 + (el >> 2) * 128 + lane * 4 + (el & 3u);
             cut = wc.thr == kThrInit ? 0u : (uint32_t)(wc.thr >> 32);
-            bool pass = bits[e] >= cut && bits[e] != 0u && doc < seg.doc_count;
+            bool pass = had && bits >= cut;
             if (!__any_sync(0xFFFFFFFFu, pass)) continue;
             if (pass && nsp) {
               // a doc of one of the query's sparse lists belongs to the sparse pass
@@ -633,14 +652,13 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_colgroups_kernel(Seg
                 if (lo < end && __ldg(dp + lo) == doc) pass = false;
               }
             }
-            wc.offer(seg, wb, qi, filter, pass, doc, __uint_as_float(bits[e]));
+            wc.offer(seg, wb, qi, filter, pass, doc, __uint_as_float(bits));
           }
         }
         wc.merge(wb, qi);
-        if (lane == g) thr = max(thr, wc.thr);
       }
     }
-    item = __shfl_sync(0xFFFFFFFFu, next_item, 0);
+    __syncthreads();  // everyone is done with buffer b: the fetch two blocks ahead may overwrite it
   }
   if (sd.counters && lane == 0) {
     if (n_looked) atomicAdd(sd.counters + 1, n_looked);

@@ -39,7 +39,7 @@ constexpr uint32_t kWarpCand = 64;
 struct __align__(16) QTerm {  // one query term resolved against one segment (32 B)
   uint64_t base;      // term_start: first padded posting index
   uint64_t sc_base;   // element offset of the term's dense column in seg.cols, ~0 = the term has none
-  uint32_t term;      // term id in the segment
+  uint32_t term;      // term id in the segment (a term streamed from its column, flags bit2: the column index)
   uint32_t uterm;     // row of the range / bound tables
   float weight;
   uint32_t flags;     // bit0 scored, bit1 valid, bit2 streamed from its dense column (items kernel), bits 8..15 group, 16..19 leaf
@@ -109,7 +109,10 @@ static __global__ void slg_build_qterms_kernel(SegmentDev seg, BatchDev bt, QTer
       r.weight = bt.qt_weight[t0 + t];
       r.flags = (scored ? 1u : 0u) | 2u | ((uint32_t)bt.qt_group[t0 + t] << 8);
       if (bt.qt_leaf) r.flags |= (uint32_t)bt.qt_leaf[t0 + t] << 16;
-      if (has_col && use_cols) r.flags |= 4u;
+      if (has_col && use_cols) {
+        r.flags |= 4u;
+        r.term = (uint32_t)seg.term_col[term];  // streamed terms are addressed by their column, never by their term id
+      }
       qterms[(uint64_t)slot * kWarpMaxTerms + out++] = r;
     }
   }
