@@ -302,7 +302,7 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bt->items_cap = want_items ? max_groups * n_queries : 0;
   bt->done_bytes = want_items ? (size_t)max_groups * n_queries : 0;
   const size_t o_items = want_items ? carve((size_t)bt->items_cap * sizeof(uint2)) : 0;
-  const bool want_stream = bt->can_items && exec == SLG_EXEC_BM25 && ix->stream_kernels;
+  const bool want_stream = bt->can_items && exec == SLG_EXEC_BM25 && ix->stream_kernels && ix->sub_docs <= 2048;  // (posting numbers of a sub-tile fit 15 bits)
   for (auto &s : ix->segs) bt->max_cols = std::max(bt->max_cols, s->n_cols);
   const size_t o_colq = want_stream ? carve((size_t)n_queries * sizeof(ColQ)) : 0;
   const size_t o_ucol = want_stream ? carve((size_t)(bt->max_cols + 1) * 4) : 0;

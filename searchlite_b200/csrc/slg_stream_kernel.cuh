@@ -42,7 +42,7 @@ namespace slg {
 
 constexpr uint32_t kColBlock = 256;      // docs per column-pass block (1 KB of every column)
 constexpr int kSparseWarps = 4;          // warps per CTA of the sparse pass
-constexpr int kColWarps = 8;             // warps per CTA of the column pass
+constexpr int kColWarps = 16;            // warps per CTA of the column pass
 constexpr uint32_t kColMaxSlots = 4096;  // used columns whose block maximum is kept (beyond: always looked at per doc)
 
 struct __align__(16) ColQ {  // one query with >= 1 column term (32 B)
@@ -200,25 +200,40 @@ struct WarpCand {
 
 // shared memory of one warp of the sparse pass
 __host__ __device__ inline size_t sparse_smem_per_warp(uint32_t sub_docs, uint32_t stage_cap) {
-  // acc f32[sub_docs] | sdoc u32[cap] | ssc f32[cap] | cand u64[64] | qt QTerm[8] | rb u32[8][9] | runs u32[8][8] | rest f32[8] | soff u32[8] | slo u32[8] | bar u64 (+ pad)
-  return (size_t)sub_docs * 4 + (size_t)stage_cap * 8 + kWarpCand * 8 + kWarpMaxTerms * sizeof(QTerm) + kWarpMaxTerms * kRbStride * 4 +
-         kSubPerGroup * kWarpMaxTerms * 4 + kSubPerGroup * 4 + kWarpMaxTerms * 4 * 2 + 16;
+  // own u16[sub_docs] | sdoc u32[cap] | ssc f32[cap] | cand u64[64] | qt QTerm[8] | rb u32[8][9] | cum u32[65 (+3)] | rest f32[8] | pend u32[64] | bar u64 (+ pad)
+  return (((size_t)sub_docs * 2 + 15) & ~(size_t)15) + (size_t)stage_cap * 8 + kWarpCand * 8 + kWarpMaxTerms * sizeof(QTerm) +
+         kWarpMaxTerms * kRbStride * 4 + 68 * 4 + kSubPerGroup * 4 + 64 * 4 + 16;
 }
 
-// One sub-tile of the sparse pass.  Lane t < nsp holds the run [r0, r1) of sparse term t inside the sub-tile: indices into the
-// staged stream (STAGED) or into the term's posting list in global memory (a sub-tile whose runs do not fit the staging area).
+constexpr uint32_t kOwnFlag = 0x8000u;  // own[slot]: index of the posting that owns the doc | this flag when other lists hold it too
+
+// One sub-tile of the sparse pass, posting-parallel over ALL the query's sparse terms at once.
+//
+// The postings of the sub-tile are numbered p = 0 .. P-1, term after term (slot order).  Accumulating per doc needs
+// no float read-modify-write — and therefore no term-by-term ordering of the shared-memory traffic — because a doc
+// that sits in ONE of the query's sparse lists (the usual case: the lists are sparse) has a one-term sum:
+//   L1  every posting writes its number into own[doc - tile_lo]: some posting of the doc ends up owning the slot
+//   L2  every posting reads the slot back; one that finds another number there sets the flag: the doc has several postings
+//   L3  the owner of an unflagged slot offers its own contribution (the doc's exact sparse sum); the owner of a flagged
+//       slot is parked and later sums the doc over all terms, slot order, finding it in the other terms' runs by
+//       binary search (runs are sorted by doc)
+// own[] needs no clearing: every slot read in L2/L3 was written in L1 of the same sub-tile.
+// STAGED: postings [P0, P1) of the staged stream, cells (term runs, rounded out to 16 bytes) back to back, cell t at
+// cb[t] - base .. cb[t+1] - base; postings outside the sub-tile's doc range (the rounding) fail the range test.
+// Not staged (a sub-tile whose runs do not fit the staging area): the same three loops straight from global memory.
 template <bool STAGED>
-__device__ __forceinline__ void sparse_sub(const SegmentDev &seg, const WarpBatchDev &wb, const QHead &head, const QTerm *qt, const uint32_t r0,
-                                           const uint32_t r1, const uint32_t colmask, const float rest, const uint32_t tile_lo, float *acc,
-                                           const uint32_t *sdoc, const float *ssc, WarpCand &wc, const int lane) {
-  const uint32_t ne = __ballot_sync(0xFFFFFFFFu, r1 > r0);
-  if (!ne) return;
+__device__ __forceinline__ void sparse_sub(const SegmentDev &seg, const WarpBatchDev &wb, const QHead &head, const QTerm *qt, const uint32_t *rbj,
+                                           const uint32_t *cb, const uint32_t base, const uint32_t nsp, const uint32_t colmask, const bool unit_w, const float rest,
+                                           const uint32_t tile_lo, const uint32_t sub_docs, unsigned short *own, const uint32_t *sdoc,
+                                           const float *ssc, uint32_t *pend, WarpCand &wc, const int lane) {
+  // run of term t: STAGED staged indices [cb[t], cb[t+1]); else postings [rbj[t*9], rbj[t*9+1]) of the term's list,
+  // numbered from the sum of the earlier runs' lengths
   auto cut_now = [&]() {
     if (wc.thr == kThrInit) return 0u;
     const float cf = __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f - rest * 1.00002f;
     return cf > 0.0f ? __float_as_uint(cf) : 0u;
   };
-  // a doc of the sparse lists whose partial is v: add the column terms of exactly this doc, slot order
+  // a doc whose sparse sum is v: add the column terms of exactly this doc, slot order
   auto complete = [&](bool pass, uint32_t doc, float v) {
     float s = v;
     if (pass)
@@ -229,73 +244,178 @@ __device__ __forceinline__ void sparse_sub(const SegmentDev &seg, const WarpBatc
       }
     wc.offer(seg, wb, head.qi, head.filter, pass, doc, s);
   };
-  uint32_t cut = cut_now();
-  if ((ne & (ne - 1u)) == 0u) {
-    // one term has postings here: its contributions are the partials, nothing to accumulate
-    const uint32_t t = __ffs(ne) - 1;
-    const uint32_t i0 = __shfl_sync(0xFFFFFFFFu, r0, t), i1 = __shfl_sync(0xFFFFFFFFu, r1, t);
-    const float w = qt[t].weight;
-    const uint32_t *dp = STAGED ? sdoc : seg.post_doc + qt[t].base;
-    const float *sp = STAGED ? ssc : wb.scores + qt[t].base;
-#pragma unroll 1
-    for (uint32_t b = i0; b < i1; b += 32) {
-      const uint32_t i = b + lane;
-      const bool in = i < i1;
-      float v = 0.0f;
-      if (in) v = __fmul_rn(sp[i], w);
-      const bool pass = in && __float_as_uint(v) >= cut;
-      if (!__any_sync(0xFFFFFFFFu, pass)) continue;
-      const uint32_t doc = pass ? dp[i] : 0u;
-      complete(pass, doc, v);
-      cut = cut_now();
+  uint32_t npend = 0;
+  // parked owners of docs with several postings: pend[] holds (slot << 16 | p), resolved 32 at a time
+  auto resolve = [&](uint32_t n) {
+    const bool have = lane < (int)n;
+    const uint32_t e = have ? pend[lane] : 0u;
+    const uint32_t slot = e >> 16, pp = e & 0xFFFFu, doc = tile_lo + slot;
+    float s = 0.0f;
+    if (have) {
+      uint32_t start = 0;  // not staged: number of the first posting of term t
+      for (uint32_t t = 0; t < nsp; t++) {
+        uint32_t lo, hi;
+        const uint32_t *dp;
+        const float *sp;
+        bool mine;
+        uint32_t at = 0;
+        if (STAGED) {
+          lo = cb[t] - base;
+          hi = cb[t + 1] - base;
+          dp = sdoc;
+          sp = ssc;
+          mine = pp >= lo && pp < hi;
+          at = pp;
+        } else {
+          lo = rbj[t * kRbStride];
+          hi = rbj[t * kRbStride + 1];
+          dp = seg.post_doc + qt[t].base;
+          sp = wb.scores + qt[t].base;
+          mine = pp >= start && pp < start + (hi - lo);
+          at = lo + (pp - start);
+          start += hi - lo;
+        }
+        float c = 0.0f;
+        if (mine) {
+          c = sp[at];
+        } else {
+          const uint32_t end = hi;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (dp[mid] < doc) lo = mid + 1;
+            else hi = mid;
+          }
+          if (lo < end && dp[lo] == doc) c = sp[lo];
+        }
+        if (c != 0.0f) s = __fadd_rn(s, __fmul_rn(c, qt[t].weight));  // (a sum that starts at +0 and skips absent terms: brute_force on the doc's lists)
+      }
     }
-    return;
-  }
-  // ---- several terms: accumulate in slot order, then visit the same runs again: collect or just restore the zeros ----
-  uint32_t wmax = 0;
-  for (uint32_t m = ne; m; m &= m - 1) {
-    const uint32_t t = __ffs(m) - 1;
-    const uint32_t i0 = __shfl_sync(0xFFFFFFFFu, r0, t), i1 = __shfl_sync(0xFFFFFFFFu, r1, t);
-    const float w = qt[t].weight;
-    const uint32_t *dp = STAGED ? sdoc : seg.post_doc + qt[t].base;
-    const float *sp = STAGED ? ssc : wb.scores + qt[t].base;
+    const bool pass = have && __float_as_uint(s) >= cut_now();
+    if (__any_sync(0xFFFFFFFFu, pass)) complete(pass, doc, s);
+  };
+  auto park = [&](bool conf, uint32_t slot, uint32_t pp) {
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, conf);
+    if (!bal) return;
+    if (conf) pend[npend + __popc(bal & ((1u << lane) - 1u))] = (slot << 16) | pp;
+    npend += __popc(bal);
+    __syncwarp();
+    if (npend >= 32u) {
+      resolve(32u);
+      __syncwarp();
+      if (lane < (int)(npend - 32u)) {
+        const uint32_t x = pend[32 + lane];
+        pend[lane] = x;
+      }
+      npend -= 32u;
+      __syncwarp();
+    }
+  };
+  // the weight of posting number pp (only when some weight differs from 1)
+  auto weight_of = [&](uint32_t pp) {
+    uint32_t t = 0, start = 0;
+    for (uint32_t u = 0; u + 1 < nsp; u++) {
+      const uint32_t end = STAGED ? cb[u + 1] - base : start + (rbj[u * kRbStride + 1] - rbj[u * kRbStride]);
+      if (pp >= end) t = u + 1;
+      start = end;
+    }
+    return qt[t].weight;
+  };
+
+  if (STAGED) {
+    const uint32_t P0 = cb[0] - base, P1 = cb[nsp] - base;  // staged indices relative to the span (< stage_cap <= 8192)
+    if (P1 <= P0) return;
 #pragma unroll 1
-    for (uint32_t i = i0 + lane; i < i1; i += 32) {
-      const uint32_t slot = dp[i] - tile_lo;
-      const float v = __fadd_rn(acc[slot], __fmul_rn(sp[i], w));  // distinct docs inside a list: no aliasing between lanes
-      acc[slot] = v;
-      wmax = max(wmax, __float_as_uint(v));
+    for (uint32_t p = P0 + lane; p < P1; p += 32) {
+      const uint32_t slot = sdoc[p] - tile_lo;
+      if (slot < sub_docs) own[slot] = (unsigned short)p;
     }
     __syncwarp();
-  }
-  const bool collect = __reduce_max_sync(0xFFFFFFFFu, wmax) >= cut;
-  for (uint32_t m = ne; m; m &= m - 1) {
-    const uint32_t t = __ffs(m) - 1;
-    const uint32_t i0 = __shfl_sync(0xFFFFFFFFu, r0, t), i1 = __shfl_sync(0xFFFFFFFFu, r1, t);
-    const uint32_t *dp = STAGED ? sdoc : seg.post_doc + qt[t].base;
-    if (!collect) {
 #pragma unroll 1
-      for (uint32_t i = i0 + lane; i < i1; i += 32) acc[dp[i] - tile_lo] = 0.0f;
-    } else {
-#pragma unroll 1
-      for (uint32_t b = i0; b < i1; b += 32) {
-        const uint32_t i = b + lane;
-        const bool in = i < i1;
-        uint32_t slot = 0;
-        float v = 0.0f;
-        if (in) {
-          slot = dp[i] - tile_lo;
-          v = acc[slot];
-          acc[slot] = 0.0f;
-        }
-        const bool pass = in && __float_as_uint(v) >= cut && v != 0.0f;  // v == 0: an earlier run already took this doc
-        if (!__any_sync(0xFFFFFFFFu, pass)) continue;
-        complete(pass, tile_lo + slot, v);
-        cut = cut_now();
+    for (uint32_t p = P0 + lane; p < P1; p += 32) {
+      const uint32_t slot = sdoc[p] - tile_lo;
+      if (slot < sub_docs) {
+        const uint32_t o = own[slot];
+        if ((o & (kOwnFlag - 1u)) != p) own[slot] = (unsigned short)(o | kOwnFlag);
       }
     }
     __syncwarp();
+    uint32_t cut = cut_now();
+#pragma unroll 1
+    for (uint32_t b = P0; b < P1; b += 32) {
+      const uint32_t p = b + lane;
+      uint32_t slot = 0xFFFFFFFFu;
+      if (p < P1) slot = sdoc[p] - tile_lo;
+      uint32_t o = 0xFFFFFFFFu;
+      if (slot < sub_docs) o = own[slot];
+      const bool mine = (o & (kOwnFlag - 1u)) == p && o != 0xFFFFFFFFu;
+      const bool conf = mine && (o & kOwnFlag);
+      float v = 0.0f;
+      if (mine && !conf) {
+        v = ssc[p];
+        if (!unit_w) v = __fmul_rn(v, weight_of(p));
+      }
+      const bool pass = mine && !conf && __float_as_uint(v) >= cut;
+      if (__any_sync(0xFFFFFFFFu, pass)) {
+        complete(pass, tile_lo + slot, v);
+        cut = cut_now();
+      }
+      park(conf, slot, p);
+    }
+  } else {
+    uint32_t start = 0;
+    for (uint32_t t = 0; t < nsp; t++) {
+      const uint32_t lo = rbj[t * kRbStride], hi = rbj[t * kRbStride + 1];
+      const uint32_t *dp = seg.post_doc + qt[t].base;
+#pragma unroll 1
+      for (uint32_t i = lo + lane; i < hi; i += 32) own[dp[i] - tile_lo] = (unsigned short)(start + (i - lo));
+      start += hi - lo;
+    }
+    __syncwarp();
+    start = 0;
+    for (uint32_t t = 0; t < nsp; t++) {
+      const uint32_t lo = rbj[t * kRbStride], hi = rbj[t * kRbStride + 1];
+      const uint32_t *dp = seg.post_doc + qt[t].base;
+#pragma unroll 1
+      for (uint32_t i = lo + lane; i < hi; i += 32) {
+        const uint32_t slot = dp[i] - tile_lo, o = own[slot];
+        if ((o & (kOwnFlag - 1u)) != start + (i - lo)) own[slot] = (unsigned short)(o | kOwnFlag);
+      }
+      start += hi - lo;
+    }
+    __syncwarp();
+    uint32_t cut = cut_now();
+    start = 0;
+    for (uint32_t t = 0; t < nsp; t++) {
+      const uint32_t lo = rbj[t * kRbStride], hi = rbj[t * kRbStride + 1];
+      const uint32_t *dp = seg.post_doc + qt[t].base;
+      const float *sp = wb.scores + qt[t].base;
+      const float w = qt[t].weight;
+#pragma unroll 1
+      for (uint32_t b = lo; b < hi; b += 32) {
+        const uint32_t i = b + lane;
+        const bool in = i < hi;
+        uint32_t slot = 0, o = 0xFFFFFFFFu;
+        const uint32_t pp = start + (i - lo);
+        if (in) {
+          slot = dp[i] - tile_lo;
+          o = own[slot];
+        }
+        const bool mine = in && (o & (kOwnFlag - 1u)) == pp;
+        const bool conf = mine && (o & kOwnFlag);
+        float v = 0.0f;
+        if (mine && !conf) v = __fmul_rn(sp[i], w);
+        const bool pass = mine && !conf && __float_as_uint(v) >= cut;
+        if (__any_sync(0xFFFFFFFFu, pass)) {
+          complete(pass, tile_lo + slot, v);
+          cut = cut_now();
+        }
+        park(conf, slot, pp);
+      }
+      start += hi - lo;
+    }
   }
+  if (npend) resolve(npend);
+  __syncwarp();
 }
 
 // ---- sparse pass -----------------------------------------------------------------------------------------------
@@ -305,18 +425,16 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t sub_docs = wb.sub_docs, cap = sd.stage_cap, k = wb.k;
   unsigned char *mine = smem_raw + (size_t)warp * sparse_smem_per_warp(sub_docs, cap);
-  float *acc = reinterpret_cast<float *>(mine);
-  uint32_t *sdoc = reinterpret_cast<uint32_t *>(acc + sub_docs);
+  unsigned short *own = reinterpret_cast<unsigned short *>(mine);
+  uint32_t *sdoc = reinterpret_cast<uint32_t *>(mine + (((size_t)sub_docs * 2 + 15) & ~(size_t)15));
   float *ssc = reinterpret_cast<float *>(sdoc + cap);
   unsigned long long *cand = reinterpret_cast<unsigned long long *>(ssc + cap);
   QTerm *qt = reinterpret_cast<QTerm *>(cand + kWarpCand);
   uint32_t *rb = reinterpret_cast<uint32_t *>(qt + kWarpMaxTerms);
-  uint32_t *runs = rb + kWarpMaxTerms * kRbStride;                                   // [jj][t] = i0 | i1 << 16, staged indices
-  float *rest = reinterpret_cast<float *>(runs + kSubPerGroup * kWarpMaxTerms);      // [jj] what the column terms can add
-  uint32_t *soff = reinterpret_cast<uint32_t *>(rest + kSubPerGroup);
-  uint32_t *slo = soff + kWarpMaxTerms;
-  unsigned long long *bar = reinterpret_cast<unsigned long long *>(slo + kWarpMaxTerms);
-  for (uint32_t i = lane * 4; i < sub_docs; i += 128) *reinterpret_cast<float4 *>(acc + i) = make_float4(0, 0, 0, 0);
+  uint32_t *cum = rb + kWarpMaxTerms * kRbStride;                 // [65]: staged offset of cell j*8+t, whole item
+  float *rest = reinterpret_cast<float *>(cum + 68);              // [jj] what the column terms can add
+  uint32_t *pend = reinterpret_cast<uint32_t *>(rest + kSubPerGroup);
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(pend + 64);
   if (lane == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -348,6 +466,7 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
     if (spmask) {
       n_items++;
       const uint32_t nsp = __popc(spmask);
+      const bool unit_w = __all_sync(0xFFFFFFFFu, lane >= (int)nsp || qt[lane & 7].weight == 1.0f);
       const uint32_t sub0 = tg * kSubPerGroup;
       const uint32_t jmax = min(kSubPerGroup, wb.n_sub - sub0);
       {
@@ -374,86 +493,78 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
         }
       }
       __syncwarp();
+      // cells e = j*8 + t, two per lane: the run of term t in sub-tile j rounded out to 16-byte pieces; cum = exclusive scan
+      uint32_t len[2], alo[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const uint32_t e = lane + 32 * h, t = e & 7, j = e >> 3;
+        len[h] = 0;
+        alo[h] = 0;
+        if (t < nsp && j < jmax) {
+          const uint32_t lo = rb[t * kRbStride + j], hi = rb[t * kRbStride + j + 1];
+          if (hi > lo) {
+            alo[h] = lo & ~3u;
+            len[h] = ((hi + 3u) & ~3u) - alo[h];
+            n_post += hi - lo;
+          }
+        }
+      }
+      {
+        uint32_t s0 = len[0], s1 = len[1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, s0, o), b2 = __shfl_up_sync(0xFFFFFFFFu, s1, o);
+          if (lane >= o) {
+            s0 += a;
+            s1 += b2;
+          }
+        }
+        s1 += __shfl_sync(0xFFFFFFFFu, s0, 31);
+        cum[lane + 1] = s0;
+        cum[lane + 33] = s1;
+        if (lane == 0) cum[0] = 0;
+      }
+      __syncwarp();
       wc.begin(cand, thr0, k, lane);
 
       uint32_t j0 = 0;
       while (j0 < jmax) {
-        // the longest span of sub-tiles [j0, j1) whose runs (rounded out to 16-byte pieces) fit the staging area
-        uint32_t tot = 0;
+        // the longest span of sub-tiles [j0, j1) that fits the staging area
+        const uint32_t base = cum[j0 * 8];
         const uint32_t jc = j0 + 1 + lane;  // lanes 0..7 try j1 = j0+1 .. j0+8
-        if (jc <= jmax)
-          for (uint32_t t = 0; t < nsp; t++) {
-            const uint32_t lo = rb[t * kRbStride + j0], hi = rb[t * kRbStride + jc];
-            if (hi > lo) tot += ((hi + 3u) & ~3u) - (lo & ~3u);
-          }
+        const uint32_t tot = jc <= jmax ? cum[jc * 8] - base : 0xFFFFFFFFu;
         const uint32_t fits = __ballot_sync(0xFFFFFFFFu, jc <= jmax && tot <= cap);
         if (!(fits & 1u)) {  // a single sub-tile does not fit: straight from global memory
-          uint32_t r0 = 0, r1 = 0;
-          if (lane < (int)nsp) {
-            r0 = rb[lane * kRbStride + j0];
-            r1 = rb[lane * kRbStride + j0 + 1];
-            n_post += r1 - r0;
-          }
-          sparse_sub<false>(seg, wb, head, qt, r0, r1, colmask, rest[j0], (sub0 + j0) * sub_docs, acc, sdoc, ssc, wc, lane);
+          sparse_sub<false>(seg, wb, head, qt, rb + j0, cum, 0u, nsp, colmask, unit_w, rest[j0], (sub0 + j0) * sub_docs, sub_docs, own, sdoc, ssc, pend, wc,
+                            lane);
           j0++;
           continue;
         }
-        const uint32_t nspan = __ffs(~fits) - 1;  // fits is a run of ones from bit 0 (tot grows with j1)
+        const uint32_t nspan = __ffs(~fits) - 1;  // fits is a run of ones from bit 0 (cum grows)
         const uint32_t j1 = j0 + nspan;
         const uint32_t span_tot = __shfl_sync(0xFFFFFFFFu, tot, nspan - 1);
         if (span_tot == 0) {
           j0 = j1;
           continue;
         }
-        // ---- stage: lanes 0..7 lay the terms out, lanes 0..15 issue one bulk copy each (docs / scores per term) ----
-        {
-          uint32_t len = 0, lo_al = 0;
-          if (lane < (int)nsp) {
-            const uint32_t lo = rb[lane * kRbStride + j0], hi = rb[lane * kRbStride + j1];
-            if (hi > lo) {
-              lo_al = lo & ~3u;
-              len = ((hi + 3u) & ~3u) - lo_al;
-              n_post += hi - lo;
-            }
-          }
-          uint32_t off = len;  // inclusive scan over lanes 0..7
+        // ---- stage: one bulk copy per non-empty cell and array, each lane its own cells ----
+        __syncwarp();  // every lane is done reading the staging area of the previous span
+        if (lane == 0) mbar_arrive_expect_tx(bar, span_tot * 8u);
+        __syncwarp();
 #pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, off, o);
-            if (lane >= o) off += n;
+        for (int h = 0; h < 2; h++) {
+          const uint32_t e = lane + 32 * h, t = e & 7, j = e >> 3;
+          if (len[h] && j >= j0 && j < j1) {
+            const uint32_t off = cum[e] - base;
+            bulk_copy_g2s(sdoc + off, seg.post_doc + qt[t].base + alo[h], len[h] * 4u, bar);
+            bulk_copy_g2s(ssc + off, wb.scores + qt[t].base + alo[h], len[h] * 4u, bar);
           }
-          off -= len;
-          if (lane < (int)kWarpMaxTerms) {
-            soff[lane] = off;
-            slo[lane] = lo_al;
-          }
-          __syncwarp();  // every lane is done reading the staging area of the previous span
-          if (lane == 0) mbar_arrive_expect_tx(bar, span_tot * 8u);
-          __syncwarp();
-          const uint32_t t = (lane >> 1) & 7;
-          const uint32_t tlen = __shfl_sync(0xFFFFFFFFu, len, t), tlo = __shfl_sync(0xFFFFFFFFu, lo_al, t), toff = __shfl_sync(0xFFFFFFFFu, off, t);
-          if (lane < 16 && tlen) {
-            if (lane & 1) bulk_copy_g2s(ssc + toff, wb.scores + qt[t].base + tlo, tlen * 4u, bar);
-            else bulk_copy_g2s(sdoc + toff, seg.post_doc + qt[t].base + tlo, tlen * 4u, bar);
-          }
-          // run table of the span while the copies fly: entry e = jj*8 + t, two per lane
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const uint32_t e = lane + 32 * h, et = e & 7, ej = e >> 3;
-            uint32_t v = 0;
-            if (et < nsp && j0 + ej < j1) {
-              const uint32_t sh = soff[et] - slo[et];
-              v = (rb[et * kRbStride + j0 + ej] + sh) | ((rb[et * kRbStride + j0 + ej + 1] + sh) << 16);
-            }
-            runs[e] = v;
-          }
-          __syncwarp();
-          mbar_wait(bar, parity);
-          parity ^= 1u;
         }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
         for (uint32_t j = j0; j < j1; j++) {
-          const uint32_t r = lane < (int)kWarpMaxTerms ? runs[(j - j0) * kWarpMaxTerms + lane] : 0u;
-          sparse_sub<true>(seg, wb, head, qt, r & 0xFFFFu, r >> 16, colmask, rest[j], (sub0 + j) * sub_docs, acc, sdoc, ssc, wc, lane);
+          sparse_sub<true>(seg, wb, head, qt, rb + j, cum + j * 8, base, nsp, colmask, unit_w, rest[j], (sub0 + j) * sub_docs, sub_docs, own, sdoc, ssc,
+                           pend, wc, lane);
         }
         j0 = j1;
       }
@@ -569,6 +680,32 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(Segme
         look = !known || (bound != 0.0f && __float_as_uint(bound) >= thr_bits);
       }
       uint32_t hits = __ballot_sync(0xFFFFFFFFu, look);
+      if (!PRUNE) {
+        // the common several-column shape — two unit-weight columns resident in shared memory: sum the block per doc
+        // (slot order) and leave the query out of the per-doc pass below unless some doc can enter its top k
+        const bool two = look && cq.ncol == 2 && cq.unit_w && cq.slot[0] < resident && cq.slot[1] < resident;
+        uint32_t m2 = __ballot_sync(0xFFFFFFFFu, two);
+        const uint32_t my01 = (uint32_t)cq.slot[0] | ((uint32_t)cq.slot[1] << 16);
+        const uint32_t my_thr = thr == kThrInit ? 0u : (uint32_t)(thr >> 32);
+        while (m2) {
+          const int g = __ffs(m2) - 1;
+          m2 &= m2 - 1;
+          const uint32_t s01 = __shfl_sync(0xFFFFFFFFu, my01, g);
+          const uint32_t tb = __shfl_sync(0xFFFFFFFFu, my_thr, g);
+          const float4 *pa = reinterpret_cast<const float4 *>(cb + (size_t)(s01 & 0xFFFFu) * kColBlock) + lane;
+          const float4 *pb = reinterpret_cast<const float4 *>(cb + (size_t)(s01 >> 16) * kColBlock) + lane;
+          uint32_t mx = 0u;
+#pragma unroll
+          for (uint32_t x = 0; x < kColBlock / 128; x++) {
+            const float4 a = pa[x * 32], c = pb[x * 32];
+            const uint32_t m01 = max(__float_as_uint(__fadd_rn(a.x, c.x)), __float_as_uint(__fadd_rn(a.y, c.y)));
+            const uint32_t m23 = max(__float_as_uint(__fadd_rn(a.z, c.z)), __float_as_uint(__fadd_rn(a.w, c.w)));
+            mx = max(mx, max(m01, m23));
+          }
+          n_looked++;
+          if (!__any_sync(0xFFFFFFFFu, mx >= tb && mx != 0u)) hits &= ~(1u << g);
+        }
+      }
       while (hits) {
         const int g = __ffs(hits) - 1;
         hits &= hits - 1;

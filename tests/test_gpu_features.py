@@ -356,6 +356,7 @@ def test_list_column_filters_match_oracle():
     qb = synth.generate_queries(40, spec.vocab, seed=25, min_rank=2)
     for fid, onodes, strings in (fids[0], fids[6]):
         qb.filter_id = np.full(qb.n_queries, fid, dtype=np.int32)
+        qb._structs = None  # (the struct array is cached per batch)
         ref = ora.search_batch(qb, 11, "bm25", filter_nodes=onodes, strings=strings)
         assert_parity(*ref, *gi.search_batch(qb, 11, "bm25"), strict=False)
     gi.close()
