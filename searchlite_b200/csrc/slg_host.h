@@ -181,6 +181,7 @@ struct slg_index {
   uint32_t dense_min_df = 256;   // ... and df >= this
   uint64_t max_column_bytes = 24ull << 30;
   uint32_t stage_cap = 1024;     // sparse pass: postings a warp stages in shared memory per span (slg_stream_kernel.cuh)
+  uint32_t strict_accumulate = 0; // exhaustive stream kernels: 1 = sum every posting per doc; 0 = bounded accumulation (slg_stream_kernel.cuh)
   uint32_t stream_kernels = 1;   // exhaustive plain OR batches: 1 = sparse pass + column pass, 0 = the items kernel
   uint32_t maxscore_pct = 35;    // pruned warp kernel: non-essential bounds may sum to this % of the k-th score (0 = tile skip only)
   bool keep_positions = true;    // keep term positions resident when a posting image carries them (SegmentReader keep_positions)

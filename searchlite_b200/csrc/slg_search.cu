@@ -555,6 +555,7 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
         sdv.sparse_counter = bt->work_counter + 1;
         sdv.col_counter = bt->work_counter + 2;
         sdv.stage_cap = ix->stage_cap;
+        sdv.strict = ix->strict_accumulate;
         sdv.counters = bt->item_counters;
         const size_t ssmem = (size_t)kSparseWarps * sparse_smem_per_warp(wb.sub_docs, sdv.stage_cap);
         if (ssmem + 1024 > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "sub_docs %u with stage_cap %u needs %zu B shared memory", wb.sub_docs, sdv.stage_cap, ssmem);

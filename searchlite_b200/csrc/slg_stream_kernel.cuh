@@ -62,6 +62,7 @@ struct StreamDev {
   uint32_t stage_cap;    // postings a warp of the sparse pass can stage per span (multiple of 4)
   uint32_t col_resident; // columns of a block the column pass keeps in shared memory (per buffer)
   uint32_t n_smax;       // block maxima kept in shared memory (min(columns of the segment, kColMaxSlots))
+  uint32_t strict;       // 1: accumulate every posting per doc (option strict_accumulate); 0: bounded accumulation, see sparse_sub_bounded
   unsigned long long *counters;  // [4] sparse postings visited, (query, column block) pairs looked at per doc, (query, column block) pairs scored, sparse items
 };
 
@@ -200,9 +201,9 @@ struct WarpCand {
 
 // shared memory of one warp of the sparse pass
 __host__ __device__ inline size_t sparse_smem_per_warp(uint32_t sub_docs, uint32_t stage_cap) {
-  // own u16[sub_docs] | sdoc u32[cap] | ssc f32[cap] | cand u64[64] | qt QTerm[8] | rb u32[8][9] | cum u32[65 (+3)] | rest f32[8] | pend u32[64] | bar u64 (+ pad)
+  // own u16[sub_docs] | sdoc u32[cap] | ssc f32[cap] | cand u64[64] | qt QTerm[8] | rb u32[8][9] | cum u32[65 (+3)] | rest f32[8] | cmx f32[8] | pend u32[64] | bar u64 (+ pad)
   return (((size_t)sub_docs * 2 + 15) & ~(size_t)15) + (size_t)stage_cap * 8 + kWarpCand * 8 + kWarpMaxTerms * sizeof(QTerm) +
-         kWarpMaxTerms * kRbStride * 4 + 68 * 4 + kSubPerGroup * 4 + 64 * 4 + 16;
+         kWarpMaxTerms * kRbStride * 4 + 68 * 4 + kSubPerGroup * 4 + kWarpMaxTerms * 4 + 64 * 4 + 16;
 }
 
 constexpr uint32_t kOwnFlag = 0x8000u;  // own[slot]: index of the posting that owns the doc | this flag when other lists hold it too
@@ -418,6 +419,112 @@ __device__ __forceinline__ void sparse_sub(const SegmentDev &seg, const WarpBatc
   __syncwarp();
 }
 
+// One sub-tile of the sparse pass with BOUNDED ACCUMULATION (the default; option strict_accumulate 0).
+//
+// Every staged score of the sub-tile is read and compared; what is bounded is the per-doc summation.  A doc's sparse sum is
+// at most (its posting's contribution) + (the largest contribution of every OTHER sparse term inside the sub-tile), and its
+// score at most that + what the column terms can add (rest).  The maxima are taken from the staged values themselves — no
+// index-time bound is consulted, the pruned executions do that — so:
+//   A   the largest staged score M (one pass over the scores).  nsp * M * max weight + rest below the k-th score: no doc of
+//       the sub-tile can enter the top k and nothing is summed
+//   A2  otherwise the largest contribution per term, cmx[t]
+//   B   a posting whose contribution + the other terms' maxima + rest reaches the k-th score has its doc summed exactly:
+//       every sparse term in slot order (own contribution; the others found by binary search in their staged runs), then
+//       the column terms (complete).  A doc with postings in several lists passes the test with each of them when it
+//       matters; the posting of its first list offers it, the others stand back.
+// The staging rounds runs out to 16 bytes: the few neighbours it drags in only loosen the maxima, and B tests the doc range.
+__device__ __forceinline__ void sparse_sub_bounded(const SegmentDev &seg, const WarpBatchDev &wb, const QHead &head, const QTerm *qt, const uint32_t *cb,
+                                                   const uint32_t base, const uint32_t nsp, const uint32_t colmask, const bool unit_w,
+                                                   const float wmx, const float rest, const uint32_t tile_lo, const uint32_t sub_docs,
+                                                   const uint32_t *sdoc, const float *ssc, float *cmx, WarpCand &wc, const int lane) {
+  const uint32_t P0 = cb[0] - base, P1 = cb[nsp] - base;
+  if (P1 <= P0) return;
+  const bool have_thr = wc.thr != kThrInit;
+  float thr_score = __uint_as_float((uint32_t)(wc.thr >> 32));
+  if (have_thr) {
+    uint32_t m = 0u;
+#pragma unroll 1
+    for (uint32_t p = P0 + lane; p < P1; p += 32) m = max(m, __float_as_uint(ssc[p]));
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if (((float)nsp * (__uint_as_float(m) * wmx) + rest) * 1.00002f < thr_score) return;
+  }
+  // ---- A2: per-term maxima ----
+  float sum_all = 0.0f;
+  for (uint32_t t = 0; t < nsp; t++) {
+    const uint32_t c0 = cb[t] - base, c1 = cb[t + 1] - base;
+    uint32_t m = 0u;
+#pragma unroll 1
+    for (uint32_t p = c0 + lane; p < c1; p += 32) m = max(m, __float_as_uint(ssc[p]));
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    const float mt = __fmul_rn(__uint_as_float(m), qt[t].weight);
+    if (lane == 0) cmx[t] = mt;
+    sum_all += mt;
+  }
+  __syncwarp();
+  if (have_thr && (sum_all + rest) * 1.00002f < thr_score) return;
+  // ---- B: the postings whose docs can still qualify ----
+  for (uint32_t t = 0; t < nsp; t++) {
+    const uint32_t c0 = cb[t] - base, c1 = cb[t + 1] - base;
+    if (c1 <= c0) continue;
+    float other = rest;
+    for (uint32_t u = 0; u < nsp; u++)
+      if (u != t) other += cmx[u];
+    const float w = qt[t].weight;
+#pragma unroll 1
+    for (uint32_t b = c0; b < c1; b += 32) {
+      const uint32_t p = b + lane;
+      float v = 0.0f;
+      if (p < c1) v = unit_w ? ssc[p] : __fmul_rn(ssc[p], w);
+      uint32_t cut = 0u;
+      if (wc.thr != kThrInit) {
+        const float cf = __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f - other * 1.00002f;
+        cut = cf > 0.0f ? __float_as_uint(cf) : 0u;
+      }
+      bool pass = p < c1 && __float_as_uint(v) >= cut;
+      if (!__any_sync(0xFFFFFFFFu, pass)) continue;
+      uint32_t doc = 0u;
+      if (pass) {
+        doc = sdoc[p];
+        pass = doc - tile_lo < sub_docs;
+      }
+      // the doc's exact sparse sum, slot order; a doc that an earlier list holds is that posting's to offer
+      float s = 0.0f;
+      if (pass) {
+        for (uint32_t u = 0; u < nsp; u++) {
+          float c = 0.0f;
+          if (u == t) {
+            c = v;
+          } else {
+            uint32_t lo = cb[u] - base, hi = cb[u + 1] - base;
+            const uint32_t end = hi;
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if (sdoc[mid] < doc) lo = mid + 1;
+              else hi = mid;
+            }
+            if (lo < end && sdoc[lo] == doc) {
+              if (u < t) {
+                pass = false;
+                break;
+              }
+              c = __fmul_rn(ssc[lo], qt[u].weight);
+            }
+          }
+          if (c != 0.0f) s = __fadd_rn(s, c);
+        }
+      }
+      if (!__any_sync(0xFFFFFFFFu, pass)) continue;
+      if (pass)
+        for (uint32_t cm = colmask; cm; cm &= cm - 1) {
+          const uint32_t ct = __ffs(cm) - 1;
+          const float c = __ldg(seg.cols + qt[ct].sc_base + doc);
+          s = __fadd_rn(s, __fmul_rn(c, qt[ct].weight));
+        }
+      wc.offer(seg, wb, head.qi, head.filter, pass, doc, s);
+    }
+  }
+}
+
 // ---- sparse pass -----------------------------------------------------------------------------------------------
 template <bool UNUSED>
 __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(SegmentDev seg, WarpBatchDev wb, StreamDev sd) {
@@ -433,7 +540,8 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
   uint32_t *rb = reinterpret_cast<uint32_t *>(qt + kWarpMaxTerms);
   uint32_t *cum = rb + kWarpMaxTerms * kRbStride;                 // [65]: staged offset of cell j*8+t, whole item
   float *rest = reinterpret_cast<float *>(cum + 68);              // [jj] what the column terms can add
-  uint32_t *pend = reinterpret_cast<uint32_t *>(rest + kSubPerGroup);
+  float *cmx = rest + kSubPerGroup;                               // [t] largest contribution of term t inside the sub-tile at hand
+  uint32_t *pend = reinterpret_cast<uint32_t *>(cmx + kWarpMaxTerms);
   unsigned long long *bar = reinterpret_cast<unsigned long long *>(pend + 64);
   if (lane == 0) {
     mbar_init(bar, 1);
@@ -467,6 +575,10 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
       n_items++;
       const uint32_t nsp = __popc(spmask);
       const bool unit_w = __all_sync(0xFFFFFFFFu, lane >= (int)nsp || qt[lane & 7].weight == 1.0f);
+      float wmx = lane < (int)nsp ? qt[lane & 7].weight : 0.0f;  // largest weight of a sparse term
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) wmx = fmaxf(wmx, __shfl_xor_sync(0xFFFFFFFFu, wmx, o));
+      wmx = __shfl_sync(0xFFFFFFFFu, wmx, 0);
       const uint32_t sub0 = tg * kSubPerGroup;
       const uint32_t jmax = min(kSubPerGroup, wb.n_sub - sub0);
       {
@@ -563,8 +675,12 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
         mbar_wait(bar, parity);
         parity ^= 1u;
         for (uint32_t j = j0; j < j1; j++) {
-          sparse_sub<true>(seg, wb, head, qt, rb + j, cum + j * 8, base, nsp, colmask, unit_w, rest[j], (sub0 + j) * sub_docs, sub_docs, own, sdoc, ssc,
-                           pend, wc, lane);
+          if (sd.strict)
+            sparse_sub<true>(seg, wb, head, qt, rb + j, cum + j * 8, base, nsp, colmask, unit_w, rest[j], (sub0 + j) * sub_docs, sub_docs, own, sdoc, ssc,
+                             pend, wc, lane);
+          else
+            sparse_sub_bounded(seg, wb, head, qt, cum + j * 8, base, nsp, colmask, unit_w, wmx, rest[j], (sub0 + j) * sub_docs, sub_docs, sdoc, ssc, cmx,
+                               wc, lane);
         }
         j0 = j1;
       }
@@ -669,7 +785,7 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(Segme
         // (same slot order, every operation monotone: it dominates every doc's sum).
         float bound = 0.0f;
         bool known = true;
-        if (PRUNE || cq.ncol == 1)
+        if (PRUNE || !sd.strict || cq.ncol == 1)
           for (uint32_t i = 0; i < cq.ncol; i++) {
             const uint32_t s = cq.slot[i];
             if (s >= n_smax) known = false;
@@ -680,7 +796,7 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(Segme
         look = !known || (bound != 0.0f && __float_as_uint(bound) >= thr_bits);
       }
       uint32_t hits = __ballot_sync(0xFFFFFFFFu, look);
-      if (!PRUNE) {
+      if (!PRUNE && sd.strict) {
         // the common several-column shape — two unit-weight columns resident in shared memory: sum the block per doc
         // (slot order) and leave the query out of the per-doc pass below unless some doc can enter its top k
         const bool two = look && cq.ncol == 2 && cq.unit_w && cq.slot[0] < resident && cq.slot[1] < resident;
