@@ -171,7 +171,9 @@ typedef struct {
   uint64_t last_postings_scattered;     /* postings read and accumulated (compare with last_posting_count) */
   uint64_t last_subtiles_skipped;       /* (query, sub-tile) pairs dropped inside the sweep by the bound */
   uint64_t last_column_blocks_streamed; /* 512-doc blocks of dense columns read */
-  uint64_t last_items;                  /* (query, doc-range) items scored, seeds included */
+  uint64_t last_items;                  /* (query, doc-range) items scored, seeds included; flat scan: (query, term, chunk) items scanned */
+  uint64_t last_postings_verified;      /* flat scan: postings whose doc got its exact score (binary searches + column gathers) */
+  uint64_t last_items_dropped;          /* flat scan, pruned: items of non-essential terms dropped (MaxScore) */
 } slg_counters_t;
 
 /* ---- lifetime ---- */

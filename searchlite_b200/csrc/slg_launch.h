@@ -2,7 +2,7 @@
 // translation unit (slg_launch_tiles.cu, slg_launch_warp.cu, slg_launch_items.cu) so that the library builds in
 // parallel; the host code selects a variant by flags.
 #pragma once
-#include "slg_stream_kernel.cuh"
+#include "slg_scan_kernel.cuh"
 
 namespace slg {
 
@@ -14,6 +14,7 @@ cudaError_t launch_score_items(bool prune, const SegmentDev &sd, const WarpBatch
                                cudaStream_t st);
 cudaError_t launch_score_sparse(const SegmentDev &sd, const WarpBatchDev &wb, const StreamDev &st_dev, size_t smem, int grid, cudaStream_t st);
 cudaError_t launch_score_columns(bool prune, const SegmentDev &sd, const WarpBatchDev &wb, const StreamDev &st_dev, size_t smem, int grid, cudaStream_t st);
+cudaError_t launch_scan(bool prune, const SegmentDev &sd, const WarpBatchDev &wb, const ScanDev &sc, int grid, cudaStream_t st);
 cudaError_t launch_seed_items(const SegmentDev &sd, const WarpBatchDev &wb, const ItemsDev &it, size_t smem, int grid, cudaStream_t st);
 
 }  // namespace slg

@@ -33,6 +33,11 @@ cudaError_t launch_score_columns(bool prune, const SegmentDev &sd, const WarpBat
   return prune ? go_n(slg_score_columns_kernel<true>, kColWarps * 32, smem, grid, st, sd, wb, st_dev)
                : go_n(slg_score_columns_kernel<false>, kColWarps * 32, smem, grid, st, sd, wb, st_dev);
 }
+cudaError_t launch_scan(bool prune, const SegmentDev &sd, const WarpBatchDev &wb, const ScanDev &sc, int grid, cudaStream_t st) {
+  if (prune) slg_scan_kernel<true><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
+  else slg_scan_kernel<false><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
+  return cudaGetLastError();
+}
 cudaError_t launch_seed_items(const SegmentDev &sd, const WarpBatchDev &wb, const ItemsDev &it, size_t smem, int grid, cudaStream_t st) {
   return go(slg_seed_items_kernel<0>, smem, grid, st, sd, wb, it);
 }

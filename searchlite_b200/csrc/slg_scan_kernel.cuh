@@ -1,0 +1,346 @@
+// slg_scan_kernel.cuh — K2/K3/K5, flat posting scan: the automatic choice for plain OR queries with k <= 32 and <= 8 terms
+// per query on segments with resident scores (the shape of BASELINE.json configs[1]), exhaustive and pruned.
+//
+// brute_force (query/wand.rs:459-566) sums every posting into its doc and offers every touched doc to push_top_k; wand_loop
+// (:659-903) walks the lists document-at-a-time and skips what cannot beat the k-th score.  For small k both produce a top k
+// that almost no doc enters, so this kernel never builds per-doc accumulators.  A term WITHOUT a dense column is scanned flat:
+//
+//   work item  = (query, term, chunk of kScanChunk postings), handed out from a global counter, RAREST TERMS FIRST: the
+//                docs that end up in a query's top k nearly always hold its rarest term, so every query's k-th score is close
+//                to final before its long lists are streamed
+//   scan       = the resident unit-weight scores of the chunk, 128-bit loads, 128 postings per warp step; a posting is looked
+//                at further only if  contribution + (largest contribution of every OTHER term of the query)  can reach the
+//                query's running k-th score.  Doc ids are not even read for the rest
+//   verify     = the doc of such a posting gets its EXACT score: every term of the query in slot (= declared) order — the
+//                posting's own contribution, the other sparse terms by binary search in their lists, the column terms by one
+//                4-byte gather — the sum brute_force computes for that doc, then accept (api/reader.rs:3009-3036) and the
+//                warp's candidate buffer.  A doc held by several scanned lists is offered by the posting of its
+//                highest-priority list; should two passes still offer the same doc, equal keys collapse in the merge
+//
+// Exhaustive execution (bm25): every posting of every sparse term is read and compared; the "largest contribution of the other
+// terms" comes from slg_term_max_kernel, a reduction over the batch's own posting scores at run time — no index-time bound is
+// consulted.  Docs held by no sparse list are the column pass's (slg_score_columns_kernel), which runs afterwards.
+// Pruned execution (wand / bmw): MaxScore over whole lists.  With the terms ordered by their bound, the longest prefix of
+// smallest bounds whose sum stays below the k-th score is non-essential: a doc holding only such terms cannot enter the top k,
+// so their items are dropped when they come up (the k-th score only rises, so the set only grows); every doc that matters
+// holds an essential term, is met in that term's scan and verified exactly as above.  Results are byte-identical to bm25.
+//
+// Float contract (include/searchlite_gpu.h): slot order = the query's terms WITHOUT a column first, then those WITH one,
+// each group in query order (slg_build_qterms_kernel); verify() adds in slot order starting from +0.
+#pragma once
+#include "slg_stream_kernel.cuh"
+
+namespace slg {
+
+constexpr uint32_t kScanChunk = 4096;  // postings per scan item
+constexpr int kScanWarps = 8;
+
+struct __align__(16) ScanPair {  // one scanned (query, sparse term): 48 B
+  uint64_t base;      // first padded posting index of the term
+  uint32_t df;
+  uint32_t qslot_t;   // qslot << 3 | slot
+  uint32_t qi;
+  float w;
+  float others;       // sum of the other terms' bounds (weight applied)
+  float ne_prefix;    // sum of the bounds of the terms with a bound <= this term's (this term included): the MaxScore test
+  int32_t filter;
+  uint32_t first_item;
+  uint32_t pad[2];
+};
+
+struct ScanDev {
+  const uint32_t *ut_term;   // [U] unique terms of the batch
+  float *ut_max;             // [U] largest unit-weight contribution of each (slg_term_max_kernel)
+  ScanPair *pairs;           // [Q * 8] indexed by qslot * 8 + slot; df == 0: not scanned
+  uint32_t *order;           // [Q * 8] pair indices, rarest first
+  uint32_t *n_pairs;         // device counters: scanned pairs, items
+  uint32_t *n_items;
+  uint32_t *item_start;      // [n_pairs + 1] first item of every ordered pair
+  uint32_t *items;           // [items_cap] ordered-pair index of every item
+  uint32_t items_cap;
+  uint32_t *counter;         // work counter
+  unsigned long long *counters;  // [8]: 0 postings scanned, 3 items scanned, 4 postings verified, 5 items dropped by MaxScore
+};
+
+// largest unit-weight contribution of every unique term of the batch: a reduction over the term's resident scores
+static __global__ void __launch_bounds__(256) slg_term_max_kernel(SegmentDev seg, ScanDev sc, uint32_t n_uterms) {
+  const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (u >= n_uterms) return;
+  const uint32_t term = sc.ut_term[u];
+  uint32_t m = 0u;
+  if (term < seg.n_terms) {
+    const uint32_t df = seg.term_df[term];
+    const float4 *p = reinterpret_cast<const float4 *>(seg.post_score + seg.term_start[term]);
+    // (the padding of a list is zero: whole 16-byte pieces up to the 32-posting boundary are safe to read)
+    for (uint32_t i = lane; i * 4 < df; i += 32) {
+      const float4 v = __ldg(p + i);
+      m = max(m, max(max(__float_as_uint(v.x), __float_as_uint(v.y)), max(__float_as_uint(v.z), __float_as_uint(v.w))));
+    }
+  }
+  m = __reduce_max_sync(0xFFFFFFFFu, m);
+  if (lane == 0) sc.ut_max[u] = __uint_as_float(m);
+}
+
+// per query slot: the scanned pairs with their bounds.  Thread per query.
+static __global__ void __launch_bounds__(128) slg_scan_pairs_kernel(SegmentDev seg, WarpBatchDev wb, ScanDev sc) {
+  const uint32_t qslot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qslot >= wb.n_queries) return;
+  const QHead h = wb.qheads[qslot];
+  float ub[kWarpMaxTerms];
+  float total = 0.0f;
+  for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
+    ub[t] = 0.0f;
+    if (t < h.nt) {
+      const QTerm &q = wb.qterms[(uint64_t)qslot * kWarpMaxTerms + t];
+      if (q.flags & 1u) ub[t] = __fmul_rn(sc.ut_max[q.uterm], q.weight);
+    }
+    total += ub[t];
+  }
+  for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
+    ScanPair p;
+    p.base = 0;
+    p.df = 0;
+    p.qslot_t = (qslot << 3) | t;
+    p.qi = h.qi;
+    p.w = 0.0f;
+    p.others = 0.0f;
+    p.ne_prefix = 0.0f;
+    p.filter = h.filter;
+    p.first_item = 0;
+    p.pad[0] = p.pad[1] = 0;
+    if (t < h.nt) {
+      const QTerm &q = wb.qterms[(uint64_t)qslot * kWarpMaxTerms + t];
+      if ((q.flags & 5u) == 1u && q.term < seg.n_terms) {
+        p.base = q.base;
+        p.df = seg.term_df[q.term];
+        p.w = q.weight;
+        float o = 0.0f, pre = 0.0f;
+        for (uint32_t u = 0; u < kWarpMaxTerms; u++) {
+          if (u != t) o += ub[u];
+          if (ub[u] < ub[t] || (ub[u] == ub[t] && u >= t)) pre += ub[u];  // terms of lower priority, and this one
+        }
+        p.others = o;
+        p.ne_prefix = pre;
+      }
+    }
+    sc.pairs[(uint64_t)qslot * kWarpMaxTerms + t] = p;
+  }
+}
+
+// order the scanned pairs rarest first (buckets of log2 df; inside a bucket any order) and lay out their items.  One CTA.
+static __global__ void __launch_bounds__(1024) slg_scan_order_kernel(WarpBatchDev wb, ScanDev sc) {
+  __shared__ uint32_t s_hist[33], s_cur[33], s_carry;
+  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+  const uint32_t n = wb.n_queries * kWarpMaxTerms;
+  if (tid < 33) s_hist[tid] = 0u;
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += nthr) {
+    const uint32_t df = sc.pairs[i].df;
+    if (df) atomicAdd(&s_hist[32 - __clz(df)], 1u);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (int b = 0; b < 33; b++) {
+      s_cur[b] = run;
+      run += s_hist[b];
+    }
+    *sc.n_pairs = run;
+    s_carry = 0;
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += nthr) {
+    const uint32_t df = sc.pairs[i].df;
+    if (df) sc.order[atomicAdd(&s_cur[32 - __clz(df)], 1u)] = i;
+  }
+  __syncthreads();
+  // exclusive scan of the item counts in order: 1024 pairs per round
+  const uint32_t np = *sc.n_pairs;
+  __shared__ uint32_t s_scan[1024];
+  for (uint32_t b0 = 0; b0 < np; b0 += nthr) {
+    const uint32_t i = b0 + tid;
+    uint32_t c = 0;
+    if (i < np) c = (sc.pairs[sc.order[i]].df + kScanChunk - 1) / kScanChunk;
+    s_scan[tid] = c;
+    __syncthreads();
+    for (uint32_t o = 1; o < nthr; o <<= 1) {
+      const uint32_t v = tid >= o ? s_scan[tid - o] : 0u;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    const uint32_t excl = s_scan[tid] - c + s_carry;
+    if (i < np) {
+      sc.item_start[i] = excl;
+      sc.pairs[sc.order[i]].first_item = excl;
+    }
+    __syncthreads();
+    if (tid == nthr - 1) s_carry += s_scan[tid];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    sc.item_start[np] = s_carry;
+    *sc.n_items = min(s_carry, sc.items_cap);
+  }
+}
+
+// items[i] = ordered pair of item i (binary search over item_start).  Grid-wide.
+static __global__ void __launch_bounds__(256) slg_scan_items_kernel(ScanDev sc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_items = *sc.n_items, np = *sc.n_pairs;
+  if (i >= n_items) return;
+  uint32_t lo = 0, hi = np;  // last pair with item_start <= i
+  while (lo + 1 < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (sc.item_start[mid] <= i) lo = mid;
+    else hi = mid;
+  }
+  sc.items[i] = lo;
+}
+
+// pruned execution, between the posting scan and the column pass: which queries still need the column pass, and what the
+// sparse terms the scan may have dropped could add to a doc it never met.  With the k-th score the scan left behind, the
+// non-essential terms are the longest lowest-priority prefix whose bounds sum below it; a query whose column terms are all
+// non-essential sits the column pass out (a doc without an essential term cannot enter the top k), the others look at
+// v + extra, extra = the bounds of the non-essential SPARSE terms.  Thread per ColQ.
+static __global__ void __launch_bounds__(128) slg_colq_prune_kernel(WarpBatchDev wb, StreamDev sd, ScanDev sc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *sd.n_colq) return;
+  ColQ cq = sd.colq[i];
+  const unsigned long long thr = wb.thr_key[cq.qi];
+  const uint32_t nt = (uint32_t)cq.nsp + cq.ncol;
+  float ub[kWarpMaxTerms];
+  for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
+    ub[t] = 0.0f;
+    if (t < nt) {
+      const QTerm &q = wb.qterms[(uint64_t)cq.qslot * kWarpMaxTerms + t];
+      ub[t] = __fmul_rn(sc.ut_max[q.uterm], q.weight);
+    }
+  }
+  float extra = 0.0f;
+  bool any_essential_col = false;
+  for (uint32_t t = 0; t < nt; t++) {
+    float pre = 0.0f;
+    for (uint32_t u = 0; u < nt; u++)
+      if (ub[u] < ub[t] || (ub[u] == ub[t] && u >= t)) pre += ub[u];
+    const bool ne = thr != kThrInit && pre * 1.00002f < __uint_as_float((uint32_t)(thr >> 32));
+    if (t < cq.nsp) {
+      if (ne) extra += ub[t];
+    } else if (!ne) {
+      any_essential_col = true;
+    }
+  }
+  cq.off = any_essential_col ? 0 : 1;
+  cq.extra = extra;
+  sd.colq[i] = cq;
+}
+
+template <bool PRUNE>
+__global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev seg, WarpBatchDev wb, ScanDev sc) {
+  __shared__ __align__(16) unsigned long long s_cand[kScanWarps][kWarpCand];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long *cand = s_cand[warp];
+  const uint32_t k = wb.k;
+  const uint32_t n_items = *sc.n_items;
+  unsigned long long n_scanned = 0, n_verified = 0;
+  uint32_t n_dropped = 0, n_done = 0;
+  WarpCand wc;
+
+  uint32_t item = 0;
+  if (lane == 0) item = atomicAdd(sc.counter, 1u);
+  item = __shfl_sync(0xFFFFFFFFu, item, 0);
+  while (item < n_items) {
+    uint32_t next_item = 0;
+    if (lane == 0) next_item = atomicAdd(sc.counter, 1u);
+    const uint32_t pi = __ldg(sc.order + __ldg(sc.items + item));
+    const ScanPair pr = sc.pairs[pi];
+    const unsigned long long thr0 = ld_cg_u64(wb.thr_key + pr.qi);
+    const uint32_t chunk = item - pr.first_item;
+    const bool have_thr0 = thr0 != kThrInit;
+    const float thr0_score = __uint_as_float((uint32_t)(thr0 >> 32));
+    if (PRUNE && have_thr0 && pr.ne_prefix * 1.00002f < thr0_score) {
+      n_dropped++;  // this term and everything of lower priority cannot lift a doc into the top k
+    } else {
+      n_done++;
+      wc.begin(cand, thr0, k, lane);
+      const uint32_t qslot = pr.qslot_t >> 3, t = pr.qslot_t & 7u;
+      const QTerm *qts = wb.qterms + (uint64_t)qslot * kWarpMaxTerms;
+      const uint32_t nt = __ldg(&wb.qheads[qslot].nt);
+      const float4 *sp = reinterpret_cast<const float4 *>(wb.scores + pr.base);
+      const uint32_t i0 = chunk * kScanChunk, i1 = min(pr.df, i0 + kScanChunk);
+      n_scanned += i1 - i0;
+      uint32_t cut = 0u;
+      auto recut = [&]() {
+        cut = 0u;
+        if (wc.thr != kThrInit) {
+          const float cf = __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f - pr.others * 1.00002f;
+          cut = cf > 0.0f ? __float_as_uint(cf) : 0u;
+        }
+      };
+      recut();
+#pragma unroll 1
+      for (uint32_t b = i0; b < i1; b += 256) {
+        // two 128-posting steps in flight
+        const uint32_t ia = b + lane * 4, ib = ia + 128;
+        float4 va = make_float4(0, 0, 0, 0), vb = make_float4(0, 0, 0, 0);
+        if (ia < i1) va = __ldg(sp + (ia >> 2));
+        if (ib < i1) vb = __ldg(sp + (ib >> 2));
+        float x[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        uint32_t todo = 0u;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          x[e] = __fmul_rn(x[e], pr.w);
+          const uint32_t idx = (e < 4 ? ia : ib) + (e & 3);
+          if (__float_as_uint(x[e]) >= cut && x[e] != 0.0f && idx < i1) todo |= 1u << e;  // (16-byte pieces may reach past the list's end)
+        }
+        while (__any_sync(0xFFFFFFFFu, todo != 0u)) {
+          const bool had = todo != 0u;
+          const uint32_t e = had ? __ffs(todo) - 1 : 0u;
+          todo &= todo - 1u;
+          float v = 0.0f;
+#pragma unroll
+          for (int z = 0; z < 8; z++)
+            if (e == (uint32_t)z) v = x[z];
+          bool pass = had && __float_as_uint(v) >= cut;
+          if (!__any_sync(0xFFFFFFFFu, pass)) continue;
+          uint32_t doc = 0u;
+          if (pass) doc = __ldg(seg.post_doc + pr.base + (e < 4 ? ia : ib) + (e & 3));
+          uint32_t holders = 0u;
+          n_verified += pass ? 1u : 0u;
+          const float s = verify_doc(seg, wb, qts, nt, pass, doc, holders);
+          // the doc is offered by the posting of its highest-priority holder: exhaustive — the lowest slot (every sparse list
+          // is scanned); pruned — the largest bound, ties to the lower slot (that list is never dropped while the doc matters)
+          if (pass) {
+            if (!PRUNE) {
+              pass = (holders & ((1u << t) - 1u)) == 0u;
+            } else {
+              const float my_ub = __fmul_rn(sc.ut_max[__ldg(&qts[t].uterm)], pr.w);
+              for (uint32_t hm = holders & ~(1u << t); hm && pass; hm &= hm - 1) {
+                const uint32_t u = __ffs(hm) - 1;
+                const float ub_u = __fmul_rn(sc.ut_max[__ldg(&qts[u].uterm)], __ldg(&qts[u].weight));
+                if (ub_u > my_ub || (ub_u == my_ub && u < t)) pass = false;
+              }
+            }
+          }
+          wc.offer(seg, wb, pr.qi, pr.filter, pass, doc, s);
+          recut();
+        }
+      }
+      wc.merge(wb, pr.qi);
+    }
+    item = __shfl_sync(0xFFFFFFFFu, next_item, 0);
+  }
+  if (sc.counters) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_verified += __shfl_xor_sync(0xFFFFFFFFu, n_verified, o);
+    if (lane == 0) {
+      if (n_scanned) atomicAdd(sc.counters + 0, n_scanned);
+      if (n_verified) atomicAdd(sc.counters + 4, n_verified);
+      if (n_dropped) atomicAdd(sc.counters + 5, (unsigned long long)n_dropped);
+      if (n_done) atomicAdd(sc.counters + 3, (unsigned long long)n_done);
+    }
+  }
+}
+
+}  // namespace slg

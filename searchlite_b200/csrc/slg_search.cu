@@ -302,8 +302,27 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bt->items_cap = want_items ? max_groups * n_queries : 0;
   bt->done_bytes = want_items ? (size_t)max_groups * n_queries : 0;
   const size_t o_items = want_items ? carve((size_t)bt->items_cap * sizeof(uint2)) : 0;
-  const bool want_stream = bt->can_items && exec == SLG_EXEC_BM25 && ix->stream_kernels && ix->sub_docs <= 2048;  // (posting numbers of a sub-tile fit 15 bits)
+  const bool want_stream = bt->can_items && ix->stream_kernels;
   for (auto &s : ix->segs) bt->max_cols = std::max(bt->max_cols, s->n_cols);
+  // flat posting scan: item capacity = the largest segment's sum over scanned term instances of ceil(df / kScanChunk)
+  if (bt->can_items) {
+    for (auto &sg : ix->segs) {
+      uint64_t n = 0;
+      for (size_t i = 0; i < qt_u.size(); i++) {
+        const uint32_t term = ut[qt_u[i]];
+        if (term >= sg->n_terms || !qt_f[i]) continue;
+        if (!sg->h_term_col.empty() && sg->h_term_col[term] >= 0) continue;
+        n += (sg->h_df[term] + kScanChunk - 1) / kScanChunk;
+      }
+      bt->scan_items_cap = (uint32_t)std::max<uint64_t>(bt->scan_items_cap, std::min<uint64_t>(n, 0xFFFFFFF0ull));
+    }
+  }
+  const bool want_scan = bt->can_items;
+  const size_t o_utmax = want_scan ? carve((size_t)std::max(bt->U, 1u) * 4) : 0;
+  const size_t o_pairs = want_scan ? carve((size_t)n_queries * kWarpMaxTerms * sizeof(ScanPair)) : 0;
+  const size_t o_order = want_scan ? carve((size_t)n_queries * kWarpMaxTerms * 4) : 0;
+  const size_t o_istart = want_scan ? carve(((size_t)n_queries * kWarpMaxTerms + 1) * 4) : 0;
+  const size_t o_sitems = want_scan ? carve((size_t)std::max(bt->scan_items_cap, 1u) * 4) : 0;
   const size_t o_colq = want_stream ? carve((size_t)n_queries * sizeof(ColQ)) : 0;
   const size_t o_ucol = want_stream ? carve((size_t)(bt->max_cols + 1) * 4) : 0;
   const size_t o_colslot = want_stream ? carve((size_t)(bt->max_cols + 1) * 4) : 0;
@@ -330,6 +349,11 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bt->qheads = bt->use_warp ? reinterpret_cast<QHead *>(base + o_qheads) : nullptr;
   bt->items = want_items ? reinterpret_cast<uint2 *>(base + o_items) : nullptr;
   bt->done = want_items ? base + o_done : nullptr;
+  bt->ut_max = want_scan ? reinterpret_cast<float *>(base + o_utmax) : nullptr;
+  bt->scan_pairs = want_scan ? reinterpret_cast<ScanPair *>(base + o_pairs) : nullptr;
+  bt->scan_order = want_scan ? reinterpret_cast<uint32_t *>(base + o_order) : nullptr;
+  bt->scan_item_start = want_scan ? reinterpret_cast<uint32_t *>(base + o_istart) : nullptr;
+  bt->scan_items = want_scan ? reinterpret_cast<uint32_t *>(base + o_sitems) : nullptr;
   bt->colq = want_stream ? reinterpret_cast<ColQ *>(base + o_colq) : nullptr;
   bt->ucol = want_stream ? reinterpret_cast<uint32_t *>(base + o_ucol) : nullptr;
   bt->col_slot = want_stream ? reinterpret_cast<uint32_t *>(base + o_colslot) : nullptr;
@@ -385,8 +409,10 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
   const bool prune = bt->exec != SLG_EXEC_BM25;
   const uint32_t Q = bt->Q, k = bt->k;
   const bool run_items = bt->can_items && !bt->want_stats;
+  // flat posting scan + column pass: the automatic choice; scan_kernels 0 keeps the sub-tile kernels (stream / items)
+  const bool run_scan = run_items && ix->scan_kernels && bt->colq != nullptr && !(ix->strict_accumulate && !prune);
   const bool two_step = !(do_seeds && do_sweep);
-  if (two_step && (ix->segs.size() != 1 || !run_items || !prune))
+  if (two_step && (ix->segs.size() != 1 || !run_items || !prune || run_scan))
     return fail(ix, SLG_ERR_UNSUPPORTED, "the two-step run (seeds, threshold exchange, sweep) needs one segment per handle, a pruned execution and the items kernel");
   unsigned char *dp = bt->d_pack;
   size_t smem = 0;
@@ -510,7 +536,12 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       slg_reset_state_kernel<<<(n_reset + 255) / 256, 256, 0, st>>>(bd.thr_key, Q, reinterpret_cast<uint32_t *>(bt->state),
                                                                     (uint32_t)(bt->state_bytes / 4));
       count_launch(ix);
-      if (score) {
+      if (score && run_scan) {
+        // no doc-range plan: the scan walks whole lists and looks terms up by binary search
+        slg_build_qterms_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, bd, bt->qterms, bt->qheads, bt->canonical, true);
+        count_launch(ix);
+        SLG_CUDA(ix, cudaGetLastError());
+      } else if (score) {
         const uint64_t n2 = (uint64_t)bt->U * bd.n_tiles;
         // every unique term: short lists are walked once, long lists take one binary search per boundary.  The items
         // kernel never walks the postings of a column term, so their rows are not planned for it.
@@ -532,8 +563,8 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
         }
         SLG_CUDA(ix, cudaGetLastError());
       }
-      SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));
-      if (score && run_items && prune) {
+      if (!(score && run_scan)) SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));
+      if (score && run_items && prune && !run_scan) {
         // ---- seeds: every query's best items first ----
         SLG_CUDA(ix, cudaMemsetAsync(bt->done, 0, (size_t)wb.n_groups * Q, st));
         const int sgrid = (int)std::min<uint32_t>((uint32_t)ix->n_sm * 3u, (Q + warps - 1) / warps);
@@ -541,10 +572,64 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
         count_launch(ix);
       }
     }
-    const bool run_stream = run_items && !prune && bt->colq != nullptr;
+    const bool run_stream = run_items && !prune && bt->colq != nullptr && !run_scan && bt->plan_docs <= 2048;  // (posting numbers of a sub-tile fit 15 bits)
+    if (do_sweep && score && run_scan) {
+      ScanDev sc{};
+      sc.ut_term = bd.ut_term;
+      sc.ut_max = bt->ut_max;
+      sc.pairs = bt->scan_pairs;
+      sc.order = bt->scan_order;
+      sc.n_pairs = bt->work_counter + 5;
+      sc.n_items = bt->work_counter + 6;
+      sc.item_start = bt->scan_item_start;
+      sc.items = bt->scan_items;
+      sc.items_cap = bt->scan_items_cap;
+      sc.counter = bt->work_counter + 7;
+      sc.counters = bt->item_counters;
+      StreamDev sdv{};
+      sdv.colq = bt->colq;
+      sdv.n_colq = bt->work_counter + 3;
+      sdv.ucol = bt->ucol;
+      sdv.n_ucol = bt->work_counter + 4;
+      sdv.col_slot = bt->col_slot;
+      sdv.sparse_counter = bt->work_counter + 1;
+      sdv.col_counter = bt->work_counter + 2;
+      sdv.stage_cap = ix->stage_cap;
+      sdv.strict = 0;
+      sdv.counters = bt->item_counters;
+      slg_term_max_kernel<<<(bt->U * 32 + 255) / 256, 256, 0, st>>>(s->dev, sc, bt->U);
+      slg_scan_pairs_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, wb, sc);
+      slg_scan_order_kernel<<<1, 1024, 0, st>>>(wb, sc);
+      if (bt->scan_items_cap) slg_scan_items_kernel<<<(bt->scan_items_cap + 255) / 256, 256, 0, st>>>(sc);
+      for (int i = 0; i < 4; i++) count_launch(ix);
+      SLG_CUDA(ix, cudaGetLastError());
+      SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));  // (the scoring time of this path starts here)
+      SLG_CUDA(ix, launch_scan(prune, s->dev, wb, sc, ix->n_sm * 8, st));
+      count_launch(ix);
+      if (s->n_cols) {
+        slg_colgroups_kernel<<<1, 1024, 0, st>>>(s->dev, wb, sdv, s->n_cols);
+        count_launch(ix);
+        if (prune) {
+          slg_colq_prune_kernel<<<(Q + 127) / 128, 128, 0, st>>>(wb, sdv, sc);
+          count_launch(ix);
+        }
+        SLG_CUDA(ix, cudaGetLastError());
+        sdv.n_smax = std::min(s->n_cols, kColMaxSlots);
+        const size_t fixed = column_smem(0, sdv.n_smax);
+        const size_t budget = ix->smem_optin > fixed + 2048 ? ix->smem_optin - fixed - 2048 : 0;
+        sdv.col_resident = (uint32_t)std::min<size_t>(s->n_cols, budget / (2 * kColBlock * 4));
+        const size_t csmem = column_smem(sdv.col_resident, sdv.n_smax);
+        const uint32_t n_cblocks = (s->doc_count + kColBlock - 1) / kColBlock;
+        SLG_CUDA(ix, launch_score_columns(prune, s->dev, wb, sdv, csmem, (int)std::min<uint32_t>((uint32_t)ix->n_sm, n_cblocks), st));
+        count_launch(ix);
+      }
+      ix->ctr.score_launches++;
+    }
     if (do_sweep) {
       // ---- scoring ----
-      if (score && run_stream) {
+      if (score && run_scan) {
+        // (launched above)
+      } else if (score && run_stream) {
         // exhaustive: sparse pass (staged posting runs), then column pass (queries grouped by their first column)
         StreamDev sdv{};
         sdv.colq = bt->colq;
@@ -736,7 +821,7 @@ int32_t slg_batch_fetch(slg_batch_t *bt, slg_hit_t *out_hits, uint32_t *out_coun
   SLG_CUDA(ix, cudaSetDevice(ix->device));
   cudaStream_t st = ix->stream;
   static_assert(sizeof(slg_hit_t) == sizeof(HitDev), "hit layout");
-  const size_t hb = (size_t)bt->Q * bt->k * sizeof(slg_hit_t), cb = (size_t)bt->Q * 4, sb = (size_t)bt->Q * 40 + 32;
+  const size_t hb = (size_t)bt->Q * bt->k * sizeof(slg_hit_t), cb = (size_t)bt->Q * 4, sb = (size_t)bt->Q * 40 + 64;
   unsigned char *pin = static_cast<unsigned char *>(bt->pinned) + bt->pinned_result_off;
   SLG_CUDA(ix, cudaMemcpyAsync(pin, result_block(bt), hb + cb, cudaMemcpyDeviceToHost, st));
   SLG_CUDA(ix, cudaMemcpyAsync(pin + bt->result_stride, bt->stats, sb, cudaMemcpyDeviceToHost, st));
@@ -750,6 +835,8 @@ int32_t slg_batch_fetch(slg_batch_t *bt, slg_hit_t *out_hits, uint32_t *out_coun
   ix->ctr.last_subtiles_skipped = ic[1];
   ix->ctr.last_column_blocks_streamed = ic[2];
   ix->ctr.last_items = ic[3];
+  ix->ctr.last_postings_verified = ic[4];
+  ix->ctr.last_items_dropped = ic[5];
   if (out_stats) {
     for (uint32_t q = 0; q < bt->Q; q++) {
       out_stats[q].scored_docs = sv[q * 4 + 0];

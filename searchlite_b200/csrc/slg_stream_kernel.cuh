@@ -45,11 +45,14 @@ constexpr int kSparseWarps = 4;          // warps per CTA of the sparse pass
 constexpr int kColWarps = 16;            // warps per CTA of the column pass
 constexpr uint32_t kColMaxSlots = 4096;  // used columns whose block maximum is kept (beyond: always looked at per doc)
 
-struct __align__(16) ColQ {  // one query with >= 1 column term (32 B)
+struct __align__(16) ColQ {  // one query with >= 1 column term (48 B)
   uint32_t qslot, qi;
   int32_t filter;
-  uint8_t nsp, ncol, unit_w, pad;  // slots [0, nsp) sparse, [nsp, nsp + ncol) columns; unit_w: every column weight is 1.0
+  uint8_t nsp, ncol, unit_w, off;  // slots [0, nsp) sparse, [nsp, nsp + ncol) columns; unit_w: every column weight is 1.0;
+                                   // off: the query sits this pass out (pruned: no column term of it is essential)
   uint16_t slot[8];                // used-column slots of the column terms, slot order
+  float extra;                     // pruned: what the sparse terms a doc may still hold unseen can add (their bounds)
+  uint32_t pad[3];
 };
 
 struct StreamDev {
@@ -105,7 +108,9 @@ static __global__ void __launch_bounds__(1024) slg_colgroups_kernel(SegmentDev s
     r.nsp = 0;
     r.ncol = 0;
     r.unit_w = 1;
-    r.pad = 0;
+    r.off = 0;
+    r.extra = 0.0f;
+    r.pad[0] = r.pad[1] = r.pad[2] = 0;
     for (int i = 0; i < 8; i++) r.slot[i] = 0;
     for (uint32_t t = 0; t < h.nt; t++) {
       const QTerm &q = wb.qterms[(uint64_t)slot * kWarpMaxTerms + t];
@@ -119,6 +124,23 @@ static __global__ void __launch_bounds__(1024) slg_colgroups_kernel(SegmentDev s
     }
     if (r.ncol) sd.colq[atomicAdd(sd.n_colq, 1u)] = r;
   }
+}
+
+// the 64 keys of the warp's buffer are sorted (descending, zeros last): drop repeated keys, return the number of keys left.
+// The same doc can be offered twice with the same exact score when two passes (or two of its postings) both find it.
+__device__ __forceinline__ uint32_t warp_dedupe64(unsigned long long *a, int lane) {
+  const unsigned long long x0 = a[lane], x1 = a[lane + 32];
+  const unsigned long long p0 = lane ? a[lane - 1] : ~0ull, p1 = a[lane + 31];
+  const bool k0 = x0 != 0ull && x0 != p0, k1 = x1 != 0ull && x1 != p1;
+  const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, k0), b1 = __ballot_sync(0xFFFFFFFFu, k1);
+  const uint32_t lt = (1u << lane) - 1u, n0 = __popc(b0), n = n0 + __popc(b1);
+  __syncwarp();
+  if (k0) a[__popc(b0 & lt)] = x0;
+  if (k1) a[n0 + __popc(b1 & lt)] = x1;
+  __syncwarp();
+  for (uint32_t z = n + lane; z < kWarpCand; z += 32) a[z] = 0ull;
+  __syncwarp();
+  return n;
 }
 
 // ---- the warp's candidate buffer: push_top_k (query/wand.rs:905-916) ------------------------------------------
@@ -147,7 +169,7 @@ struct WarpCand {
       for (uint32_t z = cnt + lane; z < kWarpCand; z += 32) cand[z] = 0ull;
       __syncwarp();
       warp_sort64_desc(cand, lane);
-      cnt = min(cnt, k);
+      cnt = min(warp_dedupe64(cand, lane), k);
       if (cnt == k) thr = max(thr, cand[k - 1]);
       __syncwarp();
     }
@@ -180,7 +202,7 @@ struct WarpCand {
       for (uint32_t z = total + lane; z < kWarpCand; z += 32) cand[z] = 0ull;
       __syncwarp();
       warp_sort64_desc(cand, lane);
-      total = min(total, k);
+      total = min(warp_dedupe64(cand, lane), k);
       if (lane < (int)total) st_cg_u64(gk + lane, cand[lane]);
       __threadfence();
       __syncwarp();
@@ -703,6 +725,43 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
   }
 }
 
+// exact score of one doc per lane: every term of the query in slot order (brute_force on the doc's lists).  holders: bit u set
+// when sparse term u holds the doc.
+__device__ __forceinline__ float verify_doc(const SegmentDev &seg, const WarpBatchDev &wb, const QTerm *qts, uint32_t nt, bool have, uint32_t doc,
+                                            uint32_t &holders) {
+  float s = 0.0f;
+  holders = 0u;
+  if (have) {
+    for (uint32_t u = 0; u < nt; u++) {
+      const uint32_t flags = __ldg(&qts[u].flags);
+      if (!(flags & 1u)) continue;
+      float c = 0.0f;
+      if (flags & 4u) {
+        c = __ldg(seg.cols + __ldg(&qts[u].sc_base) + doc);
+      } else {
+        const uint32_t term = __ldg(&qts[u].term);
+        if (term < seg.n_terms) {
+          const uint64_t base = __ldg(&qts[u].base);
+          const uint32_t *dp = seg.post_doc + base;
+          const uint32_t end = __ldg(seg.term_df + term);
+          uint32_t lo = 0, hi = end;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(dp + mid) < doc) lo = mid + 1;
+            else hi = mid;
+          }
+          if (lo < end && __ldg(dp + lo) == doc) {
+            c = __ldg(wb.scores + base + lo);
+            holders |= 1u << u;
+          }
+        }
+      }
+      if (c != 0.0f) s = __fadd_rn(s, __fmul_rn(c, __ldg(&qts[u].weight)));
+    }
+  }
+  return s;
+}
+
 // ---- column pass -----------------------------------------------------------------------------------------------
 // shared memory: buf f32[2][resident][kColBlock] | smax f32[n_smax] | cand u64[kColWarps][64] | bar u64[2]
 __host__ __device__ inline size_t column_smem(uint32_t resident, uint32_t n_smax) {
@@ -778,11 +837,11 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(Segme
         thr = ld_cg_u64(wb.thr_key + cq.qi);
       }
       bool look = false;
-      if (live) {
+      if (live && !cq.off) {
         n_tests++;
         // one column: the maximum over the block of c * w is max(c) * w, the comparison of every doc collapses into one.
-        // Several columns: the exhaustive execution sums them per doc; a pruned one first asks the sum of the maxima
-        // (same slot order, every operation monotone: it dominates every doc's sum).
+        // Several columns: the sum of the maxima (same slot order, every operation monotone) dominates every doc's sum; the
+        // strict exhaustive execution sums them per doc regardless.  extra (pruned): what unseen sparse terms could add.
         float bound = 0.0f;
         bool known = true;
         if (PRUNE || !sd.strict || cq.ncol == 1)
@@ -793,6 +852,7 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(Segme
           }
         else known = false;
         const uint32_t thr_bits = thr == kThrInit ? 0u : (uint32_t)(thr >> 32);
+        if (PRUNE && cq.extra > 0.0f) bound = (bound + cq.extra) * 1.00002f;
         look = !known || (bound != 0.0f && __float_as_uint(bound) >= thr_bits);
       }
       uint32_t hits = __ballot_sync(0xFFFFFFFFu, look);
@@ -830,6 +890,8 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(Segme
         const uint32_t unit_w = __shfl_sync(0xFFFFFFFFu, (uint32_t)cq.unit_w, g);
         const int32_t filter = __shfl_sync(0xFFFFFFFFu, cq.filter, g);
         const unsigned long long qthr = __shfl_sync(0xFFFFFFFFu, thr, g);
+        const float extra = PRUNE ? __shfl_sync(0xFFFFFFFFu, cq.extra, g) : 0.0f;
+        const uint32_t nt = nsp + ncol;
         const uint32_t s01 = __shfl_sync(0xFFFFFFFFu, (uint32_t)cq.slot[0] | ((uint32_t)cq.slot[1] << 16), g);
         const uint32_t s23 = __shfl_sync(0xFFFFFFFFu, (uint32_t)cq.slot[2] | ((uint32_t)cq.slot[3] << 16), g);
         const uint32_t s45 = __shfl_sync(0xFFFFFFFFu, (uint32_t)cq.slot[4] | ((uint32_t)cq.slot[5] << 16), g);
@@ -855,7 +917,14 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(Segme
             v[x].w = __fadd_rn(v[x].w, __fmul_rn(c.w, w));
           }
         }
-        uint32_t cut = qthr == kThrInit ? 0u : (uint32_t)(qthr >> 32);
+        // v can enter the top k when v (+ extra) reaches the k-th score
+        auto cut_of = [&](unsigned long long th) {
+          if (th == kThrInit) return 0u;
+          if (!(PRUNE && extra > 0.0f)) return (uint32_t)(th >> 32);
+          const float cf = __uint_as_float((uint32_t)(th >> 32)) * 0.99998f - extra * 1.00002f;
+          return cf > 0.0f ? __float_as_uint(cf) : 0u;
+        };
+        uint32_t cut = cut_of(qthr);
         uint32_t mx = 0u;
 #pragma unroll
         for (uint32_t x = 0; x < kColBlock / 128; x++)
@@ -872,41 +941,30 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(Segme
             if (bx[e] >= cut && bx[e] != 0u && d0 + x * 128 + lane * 4 + e < seg.doc_count) todo |= 1u << (x * 4 + e);
         }
         while (__any_sync(0xFFFFFFFFu, todo != 0u)) {
-          {
-            const uint32_t el = todo ? __ffs(todo) - 1 : 0u;
-            const bool had = todo != 0u;
-            todo &= todo - 1u;
-            uint32_t bits = 0u;
+          const uint32_t el = todo ? __ffs(todo) - 1 : 0u;
+          const bool had = todo != 0u;
+          todo &= todo - 1u;
+          uint32_t bits = 0u;
 #pragma unroll
-            for (uint32_t x = 0; x < kColBlock / 128; x++) {
-              if (el == x * 4 + 0) bits = __float_as_uint(v[x].x);
-              if (el == x * 4 + 1) bits = __float_as_uint(v[x].y);
-              if (el == x * 4 + 2) bits = __float_as_uint(v[x].z);
-              if (el == x * 4 + 3) bits = __float_as_uint(v[x].w);
-            }
-            const uint32_t doc = d0 + (el >> 2) * 128 + lane * 4 + (el & 3u);
-            cut = wc.thr == kThrInit ? 0u : (uint32_t)(wc.thr >> 32);
-            bool pass = had && bits >= cut;
-            if (!__any_sync(0xFFFFFFFFu, pass)) continue;
-            if (pass && nsp) {
-              // a doc of one of the query's sparse lists belongs to the sparse pass
-              const uint32_t sub = doc / wb.sub_docs;
-              for (uint32_t t = 0; t < nsp && pass; t++) {
-                const uint32_t *row = wb.rng + (uint64_t)__ldg(&qts[t].uterm) * (wb.n_sub + 1);
-                const uint32_t *dp = seg.post_doc + __ldg(&qts[t].base);
-                uint32_t lo = __ldg(row + sub);
-                const uint32_t end = __ldg(row + sub + 1);
-                uint32_t hi = end;
-                while (lo < hi) {
-                  const uint32_t mid = (lo + hi) >> 1;
-                  if (__ldg(dp + mid) < doc) lo = mid + 1;
-                  else hi = mid;
-                }
-                if (lo < end && __ldg(dp + lo) == doc) pass = false;
-              }
-            }
-            wc.offer(seg, wb, qi, filter, pass, doc, __uint_as_float(bits));
+          for (uint32_t x = 0; x < kColBlock / 128; x++) {
+            if (el == x * 4 + 0) bits = __float_as_uint(v[x].x);
+            if (el == x * 4 + 1) bits = __float_as_uint(v[x].y);
+            if (el == x * 4 + 2) bits = __float_as_uint(v[x].z);
+            if (el == x * 4 + 3) bits = __float_as_uint(v[x].w);
           }
+          const uint32_t doc = d0 + (el >> 2) * 128 + lane * 4 + (el & 3u);
+          cut = cut_of(wc.thr);
+          bool pass = had && bits >= cut;
+          if (!__any_sync(0xFFFFFFFFu, pass)) continue;
+          float sc_exact = __uint_as_float(bits);
+          if (nsp) {
+            // exhaustive: a doc of one of the query's sparse lists was met by the posting scan.  Pruned: such a list may have
+            // been dropped as non-essential, so the doc gets its exact score here (the merge drops a key offered twice).
+            uint32_t holders = 0u;
+            sc_exact = verify_doc(seg, wb, qts, nt, pass, doc, holders);
+            if (!PRUNE && holders) pass = false;
+          }
+          wc.offer(seg, wb, qi, filter, pass, doc, sc_exact);
         }
         wc.merge(wb, qi);
       }

@@ -102,6 +102,7 @@ class Counters(C.Structure):
         ("resident_bytes", C.c_uint64), ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64),
         ("last_postings_scattered", C.c_uint64), ("last_subtiles_skipped", C.c_uint64),
         ("last_column_blocks_streamed", C.c_uint64), ("last_items", C.c_uint64),
+        ("last_postings_verified", C.c_uint64), ("last_items_dropped", C.c_uint64),
     ]
 
 

@@ -69,7 +69,7 @@ def test_struct_layouts_match_the_header():
     assert engine.STATS_DTYPE.itemsize == 40
     assert engine.FILTER_DTYPE.itemsize == 56
     assert C.sizeof(engine.SegmentView) == 80
-    assert C.sizeof(engine.Counters) == 104
+    assert C.sizeof(engine.Counters) == 120
     src = r'''
     #include "include/searchlite_gpu.h"
     #include <stdio.h>
@@ -85,7 +85,7 @@ def test_struct_layouts_match_the_header():
         exe = os.path.join(td, "s")
         subprocess.run(["gcc", "-std=c99", "-I", ROOT, "-o", exe, c], check=True, cwd=ROOT)  # the header is plain C
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [20, 72, 12, 40, 56, 80, 104, C.sizeof(engine.SegmentFiles), C.sizeof(engine.SegmentInfo), 12]
+    assert sizes == [20, 72, 12, 40, 56, 80, 120, C.sizeof(engine.SegmentFiles), C.sizeof(engine.SegmentInfo), 12]
 
 
 def test_query_batch_builders():
