@@ -1,31 +1,38 @@
 #!/usr/bin/env python
 """bench.py — BM25 top-10 queries/sec at 10 M docs on 1/2/4/8 B200 (BASELINE.json metric).
 
-Workload (config C2 of BASELINE.md §4): synthetic 10 M-doc Zipfian corpus (uniform 100..300 tokens
-per doc, 1 M-term vocabulary, seed 20260101), a batch of 4096 two-to-five-term OR queries
-(seed 20260102), top-10 (internal k = 11), k1 = 0.9, b = 0.4.  The corpus is generated on the GPU
-(searchlite_b200.synth) and loaded once into the engine's HBM-resident layout; a "step" is one
-pass of the whole 4096-query batch.
+Default workload = configs[1] of BASELINE.json (C2): synthetic 10 M-doc Zipfian corpus (uniform 100..300 tokens per doc,
+1 M-term vocabulary, seed 20260101), a batch of 4096 two-to-five-term OR queries (seed 20260102), top-10 (internal
+k = 11) WITH BLOCK-MAX PRUNING (`execution = bmw`: exact, byte-identical to the exhaustive result), k1 = 0.9, b = 0.4.
+The corpus is generated on the GPU (searchlite_b200.synth) and loaded once into the engine's HBM-resident layout; a
+"step" is one pass of the whole 4096-query batch.
 
-  value      queries/sec with the prepared batch already resident in HBM (slg_batch_run)
+  value      queries/sec with the prepared batch already resident in HBM (slg_batch_run), headline execution
   e2e        queries/sec through slg_search_batch with HOST query structs in and HOST hits out
              (H2D of the packed batch + all kernels + D2H of the hits inside the timed region)
-  roofline   scoring kernel: algorithmic posting bytes (5 B x sum of df over query terms) / its
-             CUDA-event time, against the measured HBM copy bandwidth
-  cpu_baseline  the oracle ("port" of the reference CPU path) on a bounded sample of the same
-             queries on the host cores, with a parity check of the GPU results against it
+  exhaustive the same batch under `execution = bm25` (every posting read and compared): value, e2e, kernel time
+  roofline   the exhaustive scoring kernels: algorithmic posting bytes (5 B x sum of df over query terms)
+             / their CUDA-event time, against the measured HBM copy bandwidth
+  pruned     work counters of the pruned run: postings scanned / verified, items dropped, speed-up over exhaustive
+  parity     EVERY query of the batch against the oracle's exact top-k (at N > 1: against the oracle's per-segment
+             results merged in SortKey order), plus byte-identity of the pruned and exhaustive results
+  cpu_baseline  the oracle ("port" of the reference CPU path) timed on the host cores on the same queries
 
-N > 1 (torchrun): the corpus is split into N contiguous doc-range segments, one per rank; every
-rank scores all queries on its segment, one NCCL all-gather exchanges the local top-k and every
-rank merges (strong scaling: total corpus fixed).
+N > 1 (torchrun): the corpus is split into N contiguous doc-range segments, one per rank; every rank scores all
+queries on its segment, ONE NCCL all-gather exchanges the packed local top-k blocks and every rank merges (strong
+scaling: total corpus fixed).
 
-`--impl reference` times the reference's own CPU algorithm (oracle restatement, faithful mode:
-per-query varint decode + doc-length vector + WAND, the reference's default execution) on the
-host cores; rank 0 only.
+Other configurations (`--config`): c3 (8.84 M short passages, top-1000, bmw), c4 (Bool{must} / phrase-free AND queries
+behind And[KeywordEq(lang), I64Range(year)] at 50 / 10 / 1 % selectivity), c5 (BM25 top-1000 -> exact 768-d bf16
+rerank, docs sharded over the ranks).  They print the same JSON line shape with their own `config.workload`.
+
+`--impl reference` times the reference's own CPU algorithm (oracle restatement, faithful mode: per-query varint
+decode + doc-length vector + WAND, the reference's default execution) on the host cores; rank 0 only.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -45,21 +52,29 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--docs", type=int, default=10_000_000)
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--docs", type=int, default=0, help="0 = the configuration's size")
     ap.add_argument("--vocab", type=int, default=1_000_000)
-    ap.add_argument("--queries", type=int, default=4096)
-    ap.add_argument("--limit", type=int, default=10)
-    ap.add_argument("--execution", default="bm25", choices=["bm25", "wand", "bmw"])
+    ap.add_argument("--queries", type=int, default=0, help="0 = the configuration's batch")
+    ap.add_argument("--limit", type=int, default=0, help="0 = the configuration's limit")
+    ap.add_argument("--execution", default="bmw", choices=["bm25", "wand", "bmw"])
     ap.add_argument("--tile-docs", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--sub-docs", type=int, default=0)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "cta", "warp", "reg", "warp-inplace", "auto-inplace"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "cta", "warp", "items", "reg", "warp-inplace", "auto-inplace"])
     ap.add_argument("--option", action="append", default=[], help="engine residency option name=value (slg_set_option)")
-    ap.add_argument("--cpu-sample", type=int, default=256, help="queries in the CPU baseline sample (0 = skip)")
+    ap.add_argument("--cpu-sample", type=int, default=-1, help="queries checked against / timed on the CPU oracle (-1 = all, 0 = skip)")
     ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-pruned", action="store_true", help="skip the extra timing of the block-max pruned execution")
-    return ap.parse_args()
+    ap.add_argument("--no-exhaustive", action="store_true", help="skip the exhaustive (bm25) leg and its roofline")
+    ap.add_argument("--no-pruned", action="store_true", help=argparse.SUPPRESS)  # (round-1 flag: same as --no-exhaustive)
+    args = ap.parse_args()
+    cfg = {"c2": (10_000_000, 4096, 10), "c3": (8_841_823, 1024, 1000), "c4": (10_000_000, 4096, 10), "c5": (0, 1024, 10)}[args.config]
+    args.docs = args.docs or cfg[0]
+    args.queries = args.queries or cfg[1]
+    args.limit = args.limit or cfg[2]
+    args.no_exhaustive = args.no_exhaustive or args.no_pruned
+    return args
 
 
 def read_peaks():
@@ -71,6 +86,29 @@ def read_peaks():
         return 6650.0, "fallback"
 
 
+def kernel_source_hash() -> str:
+    """hash of the CUDA sources: a DRAM-traffic figure taken with ncu is only reported next to the kernels it was taken from"""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "searchlite_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(kernel_key: str):
+    """(bytes per launch, source) from profiles/traffic.json when it was captured from THIS build of the kernels, else (None, why)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+    except Exception:
+        return None, "no ncu capture recorded for this build"
+    e = t.get(kernel_key)
+    if not e or e.get("source_hash") != kernel_source_hash():
+        return None, "the recorded ncu capture belongs to an older build of the kernels"
+    return float(e["dram_bytes"]), e.get("file")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -80,7 +118,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -118,18 +156,25 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_corpus(args, rank: int, world: int, device):
-    """this rank's segment of the C2 corpus (contiguous doc range), generated on `device`"""
+# ---- workloads ---------------------------------------------------------------------------------------------------
+def corpus_spec(args, rank: int, world: int):
     from searchlite_b200 import synth
     from searchlite_b200.shard import shard_ranges
     lo, hi = shard_ranges(args.docs, world)[rank]
-    spec = synth.CorpusSpec(n_docs=hi - lo, vocab=args.vocab, seed=20260101, segment_ord=rank, doc_base=lo)
-    seg = synth.generate_segment(spec, device)
-    qb = synth.generate_queries(args.queries, args.vocab, seed=20260102)
-    return seg, qb
+    if args.config == "c3":  # MS-MARCO-passage-like: short docs (8..104 tokens, mean 56)
+        return synth.CorpusSpec(n_docs=hi - lo, vocab=args.vocab, seed=20260103, len_lo=8, len_hi=104, segment_ord=rank, doc_base=lo)
+    return synth.CorpusSpec(n_docs=hi - lo, vocab=args.vocab, seed=20260101, segment_ord=rank, doc_base=lo)
+
+
+def query_batch(args):
+    from searchlite_b200 import synth
+    return synth.generate_queries(args.queries, args.vocab, seed=20260104 if args.config == "c3" else 20260102)
 
 
 def workload_name(args, world: int) -> str:
+    if args.config == "c3":
+        return (f"C3: synthetic {args.docs / 1e6:g}M-passage Zipf(s=1) corpus, uniform 8..104 tokens/doc (mean 56), {args.vocab / 1e6:g}M-term vocab, "
+                f"{args.queries} OR queries of 2-5 terms, top-{args.limit} (k={args.limit + 1}), k1=0.9 b=0.4, {world} doc-range segment(s)")
     return (f"C2: synthetic {args.docs / 1e6:g}M-doc Zipf(s=1) corpus, uniform 100..300 tokens/doc, {args.vocab / 1e6:g}M-term vocab, "
             f"{args.queries} OR queries of 2-5 terms, top-{args.limit} (k={args.limit + 1}), k1=0.9 b=0.4, "
             f"{world} doc-range segment(s)")
@@ -144,21 +189,18 @@ def run_reference(args, rank: int, world: int):
     slo.build()
     t0 = time.time()
     device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
-    # the reference arm searches the whole corpus as ONE segment per rank-equivalent; at N>1 it still
-    # times the same bounded sample over the full corpus split into `world` segments, sequentially,
-    # as IndexReader::search does (api/reader.rs:2670)
+    # the reference arm searches the corpus split into `world` segments sequentially, as IndexReader::search does
+    # (api/reader.rs:2670), on a bounded sample of the batch per step
     from searchlite_b200 import synth
-    from searchlite_b200.shard import shard_ranges
     oracles = []
-    for r, (lo, hi) in enumerate(shard_ranges(args.docs, world)):
-        spec = synth.CorpusSpec(n_docs=hi - lo, vocab=args.vocab, seed=20260101, segment_ord=r, doc_base=lo)
-        seg = synth.generate_segment(spec, device).to_host()
+    for r in range(world):
+        seg = synth.generate_segment(corpus_spec(args, r, world), device).to_host()
         if device.type == "cuda":
             torch.cuda.empty_cache()
         o = slo.OracleIndex(seg)
         o.build_post_image()
         oracles.append(o)
-    qb = synth.generate_queries(args.queries, args.vocab, seed=20260102)
+    qb = query_batch(args)
     k = args.limit + 1
     threads = slo.max_threads()
     sample = min(args.ref_sample, args.queries)
@@ -182,7 +224,7 @@ def run_reference(args, rank: int, world: int):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, world), "execution": "wand (reference default)",
-                   "step": f"{sample} queries per step (bounded sample of the 4096-query batch)"},
+                   "step": f"{sample} queries per step (bounded sample of the {args.queries}-query batch)"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} queries/step, faithful mode: per-query varint decode of every term list + per-query "
                                    f"doc-length vector + WAND (oracle restatement; the Rust reference cannot be built here)"},
@@ -200,10 +242,14 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, max(world, args.gpus if world == 1 else world))
         return
+    if args.config in ("c4", "c5"):
+        from tools import bench_configs
+        bench_configs.main(args, rank, local_rank, world)
+        return
 
     import torch
     import torch.distributed as dist
-    from searchlite_b200 import GpuIndex
+    from searchlite_b200 import GpuIndex, synth
     from searchlite_b200.shard import ShardedSearcher
 
     if not torch.cuda.is_available():
@@ -215,7 +261,8 @@ def main():
     k = args.limit + 1
 
     t0 = time.time()
-    seg, qb = build_corpus(args, rank, world, device)
+    seg = synth.generate_segment(corpus_spec(args, rank, world), device)
+    qb = query_batch(args)
     torch.cuda.synchronize()
     gen_s = time.time() - t0
     t0 = time.time()
@@ -225,136 +272,100 @@ def main():
     gi.load_segment(seg)
     load_s = time.time() - t0
     n_postings = gi.segment_stats(rank)["n_postings"]
-    host_seg = None
-    if rank == 0 and world == 1 and args.cpu_sample > 0:
-        host_seg = seg.to_host()
     del seg
     torch.cuda.empty_cache()
 
     stream = torch.cuda.ExternalStream(gi.stream_ptr(), device=device)
     searcher = ShardedSearcher(gi, args.queries, k) if world > 1 else None
-    prepared = gi.prepare(qb, k, args.execution)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        prepared.run(sync=True)
+    def max_over_ranks(ms: float) -> float:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
         if world > 1:
-            return searcher.exchange_and_merge(prepared)
-        return None
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- value: batch resident in HBM ----
-    for _ in range(args.warmup):
-        step_resident()
-    barrier()
-    c0 = gi.counters()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for _ in range(args.steps):
-            step_resident()
-        ev1.record(stream)
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    c1 = gi.counters()
-    ms_total = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    score_launches = c1["score_launches"] - c0["score_launches"]
-    score_ms = (c1["score_ms_total"] - c0["score_ms_total"]) / max(score_launches, 1)
-    launches = (c1["kernel_launches"] - c0["kernel_launches"])
-    posting_count = c1["last_posting_count"]
+    def time_resident(execution: str):
+        """(ms per step, kernel ms, launches per step, results, counters) of one execution with the batch resident"""
+        p = gi.prepare(qb, k, execution)
 
-    # ---- e2e: host buffers in and out through the C ABI ----
-    e2e = None
-    if not args.no_e2e:
-        def step_e2e():
-            if world == 1:
-                return gi.search_batch(qb, k, args.execution)
-            p = gi.prepare(qb, k, args.execution)
+        def step():
+            if world > 1:
+                return searcher.run(p)
             p.run(sync=True)
-            out = searcher.exchange_and_merge(p)
+            return None
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        c0 = gi.counters()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(args.steps):
+                step()
+            ev1.record(stream)
+        barrier()
+        c1 = gi.counters()
+        ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+        n_score = max(c1["score_launches"] - c0["score_launches"], 1)
+        kernel_ms = (c1["score_ms_total"] - c0["score_ms_total"]) / n_score
+        launches = (c1["kernel_launches"] - c0["kernel_launches"]) / args.steps
+        p.run(sync=True)
+        res = searcher.exchange_and_merge(p) if world > 1 else p.fetch()
+        ctr = gi.counters()
+        p.free()
+        return ms, kernel_ms, launches, res, ctr
+
+    def time_e2e(execution: str):
+        def step():
+            if world == 1:
+                return gi.search_batch(qb, k, execution)
+            p = gi.prepare(qb, k, execution)
+            out = searcher.run(p)
             p.free()
             return out
         for _ in range(max(1, args.warmup)):
-            step_e2e()
+            step()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         with torch.cuda.stream(stream):
             e0.record(stream)
             for _ in range(args.steps):
-                last = step_e2e()
+                step()
             e1.record(stream)
         barrier()
         wall_ms = 1e3 * (time.perf_counter() - w0)
-        dev_ms = e0.elapsed_time(e1)
-        te = torch.tensor([max(dev_ms, wall_ms)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / args.steps
         cc = gi.counters()
-        e2e_ms = float(te.item()) / args.steps
-        e2e = {"value": args.queries / (e2e_ms / 1e3), "unit": "queries/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(cc["last_h2d_bytes"]), "d2h_bytes_per_step": int(cc["last_d2h_bytes"])}
+        return {"value": args.queries / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms,
+                "h2d_bytes_per_step": int(cc["last_h2d_bytes"]), "d2h_bytes_per_step": int(cc["last_d2h_bytes"])}
 
-    # results of the resident path for the parity check
-    prepared.run(sync=True)
-    got_h, got_c = (searcher.exchange_and_merge(prepared) if world > 1 else prepared.fetch())
+    # ---- headline execution ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_step, kernel_ms, launches, (got_h, got_c), ctr = time_resident(args.execution)
+    clocks = sampler.stop() if sampler else None
+    e2e = None if args.no_e2e else time_e2e(args.execution)
 
-    # ---- the same batch with block-max pruning (configs[1] names it): exact result, fewer postings scored ----
-    pruned = None
-    if args.execution == "bm25" and not args.no_pruned:
-        pp = gi.prepare(qb, k, "bmw")
-
-        def step_pruned():
-            pp.run(sync=True)
-            return searcher.exchange_and_merge(pp) if world > 1 else None
-        for _ in range(args.warmup):
-            step_pruned()
-        barrier()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            p0.record(stream)
-            for _ in range(args.steps):
-                step_pruned()
-            p1.record(stream)
-        barrier()
-        tp = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-        pr_ms = float(tp.item()) / args.steps
-        pp.run(sync=True)
-        pr_h, pr_c = (searcher.exchange_and_merge(pp) if world > 1 else pp.fetch())
-        pruned = {"execution": "bmw", "value": args.queries / (pr_ms / 1e3), "unit": "queries/s", "ms_per_step": pr_ms,
-                  "speedup_vs_exhaustive": ms_step / pr_ms,
-                  "identical_to_exhaustive": bool(pr_h.tobytes() == got_h.tobytes() and pr_c.tobytes() == got_c.tobytes())}
-        if world == 1 and not args.no_e2e:
-            for _ in range(max(1, args.warmup)):
-                gi.search_batch(qb, k, "bmw")
-            torch.cuda.synchronize()
-            w0 = time.perf_counter()
-            for _ in range(args.steps):
-                gi.search_batch(qb, k, "bmw")
-            torch.cuda.synchronize()
-            pe_ms = 1e3 * (time.perf_counter() - w0) / args.steps
-            pruned["e2e"] = {"value": args.queries / (pe_ms / 1e3), "unit": "queries/s", "ms_per_step": pe_ms}
-        pp.free()
-
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+    # ---- exhaustive leg: roofline of the scoring kernels, and the result the pruned run must reproduce byte for byte ----
+    exhaustive = None
+    ex_h = ex_c = None
+    if args.execution != "bm25" and not args.no_exhaustive:
+        x_ms, x_kernel_ms, x_launches, (ex_h, ex_c), x_ctr = time_resident("bm25")
+        exhaustive = {"execution": "bm25", "value": args.queries / (x_ms / 1e3), "unit": "queries/s", "ms_per_step": x_ms,
+                      "kernel_ms": x_kernel_ms, "gpu_launches": x_launches,
+                      "postings_scanned": int(x_ctr["last_postings_scattered"]), "postings_verified": int(x_ctr["last_postings_verified"])}
+        if not args.no_e2e:
+            exhaustive["e2e"] = time_e2e("bm25")
+    elif args.execution == "bm25":
+        x_kernel_ms, x_ctr = kernel_ms, ctr
 
     hbm_peak, peak_kind = read_peaks()
-    alg_bytes = 5.0 * posting_count
-    achieved = alg_bytes / (score_ms / 1e3) / 1e9 if score_ms > 0 else 0.0
+    posting_count = ctr["last_posting_count"]
     line = {
         "metric": "bm25_top10_queries_per_sec", "value": args.queries / (ms_step / 1e3), "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -363,53 +374,79 @@ def main():
                    "l2": "inputs larger than L2 (resident postings >> 126 MB); no explicit flush",
                    "postings_resident_this_rank": int(n_postings), "kernel": args.kernel, "options": options},
         "e2e": e2e,
-        "gpu_launches": int(launches),
+        "gpu_launches": int(round(launches * args.steps)),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_kind": peak_kind,
-                     "kernel": {"auto": "slg_score_warp_kernel<COLS>", "reg": "slg_score_warp_kernel<COLS> / slg_score_sweep_kernel", "cta": "slg_score_tiles_kernel"}.get(args.kernel, "slg_score_warp_kernel"),
-                     "kernel_ms": score_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "5 B x sum of df over the batch's query terms (this rank's segment)"},
-        "pruned": pruned,
-        "setup": {"corpus_gen_s": round(gen_s, 1), "load_segment_s": round(load_s, 1), "resident_bytes": int(c1["resident_bytes"])},
+        "setup": {"corpus_gen_s": round(gen_s, 1), "load_segment_s": round(load_s, 1), "resident_bytes": int(ctr["resident_bytes"])},
     }
-    if (world == 1 and args.execution == "bm25" and args.kernel in ("auto", "warp") and args.docs == 10_000_000
-            and args.queries == 4096 and not options and not args.sub_docs):
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one `ncu --set full` capture
-        if args.kernel == "auto":
-            line["roofline"]["traffic"] = 7.356216e9 + 13.366272e6
-            line["roofline"]["traffic_source"] = "profiles/r1_v8_warp_cols_kernel_summary.txt"
-        else:
-            line["roofline"]["traffic"] = 5.608199e9 + 13.091840e6
-            line["roofline"]["traffic_source"] = "profiles/r1_v7_warp_kernel_summary.txt"
+    if args.execution != "bm25":
+        scanned = int(ctr["last_postings_scattered"])
+        line["pruned"] = {
+            "execution": args.execution, "kernel_ms": kernel_ms,
+            "posting_count": int(posting_count), "postings_scanned": scanned, "postings_scanned_frac": scanned / max(posting_count, 1),
+            "postings_verified": int(ctr["last_postings_verified"]), "scan_items": int(ctr["last_items"]),
+            "scan_items_dropped": int(ctr["last_items_dropped"]),
+            "column_blocks_scored": int(ctr["last_column_blocks_streamed"]), "column_blocks_per_doc": int(ctr["last_subtiles_skipped"]),
+            "note": "this rank's segment; posting_count = sum of df over the batch's query terms; a dropped item = 4096 postings of a non-essential term",
+        }
+        if exhaustive:
+            line["pruned"]["speedup_vs_exhaustive"] = exhaustive["ms_per_step"] / ms_step
+            line["pruned"]["identical_to_exhaustive"] = bool(ex_h.tobytes() == got_h.tobytes() and ex_c.tobytes() == got_c.tobytes())
+    line["exhaustive"] = exhaustive
+    if args.execution == "bm25" or exhaustive:
+        alg_bytes = 5.0 * posting_count
+        achieved = alg_bytes / (x_kernel_ms / 1e3) / 1e9 if x_kernel_ms > 0 else 0.0
+        traffic, traffic_src = measured_traffic("scan+columns:bm25:c2" if args.config == "c2" and world == 1 and not options else "none")
+        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                            "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
+                            "kernel": "slg_scan_kernel<false> + slg_score_columns_kernel<false> (execution bm25: every posting read and compared)",
+                            "kernel_ms": x_kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                            "note": "5 B x sum of df over the batch's query terms (this rank's segment), SURVEY.md §8d; a fraction above 1 means "
+                                    "posting bytes are shared between the queries of the batch (one column block read serves every query that names the column)"}
 
-    # ---- CPU baseline + parity on a bounded sample (rank 0, N = 1) ----
-    if host_seg is not None:
+    # ---- CPU baseline + parity on EVERY query (rank 0; at N > 1 against the oracle's merged per-segment results) ----
+    n_cpu = args.queries if args.cpu_sample < 0 else min(args.cpu_sample, args.queries)
+    line["cpu_baseline"] = None
+    if rank == 0 and n_cpu > 0:
         from oracle import slo
         from tests.parity import parity_report
         slo.build()
-        ora = slo.OracleIndex(host_seg)
         threads = slo.max_threads()
-        n = min(args.cpu_sample, args.queries)
-        sub = qb.subset(0, n)
-        tcpu = time.perf_counter()
-        ref_h, ref_c = ora.search_batch(sub, k, "bm25_dense", threads=threads)
-        cpu_s = time.perf_counter() - tcpu
-        line["cpu_baseline"] = {"value": n / cpu_s, "unit": "queries/s", "cores": threads, "kind": "port",
-                                "sample": f"first {n} of the {args.queries} queries, oracle bm25_dense (pre-decoded postings, "
-                                          f"{threads} threads over queries; the 'fair' port of BASELINE.md §3)"}
-        rep = parity_report(ref_h, ref_c, got_h[:n], got_c[:n])
-        # the automatic kernel sums column terms first (include/searchlite_gpu.h): bit-exactness is checked against
-        # the oracle run on that permutation of each query, the 1e-5 rule against the reference (query) order
-        from tests.helpers import canonical_batch
-        can_h, can_c = ora.search_batch(canonical_batch(gi, sub), k, "bm25_dense", threads=threads)
-        rep["bit_exact_declared_order"] = parity_report(can_h, can_c, got_h[:n], got_c[:n])["bit_exact"]
-        rep["note"] = ("bit_exact / within_rule: against the oracle in the reference's (query) summation order; "
-                       "bit_exact_declared_order: against the oracle on the kernel's declared term order")
+        sub = qb.subset(0, n_cpu)
+        per_seg = []
+        cpu_s = 0.0
+        for r in range(world):
+            host = synth.generate_segment(corpus_spec(args, r, world), device).to_host()
+            torch.cuda.empty_cache()
+            ora = slo.OracleIndex(host)
+            tcpu = time.perf_counter()
+            per_seg.append(ora.search_batch(sub, k, "bm25_dense", threads=threads))
+            cpu_s += time.perf_counter() - tcpu
+            if world > 1:
+                del ora
+            del host
+        if world == 1:
+            ref_h, ref_c = per_seg[0]
+        else:
+            ref_h = np.zeros_like(per_seg[0][0])
+            ref_c = np.zeros_like(per_seg[0][1])
+            for qi in range(n_cpu):
+                m = slo.merge_hits([h[qi, : c[qi]] for h, c in per_seg], k)
+                ref_h[qi, : len(m)] = m
+                ref_c[qi] = len(m)
+        line["cpu_baseline"] = {"value": n_cpu / cpu_s, "unit": "queries/s", "cores": threads, "kind": "port",
+                                "sample": f"{n_cpu} of the {args.queries} queries, oracle bm25_dense (pre-decoded postings, {threads} threads over "
+                                          f"queries; the 'fair' port of BASELINE.md §3), {world} segment(s) searched one after the other"}
+        rep = parity_report(ref_h, ref_c, got_h[:n_cpu], got_c[:n_cpu])
+        rep["note"] = ("every listed query against the oracle's exact result in the reference's (query) summation order: bit_exact = ids, order and "
+                       "f32 score bits equal; within_rule = the north-star rule (ids and order equal, scores within 1e-5 relative, id swaps only inside "
+                       "1e-5 of the k-th score).  The engine sums a doc's terms without a dense column first, then those with one (declared order)")
+        if world == 1:
+            from tests.helpers import canonical_batch
+            can_h, can_c = ora.search_batch(canonical_batch(gi, sub), k, "bm25_dense", threads=threads)
+            rep["bit_exact_declared_order"] = parity_report(can_h, can_c, got_h[:n_cpu], got_c[:n_cpu])["bit_exact"]
         line["parity"] = rep
-    else:
-        line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -8,9 +8,10 @@
 //   work item  = (query, term, chunk of kScanChunk postings), handed out from a global counter, RAREST TERMS FIRST: the
 //                docs that end up in a query's top k nearly always hold its rarest term, so every query's k-th score is close
 //                to final before its long lists are streamed
-//   scan       = the resident unit-weight scores of the chunk, 128-bit loads, 128 postings per warp step; a posting is looked
-//                at further only if  contribution + (largest contribution of every OTHER term of the query)  can reach the
-//                query's running k-th score.  Doc ids are not even read for the rest
+//   scan       = the resident unit-weight scores of the chunk, 128-bit loads, 128 postings per warp step.  Terms have a
+//                priority (larger bound first) and a doc is the business of its highest-priority holder, so a posting is
+//                looked at further only if  contribution + (largest contribution of every LOWER-priority term of the
+//                query)  can reach the query's running k-th score.  Doc ids are not even read for the rest
 //   verify     = the doc of such a posting gets its EXACT score: every term of the query in slot (= declared) order — the
 //                posting's own contribution, the other sparse terms by binary search in their lists, the column terms by one
 //                4-byte gather — the sum brute_force computes for that doc, then accept (api/reader.rs:3009-3036) and the
@@ -41,7 +42,7 @@ struct __align__(16) ScanPair {  // one scanned (query, sparse term): 48 B
   uint32_t qslot_t;   // qslot << 3 | slot
   uint32_t qi;
   float w;
-  float others;       // sum of the other terms' bounds (weight applied)
+  float others;       // bounds (weight applied) of the query's column terms and of its lower-priority sparse terms: what a doc first met here can gain
   float ne_prefix;    // sum of the bounds of the terms with a bound <= this term's (this term included): the MaxScore test
   int32_t filter;
   uint32_t first_item;
@@ -62,24 +63,29 @@ struct ScanDev {
   unsigned long long *counters;  // [8]: 0 postings scanned, 3 items scanned, 4 postings verified, 5 items dropped by MaxScore
 };
 
-// largest unit-weight contribution of every unique term of the batch: a reduction over the term's resident scores
+// largest unit-weight contribution of every unique term of the batch: a reduction over the term's resident scores.
+// grid (ceil(U / 8), kMaxSlices): warp (u, slice) reduces one slice of the list and folds it in with atomicMax (scores are
+// positive floats: their bit patterns order like the values).  ut_max must be zero on entry.
+constexpr uint32_t kMaxSlices = 32;
 static __global__ void __launch_bounds__(256) slg_term_max_kernel(SegmentDev seg, ScanDev sc, uint32_t n_uterms) {
-  const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (u >= n_uterms) return;
   const uint32_t term = sc.ut_term[u];
+  if (term >= seg.n_terms) return;
+  const uint32_t df = seg.term_df[term];
+  const uint32_t quads = (df + 3) >> 2;  // (the padding of a list is zero: whole 16-byte pieces up to the 32-posting boundary are safe to read)
+  const uint32_t per = (quads + kMaxSlices - 1) / kMaxSlices;
+  const uint32_t q0 = blockIdx.y * per, q1 = min(quads, q0 + per);
+  if (q0 >= q1) return;
+  const float4 *p = reinterpret_cast<const float4 *>(seg.post_score + seg.term_start[term]);
   uint32_t m = 0u;
-  if (term < seg.n_terms) {
-    const uint32_t df = seg.term_df[term];
-    const float4 *p = reinterpret_cast<const float4 *>(seg.post_score + seg.term_start[term]);
-    // (the padding of a list is zero: whole 16-byte pieces up to the 32-posting boundary are safe to read)
-    for (uint32_t i = lane; i * 4 < df; i += 32) {
-      const float4 v = __ldg(p + i);
-      m = max(m, max(max(__float_as_uint(v.x), __float_as_uint(v.y)), max(__float_as_uint(v.z), __float_as_uint(v.w))));
-    }
+  for (uint32_t i = q0 + lane; i < q1; i += 32) {
+    const float4 v = __ldg(p + i);
+    m = max(m, max(max(__float_as_uint(v.x), __float_as_uint(v.y)), max(__float_as_uint(v.z), __float_as_uint(v.w))));
   }
   m = __reduce_max_sync(0xFFFFFFFFu, m);
-  if (lane == 0) sc.ut_max[u] = __uint_as_float(m);
+  if (lane == 0 && m) atomicMax(reinterpret_cast<uint32_t *>(sc.ut_max) + u, m);
 }
 
 // per query slot: the scanned pairs with their bounds.  Thread per query.
@@ -88,14 +94,15 @@ static __global__ void __launch_bounds__(128) slg_scan_pairs_kernel(SegmentDev s
   if (qslot >= wb.n_queries) return;
   const QHead h = wb.qheads[qslot];
   float ub[kWarpMaxTerms];
-  float total = 0.0f;
+  bool is_col[kWarpMaxTerms];
   for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
     ub[t] = 0.0f;
+    is_col[t] = false;
     if (t < h.nt) {
       const QTerm &q = wb.qterms[(uint64_t)qslot * kWarpMaxTerms + t];
       if (q.flags & 1u) ub[t] = __fmul_rn(sc.ut_max[q.uterm], q.weight);
+      is_col[t] = (q.flags & 4u) != 0u;
     }
-    total += ub[t];
   }
   for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
     ScanPair p;
@@ -115,13 +122,17 @@ static __global__ void __launch_bounds__(128) slg_scan_pairs_kernel(SegmentDev s
         p.base = q.base;
         p.df = seg.term_df[q.term];
         p.w = q.weight;
-        float o = 0.0f, pre = 0.0f;
+        // priority: larger bound first, ties to the lower slot.  A doc with sparse holders is the business of the
+        // highest-priority one of them, so a posting met in this term's scan can still gain: every column term, and the
+        // sparse terms of LOWER priority
+        float lower = 0.0f, gain = 0.0f;
         for (uint32_t u = 0; u < kWarpMaxTerms; u++) {
-          if (u != t) o += ub[u];
-          if (ub[u] < ub[t] || (ub[u] == ub[t] && u >= t)) pre += ub[u];  // terms of lower priority, and this one
+          const bool lo = u != t && (ub[u] < ub[t] || (ub[u] == ub[t] && u > t));
+          if (lo) lower += ub[u];
+          if (u != t && (is_col[u] || lo)) gain += ub[u];
         }
-        p.others = o;
-        p.ne_prefix = pre;
+        p.others = gain;
+        p.ne_prefix = lower + ub[t];
       }
     }
     sc.pairs[(uint64_t)qslot * kWarpMaxTerms + t] = p;
@@ -309,18 +320,14 @@ __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev se
           uint32_t holders = 0u;
           n_verified += pass ? 1u : 0u;
           const float s = verify_doc(seg, wb, qts, nt, pass, doc, holders);
-          // the doc is offered by the posting of its highest-priority holder: exhaustive — the lowest slot (every sparse list
-          // is scanned); pruned — the largest bound, ties to the lower slot (that list is never dropped while the doc matters)
+          // the doc is offered by the posting of its highest-priority holder (largest bound, ties to the lower slot): the
+          // pruned executions never drop that list while the doc matters
           if (pass) {
-            if (!PRUNE) {
-              pass = (holders & ((1u << t) - 1u)) == 0u;
-            } else {
-              const float my_ub = __fmul_rn(sc.ut_max[__ldg(&qts[t].uterm)], pr.w);
-              for (uint32_t hm = holders & ~(1u << t); hm && pass; hm &= hm - 1) {
-                const uint32_t u = __ffs(hm) - 1;
-                const float ub_u = __fmul_rn(sc.ut_max[__ldg(&qts[u].uterm)], __ldg(&qts[u].weight));
-                if (ub_u > my_ub || (ub_u == my_ub && u < t)) pass = false;
-              }
+            const float my_ub = __fmul_rn(sc.ut_max[__ldg(&qts[t].uterm)], pr.w);
+            for (uint32_t hm = holders & ~(1u << t); hm && pass; hm &= hm - 1) {
+              const uint32_t u = __ffs(hm) - 1;
+              const float ub_u = __fmul_rn(sc.ut_max[__ldg(&qts[u].uterm)], __ldg(&qts[u].weight));
+              if (ub_u > my_ub || (ub_u == my_ub && u < t)) pass = false;
             }
           }
           wc.offer(seg, wb, pr.qi, pr.filter, pass, doc, s);

@@ -597,7 +597,8 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       sdv.stage_cap = ix->stage_cap;
       sdv.strict = 0;
       sdv.counters = bt->item_counters;
-      slg_term_max_kernel<<<(bt->U * 32 + 255) / 256, 256, 0, st>>>(s->dev, sc, bt->U);
+      SLG_CUDA(ix, cudaMemsetAsync(bt->ut_max, 0, (size_t)bt->U * 4, st));
+      slg_term_max_kernel<<<dim3((bt->U + 7) / 8, kMaxSlices), 256, 0, st>>>(s->dev, sc, bt->U);
       slg_scan_pairs_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, wb, sc);
       slg_scan_order_kernel<<<1, 1024, 0, st>>>(wb, sc);
       if (bt->scan_items_cap) slg_scan_items_kernel<<<(bt->scan_items_cap + 255) / 256, 256, 0, st>>>(sc);
