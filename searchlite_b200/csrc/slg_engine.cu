@@ -397,6 +397,7 @@ int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
   else if (n == "stream_kernels") ix->stream_kernels = value != 0;
   else if (n == "strict_accumulate") ix->strict_accumulate = value != 0;
   else if (n == "scan_kernels") ix->scan_kernels = value != 0;
+  else if (n == "dbg") ix->dbg = (uint32_t)value;
   else if (n == "maxscore_pct") ix->maxscore_pct = (uint32_t)std::min<uint64_t>(value, 100);
   else if (n == "heavy_kernel") {  // the tile-sweep front end of round 1 is gone (it carried an unlocalised intermittent fault)
     if (value != 0) return fail(ix, SLG_ERR_UNSUPPORTED, "heavy_kernel 1 (tile-sweep kernel) was removed; the column path is the items kernel");

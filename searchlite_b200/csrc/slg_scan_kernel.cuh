@@ -75,7 +75,7 @@ static __global__ void __launch_bounds__(256) slg_term_max_kernel(SegmentDev seg
   if (term >= seg.n_terms) return;
   const uint32_t df = seg.term_df[term];
   const uint32_t quads = (df + 3) >> 2;  // (the padding of a list is zero: whole 16-byte pieces up to the 32-posting boundary are safe to read)
-  const uint32_t per = (quads + kMaxSlices - 1) / kMaxSlices;
+  const uint32_t per = (quads + gridDim.y - 1) / gridDim.y;
   const uint32_t q0 = blockIdx.y * per, q1 = min(quads, q0 + per);
   if (q0 >= q1) return;
   const float4 *p = reinterpret_cast<const float4 *>(seg.post_score + seg.term_start[term]);
@@ -89,7 +89,7 @@ static __global__ void __launch_bounds__(256) slg_term_max_kernel(SegmentDev seg
 }
 
 // per query slot: the scanned pairs with their bounds.  Thread per query.
-static __global__ void __launch_bounds__(128) slg_scan_pairs_kernel(SegmentDev seg, WarpBatchDev wb, ScanDev sc) {
+static __global__ void __launch_bounds__(128) slg_scan_pairs_kernel(SegmentDev seg, WarpBatchDev wb, ScanDev sc, uint32_t dbg) {
   const uint32_t qslot = blockIdx.x * blockDim.x + threadIdx.x;
   if (qslot >= wb.n_queries) return;
   const QHead h = wb.qheads[qslot];
@@ -132,6 +132,7 @@ static __global__ void __launch_bounds__(128) slg_scan_pairs_kernel(SegmentDev s
           if (u != t && (is_col[u] || lo)) gain += ub[u];
         }
         p.others = gain;
+        if (dbg & 1u) { float o = 0.0f; for (uint32_t u = 0; u < kWarpMaxTerms; u++) if (u != t) o += ub[u]; p.others = o; }
         p.ne_prefix = lower + ub[t];
       }
     }

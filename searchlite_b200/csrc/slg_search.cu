@@ -598,8 +598,8 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       sdv.strict = 0;
       sdv.counters = bt->item_counters;
       SLG_CUDA(ix, cudaMemsetAsync(bt->ut_max, 0, (size_t)bt->U * 4, st));
-      slg_term_max_kernel<<<dim3((bt->U + 7) / 8, kMaxSlices), 256, 0, st>>>(s->dev, sc, bt->U);
-      slg_scan_pairs_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, wb, sc);
+      slg_term_max_kernel<<<dim3((bt->U + 7) / 8, (ix->dbg & 2u) ? 1u : kMaxSlices), 256, 0, st>>>(s->dev, sc, bt->U);
+      slg_scan_pairs_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, wb, sc, ix->dbg);
       slg_scan_order_kernel<<<1, 1024, 0, st>>>(wb, sc);
       if (bt->scan_items_cap) slg_scan_items_kernel<<<(bt->scan_items_cap + 255) / 256, 256, 0, st>>>(sc);
       for (int i = 0; i < 4; i++) count_launch(ix);
@@ -607,7 +607,7 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));  // (the scoring time of this path starts here)
       SLG_CUDA(ix, launch_scan(prune, s->dev, wb, sc, ix->n_sm * 8, st));
       count_launch(ix);
-      if (s->n_cols) {
+      if (s->n_cols && !(ix->dbg & 4u)) {
         slg_colgroups_kernel<<<1, 1024, 0, st>>>(s->dev, wb, sdv, s->n_cols);
         count_launch(ix);
         if (prune) {
