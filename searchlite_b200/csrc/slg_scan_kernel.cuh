@@ -248,6 +248,29 @@ static __global__ void __launch_bounds__(128) slg_colq_prune_kernel(WarpBatchDev
   sd.colq[i] = cq;
 }
 
+// position of the first posting with doc id >= doc in a list of n ascending doc ids.  Lists are near-uniform samples of the
+// doc range, so a few guesses by local density (position + (doc - d) * n / doc_count) close in on the place before a binary
+// search finishes in the bracket that is left; the bracket invariant keeps the result exact for any list.
+__device__ __forceinline__ uint32_t lower_bound_interp(const uint32_t *dp, uint32_t n, uint32_t doc, float dens) {
+  uint32_t lo = 0, hi = n;  // dp[i] < doc for i < lo, dp[i] >= doc for i >= hi
+  float est = (float)doc * dens;
+#pragma unroll 1
+  for (int it = 0; it < 4 && lo < hi; it++) {
+    const uint32_t pos = min(max(est < 0.0f ? 0u : (uint32_t)est, lo), hi - 1u);
+    const uint32_t d = __ldg(dp + pos);
+    if (d < doc) lo = pos + 1u;
+    else hi = pos;
+    if (d == doc) break;
+    est = (float)pos + ((float)doc - (float)d) * dens;
+  }
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(dp + mid) < doc) lo = mid + 1u;
+    else hi = mid;
+  }
+  return lo;
+}
+
 template <bool PRUNE>
 __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev seg, WarpBatchDev wb, ScanDev sc) {
   __shared__ __align__(16) unsigned long long s_cand[kScanWarps][kWarpCand];
@@ -255,7 +278,8 @@ __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev se
   unsigned long long *cand = s_cand[warp];
   const uint32_t k = wb.k;
   const uint32_t n_items = *sc.n_items;
-  unsigned long long n_scanned = 0, n_verified = 0;
+  const float inv_docs = 1.0f / (float)max(seg.doc_count, 1u);
+  unsigned long long n_scanned = 0, n_verified = 0, n_lookups = 0;
   uint32_t n_dropped = 0, n_done = 0;
   WarpCand wc;
 
@@ -279,6 +303,27 @@ __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev se
       const uint32_t qslot = pr.qslot_t >> 3, t = pr.qslot_t & 7u;
       const QTerm *qts = wb.qterms + (uint64_t)qslot * kWarpMaxTerms;
       const uint32_t nt = __ldg(&wb.qheads[qslot].nt);
+      // lane u < nt keeps term u of the query: what verify needs, handed round by shuffles
+      uint64_t m_base = 0;      // sparse: first posting; column: element offset of the column
+      uint32_t m_df = 0, m_kind = 0;  // kind: 0 absent / unscored, 1 sparse, 2 column
+      float m_w = 0.0f, m_ub = 0.0f, m_dens = 0.0f;
+      if (lane < (int)nt) {
+        const QTerm q = qts[lane];
+        if (q.flags & 1u) {
+          m_w = q.weight;
+          m_ub = __fmul_rn(sc.ut_max[q.uterm], q.weight);
+          if (q.flags & 4u) {
+            m_kind = 2;
+            m_base = q.sc_base;
+          } else if (q.term < seg.n_terms) {
+            m_kind = 1;
+            m_base = q.base;
+            m_df = __ldg(seg.term_df + q.term);
+            m_dens = (float)m_df * inv_docs;
+          }
+        }
+      }
+      const float my_ub = __shfl_sync(0xFFFFFFFFu, m_ub, t);
       const float4 *sp = reinterpret_cast<const float4 *>(wb.scores + pr.base);
       const uint32_t i0 = chunk * kScanChunk, i1 = min(pr.df, i0 + kScanChunk);
       n_scanned += i1 - i0;
@@ -314,24 +359,63 @@ __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev se
 #pragma unroll
           for (int z = 0; z < 8; z++)
             if (e == (uint32_t)z) v = x[z];
-          bool pass = had && __float_as_uint(v) >= cut;
-          if (!__any_sync(0xFFFFFFFFu, pass)) continue;
+          bool alive = had && __float_as_uint(v) >= cut;
+          if (!__any_sync(0xFFFFFFFFu, alive)) continue;
           uint32_t doc = 0u;
-          if (pass) doc = __ldg(seg.post_doc + pr.base + (e < 4 ? ia : ib) + (e & 3));
-          uint32_t holders = 0u;
-          n_verified += pass ? 1u : 0u;
-          const float s = verify_doc(seg, wb, qts, nt, pass, doc, holders);
-          // the doc is offered by the posting of its highest-priority holder (largest bound, ties to the lower slot): the
-          // pruned executions never drop that list while the doc matters
-          if (pass) {
-            const float my_ub = __fmul_rn(sc.ut_max[__ldg(&qts[t].uterm)], pr.w);
-            for (uint32_t hm = holders & ~(1u << t); hm && pass; hm &= hm - 1) {
-              const uint32_t u = __ffs(hm) - 1;
-              const float ub_u = __fmul_rn(sc.ut_max[__ldg(&qts[u].uterm)], __ldg(&qts[u].weight));
-              if (ub_u > my_ub || (ub_u == my_ub && u < t)) pass = false;
+          if (alive) doc = __ldg(seg.post_doc + pr.base + (e < 4 ? ia : ib) + (e & 3));
+          n_verified += alive ? 1u : 0u;
+          // ---- verify, cheapest evidence first: the column terms (one gather each), then the other sparse terms (a search
+          // each), dropping the doc as soon as  known contributions + bounds of the unknown ones  falls below the k-th score.
+          // The exact score is the sum of the contributions in slot order.
+          const float thr_s = wc.thr == kThrInit ? 0.0f : __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f;
+          float c[kWarpMaxTerms];
+          float known = v, unknown = pr.others;  // (pr.others = the bounds of exactly the terms that can still add: columns + lower-priority sparse)
+#pragma unroll
+          for (int u = 0; u < (int)kWarpMaxTerms; u++) {
+            c[u] = 0.0f;
+            const uint32_t kind = __shfl_sync(0xFFFFFFFFu, m_kind, u);
+            if (kind != 2u) continue;  // (uniform)
+            const uint64_t cb = __shfl_sync(0xFFFFFFFFu, m_base, u);
+            const float w = __shfl_sync(0xFFFFFFFFu, m_w, u), ub = __shfl_sync(0xFFFFFFFFu, m_ub, u);
+            if (alive) {
+              c[u] = __fmul_rn(__ldg(seg.cols + cb + doc), w);
+              known += c[u];
+              unknown -= ub;
             }
           }
-          wc.offer(seg, wb, pr.qi, pr.filter, pass, doc, s);
+          alive = alive && (known + fmaxf(unknown, 0.0f)) * 1.0001f >= thr_s;
+          bool stand_back = false;
+#pragma unroll
+          for (int u = 0; u < (int)kWarpMaxTerms; u++) {
+            const uint32_t kind = __shfl_sync(0xFFFFFFFFu, m_kind, u);
+            if (kind != 1u || u == (int)t) continue;  // (uniform)
+            if (!__any_sync(0xFFFFFFFFu, alive)) break;
+            const uint64_t pb = __shfl_sync(0xFFFFFFFFu, m_base, u);
+            const uint32_t dfu = __shfl_sync(0xFFFFFFFFu, m_df, u);
+            const float w = __shfl_sync(0xFFFFFFFFu, m_w, u), ub = __shfl_sync(0xFFFFFFFFu, m_ub, u),
+                        dens = __shfl_sync(0xFFFFFFFFu, m_dens, u);
+            const bool higher = ub > my_ub || (ub == my_ub && u < (int)t);  // a holder of higher priority offers the doc itself
+            if (alive) {
+              n_lookups++;
+              const uint32_t *dp = seg.post_doc + pb;
+              const uint32_t at = lower_bound_interp(dp, dfu, doc, dens);
+              if (at < dfu && __ldg(dp + at) == doc) {
+                if (higher) stand_back = true;
+                c[u] = __fmul_rn(__ldg(wb.scores + pb + at), w);
+                known += c[u];
+              }
+              if (!higher) unknown -= ub;
+              alive = !stand_back && (known + fmaxf(unknown, 0.0f)) * 1.0001f >= thr_s;
+            }
+          }
+          if (!__any_sync(0xFFFFFFFFu, alive)) continue;
+          float s = 0.0f;
+#pragma unroll
+          for (int u = 0; u < (int)kWarpMaxTerms; u++) {
+            const float cu = u == (int)t ? v : c[u];
+            if (cu != 0.0f) s = __fadd_rn(s, cu);
+          }
+          wc.offer(seg, wb, pr.qi, pr.filter, alive, doc, s);
           recut();
         }
       }
@@ -341,11 +425,15 @@ __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev se
   }
   if (sc.counters) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n_verified += __shfl_xor_sync(0xFFFFFFFFu, n_verified, o);
+    for (int o = 16; o > 0; o >>= 1) {
+      n_verified += __shfl_xor_sync(0xFFFFFFFFu, n_verified, o);
+      n_lookups += __shfl_xor_sync(0xFFFFFFFFu, n_lookups, o);
+    }
     if (lane == 0) {
       if (n_scanned) atomicAdd(sc.counters + 0, n_scanned);
       if (n_verified) atomicAdd(sc.counters + 4, n_verified);
       if (n_dropped) atomicAdd(sc.counters + 5, (unsigned long long)n_dropped);
+      if (n_lookups) atomicAdd(sc.counters + 6, n_lookups);
       if (n_done) atomicAdd(sc.counters + 3, (unsigned long long)n_done);
     }
   }
