@@ -127,6 +127,9 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
   d.col_tmax = nullptr;
   d.tmax_stride = 0;
   d.col_stride = 0;
+  d.term_bits = nullptr;
+  d.pres_bits = nullptr;
+  d.bits_stride = 0;
   d.n_terms = s->n_terms;
   d.doc_count = s->doc_count;
   d.k1p1 = s->k1 + 1.0f;
@@ -194,6 +197,38 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
         d.col_tmax = s->col_tmax.as<float>();
         d.tmax_stride = s->tmax_stride;
       }
+    }
+  }
+  // presence bitmaps for the mid-dense terms without a column: the posting scan's verification asks "does this list hold
+  // the doc" far more often than the answer is yes, and a bit test is one 32-byte sector where a search is several
+  if (ix->resident_scores && ix->bitmap_den && s->doc_count && s->n_blocks) {
+    const uint32_t stride = (uint32_t)align_up(((uint64_t)s->doc_count + 31) / 32, 32);
+    std::vector<uint32_t> cand;
+    for (uint64_t t = 0; t < s->n_terms; t++) {
+      const uint64_t df = s->h_df[t];
+      if (df >= 64 && df * ix->bitmap_den >= s->doc_count && (s->h_term_col.empty() || s->h_term_col[t] < 0)) cand.push_back((uint32_t)t);
+    }
+    std::sort(cand.begin(), cand.end(), [&](uint32_t a, uint32_t b2) { return s->h_df[a] != s->h_df[b2] ? s->h_df[a] > s->h_df[b2] : a < b2; });
+    const uint64_t max_rows = std::min<uint64_t>(32768, ix->max_bitmap_bytes / ((uint64_t)stride * 4));
+    if (cand.size() > max_rows) cand.resize(max_rows);
+    if (!cand.empty()) {
+      std::vector<int32_t> tb(s->n_terms, -1);
+      for (size_t r = 0; r < cand.size(); r++) tb[cand[r]] = (int32_t)r;
+      DevBuf d_terms;
+      SLG_CUDA(ix, d_terms.alloc(cand.size() * 4));
+      SLG_CUDA(ix, cudaMemcpyAsync(d_terms.p, cand.data(), cand.size() * 4, cudaMemcpyHostToDevice, st));
+      SLG_CUDA(ix, s->term_bits.alloc(s->n_terms * 4));
+      SLG_CUDA(ix, cudaMemcpyAsync(s->term_bits.p, tb.data(), s->n_terms * 4, cudaMemcpyHostToDevice, st));
+      SLG_CUDA(ix, s->pres_bits.alloc(cand.size() * (uint64_t)stride * 4));
+      SLG_CUDA(ix, cudaMemsetAsync(s->pres_bits.p, 0, cand.size() * (uint64_t)stride * 4, st));
+      slg_fill_presence_kernel<<<dim3(64, (unsigned)cand.size()), 256, 0, st>>>(d, d_terms.as<uint32_t>(), (uint32_t)cand.size(), s->pres_bits.as<uint32_t>(), stride);
+      count_launch(ix);
+      SLG_CUDA(ix, cudaGetLastError());
+      SLG_CUDA(ix, cudaStreamSynchronize(st));
+      s->n_bitmaps = (uint32_t)cand.size();
+      d.term_bits = s->term_bits.as<int32_t>();
+      d.pres_bits = s->pres_bits.as<uint32_t>();
+      d.bits_stride = stride;
     }
   }
   ix->ctr.resident_bytes += s->resident();
@@ -390,6 +425,8 @@ int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
   else if (n == "dense_den") ix->dense_den = (uint32_t)value;
   else if (n == "dense_min_df") ix->dense_min_df = (uint32_t)value;
   else if (n == "max_column_bytes") ix->max_column_bytes = value;
+  else if (n == "bitmap_den") ix->bitmap_den = (uint32_t)value;
+  else if (n == "max_bitmap_bytes") ix->max_bitmap_bytes = value;
   else if (n == "stage_cap") {
     if (value < 64 || value > 8192 || value % 4) return fail(ix, SLG_ERR_INVALID, "stage_cap must be a multiple of 4 in [64, 8192]");
     ix->stage_cap = (uint32_t)value;

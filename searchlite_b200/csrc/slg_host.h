@@ -114,7 +114,8 @@ struct Segment {
   float k1 = 0.9f, b = 0.4f, avgdl = 0, live_docs = 0, min_doc_len = 1;
   std::vector<uint32_t> h_df;  // host copy (query ordering, validation)
   DevBuf post_doc, post_tf, term_start, term_df, term_idf, term_max_tf, term_wide, tf_wide, term_blk, blk_max_doc,
-      blk_max_tf, nk, live_bits, post_score, mb_max, cols, term_col, col_tmax;
+      blk_max_tf, nk, live_bits, post_score, mb_max, cols, term_col, col_tmax, term_bits, pres_bits;
+  uint32_t n_bitmaps = 0;
   uint32_t n_cols = 0, tmax_stride = 0;
   uint64_t col_stride = 0;
   std::vector<int32_t> h_term_col;  // host copy (tests, introspection); empty = no columns
@@ -144,7 +145,7 @@ struct Segment {
   size_t resident() const {
     return post_doc.bytes + post_tf.bytes + term_start.bytes + term_df.bytes + term_idf.bytes + term_max_tf.bytes +
            term_wide.bytes + tf_wide.bytes + term_blk.bytes + blk_max_doc.bytes + blk_max_tf.bytes + nk.bytes + term_field.bytes +
-           live_bits.bytes + post_score.bytes + mb_max.bytes + cols.bytes + term_col.bytes + col_tmax.bytes +
+           live_bits.bytes + post_score.bytes + mb_max.bytes + cols.bytes + term_col.bytes + col_tmax.bytes + term_bits.bytes + pres_bits.bytes +
            pos_begin.bytes + pos.bytes;
   }
 };
@@ -179,6 +180,8 @@ struct slg_index {
   bool resident_scores = true;   // build seg.post_score at load
   uint32_t dense_den = 8;        // a term gets a dense column when df * dense_den >= doc_count; 0 = no columns
   uint32_t dense_min_df = 256;   // ... and df >= this
+  uint32_t bitmap_den = 512;     // a term without a column gets a presence bitmap (1 bit per doc) when df * bitmap_den >= doc_count; 0 = none
+  uint64_t max_bitmap_bytes = 16ull << 30;
   uint64_t max_column_bytes = 24ull << 30;
   uint32_t stage_cap = 1024;     // sparse pass: postings a warp stages in shared memory per span (slg_stream_kernel.cuh)
   uint32_t strict_accumulate = 0; // exhaustive stream kernels: 1 = sum every posting per doc; 0 = bounded accumulation (slg_stream_kernel.cuh)

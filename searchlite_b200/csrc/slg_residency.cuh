@@ -96,6 +96,20 @@ static __global__ void slg_fill_columns_kernel(SegmentDev seg, const uint32_t *c
     col[seg.post_doc[base + i]] = seg.post_score[base + i];
 }
 
+// grid (chunks, n_rows): row r holds one bit per doc for term bm_terms[r] (rows are zero on entry)
+static __global__ void slg_fill_presence_kernel(SegmentDev seg, const uint32_t *bm_terms, uint32_t n_rows, uint32_t *bits, uint32_t stride) {
+  const uint32_t r = blockIdx.y;
+  if (r >= n_rows) return;
+  const uint32_t term = bm_terms[r];
+  const uint32_t df = seg.term_df[term];
+  const uint32_t *d = seg.post_doc + seg.term_start[term];
+  uint32_t *row = bits + (uint64_t)r * stride;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < df; i += gridDim.x * blockDim.x) {
+    const uint32_t doc = d[i];
+    atomicOr(row + (doc >> 5), 1u << (doc & 31));
+  }
+}
+
 // one warp per (512-doc slice, column): the exact maximum contribution inside the slice
 static __global__ void slg_column_tmax_kernel(const float *cols, uint64_t col_stride, uint32_t n_cols, uint32_t tmax_stride, float *tmax) {
   const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

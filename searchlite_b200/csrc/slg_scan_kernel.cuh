@@ -211,43 +211,6 @@ static __global__ void __launch_bounds__(256) slg_scan_items_kernel(ScanDev sc) 
   sc.items[i] = lo;
 }
 
-// pruned execution, between the posting scan and the column pass: which queries still need the column pass, and what the
-// sparse terms the scan may have dropped could add to a doc it never met.  With the k-th score the scan left behind, the
-// non-essential terms are the longest lowest-priority prefix whose bounds sum below it; a query whose column terms are all
-// non-essential sits the column pass out (a doc without an essential term cannot enter the top k), the others look at
-// v + extra, extra = the bounds of the non-essential SPARSE terms.  Thread per ColQ.
-static __global__ void __launch_bounds__(128) slg_colq_prune_kernel(WarpBatchDev wb, StreamDev sd, ScanDev sc) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= *sd.n_colq) return;
-  ColQ cq = sd.colq[i];
-  const unsigned long long thr = wb.thr_key[cq.qi];
-  const uint32_t nt = (uint32_t)cq.nsp + cq.ncol;
-  float ub[kWarpMaxTerms];
-  for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
-    ub[t] = 0.0f;
-    if (t < nt) {
-      const QTerm &q = wb.qterms[(uint64_t)cq.qslot * kWarpMaxTerms + t];
-      ub[t] = __fmul_rn(sc.ut_max[q.uterm], q.weight);
-    }
-  }
-  float extra = 0.0f;
-  bool any_essential_col = false;
-  for (uint32_t t = 0; t < nt; t++) {
-    float pre = 0.0f;
-    for (uint32_t u = 0; u < nt; u++)
-      if (ub[u] < ub[t] || (ub[u] == ub[t] && u >= t)) pre += ub[u];
-    const bool ne = thr != kThrInit && pre * 1.00002f < __uint_as_float((uint32_t)(thr >> 32));
-    if (t < cq.nsp) {
-      if (ne) extra += ub[t];
-    } else if (!ne) {
-      any_essential_col = true;
-    }
-  }
-  cq.off = any_essential_col ? 0 : 1;
-  cq.extra = extra;
-  sd.colq[i] = cq;
-}
-
 // position of the first posting with doc id >= doc in a list of n ascending doc ids.  Lists are near-uniform samples of the
 // doc range, so a few guesses by local density (position + (doc - d) * n / doc_count) close in on the place before a binary
 // search finishes in the bracket that is left; the bracket invariant keeps the result exact for any list.
@@ -305,6 +268,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev se
       const uint32_t nt = __ldg(&wb.qheads[qslot].nt);
       // lane u < nt keeps term u of the query: what verify needs, handed round by shuffles
       uint64_t m_base = 0;      // sparse: first posting; column: element offset of the column
+      uint64_t m_bits = 0;      // sparse: word offset of the term's presence bitmap in seg.pres_bits, ~0 = none
       uint32_t m_df = 0, m_kind = 0;  // kind: 0 absent / unscored, 1 sparse, 2 column
       float m_w = 0.0f, m_ub = 0.0f, m_dens = 0.0f;
       if (lane < (int)nt) {
@@ -320,6 +284,11 @@ __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev se
             m_base = q.base;
             m_df = __ldg(seg.term_df + q.term);
             m_dens = (float)m_df * inv_docs;
+            m_bits = ~0ull;
+            if (seg.term_bits) {
+              const int32_t row = __ldg(seg.term_bits + q.term);
+              if (row >= 0) m_bits = (uint64_t)row * seg.bits_stride;
+            }
           }
         }
       }
@@ -390,7 +359,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev se
             const uint32_t kind = __shfl_sync(0xFFFFFFFFu, m_kind, u);
             if (kind != 1u || u == (int)t) continue;  // (uniform)
             if (!__any_sync(0xFFFFFFFFu, alive)) break;
-            const uint64_t pb = __shfl_sync(0xFFFFFFFFu, m_base, u);
+            const uint64_t pb = __shfl_sync(0xFFFFFFFFu, m_base, u), bo = __shfl_sync(0xFFFFFFFFu, m_bits, u);
             const uint32_t dfu = __shfl_sync(0xFFFFFFFFu, m_df, u);
             const float w = __shfl_sync(0xFFFFFFFFu, m_w, u), ub = __shfl_sync(0xFFFFFFFFu, m_ub, u),
                         dens = __shfl_sync(0xFFFFFFFFu, m_dens, u);
@@ -398,7 +367,10 @@ __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev se
             if (alive) {
               n_lookups++;
               const uint32_t *dp = seg.post_doc + pb;
-              const uint32_t at = lower_bound_interp(dp, dfu, doc, dens);
+              // one bit per doc says whether the list holds it at all (one sector instead of a search: usually it does not)
+              bool held = true;
+              if (bo != ~0ull) held = (__ldg(seg.pres_bits + bo + (doc >> 5)) >> (doc & 31)) & 1u;
+              const uint32_t at = held ? lower_bound_interp(dp, dfu, doc, dens) : dfu;
               if (at < dfu && __ldg(dp + at) == doc) {
                 if (higher) stand_back = true;
                 c[u] = __fmul_rn(__ldg(wb.scores + pb + at), w);

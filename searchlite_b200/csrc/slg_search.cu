@@ -608,12 +608,8 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       SLG_CUDA(ix, launch_scan(prune, s->dev, wb, sc, ix->n_sm * 8, st));
       count_launch(ix);
       if (s->n_cols && !(ix->dbg & 4u)) {
-        slg_colgroups_kernel<<<1, 1024, 0, st>>>(s->dev, wb, sdv, s->n_cols);
+        slg_colgroups_kernel<<<1, 1024, 0, st>>>(s->dev, wb, sdv, s->n_cols, prune ? bt->ut_max : nullptr);
         count_launch(ix);
-        if (prune) {
-          slg_colq_prune_kernel<<<(Q + 127) / 128, 128, 0, st>>>(wb, sdv, sc);
-          count_launch(ix);
-        }
         SLG_CUDA(ix, cudaGetLastError());
         sdv.n_smax = std::min(s->n_cols, kColMaxSlots);
         const size_t fixed = column_smem(0, sdv.n_smax);
@@ -652,7 +648,7 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
         SLG_CUDA(ix, launch_score_sparse(s->dev, wb, sdv, ssmem, sgrid, st));
         count_launch(ix);
         if (s->n_cols) {
-          slg_colgroups_kernel<<<1, 1024, 0, st>>>(s->dev, wb, sdv, s->n_cols);
+          slg_colgroups_kernel<<<1, 1024, 0, st>>>(s->dev, wb, sdv, s->n_cols, nullptr);
           count_launch(ix);
           SLG_CUDA(ix, cudaGetLastError());
           // one CTA per SM: as many columns of a block resident in shared memory (double buffered) as fit

@@ -70,7 +70,38 @@ struct StreamDev {
 };
 
 // ---- the batch's column terms: used columns -> slots, queries with a column term -> ColQ (one CTA) -------------
-static __global__ void __launch_bounds__(1024) slg_colgroups_kernel(SegmentDev seg, WarpBatchDev wb, StreamDev sd, uint32_t n_cols) {
+// Pruned executions (ut_max != nullptr): with the k-th score the posting scan left behind, a query's non-essential terms are
+// its longest lowest-priority prefix (priority: larger bound first, ties to the lower slot) whose bounds sum below that
+// score.  A query whose column terms are ALL non-essential sits the column pass out — a doc without an essential term
+// cannot enter the top k — and the others look at v + extra, extra = the bounds of their non-essential SPARSE terms (lists
+// the scan may have dropped, so a doc may hold them unseen).
+__device__ __forceinline__ bool colq_prune(const WarpBatchDev &wb, const float *ut_max, uint32_t qslot, uint32_t qi, uint32_t nt, float &extra) {
+  const unsigned long long thr = wb.thr_key[qi];
+  float ub[kWarpMaxTerms];
+  bool col[kWarpMaxTerms];
+  for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
+    ub[t] = 0.0f;
+    col[t] = false;
+    if (t < nt) {
+      const QTerm &q = wb.qterms[(uint64_t)qslot * kWarpMaxTerms + t];
+      if (q.flags & 1u) ub[t] = __fmul_rn(ut_max[q.uterm], q.weight);
+      col[t] = (q.flags & 5u) == 5u;
+    }
+  }
+  extra = 0.0f;
+  bool any_essential_col = false;
+  for (uint32_t t = 0; t < nt; t++) {
+    float pre = 0.0f;
+    for (uint32_t u = 0; u < nt; u++)
+      if (ub[u] < ub[t] || (ub[u] == ub[t] && u >= t)) pre += ub[u];
+    const bool ne = thr != kThrInit && pre * 1.00002f < __uint_as_float((uint32_t)(thr >> 32));
+    if (col[t]) any_essential_col = any_essential_col || !ne;
+    else if (ne) extra += ub[t];
+  }
+  return any_essential_col;
+}
+
+static __global__ void __launch_bounds__(1024) slg_colgroups_kernel(SegmentDev seg, WarpBatchDev wb, StreamDev sd, uint32_t n_cols, const float *ut_max) {
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
   for (uint32_t c = tid; c < n_cols; c += nthr) sd.col_slot[c] = 0u;
   if (tid == 0) {
@@ -79,8 +110,10 @@ static __global__ void __launch_bounds__(1024) slg_colgroups_kernel(SegmentDev s
   }
   __syncthreads();
   for (uint32_t slot = tid; slot < wb.n_queries; slot += nthr) {
-    const uint32_t nt = wb.qheads[slot].nt;
-    for (uint32_t t = 0; t < nt; t++) {
+    const QHead h = wb.qheads[slot];
+    float extra;
+    if (ut_max && !colq_prune(wb, ut_max, slot, h.qi, h.nt, extra)) continue;
+    for (uint32_t t = 0; t < h.nt; t++) {
       const QTerm &q = wb.qterms[(uint64_t)slot * kWarpMaxTerms + t];
       if ((q.flags & 5u) == 5u) sd.col_slot[q.term] = 1u;
     }
@@ -122,7 +155,14 @@ static __global__ void __launch_bounds__(1024) slg_colgroups_kernel(SegmentDev s
         r.nsp++;
       }
     }
-    if (r.ncol) sd.colq[atomicAdd(sd.n_colq, 1u)] = r;
+    if (r.ncol && ut_max) {
+      // (the k-th score may have risen since the first loop: a query that now tests out names columns that are all in the table)
+      if (!colq_prune(wb, ut_max, slot, h.qi, h.nt, r.extra)) continue;
+      bool all_in = true;
+      for (uint32_t i = 0; i < r.ncol; i++) all_in = all_in && r.slot[i] != 0xFFFFu;
+      if (!all_in) r.off = 1;  // cannot happen (the score only rises); stay safe
+    }
+    if (r.ncol && !r.off) sd.colq[atomicAdd(sd.n_colq, 1u)] = r;
   }
 }
 
