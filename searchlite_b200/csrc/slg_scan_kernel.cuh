@@ -35,6 +35,7 @@ namespace slg {
 
 constexpr uint32_t kScanChunk = 4096;  // postings per scan item
 constexpr int kScanWarps = 8;
+constexpr uint32_t kScanQueue = 512;  // ring: a step queues at most 256 candidates on top of a remainder below 32
 
 struct __align__(16) ScanPair {  // one scanned (query, sparse term): 48 B
   uint64_t base;      // first padded posting index of the term
@@ -237,8 +238,12 @@ __device__ __forceinline__ uint32_t lower_bound_interp(const uint32_t *dp, uint3
 template <bool PRUNE>
 __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev seg, WarpBatchDev wb, ScanDev sc) {
   __shared__ __align__(16) unsigned long long s_cand[kScanWarps][kWarpCand];
+  __shared__ uint32_t s_qidx[kScanWarps][kScanQueue];
+  __shared__ float s_qval[kScanWarps][kScanQueue];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long *cand = s_cand[warp];
+  uint32_t *q_idx = s_qidx[warp];
+  float *q_val = s_qval[warp];
   const uint32_t k = wb.k;
   const uint32_t n_items = *sc.n_items;
   const float inv_docs = 1.0f / (float)max(seg.doc_count, 1u);
@@ -305,6 +310,82 @@ __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev se
         }
       };
       recut();
+      // candidates wait in the warp's queue (posting index, contribution) until a full round of 32 can be verified at once:
+      // a verification is a chain of dependent memory accesses, so what counts is how many docs share each chain
+      uint32_t nq = 0, qhead = 0;
+      auto verify_round = [&](uint32_t n) {
+        bool alive = lane < (int)n;
+        uint32_t idx = 0;
+        float v = 0.0f;
+        if (alive) {
+          idx = q_idx[(qhead + lane) & (kScanQueue - 1u)];
+          v = q_val[(qhead + lane) & (kScanQueue - 1u)];
+        }
+        qhead += n;
+        nq -= n;
+        alive = alive && __float_as_uint(v) >= cut;  // (the k-th score may have risen since the posting was queued)
+        uint32_t doc = 0u;
+        if (alive) doc = __ldg(seg.post_doc + pr.base + idx);
+        n_verified += alive ? 1u : 0u;
+        // ---- verify, cheapest evidence first: the column terms (one gather each), then the other sparse terms (a bit test,
+        // a search when the bit is set), dropping the doc as soon as  known contributions + bounds of the unknown ones  falls
+        // below the k-th score.  The exact score is the sum of the contributions in slot order.
+        const float thr_s = wc.thr == kThrInit ? 0.0f : __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f;
+        float c[kWarpMaxTerms];
+        float known = v, unknown = pr.others;  // (pr.others = the bounds of exactly the terms that can still add: columns + lower-priority sparse)
+#pragma unroll
+        for (int u = 0; u < (int)kWarpMaxTerms; u++) {
+          c[u] = 0.0f;
+          const uint32_t kind = __shfl_sync(0xFFFFFFFFu, m_kind, u);
+          if (kind != 2u) continue;  // (uniform)
+          const uint64_t cb = __shfl_sync(0xFFFFFFFFu, m_base, u);
+          const float w = __shfl_sync(0xFFFFFFFFu, m_w, u), ub = __shfl_sync(0xFFFFFFFFu, m_ub, u);
+          if (alive) {
+            c[u] = __fmul_rn(__ldg(seg.cols + cb + doc), w);
+            known += c[u];
+            unknown -= ub;
+          }
+        }
+        alive = alive && (known + fmaxf(unknown, 0.0f)) * 1.0001f >= thr_s;
+        bool stand_back = false;
+#pragma unroll
+        for (int u = 0; u < (int)kWarpMaxTerms; u++) {
+          const uint32_t kind = __shfl_sync(0xFFFFFFFFu, m_kind, u);
+          if (kind != 1u || u == (int)t) continue;  // (uniform)
+          if (!__any_sync(0xFFFFFFFFu, alive)) break;
+          const uint64_t pb = __shfl_sync(0xFFFFFFFFu, m_base, u), bo = __shfl_sync(0xFFFFFFFFu, m_bits, u);
+          const uint32_t dfu = __shfl_sync(0xFFFFFFFFu, m_df, u);
+          const float w = __shfl_sync(0xFFFFFFFFu, m_w, u), ub = __shfl_sync(0xFFFFFFFFu, m_ub, u),
+                      dens = __shfl_sync(0xFFFFFFFFu, m_dens, u);
+          const bool higher = ub > my_ub || (ub == my_ub && u < (int)t);  // a holder of higher priority offers the doc itself
+          if (alive) {
+            n_lookups++;
+            const uint32_t *dp = seg.post_doc + pb;
+            // one bit per doc says whether the list holds it at all (one sector instead of a search: usually it does not)
+            bool held = true;
+            if (bo != ~0ull) held = (__ldg(seg.pres_bits + bo + (doc >> 5)) >> (doc & 31)) & 1u;
+            const uint32_t at = held ? lower_bound_interp(dp, dfu, doc, dens) : dfu;
+            if (at < dfu && __ldg(dp + at) == doc) {
+              if (higher) stand_back = true;
+              c[u] = __fmul_rn(__ldg(wb.scores + pb + at), w);
+              known += c[u];
+            }
+            if (!higher) unknown -= ub;
+            alive = !stand_back && (known + fmaxf(unknown, 0.0f)) * 1.0001f >= thr_s;
+          }
+        }
+        if (__any_sync(0xFFFFFFFFu, alive)) {
+          float sx = 0.0f;
+#pragma unroll
+          for (int u = 0; u < (int)kWarpMaxTerms; u++) {
+            const float cu = u == (int)t ? v : c[u];
+            if (cu != 0.0f) sx = __fadd_rn(sx, cu);
+          }
+          wc.offer(seg, wb, pr.qi, pr.filter, alive, doc, sx);
+          recut();
+        }
+        __syncwarp();
+      };
 #pragma unroll 1
       for (uint32_t b = i0; b < i1; b += 256) {
         // two 128-posting steps in flight
@@ -320,77 +401,30 @@ __global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev se
           const uint32_t idx = (e < 4 ? ia : ib) + (e & 3);
           if (__float_as_uint(x[e]) >= cut && x[e] != 0.0f && idx < i1) todo |= 1u << e;  // (16-byte pieces may reach past the list's end)
         }
-        while (__any_sync(0xFFFFFFFFu, todo != 0u)) {
-          const bool had = todo != 0u;
-          const uint32_t e = had ? __ffs(todo) - 1 : 0u;
-          todo &= todo - 1u;
-          float v = 0.0f;
+        if (!__any_sync(0xFFFFFFFFu, todo != 0u)) continue;
+        // queue this step's candidates: every lane appends its own (an exclusive scan of the counts gives the places)
+        {
+          const uint32_t mine = __popc(todo);
+          uint32_t incl = mine;
 #pragma unroll
-          for (int z = 0; z < 8; z++)
-            if (e == (uint32_t)z) v = x[z];
-          bool alive = had && __float_as_uint(v) >= cut;
-          if (!__any_sync(0xFFFFFFFFu, alive)) continue;
-          uint32_t doc = 0u;
-          if (alive) doc = __ldg(seg.post_doc + pr.base + (e < 4 ? ia : ib) + (e & 3));
-          n_verified += alive ? 1u : 0u;
-          // ---- verify, cheapest evidence first: the column terms (one gather each), then the other sparse terms (a search
-          // each), dropping the doc as soon as  known contributions + bounds of the unknown ones  falls below the k-th score.
-          // The exact score is the sum of the contributions in slot order.
-          const float thr_s = wc.thr == kThrInit ? 0.0f : __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f;
-          float c[kWarpMaxTerms];
-          float known = v, unknown = pr.others;  // (pr.others = the bounds of exactly the terms that can still add: columns + lower-priority sparse)
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += nb;
+          }
+          uint32_t at = qhead + nq + incl - mine;
 #pragma unroll
-          for (int u = 0; u < (int)kWarpMaxTerms; u++) {
-            c[u] = 0.0f;
-            const uint32_t kind = __shfl_sync(0xFFFFFFFFu, m_kind, u);
-            if (kind != 2u) continue;  // (uniform)
-            const uint64_t cb = __shfl_sync(0xFFFFFFFFu, m_base, u);
-            const float w = __shfl_sync(0xFFFFFFFFu, m_w, u), ub = __shfl_sync(0xFFFFFFFFu, m_ub, u);
-            if (alive) {
-              c[u] = __fmul_rn(__ldg(seg.cols + cb + doc), w);
-              known += c[u];
-              unknown -= ub;
+          for (int e = 0; e < 8; e++)
+            if ((todo >> e) & 1u) {
+              q_idx[at & (kScanQueue - 1u)] = (e < 4 ? ia : ib) + (e & 3);
+              q_val[at & (kScanQueue - 1u)] = x[e];
+              at++;
             }
-          }
-          alive = alive && (known + fmaxf(unknown, 0.0f)) * 1.0001f >= thr_s;
-          bool stand_back = false;
-#pragma unroll
-          for (int u = 0; u < (int)kWarpMaxTerms; u++) {
-            const uint32_t kind = __shfl_sync(0xFFFFFFFFu, m_kind, u);
-            if (kind != 1u || u == (int)t) continue;  // (uniform)
-            if (!__any_sync(0xFFFFFFFFu, alive)) break;
-            const uint64_t pb = __shfl_sync(0xFFFFFFFFu, m_base, u), bo = __shfl_sync(0xFFFFFFFFu, m_bits, u);
-            const uint32_t dfu = __shfl_sync(0xFFFFFFFFu, m_df, u);
-            const float w = __shfl_sync(0xFFFFFFFFu, m_w, u), ub = __shfl_sync(0xFFFFFFFFu, m_ub, u),
-                        dens = __shfl_sync(0xFFFFFFFFu, m_dens, u);
-            const bool higher = ub > my_ub || (ub == my_ub && u < (int)t);  // a holder of higher priority offers the doc itself
-            if (alive) {
-              n_lookups++;
-              const uint32_t *dp = seg.post_doc + pb;
-              // one bit per doc says whether the list holds it at all (one sector instead of a search: usually it does not)
-              bool held = true;
-              if (bo != ~0ull) held = (__ldg(seg.pres_bits + bo + (doc >> 5)) >> (doc & 31)) & 1u;
-              const uint32_t at = held ? lower_bound_interp(dp, dfu, doc, dens) : dfu;
-              if (at < dfu && __ldg(dp + at) == doc) {
-                if (higher) stand_back = true;
-                c[u] = __fmul_rn(__ldg(wb.scores + pb + at), w);
-                known += c[u];
-              }
-              if (!higher) unknown -= ub;
-              alive = !stand_back && (known + fmaxf(unknown, 0.0f)) * 1.0001f >= thr_s;
-            }
-          }
-          if (!__any_sync(0xFFFFFFFFu, alive)) continue;
-          float s = 0.0f;
-#pragma unroll
-          for (int u = 0; u < (int)kWarpMaxTerms; u++) {
-            const float cu = u == (int)t ? v : c[u];
-            if (cu != 0.0f) s = __fadd_rn(s, cu);
-          }
-          wc.offer(seg, wb, pr.qi, pr.filter, alive, doc, s);
-          recut();
+          nq += __shfl_sync(0xFFFFFFFFu, incl, 31);
+          __syncwarp();
         }
+        while (nq >= 32u) verify_round(32u);
       }
+      while (nq) verify_round(min(nq, 32u));
       wc.merge(wb, pr.qi);
     }
     item = __shfl_sync(0xFFFFFFFFu, next_item, 0);
