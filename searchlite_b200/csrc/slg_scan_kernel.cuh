@@ -212,31 +212,8 @@ static __global__ void __launch_bounds__(256) slg_scan_items_kernel(ScanDev sc) 
   sc.items[i] = lo;
 }
 
-// position of the first posting with doc id >= doc in a list of n ascending doc ids.  Lists are near-uniform samples of the
-// doc range, so a few guesses by local density (position + (doc - d) * n / doc_count) close in on the place before a binary
-// search finishes in the bracket that is left; the bracket invariant keeps the result exact for any list.
-__device__ __forceinline__ uint32_t lower_bound_interp(const uint32_t *dp, uint32_t n, uint32_t doc, float dens) {
-  uint32_t lo = 0, hi = n;  // dp[i] < doc for i < lo, dp[i] >= doc for i >= hi
-  float est = (float)doc * dens;
-#pragma unroll 1
-  for (int it = 0; it < 4 && lo < hi; it++) {
-    const uint32_t pos = min(max(est < 0.0f ? 0u : (uint32_t)est, lo), hi - 1u);
-    const uint32_t d = __ldg(dp + pos);
-    if (d < doc) lo = pos + 1u;
-    else hi = pos;
-    if (d == doc) break;
-    est = (float)pos + ((float)doc - (float)d) * dens;
-  }
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(dp + mid) < doc) lo = mid + 1u;
-    else hi = mid;
-  }
-  return lo;
-}
-
 template <bool PRUNE>
-__global__ void __launch_bounds__(kScanWarps * 32) slg_scan_kernel(SegmentDev seg, WarpBatchDev wb, ScanDev sc) {
+__global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev seg, WarpBatchDev wb, ScanDev sc) {
   __shared__ __align__(16) unsigned long long s_cand[kScanWarps][kWarpCand];
   __shared__ uint32_t s_qidx[kScanWarps][kScanQueue];
   __shared__ float s_qval[kScanWarps][kScanQueue];

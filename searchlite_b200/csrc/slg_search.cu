@@ -605,7 +605,7 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       for (int i = 0; i < 4; i++) count_launch(ix);
       SLG_CUDA(ix, cudaGetLastError());
       SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));  // (the scoring time of this path starts here)
-      SLG_CUDA(ix, launch_scan(prune, s->dev, wb, sc, ix->n_sm * 8, st));
+      SLG_CUDA(ix, launch_scan(prune, s->dev, wb, sc, ix->n_sm * 4, st));
       count_launch(ix);
       if (s->n_cols && !(ix->dbg & 4u)) {
         slg_colgroups_kernel<<<1, 1024, 0, st>>>(s->dev, wb, sdv, s->n_cols, prune ? bt->ut_max : nullptr);

@@ -765,6 +765,29 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
   }
 }
 
+// position of the first posting with doc id >= doc in a list of n ascending doc ids.  Lists are near-uniform samples of the
+// doc range, so a few guesses by local density (position + (doc - d) * n / doc_count) close in on the place before a binary
+// search finishes in the bracket that is left; the bracket invariant keeps the result exact for any list.
+__device__ __forceinline__ uint32_t lower_bound_interp(const uint32_t *dp, uint32_t n, uint32_t doc, float dens) {
+  uint32_t lo = 0, hi = n;  // dp[i] < doc for i < lo, dp[i] >= doc for i >= hi
+  float est = (float)doc * dens;
+#pragma unroll 1
+  for (int it = 0; it < 4 && lo < hi; it++) {
+    const uint32_t pos = min(max(est < 0.0f ? 0u : (uint32_t)est, lo), hi - 1u);
+    const uint32_t d = __ldg(dp + pos);
+    if (d < doc) lo = pos + 1u;
+    else hi = pos;
+    if (d == doc) break;
+    est = (float)pos + ((float)doc - (float)d) * dens;
+  }
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(dp + mid) < doc) lo = mid + 1u;
+    else hi = mid;
+  }
+  return lo;
+}
+
 // exact score of one doc per lane: every term of the query in slot order (brute_force on the doc's lists).  holders: bit u set
 // when sparse term u holds the doc.
 __device__ __forceinline__ float verify_doc(const SegmentDev &seg, const WarpBatchDev &wb, const QTerm *qts, uint32_t nt, bool have, uint32_t doc,
@@ -784,12 +807,13 @@ __device__ __forceinline__ float verify_doc(const SegmentDev &seg, const WarpBat
           const uint64_t base = __ldg(&qts[u].base);
           const uint32_t *dp = seg.post_doc + base;
           const uint32_t end = __ldg(seg.term_df + term);
-          uint32_t lo = 0, hi = end;
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(dp + mid) < doc) lo = mid + 1;
-            else hi = mid;
+          // one bit per doc says whether the list holds it at all; a search only when it does
+          bool held = true;
+          if (seg.term_bits) {
+            const int32_t row = __ldg(seg.term_bits + term);
+            if (row >= 0) held = (__ldg(seg.pres_bits + (uint64_t)row * seg.bits_stride + (doc >> 5)) >> (doc & 31)) & 1u;
           }
+          const uint32_t lo = held ? lower_bound_interp(dp, end, doc, (float)end / (float)max(seg.doc_count, 1u)) : end;
           if (lo < end && __ldg(dp + lo) == doc) {
             c = __ldg(wb.scores + base + lo);
             holders |= 1u << u;
