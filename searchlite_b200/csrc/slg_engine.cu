@@ -127,6 +127,7 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
   d.col_tmax = nullptr;
   d.tmax_stride = 0;
   d.col_stride = 0;
+  d.term_ub = nullptr;
   d.term_bits = nullptr;
   d.pres_bits = nullptr;
   d.bits_stride = 0;
@@ -198,6 +199,19 @@ int32_t finish_segment(slg_index *ix, std::unique_ptr<Segment> seg, const int64_
         d.tmax_stride = s->tmax_stride;
       }
     }
+  }
+  // the largest contribution of every term: the bounds of the pruned executions (wand.rs:126-135 takes the stored max tf at the
+  // segment's minimum doc length; this is the maximum over the postings themselves, tighter and safe for the same reason)
+  if (d.post_score && s->n_terms) {
+    SLG_CUDA(ix, s->term_ub.alloc(s->n_terms * 4));
+    SLG_CUDA(ix, cudaMemsetAsync(s->term_ub.p, 0, s->n_terms * 4, st));
+    ScanDev sc{};
+    sc.ut_term = nullptr;
+    sc.ut_max = s->term_ub.as<float>();
+    slg_term_max_kernel<<<dim3((unsigned)((s->n_terms + 7) / 8), kMaxSlices), 256, 0, st>>>(d, sc, (uint32_t)s->n_terms);
+    count_launch(ix);
+    SLG_CUDA(ix, cudaGetLastError());
+    d.term_ub = s->term_ub.as<float>();
   }
   // presence bitmaps for the mid-dense terms without a column: the posting scan's verification asks "does this list hold
   // the doc" far more often than the answer is yes, and a bit test is one 32-byte sector where a search is several

@@ -114,7 +114,7 @@ struct Segment {
   float k1 = 0.9f, b = 0.4f, avgdl = 0, live_docs = 0, min_doc_len = 1;
   std::vector<uint32_t> h_df;  // host copy (query ordering, validation)
   DevBuf post_doc, post_tf, term_start, term_df, term_idf, term_max_tf, term_wide, tf_wide, term_blk, blk_max_doc,
-      blk_max_tf, nk, live_bits, post_score, mb_max, cols, term_col, col_tmax, term_bits, pres_bits;
+      blk_max_tf, nk, live_bits, post_score, mb_max, cols, term_col, col_tmax, term_bits, pres_bits, term_ub;
   uint32_t n_bitmaps = 0;
   uint32_t n_cols = 0, tmax_stride = 0;
   uint64_t col_stride = 0;
@@ -145,7 +145,7 @@ struct Segment {
   size_t resident() const {
     return post_doc.bytes + post_tf.bytes + term_start.bytes + term_df.bytes + term_idf.bytes + term_max_tf.bytes +
            term_wide.bytes + tf_wide.bytes + term_blk.bytes + blk_max_doc.bytes + blk_max_tf.bytes + nk.bytes + term_field.bytes +
-           live_bits.bytes + post_score.bytes + mb_max.bytes + cols.bytes + term_col.bytes + col_tmax.bytes + term_bits.bytes + pres_bits.bytes +
+           live_bits.bytes + post_score.bytes + mb_max.bytes + cols.bytes + term_col.bytes + col_tmax.bytes + term_bits.bytes + pres_bits.bytes + term_ub.bytes +
            pos_begin.bytes + pos.bytes;
   }
 };

@@ -72,7 +72,7 @@ static __global__ void __launch_bounds__(256) slg_term_max_kernel(SegmentDev seg
   const uint32_t u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (u >= n_uterms) return;
-  const uint32_t term = sc.ut_term[u];
+  const uint32_t term = sc.ut_term ? sc.ut_term[u] : u;  // (no list of terms: every term of the segment, at load)
   if (term >= seg.n_terms) return;
   const uint32_t df = seg.term_df[term];
   const uint32_t quads = (df + 3) >> 2;  // (the padding of a list is zero: whole 16-byte pieces up to the 32-posting boundary are safe to read)
@@ -87,6 +87,105 @@ static __global__ void __launch_bounds__(256) slg_term_max_kernel(SegmentDev seg
   }
   m = __reduce_max_sync(0xFFFFFFFFu, m);
   if (lane == 0 && m) atomicMax(reinterpret_cast<uint32_t *>(sc.ut_max) + u, m);
+}
+
+// pruned executions: the same maxima were reduced once at load for every term (seg.term_ub)
+static __global__ void slg_term_ub_gather_kernel(SegmentDev seg, ScanDev sc, uint32_t n_uterms) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_uterms) return;
+  const uint32_t term = sc.ut_term[u];
+  sc.ut_max[u] = term < seg.n_terms ? seg.term_ub[term] : 0.0f;
+}
+
+// pruned executions: the column terms of the few queries that still have an essential one.  Warp per (query, slice of
+// the doc range): 32 blocks of 512 docs at a time, lane = block: the sum of the columns' exact block maxima (seg.col_tmax,
+// slot order) + extra below the k-th score means no doc of the block can enter the top k and the block is not read; the
+// others are summed per doc (16 docs per lane, slot order) and the docs that can still qualify are verified exactly.
+constexpr uint32_t kColSlices = 64;
+template <int UNUSED>
+__global__ void __launch_bounds__(256) slg_columns_pruned_kernel(SegmentDev seg, WarpBatchDev wb, StreamDev sd) {
+  __shared__ __align__(16) unsigned long long s_cand[8][kWarpCand];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_colq = *sd.n_colq;
+  const uint32_t wid = blockIdx.x * 8 + warp;
+  const uint32_t qidx = wid / kColSlices, slice = wid % kColSlices;
+  if (qidx >= n_colq) return;
+  const ColQ cq = sd.colq[qidx];
+  const QTerm *qts = wb.qterms + (uint64_t)cq.qslot * kWarpMaxTerms;
+  const uint32_t nt = (uint32_t)cq.nsp + cq.ncol;
+  const uint32_t n_blocks = (seg.doc_count + 511u) >> 9;
+  const uint32_t per = (n_blocks + kColSlices - 1) / kColSlices;
+  const uint32_t b0 = slice * per, b1 = min(n_blocks, b0 + per);
+  WarpCand wc;
+  wc.begin(s_cand[warp], ld_cg_u64(wb.thr_key + cq.qi), wb.k, lane);
+  auto cut_of = [&]() {
+    if (wc.thr == kThrInit) return 0u;
+    const float cf = __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f - cq.extra * 1.00002f;
+    return cf > 0.0f ? __float_as_uint(cf) : 0u;
+  };
+  for (uint32_t bb = b0; bb < b1; bb += 32) {
+    const uint32_t blk = bb + lane;
+    float bound = 0.0f;
+    if (blk < b1)
+      for (uint32_t i = 0; i < cq.ncol; i++) {
+        const QTerm &q = qts[cq.nsp + i];
+        bound = __fadd_rn(bound, __fmul_rn(__ldg(seg.col_tmax + (uint64_t)q.term * seg.tmax_stride + blk), q.weight));
+      }
+    uint32_t open = __ballot_sync(0xFFFFFFFFu, blk < b1 && bound != 0.0f && __float_as_uint(bound) >= cut_of());
+    while (open) {
+      const uint32_t d0 = (bb + (__ffs(open) - 1)) << 9;
+      open &= open - 1;
+      float4 v[4];
+#pragma unroll
+      for (int x = 0; x < 4; x++) v[x] = make_float4(0, 0, 0, 0);
+      for (uint32_t i = 0; i < cq.ncol; i++) {
+        const QTerm &q = qts[cq.nsp + i];
+        const float4 *p = reinterpret_cast<const float4 *>(seg.cols + q.sc_base + d0) + lane;
+        const float w = q.weight;
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+          const float4 c = __ldg(p + x * 32);
+          v[x].x = __fadd_rn(v[x].x, __fmul_rn(c.x, w));
+          v[x].y = __fadd_rn(v[x].y, __fmul_rn(c.y, w));
+          v[x].z = __fadd_rn(v[x].z, __fmul_rn(c.z, w));
+          v[x].w = __fadd_rn(v[x].w, __fmul_rn(c.w, w));
+        }
+      }
+      uint32_t cut = cut_of();
+      uint32_t todo = 0u;
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        const uint32_t bx[4] = {__float_as_uint(v[x].x), __float_as_uint(v[x].y), __float_as_uint(v[x].z), __float_as_uint(v[x].w)};
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          if (bx[e] >= cut && bx[e] != 0u && d0 + x * 128 + lane * 4 + e < seg.doc_count) todo |= 1u << (x * 4 + e);
+      }
+      while (__any_sync(0xFFFFFFFFu, todo != 0u)) {
+        const uint32_t el = todo ? __ffs(todo) - 1 : 0u;
+        const bool had = todo != 0u;
+        todo &= todo - 1u;
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+          if (el == (uint32_t)x * 4 + 0) bits = __float_as_uint(v[x].x);
+          if (el == (uint32_t)x * 4 + 1) bits = __float_as_uint(v[x].y);
+          if (el == (uint32_t)x * 4 + 2) bits = __float_as_uint(v[x].z);
+          if (el == (uint32_t)x * 4 + 3) bits = __float_as_uint(v[x].w);
+        }
+        const uint32_t doc = d0 + (el >> 2) * 128 + lane * 4 + (el & 3u);
+        cut = cut_of();
+        const bool pass = had && bits >= cut;
+        if (!__any_sync(0xFFFFFFFFu, pass)) continue;
+        float s = __uint_as_float(bits);
+        if (cq.nsp) {
+          uint32_t holders = 0u;
+          s = verify_doc(seg, wb, qts, nt, pass, doc, holders);  // (a sparse list the scan dropped may hold the doc)
+        }
+        wc.offer(seg, wb, cq.qi, cq.filter, pass, doc, s);
+      }
+    }
+  }
+  wc.merge(wb, cq.qi);
 }
 
 // per query slot: the scanned pairs with their bounds.  Thread per query.

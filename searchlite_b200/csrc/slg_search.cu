@@ -597,8 +597,12 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       sdv.stage_cap = ix->stage_cap;
       sdv.strict = 0;
       sdv.counters = bt->item_counters;
-      SLG_CUDA(ix, cudaMemsetAsync(bt->ut_max, 0, (size_t)bt->U * 4, st));
-      slg_term_max_kernel<<<dim3((bt->U + 7) / 8, (ix->dbg & 2u) ? 1u : kMaxSlices), 256, 0, st>>>(s->dev, sc, bt->U);
+      if (prune && s->dev.term_ub) {
+        slg_term_ub_gather_kernel<<<(bt->U + 255) / 256, 256, 0, st>>>(s->dev, sc, bt->U);
+      } else {  // exhaustive: no index-time bound, the maxima are reduced from the batch's posting scores
+        SLG_CUDA(ix, cudaMemsetAsync(bt->ut_max, 0, (size_t)bt->U * 4, st));
+        slg_term_max_kernel<<<dim3((bt->U + 7) / 8, kMaxSlices), 256, 0, st>>>(s->dev, sc, bt->U);
+      }
       slg_scan_pairs_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, wb, sc, ix->dbg);
       slg_scan_order_kernel<<<1, 1024, 0, st>>>(wb, sc);
       if (bt->scan_items_cap) slg_scan_items_kernel<<<(bt->scan_items_cap + 255) / 256, 256, 0, st>>>(sc);
