@@ -621,7 +621,15 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
         sdv.col_resident = (uint32_t)std::min<size_t>(s->n_cols, budget / (2 * kColBlock * 4));
         const size_t csmem = column_smem(sdv.col_resident, sdv.n_smax);
         const uint32_t n_cblocks = (s->doc_count + kColBlock - 1) / kColBlock;
-        SLG_CUDA(ix, launch_score_columns(prune, s->dev, wb, sdv, csmem, (int)std::min<uint32_t>((uint32_t)ix->n_sm, n_cblocks), st));
+        if (prune) {
+          // few queries keep an essential column term: one warp per (query, slice of the doc range), blocks skipped by col_tmax
+          (void)csmem;
+          (void)n_cblocks;
+          slg_columns_pruned_kernel<0><<<(Q * kColSlices + 7) / 8, 256, 0, st>>>(s->dev, wb, sdv);
+          SLG_CUDA(ix, cudaGetLastError());
+        } else {
+          SLG_CUDA(ix, launch_score_columns(false, s->dev, wb, sdv, csmem, (int)std::min<uint32_t>((uint32_t)ix->n_sm, n_cblocks), st));
+        }
         count_launch(ix);
       }
       ix->ctr.score_launches++;
