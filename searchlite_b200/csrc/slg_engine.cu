@@ -407,6 +407,7 @@ int32_t slg_close(slg_index_t *ix) {
   cudaSetDevice(ix->device);
   cudaStreamSynchronize(ix->stream);
   if (ix->pinned) cudaFreeHost(ix->pinned);
+  if (ix->merge_pinned) cudaFreeHost(ix->merge_pinned);
   ix->segs.clear();
   for (auto &ev : ix->ev)
     if (ev) cudaEventDestroy(ev);

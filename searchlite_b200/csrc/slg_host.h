@@ -171,6 +171,8 @@ struct slg_index {
   void *pinned = nullptr;        // host staging buffer kept between batches (one batch at a time uses it)
   size_t pinned_bytes = 0;
   bool pinned_busy = false;
+  void *merge_pinned = nullptr;  // staging of slg_merge_gathered*
+  size_t merge_pinned_bytes = 0;
   uint32_t tile_docs = 16384;
   uint32_t ctas_per_sm = 0;  // 0 = as many as shared memory allows
   uint32_t sub_docs = 2048;  // warp kernel: docs per warp-private accumulator

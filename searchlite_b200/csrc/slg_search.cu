@@ -930,13 +930,12 @@ int32_t slg_merge_gathered_packed(slg_index_t *ix, const void *dev_gathered, uin
   PoolScope pool_scope(st);  // per-call buffers from the stream-ordered pool
   DevBuf ob;
   SLG_CUDA(ix, ob.alloc(hb + cb));
-  if (ix->pinned_busy || ix->pinned_bytes < hb + cb) {
-    if (ix->pinned_busy) return fail(ix, SLG_ERR_INVALID, "free the batch before merging gathered results on this handle, or merge on another handle");
-    if (ix->pinned) cudaFreeHost(ix->pinned);
-    ix->pinned = nullptr;
-    ix->pinned_bytes = 0;
-    SLG_CUDA(ix, cudaMallocHost(&ix->pinned, hb + cb));
-    ix->pinned_bytes = hb + cb;
+  if (ix->merge_pinned_bytes < hb + cb) {  // the merge has its own staging buffer: a prepared batch may hold the handle's other one
+    if (ix->merge_pinned) cudaFreeHost(ix->merge_pinned);
+    ix->merge_pinned = nullptr;
+    ix->merge_pinned_bytes = 0;
+    SLG_CUDA(ix, cudaMallocHost(&ix->merge_pinned, hb + cb));
+    ix->merge_pinned_bytes = hb + cb;
   }
   SLG_CUDA(ix, cudaFuncSetAttribute(slg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
   slg_merge_kernel<<<n_queries, kThreads, msmem, st>>>(static_cast<const uint32_t *>(dev_gathered), n_shards, n_queries, k,
@@ -944,10 +943,10 @@ int32_t slg_merge_gathered_packed(slg_index_t *ix, const void *dev_gathered, uin
                                                        reinterpret_cast<uint32_t *>(ob.as<unsigned char>() + hb));
   count_launch(ix);
   SLG_CUDA(ix, cudaGetLastError());
-  SLG_CUDA(ix, cudaMemcpyAsync(ix->pinned, ob.p, hb + cb, cudaMemcpyDeviceToHost, st));
+  SLG_CUDA(ix, cudaMemcpyAsync(ix->merge_pinned, ob.p, hb + cb, cudaMemcpyDeviceToHost, st));
   SLG_CUDA(ix, cudaStreamSynchronize(st));
-  std::memcpy(out_hits, ix->pinned, hb);
-  std::memcpy(out_counts, static_cast<unsigned char *>(ix->pinned) + hb, cb);
+  std::memcpy(out_hits, ix->merge_pinned, hb);
+  std::memcpy(out_counts, static_cast<unsigned char *>(ix->merge_pinned) + hb, cb);
   ix->ctr.last_d2h_bytes = hb + cb;
   return SLG_OK;
 }
