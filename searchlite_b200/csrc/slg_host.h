@@ -301,6 +301,10 @@ struct slg_batch {
   bool staged = false;                // the (doc, score) stream form of the warp kernel applies
   uint32_t max_terms = 0;
   bool use_warp = false, can_items = false, canonical = false;
+  bool big_k = false;                 // k > 32 on the flat posting scan: candidate pools
+  unsigned long long *pool_keys = nullptr;
+  uint32_t *pool_count = nullptr, *pool_lock = nullptr;
+  uint32_t pool_cap = 0;
   bool has_cursor = false;            // some query carries a search-after cursor
   std::vector<uint8_t> h_has_cursor;
   uint32_t n_cursor_segs = 0;

@@ -105,6 +105,7 @@ constexpr uint32_t kColSlices = 64;
 template <int UNUSED>
 __global__ void __launch_bounds__(256) slg_columns_pruned_kernel(SegmentDev seg, WarpBatchDev wb, StreamDev sd) {
   __shared__ __align__(16) unsigned long long s_cand[8][kWarpCand];
+  __shared__ uint32_t s_hist[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_colq = *sd.n_colq;
   const uint32_t wid = blockIdx.x * 8 + warp;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) slg_columns_pruned_kernel(SegmentDev seg,
   const uint32_t per = (n_blocks + kColSlices - 1) / kColSlices;
   const uint32_t b0 = slice * per, b1 = min(n_blocks, b0 + per);
   WarpCand wc;
-  wc.begin(s_cand[warp], ld_cg_u64(wb.thr_key + cq.qi), wb.k, lane);
+  wc.begin(s_cand[warp], ld_cg_u64(wb.thr_key + cq.qi), wb.k, lane, 1u, wb.pool_keys ? s_hist[warp] : nullptr);
   auto cut_of = [&]() {
     if (wc.thr == kThrInit) return 0u;
     const float cf = __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f - cq.extra * 1.00002f;
@@ -314,6 +315,7 @@ static __global__ void __launch_bounds__(256) slg_scan_items_kernel(ScanDev sc) 
 template <bool PRUNE>
 __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev seg, WarpBatchDev wb, ScanDev sc) {
   __shared__ __align__(16) unsigned long long s_cand[kScanWarps][kWarpCand];
+  __shared__ uint32_t s_hist[kScanWarps][256];
   __shared__ uint32_t s_qidx[kScanWarps][kScanQueue];
   __shared__ float s_qval[kScanWarps][kScanQueue];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
       n_dropped++;  // this term and everything of lower priority cannot lift a doc into the top k
     } else {
       n_done++;
-      wc.begin(cand, thr0, k, lane);
+      wc.begin(cand, thr0, k, lane, 0u, wb.pool_keys ? s_hist[warp] : nullptr);
       const uint32_t qslot = pr.qslot_t >> 3, t = pr.qslot_t & 7u;
       const QTerm *qts = wb.qterms + (uint64_t)qslot * kWarpMaxTerms;
       const uint32_t nt = __ldg(&wb.qheads[qslot].nt);

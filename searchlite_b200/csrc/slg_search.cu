@@ -228,9 +228,13 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
                 "the items kernel handles plain OR queries without a ScorePlan, k <= %u, <= %u terms per query, resident scores, sub_docs <= 4096",
                 kWarpMaxK, kWarpMaxTerms);
   bt->can_items = items_ok && (ix->kernel_choice == 0 || ix->kernel_choice == 3);
+  // k up to SLG_MAX_K on the flat posting scan: candidate pools + radix select instead of the warp's sorted top-k
+  bt->big_k = k > kWarpMaxK && bt->max_terms <= kWarpMaxTerms && !matcher && all_scores && !bt->has_plan && ix->scan_kernels && ix->stream_kernels &&
+              (ix->kernel_choice == 0 || ix->kernel_choice == 3);
+  if (bt->big_k) bt->can_items = true;
   bt->canonical = bt->can_items;
   bt->use_warp = bt->can_items || ix->kernel_choice == 2 || (ix->kernel_choice == 0 && small);
-  if (bt->use_warp && !small)
+  if (bt->use_warp && !small && !bt->big_k)
     return fail(ix, SLG_ERR_UNSUPPORTED, "the warp kernel handles k <= %u and <= %u terms per query", kWarpMaxK, kWarpMaxTerms);
   bt->staged = all_scores && !matcher && bt->U > 0;
 
@@ -291,9 +295,13 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   const size_t o_rng = carve((size_t)std::max(bt->U, 1u) * (max_tiles + 1) * 4);
   const size_t o_ub = (exec != SLG_EXEC_BM25 || bt->can_items) ? carve((size_t)std::max(bt->U, 1u) * max_tiles * 4) : 0;
   // state block, reset per segment: thr_key [Q] u64 | topk_count [Q] | lock [Q] | work_counter [64] | n_items [2]
-  const size_t state_words = (size_t)n_queries * 2 + 64 + 2;
+  uint32_t kp = 1;
+  while (kp < k) kp <<= 1;
+  bt->pool_cap = bt->big_k ? 2 * kp : 0;
+  const size_t state_words = (size_t)n_queries * 2 + 64 + 2 + (bt->big_k ? (size_t)n_queries * 4 : 0);
   const size_t o_thr = carve((size_t)n_queries * 8 + state_words * 4);
   const size_t o_topk = carve((size_t)n_queries * k * 8);
+  const size_t o_pools = bt->big_k ? carve((size_t)n_queries * 2 * bt->pool_cap * 8) : 0;
   const size_t o_stats = carve((size_t)n_queries * 5 * 8 + 64);  // [Q][4] counters, [Q] accepted docs, then the items counters [4]
   const size_t o_saw = bt->has_cursor ? carve((size_t)n_queries * 4) : 0;
   const size_t o_qterms = bt->use_warp ? carve((size_t)n_queries * kWarpMaxTerms * sizeof(QTerm)) : 0;
@@ -341,6 +349,9 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bt->lock = bt->topk_count + n_queries;
   bt->work_counter = bt->lock + n_queries;
   bt->n_items = bt->work_counter + 64;
+  bt->pool_count = bt->big_k ? bt->n_items + 2 : nullptr;
+  bt->pool_lock = bt->big_k ? bt->pool_count + (size_t)n_queries * 2 : nullptr;
+  bt->pool_keys = bt->big_k ? reinterpret_cast<unsigned long long *>(base + o_pools) : nullptr;
   bt->topk_keys = reinterpret_cast<unsigned long long *>(base + o_topk);
   bt->stats = reinterpret_cast<unsigned long long *>(base + o_stats);
   bt->item_counters = bt->stats + (size_t)n_queries * 5;
@@ -408,7 +419,7 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
   cudaStream_t st = ix->stream;
   const bool prune = bt->exec != SLG_EXEC_BM25;
   const uint32_t Q = bt->Q, k = bt->k;
-  const bool run_items = bt->can_items && !bt->want_stats;
+  const bool run_items = bt->can_items && !bt->want_stats && !(bt->big_k && (!ix->scan_kernels || (ix->strict_accumulate && bt->exec == SLG_EXEC_BM25)));
   // flat posting scan + column pass: the automatic choice; scan_kernels 0 keeps the sub-tile kernels (stream / items)
   const bool run_scan = run_items && ix->scan_kernels && bt->colq != nullptr && !(ix->strict_accumulate && !prune);
   const bool two_step = !(do_seeds && do_sweep);
@@ -416,7 +427,9 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
     return fail(ix, SLG_ERR_UNSUPPORTED, "the two-step run (seeds, threshold exchange, sweep) needs one segment per handle, a pruned execution and the items kernel");
   unsigned char *dp = bt->d_pack;
   size_t smem = 0;
-  if (!bt->use_warp) {
+  const bool run_scan_pre = bt->can_items && !bt->want_stats && ix->scan_kernels && bt->colq != nullptr && !(ix->strict_accumulate && !prune);
+  const bool warp_path = bt->use_warp && !(bt->big_k && !run_scan_pre);  // k > 32 without the scan: the CTA-per-item kernel
+  if (!warp_path) {
     int32_t rc = bt->has_plan ? select_smem(ix, bt->plan_docs, bt->cap, bt->matcher, &smem, bt->max_leaves)
                               : select_smem(ix, ix->tile_docs, bt->cap, bt->matcher, &smem);
     if (rc) return rc;
@@ -512,6 +525,10 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       wb.match_count = bd.match_count;
       wb.q_cursor = bd.q_cursor;
       wb.q_saw = bd.q_saw;
+      wb.pool_keys = run_scan ? bt->pool_keys : nullptr;
+      wb.pool_count = bt->pool_count;
+      wb.pool_lock = bt->pool_lock;
+      wb.pool_cap = bt->pool_cap;
       // (plan batches: the matcher form of the kernel unless the staged plain-OR form applies — size for the larger)
       wsmem = run_items ? (size_t)warps * warp_kernel_smem_per_warp(wb.sub_docs, false, true, 1)
                         : (size_t)warps * warp_kernel_smem_per_warp(wb.sub_docs, bt->matcher || (bt->has_plan && !bt->staged), prune,
@@ -617,7 +634,8 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
         SLG_CUDA(ix, cudaGetLastError());
         sdv.n_smax = std::min(s->n_cols, kColMaxSlots);
         const size_t fixed = column_smem(0, sdv.n_smax);
-        const size_t budget = ix->smem_optin > fixed + 2048 ? ix->smem_optin - fixed - 2048 : 0;
+        const size_t reserve = 2048 + (size_t)kColWarps * 256 * 4;  // (+ the kernel's static shared memory)
+        const size_t budget = ix->smem_optin > fixed + reserve ? ix->smem_optin - fixed - reserve : 0;
         sdv.col_resident = (uint32_t)std::min<size_t>(s->n_cols, budget / (2 * kColBlock * 4));
         const size_t csmem = column_smem(sdv.col_resident, sdv.n_smax);
         const uint32_t n_cblocks = (s->doc_count + kColBlock - 1) / kColBlock;
@@ -666,7 +684,8 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
           // one CTA per SM: as many columns of a block resident in shared memory (double buffered) as fit
           sdv.n_smax = std::min(s->n_cols, kColMaxSlots);
           const size_t fixed = column_smem(0, sdv.n_smax);
-          const size_t budget = ix->smem_optin > fixed + 2048 ? ix->smem_optin - fixed - 2048 : 0;
+          const size_t reserve = 2048 + (size_t)kColWarps * 256 * 4;  // (+ the kernel's static shared memory)
+        const size_t budget = ix->smem_optin > fixed + reserve ? ix->smem_optin - fixed - reserve : 0;
           sdv.col_resident = (uint32_t)std::min<size_t>(s->n_cols, budget / (2 * kColBlock * 4));
           const size_t csmem = column_smem(sdv.col_resident, sdv.n_smax);
           const uint32_t n_cblocks = (s->doc_count + kColBlock - 1) / kColBlock;
@@ -685,7 +704,7 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
         SLG_CUDA(ix, launch_score_items(prune, s->dev, wb, it, wsmem, wgrid, st));
         count_launch(ix);
         ix->ctr.score_launches++;
-      } else if (score && bt->use_warp) {
+      } else if (score && warp_path) {
         SLG_CUDA(ix, launch_score_warp(bt->matcher, prune, bt->want_stats, bt->staged, bt->has_plan, s->dev, wb, wsmem, wgrid, st));
         count_launch(ix);
         ix->ctr.score_launches++;
@@ -699,7 +718,13 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       HitDev *hits = reinterpret_cast<HitDev *>(bt->results + (size_t)si * bt->result_stride);
       uint32_t *cnts = reinterpret_cast<uint32_t *>(bt->results + (size_t)si * bt->result_stride + (size_t)Q * k * sizeof(HitDev));
       size_t fsmem = (size_t)(1u << (32 - __builtin_clz(std::max(k, 2u) - 1))) * 8;
-      slg_finalize_kernel<<<Q, kThreads, fsmem, st>>>(bd, s->ord, hits, cnts);
+      if (run_scan && bt->pool_keys && score) {
+        const size_t psmem = (size_t)bt->pool_cap * 2 * 8;
+        SLG_CUDA(ix, cudaFuncSetAttribute(slg_finalize_pools_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        slg_finalize_pools_kernel<<<Q, kThreads, psmem, st>>>(bt->pool_keys, bt->pool_count, bt->pool_cap, k, s->ord, hits, cnts);
+      } else {
+        slg_finalize_kernel<<<Q, kThreads, fsmem, st>>>(bd, s->ord, hits, cnts);
+      }
       count_launch(ix);
       SLG_CUDA(ix, cudaGetLastError());
       if (ix->segs.size() > 1 && score) {

@@ -190,13 +190,115 @@ struct WarpCand {
   uint32_t cnt;
   uint32_t k;
   int lane;
+  uint32_t pool;             // k > kWarpMaxK: which of the query's pools this pass appends to
+  uint32_t *hist;            // k > kWarpMaxK: 256 counters of shared memory private to the warp (radix select)
 
-  __device__ __forceinline__ void begin(unsigned long long *buf, unsigned long long thr0, uint32_t k_, int lane_) {
+  __device__ __forceinline__ void begin(unsigned long long *buf, unsigned long long thr0, uint32_t k_, int lane_, uint32_t pool_ = 0,
+                                        uint32_t *hist_ = nullptr) {
     cand = buf;
     thr = thr0;
     cnt = 0;
     k = k_;
     lane = lane_;
+    pool = pool_;
+    hist = hist_;
+  }
+  // k > kWarpMaxK.  The pool holds up to pool_cap distinct keys in no order.  When an append would overflow it, the warp
+  // holding the lock finds the k-th largest key by radix select (8 bits a pass, histogram in shared memory), keeps the keys
+  // >= it (exactly k: the keys of a pool are distinct) and publishes it as the query's threshold.
+  __device__ __forceinline__ uint32_t compact_pool(const WarpBatchDev &wb, uint32_t qi, unsigned long long *pk, uint32_t n) {
+    unsigned long long prefix = 0ull;
+    uint32_t want = k;  // rank (from the top) of the key looked for among the keys that share the prefix
+    for (int pass = 0; pass < 8; pass++) {
+      const int shift = 56 - 8 * pass;
+      for (uint32_t z = lane; z < 256; z += 32) hist[z] = 0u;
+      __syncwarp();
+      for (uint32_t i = lane; i < n; i += 32) {
+        const unsigned long long key = ld_cg_u64(pk + i);
+        if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(hist + (uint32_t)((key >> shift) & 255ull), 1u);
+      }
+      __syncwarp();
+      // bins from the top: lane L owns bins 255 - 8L .. 248 - 8L
+      uint32_t mine = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) mine += hist[255 - 8 * lane - j];
+      uint32_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += nb;
+      }
+      const uint32_t owner = __ffs(__ballot_sync(0xFFFFFFFFu, incl >= want)) - 1;  // (some lane qualifies: n >= want)
+      uint32_t before = __shfl_sync(0xFFFFFFFFu, incl - mine, owner);
+      uint32_t bin = 0;
+      if (lane == (int)owner) {
+        for (int j = 0; j < 8; j++) {
+          const uint32_t c = hist[255 - 8 * lane - j];
+          if (before + c >= want) {
+            bin = 255 - 8 * lane - j;
+            break;
+          }
+          before += c;
+        }
+      }
+      bin = __shfl_sync(0xFFFFFFFFu, bin, owner);
+      before = __shfl_sync(0xFFFFFFFFu, before, owner);
+      want -= before;
+      prefix |= (unsigned long long)bin << shift;
+      __syncwarp();
+    }
+    const unsigned long long kth = prefix;
+    uint32_t out = 0;
+    for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+      const uint32_t i = b0 + lane;
+      unsigned long long key = 0ull;
+      if (i < n) key = ld_cg_u64(pk + i);
+      const bool keep = i < n && key >= kth;
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+      if (keep) st_cg_u64(pk + out + __popc(bal & ((1u << lane) - 1u)), key);  // (out <= b0: never ahead of the reads)
+      out += __popc(bal);
+      __syncwarp();
+    }
+    if (lane == 0) atomicMax(wb.thr_key + qi, kth);
+    thr = max(thr, kth);
+    return out;
+  }
+  // k > kWarpMaxK: append the pending keys to the query's pool
+  __device__ __forceinline__ void flush(const WarpBatchDev &wb, uint32_t qi) {
+    if (cnt == 0) return;
+    const unsigned long long thr_now = ld_cg_u64(wb.thr_key + qi);
+    thr = max(thr, thr_now);
+    // drop what the published threshold already rules out, then append under the pool's lock
+    unsigned long long k0 = lane < (int)cnt ? cand[lane] : 0ull, k1 = 32 + lane < (int)cnt ? cand[32 + lane] : 0ull;
+    if (k0 <= thr) k0 = 0ull;
+    if (k1 <= thr) k1 = 0ull;
+    const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, k0 != 0ull), b1 = __ballot_sync(0xFFFFFFFFu, k1 != 0ull);
+    const uint32_t n_new = __popc(b0) + __popc(b1);
+    cnt = 0;
+    __syncwarp();
+    if (n_new == 0) return;
+    const uint32_t slot = qi * 2u + pool;
+    unsigned long long *pk = wb.pool_keys + (uint64_t)slot * wb.pool_cap;
+    if (lane == 0) {
+      while (atomicCAS(wb.pool_lock + slot, 0u, 1u) != 0u) __nanosleep(64);
+      __threadfence();
+    }
+    __syncwarp();
+    uint32_t n = ld_cg_u32(wb.pool_count + slot);
+    if (n + n_new > wb.pool_cap) n = compact_pool(wb, qi, pk, n);
+    const uint32_t lt = (1u << lane) - 1u;
+    // (the compaction may have raised the threshold: keys it rules out are not written)
+    const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, k0 > thr), w1 = __ballot_sync(0xFFFFFFFFu, k1 > thr);
+    if (k0 > thr) st_cg_u64(pk + n + __popc(w0 & lt), k0);
+    if (k1 > thr) st_cg_u64(pk + n + __popc(w0) + __popc(w1 & lt), k1);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      st_cg_u32(wb.pool_count + slot, n + __popc(w0) + __popc(w1));
+      __threadfence();
+      atomicExch(wb.pool_lock + slot, 0u);
+    }
+    __syncwarp();
   }
   // append one ballot round of keys; past 32 pending: sort, keep the best k, raise the local threshold
   __device__ __forceinline__ void push(bool pass, unsigned long long key) {
@@ -205,6 +307,9 @@ struct WarpCand {
     if (pass) cand[cnt + __popc(bal & ((1u << lane) - 1u))] = key;
     cnt += __popc(bal);
     __syncwarp();
+    if (cnt > 32 && hist) {  // k > kWarpMaxK: no local top-k, the pending keys go to the pool (flush needs wb: see offer)
+      return;
+    }
     if (cnt > 32) {
       for (uint32_t z = cnt + lane; z < kWarpCand; z += 32) cand[z] = 0ull;
       __syncwarp();
@@ -223,9 +328,14 @@ struct WarpCand {
     if (pass && filter >= 0) pass = (wb.filter_bits[filter][doc >> 5] >> (doc & 31)) & 1u;
     if (pass) pass = cursor_accepts(wb.q_cursor, wb.q_saw, qi, key);
     push(pass, key);
+    if (hist && cnt > 32) flush(wb, qi);
   }
   // merge into the query's global top-k under its lock; returns the query's k-th key afterwards
   __device__ __forceinline__ void merge(const WarpBatchDev &wb, uint32_t qi) {
+    if (hist) {
+      flush(wb, qi);
+      return;
+    }
     if (cnt == 0) return;
     const unsigned long long thr_now = ld_cg_u64(wb.thr_key + qi);
     const bool useful = lane < (int)cnt && cand[lane] > thr_now;  // cnt <= 32 after every push
@@ -835,6 +945,7 @@ __host__ __device__ inline size_t column_smem(uint32_t resident, uint32_t n_smax
 template <bool PRUNE>
 __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(SegmentDev seg, WarpBatchDev wb, StreamDev sd) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_hist[kColWarps][256];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n_used = *sd.n_ucol, n_colq = *sd.n_colq;
   const uint32_t resident = min(sd.col_resident, n_used), n_smax = min(n_used, sd.n_smax);
@@ -995,7 +1106,7 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(Segme
           mx = max(mx, max(max(__float_as_uint(v[x].x), __float_as_uint(v[x].y)), max(__float_as_uint(v[x].z), __float_as_uint(v[x].w))));
         if (!__any_sync(0xFFFFFFFFu, mx >= cut && mx != 0u)) continue;
         // ---- per doc: the docs that can enter the top k, one per lane and round ----
-        wc.begin(cand, qthr, k, lane);
+        wc.begin(cand, qthr, k, lane, 1u, wb.pool_keys ? s_hist[warp] : nullptr);
         uint32_t todo = 0u;
 #pragma unroll
         for (uint32_t x = 0; x < kColBlock / 128; x++) {

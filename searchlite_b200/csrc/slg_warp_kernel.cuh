@@ -74,6 +74,11 @@ struct WarpBatchDev {
   const PlanNodeDev *plan_nodes;
   uint32_t max_leaves;
   unsigned long long *match_count;  // [Q] accepted docs (STATS)
+  // k > kWarpMaxK (flat scan only): per query two candidate pools of pool_cap keys (0: posting scan, 1: column pass), each
+  // with its own count and lock; slg_finalize_pools_kernel merges them.  nullptr: the query's sorted top-k in topk_keys.
+  unsigned long long *pool_keys;    // [Q][2][pool_cap]
+  uint32_t *pool_count, *pool_lock; // [Q][2]
+  uint32_t pool_cap;
 };
 
 // resolve the batch's query terms against one segment (runs once per segment per batch).

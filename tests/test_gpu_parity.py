@@ -264,3 +264,24 @@ def test_full_size_c2_properties():
     assert_parity(ref_h, ref_c, base_h[:n], base_c[:n], strict=False)
     can_h, can_c = ora.search_batch(canon, k, "bm25_dense", threads=slo.max_threads())
     assert_parity(can_h, can_c, base_h[:n], base_c[:n], strict=True)
+
+
+@pytest.mark.parametrize("k,dense_den", [(33, 8), (101, 8), (101, 0), (1001, 8), (2048, 64)])
+def test_scan_kernel_large_k(small, k, dense_den):
+    """k above the warp's sorted top-k (32): candidate pools + radix select on the flat posting scan.  bm25 / wand / bmw
+    return the same bytes and match the oracle on the declared term order."""
+    seg, qb = small
+    ora = _oracle(seg)
+    gi = GpuIndex(0, kernel="items", options={**DENSE, "dense_den": dense_den})
+    gi.load_segment(seg)
+    sub = qb.subset(0, 60)
+    first = None
+    for mode in ("bm25", "wand", "bmw"):
+        got = gi.search_batch(sub, k, mode)
+        assert_engine_parity(gi, ora, sub, k, got, exact_order=(dense_den == 0))
+        if first is None:
+            first = got
+        assert got[0].tobytes() == first[0].tobytes() and got[1].tobytes() == first[1].tobytes(), mode
+    c = gi.counters()
+    assert c["last_items"] > 0  # the scan ran (not the CTA-per-item kernel)
+    gi.close()
