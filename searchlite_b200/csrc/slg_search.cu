@@ -223,15 +223,16 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   bool all_scores = ix->staging;
   for (auto &s : ix->segs) all_scores = all_scores && (s->post_score.p != nullptr || s->n_blocks == 0);
   const bool items_ok = small && !matcher && all_scores && !bt->has_plan && ix->sub_docs <= 4096;
-  if (ix->kernel_choice == 3 && !items_ok)
-    return fail(ix, SLG_ERR_UNSUPPORTED,
-                "the items kernel handles plain OR queries without a ScorePlan, k <= %u, <= %u terms per query, resident scores, sub_docs <= 4096",
-                kWarpMaxK, kWarpMaxTerms);
   bt->can_items = items_ok && (ix->kernel_choice == 0 || ix->kernel_choice == 3);
   // k up to SLG_MAX_K on the flat posting scan: candidate pools + radix select instead of the warp's sorted top-k
   bt->big_k = k > kWarpMaxK && bt->max_terms <= kWarpMaxTerms && !matcher && all_scores && !bt->has_plan && ix->scan_kernels && ix->stream_kernels &&
               (ix->kernel_choice == 0 || ix->kernel_choice == 3);
   if (bt->big_k) bt->can_items = true;
+  if (ix->kernel_choice == 3 && !items_ok && !bt->big_k)
+    return fail(ix, SLG_ERR_UNSUPPORTED,
+                "the items kernel handles plain OR queries without a ScorePlan, k <= %u, <= %u terms per query, resident scores, sub_docs <= 4096",
+                kWarpMaxK, kWarpMaxTerms);
+
   bt->canonical = bt->can_items;
   bt->use_warp = bt->can_items || ix->kernel_choice == 2 || (ix->kernel_choice == 0 && small);
   if (bt->use_warp && !small && !bt->big_k)
