@@ -174,7 +174,23 @@ typedef struct {
   uint64_t last_items;                  /* (query, doc-range) items scored, seeds included; flat scan: (query, term, chunk) items scanned */
   uint64_t last_postings_verified;      /* flat scan: postings whose doc got its exact score (binary searches + column gathers) */
   uint64_t last_items_dropped;          /* flat scan, pruned: items of non-essential terms dropped (MaxScore) */
+  /* hybrid rerank (slg_rerank_batch with sync != 0): */
+  uint64_t rerank_launches;    /* calls timed */
+  double rerank_ms_total;      /* CUDA-event time of their kernels (scores + sort per segment, merge) */
+  double last_rerank_ms;
 } slg_counters_t;
+
+/* One vector clause of a hybrid request (VectorClausePlan, api/reader.rs:2162-2171).  query_vecs: n_queries x dim f32,
+ * host or device memory, already normalised for cosine fields (normalize_in_place is the planner's step,
+ * api/reader.rs:2119-2125).  The clause's similarity is multiplied by boost (api/reader.rs:2421) and blended with the
+ * BM25 score by alpha (compute_hybrid_score, api/reader.rs:226-254); several clauses are averaged. */
+typedef struct {
+  const float *query_vecs;
+  float alpha;          /* 0..1; >= 1 keeps the BM25 score, <= 0 the vector score */
+  float boost;          /* >= 0, finite; 1.0 = none */
+  slg_metric_t metric;  /* the field's metric */
+  uint32_t reserved;
+} slg_vector_clause_t;
 
 /* ---- lifetime ---- */
 int32_t slg_open(int32_t device, slg_index_t **out);
@@ -410,16 +426,42 @@ int32_t slg_merge_gathered_packed(slg_index_t *, const void *dev_gathered, uint6
                                   uint32_t n_queries, uint32_t k, slg_hit_t *out_hits, uint32_t *out_counts);
 
 /* ---- vectors + rerank (what gpu::rerank should have been; vectors/mod.rs:63-129, api/reader.rs:218-254) ----
- * offsets: doc -> row in values or UINT32_MAX (VectorStore, index/segment.rs:1030-1053).
- * store_bf16 != 0 keeps the rows as bf16 in HBM (documented tolerance), else f32. */
+ * offsets: doc -> row in values or UINT32_MAX (VectorStore, index/segment.rs:1030-1053); offsets past n_rows are
+ * refused (SLG_ERR_INVALID).  offsets / values may be host or device memory.
+ * store_bf16 != 0 keeps the rows as bf16 in HBM (rounded once; the arithmetic stays f32), else f32. */
 int32_t slg_load_vectors(slg_index_t *, uint32_t segment_ord, uint32_t dim, const uint32_t *offsets,
                          const float *values, uint64_t n_rows, int32_t store_bf16);
-/* For each query: score every candidate hit as compute_hybrid_score (one clause):
+/* the same from rows that already are bf16 (host or device memory) */
+int32_t slg_load_vectors_bf16(slg_index_t *, uint32_t segment_ord, uint32_t dim, const uint32_t *offsets,
+                              const uint16_t *values_bf16, uint64_t n_rows);
+/* For each query: score every candidate hit as compute_hybrid_score (one clause, boost 1):
  * alpha*bm25 + (1-alpha)*similarity, missing vector => -1 (cosine) / f32::MIN (L2); re-sort by
- * (score desc, segment_ord asc, doc_id asc).  cands is n_queries*cand_stride hits. */
+ * (score desc, segment_ord asc, doc_id asc).  cands is n_queries*cand_stride hits (HOST memory).  The dot product /
+ * squared distance is folded in dimension order with unfused multiply and add, like the reference's iterator sum:
+ * f32 rows give the reference's bits.  Any dim; multiples of 32 (f32 rows) / 64 (bf16 rows) take the coalesced path. */
 int32_t slg_rerank(slg_index_t *, const float *query_vecs, uint32_t n_queries, uint32_t dim,
                    const slg_hit_t *cands, const uint32_t *cand_counts, uint32_t cand_stride, float alpha,
                    slg_metric_t metric, slg_hit_t *out_hits, float *out_vector_scores);
+/* The same for up to 8 clauses (MAX_VECTOR_CLAUSES, api/reader.rs:134): final = mean of the clause blends.  When every
+ * clause has alpha <= 0, candidates without a vector are dropped (api/reader.rs:2474-2476) and out_counts (nullable)
+ * receives the new counts.  out_vector_scores (nullable): RankedHit.vector_score = sum of the clause similarities,
+ * 0.0 where the candidate has no vector. */
+int32_t slg_rerank_clauses(slg_index_t *, const slg_vector_clause_t *clauses, uint32_t n_clauses, uint32_t n_queries,
+                           uint32_t dim, const slg_hit_t *cands, const uint32_t *cand_counts, uint32_t cand_stride,
+                           slg_hit_t *out_hits, uint32_t *out_counts, float *out_vector_scores);
+/* Pipeline form (no host round trip): rescore and re-sort the DEVICE-resident top-k of the batch's last slg_batch_run —
+ * every segment's own list, as the reference hands the concatenated per-segment lists to merge_vector_hits
+ * (api/reader.rs:2752-2773) — then merge the segments again by hybrid score.  Afterwards slg_batch_fetch,
+ * slg_batch_device_results and slg_batch_packed_results (now hits, counts AND vector scores) describe the hybrid
+ * ranking.  Asynchronous on the handle's stream unless sync != 0. */
+int32_t slg_rerank_batch(slg_batch_t *, const slg_vector_clause_t *clauses, uint32_t n_clauses, uint32_t dim, int32_t sync);
+/* n_queries x k vector scores of the hits slg_batch_fetch returns after slg_rerank_batch */
+int32_t slg_batch_fetch_vector_scores(slg_batch_t *, float *out_vector_scores);
+/* shard merge of reranked blocks (slg_batch_packed_results after slg_rerank_batch: hits, counts, vector scores);
+ * out_vector_scores nullable */
+int32_t slg_merge_gathered_hybrid(slg_index_t *, const void *dev_gathered, uint64_t shard_stride, uint32_t n_shards,
+                                  uint32_t n_queries, uint32_t k, slg_hit_t *out_hits, uint32_t *out_counts,
+                                  float *out_vector_scores);
 
 /* ---- introspection ---- */
 int32_t slg_get_counters(const slg_index_t *, slg_counters_t *out);

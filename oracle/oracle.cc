@@ -1348,4 +1348,114 @@ float slo_hybrid_score(float bm25_score, int has_vec, float vec_score, float alp
   return blended_sum / 1.0f;
 }
 
+// api/reader.rs:226-254 for any number of clauses: vec_scores[c] is the clause's similarity already multiplied by its
+// boost (api/reader.rs:2421) when has_vec[c], else ignored.  Returns the final score; *vector_sum / *has_vector as the
+// tuple's second and third members.
+float slo_hybrid_score_clauses(float bm25_score, uint32_t n_clauses, const int *has_vec, const float *vec_scores, const float *alpha,
+                               const int *metric, float *vector_sum_out, int *has_vector_out) {
+  float blended_sum = 0.0f, vector_sum = 0.0f;
+  int has_vector = 0;
+  for (uint32_t c = 0; c < n_clauses; c++) {
+    if (has_vec[c]) {
+      vector_sum += vec_scores[c];
+      has_vector = 1;
+    }
+    const float vec_score = has_vec[c] ? vec_scores[c] : (metric[c] == SLO_METRIC_COSINE ? -1.0f : -std::numeric_limits<float>::max());
+    float blended;
+    if (alpha[c] >= 1.0f) blended = bm25_score;
+    else if (alpha[c] <= 0.0f) blended = vec_score;
+    else blended = slo_blend_scores(bm25_score, vec_score, alpha[c], 1);
+    blended_sum += blended;
+  }
+  const float denom = (float)(n_clauses > 1 ? n_clauses : 1);
+  if (vector_sum_out) *vector_sum_out = vector_sum;
+  if (has_vector_out) *has_vector_out = has_vector;
+  return blended_sum / denom;
+}
+// the engine's bf16 storage option (not in the reference): round-to-nearest-even to the upper 16 bits, in place
+void slo_round_bf16(float *v, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    uint32_t b;
+    std::memcpy(&b, &v[i], 4);
+    if ((b & 0x7F800000u) == 0x7F800000u && (b & 0x007FFFFFu)) b |= 0x00400000u;  // NaN stays NaN
+    else b += 0x7FFFu + ((b >> 16) & 1u);
+    b &= 0xFFFF0000u;
+    std::memcpy(&v[i], &b, 4);
+  }
+}
+
+// The hybrid step of IndexReader::search for the BM25 candidate set (api/reader.rs:2752-2773 -> merge_vector_hits
+// :2477-2537), exact instead of HNSW-approximate similarities: every candidate's vector is looked up
+// (VectorStore::vector, vectors/mod.rs:63-71), scored per clause (metric_similarity x boost, api/reader.rs:2421), blended
+// (compute_hybrid_score), vector-less candidates of an all-vector plan dropped (:2474-2476), and the rest ordered by
+// (score desc, segment_ord asc, doc_id asc).  One vector store per segment_ord listed in seg_ords.
+int slo_rerank_batch(uint32_t n_queries, uint32_t stride, const slo_hit_t *cands, const uint32_t *counts, uint32_t n_segs,
+                     const uint32_t *seg_ords, const uint32_t *seg_doc_counts, const uint32_t *const *seg_offsets,
+                     const float *const *seg_values, const uint64_t *seg_rows, uint32_t dim, uint32_t n_clauses,
+                     const float *const *clause_qv, const float *alpha, const float *boost, const int *metric, slo_hit_t *out_hits,
+                     uint32_t *out_counts, float *out_vs, int threads) {
+  bool all_vector_only = true;
+  for (uint32_t c = 0; c < n_clauses; c++) all_vector_only = all_vector_only && alpha[c] <= 0.0f;
+  auto work = [&](uint32_t q0, uint32_t q1) {
+    std::vector<int> has(n_clauses);
+    std::vector<float> vs(n_clauses);
+    struct Row {
+      slo_hit_t h;
+      float v;
+    };
+    std::vector<Row> rows;
+    for (uint32_t q = q0; q < q1; q++) {
+      rows.clear();
+      const uint32_t n = std::min(counts[q], stride);
+      for (uint32_t i = 0; i < n; i++) {
+        slo_hit_t h = cands[(size_t)q * stride + i];
+        const float *row = nullptr;
+        for (uint32_t s = 0; s < n_segs; s++) {
+          if (seg_ords[s] != h.segment_ord || h.doc_id >= seg_doc_counts[s]) continue;
+          const uint32_t o = seg_offsets[s][h.doc_id];
+          if (o != 0xFFFFFFFFu && (uint64_t)o < seg_rows[s]) row = seg_values[s] + (size_t)o * dim;
+        }
+        for (uint32_t c = 0; c < n_clauses; c++) {
+          has[c] = row != nullptr;
+          vs[c] = row ? slo_metric_similarity(metric[c], clause_qv[c] + (size_t)q * dim, row, dim) * boost[c] : 0.0f;
+        }
+        float vsum = 0.0f;
+        int hv = 0;
+        h.score = slo_hybrid_score_clauses(h.score, n_clauses, has.data(), vs.data(), alpha, metric, &vsum, &hv);
+        if (all_vector_only && !hv) continue;
+        rows.push_back({h, hv ? vsum : 0.0f});
+      }
+      std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
+        int c = total_cmp(b.h.score, a.h.score);
+        if (c != 0) return c < 0;
+        if (a.h.segment_ord != b.h.segment_ord) return a.h.segment_ord < b.h.segment_ord;
+        return a.h.doc_id < b.h.doc_id;
+      });
+      for (uint32_t i = 0; i < stride; i++) {
+        slo_hit_t h{};
+        h.segment_ord = 0xFFFFFFFFu;
+        h.doc_id = 0xFFFFFFFFu;
+        float v = 0.0f;
+        if (i < rows.size()) {
+          h = rows[i].h;
+          v = rows[i].v;
+        }
+        out_hits[(size_t)q * stride + i] = h;
+        if (out_vs) out_vs[(size_t)q * stride + i] = v;
+      }
+      out_counts[q] = (uint32_t)rows.size();
+    }
+  };
+  const uint32_t nt = (uint32_t)std::max(1, std::min<int>(threads, (int)n_queries));
+  if (nt <= 1) {
+    work(0, n_queries);
+  } else {
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < nt; t++)
+      pool.emplace_back(work, (uint32_t)((uint64_t)n_queries * t / nt), (uint32_t)((uint64_t)n_queries * (t + 1) / nt));
+    for (auto &th : pool) th.join();
+  }
+  return 0;
+}
+
 }  // extern "C"

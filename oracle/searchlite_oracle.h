@@ -206,6 +206,18 @@ float slo_metric_similarity(int metric, const float *a, const float *b, size_t d
 float slo_blend_scores(float bm25, float vector_score, float alpha, int higher_is_better);
 /* single-clause compute_hybrid_score; has_vec=0 => missing_vector_score(metric) */
 float slo_hybrid_score(float bm25_score, int has_vec, float vec_score, float alpha, int metric);
+/* compute_hybrid_score for n clauses (vec_scores already boosted); returns the final score */
+float slo_hybrid_score_clauses(float bm25_score, uint32_t n_clauses, const int *has_vec, const float *vec_scores, const float *alpha,
+                               const int *metric, float *vector_sum_out, int *has_vector_out);
+/* hybrid rescoring + re-sort of per-query BM25 candidates with exact similarities (api/reader.rs:2477-2537); one vector
+ * store (offsets u32[doc_count], rows f32[n_rows][dim]) per listed segment_ord */
+int slo_rerank_batch(uint32_t n_queries, uint32_t stride, const slo_hit_t *cands, const uint32_t *counts, uint32_t n_segs,
+                     const uint32_t *seg_ords, const uint32_t *seg_doc_counts, const uint32_t *const *seg_offsets,
+                     const float *const *seg_values, const uint64_t *seg_rows, uint32_t dim, uint32_t n_clauses,
+                     const float *const *clause_qv, const float *alpha, const float *boost, const int *metric, slo_hit_t *out_hits,
+                     uint32_t *out_counts, float *out_vs, int threads);
+/* round f32 values to bf16 precision in place (the engine's storage option; round to nearest even) */
+void slo_round_bf16(float *v, size_t n);
 
 #ifdef __cplusplus
 }

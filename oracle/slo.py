@@ -103,6 +103,12 @@ def lib() -> C.CDLL:
     L.slo_blend_scores.restype = f32
     L.slo_hybrid_score.argtypes = [f32, C.c_int, f32, f32, C.c_int]
     L.slo_hybrid_score.restype = f32
+    L.slo_hybrid_score_clauses.argtypes = [f32, u32, vp, vp, vp, vp, vp, vp]
+    L.slo_hybrid_score_clauses.restype = f32
+    L.slo_round_bf16.argtypes = [vp, sz]
+    L.slo_round_bf16.restype = None
+    L.slo_rerank_batch.argtypes = [u32, u32, vp, vp, u32, vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+    L.slo_rerank_batch.restype = C.c_int
     _LIB = L
     return L
 
@@ -226,6 +232,42 @@ def merge_hits(hit_lists, limit: int):
     out = np.zeros(limit, dtype=HIT_DTYPE)
     n = lib().slo_merge_hits(_p(allh), len(allh), limit, _p(out))
     return out[:n]
+
+
+def round_bf16(values: np.ndarray) -> np.ndarray:
+    """a copy of `values` (f32) rounded to bf16 precision — the engine's storage option"""
+    out = np.array(values, dtype=np.float32, order="C", copy=True)
+    lib().slo_round_bf16(_p(out), out.size)
+    return out
+
+
+def rerank_batch(cands: np.ndarray, counts: np.ndarray, stores, clauses, threads: int = 1):
+    """hybrid step over the BM25 candidates (slo_rerank_batch).  stores: [(segment_ord, offsets u32[doc_count], rows f32[n, dim])];
+    clauses: [(query_vecs f32[Q, dim], alpha, boost, metric name)] -> (hits, counts, vector scores)"""
+    L = lib()
+    cands = np.ascontiguousarray(cands, dtype=HIT_DTYPE)
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    nq, stride = cands.shape
+    ords = np.array([s[0] for s in stores], dtype=np.uint32)
+    offs = [np.ascontiguousarray(s[1], dtype=np.uint32) for s in stores]
+    vals = [np.ascontiguousarray(s[2], dtype=np.float32) for s in stores]
+    dcs = np.array([len(o) for o in offs], dtype=np.uint32)
+    rows = np.array([v.shape[0] for v in vals], dtype=np.uint64)
+    dim = int(clauses[0][0].shape[1])
+    off_ptrs = (C.c_void_p * max(len(offs), 1))(*[o.ctypes.data for o in offs])
+    val_ptrs = (C.c_void_p * max(len(vals), 1))(*[v.ctypes.data for v in vals])
+    qvs = [np.ascontiguousarray(c[0], dtype=np.float32) for c in clauses]
+    qv_ptrs = (C.c_void_p * len(qvs))(*[q.ctypes.data for q in qvs])
+    alpha = np.array([c[1] for c in clauses], dtype=np.float32)
+    boost = np.array([c[2] for c in clauses], dtype=np.float32)
+    metric = np.array([0 if c[3] == "cosine" else 1 for c in clauses], dtype=np.int32)
+    out = np.zeros((nq, stride), dtype=HIT_DTYPE)
+    oc = np.zeros(nq, dtype=np.uint32)
+    vs = np.zeros((nq, stride), dtype=np.float32)
+    rc = L.slo_rerank_batch(nq, stride, _p(cands), _p(counts), len(stores), _p(ords), _p(dcs), off_ptrs, val_ptrs, _p(rows), dim,
+                            len(clauses), qv_ptrs, _p(alpha), _p(boost), _p(metric), _p(out), _p(oc), _p(vs), threads)
+    assert rc == 0
+    return out, oc, vs
 
 
 def max_threads() -> int:

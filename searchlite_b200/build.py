@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsearchlite_gpu.so")
-SOURCES = ["slg_engine.cu", "slg_search.cu", "slg_launch_tiles.cu", "slg_launch_warp.cu", "slg_launch_items.cu"]
+SOURCES = ["slg_engine.cu", "slg_search.cu", "slg_rerank.cu", "slg_launch_tiles.cu", "slg_launch_warp.cu", "slg_launch_items.cu"]
 HEADERS = ["slg_kernels.cuh", "slg_phrase.cuh", "slg_segfiles.h", "slg_warp_kernel.cuh", "slg_items_kernel.cuh", "slg_stream_kernel.cuh", "slg_scan_kernel.cuh",
            "slg_residency.cuh", "slg_async.cuh",
            "slg_host.h", "slg_launch.h", "slg_filter.cuh", "slg_postimage.cuh", "slg_rerank.cuh",

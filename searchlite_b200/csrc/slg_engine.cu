@@ -18,7 +18,6 @@
 #include "slg_filter.cuh"
 #include "slg_phrase.cuh"
 #include "slg_postimage.cuh"
-#include "slg_rerank.cuh"
 #include "slg_residency.cuh"
 #include "slg_segfiles.h"
 
@@ -392,7 +391,7 @@ int32_t slg_open(int32_t device, slg_index_t **out) {
     }
   }
   e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
-  for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ix->ev[i]);
+  for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&ix->ev[i]);
   if (e != cudaSuccess) {
     int32_t rc = fail(nullptr, SLG_ERR_CUDA, "stream/event creation: %s", cudaGetErrorString(e));
     delete ix;
@@ -1608,87 +1607,6 @@ int32_t slg_cursor_decode(const char *raw, uint32_t manifest_generation, slg_hit
 }
 
 /* ---- vectors + rerank ---- */
-int32_t slg_load_vectors(slg_index_t *ix, uint32_t segment_ord, uint32_t dim, const uint32_t *offsets, const float *values,
-                         uint64_t n_rows, int32_t store_bf16) {
-  if (!ix || !offsets || (!values && n_rows) || !dim) return SLG_ERR_INVALID;
-  SLG_CUDA(ix, cudaSetDevice(ix->device));
-  Segment *s = ix->find(segment_ord);
-  if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
-  if (dim % 8) return fail(ix, SLG_ERR_UNSUPPORTED, "vector dim must be a multiple of 8");
-  cudaStream_t st = ix->stream;
-  Vectors &v = s->vec;
-  v.dim = dim;
-  v.n_rows = n_rows;
-  v.bf16 = store_bf16 != 0;
-  SLG_CUDA(ix, v.offsets.alloc(std::max<size_t>(s->doc_count, 1) * 4));
-  SLG_CUDA(ix, cudaMemcpyAsync(v.offsets.p, offsets, (size_t)s->doc_count * 4, cudaMemcpyHostToDevice, st));
-  size_t n = (size_t)n_rows * dim;
-  if (!v.bf16) {
-    SLG_CUDA(ix, v.values.alloc(std::max<size_t>(n, 1) * 4));
-    if (n) SLG_CUDA(ix, cudaMemcpyAsync(v.values.p, values, n * 4, cudaMemcpyHostToDevice, st));
-  } else {
-    DevBuf tmp;
-    SLG_CUDA(ix, tmp.alloc(std::max<size_t>(n, 1) * 4));
-    if (n) SLG_CUDA(ix, cudaMemcpyAsync(tmp.p, values, n * 4, cudaMemcpyHostToDevice, st));
-    SLG_CUDA(ix, v.values.alloc(std::max<size_t>(n, 1) * 2));
-    if (n) {
-      slg_f32_to_bf16_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 1u << 20), 256, 0, st>>>(tmp.as<float>(), v.values.as<__nv_bfloat16>(), n);
-      count_launch(ix);
-    }
-    SLG_CUDA(ix, cudaStreamSynchronize(st));
-  }
-  SLG_CUDA(ix, cudaStreamSynchronize(st));
-  return SLG_OK;
-}
-
-int32_t slg_rerank(slg_index_t *ix, const float *query_vecs, uint32_t n_queries, uint32_t dim, const slg_hit_t *cands,
-                   const uint32_t *cand_counts, uint32_t cand_stride, float alpha, slg_metric_t metric, slg_hit_t *out_hits,
-                   float *out_vector_scores) {
-  if (!ix || !query_vecs || !cands || !cand_counts || !out_hits || !n_queries || !cand_stride) return SLG_ERR_INVALID;
-  if (metric != SLG_METRIC_COSINE && metric != SLG_METRIC_L2) return fail(ix, SLG_ERR_INVALID, "unknown metric");
-  SLG_CUDA(ix, cudaSetDevice(ix->device));
-  cudaStream_t st = ix->stream;
-  // segment table for the kernel
-  std::vector<RerankSegDev> segs;
-  for (auto &s : ix->segs) {
-    RerankSegDev r{};
-    r.segment_ord = s->ord;
-    r.doc_count = s->doc_count;
-    r.offsets = s->vec.offsets.as<uint32_t>();
-    r.values = s->vec.values.p;
-    r.bf16 = s->vec.bf16 ? 1 : 0;
-    r.dim = s->vec.dim;
-    if (s->vec.dim && s->vec.dim != dim) return fail(ix, SLG_ERR_INVALID, "query dim %u != stored dim %u", dim, s->vec.dim);
-    segs.push_back(r);
-  }
-  if (cand_stride > kMaxRerankCands) return fail(ix, SLG_ERR_UNSUPPORTED, "more than %u candidates per query", kMaxRerankCands);
-  PoolScope pool_scope(st);  // per-call buffers from the stream-ordered pool
-  DevBuf d_segs, d_q, d_c, d_n, d_o, d_vs;
-  size_t nh = (size_t)n_queries * cand_stride;
-  SLG_CUDA(ix, d_segs.alloc(segs.size() * sizeof(RerankSegDev)));
-  SLG_CUDA(ix, cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(RerankSegDev), cudaMemcpyHostToDevice, st));
-  SLG_CUDA(ix, d_q.alloc((size_t)n_queries * dim * 4));
-  SLG_CUDA(ix, cudaMemcpyAsync(d_q.p, query_vecs, (size_t)n_queries * dim * 4, cudaMemcpyHostToDevice, st));
-  SLG_CUDA(ix, d_c.alloc(nh * sizeof(HitDev)));
-  SLG_CUDA(ix, cudaMemcpyAsync(d_c.p, cands, nh * sizeof(HitDev), cudaMemcpyHostToDevice, st));
-  SLG_CUDA(ix, d_n.alloc((size_t)n_queries * 4));
-  SLG_CUDA(ix, cudaMemcpyAsync(d_n.p, cand_counts, (size_t)n_queries * 4, cudaMemcpyHostToDevice, st));
-  SLG_CUDA(ix, d_o.alloc(nh * sizeof(HitDev)));
-  SLG_CUDA(ix, d_vs.alloc(nh * 4));
-  size_t smem = (size_t)dim * 4 + (size_t)cand_stride * (sizeof(HitDev) + 4);
-  if (smem > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "rerank tile does not fit shared memory");
-  SLG_CUDA(ix, cudaFuncSetAttribute(slg_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  slg_rerank_kernel<<<n_queries, 256, smem, st>>>(d_segs.as<RerankSegDev>(), (uint32_t)segs.size(), d_q.as<float>(), dim,
-                                                  d_c.as<HitDev>(), d_n.as<uint32_t>(), cand_stride, alpha, (int)metric,
-                                                  d_o.as<HitDev>(), d_vs.as<float>());
-  count_launch(ix);
-  SLG_CUDA(ix, cudaGetLastError());
-  SLG_CUDA(ix, cudaMemcpyAsync(out_hits, d_o.p, nh * sizeof(HitDev), cudaMemcpyDeviceToHost, st));
-  if (out_vector_scores) SLG_CUDA(ix, cudaMemcpyAsync(out_vector_scores, d_vs.p, nh * 4, cudaMemcpyDeviceToHost, st));
-  SLG_CUDA(ix, cudaStreamSynchronize(st));
-  return SLG_OK;
-}
-
 int32_t slg_selftest_div(slg_index_t *ix, uint64_t n, uint64_t seed, uint64_t *mismatches) {
   if (!ix || !mismatches) return SLG_ERR_INVALID;
   SLG_CUDA(ix, cudaSetDevice(ix->device));

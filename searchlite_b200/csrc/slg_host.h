@@ -163,7 +163,7 @@ struct slg_index {
   int n_sm = 148;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 0/1 batch, 2/3 scoring, 4/5 rerank
   std::vector<std::unique_ptr<slg::Segment>> segs;
   std::vector<slg::FilterProg> filters;
   std::string err;
@@ -296,8 +296,8 @@ struct slg_batch {
   uint8_t *done = nullptr;
   size_t done_bytes = 0;
   uint32_t items_cap = 0;
-  unsigned char *results = nullptr;   // per segment: hits [Q][k] then counts [Q]; then the merged block (S > 1)
-  size_t result_stride = 0;           // bytes of one (hits, counts) block
+  unsigned char *results = nullptr;   // per segment: hits [Q][k], counts [Q], vector scores [Q][k] (after a rerank); then the merged block (S > 1)
+  size_t result_stride = 0;           // bytes of one such block
   bool staged = false;                // the (doc, score) stream form of the warp kernel applies
   uint32_t max_terms = 0;
   bool use_warp = false, can_items = false, canonical = false;
@@ -313,6 +313,7 @@ struct slg_batch {
   uint32_t plan_docs = 0;             // docs per tile / sub-tile of this batch
   uint32_t sub_tiles_max = 0;
   uint32_t n_segs_run = 0;
+  bool reranked = false;              // slg_rerank_batch ran on the last results: the blocks carry hybrid scores + vector scores
   bool seeds_done = false;            // two-step run (slg_batch_run_seeds / slg_batch_run_sweep)
   void *pinned = nullptr;             // [pack | results | stats]
   size_t pinned_bytes = 0, pinned_result_off = 0;

@@ -336,7 +336,7 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   const size_t o_ucol = want_stream ? carve((size_t)(bt->max_cols + 1) * 4) : 0;
   const size_t o_colslot = want_stream ? carve((size_t)(bt->max_cols + 1) * 4) : 0;
   const size_t o_done = want_items ? carve(bt->done_bytes) : 0;
-  bt->result_stride = align_up((size_t)n_queries * k * sizeof(HitDev) + (size_t)n_queries * 4, 256);
+  bt->result_stride = align_up((size_t)n_queries * k * sizeof(HitDev) + (size_t)n_queries * 4 + (size_t)n_queries * k * 4, 256);  // hits | counts | vector scores
   const size_t o_results = carve(bt->result_stride * (S + (S > 1 ? 1 : 0)));
   SLG_CUDA(ix, bt->slab.alloc(dpos));
   unsigned char *base = bt->slab.as<unsigned char>();
@@ -741,9 +741,10 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
   }
   if (do_sweep) {
     bt->n_segs_run = si;
+    bt->reranked = false;
     if (si > 1) {
       size_t msmem = (size_t)si * k * sizeof(HitDev);
-      if (msmem > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "merge of %u segments x k=%u does not fit shared memory", si, k);
+      if (msmem > ix->smem_optin || si > kMaxMergeLists) return fail(ix, SLG_ERR_UNSUPPORTED, "merge of %u segments x k=%u does not fit shared memory", si, k);
       SLG_CUDA(ix, cudaFuncSetAttribute(slg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
       unsigned char *mo = bt->results + (size_t)si * bt->result_stride;
       slg_merge_kernel<<<Q, kThreads, msmem, st>>>(reinterpret_cast<const uint32_t *>(bt->results), si, Q, k,
@@ -846,7 +847,7 @@ int32_t slg_batch_device_results(slg_batch_t *bt, void **dev_hits, void **dev_co
 int32_t slg_batch_packed_results(slg_batch_t *bt, void **dev_block, uint64_t *n_bytes) {
   if (!bt || !dev_block || !n_bytes) return SLG_ERR_INVALID;
   *dev_block = result_block(bt);
-  *n_bytes = (uint64_t)bt->Q * bt->k * sizeof(HitDev) + (uint64_t)bt->Q * 4;
+  *n_bytes = (uint64_t)bt->Q * bt->k * sizeof(HitDev) + (uint64_t)bt->Q * 4 + (bt->reranked ? (uint64_t)bt->Q * bt->k * 4 : 0);
   return SLG_OK;
 }
 
@@ -941,40 +942,54 @@ int32_t slg_search_batch(slg_index_t *ix, const slg_query_t *queries, uint32_t n
   return rc;
 }
 
-// gathered: n_shards blocks of shard_stride bytes, each [n_queries][k] hits then [n_queries] counts (the layout of
-// slg_batch_packed_results; shard_stride 0 = tightly packed)
-int32_t slg_merge_gathered_packed(slg_index_t *ix, const void *dev_gathered, uint64_t shard_stride, uint32_t n_shards, uint32_t n_queries,
-                                  uint32_t k, slg_hit_t *out_hits, uint32_t *out_counts) {
+// gathered: n_shards blocks of shard_stride bytes, each [n_queries][k] hits then [n_queries] counts (then, hybrid form,
+// [n_queries][k] vector scores) — the layout of slg_batch_packed_results; shard_stride 0 = tightly packed
+static int32_t merge_packed(slg_index_t *ix, const void *dev_gathered, uint64_t shard_stride, uint32_t n_shards, uint32_t n_queries, uint32_t k,
+                            slg_hit_t *out_hits, uint32_t *out_counts, bool hybrid, float *out_vs) {
   if (!ix || !dev_gathered || !out_hits || !out_counts || !n_shards || !n_queries || !k) return SLG_ERR_INVALID;
   SLG_CUDA(ix, cudaSetDevice(ix->device));
   cudaStream_t st = ix->stream;
-  const size_t hb = (size_t)n_queries * k * sizeof(HitDev), cb = (size_t)n_queries * 4;
-  if (shard_stride == 0) shard_stride = hb + cb;
-  if (shard_stride % 4 || shard_stride < hb + cb) return fail(ix, SLG_ERR_INVALID, "shard stride %llu does not hold %zu bytes", (unsigned long long)shard_stride, hb + cb);
+  const size_t hb = (size_t)n_queries * k * sizeof(HitDev), cb = (size_t)n_queries * 4, vb = hybrid ? (size_t)n_queries * k * 4 : 0;
+  if (shard_stride == 0) shard_stride = hb + cb + vb;
+  if (shard_stride % 4 || shard_stride < hb + cb + vb)
+    return fail(ix, SLG_ERR_INVALID, "shard stride %llu does not hold %zu bytes", (unsigned long long)shard_stride, hb + cb + vb);
   size_t msmem = (size_t)n_shards * k * sizeof(HitDev);
-  if (msmem > ix->smem_optin) return fail(ix, SLG_ERR_UNSUPPORTED, "merge of %u shards x k=%u does not fit shared memory", n_shards, k);
+  if (msmem > ix->smem_optin || n_shards > kMaxMergeLists) return fail(ix, SLG_ERR_UNSUPPORTED, "merge of %u shards x k=%u does not fit shared memory", n_shards, k);
   PoolScope pool_scope(st);  // per-call buffers from the stream-ordered pool
   DevBuf ob;
-  SLG_CUDA(ix, ob.alloc(hb + cb));
-  if (ix->merge_pinned_bytes < hb + cb) {  // the merge has its own staging buffer: a prepared batch may hold the handle's other one
+  SLG_CUDA(ix, ob.alloc(hb + cb + vb));
+  if (ix->merge_pinned_bytes < hb + cb + vb) {  // the merge has its own staging buffer: a prepared batch may hold the handle's other one
     if (ix->merge_pinned) cudaFreeHost(ix->merge_pinned);
     ix->merge_pinned = nullptr;
     ix->merge_pinned_bytes = 0;
-    SLG_CUDA(ix, cudaMallocHost(&ix->merge_pinned, hb + cb));
-    ix->merge_pinned_bytes = hb + cb;
+    SLG_CUDA(ix, cudaMallocHost(&ix->merge_pinned, hb + cb + vb));
+    ix->merge_pinned_bytes = hb + cb + vb;
   }
   SLG_CUDA(ix, cudaFuncSetAttribute(slg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
   slg_merge_kernel<<<n_queries, kThreads, msmem, st>>>(static_cast<const uint32_t *>(dev_gathered), n_shards, n_queries, k,
                                                        (uint32_t)(shard_stride / 4), ob.as<HitDev>(),
-                                                       reinterpret_cast<uint32_t *>(ob.as<unsigned char>() + hb));
+                                                       reinterpret_cast<uint32_t *>(ob.as<unsigned char>() + hb), hybrid ? (uint32_t)((hb + cb) / 4) : 0u,
+                                                       hybrid ? reinterpret_cast<float *>(ob.as<unsigned char>() + hb + cb) : nullptr);
   count_launch(ix);
   SLG_CUDA(ix, cudaGetLastError());
-  SLG_CUDA(ix, cudaMemcpyAsync(ix->merge_pinned, ob.p, hb + cb, cudaMemcpyDeviceToHost, st));
+  const size_t out_bytes = hb + cb + (out_vs ? vb : 0);
+  SLG_CUDA(ix, cudaMemcpyAsync(ix->merge_pinned, ob.p, out_bytes, cudaMemcpyDeviceToHost, st));
   SLG_CUDA(ix, cudaStreamSynchronize(st));
   std::memcpy(out_hits, ix->merge_pinned, hb);
   std::memcpy(out_counts, static_cast<unsigned char *>(ix->merge_pinned) + hb, cb);
-  ix->ctr.last_d2h_bytes = hb + cb;
+  if (out_vs && vb) std::memcpy(out_vs, static_cast<unsigned char *>(ix->merge_pinned) + hb + cb, vb);
+  ix->ctr.last_d2h_bytes = out_bytes;
   return SLG_OK;
+}
+
+int32_t slg_merge_gathered_packed(slg_index_t *ix, const void *dev_gathered, uint64_t shard_stride, uint32_t n_shards, uint32_t n_queries,
+                                  uint32_t k, slg_hit_t *out_hits, uint32_t *out_counts) {
+  return merge_packed(ix, dev_gathered, shard_stride, n_shards, n_queries, k, out_hits, out_counts, false, nullptr);
+}
+
+int32_t slg_merge_gathered_hybrid(slg_index_t *ix, const void *dev_gathered, uint64_t shard_stride, uint32_t n_shards, uint32_t n_queries,
+                                  uint32_t k, slg_hit_t *out_hits, uint32_t *out_counts, float *out_vector_scores) {
+  return merge_packed(ix, dev_gathered, shard_stride, n_shards, n_queries, k, out_hits, out_counts, true, out_vector_scores);
 }
 
 int32_t slg_merge_gathered(slg_index_t *ix, const void *dev_hits, const void *dev_counts, uint32_t n_shards, uint32_t n_queries,

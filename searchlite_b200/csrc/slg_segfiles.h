@@ -500,8 +500,10 @@ inline bool parse_vector_file(const uint8_t *buf, uint64_t n, VectorFile &out, s
   }
   std::memcpy(&out.doc_count, buf + 16, 4);
   std::memcpy(&out.vector_count, buf + 20, 4);
-  const uint64_t need = 24 + (uint64_t)out.doc_count * 4 + (uint64_t)out.vector_count * out.dim * 4;
-  if (need > n) {
+  // (checked: vector_count * dim * 4 can pass 2^64)
+  const uint64_t head = 24 + (uint64_t)out.doc_count * 4;
+  const uint64_t row_bytes = (uint64_t)out.dim * 4;
+  if (head > n || (row_bytes && (uint64_t)out.vector_count > (n - head) / row_bytes)) {
     err = "vector file ended unexpectedly";
     return false;
   }

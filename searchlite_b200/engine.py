@@ -103,7 +103,13 @@ class Counters(C.Structure):
         ("last_postings_scattered", C.c_uint64), ("last_subtiles_skipped", C.c_uint64),
         ("last_column_blocks_streamed", C.c_uint64), ("last_items", C.c_uint64),
         ("last_postings_verified", C.c_uint64), ("last_items_dropped", C.c_uint64),
+        ("rerank_launches", C.c_uint64), ("rerank_ms_total", C.c_double), ("last_rerank_ms", C.c_double),
     ]
+
+
+class VectorClause(C.Structure):
+    """slg_vector_clause_t"""
+    _fields_ = [("query_vecs", C.c_void_p), ("alpha", C.c_float), ("boost", C.c_float), ("metric", C.c_int32), ("reserved", C.c_uint32)]
 
 
 class SearchliteGpuError(RuntimeError):
@@ -127,6 +133,7 @@ EXPORTED_SYMBOLS = [
     "slg_batch_cursor_seen", "slg_cursor_encode", "slg_cursor_decode",
     "slg_batch_run_seeds", "slg_batch_threshold_keys", "slg_batch_import_thresholds", "slg_batch_run_sweep",
     "slg_batch_packed_results", "slg_merge_gathered_packed",
+    "slg_load_vectors_bf16", "slg_rerank_clauses", "slg_rerank_batch", "slg_batch_fetch_vector_scores", "slg_merge_gathered_hybrid",
 ]
 
 
@@ -199,6 +206,11 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_batch_run_sweep": [vp, i32],
         "slg_batch_packed_results": [vp, C.POINTER(vp), C.POINTER(u64)],
         "slg_merge_gathered_packed": [vp, vp, u64, u32, u32, u32, vp, vp],
+        "slg_load_vectors_bf16": [vp, u32, u32, vp, vp, u64],
+        "slg_rerank_clauses": [vp, vp, u32, u32, u32, vp, vp, u32, vp, vp, vp],
+        "slg_rerank_batch": [vp, vp, u32, u32, i32],
+        "slg_batch_fetch_vector_scores": [vp, vp],
+        "slg_merge_gathered_hybrid": [vp, vp, u64, u32, u32, u32, vp, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -434,6 +446,24 @@ class QueryBatch:
         return qb
 
 
+def vector_clauses(clauses):
+    """[(query_vecs [Q, dim] f32 numpy array or CUDA tensor, alpha, boost, metric name)] -> (slg_vector_clause_t array, keepalive, dim)"""
+    arr = (VectorClause * len(clauses))()
+    keep, dim = [], 0
+    for i, (qv, alpha, boost, metric) in enumerate(clauses):
+        if isinstance(qv, np.ndarray):
+            qv = np.ascontiguousarray(qv, dtype=np.float32)
+            ptr = qv.ctypes.data
+        else:  # torch tensor (host or device)
+            qv = qv.contiguous().float()
+            ptr = qv.data_ptr()
+        keep.append(qv)
+        dim = int(qv.shape[1])
+        arr[i].query_vecs = ptr
+        arr[i].alpha, arr[i].boost, arr[i].metric = float(alpha), float(boost), METRIC[metric]
+    return arr, keep, dim
+
+
 class PreparedBatch:
     """A query batch resident on the device (slg_batch_prepare)."""
 
@@ -479,8 +509,20 @@ class PreparedBatch:
     def run_sweep(self, sync: bool = True) -> None:
         self.index._check(self.index.lib.slg_batch_run_sweep(self.handle, 1 if sync else 0))
 
+    def rerank(self, clauses, sync: bool = True) -> None:
+        """slg_rerank_batch: hybrid rescoring of the device-resident top-k of the last run; clauses as vector_clauses()"""
+        arr, keep, dim = vector_clauses(clauses)
+        self.index._check(self.index.lib.slg_rerank_batch(self.handle, arr, len(clauses), dim, 1 if sync else 0))
+        self._rerank_keepalive = keep
+
+    def fetch_vector_scores(self) -> np.ndarray:
+        vs = np.zeros((self.n_queries, self.k), dtype=np.float32)
+        self.index._check(self.index.lib.slg_batch_fetch_vector_scores(self.handle, _ptr(vs)))
+        return vs
+
     def packed_results(self):
-        """(device pointer, bytes) of the last run's result block: n_queries*k hits, then n_queries counts"""
+        """(device pointer, bytes) of the last run's result block: n_queries*k hits, then n_queries counts (then, after a
+        rerank, n_queries*k vector scores)"""
         p, n = C.c_void_p(), C.c_uint64()
         self.index._check(self.index.lib.slg_batch_packed_results(self.handle, C.byref(p), C.byref(n)))
         return p.value, n.value
@@ -783,13 +825,49 @@ class GpuIndex:
                                                        _ptr(hits), _ptr(counts)))
         return hits, counts
 
+    def merge_gathered_hybrid(self, dev_blocks_ptr: int, n_shards: int, n_queries: int, k: int, shard_stride: int = 0):
+        """merge of reranked blocks (hits, counts, vector scores) -> (hits, counts, vector scores)"""
+        hits = np.zeros((n_queries, k), dtype=HIT_DTYPE)
+        counts = np.zeros(n_queries, dtype=np.uint32)
+        vs = np.zeros((n_queries, k), dtype=np.float32)
+        self._check(self.lib.slg_merge_gathered_hybrid(self.handle, dev_blocks_ptr, shard_stride, n_shards, n_queries, k,
+                                                       _ptr(hits), _ptr(counts), _ptr(vs)))
+        return hits, counts, vs
+
     # ---- vectors ---------------------------------------------------------------------------
-    def load_vectors(self, segment_ord: int, offsets: np.ndarray, values: np.ndarray, store_bf16: bool = False) -> None:
-        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
-        values = np.ascontiguousarray(values, dtype=np.float32)
-        n_rows, dim = (values.shape if values.ndim == 2 else (0, 0))
-        self._check(self.lib.slg_load_vectors(self.handle, segment_ord, dim, _ptr(offsets), _ptr(values), n_rows,
-                                              1 if store_bf16 else 0))
+    def load_vectors(self, segment_ord: int, offsets, values, store_bf16: bool = False) -> None:
+        """numpy arrays (host) or torch CUDA tensors: offsets u32/int32 [doc_count], values f32 or bf16 [n_rows, dim]"""
+        if isinstance(values, np.ndarray):
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+            values = np.ascontiguousarray(values, dtype=np.float32)
+            n_rows, dim = (values.shape if values.ndim == 2 else (0, 0))
+            self._check(self.lib.slg_load_vectors(self.handle, segment_ord, dim, _ptr(offsets), _ptr(values), n_rows,
+                                                  1 if store_bf16 else 0))
+            return
+        import torch
+        assert offsets.dtype in (torch.int32, torch.uint32) and values.is_contiguous() and offsets.is_contiguous()
+        n_rows, dim = values.shape
+        torch.cuda.synchronize()
+        if values.dtype == torch.bfloat16:
+            self._check(self.lib.slg_load_vectors_bf16(self.handle, segment_ord, dim, offsets.data_ptr(), values.data_ptr(), n_rows))
+        else:
+            assert values.dtype == torch.float32
+            self._check(self.lib.slg_load_vectors(self.handle, segment_ord, dim, offsets.data_ptr(), values.data_ptr(), n_rows,
+                                                  1 if store_bf16 else 0))
+
+    def rerank_clauses(self, clauses, cands: np.ndarray, cand_counts: np.ndarray):
+        """slg_rerank_clauses on host candidates -> (hits, counts, vector scores); clauses as vector_clauses()"""
+        arr, keep, dim = vector_clauses(clauses)
+        cands = np.ascontiguousarray(cands, dtype=HIT_DTYPE)
+        cand_counts = np.ascontiguousarray(cand_counts, dtype=np.uint32)
+        nq, stride = cands.shape
+        out = np.zeros((nq, stride), dtype=HIT_DTYPE)
+        oc = np.zeros(nq, dtype=np.uint32)
+        vs = np.zeros((nq, stride), dtype=np.float32)
+        self._check(self.lib.slg_rerank_clauses(self.handle, arr, len(clauses), nq, dim, _ptr(cands), _ptr(cand_counts), stride,
+                                                _ptr(out), _ptr(oc), _ptr(vs)))
+        del keep
+        return out, oc, vs
 
     def rerank(self, query_vecs: np.ndarray, cands: np.ndarray, cand_counts: np.ndarray, alpha: float, metric: str = "cosine"):
         query_vecs = np.ascontiguousarray(query_vecs, dtype=np.float32)

@@ -50,6 +50,14 @@ def token_corpus(doc_tokens, vocab: int, segment_ord: int = 0) -> SegmentData:
     return segment_from_postings(post, [len(t) for t in doc_tokens], segment_ord=segment_ord)
 
 
+def gpu_index(seg: SegmentData, kernel: str = "auto", k1: float = 0.9, b: float = 0.4, **kw):
+    """a GpuIndex on cuda:0 holding `seg`"""
+    from searchlite_b200 import GpuIndex
+    gi = GpuIndex(0, kernel=kernel, **kw)
+    gi.load_segment(seg, k1=k1, b=b)
+    return gi
+
+
 def or_queries(term_lists, weights=None) -> QueryBatch:
     return QueryBatch.from_term_lists(term_lists, weights)
 

@@ -518,7 +518,8 @@ def test_rerank_matches_oracle_formulae(metric, bf16):
     out, vs = gi.rerank(qv, cands, cc, alpha, metric)
     m = 0 if metric == "cosine" else 1
     # bf16 storage is this build's choice: rows are rounded once, the arithmetic stays f32
-    tol = 2e-2 if bf16 else 2e-5
+    # f32 rows: the kernel folds in dimension order like the reference, so the score is the oracle's to the bit
+    tol = 2e-2 if bf16 else 0.0
     for q in range(nq):
         n = int(cc[q])
         exp = {}
@@ -542,7 +543,7 @@ def test_rerank_matches_oracle_formulae(metric, bf16):
         if missing and metric == "cosine":
             for h, v in zip(got, vs[q, :n]):
                 if int(h["doc_id"]) in missing:
-                    assert v == -1.0
+                    assert v == 0.0  # RankedHit.vector_score is None without a vector (api/reader.rs:253)
     # alpha shortcuts (api/reader.rs:241-247)
     out1, _ = gi.rerank(qv, cands, cc, 1.0, metric)
     for q in range(nq):
