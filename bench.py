@@ -65,6 +65,8 @@ def parse_args():
     ap.add_argument("--option", action="append", default=[], help="engine residency option name=value (slg_set_option)")
     ap.add_argument("--cpu-sample", type=int, default=-1, help="queries checked against / timed on the CPU oracle (-1 = all, 0 = skip)")
     ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of --impl reference")
+    ap.add_argument("--candidates", type=int, default=1000, help="c5: BM25 candidates per query handed to the rerank")
+    ap.add_argument("--no-phrases", action="store_true", help="c4: skip the phrase leg (positions resident: +21 GB)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-exhaustive", action="store_true", help="skip the exhaustive (bm25) leg and its roofline")
     ap.add_argument("--no-pruned", action="store_true", help=argparse.SUPPRESS)  # (round-1 flag: same as --no-exhaustive)
