@@ -35,6 +35,29 @@ def test_library_exports_every_declared_symbol(lib):
     assert b"sm_100a" in lib.slg_version()
 
 
+def test_rust_sys_crate_is_in_sync_with_the_header():
+    """rust/searchlite-gpu-sys/src/lib.rs is generated from the header (tools/gen_rust_sys.py): it must be current and
+    declare every exported entry point plus a #[repr(C)] mirror of every struct whose size ctypes can cross-check"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_rust_sys
+    text = open(gen_rust_sys.OUT).read()
+    assert text == gen_rust_sys.generate(), "run python tools/gen_rust_sys.py"
+    fns = sorted(re.findall(r"pub fn (slg_[a-z0-9_]+)\(", text))
+    assert fns == _declared_symbols()
+    for name in ("slg_term_t", "slg_hit_t", "slg_query_t", "slg_plan_node_t", "slg_stats_t", "slg_segment_view_t", "slg_filter_node_t",
+                 "slg_counters_t", "slg_vector_clause_t", "slg_segment_files_t", "slg_segment_info_t"):
+        assert f"pub struct {name} {{" in text, name
+    # field counts agree with the ctypes / numpy mirrors the tests drive the library through
+    def n_fields(struct):
+        body = text[text.index(f"pub struct {struct} {{"):]
+        return len(re.findall(r"^    pub \w+:", body[: body.index("\n}")], flags=re.M))
+    assert n_fields("slg_counters_t") == len(engine.Counters._fields_)
+    assert n_fields("slg_vector_clause_t") == len(engine.VectorClause._fields_)
+    assert n_fields("slg_hit_t") == len(engine.HIT_DTYPE.names)
+    assert n_fields("slg_filter_node_t") == len(engine.FILTER_DTYPE.names)
+
+
 def test_library_is_built_for_sm_100a_only():
     out = os.popen(f"cuobjdump --list-elf {slg_build.LIB_PATH} 2>/dev/null").read()
     archs = set(re.findall(r"sm_\d+a?", out))
@@ -69,13 +92,14 @@ def test_struct_layouts_match_the_header():
     assert engine.STATS_DTYPE.itemsize == 40
     assert engine.FILTER_DTYPE.itemsize == 56
     assert C.sizeof(engine.SegmentView) == 80
-    assert C.sizeof(engine.Counters) == 120
+    assert C.sizeof(engine.Counters) == 144
+    assert C.sizeof(engine.VectorClause) == 24
     src = r'''
     #include "include/searchlite_gpu.h"
     #include <stdio.h>
-    int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(slg_term_t), sizeof(slg_query_t), sizeof(slg_hit_t),
+    int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(slg_term_t), sizeof(slg_query_t), sizeof(slg_hit_t),
       sizeof(slg_stats_t), sizeof(slg_filter_node_t), sizeof(slg_segment_view_t), sizeof(slg_counters_t),
-      sizeof(slg_segment_files_t), sizeof(slg_segment_info_t), sizeof(slg_plan_node_t));return 0;}
+      sizeof(slg_segment_files_t), sizeof(slg_segment_info_t), sizeof(slg_plan_node_t), sizeof(slg_vector_clause_t));return 0;}
     '''
     import subprocess
     import tempfile
@@ -85,7 +109,7 @@ def test_struct_layouts_match_the_header():
         exe = os.path.join(td, "s")
         subprocess.run(["gcc", "-std=c99", "-I", ROOT, "-o", exe, c], check=True, cwd=ROOT)  # the header is plain C
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [20, 72, 12, 40, 56, 80, 120, C.sizeof(engine.SegmentFiles), C.sizeof(engine.SegmentInfo), 12]
+    assert sizes == [20, 72, 12, 40, 56, 80, 144, C.sizeof(engine.SegmentFiles), C.sizeof(engine.SegmentInfo), 12, 24]
 
 
 def test_query_batch_builders():
