@@ -313,10 +313,13 @@ def main():
         barrier()
         c1 = gi.counters()
         ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
-        n_score = max(c1["score_launches"] - c0["score_launches"], 1)
-        kernel_ms = (c1["score_ms_total"] - c0["score_ms_total"]) / n_score
         launches = (c1["kernel_launches"] - c0["kernel_launches"]) / args.steps
+        # the scoring kernels' own CUDA-event time (handle's stream): one more, synchronous, pass — the sharded loop above
+        # runs asynchronously, so its passes leave no per-kernel time behind; max over ranks like the step time
+        c0 = gi.counters()
         p.run(sync=True)
+        c1 = gi.counters()
+        kernel_ms = max_over_ranks((c1["score_ms_total"] - c0["score_ms_total"]) / max(c1["score_launches"] - c0["score_launches"], 1))
         res = searcher.exchange_and_merge(p) if world > 1 else p.fetch()
         ctr = gi.counters()
         p.free()

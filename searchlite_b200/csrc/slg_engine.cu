@@ -298,9 +298,24 @@ int32_t build_layout(slg_index *ix, Segment *s) {
 }
 
 // after post_tf / blk_max_tf are filled: per-term max tf and the wide-tf side table
-int32_t build_wide(slg_index *ix, Segment *s, const uint64_t *d_csr_off, const uint32_t *d_csr_tfs) {
+int32_t build_wide(slg_index *ix, Segment *s, const uint64_t *d_csr_off, const uint32_t *d_csr_tfs, const uint4 *d_ovf = nullptr,
+                   uint32_t n_ovf = 0) {
   cudaStream_t st = ix->stream;
   if (!s->n_terms) return SLG_OK;
+  if (s->n_blocks) {  // untrusted input: doc ids inside the segment, lists strictly ascending
+    DevBuf bad;
+    SLG_CUDA(ix, bad.alloc(4));
+    SLG_CUDA(ix, cudaMemsetAsync(bad.p, 0, 4, st));
+    slg_validate_postings_kernel<<<s->n_blocks, 128, 0, st>>>(s->term_start.as<uint64_t>(), s->term_blk.as<uint32_t>(), s->term_df.as<uint32_t>(),
+                                                              s->n_terms, s->n_blocks, s->post_doc.as<uint32_t>(), s->doc_count, bad.as<uint32_t>());
+    count_launch(ix);
+    uint32_t n_bad = 0;
+    SLG_CUDA(ix, cudaMemcpyAsync(&n_bad, bad.p, 4, cudaMemcpyDeviceToHost, st));
+    SLG_CUDA(ix, cudaStreamSynchronize(st));
+    if (n_bad)
+      return fail(ix, SLG_ERR_INVALID, "segment %u: %u postings name a doc outside the segment's %u docs or break the ascending order of their list",
+                  s->ord, n_bad, s->doc_count);
+  }
   slg_term_max_tf_kernel<<<(unsigned)((s->n_terms + 255) / 256), 256, 0, st>>>(s->term_blk.as<uint32_t>(), s->blk_max_tf.as<float>(),
                                                                               s->n_terms, s->term_max_tf.as<float>());
   count_launch(ix);
@@ -317,7 +332,6 @@ int32_t build_wide(slg_index *ix, Segment *s, const uint64_t *d_csr_off, const u
       wpos += s->h_df[t];
     }
   if (wide_terms.empty()) return SLG_OK;
-  if (!d_csr_tfs) return fail(ix, SLG_ERR_UNSUPPORTED, "term frequency >= 255 needs the CSR load path");
   SLG_CUDA(ix, s->tf_wide.alloc(wpos * 4));
   DevBuf d_wt, d_wo;
   SLG_CUDA(ix, d_wt.alloc(wide_terms.size() * 4));
@@ -329,9 +343,22 @@ int32_t build_wide(slg_index *ix, Segment *s, const uint64_t *d_csr_off, const u
   for (size_t w = 0; w < wide_terms.size(); w++) tw[wide_terms[w]] = wide_off[w];
   SLG_CUDA(ix, cudaMemcpyAsync(s->term_wide.p, tw.data(), s->n_terms * 8, cudaMemcpyHostToDevice, st));
   dim3 grid(64, (unsigned)wide_terms.size());
-  slg_wide_tf_kernel<<<grid, 256, 0, st>>>(d_csr_off, d_csr_tfs, d_wt.as<uint32_t>(), d_wo.as<uint64_t>(),
-                                           (uint32_t)wide_terms.size(), s->tf_wide.as<uint32_t>());
-  count_launch(ix);
+  if (d_csr_tfs) {
+    slg_wide_tf_kernel<<<grid, 256, 0, st>>>(d_csr_off, d_csr_tfs, d_wt.as<uint32_t>(), d_wo.as<uint64_t>(),
+                                             (uint32_t)wide_terms.size(), s->tf_wide.as<uint32_t>());
+    count_launch(ix);
+  } else {
+    // posting-image load: the resident bytes give every tf < 255, the decode's side list the saturated ones
+    slg_wide_from_bytes_kernel<<<grid, 256, 0, st>>>(s->term_start.as<uint64_t>(), s->term_df.as<uint32_t>(), s->post_tf.as<uint8_t>(),
+                                                     d_wt.as<uint32_t>(), d_wo.as<uint64_t>(), (uint32_t)wide_terms.size(),
+                                                     s->tf_wide.as<uint32_t>());
+    count_launch(ix);
+    if (n_ovf) {
+      slg_wide_patch_tf_kernel<<<(n_ovf + 255) / 256, 256, 0, st>>>(d_ovf, n_ovf, s->term_wide.as<uint64_t>(), s->tf_wide.as<uint32_t>());
+      count_launch(ix);
+    }
+  }
+  SLG_CUDA(ix, cudaGetLastError());
   SLG_CUDA(ix, cudaStreamSynchronize(st));
   return SLG_OK;
 }
@@ -575,7 +602,8 @@ int32_t load_post_image(slg_index *ix, const slg_segment_view_t *v, const uint8_
       s->h_df[t] = 0;
       continue;
     }
-    if (o + 17 > post_image_bytes) return fail(ix, SLG_ERR_INVALID, "posting header of term %llu is out of bounds", (unsigned long long)t);
+    if (post_image_bytes < 17 || o > post_image_bytes - 17)  // (written so that an offset near 2^64 cannot wrap)
+      return fail(ix, SLG_ERR_INVALID, "posting header of term %llu is out of bounds", (unsigned long long)t);
     const uint8_t *p = post_image + o;
     uint32_t df, raw_block;
     std::memcpy(&df, p, 4);
@@ -608,24 +636,37 @@ int32_t load_post_image(slg_index *ix, const slg_segment_view_t *v, const uint8_
     SLG_CUDA(ix, d_posbyte.alloc((s->n_post_padded + 1) * 4));
     SLG_CUDA(ix, cudaMemsetAsync(d_npos.p, 0, (s->n_post_padded + 1) * 4, st));
   }
-  DevBuf d_err;
-  SLG_CUDA(ix, d_err.alloc(4));
-  SLG_CUDA(ix, cudaMemsetAsync(d_err.p, 0, 4, st));
+  DevBuf d_err, d_ovf;
+  SLG_CUDA(ix, d_err.alloc(8));
   tm.mark("image -> device");
-  if (v->n_terms) {
-    slg_decode_post_image_kernel<<<(unsigned)((v->n_terms + 3) / 4), 128, 0, st>>>(
-        d_img.as<uint8_t>(), post_image_bytes, d_hdr.as<PostTermHeader>(), v->n_terms, s->term_start.as<uint64_t>(),
-        s->term_blk.as<uint32_t>(), s->post_doc.as<uint32_t>(), s->post_tf.as<uint8_t>(), s->blk_max_doc.as<uint32_t>(),
-        s->blk_max_tf.as<float>(), keep_pos ? d_npos.as<uint32_t>() : nullptr, keep_pos ? d_posbyte.as<uint32_t>() : nullptr,
-        d_err.as<uint32_t>());
+  // postings with tf >= 255 go to a side list (term, posting number, tf); when it overflows the decode is repeated with room
+  uint32_t ovf_cap = 1u << 16, n_ovf = 0, derr = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    SLG_CUDA(ix, d_ovf.alloc((size_t)ovf_cap * sizeof(uint4)));
+    SLG_CUDA(ix, cudaMemsetAsync(d_err.p, 0, 8, st));
+    if (v->n_terms) {
+      slg_decode_post_image_kernel<<<(unsigned)((v->n_terms + 3) / 4), 128, 0, st>>>(
+          d_img.as<uint8_t>(), post_image_bytes, d_hdr.as<PostTermHeader>(), v->n_terms, s->term_start.as<uint64_t>(),
+          s->term_blk.as<uint32_t>(), s->post_doc.as<uint32_t>(), s->post_tf.as<uint8_t>(), s->blk_max_doc.as<uint32_t>(),
+          s->blk_max_tf.as<float>(), keep_pos ? d_npos.as<uint32_t>() : nullptr, keep_pos ? d_posbyte.as<uint32_t>() : nullptr,
+          d_err.as<uint32_t>(), d_err.as<uint32_t>() + 1, ovf_cap, d_ovf.as<uint4>());
+      count_launch(ix);
+      SLG_CUDA(ix, cudaGetLastError());
+    }
+    uint32_t back[2] = {0, 0};
+    SLG_CUDA(ix, cudaMemcpyAsync(back, d_err.p, 8, cudaMemcpyDeviceToHost, st));
+    SLG_CUDA(ix, cudaStreamSynchronize(st));
+    derr = back[0];
+    n_ovf = back[1];
+    if (n_ovf <= ovf_cap) break;
+    ovf_cap = n_ovf;
+  }
+  if (derr == 1) return fail(ix, SLG_ERR_INVALID, "malformed varint in the posting image");
+  if (n_ovf && derr == 0) {
+    slg_wide_patch_blockmax_kernel<<<(n_ovf + 255) / 256, 256, 0, st>>>(d_ovf.as<uint4>(), n_ovf, s->term_blk.as<uint32_t>(), s->blk_max_tf.as<float>());
     count_launch(ix);
     SLG_CUDA(ix, cudaGetLastError());
   }
-  uint32_t derr = 0;
-  SLG_CUDA(ix, cudaMemcpyAsync(&derr, d_err.p, 4, cudaMemcpyDeviceToHost, st));
-  SLG_CUDA(ix, cudaStreamSynchronize(st));
-  if (derr == 1) return fail(ix, SLG_ERR_INVALID, "malformed varint in the posting image");
-  if (derr == 2) return fail(ix, SLG_ERR_UNSUPPORTED, "term frequency >= 255 in a posting image (use the CSR load path)");
   if (derr == 3) return fail(ix, SLG_ERR_UNSUPPORTED, "a posting list with positions is longer than 4 GiB");
   tm.mark("decode docs + tfs");
   if (keep_pos) {
@@ -644,7 +685,7 @@ int32_t load_post_image(slg_index *ix, const slg_segment_view_t *v, const uint8_
     s->has_positions = true;
     tm.mark("decode positions");
   }
-  if ((rc = build_wide(ix, s, nullptr, nullptr))) return rc;
+  if ((rc = build_wide(ix, s, nullptr, nullptr, d_ovf.as<uint4>(), n_ovf))) return rc;
   const int64_t *d_lens;
   const uint8_t *d_pres;
   if ((rc = to_device(ix, v->field_lengths, (size_t)v->doc_count, SLG_MEM_HOST, t_lens, &d_lens))) return rc;
@@ -764,7 +805,7 @@ bool parse_segment_files(const slg_segment_files_t *f, const char *field_spec, P
   out.term_field.assign(out.terms.size(), -1);
   for (size_t i = 0; i < out.terms.size(); i++) {
     const slgf::TermEntry &t = out.terms[i];
-    if (t.offset + 17 > f->post_bytes) {
+    if (f->post_bytes < 17 || t.offset > f->post_bytes - 17) {  // (an offset near 2^64 must not wrap)
       err = "a term's posting offset lies outside the posting file";
       return false;
     }

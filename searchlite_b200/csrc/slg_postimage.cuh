@@ -77,13 +77,48 @@ __device__ __forceinline__ bool window_varint(uint64_t w, uint32_t avail, uint32
   return true;
 }
 
+// A term frequency that does not fit the resident byte (tf >= 255: long documents, frequent tokens) is kept exactly in a
+// side list: (term, posting number inside the term, tf).  The load path patches the block maxima and the term's tf_wide
+// row from it (slg_wide_patch_*).  Entries past the capacity are only counted; the host then repeats the decode with room.
+__device__ __forceinline__ void wide_tf_record(uint32_t *count, uint32_t cap, uint4 *ovf, uint32_t term, uint32_t index, uint32_t tf) {
+  const uint32_t at = atomicAdd(count, 1u);
+  if (at < cap) ovf[at] = make_uint4(term, index, tf, 0u);
+}
+
+// exact block maxima for blocks that hold a saturated posting (float bits of non-negative values order like ints)
+static __global__ void slg_wide_patch_blockmax_kernel(const uint4 *ovf, uint32_t n, const uint32_t *term_blk, float *blk_max_tf) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const uint4 v = ovf[e];
+  atomicMax(reinterpret_cast<int *>(blk_max_tf + term_blk[v.x] + v.y / kBlock), __float_as_int((float)v.z));
+}
+
+// tf_wide rows of the wide terms from the resident bytes, then the exact values of the saturated postings on top
+static __global__ void slg_wide_from_bytes_kernel(const uint64_t *term_start, const uint32_t *term_df, const uint8_t *post_tf,
+                                                  const uint32_t *wide_terms, const uint64_t *wide_off, uint32_t n_wide, uint32_t *tf_wide) {
+  const uint32_t w = blockIdx.y;
+  if (w >= n_wide) return;
+  const uint32_t term = wide_terms[w];
+  const uint64_t src0 = term_start[term];
+  const uint32_t df = term_df[term];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < df; i += gridDim.x * blockDim.x) tf_wide[wide_off[w] + i] = post_tf[src0 + i];
+}
+static __global__ void slg_wide_patch_tf_kernel(const uint4 *ovf, uint32_t n, const uint64_t *term_wide, uint32_t *tf_wide) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const uint4 v = ovf[e];
+  const uint64_t row = term_wide[v.x];
+  if (row != ~0ull) tf_wide[row + v.y] = v.z;
+}
+
 static __global__ void __launch_bounds__(128) slg_decode_post_image_kernel(const uint8_t *img, uint64_t img_bytes,
                                                                      const PostTermHeader *hdr, uint64_t n_terms,
                                                                      const uint64_t *term_start, const uint32_t *term_blk,
                                                                      uint32_t *post_doc, uint8_t *post_tf,
                                                                      uint32_t *blk_max_doc, float *blk_max_tf,
                                                                      uint32_t *post_npos, uint32_t *post_posbyte,
-                                                                     uint32_t *err) {
+                                                                     uint32_t *err, uint32_t *ovf_count, uint32_t ovf_cap,
+                                                                     uint4 *ovf) {
   const uint64_t term = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (term >= n_terms) return;
@@ -220,7 +255,7 @@ static __global__ void __launch_bounds__(128) slg_decode_post_image_kernel(const
           post_npos[out0 + i + j] = val[s + 2];
           post_posbyte[out0 + i + j] = (uint32_t)at;
         }
-        if (tf >= 255u) atomicMax(err, 2u);
+        if (tf >= 255u) wide_tf_record(ovf_count, ovf_cap, ovf, (uint32_t)term, i + j, tf);
         post_doc[out0 + i + j] = val[s];
         post_tf[out0 + i + j] = (uint8_t)min(tf, 255u);
       }
@@ -270,7 +305,7 @@ static __global__ void __launch_bounds__(128) slg_decode_post_image_kernel(const
         if (vi < n_var) {
           const uint32_t p = vi >> 1;
           if (vi & 1u) {
-            if (v >= 255u) atomicMax(err, 2u);
+            if (v >= 255u) wide_tf_record(ovf_count, ovf_cap, ovf, (uint32_t)term, p, v);
             post_tf[out0 + p] = (uint8_t)min(v, 255u);
           } else {
             post_doc[out0 + p] = v;

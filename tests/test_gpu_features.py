@@ -128,7 +128,9 @@ def test_argument_errors_are_reported_not_fatal():
 
 
 @pytest.mark.parametrize("k", [1, 2, 33, 257, 2048])
-def test_large_k_goes_through_the_cta_kernel(k):
+def test_large_k(k):
+    """k > 32 on plain OR queries: the flat posting scan with per-query candidate pools (declared summation order); an
+    explicit kernel="cta" keeps the reference's order"""
     spec = synth.CorpusSpec(n_docs=9_000, vocab=500, seed=5, len_lo=5, len_hi=40)
     seg = synth.generate_segment(spec, "cpu")
     qb = synth.generate_queries(40, spec.vocab, seed=6, min_rank=2)
@@ -136,7 +138,10 @@ def test_large_k_goes_through_the_cta_kernel(k):
     gi, _ = _gpu(seg)
     for mode in ("bm25", "bmw"):
         got = gi.search_batch(qb, k, mode)
-        assert_engine_parity(gi, ora, qb, k, got, exact_order=k > 32)  # k <= 32 runs the column front end (its own term order)
+        assert_engine_parity(gi, ora, qb, k, got)
+    gi.close()
+    gi, _ = _gpu(seg, "cta")
+    assert_engine_parity(gi, ora, qb, k, gi.search_batch(qb, k, "bm25"), exact_order=True)
     gi.close()
 
 
@@ -431,6 +436,66 @@ def test_post_image_load_equals_csr_load():
     with pytest.raises(SearchliteGpuError):
         gi.load_segment_post_image(seg, img[: len(img) // 2], off)
     gi.close()
+
+
+@pytest.mark.parametrize("with_positions", [False, True])
+@pytest.mark.parametrize("kernel", ["auto", "warp", "cta"])
+def test_wide_term_frequencies_through_the_post_image(kernel, with_positions):
+    """tf >= 255 in a reference-format posting image (long documents): the decode keeps the exact values in a side list and
+    the load builds the same wide-tf table as the CSR path (such indexes used to be refused)"""
+    n = 4000
+    rng = np.random.default_rng(19)
+    d0 = np.sort(rng.choice(n, size=2500, replace=False))
+    tf0 = rng.integers(1, 6, size=2500)
+    tf0[::41] = rng.integers(255, 3000, size=len(tf0[::41]))
+    tf0[5], tf0[6], tf0[-1] = 255, 254, 900
+    d1 = np.sort(rng.choice(n, size=900, replace=False))
+    tf1 = rng.integers(1, 4, size=900)
+    d2 = np.sort(rng.choice(n, size=300, replace=False))
+    tf2 = np.full(300, 300)
+    lens = rng.integers(50, 4000, size=n)
+    seg = segment_from_postings([(d0.tolist(), tf0.tolist()), (d1.tolist(), tf1.tolist()), (d2.tolist(), tf2.tolist())], lens.tolist())
+    ora = _oracle(seg)
+    if with_positions:  # position lists of tf entries (capped: the image only needs SOME positions per posting to change its layout)
+        npos = np.minimum(seg.post_tfs.astype(np.int64), 7)
+        pos_off = np.zeros(len(npos) + 1, dtype=np.uint64)
+        pos_off[1:] = np.cumsum(npos)
+        positions = np.concatenate([np.arange(k, dtype=np.uint32) * 3 for k in npos]) if len(npos) else np.zeros(0, np.uint32)
+        ora.set_positions(pos_off, positions)
+    img, off = ora.build_post_image()
+    qb = or_queries([[0], [0, 1], [1, 0], [2, 0], [2]])
+    gi = GpuIndex(0, kernel=kernel)
+    gi.load_segment_post_image(seg, img, off)
+    csr, _ = _gpu(seg, kernel)
+    for mode in ("bm25", "bmw"):
+        got = gi.search_batch(qb, 11, mode)
+        _check(gi, ora, qb, 11, got, kernel)
+        ref = csr.search_batch(qb, 11, mode)
+        assert got[0].tobytes() == ref[0].tobytes() and got[1].tobytes() == ref[1].tobytes()
+    gi.close()
+    csr.close()
+
+
+def test_corrupt_postings_are_refused_at_load():
+    """doc ids outside the segment or lists that do not ascend must not reach the scoring kernels"""
+    good = segment_from_postings([([0, 3, 7], [1, 2, 1]), ([2, 3], [1, 1])], [5, 5, 5, 5, 5, 5, 5, 5])
+    gi = GpuIndex(0)
+    gi.load_segment(good)
+    gi.close()
+    for docs in ([0, 3, 8], [0, 7, 3], [3, 3, 7]):
+        bad = segment_from_postings([(docs, [1, 2, 1]), ([2, 3], [1, 1])], [5, 5, 5, 5, 5, 5, 5, 5])
+        gi = GpuIndex(0)
+        with pytest.raises(SearchliteGpuError, match="outside the segment|ascending"):
+            gi.load_segment(bad)
+        gi.close()
+        # the same through a posting image
+        from oracle import slo
+        o = slo.OracleIndex(bad)
+        img, off = o.build_post_image()
+        gi = GpuIndex(0)
+        with pytest.raises(SearchliteGpuError, match="outside the segment|ascending"):
+            gi.load_segment_post_image(bad, img, off)
+        gi.close()
 
 
 # ---- several segments in one handle: api/reader.rs:2670-2777 ----------------------------------------------
