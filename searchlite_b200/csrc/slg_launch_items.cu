@@ -29,13 +29,27 @@ cudaError_t launch_score_sparse(const SegmentDev &sd, const WarpBatchDev &wb, co
   slg_score_sparse_kernel<false><<<grid, kSparseWarps * 32, smem, st>>>(sd, wb, st_dev);
   return cudaGetLastError();
 }
-cudaError_t launch_score_columns(bool prune, const SegmentDev &sd, const WarpBatchDev &wb, const StreamDev &st_dev, size_t smem, int grid, cudaStream_t st) {
-  return prune ? go_n(slg_score_columns_kernel<true>, kColWarps * 32, smem, grid, st, sd, wb, st_dev)
-               : go_n(slg_score_columns_kernel<false>, kColWarps * 32, smem, grid, st, sd, wb, st_dev);
+cudaError_t launch_score_columns(bool prune, bool pools, const SegmentDev &sd, const WarpBatchDev &wb, const StreamDev &st_dev, size_t smem, int grid,
+                                 cudaStream_t st) {
+  if (pools)
+    return prune ? go_n(slg_score_columns_kernel<true, true>, kColWarps * 32, smem, grid, st, sd, wb, st_dev)
+                 : go_n(slg_score_columns_kernel<false, true>, kColWarps * 32, smem, grid, st, sd, wb, st_dev);
+  return prune ? go_n(slg_score_columns_kernel<true, false>, kColWarps * 32, smem, grid, st, sd, wb, st_dev)
+               : go_n(slg_score_columns_kernel<false, false>, kColWarps * 32, smem, grid, st, sd, wb, st_dev);
 }
-cudaError_t launch_scan(bool prune, const SegmentDev &sd, const WarpBatchDev &wb, const ScanDev &sc, int grid, cudaStream_t st) {
-  if (prune) slg_scan_kernel<true><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
-  else slg_scan_kernel<false><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
+cudaError_t launch_columns_pruned(bool pools, const SegmentDev &sd, const WarpBatchDev &wb, const StreamDev &st_dev, int grid, cudaStream_t st) {
+  if (pools) slg_columns_pruned_kernel<1><<<grid, 256, 0, st>>>(sd, wb, st_dev);
+  else slg_columns_pruned_kernel<0><<<grid, 256, 0, st>>>(sd, wb, st_dev);
+  return cudaGetLastError();
+}
+cudaError_t launch_scan(bool prune, bool pools, const SegmentDev &sd, const WarpBatchDev &wb, const ScanDev &sc, int grid, cudaStream_t st) {
+  if (pools) {
+    if (prune) slg_scan_kernel<true, true><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
+    else slg_scan_kernel<false, true><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
+  } else {
+    if (prune) slg_scan_kernel<true, false><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
+    else slg_scan_kernel<false, false><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_seed_items(const SegmentDev &sd, const WarpBatchDev &wb, const ItemsDev &it, size_t smem, int grid, cudaStream_t st) {

@@ -60,7 +60,10 @@ struct ScanDev {
   uint32_t *item_start;      // [n_pairs + 1] first item of every ordered pair
   uint32_t *items;           // [items_cap] ordered-pair index of every item
   uint32_t items_cap;
-  uint32_t *counter;         // work counter
+  uint32_t *counter;         // work counters: [0] first phase, [1] second phase
+  uint32_t two_rounds;       // verification asks the lower-priority lists first, the higher-priority ones only for the survivors
+  uint32_t part_lo, part_hi; // this launch scans items [n_items * part_lo / 256, n_items * part_hi / 256): 0..256 = all.  Sharded
+                             // runs scan the rarest items first, exchange the per-query k-th keys, then scan the rest
   unsigned long long *counters;  // [8]: 0 postings scanned, 3 items scanned, 4 postings verified, 5 items dropped by MaxScore
 };
 
@@ -102,10 +105,11 @@ static __global__ void slg_term_ub_gather_kernel(SegmentDev seg, ScanDev sc, uin
 // slot order) + extra below the k-th score means no doc of the block can enter the top k and the block is not read; the
 // others are summed per doc (16 docs per lane, slot order) and the docs that can still qualify are verified exactly.
 constexpr uint32_t kColSlices = 64;
-template <int UNUSED>
+// POOLS: k > kWarpMaxK (candidate pools + radix select); compiled out otherwise so that the common small-k kernels stay lean
+template <int POOLS>
 __global__ void __launch_bounds__(256) slg_columns_pruned_kernel(SegmentDev seg, WarpBatchDev wb, StreamDev sd) {
   __shared__ __align__(16) unsigned long long s_cand[8][kWarpCand];
-  __shared__ uint32_t s_hist[8][256];
+  __shared__ uint32_t s_hist[8][POOLS ? 256 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_colq = *sd.n_colq;
   const uint32_t wid = blockIdx.x * 8 + warp;
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(256) slg_columns_pruned_kernel(SegmentDev seg,
   const uint32_t per = (n_blocks + kColSlices - 1) / kColSlices;
   const uint32_t b0 = slice * per, b1 = min(n_blocks, b0 + per);
   WarpCand wc;
-  wc.begin(s_cand[warp], ld_cg_u64(wb.thr_key + cq.qi), wb.k, lane, 1u, wb.pool_keys ? s_hist[warp] : nullptr);
+  wc.begin(s_cand[warp], ld_cg_u64(wb.thr_key + cq.qi), wb.k, lane, 1u, POOLS ? s_hist[warp] : nullptr);
   auto cut_of = [&]() {
     if (wc.thr == kThrInit) return 0u;
     const float cf = __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f - cq.extra * 1.00002f;
@@ -312,10 +316,10 @@ static __global__ void __launch_bounds__(256) slg_scan_items_kernel(ScanDev sc) 
   sc.items[i] = lo;
 }
 
-template <bool PRUNE>
+template <bool PRUNE, bool POOLS>
 __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev seg, WarpBatchDev wb, ScanDev sc) {
   __shared__ __align__(16) unsigned long long s_cand[kScanWarps][kWarpCand];
-  __shared__ uint32_t s_hist[kScanWarps][256];
+  __shared__ uint32_t s_hist[kScanWarps][POOLS ? 256 : 1];
   __shared__ uint32_t s_qidx[kScanWarps][kScanQueue];
   __shared__ float s_qval[kScanWarps][kScanQueue];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -323,18 +327,20 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
   uint32_t *q_idx = s_qidx[warp];
   float *q_val = s_qval[warp];
   const uint32_t k = wb.k;
-  const uint32_t n_items = *sc.n_items;
+  const uint32_t n_all = *sc.n_items;
+  const uint32_t item_lo = (uint32_t)(((uint64_t)n_all * sc.part_lo) >> 8), n_items = (uint32_t)(((uint64_t)n_all * sc.part_hi) >> 8);
+  uint32_t *work = sc.counter + (sc.part_lo ? 1 : 0);
   const float inv_docs = 1.0f / (float)max(seg.doc_count, 1u);
   unsigned long long n_scanned = 0, n_verified = 0, n_lookups = 0;
   uint32_t n_dropped = 0, n_done = 0;
   WarpCand wc;
 
   uint32_t item = 0;
-  if (lane == 0) item = atomicAdd(sc.counter, 1u);
+  if (lane == 0) item = item_lo + atomicAdd(work, 1u);
   item = __shfl_sync(0xFFFFFFFFu, item, 0);
   while (item < n_items) {
     uint32_t next_item = 0;
-    if (lane == 0) next_item = atomicAdd(sc.counter, 1u);
+    if (lane == 0) next_item = item_lo + atomicAdd(work, 1u);
     const uint32_t pi = __ldg(sc.order + __ldg(sc.items + item));
     const ScanPair pr = sc.pairs[pi];
     const unsigned long long thr0 = ld_cg_u64(wb.thr_key + pr.qi);
@@ -345,7 +351,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
       n_dropped++;  // this term and everything of lower priority cannot lift a doc into the top k
     } else {
       n_done++;
-      wc.begin(cand, thr0, k, lane, 0u, wb.pool_keys ? s_hist[warp] : nullptr);
+      wc.begin(cand, thr0, k, lane, 0u, POOLS ? s_hist[warp] : nullptr);
       const uint32_t qslot = pr.qslot_t >> 3, t = pr.qslot_t & 7u;
       const QTerm *qts = wb.qterms + (uint64_t)qslot * kWarpMaxTerms;
       const uint32_t nt = __ldg(&wb.qheads[qslot].nt);
@@ -426,16 +432,24 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
         }
         alive = alive && (known + fmaxf(unknown, 0.0f)) * 1.0001f >= thr_s;
         bool stand_back = false;
+        // two rounds over the other sparse terms.  First those of LOWER priority: each look-up replaces a bound by the exact
+        // contribution, so a doc that cannot reach the k-th score dies here.  Only the few survivors then ask the terms of
+        // HIGHER priority (the rarer lists, usually without a presence bitmap: a full search each) whether one of them holds
+        // the doc — then that term's scan offers it — their bounds were never part of `unknown`.
+        const int n_rounds = sc.two_rounds ? 2 : 1;
+#pragma unroll 1
+        for (int round = 0; round < n_rounds; round++)
 #pragma unroll
         for (int u = 0; u < (int)kWarpMaxTerms; u++) {
           const uint32_t kind = __shfl_sync(0xFFFFFFFFu, m_kind, u);
           if (kind != 1u || u == (int)t) continue;  // (uniform)
+          const float ub = __shfl_sync(0xFFFFFFFFu, m_ub, u);
+          const bool higher = ub > my_ub || (ub == my_ub && u < (int)t);  // a holder of higher priority offers the doc itself
+          if (n_rounds == 2 && higher != (round == 1)) continue;  // (uniform)
           if (!__any_sync(0xFFFFFFFFu, alive)) break;
           const uint64_t pb = __shfl_sync(0xFFFFFFFFu, m_base, u), bo = __shfl_sync(0xFFFFFFFFu, m_bits, u);
           const uint32_t dfu = __shfl_sync(0xFFFFFFFFu, m_df, u);
-          const float w = __shfl_sync(0xFFFFFFFFu, m_w, u), ub = __shfl_sync(0xFFFFFFFFu, m_ub, u),
-                      dens = __shfl_sync(0xFFFFFFFFu, m_dens, u);
-          const bool higher = ub > my_ub || (ub == my_ub && u < (int)t);  // a holder of higher priority offers the doc itself
+          const float w = __shfl_sync(0xFFFFFFFFu, m_w, u), dens = __shfl_sync(0xFFFFFFFFu, m_dens, u);
           if (alive) {
             n_lookups++;
             const uint32_t *dp = seg.post_doc + pb;

@@ -424,8 +424,8 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
   // flat posting scan + column pass: the automatic choice; scan_kernels 0 keeps the sub-tile kernels (stream / items)
   const bool run_scan = run_items && ix->scan_kernels && bt->colq != nullptr && !(ix->strict_accumulate && !prune);
   const bool two_step = !(do_seeds && do_sweep);
-  if (two_step && (ix->segs.size() != 1 || !run_items || !prune || run_scan))
-    return fail(ix, SLG_ERR_UNSUPPORTED, "the two-step run (seeds, threshold exchange, sweep) needs one segment per handle, a pruned execution and the items kernel");
+  if (two_step && (ix->segs.size() != 1 || !run_items || (!prune && !run_scan)))
+    return fail(ix, SLG_ERR_UNSUPPORTED, "the two-step run (first part, threshold exchange, rest) needs one segment per handle and the posting scan or the pruned items kernel");
   unsigned char *dp = bt->d_pack;
   size_t smem = 0;
   const bool run_scan_pre = bt->can_items && !bt->want_stats && ix->scan_kernels && bt->colq != nullptr && !(ix->strict_accumulate && !prune);
@@ -591,7 +591,7 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       }
     }
     const bool run_stream = run_items && !prune && bt->colq != nullptr && !run_scan && bt->plan_docs <= 2048;  // (posting numbers of a sub-tile fit 15 bits)
-    if (do_sweep && score && run_scan) {
+    if ((do_sweep || do_seeds) && score && run_scan) {
       ScanDev sc{};
       sc.ut_term = bd.ut_term;
       sc.ut_max = bt->ut_max;
@@ -615,21 +615,27 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       sdv.stage_cap = ix->stage_cap;
       sdv.strict = 0;
       sdv.counters = bt->item_counters;
-      if (prune && s->dev.term_ub) {
-        slg_term_ub_gather_kernel<<<(bt->U + 255) / 256, 256, 0, st>>>(s->dev, sc, bt->U);
-      } else {  // exhaustive: no index-time bound, the maxima are reduced from the batch's posting scores
-        SLG_CUDA(ix, cudaMemsetAsync(bt->ut_max, 0, (size_t)bt->U * 4, st));
-        slg_term_max_kernel<<<dim3((bt->U + 7) / 8, kMaxSlices), 256, 0, st>>>(s->dev, sc, bt->U);
+      if (do_seeds) {
+        if (prune && s->dev.term_ub) {
+          slg_term_ub_gather_kernel<<<(bt->U + 255) / 256, 256, 0, st>>>(s->dev, sc, bt->U);
+        } else {  // exhaustive: no index-time bound, the maxima are reduced from the batch's posting scores
+          SLG_CUDA(ix, cudaMemsetAsync(bt->ut_max, 0, (size_t)bt->U * 4, st));
+          slg_term_max_kernel<<<dim3((bt->U + 7) / 8, kMaxSlices), 256, 0, st>>>(s->dev, sc, bt->U);
+        }
+        slg_scan_pairs_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, wb, sc, ix->dbg);
+        slg_scan_order_kernel<<<1, 1024, 0, st>>>(wb, sc);
+        if (bt->scan_items_cap) slg_scan_items_kernel<<<(bt->scan_items_cap + 255) / 256, 256, 0, st>>>(sc);
+        for (int i = 0; i < 4; i++) count_launch(ix);
+        SLG_CUDA(ix, cudaGetLastError());
+        SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));  // (the scoring time of this path starts here)
       }
-      slg_scan_pairs_kernel<<<(Q + 127) / 128, 128, 0, st>>>(s->dev, wb, sc, ix->dbg);
-      slg_scan_order_kernel<<<1, 1024, 0, st>>>(wb, sc);
-      if (bt->scan_items_cap) slg_scan_items_kernel<<<(bt->scan_items_cap + 255) / 256, 256, 0, st>>>(sc);
-      for (int i = 0; i < 4; i++) count_launch(ix);
-      SLG_CUDA(ix, cudaGetLastError());
-      SLG_CUDA(ix, cudaEventRecord(ix->ev[2], st));  // (the scoring time of this path starts here)
-      SLG_CUDA(ix, launch_scan(prune, s->dev, wb, sc, ix->n_sm * 4, st));
+      // one launch over all items, or (sharded runs) the rarest items first, the threshold exchange, then the rest
+      sc.two_rounds = (ix->dbg & 8u) ? 1u : 0u;
+      sc.part_lo = do_seeds ? 0u : ix->scan_first_part;
+      sc.part_hi = do_sweep ? 256u : ix->scan_first_part;
+      SLG_CUDA(ix, launch_scan(prune, wb.pool_keys != nullptr, s->dev, wb, sc, ix->n_sm * 4, st));
       count_launch(ix);
-      if (s->n_cols && !(ix->dbg & 4u)) {
+      if (do_sweep && s->n_cols && !(ix->dbg & 4u)) {
         slg_colgroups_kernel<<<1, 1024, 0, st>>>(s->dev, wb, sdv, s->n_cols, prune ? bt->ut_max : nullptr);
         count_launch(ix);
         SLG_CUDA(ix, cudaGetLastError());
@@ -644,14 +650,13 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
           // few queries keep an essential column term: one warp per (query, slice of the doc range), blocks skipped by col_tmax
           (void)csmem;
           (void)n_cblocks;
-          slg_columns_pruned_kernel<0><<<(Q * kColSlices + 7) / 8, 256, 0, st>>>(s->dev, wb, sdv);
-          SLG_CUDA(ix, cudaGetLastError());
+          SLG_CUDA(ix, launch_columns_pruned(wb.pool_keys != nullptr, s->dev, wb, sdv, (int)((Q * kColSlices + 7) / 8), st));
         } else {
-          SLG_CUDA(ix, launch_score_columns(false, s->dev, wb, sdv, csmem, (int)std::min<uint32_t>((uint32_t)ix->n_sm, n_cblocks), st));
+          SLG_CUDA(ix, launch_score_columns(false, wb.pool_keys != nullptr, s->dev, wb, sdv, csmem, (int)std::min<uint32_t>((uint32_t)ix->n_sm, n_cblocks), st));
         }
         count_launch(ix);
       }
-      ix->ctr.score_launches++;
+      if (do_sweep) ix->ctr.score_launches++;
     }
     if (do_sweep) {
       // ---- scoring ----
@@ -690,7 +695,7 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
           sdv.col_resident = (uint32_t)std::min<size_t>(s->n_cols, budget / (2 * kColBlock * 4));
           const size_t csmem = column_smem(sdv.col_resident, sdv.n_smax);
           const uint32_t n_cblocks = (s->doc_count + kColBlock - 1) / kColBlock;
-          SLG_CUDA(ix, launch_score_columns(false, s->dev, wb, sdv, csmem, (int)std::min<uint32_t>((uint32_t)ix->n_sm, n_cblocks), st));
+          SLG_CUDA(ix, launch_score_columns(false, wb.pool_keys != nullptr, s->dev, wb, sdv, csmem, (int)std::min<uint32_t>((uint32_t)ix->n_sm, n_cblocks), st));
           count_launch(ix);
         }
         ix->ctr.score_launches++;

@@ -357,9 +357,10 @@ struct WarpCand {
       __threadfence();
       __syncwarp();
       if (total == k) thr = max(thr, cand[k - 1]);
+      thr = max(thr, thr_now);
       if (lane == 0) {
         st_cg_u32(wb.topk_count + qi, total);
-        if (total == k) st_cg_u64(wb.thr_key + qi, cand[k - 1]);
+        if (total == k && cand[k - 1] > thr_now) st_cg_u64(wb.thr_key + qi, cand[k - 1]);  // (thr_now may be a bound imported from another shard)
         __threadfence();
         atomicExch(wb.lock + qi, 0u);
       }
@@ -942,10 +943,10 @@ __host__ __device__ inline size_t column_smem(uint32_t resident, uint32_t n_smax
   return (size_t)2 * resident * kColBlock * 4 + (((size_t)n_smax * 4 + 15) & ~(size_t)15) + (size_t)kColWarps * kWarpCand * 8 + 16;
 }
 
-template <bool PRUNE>
+template <bool PRUNE, bool POOLS>
 __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(SegmentDev seg, WarpBatchDev wb, StreamDev sd) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_hist[kColWarps][256];
+  __shared__ uint32_t s_hist[kColWarps][POOLS ? 256 : 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n_used = *sd.n_ucol, n_colq = *sd.n_colq;
   const uint32_t resident = min(sd.col_resident, n_used), n_smax = min(n_used, sd.n_smax);
@@ -1106,7 +1107,7 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(Segme
           mx = max(mx, max(max(__float_as_uint(v[x].x), __float_as_uint(v[x].y)), max(__float_as_uint(v[x].z), __float_as_uint(v[x].w))));
         if (!__any_sync(0xFFFFFFFFu, mx >= cut && mx != 0u)) continue;
         // ---- per doc: the docs that can enter the top k, one per lane and round ----
-        wc.begin(cand, qthr, k, lane, 1u, wb.pool_keys ? s_hist[warp] : nullptr);
+        wc.begin(cand, qthr, k, lane, 1u, POOLS ? s_hist[warp] : nullptr);
         uint32_t todo = 0u;
 #pragma unroll
         for (uint32_t x = 0; x < kColBlock / 128; x++) {

@@ -471,9 +471,9 @@ class PreparedBatch:
         self.index, self.handle, self.n_queries, self.k = index, handle, n_queries, k
         self._keepalive = keepalive
         self.execution = execution
-        # pruned executions can run in two steps (seeds / threshold exchange / sweep) when the engine's items kernel
-        # takes the batch; the first refusal (SLG_ERR_UNSUPPORTED) switches this off
-        self.two_step_ok = execution != "bm25"
+        # a batch the posting scan (or the pruned items kernel) takes can run in two steps — first part, exchange of the
+        # per-query k-th keys between shards, rest; the first refusal (SLG_ERR_UNSUPPORTED) switches this off
+        self.two_step_ok = True
 
     def enable_stats(self, on: bool = True) -> None:
         self.index._check(self.index.lib.slg_batch_enable_stats(self.handle, 1 if on else 0))

@@ -632,3 +632,59 @@ def test_stats_count_scored_docs_and_postings(kernel):
         assert st["postings_advanced"][q] == n_post
         assert st["scored_docs"][q] == n_docs
     gi.close()
+
+
+# ---- sharded runs: the per-query threshold exchange between the two parts of the posting scan ----------
+@pytest.mark.parametrize("k", [11, 101])
+@pytest.mark.parametrize("execution", ["bm25", "bmw"])
+def test_two_step_scan_with_threshold_exchange(execution, k):
+    """two shards (two handles on one device): first part of the scan, max of the shards' k-th keys imported into both, rest of
+    the scan.  Every shard then prunes against the better bound; the merged result must stay the exact top k"""
+    import torch
+    from oracle import slo
+    from searchlite_b200.shard import shard_ranges
+    n_docs, vocab = 60_000, 4_000
+    qb = synth.generate_queries(96, vocab, seed=232, min_rank=2)
+    gis, oras, preps = [], [], []
+    for r, (lo, hi) in enumerate(shard_ranges(n_docs, 2)):
+        spec = synth.CorpusSpec(n_docs=hi - lo, vocab=vocab, seed=231, len_lo=20, len_hi=90, segment_ord=r, doc_base=lo)
+        seg = synth.generate_segment(spec, "cpu")
+        gi = GpuIndex(0, options={"scan_first_part": 64})
+        gi.load_segment(seg)
+        gis.append(gi)
+        oras.append(slo.OracleIndex(seg))
+    one_step = []
+    for gi in gis:
+        p = gi.prepare(qb, k, execution)
+        p.run(sync=True)
+        one_step.append(p.fetch())
+        preps.append(p)
+    # two-step: seeds on both, exchange, sweep on both
+    for p in preps:
+        assert p.run_seeds()
+    torch.cuda.synchronize()
+    from searchlite_b200.shard import ShardedSearcher
+    keys = [ShardedSearcher(gi, qb.n_queries, k)._as_tensor(p.threshold_keys_ptr(), qb.n_queries * 8, torch.int64).clone() for gi, p in zip(gis, preps)]
+    glob = torch.maximum(keys[0], keys[1])
+    torch.cuda.synchronize()
+    raised = 0
+    for gi, p, own in zip(gis, preps, keys):
+        raised += int(((glob >> 32) > (own >> 32)).sum())
+        p.import_thresholds(glob.data_ptr())
+        p.run_sweep(sync=True)
+    if k <= 32:
+        assert raised > 0  # the exchange did hand some shard a better bound (k > 32: a pool publishes its bound only once it overflows)
+    two_step = [p.fetch() for p in preps]
+    from tests.helpers import canonical_batch
+    for qi in range(qb.n_queries):
+        sub = qb.subset(qi, qi + 1)
+        ref = slo.merge_hits([o.search_batch(canonical_batch(g, sub, r), k, "bm25")[0][0][: o.search_batch(canonical_batch(g, sub, r), k, "bm25")[1][0]]
+                              for r, (o, g) in enumerate(zip(oras, gis))], k)
+        got1 = slo.merge_hits([h[qi, : c[qi]] for h, c in one_step], k)
+        got2 = slo.merge_hits([h[qi, : c[qi]] for h, c in two_step], k)
+        assert got1.tobytes() == ref.tobytes(), qi
+        assert got2.tobytes() == ref.tobytes(), qi
+    for p in preps:
+        p.free()
+    for gi in gis:
+        gi.close()
