@@ -67,6 +67,8 @@ def parse_args():
     ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of --impl reference")
     ap.add_argument("--candidates", type=int, default=1000, help="c5: BM25 candidates per query handed to the rerank")
     ap.add_argument("--no-phrases", action="store_true", help="c4: skip the phrase leg (positions resident: +21 GB)")
+    ap.add_argument("--threshold-board", action="store_true",
+                    help="N > 1: shards push their per-query k-th scores into each other's boards over NVLink peer mappings during the scan")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-exhaustive", action="store_true", help="skip the exhaustive (bm25) leg and its roofline")
     ap.add_argument("--no-pruned", action="store_true", help=argparse.SUPPRESS)  # (round-1 flag: same as --no-exhaustive)
@@ -278,7 +280,7 @@ def main():
     torch.cuda.empty_cache()
 
     stream = torch.cuda.ExternalStream(gi.stream_ptr(), device=device)
-    searcher = ShardedSearcher(gi, args.queries, k) if world > 1 else None
+    searcher = ShardedSearcher(gi, args.queries, k, threshold_board=args.threshold_board) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -317,10 +319,17 @@ def main():
         # the scoring kernels' own CUDA-event time (handle's stream): one more, synchronous, pass — the sharded loop above
         # runs asynchronously, so its passes leave no per-kernel time behind; max over ranks like the step time
         c0 = gi.counters()
+        if world > 1:
+            barrier()
+            searcher.attach_board(p)  # (a fresh epoch: the pass must not start from the thresholds its peers left behind)
         p.run(sync=True)
         c1 = gi.counters()
         kernel_ms = max_over_ranks((c1["score_ms_total"] - c0["score_ms_total"]) / max(c1["score_launches"] - c0["score_launches"], 1))
-        res = searcher.exchange_and_merge(p) if world > 1 else p.fetch()
+        if world == 1:
+            res = p.fetch()
+        else:
+            res = searcher.exchange_and_merge(p)
+            p.fetch()  # (this rank's own work counters)
         ctr = gi.counters()
         p.free()
         return ms, kernel_ms, launches, res, ctr
@@ -377,7 +386,8 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, world), "execution": args.execution,
                    "l2": "inputs larger than L2 (resident postings >> 126 MB); no explicit flush",
-                   "postings_resident_this_rank": int(n_postings), "kernel": args.kernel, "options": options},
+                   "postings_resident_this_rank": int(n_postings), "kernel": args.kernel, "options": options,
+                   "threshold_board": bool(searcher is not None and searcher.board is not None)},
         "e2e": e2e,
         "gpu_launches": int(round(launches * args.steps)),
         "clocks": clocks,

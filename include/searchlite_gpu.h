@@ -391,6 +391,16 @@ int32_t slg_batch_run_seeds(slg_batch_t *);
 int32_t slg_batch_threshold_keys(slg_batch_t *, void **dev_keys);
 int32_t slg_batch_import_thresholds(slg_batch_t *, const void *dev_keys);
 int32_t slg_batch_run_sweep(slg_batch_t *, int32_t sync);
+/* Sharded runs over NVLink / NVSwitch, one segment per handle: a THRESHOLD BOARD in peer-accessible device memory (CUDA IPC
+ * or symmetric-memory mappings the caller set up; n_queries x 8 bytes per shard, zero-initialised once).  While the posting
+ * scan runs, a shard that raises a query's k-th score pushes it into every peer's board (system-scope atomic max on the peer
+ * mapping) and folds what its peers pushed into its own pruning bound — the largest k-th score of any shard is a lower
+ * bound of the global one — so all shards prune against (nearly) the global threshold with no kernel boundary, collective
+ * or host round trip.  local_board: this shard's board; peer_boards: the mappings of the OTHER shards' boards (at most 7);
+ * epoch: a number >= 1 that is the same on every shard for one batch and rises with every batch (stale pushes are ignored).
+ * The results are exact with or without a board.  local_board NULL switches it off. */
+int32_t slg_batch_set_threshold_board(slg_batch_t *, void *local_board, void *const *peer_boards, uint32_t n_peers,
+                                      uint32_t epoch);
 int32_t slg_batch_fetch(slg_batch_t *, slg_hit_t *out_hits, uint32_t *out_counts, slg_stats_t *out_stats);
 /* device pointers of the last run's results (n_queries*k slg_hit_t, n_queries u32) for an
  * allgather by the caller; valid until the batch is re-run or freed */

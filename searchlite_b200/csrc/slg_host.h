@@ -188,6 +188,7 @@ struct slg_index {
   uint32_t stage_cap = 1024;     // sparse pass: postings a warp stages in shared memory per span (slg_stream_kernel.cuh)
   uint32_t strict_accumulate = 0; // exhaustive stream kernels: 1 = sum every posting per doc; 0 = bounded accumulation (slg_stream_kernel.cuh)
   uint32_t dbg = 0;
+  uint32_t scan_chunk = 4096;    // flat posting scan: postings per work item (multiple of 256)
   uint32_t scan_first_part = 24; // two-step (sharded) runs: the first step scans this many 256ths of the items (rarest first) before the threshold exchange
   uint32_t scan_kernels = 1;     // plain OR batches: 1 = flat posting scan + column pass (slg_scan_kernel.cuh), 0 = the sub-tile kernels
   uint32_t stream_kernels = 1;   // exhaustive plain OR batches: 1 = sparse pass + column pass, 0 = the items kernel
@@ -292,7 +293,7 @@ struct slg_batch {
   float *ut_max = nullptr;
   slg::ScanPair *scan_pairs = nullptr;
   uint32_t *scan_order = nullptr, *scan_item_start = nullptr, *scan_items = nullptr;
-  uint32_t scan_items_cap = 0;
+  uint32_t scan_items_cap = 0, scan_chunk = 4096;
   uint32_t max_cols = 0;
   uint8_t *done = nullptr;
   size_t done_bytes = 0;
@@ -314,6 +315,10 @@ struct slg_batch {
   uint32_t plan_docs = 0;             // docs per tile / sub-tile of this batch
   uint32_t sub_tiles_max = 0;
   uint32_t n_segs_run = 0;
+  // sharded runs: threshold board in peer-accessible memory (slg_batch_set_threshold_board); board == nullptr: none
+  unsigned long long *board = nullptr;
+  unsigned long long *peer_board[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint32_t n_board_peers = 0, board_epoch = 0;
   bool reranked = false;              // slg_rerank_batch ran on the last results: the blocks carry hybrid scores + vector scores
   bool seeds_done = false;            // two-step run (slg_batch_run_seeds / slg_batch_run_sweep)
   void *pinned = nullptr;             // [pack | results | stats]

@@ -33,7 +33,7 @@
 
 namespace slg {
 
-constexpr uint32_t kScanChunk = 4096;  // postings per scan item
+constexpr uint32_t kScanChunk = 4096;  // postings per scan item (default of the scan_chunk option; a multiple of 256)
 constexpr int kScanWarps = 8;
 constexpr uint32_t kScanQueue = 512;  // ring: a step queues at most 256 candidates on top of a remainder below 32
 
@@ -61,6 +61,7 @@ struct ScanDev {
   uint32_t *items;           // [items_cap] ordered-pair index of every item
   uint32_t items_cap;
   uint32_t *counter;         // work counters: [0] first phase, [1] second phase
+  uint32_t chunk;            // postings per item
   uint32_t two_rounds;       // verification asks the lower-priority lists first, the higher-priority ones only for the survivors
   uint32_t part_lo, part_hi; // this launch scans items [n_items * part_lo / 256, n_items * part_hi / 256): 0..256 = all.  Sharded
                              // runs scan the rarest items first, exchange the per-query k-th keys, then scan the rest
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(256) slg_columns_pruned_kernel(SegmentDev seg,
   const uint32_t per = (n_blocks + kColSlices - 1) / kColSlices;
   const uint32_t b0 = slice * per, b1 = min(n_blocks, b0 + per);
   WarpCand wc;
-  wc.begin(s_cand[warp], ld_cg_u64(wb.thr_key + cq.qi), wb.k, lane, 1u, POOLS ? s_hist[warp] : nullptr);
+  wc.begin(s_cand[warp], load_threshold(wb, cq.qi), wb.k, lane, 1u, POOLS ? s_hist[warp] : nullptr);
   auto cut_of = [&]() {
     if (wc.thr == kThrInit) return 0u;
     const float cf = __uint_as_float((uint32_t)(wc.thr >> 32)) * 0.99998f - cq.extra * 1.00002f;
@@ -278,7 +279,7 @@ static __global__ void __launch_bounds__(1024) slg_scan_order_kernel(WarpBatchDe
   for (uint32_t b0 = 0; b0 < np; b0 += nthr) {
     const uint32_t i = b0 + tid;
     uint32_t c = 0;
-    if (i < np) c = (sc.pairs[sc.order[i]].df + kScanChunk - 1) / kScanChunk;
+    if (i < np) c = (sc.pairs[sc.order[i]].df + sc.chunk - 1) / sc.chunk;
     s_scan[tid] = c;
     __syncthreads();
     for (uint32_t o = 1; o < nthr; o <<= 1) {
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
     if (lane == 0) next_item = item_lo + atomicAdd(work, 1u);
     const uint32_t pi = __ldg(sc.order + __ldg(sc.items + item));
     const ScanPair pr = sc.pairs[pi];
-    const unsigned long long thr0 = ld_cg_u64(wb.thr_key + pr.qi);
+    const unsigned long long thr0 = load_threshold(wb, pr.qi);
     const uint32_t chunk = item - pr.first_item;
     const bool have_thr0 = thr0 != kThrInit;
     const float thr0_score = __uint_as_float((uint32_t)(thr0 >> 32));
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
       }
       const float my_ub = __shfl_sync(0xFFFFFFFFu, m_ub, t);
       const float4 *sp = reinterpret_cast<const float4 *>(wb.scores + pr.base);
-      const uint32_t i0 = chunk * kScanChunk, i1 = min(pr.df, i0 + kScanChunk);
+      const uint32_t i0 = chunk * sc.chunk, i1 = min(pr.df, i0 + sc.chunk);
       n_scanned += i1 - i0;
       uint32_t cut = 0u;
       auto recut = [&]() {

@@ -321,12 +321,13 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
         const uint32_t term = ut[qt_u[i]];
         if (term >= sg->n_terms || !qt_f[i]) continue;
         if (!sg->h_term_col.empty() && sg->h_term_col[term] >= 0) continue;
-        n += (sg->h_df[term] + kScanChunk - 1) / kScanChunk;
+        n += (sg->h_df[term] + ix->scan_chunk - 1) / ix->scan_chunk;
       }
       bt->scan_items_cap = (uint32_t)std::max<uint64_t>(bt->scan_items_cap, std::min<uint64_t>(n, 0xFFFFFFF0ull));
     }
   }
   const bool want_scan = bt->can_items;
+  bt->scan_chunk = ix->scan_chunk;
   const size_t o_utmax = want_scan ? carve((size_t)std::max(bt->U, 1u) * 4) : 0;
   const size_t o_pairs = want_scan ? carve((size_t)n_queries * kWarpMaxTerms * sizeof(ScanPair)) : 0;
   const size_t o_order = want_scan ? carve((size_t)n_queries * kWarpMaxTerms * 4) : 0;
@@ -530,6 +531,10 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       wb.pool_count = bt->pool_count;
       wb.pool_lock = bt->pool_lock;
       wb.pool_cap = bt->pool_cap;
+      wb.board = run_scan ? bt->board : nullptr;  // (the posting scan and its column pass read and push; the other kernels keep to themselves)
+      for (uint32_t p = 0; p < kMaxBoardPeers; p++) wb.peer_board[p] = bt->peer_board[p];
+      wb.n_peers = bt->n_board_peers;
+      wb.epoch = bt->board_epoch;
       // (plan batches: the matcher form of the kernel unless the staged plain-OR form applies — size for the larger)
       wsmem = run_items ? (size_t)warps * warp_kernel_smem_per_warp(wb.sub_docs, false, true, 1)
                         : (size_t)warps * warp_kernel_smem_per_warp(wb.sub_docs, bt->matcher || (bt->has_plan && !bt->staged), prune,
@@ -602,6 +607,7 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       sc.item_start = bt->scan_item_start;
       sc.items = bt->scan_items;
       sc.items_cap = bt->scan_items_cap;
+      sc.chunk = bt->scan_chunk;
       sc.counter = bt->work_counter + 7;
       sc.counters = bt->item_counters;
       StreamDev sdv{};
@@ -828,6 +834,24 @@ int32_t slg_batch_run_sweep(slg_batch_t *bt, int32_t sync) {
   if (rc) return rc;
   bt->seeds_done = false;
   return sync ? finish_timing(bt) : SLG_OK;
+}
+
+int32_t slg_batch_set_threshold_board(slg_batch_t *bt, void *local_board, void *const *peer_boards, uint32_t n_peers, uint32_t epoch) {
+  if (!bt) return SLG_ERR_INVALID;
+  slg_index *ix = bt->ix;
+  if (!local_board) {  // switch the exchange off
+    bt->board = nullptr;
+    bt->n_board_peers = 0;
+    return SLG_OK;
+  }
+  if (n_peers > kMaxBoardPeers || (n_peers && !peer_boards)) return fail(ix, SLG_ERR_INVALID, "a threshold board has at most %u peers", kMaxBoardPeers);
+  if (epoch == 0) return fail(ix, SLG_ERR_INVALID, "board epochs start at 1 and rise with every batch");
+  if (ix->segs.size() != 1) return fail(ix, SLG_ERR_UNSUPPORTED, "the threshold board needs one segment per handle (shard == segment)");
+  bt->board = static_cast<unsigned long long *>(local_board);
+  for (uint32_t p = 0; p < kMaxBoardPeers; p++) bt->peer_board[p] = p < n_peers ? static_cast<unsigned long long *>(peer_boards[p]) : nullptr;
+  bt->n_board_peers = n_peers;
+  bt->board_epoch = epoch;
+  return SLG_OK;
 }
 
 int32_t slg_batch_enable_stats(slg_batch_t *bt, int32_t on) {

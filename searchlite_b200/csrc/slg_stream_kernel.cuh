@@ -76,7 +76,7 @@ struct StreamDev {
 // cannot enter the top k — and the others look at v + extra, extra = the bounds of their non-essential SPARSE terms (lists
 // the scan may have dropped, so a doc may hold them unseen).
 __device__ __forceinline__ bool colq_prune(const WarpBatchDev &wb, const float *ut_max, uint32_t qslot, uint32_t qi, uint32_t nt, float &extra) {
-  const unsigned long long thr = wb.thr_key[qi];
+  const unsigned long long thr = load_threshold(wb, qi);
   float ub[kWarpMaxTerms];
   bool col[kWarpMaxTerms];
   for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
@@ -259,14 +259,16 @@ struct WarpCand {
       out += __popc(bal);
       __syncwarp();
     }
-    if (lane == 0) atomicMax(wb.thr_key + qi, kth);
+    if (lane == 0) {
+      if (atomicMax(wb.thr_key + qi, kth) < kth) push_threshold(wb, qi, kth);
+    }
     thr = max(thr, kth);
     return out;
   }
   // k > kWarpMaxK: append the pending keys to the query's pool
   __device__ __forceinline__ void flush(const WarpBatchDev &wb, uint32_t qi) {
     if (cnt == 0) return;
-    const unsigned long long thr_now = ld_cg_u64(wb.thr_key + qi);
+    const unsigned long long thr_now = load_threshold(wb, qi);
     thr = max(thr, thr_now);
     // drop what the published threshold already rules out, then append under the pool's lock
     unsigned long long k0 = lane < (int)cnt ? cand[lane] : 0ull, k1 = 32 + lane < (int)cnt ? cand[32 + lane] : 0ull;
@@ -337,7 +339,7 @@ struct WarpCand {
       return;
     }
     if (cnt == 0) return;
-    const unsigned long long thr_now = ld_cg_u64(wb.thr_key + qi);
+    const unsigned long long thr_now = load_threshold(wb, qi);
     const bool useful = lane < (int)cnt && cand[lane] > thr_now;  // cnt <= 32 after every push
     if (__any_sync(0xFFFFFFFFu, useful)) {
       if (lane == 0) {
@@ -360,7 +362,10 @@ struct WarpCand {
       thr = max(thr, thr_now);
       if (lane == 0) {
         st_cg_u32(wb.topk_count + qi, total);
-        if (total == k && cand[k - 1] > thr_now) st_cg_u64(wb.thr_key + qi, cand[k - 1]);  // (thr_now may be a bound imported from another shard)
+        if (total == k && cand[k - 1] > thr_now) {  // (thr_now may be a bound that came from another shard)
+          st_cg_u64(wb.thr_key + qi, cand[k - 1]);
+          push_threshold(wb, qi, cand[k - 1]);
+        }
         __threadfence();
         atomicExch(wb.lock + qi, 0u);
       }
@@ -739,7 +744,7 @@ __global__ void __launch_bounds__(kSparseWarps * 32) slg_score_sparse_kernel(Seg
     const QHead head = wb.qheads[qslot];
     const uint32_t nt = head.nt;
     if (lane < 16) reinterpret_cast<uint4 *>(qt)[lane] = __ldg(reinterpret_cast<const uint4 *>(wb.qterms + (uint64_t)qslot * kWarpMaxTerms) + lane);
-    const unsigned long long thr0 = ld_cg_u64(wb.thr_key + head.qi);
+    const unsigned long long thr0 = load_threshold(wb, head.qi);
     __syncwarp();
     const uint32_t myflags = lane < (int)nt ? qt[lane].flags : 0u;
     const uint32_t spmask = __ballot_sync(0xFFFFFFFFu, (myflags & 5u) == 1u);  // canonical layout: the low nsp slots
@@ -1010,7 +1015,7 @@ __global__ void __launch_bounds__(kColWarps * 32) slg_score_columns_kernel(Segme
       const bool live = c0 + lane < n_colq;
       if (live) {
         cq = sd.colq[c0 + lane];
-        thr = ld_cg_u64(wb.thr_key + cq.qi);
+        thr = load_threshold(wb, cq.qi);
       }
       bool look = false;
       if (live && !cq.off) {

@@ -79,7 +79,36 @@ struct WarpBatchDev {
   unsigned long long *pool_keys;    // [Q][2][pool_cap]
   uint32_t *pool_count, *pool_lock; // [Q][2]
   uint32_t pool_cap;
+  // Sharded runs: the threshold board (slg_batch_set_threshold_board).  board[q] is THIS shard's slot for query q in
+  // peer-accessible memory (NVLink / NVSwitch peer mappings): epoch << 32 | score bits of a k-th key (positive floats order
+  // like their bits, and a newer epoch — the next batch — always wins, so the board is never cleared).  A shard that raises
+  // a query's k-th key pushes it into every peer's board with a system-scope atomic max (fire and forget) and reads its own
+  // board, a local access, whenever it picks the query up again — the best k-th score any shard has found is a valid lower
+  // bound of the global one, so every shard prunes against (nearly) the global threshold without a kernel boundary, a
+  // collective or the host in the loop.  nullptr: no exchange.
+  unsigned long long *board;
+  unsigned long long *peer_board[7];
+  uint32_t n_peers, epoch;
 };
+
+constexpr uint32_t kMaxBoardPeers = 7;
+
+// the query's k-th key as far as this shard knows: its own, or the bound a peer pushed (same epoch only; the doc half is
+// dropped: across shards ties on the score are decided by segment_ord, so only the score transfers)
+__device__ __forceinline__ unsigned long long load_threshold(const WarpBatchDev &wb, uint32_t qi) {
+  unsigned long long t = ld_cg_u64(wb.thr_key + qi);
+  if (wb.board) {
+    const unsigned long long b = ld_cg_u64(wb.board + qi);
+    if ((uint32_t)(b >> 32) == wb.epoch) t = max(t, b << 32);
+  }
+  return t;
+}
+// one lane: a raised k-th key goes to every peer's board
+__device__ __forceinline__ void push_threshold(const WarpBatchDev &wb, uint32_t qi, unsigned long long key) {
+  if (!wb.board) return;
+  const unsigned long long v = ((unsigned long long)wb.epoch << 32) | (key >> 32);
+  for (uint32_t p = 0; p < wb.n_peers; p++) atomicMax_system(wb.peer_board[p] + qi, v);
+}
 
 // resolve the batch's query terms against one segment (runs once per segment per batch).
 // canonical: the term slots of a query are laid out in the DECLARED summation order of the column path

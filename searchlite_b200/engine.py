@@ -133,7 +133,7 @@ EXPORTED_SYMBOLS = [
     "slg_batch_cursor_seen", "slg_cursor_encode", "slg_cursor_decode",
     "slg_batch_run_seeds", "slg_batch_threshold_keys", "slg_batch_import_thresholds", "slg_batch_run_sweep",
     "slg_batch_packed_results", "slg_merge_gathered_packed",
-    "slg_load_vectors_bf16", "slg_rerank_clauses", "slg_rerank_batch", "slg_batch_fetch_vector_scores", "slg_merge_gathered_hybrid",
+    "slg_batch_set_threshold_board", "slg_load_vectors_bf16", "slg_rerank_clauses", "slg_rerank_batch", "slg_batch_fetch_vector_scores", "slg_merge_gathered_hybrid",
 ]
 
 
@@ -206,6 +206,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_batch_run_sweep": [vp, i32],
         "slg_batch_packed_results": [vp, C.POINTER(vp), C.POINTER(u64)],
         "slg_merge_gathered_packed": [vp, vp, u64, u32, u32, u32, vp, vp],
+        "slg_batch_set_threshold_board": [vp, vp, vp, u32, u32],
         "slg_load_vectors_bf16": [vp, u32, u32, vp, vp, u64],
         "slg_rerank_clauses": [vp, vp, u32, u32, u32, vp, vp, u32, vp, vp, vp],
         "slg_rerank_batch": [vp, vp, u32, u32, i32],
@@ -519,6 +520,11 @@ class PreparedBatch:
         vs = np.zeros((self.n_queries, self.k), dtype=np.float32)
         self.index._check(self.index.lib.slg_batch_fetch_vector_scores(self.handle, _ptr(vs)))
         return vs
+
+    def set_threshold_board(self, local_ptr: int, peer_ptrs, epoch: int) -> None:
+        """slg_batch_set_threshold_board: device pointers of this shard's board and of the peers' boards (peer mappings)"""
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*peer_ptrs)
+        self.index._check(self.index.lib.slg_batch_set_threshold_board(self.handle, local_ptr, arr, len(peer_ptrs), epoch))
 
     def packed_results(self):
         """(device pointer, bytes) of the last run's result block: n_queries*k hits, then n_queries counts (then, after a

@@ -47,15 +47,36 @@ def gather_blocks(local_block: torch.Tensor, group=None) -> torch.Tensor:
 class ShardedSearcher:
     """search over world_size shards; every rank ends up with the merged result"""
 
-    def __init__(self, index, n_queries: int, k: int, group=None, host_merge: Optional[Callable] = None):
+    def __init__(self, index, n_queries: int, k: int, group=None, host_merge: Optional[Callable] = None, threshold_board: bool = False):
         self.index, self.q, self.k, self.group = index, n_queries, k, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.host_merge = host_merge
         self.stream = None
         self.block_bytes = n_queries * k * HIT_BYTES + n_queries * 4
+        self.board = None
+        self.epoch = 0
         if index is not None:
             self.dev = torch.device("cuda", index.device)
             self.stream = torch.cuda.ExternalStream(index.stream_ptr(), device=self.dev)
+            if self.world > 1 and self.world <= 8 and threshold_board:
+                self._open_board()
+
+    def _open_board(self) -> None:
+        """the threshold board: n_queries x 8 bytes of symmetric memory per rank, every rank's buffer mapped into every other
+        rank's address space over NVLink (torch symmetric memory: CUDA VMM + handle exchange through the store).  Stays off —
+        the shards then prune against their own thresholds only — where the platform cannot map peers."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty(self.q, dtype=torch.int64, device=self.dev)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group=self.group if self.group is not None else dist.group.WORLD)
+            torch.cuda.synchronize()
+            hdl.barrier()
+            rank = dist.get_rank(self.group)
+            self.board = (buf, hdl, int(hdl.buffer_ptrs[rank]), [int(p) for r, p in enumerate(hdl.buffer_ptrs) if r != rank])
+        except Exception as e:  # noqa: BLE001
+            self.board = None
+            self.board_error = repr(e)
 
     def _as_tensor(self, ptr: int, nbytes: int, dtype=torch.uint8) -> torch.Tensor:
         """zero-copy view of device memory the engine owns (valid until the batch is re-run or freed)"""
@@ -77,7 +98,11 @@ class ShardedSearcher:
             prepared.run(sync=False)
             return prepared.fetch()
         with torch.cuda.stream(self.stream):
-            if exchange_thresholds and prepared.two_step_ok and prepared.run_seeds():
+            if exchange_thresholds and self.board is not None:
+                # thresholds travel between the shards INSIDE the scan (peer pushes over NVLink): one launch, no collective
+                self.attach_board(prepared)
+                prepared.run(sync=False)
+            elif exchange_thresholds == "two-step" and prepared.two_step_ok and prepared.run_seeds():
                 keys = self._as_tensor(prepared.threshold_keys_ptr(), self.q * 8, torch.int64)  # positive-score keys: top bit clear
                 glob = keys.clone()
                 dist.all_reduce(glob, op=dist.ReduceOp.MAX, group=self.group)
@@ -86,6 +111,12 @@ class ShardedSearcher:
             else:
                 prepared.run(sync=False)
             return self._exchange(prepared)
+
+    def attach_board(self, prepared) -> None:
+        """a fresh epoch of the threshold board for the next run of `prepared` (every rank calls this the same number of times)"""
+        if self.board is not None:
+            self.epoch += 1
+            prepared.set_threshold_board(self.board[2], self.board[3], self.epoch)
 
     def _exchange(self, prepared):
         ptr, nbytes = prepared.packed_results()

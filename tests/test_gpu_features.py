@@ -688,3 +688,60 @@ def test_two_step_scan_with_threshold_exchange(execution, k):
         p.free()
     for gi in gis:
         gi.close()
+
+
+@pytest.mark.parametrize("k", [11, 101])
+@pytest.mark.parametrize("execution", ["bm25", "bmw"])
+def test_threshold_board_between_two_shards(execution, k):
+    """slg_batch_set_threshold_board: two shards as two handles on one device, each other's board as the peer mapping.  Shard
+    0 runs first and pushes its k-th scores into shard 1's board; shard 1 then prunes against them.  The merged result stays
+    the exact top k, stale epochs are ignored, and shard 1 verifies fewer postings than it does alone"""
+    import torch
+    from oracle import slo
+    from searchlite_b200.shard import shard_ranges
+    from tests.helpers import canonical_batch
+    n_docs, vocab = 80_000, 4_000
+    qb = synth.generate_queries(128, vocab, seed=242, min_rank=2)
+    gis, oras = [], []
+    for r, (lo, hi) in enumerate(shard_ranges(n_docs, 2)):
+        spec = synth.CorpusSpec(n_docs=hi - lo, vocab=vocab, seed=241, len_lo=20, len_hi=90, segment_ord=r, doc_base=lo)
+        seg = synth.generate_segment(spec, "cpu")
+        gi = GpuIndex(0)
+        gi.load_segment(seg)
+        gis.append(gi)
+        oras.append(slo.OracleIndex(seg))
+    boards = [torch.zeros(qb.n_queries, dtype=torch.int64, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+    preps = [gi.prepare(qb, k, execution) for gi in gis]
+    alone = []
+    for p in preps:
+        p.run(sync=True)
+        alone.append(p.fetch())
+    verified_alone = gis[1].counters()["last_postings_verified"]
+    for epoch in (1, 2):
+        for r, p in enumerate(preps):
+            p.set_threshold_board(boards[r].data_ptr(), [boards[1 - r].data_ptr()], epoch)
+            p.run(sync=True)
+        got = [p.fetch() for p in preps]
+        verified_board = gis[1].counters()["last_postings_verified"]
+        for qi in range(qb.n_queries):
+            sub = qb.subset(qi, qi + 1)
+            lists = []
+            for r, (o, g) in enumerate(zip(oras, gis)):
+                h, c = o.search_batch(canonical_batch(g, sub, r), k, "bm25")
+                lists.append(h[0, : c[0]])
+            ref = slo.merge_hits(lists, k)
+            assert slo.merge_hits([h[qi, : c[qi]] for h, c in got], k).tobytes() == ref.tobytes(), (epoch, qi)
+            assert slo.merge_hits([h[qi, : c[qi]] for h, c in alone], k).tobytes() == ref.tobytes(), qi
+        assert int((boards[1] >> 32).max()) == epoch  # shard 0 pushed into shard 1's board under this epoch
+        if k <= 32:
+            assert verified_board < verified_alone
+    # a board left over from an older epoch is ignored (and overwritten by the newer one)
+    preps[1].set_threshold_board(boards[1].data_ptr(), [boards[0].data_ptr()], 7)
+    preps[1].run(sync=True)
+    h, c = preps[1].fetch()
+    assert h.tobytes() == alone[1][0].tobytes() and c.tobytes() == alone[1][1].tobytes()
+    for p in preps:
+        p.free()
+    for gi in gis:
+        gi.close()
