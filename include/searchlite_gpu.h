@@ -199,35 +199,42 @@ int32_t slg_close(slg_index_t *);
 const char *slg_last_error(const slg_index_t *);
 /* tuning knobs; 0 keeps the default.  tile_docs: docs per shared-memory tile of the CTA-per-item
  * kernel (multiple of 1024); sub_docs: docs per warp-private tile of the warp-per-item kernel
- * (multiple of 128); kernel_choice: 0 = automatic (column front end — see "heavy_kernel" below — for
- * plain OR queries with k <= 32 and <= 8 terms per query, warp kernel for the same shape with a Bool
- * matcher, CTA kernel otherwise), 1 = CTA kernel, 2 = warp kernel (query summation order), 3 = column
- * front end; add 256 to ignore the resident per-posting scores and score postings in place. */
+ * (multiple of 128); kernel_choice: 0 = automatic — plain OR queries with <= 8 terms per query and
+ * k <= 2048 on the flat posting scan + column pass, queries with a Bool matcher, a ScorePlan, a cursor
+ * or statistics on the warp kernel (k <= 32, <= 8 terms) or the CTA kernel (everything else);
+ * 1 = CTA kernel, 2 = warp kernel (the reference's query summation order), 3 = the posting-driven
+ * path or an error; add 256 to ignore the resident per-posting scores and score postings in place. */
 int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, uint32_t sub_docs,
                       uint32_t kernel_choice);
 /* residency / tuning options; the residency ones apply to segments loaded AFTER the call:
  *   "resident_scores"  1/0  keep the unit-weight BM25 contribution of every posting in HBM (default 1)
- *   "dense_den"        n    terms with df * n >= doc_count also get a doc-indexed f32 score column
- *                           (default 8; 0 = no columns)
+ *   "dense_den"        n    terms with df * n >= doc_count also get a doc-indexed f32 score column: they
+ *                           are never scanned posting by posting; verification reads them with one gather
+ *                           (default 24; 0 = no columns)
  *   "dense_min_df"     n    ... and df >= n (default 256)
  *   "max_column_bytes" n    byte budget of the columns of one segment, largest df first (default 24 GiB)
+ *   "bitmap_den"       n    terms with df * n >= doc_count and no column get a presence bitmap, one bit
+ *                           per doc, for the verification's "does this list hold the doc" (default 512; 0 = none)
+ *   "max_bitmap_bytes" n    byte budget of those bitmaps (default 16 GiB)
+ *   "keep_positions"   1/0  keep term positions resident when a posting image carries them (default 1)
+ *   "scan_kernels"     1/0  plain OR batches on the flat posting scan (default 1); 0 = the sub-tile kernels
+ *   "stream_kernels"   1/0  with scan_kernels 0: exhaustive batches on the sparse pass + column pass (default 1)
+ *   "strict_accumulate" 0/1 exhaustive sub-tile kernels: 1 = add every posting into its doc's accumulator even where
+ *                           the doc provably cannot enter the top k (default 0)
+ *   "scan_chunk"       n    flat posting scan: postings per work item (multiple of 256, default 4096)
+ *   "scan_first_part"  n    two-step runs (slg_batch_run_seeds / _sweep): 256ths of the items scanned before the
+ *                           threshold exchange (default 24)
+ *   "stage_cap"        n    sparse pass: postings a warp stages in shared memory per span (default 1024)
  *   "maxscore_pct"     n    pruned executions of the warp kernel (MaxScore): per (query, tile) the terms whose
  *                           bounds sum to less than n % of the running k-th score are not scattered; docs touched
  *                           by the other terms are rescored exactly if they can still qualify (default 35;
  *                           0 = tile skipping only).  The result is bit-identical to the exhaustive run.
- *   "keep_positions"   1/0  keep term positions resident when a posting image carries them (default 1)
- *   "heavy_kernel"     0|1  column front end (kernel_choice 3): 0 = warp kernel that sums a query's column
- *                           terms from their dense columns (default), 1 = tile-sweep kernel
- *   "reg_tile_v"       8       tile-sweep kernel: 128 * v docs per register tile (4 is refused: known intermittent fault)
- *   "sweep_min_postings" n  tile-sweep kernel: a query without a column term whose terms hold fewer than
- *                           n postings is scored posting-driven by the warp kernel instead of being swept
- *                           over every tile (default 0 = doc_count / 64; 1 = sweep every query)
- *   "seed_docs"        n    tile-sweep kernel: docs scored by the seed pass (default 16384)
- *   "part_tiles"       n    tile-sweep kernel: tiles per unit of work (default 0 = automatic)
- * Float contract: the column front ends sum a doc's contributions over the query's terms WITH a
- * column first, then over the terms WITHOUT one, each group in query order (one left fold) —
- * brute_force (query/wand.rs:527-548) on that permutation of the query; the other kernels sum in
- * query order.  Both agree with the reference within the 1e-5 rule. */
+ *   "heavy_kernel"     0    (round 1's tile-sweep kernel was removed; 1 is refused)
+ * Float contract: the posting-driven kernels (flat scan, column pass, items / stream kernels) sum a doc's
+ * contributions over the query's terms WITHOUT a dense column first, then over the terms WITH one, each
+ * group in query order (one left fold from +0) — brute_force (query/wand.rs:527-548) on that
+ * permutation of the query, reproduced bit for bit; the warp and CTA kernels sum in query order.  Both
+ * agree with the reference within the 1e-5 rule (the reference's own order follows HashMap iteration). */
 int32_t slg_set_option(slg_index_t *, const char *name, uint64_t value);
 /* 1 if `term_id` of the segment has a dense column (it is summed first by the column front ends) */
 int32_t slg_term_has_column(const slg_index_t *, uint32_t segment_ord, uint32_t term_id);

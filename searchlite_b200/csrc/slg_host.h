@@ -180,7 +180,7 @@ struct slg_index {
   bool staging = true;         // use the resident per-posting scores (seg.post_score) where a kernel can
   // residency options (slg_set_option), applied to segments loaded afterwards
   bool resident_scores = true;   // build seg.post_score at load
-  uint32_t dense_den = 8;        // a term gets a dense column when df * dense_den >= doc_count; 0 = no columns
+  uint32_t dense_den = 24;       // a term gets a dense column when df * dense_den >= doc_count; 0 = no columns (C2: 8 -> 24 took the pruned batch from 9.5 to 7.6 ms for +8.7 GB)
   uint32_t dense_min_df = 256;   // ... and df >= this
   uint32_t bitmap_den = 512;     // a term without a column gets a presence bitmap (1 bit per doc) when df * bitmap_den >= doc_count; 0 = none
   uint64_t max_bitmap_bytes = 16ull << 30;
