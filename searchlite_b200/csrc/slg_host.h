@@ -303,6 +303,7 @@ struct slg_batch {
   bool staged = false;                // the (doc, score) stream form of the warp kernel applies
   uint32_t max_terms = 0;
   bool use_warp = false, can_items = false, canonical = false;
+  bool and_scan = false;              // every query is Bool{must: one term per group}: the posting scan drives from the rarest list
   bool big_k = false;                 // k > 32 on the flat posting scan: candidate pools
   unsigned long long *pool_keys = nullptr;
   uint32_t *pool_count = nullptr, *pool_lock = nullptr;

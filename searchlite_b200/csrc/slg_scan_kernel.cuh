@@ -62,6 +62,7 @@ struct ScanDev {
   uint32_t items_cap;
   uint32_t *counter;         // work counters: [0] first phase, [1] second phase
   uint32_t chunk;            // postings per item
+  uint32_t must_mode;        // AND batches: every term of a query must hold the doc; only the rarest list is scanned
   uint32_t two_rounds;       // verification asks the lower-priority lists first, the higher-priority ones only for the survivors
   uint32_t part_lo, part_hi; // this launch scans items [n_items * part_lo / 256, n_items * part_hi / 256): 0..256 = all.  Sharded
                              // runs scan the rarest items first, exchange the per-query k-th keys, then scan the rest
@@ -210,6 +211,25 @@ static __global__ void __launch_bounds__(128) slg_scan_pairs_kernel(SegmentDev s
       is_col[t] = (q.flags & 4u) != 0u;
     }
   }
+  // AND batches: the driver is the scored term with the fewest postings; a term the segment lacks means no doc can match
+  uint32_t driver = 0xFFFFFFFFu;
+  float total_ub = 0.0f;
+  if (sc.must_mode) {
+    uint32_t best_df = 0xFFFFFFFFu;
+    bool possible = h.nt > 0;
+    for (uint32_t t = 0; t < h.nt && t < kWarpMaxTerms; t++) {
+      const QTerm &q = wb.qterms[(uint64_t)qslot * kWarpMaxTerms + t];
+      const uint32_t term = sc.ut_term[q.uterm];  // (q.term of a column term is its column)
+      const uint32_t df = (q.flags & 1u) && term < seg.n_terms ? seg.term_df[term] : 0u;
+      if (df == 0u) possible = false;
+      if (df < best_df) {
+        best_df = df;
+        driver = t;
+      }
+      total_ub += ub[t];
+    }
+    if (!possible) driver = 0xFFFFFFFFu;
+  }
   for (uint32_t t = 0; t < kWarpMaxTerms; t++) {
     ScanPair p;
     p.base = 0;
@@ -224,7 +244,15 @@ static __global__ void __launch_bounds__(128) slg_scan_pairs_kernel(SegmentDev s
     p.pad[0] = p.pad[1] = 0;
     if (t < h.nt) {
       const QTerm &q = wb.qterms[(uint64_t)qslot * kWarpMaxTerms + t];
-      if ((q.flags & 5u) == 1u && q.term < seg.n_terms) {
+      if (sc.must_mode) {
+        if (t == driver) {
+          p.base = q.base;
+          p.df = seg.term_df[sc.ut_term[q.uterm]];
+          p.w = q.weight;
+          p.others = total_ub - ub[t];  // every other term must add its share
+          p.ne_prefix = total_ub;       // below the k-th score: no doc of this query can enter the top k
+        }
+      } else if ((q.flags & 5u) == 1u && q.term < seg.n_terms) {
         p.base = q.base;
         p.df = seg.term_df[q.term];
         p.w = q.weight;
@@ -357,7 +385,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
       const QTerm *qts = wb.qterms + (uint64_t)qslot * kWarpMaxTerms;
       const uint32_t nt = __ldg(&wb.qheads[qslot].nt);
       // lane u < nt keeps term u of the query: what verify needs, handed round by shuffles
-      uint64_t m_base = 0;      // sparse: first posting; column: element offset of the column
+      uint64_t m_base = 0;      // first posting of the term's list
+      uint64_t m_col = 0;       // column terms: element offset of the column
       uint64_t m_bits = 0;      // sparse: word offset of the term's presence bitmap in seg.pres_bits, ~0 = none
       uint32_t m_df = 0, m_kind = 0;  // kind: 0 absent / unscored, 1 sparse, 2 column
       float m_w = 0.0f, m_ub = 0.0f, m_dens = 0.0f;
@@ -368,7 +397,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
           m_ub = __fmul_rn(sc.ut_max[q.uterm], q.weight);
           if (q.flags & 4u) {
             m_kind = 2;
-            m_base = q.sc_base;
+            m_col = q.sc_base;
+            m_base = q.base;
           } else if (q.term < seg.n_terms) {
             m_kind = 1;
             m_base = q.base;
@@ -412,6 +442,9 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
         uint32_t doc = 0u;
         if (alive) doc = __ldg(seg.post_doc + pr.base + idx);
         n_verified += alive ? 1u : 0u;
+        // a filtered query asks the filter first: one bit, and at a selectivity of a few percent most docs are done here
+        if (alive && pr.filter >= 0) alive = (__ldg(wb.filter_bits[pr.filter] + (doc >> 5)) >> (doc & 31)) & 1u;
+        const bool must = sc.must_mode != 0u;
         // ---- verify, cheapest evidence first: the column terms (one gather each), then the other sparse terms (a bit test,
         // a search when the bit is set), dropping the doc as soon as  known contributions + bounds of the unknown ones  falls
         // below the k-th score.  The exact score is the sum of the contributions in slot order.
@@ -422,13 +455,14 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
         for (int u = 0; u < (int)kWarpMaxTerms; u++) {
           c[u] = 0.0f;
           const uint32_t kind = __shfl_sync(0xFFFFFFFFu, m_kind, u);
-          if (kind != 2u) continue;  // (uniform)
-          const uint64_t cb = __shfl_sync(0xFFFFFFFFu, m_base, u);
+          if (kind != 2u || u == (int)t) continue;  // (uniform; an AND batch may scan a term that also has a column)
+          const uint64_t cb = __shfl_sync(0xFFFFFFFFu, m_col, u);
           const float w = __shfl_sync(0xFFFFFFFFu, m_w, u), ub = __shfl_sync(0xFFFFFFFFu, m_ub, u);
           if (alive) {
             c[u] = __fmul_rn(__ldg(seg.cols + cb + doc), w);
             known += c[u];
             unknown -= ub;
+            if (must && c[u] == 0.0f) alive = false;  // (a posting's contribution is positive: +0 means the list lacks the doc)
           }
         }
         alive = alive && (known + fmaxf(unknown, 0.0f)) * 1.0001f >= thr_s;
@@ -445,7 +479,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
           const uint32_t kind = __shfl_sync(0xFFFFFFFFu, m_kind, u);
           if (kind != 1u || u == (int)t) continue;  // (uniform)
           const float ub = __shfl_sync(0xFFFFFFFFu, m_ub, u);
-          const bool higher = ub > my_ub || (ub == my_ub && u < (int)t);  // a holder of higher priority offers the doc itself
+          const bool higher = !must && (ub > my_ub || (ub == my_ub && u < (int)t));  // a holder of higher priority offers the doc itself
           if (n_rounds == 2 && higher != (round == 1)) continue;  // (uniform)
           if (!__any_sync(0xFFFFFFFFu, alive)) break;
           const uint64_t pb = __shfl_sync(0xFFFFFFFFu, m_base, u), bo = __shfl_sync(0xFFFFFFFFu, m_bits, u);
@@ -462,6 +496,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
               if (higher) stand_back = true;
               c[u] = __fmul_rn(__ldg(wb.scores + pb + at), w);
               known += c[u];
+            } else if (must) {
+              stand_back = true;  // an AND query's doc must sit in every list
             }
             if (!higher) unknown -= ub;
             alive = !stand_back && (known + fmaxf(unknown, 0.0f)) * 1.0001f >= thr_s;

@@ -104,6 +104,9 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   qt_f.reserve(t_expect);
   qt_leaf.reserve(t_expect);
   bool matcher = false;
+  // AND batches: every query is Bool{must:[t1, t2, ..]} — one scored term per group, every group a MUST, nothing else.  The
+  // posting scan then walks only the query's RAREST list and asks the other lists whether they hold the doc
+  bool all_must = true;
   for (uint32_t qi = 0; qi < n_queries; qi++) {
     const slg_query_t &q = queries[qi];
     if (q.n_terms && !q.terms) return fail(ix, SLG_ERR_INVALID, "query %u has no terms pointer", qi);
@@ -169,6 +172,16 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
       if (scored && tm.term_id < s0->n_terms) q_cost[qi] += s0->h_df[tm.term_id];
       kept++;
     }
+    {
+      bool pure = q.n_groups > 0 && kept == q.n_groups && q.n_terms == q.n_groups;  // (a MUST group that lost its term can never match: left to the matcher kernels)
+      uint32_t seen_groups = 0;
+      for (uint32_t g = 0; pure && g < q.n_groups; g++) pure = q.group_role[g] == SLG_ROLE_MUST;
+      for (uint32_t t = 0; pure && t < q.n_terms; t++) {
+        pure = (q.terms[t].flags & SLG_TERM_SCORED) && !((seen_groups >> q.terms[t].group) & 1u);
+        seen_groups |= 1u << q.terms[t].group;
+      }
+      all_must = all_must && pure;
+    }
     if (kept > SLG_MAX_QUERY_TERMS) return fail(ix, SLG_ERR_UNSUPPORTED, "query %u has %u terms; the maximum is %u", qi, kept, SLG_MAX_QUERY_TERMS);
     q_off[qi + 1] = q_off[qi] + kept;
     bt->max_terms = std::max(bt->max_terms, kept);
@@ -222,10 +235,13 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   const bool small = k <= kWarpMaxK && bt->max_terms <= kWarpMaxTerms;
   bool all_scores = ix->staging;
   for (auto &s : ix->segs) all_scores = all_scores && (s->post_score.p != nullptr || s->n_blocks == 0);
-  const bool items_ok = small && !matcher && all_scores && !bt->has_plan && ix->sub_docs <= 4096;
+  // (AND batches ride the posting scan; without it — scan_kernels 0, statistics — they are ordinary matcher batches)
+  const bool and_scan = matcher && all_must && ix->scan_kernels && ix->stream_kernels && !bt->has_cursor;
+  bt->and_scan = and_scan;
+  const bool items_ok = small && (!matcher || and_scan) && all_scores && !bt->has_plan && ix->sub_docs <= 4096;
   bt->can_items = items_ok && (ix->kernel_choice == 0 || ix->kernel_choice == 3);
   // k up to SLG_MAX_K on the flat posting scan: candidate pools + radix select instead of the warp's sorted top-k
-  bt->big_k = k > kWarpMaxK && bt->max_terms <= kWarpMaxTerms && !matcher && all_scores && !bt->has_plan && ix->scan_kernels && ix->stream_kernels &&
+  bt->big_k = k > kWarpMaxK && bt->max_terms <= kWarpMaxTerms && (!matcher || and_scan) && all_scores && !bt->has_plan && ix->scan_kernels && ix->stream_kernels &&
               (ix->kernel_choice == 0 || ix->kernel_choice == 3);
   if (bt->big_k) bt->can_items = true;
   if (ix->kernel_choice == 3 && !items_ok && !bt->big_k)
@@ -320,7 +336,7 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
       for (size_t i = 0; i < qt_u.size(); i++) {
         const uint32_t term = ut[qt_u[i]];
         if (term >= sg->n_terms || !qt_f[i]) continue;
-        if (!sg->h_term_col.empty() && sg->h_term_col[term] >= 0) continue;
+        if (!bt->and_scan && !sg->h_term_col.empty() && sg->h_term_col[term] >= 0) continue;  // (an AND batch may scan any of its terms)
         n += (sg->h_df[term] + ix->scan_chunk - 1) / ix->scan_chunk;
       }
       bt->scan_items_cap = (uint32_t)std::max<uint64_t>(bt->scan_items_cap, std::min<uint64_t>(n, 0xFFFFFFF0ull));
@@ -424,6 +440,8 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
   const bool run_items = bt->can_items && !bt->want_stats && !(bt->big_k && (!ix->scan_kernels || (ix->strict_accumulate && bt->exec == SLG_EXEC_BM25)));
   // flat posting scan + column pass: the automatic choice; scan_kernels 0 keeps the sub-tile kernels (stream / items)
   const bool run_scan = run_items && ix->scan_kernels && bt->colq != nullptr && !(ix->strict_accumulate && !prune);
+  if (bt->and_scan && !run_scan && run_items)
+    return fail(ix, SLG_ERR_UNSUPPORTED, "an AND batch prepared for the posting scan cannot run on the sub-tile kernels (strict_accumulate)");
   const bool two_step = !(do_seeds && do_sweep);
   if (two_step && (ix->segs.size() != 1 || !run_items || (!prune && !run_scan)))
     return fail(ix, SLG_ERR_UNSUPPORTED, "the two-step run (first part, threshold exchange, rest) needs one segment per handle and the posting scan or the pruned items kernel");
@@ -608,6 +626,7 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       sc.items = bt->scan_items;
       sc.items_cap = bt->scan_items_cap;
       sc.chunk = bt->scan_chunk;
+      sc.must_mode = bt->and_scan ? 1u : 0u;
       sc.counter = bt->work_counter + 7;
       sc.counters = bt->item_counters;
       StreamDev sdv{};
@@ -641,7 +660,7 @@ int32_t run_batch(slg_batch *bt, bool do_seeds, bool do_sweep) {
       sc.part_hi = do_sweep ? 256u : ix->scan_first_part;
       SLG_CUDA(ix, launch_scan(prune, wb.pool_keys != nullptr, s->dev, wb, sc, ix->n_sm * 4, st));
       count_launch(ix);
-      if (do_sweep && s->n_cols && !(ix->dbg & 4u)) {
+      if (do_sweep && s->n_cols && !(ix->dbg & 4u) && !bt->and_scan) {  // (AND: every result holds the scanned term — there is nothing left for a column pass)
         slg_colgroups_kernel<<<1, 1024, 0, st>>>(s->dev, wb, sdv, s->n_cols, prune ? bt->ut_max : nullptr);
         count_launch(ix);
         SLG_CUDA(ix, cudaGetLastError());

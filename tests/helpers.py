@@ -84,6 +84,8 @@ def canonical_batch(gi, qb: QueryBatch, segment_ord: int = 0) -> QueryBatch:
         terms[a:b] = rows[order]
     out = QueryBatch(qb.term_off.copy(), terms)
     out.filter_id = None if qb.filter_id is None else qb.filter_id.copy()
+    if qb.group_off is not None:  # Bool queries: the group of a term travels in its row, the roles stay where they are
+        out.group_off, out.group_role, out.min_should = qb.group_off.copy(), qb.group_role.copy(), qb.min_should.copy()
     return out
 
 

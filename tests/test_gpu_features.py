@@ -745,3 +745,61 @@ def test_threshold_board_between_two_shards(execution, k):
         p.free()
     for gi in gis:
         gi.close()
+
+
+# ---- AND batches on the posting scan: Bool{must:[..]} driven by the rarest list ------------------------------------------
+@pytest.mark.parametrize("k", [11, 101])
+def test_and_batch_on_the_posting_scan(k):
+    """every query Bool{must: t1, t2(, t3)} (C4's shape), with and without a root filter, two segments, terms with and without
+    columns / bitmaps, a term one segment lacks: the scan walks the rarest list only and must return what the reference's
+    OR-scan + reject returns (api/reader.rs:1527-1563)"""
+    from oracle import slo
+    from searchlite_b200.shard import shard_ranges
+    from tests.helpers import canonical_batch
+    segs, oras = [], []
+    for r, (lo, hi) in enumerate(shard_ranges(70_000, 2)):
+        spec = synth.CorpusSpec(n_docs=hi - lo, vocab=3_000, seed=251, len_lo=20, len_hi=90, segment_ord=r, doc_base=lo)
+        seg = synth.generate_segment(spec, "cpu")
+        names, lang, year = synth.fast_fields(spec)
+        seg.fast_str["lang"] = (names, lang)
+        seg.fast_i64["year"] = (year, None)
+        segs.append(seg)
+        oras.append(slo.OracleIndex(seg))
+    gi = GpuIndex(0, options={"dense_den": 16, "dense_min_df": 64, "bitmap_den": 256})
+    cols = {}
+    for seg in segs:
+        cols = gi.load_segment(seg)
+    assert any(gi.term_has_column(0, t) for t in range(1, 30))
+    rng = np.random.default_rng(8)
+    qs = []
+    for i in range(120):
+        pool = np.arange(1, 40) if i % 3 == 0 else np.arange(1, 400)   # dense-only queries, mixed queries
+        t = rng.choice(pool, size=3, replace=False).tolist()
+        if i % 7 == 0:
+            t[1] = int(rng.integers(2_000, 2_990))  # rare term: often absent from one of the segments
+        qs.append({"must": t[: 2 + i % 2]})
+    prog = lambda c: np.concatenate([node(F_AND, nc=2), node(F_KEYWORD_EQ, c["lang"], v=(0, 1)), node(F_I64_RANGE, c["year"], i=(2003, 2014))])
+    fid = gi.compile_filter(prog(cols), ["en"])
+    for filtered in (False, True):
+        qb = QueryBatch.from_bool([dict(q, filter_id=fid) for q in qs] if filtered else qs)
+        kw = dict(filter_nodes=prog(oras[0].columns), strings=["en"]) if filtered else {}
+        launches0 = gi.counters()["kernel_launches"]
+        got = {mode: gi.search_batch(qb, k, mode) for mode in ("bm25", "bmw")}
+        assert got["bm25"][0].tobytes() == got["bmw"][0].tobytes() and got["bm25"][1].tobytes() == got["bmw"][1].tobytes()
+        assert gi.counters()["last_postings_scattered"] > 0  # the posting scan ran (its work counters are filled)
+        n_hits = 0
+        for qi in range(qb.n_queries):
+            sub = qb.subset(qi, qi + 1)
+            ref_q = slo.merge_hits([h[0, : c[0]] for h, c in (o.search_batch(sub, k, "bm25", **kw) for o in oras)], k)
+            ref_c = slo.merge_hits([h[0, : c[0]] for h, c in (o.search_batch(canonical_batch(gi, sub, r), k, "bm25", **kw) for r, o in enumerate(oras))], k)
+            g = got["bm25"][0][qi, : got["bm25"][1][qi]]
+            assert g.tobytes() == ref_c.tobytes(), (filtered, qi)  # declared order: bit for bit
+            assert_parity(ref_q[None, :], np.array([len(ref_q)]), g[None, :], np.array([len(g)]), strict=False)
+            n_hits += len(g)
+        assert n_hits > 0
+    # statistics keep such a batch on the matcher kernel; the hits are the same docs
+    qb = QueryBatch.from_bool(qs)
+    h, c, st = gi.search_batch(qb, k, "bm25", want_stats=True)
+    for qi in range(qb.n_queries):
+        assert sorted(h[qi, : c[qi]]["doc_id"].tolist()) == sorted(got["bm25"][0][qi, : got["bm25"][1][qi]]["doc_id"].tolist()) or filtered
+    gi.close()
