@@ -67,8 +67,8 @@ def parse_args():
     ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of --impl reference")
     ap.add_argument("--candidates", type=int, default=1000, help="c5: BM25 candidates per query handed to the rerank")
     ap.add_argument("--no-phrases", action="store_true", help="c4: skip the phrase leg (positions resident: +21 GB)")
-    ap.add_argument("--threshold-board", action="store_true",
-                    help="N > 1: shards push their per-query k-th scores into each other's boards over NVLink peer mappings during the scan")
+    ap.add_argument("--no-threshold-board", dest="threshold_board", action="store_false",
+                    help="N > 1: do not exchange per-query k-th scores between the shards during the scan (NVLink peer pushes, on by default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-exhaustive", action="store_true", help="skip the exhaustive (bm25) leg and its roofline")
     ap.add_argument("--no-pruned", action="store_true", help=argparse.SUPPRESS)  # (round-1 flag: same as --no-exhaustive)

@@ -221,7 +221,8 @@ int32_t slg_configure(slg_index_t *, uint32_t tile_docs, uint32_t ctas_per_sm, u
  *   "stream_kernels"   1/0  with scan_kernels 0: exhaustive batches on the sparse pass + column pass (default 1)
  *   "strict_accumulate" 0/1 exhaustive sub-tile kernels: 1 = add every posting into its doc's accumulator even where
  *                           the doc provably cannot enter the top k (default 0)
- *   "scan_chunk"       n    flat posting scan: postings per work item (multiple of 256, default 4096)
+ *   "scan_chunk"       n    flat posting scan: postings per work item (multiple of 256; default 0 = by segment size:
+ *                           4096 from 4 M docs, 2048 from 2 M, else 1024)
  *   "scan_first_part"  n    two-step runs (slg_batch_run_seeds / _sweep): 256ths of the items scanned before the
  *                           threshold exchange (default 24)
  *   "stage_cap"        n    sparse pass: postings a warp stages in shared memory per span (default 1024)

@@ -468,7 +468,7 @@ int32_t slg_set_option(slg_index_t *ix, const char *name, uint64_t value) {
   else if (n == "max_column_bytes") ix->max_column_bytes = value;
   else if (n == "bitmap_den") ix->bitmap_den = (uint32_t)value;
   else if (n == "scan_chunk") {
-    if (value < 256 || value > (1u << 20) || value % 256) return fail(ix, SLG_ERR_INVALID, "scan_chunk is a multiple of 256 postings");
+    if (value && (value < 256 || value > (1u << 20) || value % 256)) return fail(ix, SLG_ERR_INVALID, "scan_chunk is a multiple of 256 postings (0 = by segment size)");
     ix->scan_chunk = (uint32_t)value;
   } else if (n == "scan_first_part") {
     if (value < 1 || value > 255) return fail(ix, SLG_ERR_INVALID, "scan_first_part is a number of 256ths: 1..255");

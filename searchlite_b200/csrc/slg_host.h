@@ -188,7 +188,7 @@ struct slg_index {
   uint32_t stage_cap = 1024;     // sparse pass: postings a warp stages in shared memory per span (slg_stream_kernel.cuh)
   uint32_t strict_accumulate = 0; // exhaustive stream kernels: 1 = sum every posting per doc; 0 = bounded accumulation (slg_stream_kernel.cuh)
   uint32_t dbg = 0;
-  uint32_t scan_chunk = 4096;    // flat posting scan: postings per work item (multiple of 256)
+  uint32_t scan_chunk = 0;       // flat posting scan: postings per work item (multiple of 256); 0 = by segment size (4096 / 2048 / 1024)
   uint32_t scan_first_part = 24; // two-step (sharded) runs: the first step scans this many 256ths of the items (rarest first) before the threshold exchange
   uint32_t scan_kernels = 1;     // plain OR batches: 1 = flat posting scan + column pass (slg_scan_kernel.cuh), 0 = the sub-tile kernels
   uint32_t stream_kernels = 1;   // exhaustive plain OR batches: 1 = sparse pass + column pass, 0 = the items kernel

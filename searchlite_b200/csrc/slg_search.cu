@@ -329,7 +329,15 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
   const size_t o_items = want_items ? carve((size_t)bt->items_cap * sizeof(uint2)) : 0;
   const bool want_stream = bt->can_items && ix->stream_kernels;
   for (auto &s : ix->segs) bt->max_cols = std::max(bt->max_cols, s->n_cols);
-  // flat posting scan: item capacity = the largest segment's sum over scanned term instances of ceil(df / kScanChunk)
+  // postings per scan item: 4096 on a 10 M-doc segment (fewer, longer items: less per-item work), smaller on small
+  // segments — the shards of a multi-GPU run — where 4096 leaves too few items to balance 4736 warps
+  // (profiles/r2_scan_experiments.txt: at 1.25 M docs 1024 takes 2.4 ms against 3.0 ms; at 10 M docs it takes 22 against 9.4)
+  {
+    uint32_t max_docs = 0;
+    for (auto &sg : ix->segs) max_docs = std::max(max_docs, sg->doc_count);
+    bt->scan_chunk = ix->scan_chunk ? ix->scan_chunk : (max_docs >= 4000000u ? 4096u : max_docs >= 2000000u ? 2048u : 1024u);
+  }
+  // flat posting scan: item capacity = the largest segment's sum over scanned term instances of ceil(df / scan_chunk)
   if (bt->can_items) {
     for (auto &sg : ix->segs) {
       uint64_t n = 0;
@@ -337,13 +345,12 @@ int32_t slg_batch_prepare(slg_index_t *ix, const slg_query_t *queries, uint32_t 
         const uint32_t term = ut[qt_u[i]];
         if (term >= sg->n_terms || !qt_f[i]) continue;
         if (!bt->and_scan && !sg->h_term_col.empty() && sg->h_term_col[term] >= 0) continue;  // (an AND batch may scan any of its terms)
-        n += (sg->h_df[term] + ix->scan_chunk - 1) / ix->scan_chunk;
+        n += (sg->h_df[term] + bt->scan_chunk - 1) / bt->scan_chunk;
       }
       bt->scan_items_cap = (uint32_t)std::max<uint64_t>(bt->scan_items_cap, std::min<uint64_t>(n, 0xFFFFFFF0ull));
     }
   }
   const bool want_scan = bt->can_items;
-  bt->scan_chunk = ix->scan_chunk;
   const size_t o_utmax = want_scan ? carve((size_t)std::max(bt->U, 1u) * 4) : 0;
   const size_t o_pairs = want_scan ? carve((size_t)n_queries * kWarpMaxTerms * sizeof(ScanPair)) : 0;
   const size_t o_order = want_scan ? carve((size_t)n_queries * kWarpMaxTerms * 4) : 0;

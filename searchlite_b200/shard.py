@@ -47,7 +47,7 @@ def gather_blocks(local_block: torch.Tensor, group=None) -> torch.Tensor:
 class ShardedSearcher:
     """search over world_size shards; every rank ends up with the merged result"""
 
-    def __init__(self, index, n_queries: int, k: int, group=None, host_merge: Optional[Callable] = None, threshold_board: bool = False):
+    def __init__(self, index, n_queries: int, k: int, group=None, host_merge: Optional[Callable] = None, threshold_board: bool = True):
         self.index, self.q, self.k, self.group = index, n_queries, k, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.host_merge = host_merge

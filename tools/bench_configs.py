@@ -119,7 +119,7 @@ def run_c4(args, rank, local_rank, world, device):
     ]
     stream = torch.cuda.ExternalStream(gi.stream_ptr(), device=device)
     tm = _Timer(torch, dist, stream, device, world, args.steps, args.warmup)
-    searcher = ShardedSearcher(gi, args.queries, k) if world > 1 else None
+    searcher = ShardedSearcher(gi, args.queries, k, threshold_board=args.threshold_board) if world > 1 else None
 
     def make_leg(label, qb, fid_desc, filter_nodes, strings, selectivity):
         out = {"leg": label, "filter": fid_desc, "selectivity": selectivity}
