@@ -42,13 +42,19 @@ cudaError_t launch_columns_pruned(bool pools, const SegmentDev &sd, const WarpBa
   else slg_columns_pruned_kernel<0><<<grid, 256, 0, st>>>(sd, wb, st_dev);
   return cudaGetLastError();
 }
+template <bool PRUNE, bool POOLS>
+static void launch_scan_pm(bool must, const SegmentDev &sd, const WarpBatchDev &wb, const ScanDev &sc, int grid, cudaStream_t st) {
+  if (must) slg_scan_kernel<PRUNE, POOLS, true><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
+  else slg_scan_kernel<PRUNE, POOLS, false><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
+}
 cudaError_t launch_scan(bool prune, bool pools, const SegmentDev &sd, const WarpBatchDev &wb, const ScanDev &sc, int grid, cudaStream_t st) {
+  const bool must = sc.must_mode != 0u;
   if (pools) {
-    if (prune) slg_scan_kernel<true, true><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
-    else slg_scan_kernel<false, true><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
+    if (prune) launch_scan_pm<true, true>(must, sd, wb, sc, grid, st);
+    else launch_scan_pm<false, true>(must, sd, wb, sc, grid, st);
   } else {
-    if (prune) slg_scan_kernel<true, false><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
-    else slg_scan_kernel<false, false><<<grid, kScanWarps * 32, 0, st>>>(sd, wb, sc);
+    if (prune) launch_scan_pm<true, false>(must, sd, wb, sc, grid, st);
+    else launch_scan_pm<false, false>(must, sd, wb, sc, grid, st);
   }
   return cudaGetLastError();
 }

@@ -345,7 +345,8 @@ static __global__ void __launch_bounds__(256) slg_scan_items_kernel(ScanDev sc) 
   sc.items[i] = lo;
 }
 
-template <bool PRUNE, bool POOLS>
+// MUST: AND batches (sc.must_mode); compiled out of the plain OR instantiations, which then carry one pointer less per lane
+template <bool PRUNE, bool POOLS, bool MUST>
 __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev seg, WarpBatchDev wb, ScanDev sc) {
   __shared__ __align__(16) unsigned long long s_cand[kScanWarps][kWarpCand];
   __shared__ uint32_t s_hist[kScanWarps][POOLS ? 256 : 1];
@@ -397,8 +398,12 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
           m_ub = __fmul_rn(sc.ut_max[q.uterm], q.weight);
           if (q.flags & 4u) {
             m_kind = 2;
-            m_col = q.sc_base;
-            m_base = q.base;
+            if (MUST) {
+              m_col = q.sc_base;
+              m_base = q.base;
+            } else {
+              m_base = q.sc_base;  // (plain OR: a column term is never scanned, its posting base is not needed)
+            }
           } else if (q.term < seg.n_terms) {
             m_kind = 1;
             m_base = q.base;
@@ -444,7 +449,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
         n_verified += alive ? 1u : 0u;
         // a filtered query asks the filter first: one bit, and at a selectivity of a few percent most docs are done here
         if (alive && pr.filter >= 0) alive = (__ldg(wb.filter_bits[pr.filter] + (doc >> 5)) >> (doc & 31)) & 1u;
-        const bool must = sc.must_mode != 0u;
+        const bool must = MUST;
         // ---- verify, cheapest evidence first: the column terms (one gather each), then the other sparse terms (a bit test,
         // a search when the bit is set), dropping the doc as soon as  known contributions + bounds of the unknown ones  falls
         // below the k-th score.  The exact score is the sum of the contributions in slot order.
@@ -456,7 +461,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
           c[u] = 0.0f;
           const uint32_t kind = __shfl_sync(0xFFFFFFFFu, m_kind, u);
           if (kind != 2u || u == (int)t) continue;  // (uniform; an AND batch may scan a term that also has a column)
-          const uint64_t cb = __shfl_sync(0xFFFFFFFFu, m_col, u);
+          const uint64_t cb = __shfl_sync(0xFFFFFFFFu, MUST ? m_col : m_base, u);
           const float w = __shfl_sync(0xFFFFFFFFu, m_w, u), ub = __shfl_sync(0xFFFFFFFFu, m_ub, u);
           if (alive) {
             c[u] = __fmul_rn(__ldg(seg.cols + cb + doc), w);

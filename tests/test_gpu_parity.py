@@ -144,10 +144,14 @@ def test_automatic_kernel_is_the_items_kernel(small):
     assert sum(capped.term_has_column(0, t) for t in range(200)) == 3
     assert_engine_parity(capped, ora, qb, 11, capped.search_batch(qb, 11, "bm25"))
     # a batch the items kernel cannot take is an error when it is required, a fallback when it is not
-    bq = QueryBatch.from_bool([{"must": [3, 5]}])
+    bq = QueryBatch.from_bool([{"must": [3], "must_not": [5]}])
     with pytest.raises(SearchliteGpuError, match="items kernel handles plain OR"):
         r0.search_batch(bq, 11, "bm25")
     gi.search_batch(bq, 11, "bm25")
+    # (a pure AND batch — one MUST term per group — rides the posting scan: accepted either way, same hits)
+    aq = QueryBatch.from_bool([{"must": [3, 5]}])
+    x, y = r0.search_batch(aq, 11, "bm25"), warp.search_batch(aq, 11, "bm25")
+    assert x[1].tobytes() == y[1].tobytes() and sorted(x[0][0]["doc_id"][: x[1][0]].tolist()) == sorted(y[0][0]["doc_id"][: y[1][0]].tolist())
     for g in (gi, warp, r0, capped):
         g.close()
 
