@@ -119,17 +119,36 @@ static __global__ void __launch_bounds__(1024) slg_colgroups_kernel(SegmentDev s
     }
   }
   __syncthreads();
-  if (tid == 0) {  // slots in column order: column 0 is the densest term (n_cols is tens to a few thousand)
-    uint32_t n = 0;
-    for (uint32_t c = 0; c < n_cols; c++) {
-      if (sd.col_slot[c]) {
-        sd.ucol[n] = c;
-        sd.col_slot[c] = n++;
-      } else {
-        sd.col_slot[c] = 0xFFFFFFFFu;
+  {  // slots in column order (column 0 is the densest term): a block-wide exclusive scan of the "named" flags, 1024 columns a round
+    __shared__ uint32_t s_scan[1024];
+    __shared__ uint32_t s_carry;
+    if (tid == 0) s_carry = 0u;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_cols; base += nthr) {
+      const uint32_t c = base + tid;
+      const uint32_t flag = c < n_cols && sd.col_slot[c] ? 1u : 0u;
+      s_scan[tid] = flag;
+      __syncthreads();
+      for (uint32_t o = 1; o < nthr; o <<= 1) {
+        const uint32_t v = tid >= o ? s_scan[tid - o] : 0u;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
       }
+      const uint32_t excl = s_scan[tid] - flag + s_carry;
+      if (c < n_cols) {
+        if (flag) {
+          sd.ucol[excl] = c;
+          sd.col_slot[c] = excl;
+        } else {
+          sd.col_slot[c] = 0xFFFFFFFFu;
+        }
+      }
+      __syncthreads();
+      if (tid == nthr - 1) s_carry += s_scan[tid];
+      __syncthreads();
     }
-    *sd.n_ucol = n;
+    if (tid == 0) *sd.n_ucol = s_carry;
   }
   __syncthreads();
   for (uint32_t slot = tid; slot < wb.n_queries; slot += nthr) {
