@@ -90,11 +90,16 @@ def read_peaks():
         return 6650.0, "fallback"
 
 
+KERNEL_SOURCES = ("slg_scan_kernel.cuh", "slg_stream_kernel.cuh", "slg_items_kernel.cuh", "slg_warp_kernel.cuh", "slg_kernels.cuh",
+                  "slg_async.cuh", "slg_launch_items.cu")
+
+
 def kernel_source_hash() -> str:
-    """hash of the CUDA sources: a DRAM-traffic figure taken with ncu is only reported next to the kernels it was taken from"""
+    """hash of the sources of the roofline kernels (scan + column pass and what they include): a DRAM-traffic figure taken with
+    ncu is only reported next to the kernels it was taken from"""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "searchlite_b200", "csrc")
-    for name in sorted(os.listdir(d)):
+    for name in KERNEL_SOURCES:
         with open(os.path.join(d, name), "rb") as f:
             h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]

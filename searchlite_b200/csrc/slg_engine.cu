@@ -1275,8 +1275,84 @@ int32_t slg_add_str_list_column(slg_index_t *ix, uint32_t segment_ord, const cha
   return add_list_column(ix, segment_ord, 5, offsets, ords, 4, dict, n_dict);
 }
 
-// index/fastfields.rs:475-481, ASCII path
+// Unicode lowercase of one code point as Rust's char::to_lowercase gives it for the bicameral blocks a keyword field is
+// likely to hold: Latin-1, Latin Extended-A / -B (the regular pairs) / Additional, Greek (+ tonos forms), Cyrillic (+ the
+// extended pairs), Armenian, fullwidth Latin.  U+0130 (İ) lowers to two code points ("i̇"), the only multi-character mapping.
+static void lower_cp(uint32_t c, std::u32string &out, bool final_sigma) {
+  if (c < 0x80) {
+    out.push_back(c >= 'A' && c <= 'Z' ? c + 32 : c);
+    return;
+  }
+  if (c == 0x130) {
+    out.push_back('i');
+    out.push_back(0x307);
+    return;
+  }
+  uint32_t r = c;
+  if ((c >= 0xC0 && c <= 0xDE && c != 0xD7)) r = c + 0x20;
+  else if ((c >= 0x100 && c <= 0x12F) || (c >= 0x132 && c <= 0x137) || (c >= 0x14A && c <= 0x177)) r = (c & 1u) ? c : c + 1;
+  else if ((c >= 0x139 && c <= 0x148) || (c >= 0x179 && c <= 0x17E)) r = (c & 1u) ? c + 1 : c;
+  else if (c == 0x178) r = 0xFF;
+  else if (c == 0x1C4 || c == 0x1C5) r = 0x1C6;  // the DŽ / LJ / NJ / DZ digraphs: upper and title case lower to one letter
+  else if (c == 0x1C7 || c == 0x1C8) r = 0x1C9;
+  else if (c == 0x1CA || c == 0x1CB) r = 0x1CC;
+  else if (c == 0x1F1 || c == 0x1F2) r = 0x1F3;
+  else if ((c >= 0x1CD && c <= 0x1DC)) r = (c & 1u) ? c + 1 : c;
+  else if ((c >= 0x1DE && c <= 0x1EF) || (c >= 0x1F8 && c <= 0x21F) || (c >= 0x222 && c <= 0x233)) r = (c & 1u) ? c : c + 1;
+  else if (c == 0x386) r = 0x3AC;
+  else if (c >= 0x388 && c <= 0x38A) r = c + 37;
+  else if (c == 0x38C) r = 0x3CC;
+  else if (c == 0x38E || c == 0x38F) r = c + 63;
+  else if (c >= 0x391 && c <= 0x3AB && c != 0x3A2) r = (c == 0x3A3 && final_sigma) ? 0x3C2 : c + 0x20;
+  else if (c >= 0x400 && c <= 0x40F) r = c + 0x50;
+  else if (c >= 0x410 && c <= 0x42F) r = c + 0x20;
+  else if ((c >= 0x460 && c <= 0x481) || (c >= 0x48A && c <= 0x4BF) || (c >= 0x4D0 && c <= 0x52F)) r = (c & 1u) ? c : c + 1;
+  else if (c >= 0x4C1 && c <= 0x4CE) r = (c & 1u) ? c + 1 : c;
+  else if (c == 0x4C0) r = 0x4CF;
+  else if (c >= 0x531 && c <= 0x556) r = c + 0x30;
+  else if (c >= 0x1E00 && c <= 0x1E95) r = (c & 1u) ? c : c + 1;
+  else if (c >= 0x1EA0 && c <= 0x1EFF) r = (c & 1u) ? c : c + 1;
+  else if (c >= 0xFF21 && c <= 0xFF3A) r = c + 0x20;
+  out.push_back(r);
+}
+static bool is_cased_letter(uint32_t c) {  // enough of Unicode's "cased" for the final-sigma rule
+  return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || (c >= 0xC0 && c <= 0x24F && c != 0xD7 && c != 0xF7) ||
+         (c >= 0x370 && c <= 0x3FF) || (c >= 0x400 && c <= 0x52F) || (c >= 0x531 && c <= 0x586) || (c >= 0x1E00 && c <= 0x1FFF);
+}
+static std::u32string utf8_lower(const std::string &s) {
+  std::u32string cps;
+  for (size_t i = 0; i < s.size();) {
+    const unsigned char b = (unsigned char)s[i];
+    uint32_t c = b;
+    int n = 1;
+    if (b >= 0xF0 && i + 3 < s.size()) {
+      c = ((b & 7u) << 18) | (((unsigned char)s[i + 1] & 63u) << 12) | (((unsigned char)s[i + 2] & 63u) << 6) | ((unsigned char)s[i + 3] & 63u);
+      n = 4;
+    } else if (b >= 0xE0 && i + 2 < s.size()) {
+      c = ((b & 15u) << 12) | (((unsigned char)s[i + 1] & 63u) << 6) | ((unsigned char)s[i + 2] & 63u);
+      n = 3;
+    } else if (b >= 0xC0 && i + 1 < s.size()) {
+      c = ((b & 31u) << 6) | ((unsigned char)s[i + 1] & 63u);
+      n = 2;
+    }
+    cps.push_back(c);
+    i += n;
+  }
+  std::u32string out;
+  for (size_t i = 0; i < cps.size(); i++) {
+    // Final_Sigma: preceded by a cased letter and not followed by one (Unicode SpecialCasing, as Rust implements it)
+    const bool fin = cps[i] == 0x3A3 && i > 0 && is_cased_letter(cps[i - 1]) && !(i + 1 < cps.size() && is_cased_letter(cps[i + 1]));
+    lower_cp(cps[i], out, fin);
+  }
+  return out;
+}
+
+// index/fastfields.rs:475-481: eq_ignore_ascii_case when both sides are ASCII, else a.to_lowercase() == b.to_lowercase()
 static bool ci_equals(const std::string &a, const std::string &b) {
+  bool ascii = true;
+  for (unsigned char ch : a) ascii = ascii && ch < 0x80;
+  for (unsigned char ch : b) ascii = ascii && ch < 0x80;
+  if (!ascii) return utf8_lower(a) == utf8_lower(b);
   if (a.size() != b.size()) return false;
   for (size_t i = 0; i < a.size(); i++) {
     unsigned char x = a[i], y = b[i];

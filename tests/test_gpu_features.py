@@ -803,3 +803,20 @@ def test_and_batch_on_the_posting_scan(k):
     for qi in range(qb.n_queries):
         assert sorted(h[qi, : c[qi]]["doc_id"].tolist()) == sorted(got["bm25"][0][qi, : got["bm25"][1][qi]]["doc_id"].tolist()) or filtered
     gi.close()
+
+
+def test_keyword_filter_lowercases_unicode_like_the_reference():
+    """case_insensitive_equals (index/fastfields.rs:475-481) with non-ASCII values: the engine's bitmaps equal the oracle's
+    and Python's str.lower()"""
+    from tests.test_oracle_golden import UNICODE_WORDS as words
+    seg = token_corpus([[0]] * len(words), 1)
+    seg.fast_str["tag"] = (words, np.arange(len(words), dtype=np.uint32))
+    ora = _oracle(seg)
+    gi, col = _gpu(seg)
+    for probe in words:
+        fid = gi.compile_filter(node(F_KEYWORD_EQ, col["tag"], v=(0, 1)), [probe])
+        bits = gi.filter_bitmap(fid, 0, len(words))
+        assert np.array_equal(bits, ora.filter_bitmap(node(F_KEYWORD_EQ, ora.columns["tag"], v=(0, 1)), [probe])), probe
+        got = [d for d in range(len(words)) if (bits[d >> 5] >> (d & 31)) & 1]
+        assert got == [d for d, w in enumerate(words) if w.lower() == probe.lower()], probe
+    gi.close()

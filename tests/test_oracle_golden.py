@@ -363,3 +363,30 @@ def test_list_columns_match_any_value():
     assert bits([(F_NOT, -1, 0, 0, 0, 0, 1, 0, 0), (F_I64, c["nums"], 0, 100, 0, 0, 0, 0, 0)]) == [len(l) == 0 for l in nums]
     # a numeric predicate on a keyword list (wrong column type) is false, as `_ => false`
     assert not any(bits([(F_I64, c["tags"], 0, 100, 0, 0, 0, 0, 0)]))
+
+
+UNICODE_WORDS = ["Straße", "ÉCOLE", "école", "Ελλάς", "ΕΛΛΆΣ", "ΟΔΟΣ", "οδος", "οδός", "Москва", "МОСКВА", "İstanbul", "i̇stanbul", "ŁÓDŹ", "łódź",
+                 "Ÿ", "ÿ", "Ǆ", "ǅ", "ՀԱՅ", "հայ", "ＡＢＣ", "ａｂｃ", "Ḃḃ", "ḃḃ", "plain", "PLAIN", "naïve", "NAÏVE", "Σ", "σ", "ς", "日本語", "ǅungla"]
+
+
+def test_keyword_compare_lowercases_unicode_like_the_reference():
+    """index/fastfields.rs:475-481: non-ASCII values compare by to_lowercase(); checked against Python's str.lower(), which
+    implements the same Unicode mapping (final sigma, İ included)"""
+    from oracle import slo
+    from searchlite_b200.engine import FILTER_DTYPE, F_KEYWORD_EQ
+    from tests.helpers import token_corpus
+    words = UNICODE_WORDS
+    seg = token_corpus([[0]] * len(words), 1)
+    seg.fast_str["tag"] = (words, np.arange(len(words), dtype=np.uint32))
+    ora = slo.OracleIndex(seg)
+    for probe in words:
+        n = np.zeros(1, dtype=FILTER_DTYPE)
+        n[0] = (F_KEYWORD_EQ, ora.columns["tag"], 0, 0, 0, 0, 0, 0, 1)
+        bits = ora.filter_bitmap(n, [probe])
+        got = [d for d in range(len(words)) if (bits[d >> 5] >> (d & 31)) & 1]
+        if all(ord(ch) < 128 for ch in probe):
+            want = [d for d, w in enumerate(words) if (all(ord(ch) < 128 for ch in w) and w.lower() == probe.lower()) or
+                    (not all(ord(ch) < 128 for ch in w) and w.lower() == probe.lower())]
+        else:
+            want = [d for d, w in enumerate(words) if w.lower() == probe.lower()]
+        assert got == want, (probe, [words[d] for d in got], [words[d] for d in want])
