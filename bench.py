@@ -396,7 +396,8 @@ def main():
         "e2e": e2e,
         "gpu_launches": int(round(launches * args.steps)),
         "clocks": clocks,
-        "setup": {"corpus_gen_s": round(gen_s, 1), "load_segment_s": round(load_s, 1), "resident_bytes": int(ctr["resident_bytes"])},
+        "setup": {"corpus_gen_s": round(gen_s, 1), "load_segment_s": round(load_s, 1), "resident_bytes": int(ctr["resident_bytes"]),
+                  "resident": gi.segment_residency(rank)},
     }
     if args.execution != "bm25":
         scanned = int(ctr["last_postings_scattered"])

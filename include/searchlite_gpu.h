@@ -344,6 +344,9 @@ int32_t slg_segment_stats(const slg_index_t *, uint32_t segment_ord, float *avgd
                           float *min_doc_len, uint64_t *n_postings);
 /* avgdl and minimum positive doc length of the field_index-th scored field (0 = the first / only one) */
 int32_t slg_field_stats(const slg_index_t *, uint32_t segment_ord, uint32_t field_index, float *avgdl, float *min_doc_len);
+/* device bytes of the segment per resident array, as a JSON object (post_doc, post_score, score_columns,
+ * presence_bitmaps, positions, vectors, ...; plus the number of score columns and presence bitmaps) */
+int32_t slg_segment_residency(const slg_index_t *, uint32_t segment_ord, char *json_out, uint64_t json_len);
 
 /* ---- filters (query/filters.rs) ---- */
 /* compiles a root filter against every loaded segment (one bitmap per segment); returns id >= 0 */

@@ -1186,6 +1186,35 @@ int32_t slg_segment_stats(const slg_index_t *ixc, uint32_t segment_ord, float *a
   return SLG_OK;
 }
 
+int32_t slg_segment_residency(const slg_index_t *ixc, uint32_t segment_ord, char *json_out, uint64_t json_len) {
+  slg_index *ix = const_cast<slg_index *>(ixc);
+  if (!ix || !json_out || json_len < 2) return SLG_ERR_INVALID;
+  Segment *s = ix->find(segment_ord);
+  if (!s) return fail(ix, SLG_ERR_INVALID, "no segment %u", segment_ord);
+  size_t cols_fast = 0, filters = 0;
+  for (auto &c : s->columns) cols_fast += c.values.bytes + c.present.bytes + c.offsets.bytes;
+  for (auto &f : s->filter_bits)
+    if (!f.borrowed) filters += f.bytes;
+  std::vector<const DevBuf *> seen;  // (the phrases of a batch share one slab)
+  for (auto &sl : s->filter_slabs)
+    if (sl && std::find(seen.begin(), seen.end(), sl.get()) == seen.end()) {
+      seen.push_back(sl.get());
+      filters += sl->bytes;
+    }
+  const int n = snprintf(
+      json_out, (size_t)json_len,
+      "{\"post_doc\": %zu, \"post_tf\": %zu, \"post_score\": %zu, \"mb_max\": %zu, \"term_tables\": %zu, \"block_tables\": %zu, \"norms\": %zu, "
+      "\"score_columns\": %zu, \"column_block_maxima\": %zu, \"presence_bitmaps\": %zu, \"wide_tf\": %zu, \"live_bits\": %zu, "
+      "\"positions\": %zu, \"fast_field_columns\": %zu, \"filter_bitmaps\": %zu, \"vectors\": %zu, \"n_score_columns\": %u, \"n_presence_bitmaps\": %u}",
+      s->post_doc.bytes, s->post_tf.bytes, s->post_score.bytes, s->mb_max.bytes,
+      s->term_start.bytes + s->term_df.bytes + s->term_idf.bytes + s->term_max_tf.bytes + s->term_wide.bytes + s->term_blk.bytes + s->term_field.bytes +
+          s->term_col.bytes + s->term_bits.bytes + s->term_ub.bytes,
+      s->blk_max_doc.bytes + s->blk_max_tf.bytes, s->nk.bytes, s->cols.bytes, s->col_tmax.bytes, s->pres_bits.bytes, s->tf_wide.bytes, s->live_bits.bytes,
+      s->pos_begin.bytes + s->pos.bytes, cols_fast, filters, s->vec.offsets.bytes + s->vec.values.bytes, s->n_cols, s->n_bitmaps);
+  if (n < 0 || (uint64_t)n >= json_len) return fail(ix, SLG_ERR_INVALID, "residency report needs %d bytes", n + 1);
+  return SLG_OK;
+}
+
 int32_t slg_field_stats(const slg_index_t *ixc, uint32_t segment_ord, uint32_t field_index, float *avgdl, float *min_doc_len) {
   slg_index *ix = const_cast<slg_index *>(ixc);
   if (!ix) return SLG_ERR_INVALID;

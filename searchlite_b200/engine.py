@@ -133,7 +133,7 @@ EXPORTED_SYMBOLS = [
     "slg_batch_cursor_seen", "slg_cursor_encode", "slg_cursor_decode",
     "slg_batch_run_seeds", "slg_batch_threshold_keys", "slg_batch_import_thresholds", "slg_batch_run_sweep",
     "slg_batch_packed_results", "slg_merge_gathered_packed",
-    "slg_batch_set_threshold_board", "slg_load_vectors_bf16", "slg_rerank_clauses", "slg_rerank_batch", "slg_batch_fetch_vector_scores", "slg_merge_gathered_hybrid",
+    "slg_batch_set_threshold_board", "slg_segment_residency", "slg_load_vectors_bf16", "slg_rerank_clauses", "slg_rerank_batch", "slg_batch_fetch_vector_scores", "slg_merge_gathered_hybrid",
 ]
 
 
@@ -207,6 +207,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "slg_batch_packed_results": [vp, C.POINTER(vp), C.POINTER(u64)],
         "slg_merge_gathered_packed": [vp, vp, u64, u32, u32, u32, vp, vp],
         "slg_batch_set_threshold_board": [vp, vp, vp, u32, u32],
+        "slg_segment_residency": [vp, u32, C.c_char_p, u64],
         "slg_load_vectors_bf16": [vp, u32, u32, vp, vp, u64],
         "slg_rerank_clauses": [vp, vp, u32, u32, u32, vp, vp, u32, vp, vp, vp],
         "slg_rerank_batch": [vp, vp, u32, u32, i32],
@@ -781,6 +782,13 @@ class GpuIndex:
         a, l, m, n = C.c_float(), C.c_float(), C.c_float(), C.c_uint64()
         self._check(self.lib.slg_segment_stats(self.handle, segment_ord, C.byref(a), C.byref(l), C.byref(m), C.byref(n)))
         return {"avgdl": a.value, "live_docs": l.value, "min_doc_len": m.value, "n_postings": n.value}
+
+    def segment_residency(self, segment_ord: int) -> dict:
+        """device bytes per resident array of the segment"""
+        import json
+        buf = C.create_string_buffer(2048)
+        self._check(self.lib.slg_segment_residency(self.handle, segment_ord, buf, 2048))
+        return json.loads(buf.value.decode())
 
     def field_stats(self, segment_ord: int, field_index: int) -> dict:
         a, m = C.c_float(), C.c_float()
