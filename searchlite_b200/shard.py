@@ -8,6 +8,10 @@ doc_id asc (searchlite-core/src/api/reader.rs:2777, src/query/sort.rs:80-93).  B
 and avgdl are per segment in the reference (api/reader.rs:2985,2994), the N-GPU result equals
 the reference run on the same N-segment index with no statistics exchange.
 
+Threshold board (on by default at N > 1 on CUDA): n_queries x 8 bytes of symmetric memory per rank, mapped into every
+peer over NVLink; while the posting scan runs, a shard that raises a query's k-th score pushes it into its peers' boards and
+prunes against the best score any shard has found (slg_batch_set_threshold_board).  Results are exact either way.
+
 The same code runs with the `gloo` backend on CPU tensors (tests): then the merge is done by
 the callable passed as `host_merge` because the CUDA merge kernel needs a device.
 """
@@ -116,7 +120,12 @@ class ShardedSearcher:
         """a fresh epoch of the threshold board for the next run of `prepared` (every rank calls this the same number of times)"""
         if self.board is not None:
             self.epoch += 1
-            prepared.set_threshold_board(self.board[2], self.board[3], self.epoch)
+            try:
+                prepared.set_threshold_board(self.board[2], self.board[3], self.epoch)
+            except Exception as e:  # noqa: BLE001  (several segments per handle: the shards then keep to their own thresholds)
+                self._board_keep = self.board  # (peers may still push into this rank's buffer: it stays mapped)
+                self.board = None
+                self.board_error = repr(e)
 
     def _exchange(self, prepared):
         ptr, nbytes = prepared.packed_results()
