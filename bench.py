@@ -20,11 +20,13 @@ The corpus is generated on the GPU (searchlite_b200.synth) and loaded once into 
 
 N > 1 (torchrun): the corpus is split into N contiguous doc-range segments, one per rank; every rank scores all
 queries on its segment, ONE NCCL all-gather exchanges the packed local top-k blocks and every rank merges (strong
-scaling: total corpus fixed).
+scaling: total corpus fixed).  While the scan runs the shards push their per-query k-th scores into each other's
+threshold boards (symmetric memory over NVLink, `--no-threshold-board` switches it off; results are exact either way).
 
-Other configurations (`--config`): c3 (8.84 M short passages, top-1000, bmw), c4 (Bool{must} / phrase-free AND queries
-behind And[KeywordEq(lang), I64Range(year)] at 50 / 10 / 1 % selectivity), c5 (BM25 top-1000 -> exact 768-d bf16
-rerank, docs sharded over the ranks).  They print the same JSON line shape with their own `config.workload`.
+Other configurations (`--config`): c3 (8.84 M short passages, top-1000, bmw), c4 (Bool{must} AND queries behind
+And[KeywordEq(lang), I64Range(year)] at 37 / 10 / 1 % selectivity + a 2-term phrase leg, every leg with full-batch oracle
+parity), c5 (BM25 top-1000 -> exact 768-d bf16 rerank on the device, 12.5 M docs per GPU, vectors sharded with their docs).
+They print the same JSON line shape with their own `config.workload` (tools/bench_configs.py).
 
 `--impl reference` times the reference's own CPU algorithm (oracle restatement, faithful mode: per-query varint
 decode + doc-length vector + WAND, the reference's default execution) on the host cores; rank 0 only.
