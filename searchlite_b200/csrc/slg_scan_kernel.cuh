@@ -430,22 +430,20 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
         }
       };
       recut();
-      // candidates wait in the warp's queue (posting index, contribution) until a full round of 32 can be verified at once:
+      // candidates wait in the warp's queue (doc id, contribution) until a full round of 32 can be verified at once:
       // a verification is a chain of dependent memory accesses, so what counts is how many docs share each chain
       uint32_t nq = 0, qhead = 0;
       auto verify_round = [&](uint32_t n) {
         bool alive = lane < (int)n;
-        uint32_t idx = 0;
+        uint32_t doc = 0u;
         float v = 0.0f;
         if (alive) {
-          idx = q_idx[(qhead + lane) & (kScanQueue - 1u)];
+          doc = q_idx[(qhead + lane) & (kScanQueue - 1u)];  // (the queue carries the doc id: it was read with the scores, coalesced)
           v = q_val[(qhead + lane) & (kScanQueue - 1u)];
         }
         qhead += n;
         nq -= n;
         alive = alive && __float_as_uint(v) >= cut;  // (the k-th score may have risen since the posting was queued)
-        uint32_t doc = 0u;
-        if (alive) doc = __ldg(seg.post_doc + pr.base + idx);
         n_verified += alive ? 1u : 0u;
         // a filtered query asks the filter first: one bit, and at a selectivity of a few percent most docs are done here
         if (alive && pr.filter >= 0) alive = (__ldg(wb.filter_bits[pr.filter] + (doc >> 5)) >> (doc & 31)) & 1u;
@@ -536,6 +534,13 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
           if (__float_as_uint(x[e]) >= cut && x[e] != 0.0f && idx < i1) todo |= 1u << e;  // (16-byte pieces may reach past the list's end)
         }
         if (!__any_sync(0xFFFFFFFFu, todo != 0u)) continue;
+        // the doc ids of the lanes that hold a candidate: 16 bytes next to the 16 bytes of scores just read — coalesced
+        // where candidates cluster, and one random 32-byte sector per candidate less than fetching post_doc[idx] later
+        const uint4 *dp4 = reinterpret_cast<const uint4 *>(seg.post_doc + pr.base);
+        uint4 da = make_uint4(0, 0, 0, 0), db = make_uint4(0, 0, 0, 0);
+        if (todo & 0x0Fu) da = __ldg(dp4 + (ia >> 2));
+        if (todo & 0xF0u) db = __ldg(dp4 + (ib >> 2));
+        const uint32_t dd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
         // queue this step's candidates: every lane appends its own (an exclusive scan of the counts gives the places)
         {
           const uint32_t mine = __popc(todo);
@@ -549,7 +554,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 4) slg_scan_kernel(SegmentDev
 #pragma unroll
           for (int e = 0; e < 8; e++)
             if ((todo >> e) & 1u) {
-              q_idx[at & (kScanQueue - 1u)] = (e < 4 ? ia : ib) + (e & 3);
+              q_idx[at & (kScanQueue - 1u)] = dd[e];
               q_val[at & (kScanQueue - 1u)] = x[e];
               at++;
             }
