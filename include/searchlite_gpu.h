@@ -110,7 +110,7 @@ typedef struct {
   uint64_t candidates_examined;
   uint64_t total_matches;     /* docs accepted by the accept closure (match counter, api/reader.rs:3029-3031): exact under
                                * BM25; under WAND/BMW an estimate, as the reference's total_hits_estimate is (skipped
-                               * tiles and MaxScore-skipped terms are not visited).  Not counted by the tile-sweep kernel. */
+                               * tiles and MaxScore-skipped terms are not visited).  Counted by the warp / CTA kernels (a batch with statistics runs there). */
 } slg_stats_t;
 
 /* Where the arrays of a view live. */
@@ -167,7 +167,7 @@ typedef struct {
   uint64_t resident_bytes;     /* device bytes held by loaded segments */
   uint64_t last_h2d_bytes;     /* host->device bytes of the last slg_batch_prepare */
   uint64_t last_d2h_bytes;     /* device->host bytes of the last slg_batch_fetch / slg_merge_gathered */
-  /* work of the last fetched run of the items kernel (whole batch, all segments): */
+  /* work of the last fetched run of the posting-driven kernels (whole batch, all segments): */
   uint64_t last_postings_scattered;     /* postings read and accumulated (compare with last_posting_count) */
   uint64_t last_subtiles_skipped;       /* (query, sub-tile) pairs dropped inside the sweep by the bound */
   uint64_t last_column_blocks_streamed; /* 512-doc blocks of dense columns read */
@@ -391,13 +391,15 @@ int32_t slg_batch_prepare(slg_index_t *, const slg_query_t *queries, uint32_t n_
 /* collect slg_stats_t counters in later runs (off by default: the counting costs a few percent) */
 int32_t slg_batch_enable_stats(slg_batch_t *, int32_t on);
 int32_t slg_batch_run(slg_batch_t *, int32_t sync);
-/* The pruned run in two steps for one-segment-per-GPU sharding: seeds give every query a local k-th
+/* The run in two steps for one-segment-per-GPU sharding: the first step (the seed pass of the sub-tile
+ * kernels, or the first "scan_first_part" of the posting scan's items, rarest terms first) gives every query a local k-th
  * key; the caller max-reduces the keys over the shards (e.g. ncclAllReduce(max) on the uint64 array of
  * slg_batch_threshold_keys, n_queries entries in query order, on the handle's stream) and hands the result to
  * slg_batch_import_thresholds, which keeps the score part (a global k-th score is a safe bound for every shard; an
  * equal score may still win on segment order, query/sort.rs:80-93); the sweep then prunes against the global bound.
  * The merged result over all shards is exact; a shard's own list may lack docs that cannot reach the global top k.
- * Needs one segment in the handle, execution wand/bmw and a batch the items kernel handles. */
+ * Needs one segment in the handle and a batch the posting scan (any execution) or the pruned items kernel handles.
+ * slg_batch_set_threshold_board below does the same exchange inside ONE launch over peer-mapped memory. */
 int32_t slg_batch_run_seeds(slg_batch_t *);
 int32_t slg_batch_threshold_keys(slg_batch_t *, void **dev_keys);
 int32_t slg_batch_import_thresholds(slg_batch_t *, const void *dev_keys);
