@@ -311,3 +311,58 @@ def test_merge_kernel_many_sorted_lists():
         assert plain_h[q, : len(m)].tobytes() == m.tobytes()
         assert np.array_equal(got_vs[q, : len(m)], (m["doc_id"] % 997).astype(np.float32))
     gi.close()
+
+
+def test_oracle_rerank_batch_matches_a_numpy_restatement():
+    """slo_rerank_batch (the C5 checker) against pure numpy-f32 loops: sequential dot / squared distance
+    (vectors/mod.rs:98-120), boost (api/reader.rs:2421), compute_hybrid_score (:226-254), the all-vector drop (:2474-2476)
+    and the SortKey order (query/sort.rs:80-93)"""
+    from oracle import slo
+    rng = np.random.default_rng(17)
+    nq, stride, dim, n_docs = 6, 23, 12, 200
+    offsets = np.full(n_docs, 0xFFFFFFFF, dtype=np.uint32)
+    have = rng.random(n_docs) < 0.75
+    offsets[have] = rng.permutation(int(have.sum())).astype(np.uint32)
+    rows = rng.standard_normal((int(have.sum()), dim)).astype(np.float32)
+    cands = np.zeros((nq, stride), dtype=HIT_DTYPE)
+    counts = rng.integers(5, stride + 1, nq).astype(np.uint32)
+    for q in range(nq):
+        cands[q, : counts[q]]["doc_id"] = rng.choice(n_docs, counts[q], replace=False)
+        cands[q, : counts[q]]["score"] = np.round(rng.random(counts[q]).astype(np.float32) * 8, 2)  # ties on purpose
+    for clauses in ([(rng.standard_normal((nq, dim)).astype(np.float32), 0.5, 1.0, "cosine")],
+                    [(rng.standard_normal((nq, dim)).astype(np.float32), 0.3, 2.0, "l2"),
+                     (rng.standard_normal((nq, dim)).astype(np.float32), 1.0, 1.0, "cosine"),
+                     (rng.standard_normal((nq, dim)).astype(np.float32), 0.0, 0.5, "cosine")],
+                    [(rng.standard_normal((nq, dim)).astype(np.float32), 0.0, 1.5, "cosine"),
+                     (rng.standard_normal((nq, dim)).astype(np.float32), 0.0, 1.0, "l2")]):
+        out, oc, vs = slo.rerank_batch(cands, counts, [(0, offsets, rows)], clauses)
+        all_vec = all(c[1] <= 0.0 for c in clauses)
+        for q in range(nq):
+            exp = []
+            for h in cands[q, : counts[q]]:
+                d = int(h["doc_id"])
+                row = rows[offsets[d]] if offsets[d] != 0xFFFFFFFF else None
+                sims = []
+                for qv, alpha, boost, metric in clauses:
+                    if row is None:
+                        sims.append(None)
+                        continue
+                    acc = _f32(0)
+                    for x, y in zip(qv[q], row):
+                        if metric == "cosine":
+                            acc = _f32(acc + _f32(x * y))
+                        else:
+                            dd = _f32(x - y)
+                            acc = _f32(acc + _f32(dd * dd))
+                    s = (_f32(0) if np.isnan(acc) else acc) if metric == "cosine" else _f32(-np.sqrt(acc, dtype=np.float32))
+                    sims.append(_f32(s * _f32(boost)))
+                score, vsum = hybrid_numpy(h["score"], sims, [c[1] for c in clauses], [c[3] for c in clauses])
+                if all_vec and vsum is None:
+                    continue
+                exp.append((float(score), d, float(vsum) if vsum is not None else 0.0))
+            exp.sort(key=lambda t: (-t[0], t[1]))
+            assert oc[q] == len(exp)
+            got = [(float(h["score"]), int(h["doc_id"]), float(v)) for h, v in zip(out[q, : oc[q]], vs[q, : oc[q]])]
+            assert [np.float32(a[0]).tobytes() + np.float32(a[2]).tobytes() for a in got] == \
+                   [np.float32(a[0]).tobytes() + np.float32(a[2]).tobytes() for a in exp], q
+            assert [a[1] for a in got] == [a[1] for a in exp], q
